@@ -1,0 +1,322 @@
+// mm_abi.cu -- the extern "C" surface declared in include/magicmirror.h.
+// Host-side orchestration only: argument validation, workspace carving, launches.
+#include "../../include/magicmirror.h"
+#include "mm_common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define MM_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(MM_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                               \
+    } while (0)
+
+#define MM_REQUIRE(cond, msg) \
+    do { if (!(cond)) return fail(MM_E_INVALID, "invalid argument: %s", msg); } while (0)
+
+// torch F.interpolate(mode='nearest') source index: min(floor(dst * scale), in - 1), scale = in/out in fp32
+int nearest_src(int dst, int in_size, int out_size) {
+    const float scale = (float)in_size / (float)out_size;
+    const int s = (int)floorf((float)dst * scale);
+    return s < in_size - 1 ? s : in_size - 1;
+}
+
+// refidx[y] = down(up(y)); lo/hi[r] = contiguous range of y with refidx[y] == r (empty unless r is a reference)
+void contour_tables(int n, int32_t* ref, int32_t* lo, int32_t* hi) {
+    const int n4 = n / 4;
+    for (int y = 0; y < n; ++y) { lo[y] = 0; hi[y] = 0; }
+    for (int y = 0; y < n; ++y) {
+        int r = y;
+        if (n4 > 0) r = nearest_src(nearest_src(y, n4, n), n, n4);
+        ref[y] = r;
+    }
+    for (int y = 0; y < n; ++y) {
+        const int r = ref[y];
+        if (hi[r] == 0) { lo[r] = y; hi[r] = y + 1; }
+        else            { hi[r] = y + 1; }
+    }
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(MM_E_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return MM_OK;
+}
+
+void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int no_mask, mm_raster_params& p) {
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.V = c->V; p.F = c->F; p.H = c->H; p.W = c->W; p.Ht = Ht; p.Wt = Wt;
+    p.nstx = c->nstx; p.st_rows = c->st_rows; p.nbands = c->nbands; p.nwords = c->nwords; p.knum = c->knum;
+    p.sx = c->sx; p.sy = c->sy; p.blen = c->blen; p.multiplier = c->multiplier; p.eps = c->eps; p.sigmainv = c->sigmainv;
+    p.no_mask = no_mask;
+    p.face_uvs = c->d_face_uvs;
+    p.tab = c->d_tab;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mm_abi_version(void) { return MM_ABI_VERSION; }
+const char* mm_last_error(void) { return g_err; }
+
+int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_host, const float* face_uvs_host,
+                  int H, int W, float proj_x, float proj_y, float sigmainv, float boxlen, int knum,
+                  float multiplier, float eps)
+{
+    MM_REQUIRE(out != nullptr, "out");
+    *out = nullptr;
+    MM_REQUIRE(V > 0 && F > 0 && H > 0 && W > 0, "V, F, H, W must be positive");
+    MM_REQUIRE(faces_host && face_uvs_host, "faces_host / face_uvs_host");
+    MM_REQUIRE(knum > 0 && knum <= MM_MAX_KNUM, "knum out of range");
+    MM_REQUIRE(multiplier > 0.0f, "multiplier");
+    for (int i = 0; i < F * 3; ++i)
+        if (faces_host[i] < 0 || faces_host[i] >= V) return fail(MM_E_INVALID, "faces[%d] = %d out of [0,%d)", i, faces_host[i], V);
+    int ndev = 0;
+    MM_CUDA(cudaGetDeviceCount(&ndev));
+    MM_REQUIRE(device >= 0 && device < ndev, "device index");
+    MM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(MM_E_UNSUPPORTED, "libmagicmirror is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+
+    mm_ctx* c = new mm_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device; c->V = V; c->F = F; c->H = H; c->W = W;
+    c->proj_x = proj_x; c->proj_y = proj_y;
+    c->sigmainv = sigmainv; c->boxlen = boxlen; c->multiplier = multiplier; c->eps = eps; c->knum = knum;
+    c->sx = multiplier / (float)W;
+    c->sy = multiplier / (float)H;
+    c->blen = boxlen * multiplier;
+    c->nstx = (W + MM_ST_W - 1) / MM_ST_W;
+    c->nwords = (F + 31) / 32;
+    c->num_sms = prop.multiProcessorCount;
+    const int st_total = (H + MM_ST_H - 1) / MM_ST_H;
+    const size_t smem_max = prop.sharedMemPerBlockOptin;
+    int st_rows = 2;
+    if (const char* e = getenv("MM_ST_ROWS")) { const int v = atoi(e); if (v > 0) st_rows = v; }
+    if (st_rows > st_total) st_rows = st_total;
+    c->rec_in_smem = ((size_t)F * MM_REC_FLOATS * 4 <= 112 * 1024) ? 1 : 0;
+    if (const char* e = getenv("MM_REC_SMEM")) c->rec_in_smem = atoi(e) ? c->rec_in_smem : 0;
+    for (;;) {
+        c->st_rows = st_rows;
+        c->nbands = (st_total + st_rows - 1) / st_rows;
+        c->smem_raster = mm_raster_smem_bytes(c);
+        if (c->smem_raster <= smem_max) break;
+        if (st_rows > 1) { st_rows >>= 1; continue; }
+        if (c->rec_in_smem) { c->rec_in_smem = 0; continue; }
+        const size_t need = c->smem_raster;
+        delete c;
+        return fail(MM_E_UNSUPPORTED, "F=%d W=%d needs %zu B of shared memory per CTA (> %zu)", F, W, need, smem_max);
+    }
+    const size_t vs_f = mm_vertex_smem_fwd(V), vs_b = mm_vertex_smem_bwd(V);
+    if (vs_f > smem_max || vs_b > smem_max) {
+        delete c;
+        return fail(MM_E_UNSUPPORTED, "V=%d needs %zu B of shared memory in the vertex stage (> %zu)", V, vs_b, smem_max);
+    }
+    mm_vertex_set_smem(vs_f, vs_b);
+    cudaError_t e = mm_raster_configure(c);
+    if (e != cudaSuccess) { delete c; return fail(MM_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+
+    std::vector<int32_t> tab(3 * (size_t)H + 3 * (size_t)W);
+    contour_tables(H, tab.data(), tab.data() + H, tab.data() + 2 * H);
+    contour_tables(W, tab.data() + 3 * H, tab.data() + 3 * H + W, tab.data() + 3 * H + 2 * W);
+    if (cudaMalloc(&c->d_faces, (size_t)F * 3 * 4) != cudaSuccess ||
+        cudaMalloc(&c->d_face_uvs, (size_t)F * 6 * 4) != cudaSuccess ||
+        cudaMalloc(&c->d_tab, tab.size() * 4) != cudaSuccess) {
+        mm_ctx_destroy(c);
+        return fail(MM_E_CUDA, "cudaMalloc of ctx tables failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    MM_CUDA(cudaMemcpy(c->d_faces, faces_host, (size_t)F * 3 * 4, cudaMemcpyHostToDevice));
+    MM_CUDA(cudaMemcpy(c->d_face_uvs, face_uvs_host, (size_t)F * 6 * 4, cudaMemcpyHostToDevice));
+    MM_CUDA(cudaMemcpy(c->d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    *out = c;
+    return MM_OK;
+}
+
+int mm_ctx_destroy(mm_ctx* c) {
+    if (!c) return MM_OK;
+    cudaFree(c->d_faces);
+    cudaFree(c->d_face_uvs);
+    cudaFree(c->d_tab);
+    delete c;
+    return MM_OK;
+}
+
+size_t mm_workspace_bytes(const mm_ctx* c, int B) {
+    if (!c || B <= 0) return 0;
+    return mm_ws_make(c, B).total;
+}
+
+int mm_render_forward(mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev, const float* dist,
+                      const float* bias, const float* tex, int Ht, int Wt, const float* lights, const float* bg,
+                      int no_mask, float* rgba, float* face_normals, float* imnormal, int32_t* face_idx,
+                      void* workspace, void* stream)
+{
+    MM_REQUIRE(c && B > 0, "ctx / B");
+    MM_REQUIRE(vertices && azim && elev && dist && bias && tex && lights, "NULL input");
+    MM_REQUIRE(Ht > 0 && Wt > 0, "texture size");
+    MM_REQUIRE(!no_mask || bg, "no_mask=1 requires bg");
+    MM_REQUIRE(rgba && workspace, "rgba / workspace");
+    cudaStream_t s = (cudaStream_t)stream;
+    const mm_ws_layout L = mm_ws_make(c, B);
+    char* ws = (char*)workspace;
+    mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg),
+                         face_normals, nullptr, s);
+    if (int r = check_launch("vertex_fwd")) return r;
+    mm_raster_params p;
+    fill_params(c, B, Ht, Wt, no_mask, p);
+    p.frec = (const float*)(ws + L.frec);
+    p.tex = tex; p.lights = lights; p.bg = bg;
+    p.rgba = rgba; p.imnormal = imnormal;
+    p.face_idx_ws = (int32_t*)(ws + L.face_idx); p.face_idx_out = face_idx;
+    p.part_fwd = (float*)(ws + L.part_fwd);
+    mm_launch_raster_fwd(c, p, false, s);
+    return check_launch("raster_fwd");
+}
+
+int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev, const float* dist,
+                       const float* bias, const float* tex, int Ht, int Wt, const float* lights, const float* bg,
+                       int no_mask, const float* rgba, const float* g_rgba, const float* g_face_normals,
+                       float* g_vertices, float* g_azim, float* g_elev, float* g_dist, float* g_bias, float* g_tex,
+                       float* g_lights, float* g_bg, void* workspace, void* stream)
+{
+    MM_REQUIRE(c && B > 0, "ctx / B");
+    MM_REQUIRE(vertices && azim && elev && dist && bias && tex && lights, "NULL input");
+    MM_REQUIRE(!no_mask || bg, "no_mask=1 requires bg");
+    MM_REQUIRE(rgba && g_rgba && workspace, "rgba / g_rgba / workspace");
+    MM_REQUIRE(g_vertices && g_azim && g_elev && g_dist && g_bias && g_tex && g_lights, "NULL gradient output");
+    cudaStream_t s = (cudaStream_t)stream;
+    const mm_ws_layout L = mm_ws_make(c, B);
+    char* ws = (char*)workspace;
+    const size_t HW = (size_t)c->H * c->W;
+    MM_CUDA(cudaMemsetAsync(ws + L.gfacc, 0, (size_t)B * c->F * 9 * 4, s));
+    MM_CUDA(cudaMemsetAsync(g_tex, 0, (size_t)B * 3 * Ht * Wt * 4, s));
+    if (g_bg && !no_mask) MM_CUDA(cudaMemsetAsync(g_bg, 0, (size_t)B * 3 * HW * 4, s));
+    mm_raster_params p;
+    fill_params(c, B, Ht, Wt, no_mask, p);
+    p.frec = (const float*)(ws + L.frec);
+    p.tex = tex; p.lights = lights; p.bg = bg;
+    p.rgba = const_cast<float*>(rgba);
+    p.face_idx_ws = (int32_t*)(ws + L.face_idx);
+    p.g_rgba = g_rgba;
+    p.analytic_loss = 0;
+    p.gfacc = (float*)(ws + L.gfacc);
+    p.g_tex = g_tex; p.g_bg = no_mask ? g_bg : nullptr;
+    p.part_bwd = (float*)(ws + L.part_bwd);
+    mm_launch_raster_bwd(c, p, s);
+    if (int r = check_launch("raster_bwd")) return r;
+    mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.part_bwd, g_vertices,
+                         g_azim, g_elev, g_dist, g_bias, g_lights, s);
+    return check_launch("vertex_bwd");
+}
+
+int mm_recon_data_forward(mm_ctx* c, int B, const float* pred, const float* gt, float image_weight, float contour,
+                          float* loss, float* iou_sums, void* workspace, void* stream)
+{
+    MM_REQUIRE(c && B > 0, "ctx / B");
+    MM_REQUIRE(pred && gt && loss && workspace, "NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const mm_ws_layout L = mm_ws_make(c, B);
+    char* ws = (char*)workspace;
+    mm_launch_recon_fwd(c, B, pred, gt, contour, (float*)(ws + L.part_fwd), s);
+    if (int r = check_launch("recon_fwd")) return r;
+    mm_launch_loss_finalize(c, B, (const float*)(ws + L.part_fwd), nullptr, image_weight, contour, loss, iou_sums, s);
+    return check_launch("loss_finalize");
+}
+
+int mm_recon_data_backward(mm_ctx* c, int B, const float* pred, const float* gt, float image_weight, float contour,
+                           float loss_scale, float* g_pred, void* workspace, void* stream)
+{
+    MM_REQUIRE(c && B > 0, "ctx / B");
+    MM_REQUIRE(pred && gt && g_pred && workspace, "NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const mm_ws_layout L = mm_ws_make(c, B);
+    char* ws = (char*)workspace;
+    // the IoU sums are re-derived so that the call does not depend on workspace state of an earlier forward
+    mm_launch_recon_fwd(c, B, pred, gt, 0.0f, (float*)(ws + L.part_fwd), s);
+    if (int r = check_launch("recon_fwd")) return r;
+    mm_launch_recon_bwd(c, B, pred, gt, (const float*)(ws + L.part_fwd), image_weight, contour, loss_scale, g_pred, s);
+    return check_launch("recon_bwd");
+}
+
+int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
+                              const float* dist, const float* bias, const float* tex, int Ht, int Wt,
+                              const float* lights, const float* bg, int no_mask, const float* gt, float image_weight,
+                              float contour, float loss_scale, const float* g_rgba_extra, const float* g_face_normals,
+                              float* rgba,
+                              float* face_normals, float* loss, float* g_vertices, float* g_azim, float* g_elev,
+                              float* g_dist, float* g_bias, float* g_tex, float* g_lights, float* g_bg,
+                              void* workspace, void* stream)
+{
+    MM_REQUIRE(c && B > 0, "ctx / B");
+    MM_REQUIRE(vertices && azim && elev && dist && bias && tex && lights && gt, "NULL input");
+    MM_REQUIRE(Ht > 0 && Wt > 0, "texture size");
+    MM_REQUIRE(!no_mask || bg, "no_mask=1 requires bg");
+    MM_REQUIRE(rgba && loss && workspace, "rgba / loss / workspace");
+    MM_REQUIRE(g_vertices && g_azim && g_elev && g_dist && g_bias && g_tex && g_lights, "NULL gradient output");
+    cudaStream_t s = (cudaStream_t)stream;
+    const mm_ws_layout L = mm_ws_make(c, B);
+    char* ws = (char*)workspace;
+    const size_t HW = (size_t)c->H * c->W;
+    MM_CUDA(cudaMemsetAsync(g_tex, 0, (size_t)B * 3 * Ht * Wt * 4, s));
+    if (g_bg && !no_mask) MM_CUDA(cudaMemsetAsync(g_bg, 0, (size_t)B * 3 * HW * 4, s));
+    mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg),
+                         face_normals, (float*)(ws + L.gfacc), s);
+    if (int r = check_launch("vertex_fwd")) return r;
+    mm_raster_params p;
+    fill_params(c, B, Ht, Wt, no_mask, p);
+    p.frec = (const float*)(ws + L.frec);
+    p.tex = tex; p.lights = lights; p.bg = bg; p.gt = gt;
+    p.rgba = rgba;
+    p.face_idx_ws = (int32_t*)(ws + L.face_idx);
+    p.part_fwd = (float*)(ws + L.part_fwd);
+    mm_launch_raster_fwd(c, p, true, s);
+    if (int r = check_launch("raster_fwd")) return r;
+    p.g_rgba = g_rgba_extra;
+    p.part_fwd_in = p.part_fwd;
+    p.image_weight = image_weight; p.contour = contour; p.loss_scale = loss_scale;
+    p.analytic_loss = 1;
+    p.gfacc = (float*)(ws + L.gfacc);
+    p.g_tex = g_tex; p.g_bg = no_mask ? g_bg : nullptr;
+    p.part_bwd = (float*)(ws + L.part_bwd);
+    mm_launch_raster_bwd(c, p, s);
+    if (int r = check_launch("raster_bwd")) return r;
+    mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.part_bwd, g_vertices, g_azim,
+                         g_elev, g_dist, g_bias, g_lights, s);
+    if (int r = check_launch("vertex_bwd")) return r;
+    mm_launch_loss_finalize(c, B, p.part_fwd, p.part_bwd, image_weight, contour, loss, nullptr, s);
+    return check_launch("loss_finalize");
+}
+
+int mm_debug_export_faces(mm_ctx* c, int B, const void* workspace, float* fvi, float* fvz, float* fnz, void* stream)
+{
+    MM_REQUIRE(c && B > 0 && workspace, "ctx / B / workspace");
+    const mm_ws_layout L = mm_ws_make(c, B);
+    const char* ws = (const char*)workspace;
+    mm_launch_export_faces(c, B, (const float*)(ws + L.frec), (const float*)(ws + L.vimg), fvi, fvz, fnz,
+                           (cudaStream_t)stream);
+    return check_launch("export_faces");
+}
+
+}  // extern "C"

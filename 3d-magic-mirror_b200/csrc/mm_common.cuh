@@ -1,0 +1,124 @@
+// mm_common.cuh -- shared definitions for libmagicmirror.so (sm_100a only).
+//
+// Data layout in HBM (all fp32 unless noted), B = batch, V vertices, F faces:
+//   ctx (library-owned, static per mesh):
+//     faces      [F,3]   int32        (DiffRender.faces,    networks.py:196,253)
+//     face_uvs   [F,3,2]              (DiffRender.face_uvs, networks.py:201,254)
+//     refrow/rowlo/rowhi [H], refcol/collo/colhi [W] int32: nearest-down/nearest-up
+//                index tables of the contour term (networks.py:381-382)
+//   workspace (caller-owned, per call):
+//     frec       [B,F,12]  face records: (ax,ay,bx,by | cx,cy,az,bz | cz,nx,ny,nz),
+//                          xy already multiplied by `multiplier`, z camera-space,
+//                          n = unit face normal in camera space.  48 B / face, one
+//                          contiguous block per image so a CTA stages it with ONE
+//                          cp.async.bulk (TMA bulk copy) into shared memory.
+//     vimg       [B,V,2]   unscaled image-plane xy (debug export / parity tests)
+//     face_idx   [B,H,W]   int32 winner of the hard pass (-1 none); saved for backward
+//     gfacc      [B,F,9]   backward accumulators: d/d(fvi) (6, unscaled) + d/d(unit normal) (3)
+//     part_fwd   [B,NB,4]  per-CTA partial sums (L1, N, D, contour)  NB = bands per image
+//     part_bwd   [B,NB,12] per-CTA partials (contour sum, 9 light grads, -, -)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#define MM_THREADS      256          // threads per raster CTA (8 warps)
+#define MM_WARPS        (MM_THREADS / 32)
+#define MM_ST_W         8            // sub-tile (one warp) = 8 x 4 pixels
+#define MM_ST_H         4
+#define MM_REC_FLOATS   12
+#define MM_MAX_KNUM     64
+
+struct mm_ctx {
+    int device;
+    int V, F, H, W;
+    float proj_x, proj_y;
+    float sigmainv, boxlen, multiplier, eps;
+    int knum;
+    // derived
+    float sx, sy;            // multiplier / W, multiplier / H  (fp32 division, DIBR_SPEC A.1)
+    float blen;              // boxlen * multiplier
+    int nstx;                // sub-tile columns  = ceil(W / 8)
+    int st_rows;             // sub-tile rows per CTA band
+    int nbands;              // CTAs per image    = ceil(ceil(H/4) / st_rows)
+    int nwords;              // bitmask words per sub-tile = ceil(F / 32)
+    int rec_in_smem;         // face records staged in shared memory (else read through L1)
+    size_t smem_raster;      // dynamic smem bytes of the raster kernels
+    int num_sms;
+    // device arrays
+    int32_t* d_faces;        // [F,3]
+    float*   d_face_uvs;     // [F,6]
+    int32_t* d_tab;          // [3*H + 3*W] contour tables: refrow,rowlo,rowhi,refcol,collo,colhi
+};
+
+struct mm_ws_layout {
+    size_t frec, vimg, face_idx, gfacc, part_fwd, part_bwd, total;
+};
+
+static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
+    mm_ws_layout L;
+    size_t off = 0;
+    L.frec = off;     off = mm_align_up(off + (size_t)B * c->F * MM_REC_FLOATS * 4, 256);
+    L.vimg = off;     off = mm_align_up(off + (size_t)B * c->V * 2 * 4, 256);
+    L.face_idx = off; off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
+    L.gfacc = off;    off = mm_align_up(off + (size_t)B * c->F * 9 * 4, 256);
+    L.part_fwd = off; off = mm_align_up(off + (size_t)B * c->nbands * 4 * 4, 256);
+    L.part_bwd = off; off = mm_align_up(off + (size_t)B * c->nbands * 12 * 4, 256);
+    L.total = off;
+    return L;
+}
+
+// parameters shared by the raster kernels (passed by value)
+struct mm_raster_params {
+    int B, V, F, H, W, Ht, Wt;
+    int nstx, st_rows, nbands, nwords, knum;
+    float sx, sy, blen, multiplier, eps, sigmainv;
+    int no_mask;
+    const float* frec;       // [B,F,12]
+    const float* face_uvs;   // [F,6]
+    const float* tex;        // [B,3,Ht,Wt]
+    const float* lights;     // [B,9]
+    const float* bg;         // [B,3,H,W] or NULL
+    const float* gt;         // [B,4,H,W] or NULL
+    const int32_t* tab;      // contour tables
+    float* rgba;             // [B,4,H,W]
+    float* imnormal;         // [B,H,W,3] or NULL
+    int32_t* face_idx_ws;    // [B,H,W]
+    int32_t* face_idx_out;   // [B,H,W] or NULL
+    float* part_fwd;         // [B,NB,4]
+    // backward
+    const float* g_rgba;     // [B,4,H,W] or NULL
+    const float* part_fwd_in;// [B,NB,4] forward partials (IoU sums re-derived per CTA)
+    float image_weight, contour, loss_scale;
+    int analytic_loss;
+    float* gfacc;            // [B,F,9]
+    float* g_tex;            // [B,3,Ht,Wt]
+    float* g_bg;             // [B,3,H,W] or NULL
+    float* part_bwd;         // [B,NB,12]
+};
+
+// launchers (defined in the .cu files)
+void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
+                          const float* dist, const float* bias, float* frec, float* vimg, float* face_normals,
+                          float* gfacc_zero, cudaStream_t s);
+void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
+                          const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,
+                          const float* part_bwd, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
+                          float* g_bias, float* g_lights, cudaStream_t s);
+void mm_launch_raster_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_loss, cudaStream_t s);
+void mm_launch_raster_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
+void mm_launch_loss_finalize(const mm_ctx* c, int B, const float* part_fwd, const float* part_bwd,
+                             float image_weight, float contour, float* loss, float* iou_out, cudaStream_t s);
+void mm_launch_recon_fwd(const mm_ctx* c, int B, const float* pred, const float* gt, float contour, float* part_fwd,
+                         cudaStream_t s);
+void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float* gt, const float* part_fwd,
+                         float image_weight, float contour, float loss_scale, float* g_pred, cudaStream_t s);
+cudaError_t mm_raster_configure(const mm_ctx* c);
+size_t mm_raster_smem_bytes(const mm_ctx* c);
+size_t mm_vertex_smem_fwd(int V);
+size_t mm_vertex_smem_bwd(int V);
+void mm_vertex_set_smem(size_t fwd, size_t bwd);
+void mm_launch_export_faces(const mm_ctx* c, int B, const float* frec, const float* vimg, float* fvi, float* fvz,
+                            float* fnz, cudaStream_t s);

@@ -1,0 +1,231 @@
+// mm_device.cuh -- per-pixel device functions shared by the raster forward and
+// backward kernels.  Geometry decisions (bbox tests, barycentric weights, depth,
+// soft-silhouette distances) are written with explicit round-to-nearest intrinsics
+// in the operation order of docs/DIBR_SPEC.md so that nvcc can neither contract
+// them into FMAs nor reorder them: `face_idx` has to be bit-identical to the
+// oracle's on identical face records, and the DIB-R distance formulas cancel badly
+// enough in fp32 (C = x2*y1 - x1*y2 on 1000-scaled coordinates) that a different
+// rounding sequence shows up at the 1e-3 level in the silhouette probability.
+#pragma once
+#include "mm_common.cuh"
+
+#define MUL(a, b) __fmul_rn((a), (b))
+#define ADD(a, b) __fadd_rn((a), (b))
+#define SUB(a, b) __fsub_rn((a), (b))
+#define DIV(a, b) __fdiv_rn((a), (b))
+
+struct FaceRec {
+    float ax, ay, bx, by, cx, cy, az, bz, cz, nx, ny, nz;
+};
+
+__device__ __forceinline__ FaceRec load_rec(const float* __restrict__ rec_base, int f) {
+    const float4* p = reinterpret_cast<const float4*>(rec_base) + f * 3;
+    const float4 r0 = p[0], r1 = p[1], r2 = p[2];
+    FaceRec r;
+    r.ax = r0.x; r.ay = r0.y; r.bx = r0.z; r.by = r0.w;
+    r.cx = r1.x; r.cy = r1.y; r.az = r1.z; r.bz = r1.w;
+    r.cz = r2.x; r.nx = r2.y; r.ny = r2.z; r.nz = r2.w;
+    return r;
+}
+
+// DIBR_SPEC A.1: pixel centre in multiplier-scaled NDC
+__device__ __forceinline__ float pix_x(int ix, int W, float sx) { return MUL(sx, (float)(2 * ix + 1 - W)); }
+__device__ __forceinline__ float pix_y(int iy, int H, float sy) { return MUL(sy, (float)(H - 2 * iy - 1)); }
+
+struct Bary {
+    float k1, k2, k3, w0, w1, w2;
+    float m, p, n, q, s, t;
+};
+
+__device__ __forceinline__ void bary_eval(const FaceRec& r, float x0, float y0, float eps, Bary& b) {
+    b.m = SUB(r.bx, r.ax); b.p = SUB(r.by, r.ay);
+    b.n = SUB(r.cx, r.ax); b.q = SUB(r.cy, r.ay);
+    b.s = SUB(x0, r.ax);   b.t = SUB(y0, r.ay);
+    b.k1 = SUB(MUL(b.s, b.q), MUL(b.n, b.t));
+    b.k2 = SUB(MUL(b.m, b.t), MUL(b.s, b.p));
+    b.k3 = SUB(MUL(b.m, b.q), MUL(b.n, b.p));
+    const float den = ADD(b.k3, eps);
+    b.w1 = DIV(b.k1, den);
+    b.w2 = DIV(b.k2, den);
+    b.w0 = SUB(SUB(1.0f, b.w1), b.w2);
+}
+
+// DIBR_SPEC A.2: returns true and fills (w, z) iff the pixel is inside the tight bbox and the triangle
+__device__ __forceinline__ bool hard_test(const FaceRec& r, float x0, float y0, float eps,
+                                          float& w0, float& w1, float& w2, float& zz) {
+    const float xmin = fminf(fminf(r.ax, r.bx), r.cx), xmax = fmaxf(fmaxf(r.ax, r.bx), r.cx);
+    const float ymin = fminf(fminf(r.ay, r.by), r.cy), ymax = fmaxf(fmaxf(r.ay, r.by), r.cy);
+    if (x0 < xmin || x0 >= xmax || y0 < ymin || y0 >= ymax) return false;
+    Bary b;
+    bary_eval(r, x0, y0, eps, b);
+    if (b.w0 < 0.0f || b.w1 < 0.0f || b.w2 < 0.0f) return false;
+    w0 = b.w0; w1 = b.w1; w2 = b.w2;
+    zz = ADD(ADD(MUL(b.w0, r.az), MUL(b.w1, r.bz)), MUL(b.w2, r.cz));
+    return true;
+}
+
+// DIBR_SPEC A.4: half-open test against the bbox enlarged by blen
+__device__ __forceinline__ bool soft_bbox_test(const FaceRec& r, float x0, float y0, float blen) {
+    const float xmin = SUB(fminf(fminf(r.ax, r.bx), r.cx), blen), xmax = ADD(fmaxf(fmaxf(r.ax, r.bx), r.cx), blen);
+    const float ymin = SUB(fminf(fminf(r.ay, r.by), r.cy), blen), ymax = ADD(fmaxf(fmaxf(r.ay, r.by), r.cy), blen);
+    return !(x0 < xmin || x0 >= xmax || y0 < ymin || y0 >= ymax);
+}
+
+// squared distance to the edge (x1,y1)-(x2,y2): perpendicular if the foot lies on the segment, else "far"
+__device__ __forceinline__ float edge_d2(float x1, float y1, float x2, float y2, float x0, float y0, float far) {
+    const float A = SUB(y2, y1), B = SUB(x1, x2), C = SUB(MUL(x2, y1), MUL(x1, y2));
+    const float up = ADD(ADD(MUL(A, x0), MUL(B, y0)), C);
+    const float down = ADD(MUL(A, A), MUL(B, B));
+    const float dn = ADD(down, 1e-10f);
+    float x3 = SUB(SUB(MUL(MUL(B, B), x0), MUL(MUL(A, B), y0)), MUL(A, C));
+    float y3 = SUB(SUB(MUL(MUL(A, A), y0), MUL(MUL(A, B), x0)), MUL(B, C));
+    x3 = DIV(x3, dn);
+    y3 = DIV(y3, dn);
+    const float direct = ADD(MUL(SUB(x3, x1), SUB(x3, x2)), MUL(SUB(y3, y1), SUB(y3, y2)));
+    return direct > 0.0f ? far : DIV(MUL(up, up), dn);
+}
+
+// DIBR_SPEC A.4: min over 3 edge + 3 vertex squared distances; returns d2 and the type 0..5
+__device__ __forceinline__ float soft_d2(const FaceRec& r, float x0, float y0, float mult, int& type) {
+    const float far = MUL(MUL(4.0f, mult), mult);
+    float d = edge_d2(r.ax, r.ay, r.bx, r.by, x0, y0, far);
+    type = 0;
+    float v = edge_d2(r.bx, r.by, r.cx, r.cy, x0, y0, far);
+    if (d > v) { d = v; type = 1; }
+    v = edge_d2(r.cx, r.cy, r.ax, r.ay, x0, y0, far);
+    if (d > v) { d = v; type = 2; }
+    v = ADD(MUL(SUB(x0, r.ax), SUB(x0, r.ax)), MUL(SUB(y0, r.ay), SUB(y0, r.ay)));
+    if (d > v) { d = v; type = 3; }
+    v = ADD(MUL(SUB(x0, r.bx), SUB(x0, r.bx)), MUL(SUB(y0, r.by), SUB(y0, r.by)));
+    if (d > v) { d = v; type = 4; }
+    v = ADD(MUL(SUB(x0, r.cx), SUB(x0, r.cx)), MUL(SUB(y0, r.cy), SUB(y0, r.cy)));
+    if (d > v) { d = v; type = 5; }
+    return d;
+}
+
+__device__ __forceinline__ float soft_prob(float d2, float sigmainv, float mult) {
+    const float z = DIV(DIV(MUL(sigmainv, d2), mult), mult);
+    return expf(-z);
+}
+
+// ------------------------------------------------------------------ shading
+// kaolin texture_mapping == grid_sample(bilinear, align_corners=False, padding_mode='border') with v flipped
+struct Bilin {
+    int ix, iy;            // north-west texel
+    float nw, ne, sw, se;  // weights
+    float x, y;            // clipped, unnormalised coordinates
+    bool in_x, in_y;       // clip gradient masks
+};
+
+__device__ __forceinline__ void bilin_setup(float u, float v, int Ht, int Wt, Bilin& s) {
+    const float gx = u * 2.0f - 1.0f;
+    const float gy = -(v * 2.0f - 1.0f);
+    float x = ((gx + 1.0f) * (float)Wt - 1.0f) * 0.5f;
+    float y = ((gy + 1.0f) * (float)Ht - 1.0f) * 0.5f;
+    s.in_x = (x > 0.0f) && (x < (float)(Wt - 1));
+    s.in_y = (y > 0.0f) && (y < (float)(Ht - 1));
+    x = fminf((float)(Wt - 1), fmaxf(x, 0.0f));
+    y = fminf((float)(Ht - 1), fmaxf(y, 0.0f));
+    const float fx = floorf(x), fy = floorf(y);
+    s.ix = (int)fx; s.iy = (int)fy;
+    s.x = x; s.y = y;
+    const float tx = x - fx, ty = y - fy;
+    s.nw = (1.0f - tx) * (1.0f - ty);
+    s.ne = tx * (1.0f - ty);
+    s.sw = (1.0f - tx) * ty;
+    s.se = tx * ty;
+}
+
+struct TexFetch {
+    float nw, ne, sw, se;
+};
+
+__device__ __forceinline__ TexFetch tex_fetch(const float* __restrict__ plane, const Bilin& s, int Ht, int Wt) {
+    TexFetch t;
+    const bool xe = (s.ix + 1) < Wt, ys = (s.iy + 1) < Ht;
+    const float* p = plane + (size_t)s.iy * Wt + s.ix;
+    t.nw = __ldg(p);
+    t.ne = xe ? __ldg(p + 1) : 0.0f;
+    t.sw = ys ? __ldg(p + Wt) : 0.0f;
+    t.se = (xe && ys) ? __ldg(p + Wt + 1) : 0.0f;
+    return t;
+}
+
+// kaolin spherical_harmonic_lighting (9 bands)
+#define SH_C0 0.28209479177f
+#define SH_C1 0.4886025119f
+#define SH_C2 1.09254843059f
+#define SH_C3 0.94617469575f
+#define SH_C3B 0.31539156525f
+#define SH_C4 0.77254840404f
+#define SH_C5 0.38627420202f
+
+__device__ __forceinline__ void sh_bands(float x, float y, float z, float* bnd) {
+    bnd[0] = SH_C0;
+    bnd[1] = SH_C1 * x;
+    bnd[2] = SH_C1 * z;
+    bnd[3] = SH_C1 * y;
+    bnd[4] = SH_C2 * (x * y);
+    bnd[5] = SH_C2 * (y * z);
+    bnd[6] = SH_C3 * (z * z) - SH_C3B;
+    bnd[7] = SH_C4 * (x * z);
+    bnd[8] = SH_C5 * (x * x - y * y);
+}
+
+__device__ __forceinline__ float sh_coef(const float* bnd, const float* l) {
+    float c = 0.0f;
+    #pragma unroll
+    for (int i = 0; i < 9; ++i) c += bnd[i] * l[i];
+    return c;
+}
+
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+// ------------------------------------------------------------------ loss (DIBR_SPEC A.7; networks.py:364-390)
+__device__ __forceinline__ float l1_term(float pred, float gt, float gm) {
+    const float one_m = 1.0f - gm;
+    const float a = pred * gm + one_m;
+    const float b = gt * gm + one_m;
+    return a - b;          // caller takes |.| / sign(.)
+}
+
+__device__ __forceinline__ float sgnf(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
+
+// block-wide sum for MM_THREADS threads; `red` holds MM_WARPS floats
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.0f;
+    #pragma unroll
+    for (int i = 0; i < MM_WARPS; ++i) r += red[i];
+    return r;
+}
+
+// ------------------------------------------------------------------ TMA bulk copy (global -> shared) helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}

@@ -1,0 +1,153 @@
+// mm_loss.cu -- DiffRender.recon_data (networks.py:364-390) as stand-alone kernels
+// (masked L1 + kaolin mask_iou + contour MSE) and the loss finalisation used by both
+// the stand-alone and the fused render-compare path.
+#include "mm_device.cuh"
+
+namespace {
+
+// One CTA per (band of rows, image): partial sums (L1, N, D, contour) -> part_fwd[b][band][4]
+__global__ void __launch_bounds__(MM_THREADS)
+k_recon_fwd(int H, int W, int band_rows, int nbands, float contour,
+            const float* __restrict__ pred, const float* __restrict__ gt, const int32_t* __restrict__ tab,
+            float* __restrict__ part_fwd)
+{
+    __shared__ float red[MM_WARPS];
+    const int b = blockIdx.y, band = blockIdx.x;
+    const size_t HW = (size_t)H * W;
+    const float* pb = pred + (size_t)b * 4 * HW;
+    const float* gb = gt + (size_t)b * 4 * HW;
+    const int32_t* refrow = tab;
+    const int32_t* refcol = tab + 3 * H;
+    const int y0 = band * band_rows, y1 = min(H, y0 + band_rows);
+    float a_l1 = 0.0f, a_n = 0.0f, a_d = 0.0f, a_c = 0.0f;
+    for (int i = y0 * W + threadIdx.x; i < y1 * W; i += MM_THREADS) {
+        const float gm = gb[3 * HW + i], m = pb[3 * HW + i];
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) a_l1 += fabsf(l1_term(pb[c * HW + i], gb[c * HW + i], gm));
+        const float mul = m * gm;
+        a_n += mul;
+        a_d += (m + gm) - mul;
+        if (contour > 0.0f) {
+            const int iy = i / W, ix = i - iy * W;
+            const size_t rp = (size_t)refrow[iy] * W + refcol[ix];
+            const float d = fabsf(m - pb[3 * HW + rp]) - fabsf(gm - gb[3 * HW + rp]);
+            a_c += d * d;
+        }
+    }
+    const float s0 = block_sum(a_l1, red), s1 = block_sum(a_n, red), s2 = block_sum(a_d, red), s3 = block_sum(a_c, red);
+    if (threadIdx.x == 0) {
+        float* pf = part_fwd + ((size_t)b * nbands + band) * 4;
+        pf[0] = s0; pf[1] = s1; pf[2] = s2; pf[3] = s3;
+    }
+}
+
+__global__ void __launch_bounds__(MM_THREADS)
+k_recon_bwd(int B, int H, int W, int band_rows, int nbands, float image_weight, float contour, float loss_scale,
+            const float* __restrict__ pred, const float* __restrict__ gt, const int32_t* __restrict__ tab,
+            const float* __restrict__ part_fwd, float* __restrict__ g_pred)
+{
+    const int b = blockIdx.y, band = blockIdx.x;
+    const size_t HW = (size_t)H * W;
+    const float* pb = pred + (size_t)b * 4 * HW;
+    const float* gb = gt + (size_t)b * 4 * HW;
+    float* go = g_pred + (size_t)b * 4 * HW;
+    const int32_t* refrow = tab;
+    const int32_t* rowlo = tab + H;
+    const int32_t* rowhi = tab + 2 * H;
+    const int32_t* refcol = tab + 3 * H;
+    const int32_t* collo = tab + 3 * H + W;
+    const int32_t* colhi = tab + 3 * H + 2 * W;
+    float Nb = 0.0f, Db = 0.0f;
+    for (int k = 0; k < nbands; ++k) {
+        Nb += part_fwd[((size_t)b * nbands + k) * 4 + 1];
+        Db += part_fwd[((size_t)b * nbands + k) * 4 + 2];
+    }
+    const float De = Db + 1e-10f;
+    const float k_img = loss_scale * image_weight / ((float)B * 3.0f * (float)HW);
+    const float k_iou = loss_scale / (float)B;
+    const float k_cont = loss_scale * contour / ((float)B * (float)HW);
+    const int y0 = band * band_rows, y1 = min(H, y0 + band_rows);
+    for (int i = y0 * W + threadIdx.x; i < y1 * W; i += MM_THREADS) {
+        const float gm = gb[3 * HW + i], m = pb[3 * HW + i];
+        #pragma unroll
+        for (int c = 0; c < 3; ++c)
+            go[c * HW + i] = k_img * sgnf(l1_term(pb[c * HW + i], gb[c * HW + i], gm)) * gm;
+        float g = -k_iou * (gm * De - Nb * (1.0f - gm)) / (De * De);
+        if (contour > 0.0f) {
+            const int iy = i / W, ix = i - iy * W;
+            const size_t rp = (size_t)refrow[iy] * W + refcol[ix];
+            const float mref = pb[3 * HW + rp], gref = gb[3 * HW + rp];
+            const float dlt = fabsf(m - mref) - fabsf(gm - gref);
+            float gc = 2.0f * dlt * sgnf(m - mref);
+            for (int yy = rowlo[iy]; yy < rowhi[iy]; ++yy)
+                for (int xx = collo[ix]; xx < colhi[ix]; ++xx) {
+                    const size_t q = (size_t)yy * W + xx;
+                    const float mq = pb[3 * HW + q], gq = gb[3 * HW + q];
+                    const float dq = fabsf(mq - m) - fabsf(gq - gm);
+                    gc -= 2.0f * dq * sgnf(mq - m);
+                }
+            g += k_cont * gc;
+        }
+        go[3 * HW + i] = g;
+    }
+}
+
+// loss[0..3] = data, image, mask (1 - mean IoU), contour term.  Single CTA, fixed summation order.
+__global__ void __launch_bounds__(MM_THREADS)
+k_loss_finalize(int B, int H, int W, int nbands, float image_weight, float contour,
+                const float* __restrict__ part_fwd, const float* __restrict__ part_bwd,
+                float* __restrict__ loss, float* __restrict__ iou_out)
+{
+    __shared__ float red[MM_WARPS];
+    float a_l1 = 0.0f, a_c = 0.0f, a_iou = 0.0f;
+    for (int i = threadIdx.x; i < B * nbands; i += MM_THREADS) {
+        a_l1 += part_fwd[(size_t)i * 4 + 0];
+        a_c += part_fwd[(size_t)i * 4 + 3];
+        if (part_bwd) a_c += part_bwd[(size_t)i * 12 + 0];
+    }
+    for (int b = threadIdx.x; b < B; b += MM_THREADS) {
+        float n = 0.0f, d = 0.0f;
+        for (int k = 0; k < nbands; ++k) {
+            n += part_fwd[((size_t)b * nbands + k) * 4 + 1];
+            d += part_fwd[((size_t)b * nbands + k) * 4 + 2];
+        }
+        a_iou += n / (d + 1e-10f);
+        if (iou_out) { iou_out[b * 2] = n; iou_out[b * 2 + 1] = d; }
+    }
+    const float s_l1 = block_sum(a_l1, red), s_c = block_sum(a_c, red), s_iou = block_sum(a_iou, red);
+    if (threadIdx.x == 0) {
+        const float l_img = s_l1 / ((float)B * 3.0f * (float)H * (float)W);
+        const float l_iou = 1.0f - s_iou / (float)B;
+        const float l_cont = (contour > 0.0f) ? s_c / ((float)B * (float)H * (float)W) : 0.0f;
+        const float l_mask = l_iou + ((contour > 0.0f) ? l_cont * contour : 0.0f);
+        loss[0] = image_weight * l_img + l_mask;
+        loss[1] = l_img;
+        loss[2] = l_iou;
+        loss[3] = l_cont;
+    }
+}
+
+}  // namespace
+
+void mm_launch_recon_fwd(const mm_ctx* c, int B, const float* pred, const float* gt, float contour, float* part_fwd,
+                         cudaStream_t s)
+{
+    const dim3 grid(c->nbands, B);
+    k_recon_fwd<<<grid, MM_THREADS, 0, s>>>(c->H, c->W, c->st_rows * MM_ST_H, c->nbands, contour, pred, gt, c->d_tab,
+                                            part_fwd);
+}
+
+void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float* gt, const float* part_fwd,
+                         float image_weight, float contour, float loss_scale, float* g_pred, cudaStream_t s)
+{
+    const dim3 grid(c->nbands, B);
+    k_recon_bwd<<<grid, MM_THREADS, 0, s>>>(B, c->H, c->W, c->st_rows * MM_ST_H, c->nbands, image_weight, contour,
+                                            loss_scale, pred, gt, c->d_tab, part_fwd, g_pred);
+}
+
+void mm_launch_loss_finalize(const mm_ctx* c, int B, const float* part_fwd, const float* part_bwd,
+                             float image_weight, float contour, float* loss, float* iou_out, cudaStream_t s)
+{
+    k_loss_finalize<<<1, MM_THREADS, 0, s>>>(B, c->H, c->W, c->nbands, image_weight, contour, part_fwd, part_bwd,
+                                             loss, iou_out);
+}

@@ -1,0 +1,333 @@
+// mm_vertex.cu -- vertex stage of the render path, forward and backward.
+//
+// Forward fuses, per image (one CTA each): camera_position_from_spherical_angles
+// (smr_utils.py:257-281), generate_transformation_matrix (smr_utils.py:284-311),
+// kaolin prepare_vertices (networks.py:284-287: [v,1]*T, perspective divide, gather
+// by faces, unit face normals) and the second face_normals call (networks.py:289),
+// and emits the 48-byte face records the raster kernels stage into shared memory.
+// The reference runs ~25 tiny kernels + a cuBLAS matmul for this.
+//
+// Backward consumes the per-face accumulators (d/d fvi, d/d unit normal) produced by
+// the raster backward plus the optional upstream gradient of `face_normals`, and
+// chains through normals, projection, transform and the look-at construction down
+// to vertices, azimuth, elevation, distance and bias.
+#include "mm_common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+struct Cam {
+    float T[12];        // 4x3 row-major: rows 0-2 rotation (columns = x,y,z axes), row 3 translation
+    float cam[3];       // camera position
+    float zr[3], zl;    // cam - look_at, its norm
+    float za[3];
+    float xr[3], xl;    // cross(up, za), its norm
+    float xa[3];
+    float ya[3];
+    float ce, se, ca, sa, d;
+};
+
+// DIBR_SPEC V.1-V.2.  Angles in degrees (smr_utils.py:274-276).
+__device__ inline void camera_setup(float az_deg, float el_deg, float d, float bx, float by, Cam& c) {
+    const float k = 3.14159265358979323846f / 180.0f;
+    const float e = k * el_deg, a = k * az_deg;
+    c.ce = cosf(e); c.se = sinf(e); c.ca = cosf(a); c.sa = sinf(a); c.d = d;
+    c.cam[0] = d * c.ce * c.sa;
+    c.cam[1] = d * c.se;
+    c.cam[2] = d * c.ce * c.ca;
+    c.zr[0] = c.cam[0] - bx; c.zr[1] = c.cam[1] - by; c.zr[2] = c.cam[2] - 0.0f;
+    c.zl = sqrtf(c.zr[0] * c.zr[0] + c.zr[1] * c.zr[1] + c.zr[2] * c.zr[2]);
+    for (int i = 0; i < 3; ++i) c.za[i] = c.zr[i] / c.zl;
+    // cross((0,1,0), za) = (za_z, 0, -za_x)
+    c.xr[0] = c.za[2]; c.xr[1] = 0.0f; c.xr[2] = -c.za[0];
+    c.xl = sqrtf(c.xr[0] * c.xr[0] + c.xr[1] * c.xr[1] + c.xr[2] * c.xr[2]);
+    for (int i = 0; i < 3; ++i) c.xa[i] = c.xr[i] / c.xl;
+    // ya = cross(za, xa)
+    c.ya[0] = c.za[1] * c.xa[2] - c.za[2] * c.xa[1];
+    c.ya[1] = c.za[2] * c.xa[0] - c.za[0] * c.xa[2];
+    c.ya[2] = c.za[0] * c.xa[1] - c.za[1] * c.xa[0];
+    for (int i = 0; i < 3; ++i) { c.T[i * 3 + 0] = c.xa[i]; c.T[i * 3 + 1] = c.ya[i]; c.T[i * 3 + 2] = c.za[i]; }
+    for (int j = 0; j < 3; ++j)
+        c.T[9 + j] = (-c.cam[0]) * c.T[0 + j] + (-c.cam[1]) * c.T[3 + j] + (-c.cam[2]) * c.T[6 + j];
+}
+
+__device__ inline void transform_vertex(const float* T, float x, float y, float z, float& cx, float& cy, float& cz) {
+    cx = x * T[0] + y * T[3] + z * T[6] + T[9];
+    cy = x * T[1] + y * T[4] + z * T[7] + T[10];
+    cz = x * T[2] + y * T[5] + z * T[8] + T[11];
+}
+
+// ------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(256)
+k_vertex_fwd(int V, int F, float proj_x, float proj_y, float multiplier,
+             const int32_t* __restrict__ faces, const float* __restrict__ vertices,
+             const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
+             const float* __restrict__ bias,
+             float* __restrict__ frec, float* __restrict__ vimg, float* __restrict__ face_normals,
+             float* __restrict__ gfacc_zero)
+{
+    extern __shared__ float sm[];
+    float* sT = sm;                  // 12
+    float* svc = sm + 16;            // V*3 camera-space
+    float* svi = svc + (size_t)V * 3;  // V*2 image-plane (unscaled)
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) {
+        Cam c;
+        camera_setup(azim[b], elev[b], dist[b], bias[b * 2], bias[b * 2 + 1], c);
+        for (int i = 0; i < 12; ++i) sT[i] = c.T[i];
+    }
+    __syncthreads();
+    const float* vb = vertices + (size_t)b * V * 3;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        float cx, cy, cz;
+        transform_vertex(sT, vb[v * 3], vb[v * 3 + 1], vb[v * 3 + 2], cx, cy, cz);
+        svc[v * 3] = cx; svc[v * 3 + 1] = cy; svc[v * 3 + 2] = cz;
+        // kaolin perspective_camera: (x*px, y*py) / (z * -1)
+        const float den = cz * -1.0f;
+        const float xi = (cx * proj_x) / den, yi = (cy * proj_y) / den;
+        svi[v * 2] = xi; svi[v * 2 + 1] = yi;
+        vimg[((size_t)b * V + v) * 2] = xi;
+        vimg[((size_t)b * V + v) * 2 + 1] = yi;
+    }
+    __syncthreads();
+    float4* rec = reinterpret_cast<float4*>(frec + (size_t)b * F * MM_REC_FLOATS);
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const int i0 = faces[f * 3], i1 = faces[f * 3 + 1], i2 = faces[f * 3 + 2];
+        const float ax = svc[i0 * 3], ay = svc[i0 * 3 + 1], az = svc[i0 * 3 + 2];
+        const float bx = svc[i1 * 3], by = svc[i1 * 3 + 1], bz = svc[i1 * 3 + 2];
+        const float cx = svc[i2 * 3], cy = svc[i2 * 3 + 1], cz = svc[i2 * 3 + 2];
+        const float e0x = bx - ax, e0y = by - ay, e0z = bz - az;
+        const float e1x = cx - ax, e1y = cy - ay, e1z = cz - az;
+        float nx = e0y * e1z - e0z * e1y;
+        float ny = e0z * e1x - e0x * e1z;
+        float nz = e0x * e1y - e0y * e1x;
+        const float len = sqrtf(nx * nx + ny * ny + nz * nz);
+        const float inv = len + 1e-10f;
+        nx /= inv; ny /= inv; nz /= inv;
+        rec[f * 3 + 0] = make_float4(__fmul_rn(svi[i0 * 2], multiplier), __fmul_rn(svi[i0 * 2 + 1], multiplier),
+                                     __fmul_rn(svi[i1 * 2], multiplier), __fmul_rn(svi[i1 * 2 + 1], multiplier));
+        rec[f * 3 + 1] = make_float4(__fmul_rn(svi[i2 * 2], multiplier), __fmul_rn(svi[i2 * 2 + 1], multiplier), az, bz);
+        rec[f * 3 + 2] = make_float4(cz, nx, ny, nz);
+        if (face_normals) {
+            float* fn = face_normals + ((size_t)b * F + f) * 3;
+            fn[0] = nx; fn[1] = ny; fn[2] = nz;
+        }
+        if (gfacc_zero) {
+            float* g = gfacc_zero + ((size_t)b * F + f) * 9;
+            #pragma unroll
+            for (int i = 0; i < 9; ++i) g[i] = 0.0f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ backward
+__device__ inline float block_sum_256(float v, float* red /* >= 8 floats */) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.0f;
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) r += red[i];
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_vertex_bwd(int V, int F, int nbands, float proj_x, float proj_y,
+             const int32_t* __restrict__ faces, const float* __restrict__ vertices,
+             const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
+             const float* __restrict__ bias,
+             const float* __restrict__ gfacc, const float* __restrict__ g_face_normals,
+             const float* __restrict__ part_bwd,
+             float* __restrict__ g_vertices, float* __restrict__ g_azim, float* __restrict__ g_elev,
+             float* __restrict__ g_dist, float* __restrict__ g_bias, float* __restrict__ g_lights)
+{
+    extern __shared__ float sm[];
+    __shared__ Cam sc;
+    __shared__ float red[8];
+    __shared__ float sacc[12];
+    float* svc = sm;                      // V*3 camera-space positions
+    float* sgv = sm + (size_t)V * 3;      // V*3 gradient w.r.t. camera-space positions
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) camera_setup(azim[b], elev[b], dist[b], bias[b * 2], bias[b * 2 + 1], sc);
+    __syncthreads();
+    const float* vb = vertices + (size_t)b * V * 3;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        float cx, cy, cz;
+        transform_vertex(sc.T, vb[v * 3], vb[v * 3 + 1], vb[v * 3 + 2], cx, cy, cz);
+        svc[v * 3] = cx; svc[v * 3 + 1] = cy; svc[v * 3 + 2] = cz;
+        sgv[v * 3] = 0.0f; sgv[v * 3 + 1] = 0.0f; sgv[v * 3 + 2] = 0.0f;
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const int idx[3] = {faces[f * 3], faces[f * 3 + 1], faces[f * 3 + 2]};
+        float P[3][3];
+        #pragma unroll
+        for (int i = 0; i < 3; ++i) { P[i][0] = svc[idx[i] * 3]; P[i][1] = svc[idx[i] * 3 + 1]; P[i][2] = svc[idx[i] * 3 + 2]; }
+        const float* ga = gfacc + ((size_t)b * F + f) * 9;
+        float G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        // (1) image-plane gradient -> camera space: xi = -px*x/z, yi = -py*y/z
+        #pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float gx = ga[i * 2], gy = ga[i * 2 + 1];
+            const float z = P[i][2];
+            const float den = z * -1.0f;
+            const float xi = (P[i][0] * proj_x) / den, yi = (P[i][1] * proj_y) / den;
+            G[i][0] += gx * proj_x / den;
+            G[i][1] += gy * proj_y / den;
+            G[i][2] += -(gx * xi + gy * yi) / z;
+        }
+        // (2) unit normal gradient (raster path + upstream face_normals gradient)
+        float gu[3] = {ga[6], ga[7], ga[8]};
+        if (g_face_normals) {
+            const float* ge = g_face_normals + ((size_t)b * F + f) * 3;
+            gu[0] += ge[0]; gu[1] += ge[1]; gu[2] += ge[2];
+        }
+        if (gu[0] != 0.0f || gu[1] != 0.0f || gu[2] != 0.0f) {
+            const float e0[3] = {P[1][0] - P[0][0], P[1][1] - P[0][1], P[1][2] - P[0][2]};
+            const float e1[3] = {P[2][0] - P[0][0], P[2][1] - P[0][1], P[2][2] - P[0][2]};
+            const float n[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+            const float L = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            const float Le = L + 1e-10f;
+            float gn[3] = {0, 0, 0};
+            if (L > 0.0f) {
+                const float dot = n[0] * gu[0] + n[1] * gu[1] + n[2] * gu[2];
+                const float k = dot / (L * Le * Le);
+                gn[0] = gu[0] / Le - n[0] * k; gn[1] = gu[1] / Le - n[1] * k; gn[2] = gu[2] / Le - n[2] * k;
+            }
+            // n = e0 x e1 :  g_e0 = e1 x gn ; g_e1 = gn x e0
+            const float ge0[3] = {e1[1] * gn[2] - e1[2] * gn[1], e1[2] * gn[0] - e1[0] * gn[2], e1[0] * gn[1] - e1[1] * gn[0]};
+            const float ge1[3] = {gn[1] * e0[2] - gn[2] * e0[1], gn[2] * e0[0] - gn[0] * e0[2], gn[0] * e0[1] - gn[1] * e0[0]};
+            #pragma unroll
+            for (int k2 = 0; k2 < 3; ++k2) { G[1][k2] += ge0[k2]; G[2][k2] += ge1[k2]; G[0][k2] -= ge0[k2] + ge1[k2]; }
+        }
+        #pragma unroll
+        for (int i = 0; i < 3; ++i)
+            #pragma unroll
+            for (int k2 = 0; k2 < 3; ++k2)
+                if (G[i][k2] != 0.0f) atomicAdd(&sgv[idx[i] * 3 + k2], G[i][k2]);
+    }
+    __syncthreads();
+    // (3) vcam = v*R + t : g_v = g_vcam * R^T ; g_R[i][j] = sum v_i g_j ; g_t[j] = sum g_j
+    float acc[12];
+    #pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] = 0.0f;
+    float* gvb = g_vertices + (size_t)b * V * 3;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        const float g0 = sgv[v * 3], g1 = sgv[v * 3 + 1], g2 = sgv[v * 3 + 2];
+        const float x = vb[v * 3], y = vb[v * 3 + 1], z = vb[v * 3 + 2];
+        gvb[v * 3 + 0] = g0 * sc.T[0] + g1 * sc.T[1] + g2 * sc.T[2];
+        gvb[v * 3 + 1] = g0 * sc.T[3] + g1 * sc.T[4] + g2 * sc.T[5];
+        gvb[v * 3 + 2] = g0 * sc.T[6] + g1 * sc.T[7] + g2 * sc.T[8];
+        acc[0] += x * g0; acc[1] += x * g1; acc[2] += x * g2;
+        acc[3] += y * g0; acc[4] += y * g1; acc[5] += y * g2;
+        acc[6] += z * g0; acc[7] += z * g1; acc[8] += z * g2;
+        acc[9] += g0; acc[10] += g1; acc[11] += g2;
+    }
+    #pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const float r = block_sum_256(acc[i], red);
+        if (threadIdx.x == 0) sacc[i] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float gR[9], gt[3], gcam[3];
+        for (int i = 0; i < 9; ++i) gR[i] = sacc[i];
+        for (int j = 0; j < 3; ++j) gt[j] = sacc[9 + j];
+        // t_j = -sum_i cam_i R_ij
+        for (int i = 0; i < 3; ++i) {
+            gcam[i] = -(gt[0] * sc.T[i * 3 + 0] + gt[1] * sc.T[i * 3 + 1] + gt[2] * sc.T[i * 3 + 2]);
+            for (int j = 0; j < 3; ++j) gR[i * 3 + j] += -sc.cam[i] * gt[j];
+        }
+        float gxa[3], gya[3], gza[3];
+        for (int i = 0; i < 3; ++i) { gxa[i] = gR[i * 3 + 0]; gya[i] = gR[i * 3 + 1]; gza[i] = gR[i * 3 + 2]; }
+        // ya = za x xa : g_za += xa x g_ya ; g_xa += g_ya x za
+        gza[0] += sc.xa[1] * gya[2] - sc.xa[2] * gya[1];
+        gza[1] += sc.xa[2] * gya[0] - sc.xa[0] * gya[2];
+        gza[2] += sc.xa[0] * gya[1] - sc.xa[1] * gya[0];
+        gxa[0] += gya[1] * sc.za[2] - gya[2] * sc.za[1];
+        gxa[1] += gya[2] * sc.za[0] - gya[0] * sc.za[2];
+        gxa[2] += gya[0] * sc.za[1] - gya[1] * sc.za[0];
+        // xa = xr/|xr|
+        const float dx = sc.xa[0] * gxa[0] + sc.xa[1] * gxa[1] + sc.xa[2] * gxa[2];
+        float gxr[3];
+        for (int i = 0; i < 3; ++i) gxr[i] = (gxa[i] - sc.xa[i] * dx) / sc.xl;
+        // xr = (za_z, 0, -za_x)
+        gza[2] += gxr[0];
+        gza[0] += -gxr[2];
+        // za = zr/|zr|
+        const float dz = sc.za[0] * gza[0] + sc.za[1] * gza[1] + sc.za[2] * gza[2];
+        float gzr[3];
+        for (int i = 0; i < 3; ++i) gzr[i] = (gza[i] - sc.za[i] * dz) / sc.zl;
+        for (int i = 0; i < 3; ++i) gcam[i] += gzr[i];
+        g_bias[b * 2] = -gzr[0];
+        g_bias[b * 2 + 1] = -gzr[1];
+        const float k = 3.14159265358979323846f / 180.0f;
+        g_dist[b] = gcam[0] * sc.ce * sc.sa + gcam[1] * sc.se + gcam[2] * sc.ce * sc.ca;
+        g_elev[b] = k * (gcam[0] * (-sc.d * sc.se * sc.sa) + gcam[1] * (sc.d * sc.ce) + gcam[2] * (-sc.d * sc.se * sc.ca));
+        g_azim[b] = k * (gcam[0] * (sc.d * sc.ce * sc.ca) + gcam[2] * (-sc.d * sc.ce * sc.sa));
+    }
+    // (4) light gradient: deterministic sum of the per-CTA partials of the raster backward
+    if (threadIdx.x < 9) {
+        float s = 0.0f;
+        for (int k = 0; k < nbands; ++k) s += part_bwd[((size_t)b * nbands + k) * 12 + 1 + threadIdx.x];
+        g_lights[b * 9 + threadIdx.x] = s;
+    }
+}
+
+__global__ void k_export_faces(int V, int F, float multiplier, const int32_t* __restrict__ faces,
+                               const float* __restrict__ frec, const float* __restrict__ vimg,
+                               float* fvi, float* fvz, float* fnz, int total)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int b = i / F, f = i - b * F;
+    const float* r = frec + (size_t)i * MM_REC_FLOATS;
+    if (fvi) {
+        for (int c = 0; c < 3; ++c) {
+            const int v = faces[f * 3 + c];
+            fvi[(size_t)i * 6 + c * 2] = vimg[((size_t)b * V + v) * 2];
+            fvi[(size_t)i * 6 + c * 2 + 1] = vimg[((size_t)b * V + v) * 2 + 1];
+        }
+    }
+    if (fvz) { fvz[(size_t)i * 3] = r[6]; fvz[(size_t)i * 3 + 1] = r[7]; fvz[(size_t)i * 3 + 2] = r[8]; }
+    if (fnz) fnz[i] = r[11];
+}
+
+}  // namespace
+
+void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
+                          const float* dist, const float* bias, float* frec, float* vimg, float* face_normals,
+                          float* gfacc_zero, cudaStream_t s)
+{
+    const size_t smem = (16 + (size_t)c->V * 5) * sizeof(float);
+    k_vertex_fwd<<<B, 256, smem, s>>>(c->V, c->F, c->proj_x, c->proj_y, c->multiplier, c->d_faces, vertices,
+                                      azim, elev, dist, bias, frec, vimg, face_normals, gfacc_zero);
+}
+
+void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
+                          const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,
+                          const float* part_bwd, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
+                          float* g_bias, float* g_lights, cudaStream_t s)
+{
+    const size_t smem = ((size_t)c->V * 6) * sizeof(float);
+    k_vertex_bwd<<<B, 256, smem, s>>>(c->V, c->F, c->nbands, c->proj_x, c->proj_y, c->d_faces, vertices, azim, elev,
+                                      dist, bias, gfacc, g_face_normals, part_bwd, g_vertices, g_azim, g_elev,
+                                      g_dist, g_bias, g_lights);
+}
+
+void mm_launch_export_faces(const mm_ctx* c, int B, const float* frec, const float* vimg, float* fvi, float* fvz,
+                            float* fnz, cudaStream_t s)
+{
+    const int total = B * c->F;
+    k_export_faces<<<(total + 255) / 256, 256, 0, s>>>(c->V, c->F, c->multiplier, c->d_faces, frec, vimg, fvi, fvz,
+                                                       fnz, total);
+}
+
+size_t mm_vertex_smem_fwd(int V) { return (16 + (size_t)V * 5) * sizeof(float); }
+size_t mm_vertex_smem_bwd(int V) { return ((size_t)V * 6) * sizeof(float); }
+void mm_vertex_set_smem(size_t fwd, size_t bwd) {
+    cudaFuncSetAttribute(k_vertex_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd);
+    cudaFuncSetAttribute(k_vertex_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd);
+}

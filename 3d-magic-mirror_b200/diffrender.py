@@ -1,0 +1,386 @@
+"""DiffRender -- drop-in for the reference's `networks.DiffRender`
+(/root/reference/networks.py:164-491), backed by libmagicmirror.so (sm_100a CUDA)
+through the C ABI in include/magicmirror.h.
+
+Same constructor, attributes and method signatures as the reference:
+    DiffRender(mesh_name, image_size, ratio=1, init_ellipsoid=1, image_weight=0.1,
+               lambda_lpl=0.1, lambda_flat=0.001)                       networks.py:165
+    .render(no_mask=False, **attributes) -> (rgbs[B,4,H,W], attributes)   networks.py:258
+    .recon_data(pred_data, gt_data, no_mask=False, contour=0) -> 0-d      networks.py:364
+    .recon_att / .recon_flip / .calc_reg_* (mesh regularisers)           networks.py:326-491
+`render` and `recon_data` are the hot path and run entirely in the CUDA library
+(one vertex-stage kernel + one raster kernel forward; raster-backward +
+vertex-backward kernels for autograd).  There is no CPU / PyTorch fallback: CPU
+tensors raise.  `render_compare` additionally exposes the fused
+render -> recon_data -> backward call (mm_render_compare_fwd_bwd).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import mesh as _mesh
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _f32c(t):
+    """float32 + contiguous, no copy when already so."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _CtxHandle(object):
+    """Owns one mm_ctx (one per DiffRender per device)."""
+
+    def __init__(self, dr, device_index):
+        L = _lib.lib()
+        faces_i32 = dr.faces.to(torch.int32).contiguous().cpu()
+        uvs = dr.face_uvs.reshape(-1).to(torch.float32).contiguous().cpu()
+        handle = ctypes.c_void_p(0)
+        H, W = dr.height, dr.image_size
+        with torch.cuda.device(device_index):
+            rc = L.mm_ctx_create(ctypes.byref(handle), device_index, dr.num_vertices, dr.num_faces,
+                                 ctypes.c_void_p(faces_i32.data_ptr()), ctypes.c_void_p(uvs.data_ptr()),
+                                 H, W, float(dr.cam_proj[0, 0]), float(dr.cam_proj[1, 0]),
+                                 float(dr.sigmainv), float(dr.boxlen), int(dr.knum), float(dr.multiplier),
+                                 float(dr.eps))
+        _lib.check(rc, "mm_ctx_create")
+        self.handle = handle
+        self.device_index = device_index
+
+    def workspace(self, B):
+        n = _lib.lib().mm_workspace_bytes(self.handle, B)
+        return torch.empty(n, dtype=torch.uint8, device=torch.device("cuda", self.device_index))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().mm_ctx_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise _lib.MagicMirrorError(
+            "DiffRender.%s: tensor '%s' is on %s; the render path is CUDA (sm_100a) only and has no CPU fallback"
+            % ("render", name, t.device))
+
+
+class _RenderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dr, no_mask, want_face_idx, vertices, azim, elev, dist, biases, textures, lights, bg):
+        for n, t in (("vertices", vertices), ("azimuths", azim), ("elevations", elev), ("distances", dist),
+                     ("biases", biases), ("textures", textures), ("lights", lights)):
+            _require_cuda(t, n)
+        dev = vertices.device
+        B = azim.shape[0]
+        H, W, V, F = dr.height, dr.image_size, dr.num_vertices, dr.num_faces
+        vertices, azim, elev, dist = _f32c(vertices), _f32c(azim).reshape(-1), _f32c(elev).reshape(-1), _f32c(dist).reshape(-1)
+        biases, textures, lights = _f32c(biases), _f32c(textures), _f32c(lights)
+        if vertices.shape != (B, V, 3):
+            raise ValueError("vertices must be (B,%d,3), got %s" % (V, tuple(vertices.shape)))
+        if textures.dim() != 4 or textures.shape[0] != B or textures.shape[1] != 3:
+            raise ValueError("textures must be (B,3,Ht,Wt), got %s" % (tuple(textures.shape),))
+        if lights.shape != (B, 9) or biases.shape != (B, 2):
+            raise ValueError("lights must be (B,9) and biases (B,2)")
+        if no_mask:
+            if bg is None:
+                raise TypeError("render(no_mask=True) needs attributes['bg'] (B,3,H,W)")
+            _require_cuda(bg, "bg")
+            bg = _f32c(bg)
+            if bg.shape != (B, 3, H, W):
+                raise ValueError("bg must be (B,3,%d,%d), got %s" % (H, W, tuple(bg.shape)))
+        else:
+            bg = None
+        Ht, Wt = textures.shape[2], textures.shape[3]
+        h = dr._ctx(dev)
+        with torch.cuda.device(dev):
+            rgba = torch.empty(B, 4, H, W, device=dev, dtype=torch.float32)
+            fn = torch.empty(B, F, 3, device=dev, dtype=torch.float32)
+            imn = torch.empty(B, H, W, 3, device=dev, dtype=torch.float32)
+            fidx = torch.empty(B, H, W, device=dev, dtype=torch.int32) if want_face_idx else None
+            ws = h.workspace(B)
+            rc = _lib.lib().mm_render_forward(h.handle, B, _ptr(vertices), _ptr(azim), _ptr(elev), _ptr(dist),
+                                              _ptr(biases), _ptr(textures), Ht, Wt, _ptr(lights), _ptr(bg),
+                                              1 if no_mask else 0, _ptr(rgba), _ptr(fn), _ptr(imn), _ptr(fidx),
+                                              _ptr(ws), _stream())
+        _lib.check(rc, "mm_render_forward")
+        ctx.dr, ctx.no_mask, ctx.h = dr, bool(no_mask), h
+        ctx.has_bg = bg is not None
+        ctx.save_for_backward(vertices, azim, elev, dist, biases, textures, lights,
+                              bg if bg is not None else torch.empty(0, device=dev), rgba, ws)
+        ctx.mark_non_differentiable(imn)
+        if fidx is None:
+            fidx = torch.empty(0, device=dev, dtype=torch.int32)
+        ctx.mark_non_differentiable(fidx)
+        return rgba, fn, imn, fidx
+
+    @staticmethod
+    def backward(ctx, g_rgba, g_fn, _g_imn, _g_fidx):
+        vertices, azim, elev, dist, biases, textures, lights, bg, rgba, ws = ctx.saved_tensors
+        dr, h = ctx.dr, ctx.h
+        dev = vertices.device
+        B = azim.shape[0]
+        bg_t = bg if ctx.has_bg else None
+        Ht, Wt = textures.shape[2], textures.shape[3]
+        if g_rgba is None:
+            g_rgba = torch.zeros_like(rgba)
+        g_rgba = _f32c(g_rgba)
+        g_fn = _f32c(g_fn) if g_fn is not None else None
+        with torch.cuda.device(dev):
+            g_v = torch.empty_like(vertices)
+            g_az, g_el, g_di = torch.empty_like(azim), torch.empty_like(elev), torch.empty_like(dist)
+            g_bi, g_tex, g_li = torch.empty_like(biases), torch.empty_like(textures), torch.empty_like(lights)
+            g_bg = torch.empty_like(bg_t) if bg_t is not None else None
+            rc = _lib.lib().mm_render_backward(h.handle, B, _ptr(vertices), _ptr(azim), _ptr(elev), _ptr(dist),
+                                               _ptr(biases), _ptr(textures), Ht, Wt, _ptr(lights), _ptr(bg_t),
+                                               1 if ctx.no_mask else 0, _ptr(rgba), _ptr(g_rgba), _ptr(g_fn),
+                                               _ptr(g_v), _ptr(g_az), _ptr(g_el), _ptr(g_di), _ptr(g_bi),
+                                               _ptr(g_tex), _ptr(g_li), _ptr(g_bg), _ptr(ws), _stream())
+        _lib.check(rc, "mm_render_backward")
+        return None, None, None, g_v, g_az, g_el, g_di, g_bi, g_tex, g_li, g_bg
+
+
+class _ReconFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dr, image_weight, contour, pred, gt):
+        _require_cuda(pred, "pred_data")
+        _require_cuda(gt, "gt_data")
+        pred, gt = _f32c(pred), _f32c(gt)
+        B = pred.shape[0]
+        if pred.shape != (B, 4, dr.height, dr.image_size) or gt.shape != pred.shape:
+            raise ValueError("recon_data expects (B,4,%d,%d) tensors, got %s and %s"
+                             % (dr.height, dr.image_size, tuple(pred.shape), tuple(gt.shape)))
+        dev = pred.device
+        h = dr._ctx(dev)
+        with torch.cuda.device(dev):
+            loss = torch.empty(4, device=dev, dtype=torch.float32)
+            ws = h.workspace(B)
+            rc = _lib.lib().mm_recon_data_forward(h.handle, B, _ptr(pred), _ptr(gt), float(image_weight),
+                                                  float(contour), _ptr(loss), _ptr(None), _ptr(ws), _stream())
+        _lib.check(rc, "mm_recon_data_forward")
+        ctx.dr, ctx.h, ctx.iw, ctx.contour = dr, h, float(image_weight), float(contour)
+        ctx.save_for_backward(pred, gt, ws)
+        ctx.mark_non_differentiable(loss)
+        return loss[0].clone(), loss
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_parts):
+        pred, gt, ws = ctx.saved_tensors
+        B = pred.shape[0]
+        dev = pred.device
+        with torch.cuda.device(dev):
+            g_pred = torch.empty_like(pred)
+            rc = _lib.lib().mm_recon_data_backward(ctx.h.handle, B, _ptr(pred), _ptr(gt), ctx.iw, ctx.contour, 1.0,
+                                                   _ptr(g_pred), _ptr(ws), _stream())
+        _lib.check(rc, "mm_recon_data_backward")
+        return None, None, None, g_pred * g_loss, None
+
+
+class DiffRender(object):
+    # kaolin dibr_rasterization defaults (call site networks.py:297-299 passes none of them)
+    sigmainv = 7000.0
+    boxlen = 0.02
+    knum = 30
+    multiplier = 1000.0
+    eps = 1e-8
+
+    def __init__(self, mesh_name, image_size, ratio=1, init_ellipsoid=1, image_weight=0.1, lambda_lpl=0.1,
+                 lambda_flat=0.001):
+        self.image_size = image_size
+        self.image_weight = image_weight
+        self.lambda_lpl = lambda_lpl
+        self.lambda_flat = lambda_flat
+        self.ratio = ratio
+        self.height = int(round(ratio * image_size))          # networks.py:298
+        # networks.py:172-174: fovy = 2*atan(1/2.5); kaolin generate_perspective_projection(fovy, ratio=1/ratio)
+        tanfov = math.tan(np.arctan(1.0 / 2.5) * 2 / 2.0)
+        self.cam_proj = torch.tensor([[1.0 / ((1 / ratio) * tanfov)], [1.0 / tanfov], [-1]], dtype=torch.float)
+
+        tm = mesh_name if isinstance(mesh_name, _mesh.TemplateMesh) else _mesh.load_obj(mesh_name)
+        self.uvs = tm.uvs
+        self.faces = tm.faces
+        self.vertices_init = _mesh.normalise_template(tm.vertices, init_ellipsoid)
+        self.face_uvs = tm.uvs[tm.face_uvs_idx].unsqueeze(0).contiguous()          # (1,F,3,2)
+        self.num_faces = self.faces.shape[0]
+        self.num_vertices = self.vertices_init.shape[0]
+        self.flip_index = _mesh.mirror_index(self.vertices_init)
+        self.edges, self.edge2faces = _mesh.edge_tables(self.faces)
+        self.vertices_laplacian_matrix = _mesh.uniform_laplacian(self.num_vertices, self.faces)
+        sign = torch.sign(self.vertices_init[:, 2])
+        self.sign_init = sign.cuda() if torch.cuda.is_available() else sign      # networks.py:252
+        self.print_contour = False      # the reference prints loss_contour on every call (a device sync)
+        self._ctxs = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _ctx(self, device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        h = self._ctxs.get(idx)
+        if h is None:
+            h = _CtxHandle(self, idx)
+            self._ctxs[idx] = h
+        return h
+
+    # ------------------------------------------------------------------ hot path
+    def render(self, no_mask=False, **attributes):
+        """networks.py:258-324.  Required keys: azimuths, elevations, distances (B,), biases (B,2),
+        bg (B,3,H,W)|None, vertices (B,V,3), textures (B,3,Ht,Wt), lights (B,9)."""
+        azimuths = attributes['azimuths']
+        elevations = attributes['elevations']
+        distances = attributes['distances']
+        biases = attributes['biases']
+        bg = attributes['bg']
+        vertices = attributes['vertices']
+        textures = attributes['textures']
+        lights = attributes['lights']
+        want_idx = bool(attributes.get('_want_face_idx', False))
+        rgbs, face_normals, imnormal, face_idx = _RenderFn.apply(
+            self, bool(no_mask), want_idx, vertices, azimuths, elevations, distances, biases, textures, lights,
+            bg if no_mask else None)
+        attributes['face_normals'] = face_normals
+        attributes['imnormal'] = imnormal          # visualisation only
+        if want_idx:
+            attributes['face_idx'] = face_idx
+        return rgbs, attributes
+
+    def recon_data(self, pred_data, gt_data, no_mask=False, contour=0):
+        """networks.py:364-390: image_weight * masked-L1 + (1 - soft IoU) + contour * contour-MSE."""
+        loss, parts = _ReconFn.apply(self, self.image_weight, contour, pred_data, gt_data)
+        if contour > 0 and self.print_contour:
+            print('loss_contour: %f' % parts[3].item())
+        return loss
+
+    def render_compare(self, gt_data, no_mask=False, contour=0, loss_scale=1.0, g_rgba_extra=None,
+                       g_face_normals=None, **attributes):
+        """Fused render -> recon_data -> backward (mm_render_compare_fwd_bwd): one call returns the loss
+        parts, the rendered RGBA and d(loss_scale*loss_data [+ <g_rgba_extra, rgba>])/d(every attribute).
+        Equivalent to trainer.py:276 + :441 + the autograd walk of :509 for the data term."""
+        A = attributes
+        dev = A['vertices'].device
+        for n in ('vertices', 'azimuths', 'elevations', 'distances', 'biases', 'textures', 'lights'):
+            _require_cuda(A[n], n)
+        vertices, textures, lights, biases = _f32c(A['vertices']), _f32c(A['textures']), _f32c(A['lights']), _f32c(A['biases'])
+        azim, elev, dist = _f32c(A['azimuths']).reshape(-1), _f32c(A['elevations']).reshape(-1), _f32c(A['distances']).reshape(-1)
+        bg = _f32c(A['bg']) if no_mask else None
+        gt = _f32c(gt_data)
+        B = azim.shape[0]
+        H, W, F = self.height, self.image_size, self.num_faces
+        Ht, Wt = textures.shape[2], textures.shape[3]
+        h = self._ctx(dev)
+        with torch.cuda.device(dev):
+            out = {
+                'rgba': torch.empty(B, 4, H, W, device=dev), 'face_normals': torch.empty(B, F, 3, device=dev),
+                'loss': torch.empty(4, device=dev),
+                'g_vertices': torch.empty_like(vertices), 'g_azimuths': torch.empty_like(azim),
+                'g_elevations': torch.empty_like(elev), 'g_distances': torch.empty_like(dist),
+                'g_biases': torch.empty_like(biases), 'g_textures': torch.empty_like(textures),
+                'g_lights': torch.empty_like(lights), 'g_bg': torch.empty_like(bg) if bg is not None else None,
+            }
+            ws = h.workspace(B)
+            rc = _lib.lib().mm_render_compare_fwd_bwd(
+                h.handle, B, _ptr(vertices), _ptr(azim), _ptr(elev), _ptr(dist), _ptr(biases), _ptr(textures), Ht, Wt,
+                _ptr(lights), _ptr(bg), 1 if no_mask else 0, _ptr(gt), float(self.image_weight), float(contour),
+                float(loss_scale), _ptr(_f32c(g_rgba_extra) if g_rgba_extra is not None else None),
+                _ptr(_f32c(g_face_normals) if g_face_normals is not None else None),
+                _ptr(out['rgba']), _ptr(out['face_normals']), _ptr(out['loss']),
+                _ptr(out['g_vertices']), _ptr(out['g_azimuths']), _ptr(out['g_elevations']), _ptr(out['g_distances']),
+                _ptr(out['g_biases']), _ptr(out['g_textures']), _ptr(out['g_lights']), _ptr(out['g_bg']),
+                _ptr(ws), _stream())
+        _lib.check(rc, "mm_render_compare_fwd_bwd")
+        out['_workspace'] = ws
+        return out
+
+    # ------------------------------------------------------------------ regularisers (networks.py:326-491)
+    def recon_att(self, pred_att, target_att, L1=False, chamfer=False, azim=1):
+        """networks.py:326-362: attribute cycle losses (camera / shape / texture / light / bias)."""
+        if chamfer:
+            raise NotImplementedError("chamfer=True needs pytorch3d.loss.chamfer_distance (off the hot path)")
+
+        def on_circle(deg):
+            rad = deg * math.pi / 180.0
+            return torch.stack([torch.cos(rad), torch.sin(rad)], 1)
+
+        def dist_fn(a, b):
+            return torch.abs(a - b).mean() if L1 else torch.pow(a - b, 2).mean()
+
+        loss_azim = dist_fn(on_circle(pred_att['azimuths']), on_circle(target_att['azimuths']))
+        loss_elev = dist_fn(on_circle(pred_att['elevations']), on_circle(target_att['elevations']))
+        loss_dist = dist_fn(pred_att['distances'], target_att['distances'])
+        loss_bias = dist_fn(pred_att['biases'], target_att['biases'])
+        loss_cam = azim * loss_azim + loss_elev + loss_dist
+        loss_shape = dist_fn(pred_att['vertices'], target_att['vertices'])
+        loss_texture = dist_fn(pred_att['textures'], target_att['textures'])
+        loss_light = 0.1 * dist_fn(pred_att['lights'], target_att['lights'])
+        return loss_cam, loss_shape, loss_texture, loss_light, loss_bias
+
+    def recon_flip(self, att, L1):
+        """networks.py:392-410: z-mirror symmetry of delta_vertices, masked where the depth sign flipped."""
+        Na = att['delta_vertices']
+        idx = self.flip_index.to(Na.device)
+        Nf = Na.index_select(1, idx)
+        Nf = Nf * Nf.new_tensor([1.0, 1.0, -1.0])
+        diff = Na - Nf
+        loss_norm = torch.abs(diff) if L1 else diff.norm(dim=2)
+        mask_a = torch.relu(torch.sign(Na[:, :, 2]) * self.sign_init.to(Na.device))
+        mask_f = mask_a.index_select(1, idx)
+        if L1:
+            # reference broadcasting: (B,V,3) * (B,V) is only valid when V == 3; mirror its intent per vertex
+            return torch.mean(loss_norm * mask_f.unsqueeze(-1))
+        return torch.mean(loss_norm * mask_f)
+
+    def calc_reg_loss(self, att):
+        """networks.py:412-451: lambda_lpl * uniform-Laplacian energy + lambda_flat * dihedral flatness."""
+        delta = att['delta_vertices']
+        dev = delta.device
+        lap = self.vertices_laplacian_matrix.to(dev)
+        e2f = self.edge2faces.to(dev)
+        fn = att['face_normals']
+        nb_vertices = delta.shape[1]
+        loss_laplacian = torch.mean(torch.matmul(lap, delta) ** 2) * nb_vertices * 3
+        cos = torch.sum(fn[:, e2f[:, 0]] * fn[:, e2f[:, 1]], dim=2)
+        loss_flat = torch.mean((cos - 1) ** 2) * e2f.shape[0]
+        return self.lambda_lpl * loss_laplacian + self.lambda_flat * loss_flat
+
+    def calc_reg_edge(self, pred):
+        """networks.py:453-461: 0.1 * mean_b || edge_len - mean(edge_len) ||_2."""
+        e = self.edges.to(pred.device)
+        length = torch.norm(pred[:, e[:, 0]] - pred[:, e[:, 1]], p=2, dim=2)
+        bias = length - torch.mean(length, dim=1, keepdim=True)
+        return 0.1 * torch.mean(torch.norm(bias, p=2, dim=1))
+
+    def calc_reg_depth(self, pred):
+        """networks.py:463-466."""
+        return torch.mean(pred[:, :, 2] ** 2)
+
+    def _depth_weighted(self, pred, weight, eps):
+        s = self.sign_init.to(pred.device)
+        z = pred[:, :, 2]
+        return torch.mean((s >= 0) * (z - eps) ** 2 * weight + (s < 0) * (z + eps) ** 2 * weight)
+
+    def calc_reg_depthR(self, pred, temp=2, eps=0.001):
+        """networks.py:468-475: depth^2 weighted by exp(temp * r^2), sign-preserving."""
+        x = pred[:, :, 0].detach()
+        y = pred[:, :, 1].detach()
+        return self._depth_weighted(pred, torch.exp(temp * (x ** 2 + (y / self.ratio) ** 2)), eps)
+
+    def calc_reg_depthC(self, pred, eps=0.001):
+        """networks.py:477-485: depth^2 weighted by r^2, sign-preserving."""
+        x = pred[:, :, 0].detach()
+        y = pred[:, :, 1].detach()
+        return self._depth_weighted(pred, x ** 2 + (y / self.ratio) ** 2, eps)
+
+    def calc_reg_deform(self, pred):
+        """networks.py:487-491: mean per-vertex displacement norm."""
+        b = pred.shape[0]
+        return torch.mean(torch.norm(pred.reshape(-1, pred.size(2)), p=2, dim=1).reshape(b, -1))

@@ -1,0 +1,131 @@
+/*
+ * magicmirror.h -- C ABI of libmagicmirror.so, the sm_100a differentiable
+ * render-and-compare hot path of layumi/3D-Magic-Mirror.
+ *
+ * The reference has no FFI of its own for this path: it reaches NVIDIA Kaolin's
+ * torch C++ extension from Python.  Each entry point below names the reference
+ * call(s) it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - every tensor argument is a DEVICE pointer to a contiguous fp32 array unless
+ *     stated otherwise; the caller owns all buffers, including `workspace`.
+ *   - the library owns only `mm_ctx` (mesh topology, per-face UVs, raster params).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     never synchronises and never allocates device memory.
+ *   - return value 0 = ok, < 0 = error (MM_E_*); mm_last_error() returns a
+ *     thread-local message for the last failing call.
+ *   - a ctx is bound to one device; calls on one ctx must be serialised by the caller.
+ *   - gradient outputs are OVERWRITTEN (the library zero-fills), never accumulated.
+ *   - `workspace` written by a forward call must be passed unmodified to the
+ *     matching backward call.
+ */
+#ifndef MAGICMIRROR_H_
+#define MAGICMIRROR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MM_ABI_VERSION 1
+
+#define MM_OK            0
+#define MM_E_INVALID    -1   /* bad argument (NULL pointer, non-positive size, ...) */
+#define MM_E_CUDA       -2   /* a CUDA runtime call failed; message has the cudaError string */
+#define MM_E_UNSUPPORTED -3  /* configuration outside what the kernels support */
+
+typedef struct mm_ctx mm_ctx;
+
+int         mm_abi_version(void);
+const char* mm_last_error(void);
+
+/* Replaces DiffRender.__init__'s device-side state (networks.py:165-256: faces,
+ * face_uvs, cam_proj = generate_perspective_projection(fovy, 1/ratio) -> proj_x =
+ * 2.5*ratio, proj_y = 2.5) and the defaults of kaolin dibr_rasterization
+ * (sigmainv=7000, boxlen=0.02, knum=30, multiplier=1000, eps=1e-8; call site
+ * networks.py:297-299).  faces_host / face_uvs_host are HOST pointers. */
+int mm_ctx_create(mm_ctx** out, int device, int V, int F,
+                  const int32_t* faces_host /* F*3 */, const float* face_uvs_host /* F*3*2 */,
+                  int H, int W, float proj_x, float proj_y,
+                  float sigmainv, float boxlen, int knum, float multiplier, float eps);
+int mm_ctx_destroy(mm_ctx* ctx);
+
+/* Bytes of caller-owned scratch needed by any call on `ctx` with batch B. */
+size_t mm_workspace_bytes(const mm_ctx* ctx, int B);
+
+/* Replaces DiffRender.render (networks.py:258-324): camera_position_from_spherical_angles
+ * + generate_transformation_matrix (smr_utils.py:257-311), kaolin prepare_vertices
+ * (:284), face_normals (:289), dibr_rasterization (:297), texture_mapping (:305),
+ * spherical_harmonic_lighting (:306), composite + clamp + pack (:307-317).
+ *   rgba          [B,4,H,W]   out
+ *   face_normals  [B,F,3]     out  (attributes['face_normals'], networks.py:319)
+ *   imnormal      [B,H,W,3]   out, may be NULL (attributes['imnormal'], :320)
+ *   face_idx      [B,H,W]     out int32, may be NULL (-1 = no face) */
+int mm_render_forward(mm_ctx* ctx, int B,
+                      const float* vertices /* B,V,3 */, const float* azim /* B */,
+                      const float* elev /* B */, const float* dist /* B */, const float* bias /* B,2 */,
+                      const float* tex /* B,3,Ht,Wt */, int Ht, int Wt,
+                      const float* lights /* B,9 */, const float* bg /* B,3,H,W or NULL */, int no_mask,
+                      float* rgba, float* face_normals, float* imnormal, int32_t* face_idx,
+                      void* workspace, void* stream);
+
+/* Backward of mm_render_forward (replaces autograd through the same Kaolin calls:
+ * rasterize_backward + dibr_soft_mask_backward + grid_sample backward + ...).
+ *   g_rgba          [B,4,H,W]  upstream gradient
+ *   g_face_normals  [B,F,3]    upstream gradient of the face_normals output, may be NULL
+ * All g_* outputs are overwritten; g_bg may be NULL (and must be when bg is NULL). */
+int mm_render_backward(mm_ctx* ctx, int B,
+                       const float* vertices, const float* azim, const float* elev, const float* dist,
+                       const float* bias, const float* tex, int Ht, int Wt, const float* lights,
+                       const float* bg, int no_mask,
+                       const float* rgba /* forward output */,
+                       const float* g_rgba, const float* g_face_normals,
+                       float* g_vertices /* B,V,3 */, float* g_azim, float* g_elev, float* g_dist,
+                       float* g_bias /* B,2 */, float* g_tex /* B,3,Ht,Wt */, float* g_lights /* B,9 */,
+                       float* g_bg /* B,3,H,W or NULL */,
+                       void* workspace, void* stream);
+
+/* Replaces DiffRender.recon_data (networks.py:364-390) incl. kaolin mask_iou (:377).
+ *   loss      [4] out: data (= image_weight*image + mask + contour*contour_term), image, mask(1-IoU), contour_term
+ *   iou_sums  [B,2] out: N_b = sum(p*g), D_b = sum(p+g-p*g); may be NULL */
+int mm_recon_data_forward(mm_ctx* ctx, int B, const float* pred /* B,4,H,W */, const float* gt /* B,4,H,W */,
+                          float image_weight, float contour,
+                          float* loss, float* iou_sums, void* workspace, void* stream);
+
+/* d(loss_scale * loss_data)/d(pred) -> g_pred [B,4,H,W] (overwritten). */
+int mm_recon_data_backward(mm_ctx* ctx, int B, const float* pred, const float* gt,
+                           float image_weight, float contour, float loss_scale,
+                           float* g_pred, void* workspace, void* stream);
+
+/* Fused benchmark path: render -> recon_data -> backward of (loss_scale*loss_data +
+ * <g_rgba_extra, rgba>) in one call; the loss gradient is formed in-kernel and
+ * never materialised.  Replaces trainer.py:276 + :441 + the autograd walk at :509.
+ *   gt            [B,4,H,W]
+ *   g_rgba_extra  [B,4,H,W] or NULL  (upstream gradient from another consumer, e.g. the GAN)
+ *   g_face_normals [B,F,3] or NULL   (upstream gradient of face_normals, e.g. from calc_reg_loss, networks.py:422)
+ *   rgba          [B,4,H,W] out (required: the backward pass re-reads the silhouette)
+ *   loss          [4] out, as mm_recon_data_forward */
+int mm_render_compare_fwd_bwd(mm_ctx* ctx, int B,
+                              const float* vertices, const float* azim, const float* elev, const float* dist,
+                              const float* bias, const float* tex, int Ht, int Wt, const float* lights,
+                              const float* bg, int no_mask,
+                              const float* gt, float image_weight, float contour, float loss_scale,
+                              const float* g_rgba_extra, const float* g_face_normals,
+                              float* rgba, float* face_normals, float* loss,
+                              float* g_vertices, float* g_azim, float* g_elev, float* g_dist, float* g_bias,
+                              float* g_tex, float* g_lights, float* g_bg,
+                              void* workspace, void* stream);
+
+/* Test hook: copies the vertex-stage products of the last forward on `workspace`
+ * (what kaolin prepare_vertices returns, networks.py:284-287) so that the oracle's
+ * rasteriser can be run on bit-identical inputs.  Any pointer may be NULL.
+ *   fvi [B,F,3,2] image-plane xy (unscaled), fvz [B,F,3] camera z, fnz [B,F] unit-normal z */
+int mm_debug_export_faces(mm_ctx* ctx, int B, const void* workspace,
+                          float* fvi, float* fvz, float* fnz, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGICMIRROR_H_ */

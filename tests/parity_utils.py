@@ -1,0 +1,168 @@
+"""Shared helpers for the parity tests, smoke() and bench.py's checker leg.
+
+`make_attributes` draws the seeded synthetic inputs of SURVEY.md section 8(d);
+`run_parity_case` runs the CUDA product (through the Python DiffRender -> C ABI)
+and the CPU oracle (oracle/ref_pipeline.py) on the same inputs and returns error
+figures.  The oracle is only ever the checker here.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+if os.path.join(ROOT, "oracle") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def load_mm():
+    import __graft_entry__ as g
+    return g.load_package()
+
+
+def get_mesh(mm, name):
+    """'icosphere' / 'icosphere2' (procedural) or a golden template name (tests/golden/templates/<name>.npz)."""
+    if name == "icosphere":
+        return mm.icosphere(3)
+    if name == "icosphere2":
+        return mm.icosphere(4)
+    path = os.path.join(GOLDEN, "templates", name + ".npz")
+    z = np.load(path)
+    return mm.TemplateMesh(torch.from_numpy(z["vertices"]), torch.from_numpy(z["faces"]).long(),
+                           torch.from_numpy(z["uvs"]), torch.from_numpy(z["face_uvs_idx"]).long())
+
+
+def make_attributes(vertices_init, B, H, W, seed, Ht=None, Wt=None, elev_range=(0.0, 30.0), dist_range=(2.0, 7.0),
+                    bias_range=0.3, deform=0.05):
+    """SURVEY 8(d) cfg-2 recipe (train.py:123-127 ranges), CPU tensors, seeded."""
+    g = torch.Generator().manual_seed(seed)
+    V = vertices_init.shape[0]
+    Ht = 2 * H if Ht is None else Ht
+    Wt = W if Wt is None else Wt
+    u = lambda *s: torch.rand(*s, generator=g)          # noqa: E731
+    n = lambda *s: torch.randn(*s, generator=g)         # noqa: E731
+    delta = deform * torch.tanh(n(B, V, 3))
+    delta = delta - delta.mean(dim=1, keepdim=True)
+    lights = torch.tensor([3.0] + [0.0] * 8) + torch.tensor([0.5] + [0.1] * 8) * torch.tanh(n(B, 9))
+    A = {
+        'azimuths': u(B) * 360.0 - 180.0,
+        'elevations': elev_range[0] + u(B) * (elev_range[1] - elev_range[0]),
+        'distances': dist_range[0] + u(B) * (dist_range[1] - dist_range[0]),
+        'biases': (u(B, 2) * 2 - 1) * bias_range,
+        'vertices': vertices_init[None] + delta,
+        'delta_vertices': delta,
+        'textures': u(B, 3, Ht, Wt),
+        'lights': lights,
+        'bg': u(B, 3, H, W),
+    }
+    return A
+
+
+def to_device(A, device, requires_grad=False):
+    out = {}
+    for k, v in A.items():
+        t = v.to(device).clone()
+        if requires_grad and k != 'delta_vertices':
+            t.requires_grad_(True)
+        out[k] = t
+    return out
+
+
+GRAD_KEYS = ['vertices', 'azimuths', 'elevations', 'distances', 'biases', 'textures', 'lights', 'bg']
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|) -- the 'relative to the tensor's scale' figure used for every gradient."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    scale = b.abs().max().item()
+    return (a - b).abs().max().item() / (scale if scale > 0 else 1.0)
+
+
+def oracle_for(dr, dtype=torch.float32):
+    import ref_pipeline
+    return ref_pipeline.OracleRender(dr.faces.cpu().numpy(), dr.face_uvs.cpu().numpy(), dr.image_size, dr.ratio,
+                                     dr.image_weight, dtype=dtype)
+
+
+def run_parity_case(mm, mesh="icosphere", B=2, image_size=32, ratio=1, no_mask=True, contour=0.1, seed=0,
+                    device="cuda:0", init_ellipsoid=1, dist_range=(2.0, 7.0), image_weight=1.0, fused=True):
+    """CUDA product vs CPU oracle on one seeded case.  Returns a dict of error figures."""
+    import ctypes
+    import kaolin_shim as kal
+    tm = get_mesh(mm, mesh)
+    dr = mm.DiffRender(tm, image_size, ratio=ratio, init_ellipsoid=init_ellipsoid, image_weight=image_weight)
+    H, W = dr.height, dr.image_size
+    A_cpu = make_attributes(dr.vertices_init, B, H, W, seed, dist_range=dist_range)
+    gt_src = make_attributes(dr.vertices_init, B, H, W, seed + 1000, dist_range=dist_range)
+    orc = oracle_for(dr)
+
+    # ---------------- oracle (CPU): GT image = render of an independent sample
+    with torch.no_grad():
+        gt_cpu, _, _, _ = orc.render(no_mask=no_mask, **gt_src)
+    Ao = to_device(A_cpu, "cpu", requires_grad=True)
+    rgb_o, fn_o, imn_o, fidx_o = orc.render(no_mask=no_mask, **Ao)
+    loss_o, parts_o = orc.recon_data(rgb_o, gt_cpu, no_mask=no_mask, contour=contour, return_parts=True)
+    # an extra consumer of face_normals so its gradient path is exercised too
+    wfn = torch.randn(fn_o.shape, generator=torch.Generator().manual_seed(seed + 7)) * 1e-3
+    (loss_o + (fn_o * wfn).sum()).backward()
+
+    # ---------------- product (CUDA) through the reference-shaped Python API
+    Ac = to_device(A_cpu, device, requires_grad=True)
+    Ac['_want_face_idx'] = True
+    gt_dev = gt_cpu.to(device)
+    rgb_c, Aout = dr.render(no_mask=no_mask, **Ac)
+    loss_c = dr.recon_data(rgb_c, gt_dev, no_mask=no_mask, contour=contour)
+    (loss_c + (Aout['face_normals'] * wfn.to(device)).sum()).backward()
+    torch.cuda.synchronize()
+
+    res = {}
+    fidx_c = Aout['face_idx'].cpu().long()
+    res["face_idx_mismatch_e2e"] = int((fidx_c != fidx_o).sum())
+    res["covered_frac"] = float((fidx_o >= 0).float().mean())
+
+    # ---------------- staged: oracle rasteriser on the product's own vertex-stage output -> bit-exact face_idx
+    h = dr._ctx(torch.device(device))
+    F = dr.num_faces
+    fvi = torch.empty(B, F, 3, 2, device=device)
+    fvz = torch.empty(B, F, 3, device=device)
+    fnz = torch.empty(B, F, device=device)
+    # re-run the forward to get a workspace we own
+    with torch.no_grad():
+        out = dr.render_compare(gt_dev, no_mask=no_mask, contour=contour, **{k: v.detach() for k, v in Ac.items()
+                                                                             if k != '_want_face_idx'})
+    ws = out['_workspace']
+    rc = mm.lib().mm_debug_export_faces(h.handle, B, ctypes.c_void_p(ws.data_ptr()), ctypes.c_void_p(fvi.data_ptr()),
+                                        ctypes.c_void_p(fvz.data_ptr()), ctypes.c_void_p(fnz.data_ptr()),
+                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    feats = torch.ones(B, F, 3, 1)
+    _, fidx_s = kal.rasterize(H, W, fvz.cpu(), fvi.cpu(), feats, fnz.cpu() >= 0)
+    soft_s = kal.dibr_soft_mask(fvi.cpu(), fidx_s)
+    res["face_idx_mismatch_staged"] = int((fidx_c != fidx_s).sum())
+    res["soft_staged_max_abs_err"] = float((rgb_c[:, 3].detach().cpu() - soft_s).abs().max())
+    res["vertex_stage_fvi_rel_err"] = rel_err(fvi, orc.vertex_stage(A_cpu)[1])
+
+    # ---------------- end-to-end numbers (pixels whose winner differs between the two vertex stages are excluded
+    # from the max-abs figure and counted separately)
+    same = (fidx_c == fidx_o)[:, None].expand(-1, 4, -1, -1)
+    diff = (rgb_c.detach().cpu() - rgb_o.detach()).abs()
+    res["rgba_max_abs_err"] = float(diff[same].max())
+    res["rgba_mean_abs_err"] = float(diff.mean())
+    res["loss_cuda"] = float(loss_c)
+    res["loss_oracle"] = float(loss_o)
+    res["loss_rel_err"] = abs(float(loss_c) - float(loss_o)) / max(abs(float(loss_o)), 1e-12)
+    res["face_normals_rel_err"] = rel_err(Aout['face_normals'], fn_o)
+    for k in GRAD_KEYS:
+        if k == 'bg' and not no_mask:
+            continue
+        res["grad_" + k + "_rel_err"] = rel_err(Ac[k].grad, Ao[k].grad)
+    # fused entry point vs the two-call path
+    if fused:
+        res["fused_loss_rel_err"] = abs(float(out['loss'][0]) - float(loss_o)) / max(abs(float(loss_o)), 1e-12)
+        res["fused_rgba_max_abs_vs_unfused"] = float((out['rgba'] - rgb_c.detach()).abs().max())
+    return res
