@@ -159,6 +159,7 @@ int mm_ctx_destroy(mm_ctx* c) {
     cudaFree(c->d_faces);
     cudaFree(c->d_face_uvs);
     cudaFree(c->d_tab);
+    for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
     return MM_OK;
 }
@@ -281,9 +282,11 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     const size_t HW = (size_t)c->H * c->W;
     MM_CUDA(cudaMemsetAsync(g_tex, 0, (size_t)B * 3 * Ht * Wt * 4, s));
     if (g_bg && !no_mask) MM_CUDA(cudaMemsetAsync(g_bg, 0, (size_t)B * 3 * HW * 4, s));
+    if (c->timing) cudaEventRecord(c->ev[0], s);
     mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg),
                          face_normals, (float*)(ws + L.gfacc), s);
     if (int r = check_launch("vertex_fwd")) return r;
+    if (c->timing) cudaEventRecord(c->ev[1], s);
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, no_mask, p);
     p.frec = (const float*)(ws + L.frec);
@@ -293,6 +296,7 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     p.part_fwd = (float*)(ws + L.part_fwd);
     mm_launch_raster_fwd(c, p, true, s);
     if (int r = check_launch("raster_fwd")) return r;
+    if (c->timing) cudaEventRecord(c->ev[2], s);
     p.g_rgba = g_rgba_extra;
     p.part_fwd_in = p.part_fwd;
     p.image_weight = image_weight; p.contour = contour; p.loss_scale = loss_scale;
@@ -302,11 +306,31 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     p.part_bwd = (float*)(ws + L.part_bwd);
     mm_launch_raster_bwd(c, p, s);
     if (int r = check_launch("raster_bwd")) return r;
+    if (c->timing) cudaEventRecord(c->ev[3], s);
     mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.part_bwd, g_vertices, g_azim,
                          g_elev, g_dist, g_bias, g_lights, s);
     if (int r = check_launch("vertex_bwd")) return r;
+    if (c->timing) cudaEventRecord(c->ev[4], s);
     mm_launch_loss_finalize(c, B, p.part_fwd, p.part_bwd, image_weight, contour, loss, nullptr, s);
+    if (c->timing) cudaEventRecord(c->ev[5], s);
     return check_launch("loss_finalize");
+}
+
+int mm_ctx_set_timing(mm_ctx* c, int enable) {
+    MM_REQUIRE(c, "ctx");
+    if (enable && !c->ev[0]) {
+        for (int i = 0; i < 6; ++i) MM_CUDA(cudaEventCreate(&c->ev[i]));
+    }
+    c->timing = enable ? 1 : 0;
+    return MM_OK;
+}
+
+int mm_ctx_get_timing(mm_ctx* c, float* ms_host, int capacity) {
+    MM_REQUIRE(c && ms_host && capacity >= 5, "ctx / ms_host / capacity >= 5");
+    MM_REQUIRE(c->timing && c->ev[0], "timing not enabled");
+    MM_CUDA(cudaEventSynchronize(c->ev[5]));
+    for (int i = 0; i < 5; ++i) MM_CUDA(cudaEventElapsedTime(&ms_host[i], c->ev[i], c->ev[i + 1]));
+    return 5;
 }
 
 int mm_debug_export_faces(mm_ctx* c, int B, const void* workspace, float* fvi, float* fvz, float* fnz, void* stream)

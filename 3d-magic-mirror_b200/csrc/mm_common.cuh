@@ -49,6 +49,9 @@ struct mm_ctx {
     int32_t* d_faces;        // [F,3]
     float*   d_face_uvs;     // [F,6]
     int32_t* d_tab;          // [3*H + 3*W] contour tables: refrow,rowlo,rowhi,refcol,collo,colhi
+    // measurement hook (mm_ctx_set_timing)
+    int timing;
+    cudaEvent_t ev[8];
 };
 
 struct mm_ws_layout {

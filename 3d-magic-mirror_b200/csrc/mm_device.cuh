@@ -50,6 +50,11 @@ __device__ __forceinline__ void bary_eval(const FaceRec& r, float x0, float y0, 
     b.w0 = SUB(SUB(1.0f, b.w1), b.w2);
 }
 
+// feature interpolation exactly as the rasteriser writes it: (w0*c0 + w1*c1) + w2*c2, no FMA contraction
+__device__ __forceinline__ float interp3(float w0, float w1, float w2, float c0, float c1, float c2) {
+    return ADD(ADD(MUL(w0, c0), MUL(w1, c1)), MUL(w2, c2));
+}
+
 // DIBR_SPEC A.2: returns true and fills (w, z) iff the pixel is inside the tight bbox and the triangle
 __device__ __forceinline__ bool hard_test(const FaceRec& r, float x0, float y0, float eps,
                                           float& w0, float& w1, float& w2, float& zz) {

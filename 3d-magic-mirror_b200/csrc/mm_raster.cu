@@ -219,13 +219,14 @@ k_raster_fwd(const mm_raster_params p)
         float tm = 0.0f, nrm[3] = {0.0f, 0.0f, 0.0f}, tcol[3] = {0.0f, 0.0f, 0.0f};
         if (best_f >= 0) {
             const float* uvp = p.face_uvs + best_f * 6;
-            const float u = w0 * __ldg(uvp + 0) + w1 * __ldg(uvp + 2) + w2 * __ldg(uvp + 4);
-            const float v = w0 * __ldg(uvp + 1) + w1 * __ldg(uvp + 3) + w2 * __ldg(uvp + 5);
+            // interpolation in the rasteriser's operation order (w0*c0 + w1*c1) + w2*c2, uncontracted
+            const float u = interp3(w0, w1, w2, __ldg(uvp + 0), __ldg(uvp + 2), __ldg(uvp + 4));
+            const float v = interp3(w0, w1, w2, __ldg(uvp + 1), __ldg(uvp + 3), __ldg(uvp + 5));
             const FaceRec r = load_rec(tc.rec, best_f);
-            tm = w0 + w1 + w2;
-            nrm[0] = w0 * r.nx + w1 * r.nx + w2 * r.nx;
-            nrm[1] = w0 * r.ny + w1 * r.ny + w2 * r.ny;
-            nrm[2] = w0 * r.nz + w1 * r.nz + w2 * r.nz;
+            tm = ADD(ADD(w0, w1), w2);
+            nrm[0] = interp3(w0, w1, w2, r.nx, r.nx, r.nx);
+            nrm[1] = interp3(w0, w1, w2, r.ny, r.ny, r.ny);
+            nrm[2] = interp3(w0, w1, w2, r.nz, r.nz, r.nz);
             Bilin bl;
             bilin_setup(u, v, p.Ht, p.Wt, bl);
             const float* tb = p.tex + (size_t)b * 3 * p.Ht * p.Wt;
@@ -439,12 +440,12 @@ k_raster_bwd(const mm_raster_params p)
             const float* uvp = p.face_uvs + best_f * 6;
             #pragma unroll
             for (int i = 0; i < 6; ++i) uv[i] = __ldg(uvp + i);
-            const float u = bar.w0 * uv[0] + bar.w1 * uv[2] + bar.w2 * uv[4];
-            const float v = bar.w0 * uv[1] + bar.w1 * uv[3] + bar.w2 * uv[5];
-            tm = bar.w0 + bar.w1 + bar.w2;
-            nrm[0] = bar.w0 * r.nx + bar.w1 * r.nx + bar.w2 * r.nx;
-            nrm[1] = bar.w0 * r.ny + bar.w1 * r.ny + bar.w2 * r.ny;
-            nrm[2] = bar.w0 * r.nz + bar.w1 * r.nz + bar.w2 * r.nz;
+            const float u = interp3(bar.w0, bar.w1, bar.w2, uv[0], uv[2], uv[4]);
+            const float v = interp3(bar.w0, bar.w1, bar.w2, uv[1], uv[3], uv[5]);
+            tm = ADD(ADD(bar.w0, bar.w1), bar.w2);
+            nrm[0] = interp3(bar.w0, bar.w1, bar.w2, r.nx, r.nx, r.nx);
+            nrm[1] = interp3(bar.w0, bar.w1, bar.w2, r.ny, r.ny, r.ny);
+            nrm[2] = interp3(bar.w0, bar.w1, bar.w2, r.nz, r.nz, r.nz);
             bilin_setup(u, v, p.Ht, p.Wt, bl);
             const float* tb = p.tex + (size_t)b * 3 * p.Ht * p.Wt;
             #pragma unroll

@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the fused render + recon_data forward+backward (the hot path).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched under torchrun by the driver)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port; rank 0 only)
+
+A "step" is one pass of mm_render_compare_fwd_bwd over one synthetic batch of BASELINE.json configs[1]
+(B=48 per GPU, ellipsoid template V=642 F=1280, 128x128, texture 256x128, no_mask, contour 0.1).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "train images/sec (fused render+loss fwd+bwd) @128x128"
+UNIT = "images/s"
+B_PER_GPU = 48
+IMAGE_SIZE = 128
+NSETS = 4                     # rotating input/output sets: 4 x ~137 MB > 126 MB L2, so every step starts L2-cold
+KERNELS = ["vertex_fwd", "raster_fwd", "raster_bwd", "vertex_bwd", "loss_finalize"]
+
+
+def algorithmic_bytes(B, V, F, H, W, Ht, Wt, bg=True, extra=False):
+    """bytes each tensor contributes when touched once per direction (fp32)."""
+    fwd = 4 * (3 * V + 3 * Ht * Wt + (3 * H * W if bg else 0) + 4 * H * W + 14) + 4 * (4 * H * W + 3 * F)
+    bwd = 4 * ((4 * H * W if extra else 0) + 3 * Ht * Wt + (3 * H * W if bg else 0) + 4 * H * W + 3 * V + 14) + \
+        4 * (3 * V + 3 * Ht * Wt + (3 * H * W if bg else 0) + 14)
+    return B * fwd + F * 36, B * bwd, B * (fwd + bwd) + F * 36
+
+
+# ------------------------------------------------------------------------------------------ distributed helpers
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def aggregate(local_ms, local_units, world):
+    """Whole-job figures: time = MAX over ranks (device-timed), units = SUM over ranks."""
+    import torch
+    import torch.distributed as dist
+    if world == 1 or not dist.is_initialized():
+        return local_ms, local_units
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([local_ms], dtype=torch.float64, device=dev)
+    u = torch.tensor([float(local_units)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    return float(t.item()), float(u.item())
+
+
+def shard_seed(rank):
+    """Every rank draws its own shard of the synthetic data set (manual_seed(1234 + rank))."""
+    return 1234 + rank
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _once(self):
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                     0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def start(self):
+        if self.nv is None:
+            return
+
+        def loop():
+            while not self._stop.is_set():
+                self._once()
+                time.sleep(0.002)
+        self._once()
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
+
+    def stop(self):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"]}
+        self._once()
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ workload
+def build_workload(mm, device, rank, nsets=NSETS, B=B_PER_GPU):
+    import torch
+    import parity_utils as pu
+    dr = mm.DiffRender(pu.get_mesh(mm, "ellipsoid"), IMAGE_SIZE, ratio=1, init_ellipsoid=1, image_weight=1.0)
+    H = W = IMAGE_SIZE
+    sets = []
+    for i in range(nsets):
+        A = pu.make_attributes(dr.vertices_init, B, H, W, shard_seed(rank) * 100 + i)
+        G = pu.make_attributes(dr.vertices_init, B, H, W, shard_seed(rank) * 100 + 50 + i)
+        sets.append((A, G))
+    return dr, sets
+
+
+class FusedRunner(object):
+    """Pre-allocates everything and calls mm_render_compare_fwd_bwd directly (inputs resident in HBM)."""
+
+    def __init__(self, mm, dr, sets_cpu, device):
+        import torch
+        self.torch, self.mm, self.dr, self.dev = torch, mm, dr, device
+        self.L = mm.lib()
+        self.h = dr._ctx(torch.device(device))
+        self.sets = []
+        B = sets_cpu[0][0]['azimuths'].shape[0]
+        self.B = B
+        H, W, F = dr.height, dr.image_size, dr.num_faces
+        for A, G in sets_cpu:
+            d = {k: v.to(device).contiguous() for k, v in A.items()}
+            with torch.no_grad():
+                gt, _ = dr.render(no_mask=True, **{k: v.to(device) for k, v in G.items()})
+            d['gt'] = gt.contiguous()
+            d['out'] = {
+                'rgba': torch.empty(B, 4, H, W, device=device), 'fn': torch.empty(B, F, 3, device=device),
+                'loss': torch.empty(4, device=device), 'g_v': torch.empty_like(d['vertices']),
+                'g_az': torch.empty(B, device=device), 'g_el': torch.empty(B, device=device),
+                'g_di': torch.empty(B, device=device), 'g_bi': torch.empty(B, 2, device=device),
+                'g_tex': torch.empty_like(d['textures']), 'g_li': torch.empty(B, 9, device=device),
+                'g_bg': torch.empty_like(d['bg']), 'ws': self.h.workspace(B)}
+            self.sets.append(d)
+        self.stream = torch.cuda.current_stream()
+
+    def step(self, i, contour=0.1):
+        d = self.sets[i % len(self.sets)]
+        o = d['out']
+        p = lambda t: ctypes.c_void_p(t.data_ptr())     # noqa: E731
+        Ht, Wt = d['textures'].shape[2], d['textures'].shape[3]
+        rc = self.L.mm_render_compare_fwd_bwd(
+            self.h.handle, self.B, p(d['vertices']), p(d['azimuths']), p(d['elevations']), p(d['distances']),
+            p(d['biases']), p(d['textures']), Ht, Wt, p(d['lights']), p(d['bg']), 1, p(d['gt']),
+            1.0, contour, 1.0, ctypes.c_void_p(0), ctypes.c_void_p(0), p(o['rgba']), p(o['fn']), p(o['loss']),
+            p(o['g_v']), p(o['g_az']), p(o['g_el']), p(o['g_di']), p(o['g_bi']), p(o['g_tex']), p(o['g_li']),
+            p(o['g_bg']), p(o['ws']), ctypes.c_void_p(self.stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(self.L.mm_last_error().decode())
+        return o
+
+
+class E2ERunner(object):
+    """The reference-facing path a trainer.py user takes -- DiffRender.render -> recon_data -> backward()
+    (trainer.py:276,441,509) -- fed from pinned HOST buffers every step, loss read back to the host."""
+
+    def __init__(self, mm, dr, sets_cpu, device):
+        import torch
+        self.torch, self.dr, self.dev = torch, dr, device
+        keys = ['vertices', 'azimuths', 'elevations', 'distances', 'biases', 'textures', 'lights', 'bg']
+        self.keys = keys
+        self.host = []
+        for A, G in sets_cpu:
+            with torch.no_grad():
+                gt, _ = dr.render(no_mask=True, **{k: v.to(device) for k, v in G.items()})
+            h = {k: A[k].contiguous().pin_memory() for k in keys}
+            h['gt'] = gt.cpu().contiguous().pin_memory()
+            self.host.append(h)
+        self.h2d_bytes = sum(t.numel() * 4 for t in self.host[0].values())
+        self.loss_host = torch.empty(1).pin_memory()
+        self.d2h_bytes = 4
+
+    def step(self, i):
+        torch = self.torch
+        h = self.host[i % len(self.host)]
+        A = {k: h[k].to(self.dev, non_blocking=True).requires_grad_(True) for k in self.keys}
+        gt = h['gt'].to(self.dev, non_blocking=True)
+        rgbs, _ = self.dr.render(no_mask=True, **A)
+        loss = self.dr.recon_data(rgbs, gt, no_mask=True, contour=0.1)
+        loss.backward()
+        self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        return loss
+
+
+def timed(torch, world, fn, steps):
+    """barrier + sync | start event | `steps` calls | end event | sync + barrier; returns local ms."""
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    return e0.elapsed_time(e1)
+
+
+def cpu_baseline(mm, dr, sets_cpu, budget_s=12.0):
+    """Oracle port (our CPU restatement of the Kaolin DIB-R path + torch-CPU glue) on a bounded sample."""
+    import torch
+    import parity_utils as pu
+    orc = pu.oracle_for(dr)
+    A, G = sets_cpu[0]
+    nb = 8
+    sub = lambda d: {k: v[:nb].clone() for k, v in d.items()}     # noqa: E731
+    with torch.no_grad():
+        gt, _, _, _ = orc.render(no_mask=True, **sub(G))
+
+    def once():
+        Ag = {k: v.requires_grad_(k != 'delta_vertices') for k, v in sub(A).items()}
+        rgb, _, _, _ = orc.render(no_mask=True, **Ag)
+        orc.recon_data(rgb, gt, no_mask=True, contour=0.1).backward()
+    once()
+    t0 = time.perf_counter()
+    once()
+    one = time.perf_counter() - t0
+    reps = max(1, min(50, int(budget_s / max(one, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    dt = time.perf_counter() - t0
+    return {"value": nb * reps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d reps of B=%d images of the bench workload (fwd+bwd), %.1f s; oracle = our CPU restatement of "
+                      "Kaolin DIB-R (kaolin itself is CUDA-only and not installable offline), host has %d logical cores"
+                      % (reps, nb, dt, os.cpu_count())}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the same path (oracle port), rank 0 only."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import torch
+    import __graft_entry__ as g
+    g.build_oracle()
+    mm = g.load_package()
+    dr, sets = build_workload(mm, "cpu", 0, nsets=1, B=8)
+    import parity_utils as pu
+    orc = pu.oracle_for(dr)
+    A, G = sets[0]
+    nb = 8
+    with torch.no_grad():
+        gt, _, _, _ = orc.render(no_mask=True, **G)
+
+    def once():
+        Ag = {k: v.clone().requires_grad_(k != 'delta_vertices') for k, v in A.items()}
+        rgb, _, _, _ = orc.render(no_mask=True, **Ag)
+        orc.recon_data(rgb, gt, no_mask=True, contour=0.1).backward()
+    steps = min(args.steps, 40)
+    for _ in range(min(args.warmup, 2)):
+        once()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        once()
+    dt = time.perf_counter() - t0
+    v = nb * steps / dt
+    sample = "each step = B=%d images of the bench workload, fwd+bwd, %d steps" % (nb, steps)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg-2: ellipsoid V=642 F=1280, 128x128, tex 256x128, no_mask, contour 0.1; "
+                                   "CPU sample of B=%d per step" % nb},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = "cuda:%d" % local_rank
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    if not os.path.exists(os.path.join(g.PKG_DIR, "libmagicmirror.so")):
+        g.build_cuda()
+    mm = g.load_package()
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    dr, sets = build_workload(mm, device, rank)
+    fused = FusedRunner(mm, dr, sets, device)
+    V, F, H, W = dr.num_vertices, dr.num_faces, dr.height, dr.image_size
+    Ht, Wt = sets[0][0]['textures'].shape[2:]
+    bytes_fwd, bytes_bwd, bytes_step = algorithmic_bytes(B_PER_GPU, V, F, H, W, Ht, Wt)
+
+    # ---- value: device-resident inputs, exactly K timed steps
+    for i in range(Wm):
+        fused.step(i)
+    clk = ClockSampler(local_rank)
+    clk.start()
+    ms_local = timed(torch, world, fused.step, K)
+    clocks = clk.stop()
+    ms, units = aggregate(ms_local, B_PER_GPU * K, world)
+    value = units / (ms * 1e-3)
+
+    # ---- per-kernel durations (CUDA events recorded by the library around each of its launches)
+    kms = None
+    L = mm.lib()
+    if hasattr(L, "mm_ctx_set_timing"):
+        h = fused.h.handle
+        L.mm_ctx_set_timing(h, 1)
+        acc = [0.0] * len(KERNELS)
+        buf = (ctypes.c_float * 8)()
+        nprof = min(K, 200)
+        for i in range(nprof):
+            fused.step(i)
+            L.mm_ctx_get_timing(h, buf, 8)
+            for j in range(len(KERNELS)):
+                acc[j] += buf[j]
+        L.mm_ctx_set_timing(h, 0)
+        kms = {k: acc[j] / nprof for j, k in enumerate(KERNELS)}
+
+    # ---- e2e: reference-facing API, pinned host inputs copied every step, loss read back
+    e2e_runner = E2ERunner(mm, dr, sets, device)
+    Ke = max(3, min(K, 200))
+    for i in range(3):
+        e2e_runner.step(i)
+    ms_e_local = timed(torch, world, e2e_runner.step, Ke)
+    ms_e, units_e = aggregate(ms_e_local, B_PER_GPU * Ke, world)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        roof = {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": None}
+        if kms:
+            dom = max(("raster_fwd", "raster_bwd"), key=lambda k: kms[k])
+            nbytes = bytes_bwd if dom == "raster_bwd" else bytes_fwd
+            ach = nbytes / (kms[dom] * 1e-3) / 1e9
+            roof.update({"kernel": "k_" + dom, "achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": nbytes,
+                         "avg_launch_ms": kms[dom], "kernel_ms": kms})
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                roof["traffic"] = tr.get("k_" + dom)
+            except Exception:
+                pass
+        ach_step = bytes_step / (ms / K * 1e-3) / 1e9
+        roof["step"] = {"achieved": ach_step, "frac": ach_step / peak, "algorithmic_bytes_per_step": bytes_step}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "cfg-2 (BASELINE.json configs[1]): B=%d/GPU, ellipsoid V=%d F=%d, %dx%d, tex %dx%d, "
+                                   "no_mask, contour 0.1, fused render+recon_data fwd+bwd" % (B_PER_GPU, V, F, H, W, Ht, Wt),
+                       "l2": "inputs larger than L2: %d rotating input/output sets (%d x %.0f MB)" % (NSETS, NSETS, bytes_step / 1e6),
+                       "parallelism": "dp%d (images sharded, no data-path collective)" % world},
+            "clocks": clocks,
+            "e2e": {"value": units_e / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e_runner.h2d_bytes,
+                    "d2h_bytes_per_step": e2e_runner.d2h_bytes, "steps": Ke,
+                    "api": "DiffRender.render -> recon_data -> backward (pinned host inputs)"},
+            "gpu_launches": len(KERNELS) * K,
+            "roofline": roof,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            g.build_oracle()
+            line["cpu_baseline"] = cpu_baseline(mm, dr, sets)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -125,6 +125,13 @@ int mm_render_compare_fwd_bwd(mm_ctx* ctx, int B,
 int mm_debug_export_faces(mm_ctx* ctx, int B, const void* workspace,
                           float* fvi, float* fvz, float* fnz, void* stream);
 
+/* Measurement hook (bench.py): when enabled, mm_render_compare_fwd_bwd records a CUDA event on
+ * `stream` before each of its kernels and after the last one.  mm_ctx_get_timing waits for the last
+ * call's final event and writes the per-kernel durations in milliseconds, in launch order
+ * (vertex_fwd, raster_fwd, raster_bwd, vertex_bwd, loss_finalize); returns the count written. */
+int mm_ctx_set_timing(mm_ctx* ctx, int enable);
+int mm_ctx_get_timing(mm_ctx* ctx, float* ms_host, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,6 +145,14 @@ def run_parity_case(mm, mesh="icosphere", B=2, image_size=32, ratio=1, no_mask=T
     soft_s = kal.dibr_soft_mask(fvi.cpu(), fidx_s)
     res["face_idx_mismatch_staged"] = int((fidx_c != fidx_s).sum())
     res["soft_staged_max_abs_err"] = float((rgb_c[:, 3].detach().cpu() - soft_s).abs().max())
+    # full staged image: oracle rasteriser + shading on the product's (fvi, fvz, unit normals)
+    fn_c = Aout['face_normals'].detach().cpu()
+    attrs = [torch.ones(B, F, 3, 1), orc.face_uvs.repeat(B, 1, 1, 1), fn_c.unsqueeze(-2).repeat(1, 1, 3, 1)]
+    with torch.no_grad():
+        (tm_s, tc_s, imn_s), soft_s2, _ = kal.dibr_rasterization(H, W, fvz.cpu(), fvi.cpu(), attrs, fnz.cpu())
+        rgb_s = orc.shade(A_cpu, no_mask, tm_s, tc_s, imn_s, soft_s2)
+    res["rgba_staged_max_abs_err"] = float((rgb_c.detach().cpu() - rgb_s).abs().max())
+    res["imnormal_staged_max_abs_err"] = float((Aout['imnormal'].detach().cpu() - imn_s).abs().max())
     res["vertex_stage_fvi_rel_err"] = rel_err(fvi, orc.vertex_stage(A_cpu)[1])
 
     # ---------------- end-to-end numbers (pixels whose winner differs between the two vertex stages are excluded
@@ -157,6 +165,17 @@ def run_parity_case(mm, mesh="icosphere", B=2, image_size=32, ratio=1, no_mask=T
     res["loss_oracle"] = float(loss_o)
     res["loss_rel_err"] = abs(float(loss_c) - float(loss_o)) / max(abs(float(loss_o)), 1e-12)
     res["face_normals_rel_err"] = rel_err(Aout['face_normals'], fn_o)
+    # fp32 noise floor of the reference algorithm itself: the same oracle in fp64 is the arbiter.  Sliver faces at
+    # the silhouette (k3 -> 0) and small faces far from the camera amplify the ~2e-7 difference between two fp32
+    # vertex stages; whatever the fp32 oracle loses against fp64, the product may lose too (x2), never more.
+    orc64 = oracle_for(dr, torch.float64)
+    with torch.no_grad():
+        rgb64, fn64, _, fidx64 = orc64.render(no_mask=no_mask, **{k: v.double() for k, v in A_cpu.items()})
+    agree = ((fidx_c == fidx_o) & (fidx_o == fidx64))[:, None].expand(-1, 4, -1, -1)
+    res["rgba_noise_f32_oracle_vs_f64"] = float((rgb_o.detach().double() - rgb64).abs()[agree].max())
+    res["rgba_err_vs_f64"] = float((rgb_c.detach().cpu().double() - rgb64).abs()[agree].max())
+    res["face_normals_noise_f32_oracle_vs_f64"] = rel_err(fn_o, fn64)
+    res["face_normals_err_vs_f64"] = rel_err(Aout['face_normals'], fn64)
     for k in GRAD_KEYS:
         if k == 'bg' and not no_mask:
             continue
