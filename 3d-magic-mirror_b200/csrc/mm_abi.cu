@@ -65,7 +65,7 @@ int check_launch(const char* what) {
 void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int no_mask, mm_raster_params& p) {
     memset(&p, 0, sizeof(p));
     p.B = B; p.V = c->V; p.F = c->F; p.H = c->H; p.W = c->W; p.Ht = Ht; p.Wt = Wt;
-    p.nstx = c->nstx; p.st_rows = c->st_rows; p.nbands = c->nbands; p.nwords = c->nwords; p.knum = c->knum;
+    p.nstx = c->nstx; p.nsty = c->nsty; p.nst = c->nst; p.nparts = c->nparts; p.nwords = c->nwords; p.knum = c->knum;
     p.sx = c->sx; p.sy = c->sy; p.blen = c->blen; p.multiplier = c->multiplier; p.eps = c->eps; p.sigmainv = c->sigmainv;
     p.no_mask = no_mask;
     p.face_uvs = c->d_face_uvs;
@@ -109,30 +109,32 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     c->sy = multiplier / (float)H;
     c->blen = boxlen * multiplier;
     c->nstx = (W + MM_ST_W - 1) / MM_ST_W;
-    c->nwords = (F + 31) / 32;
+    c->nsty = (H + MM_ST_H - 1) / MM_ST_H;
+    c->nst = c->nstx * c->nsty;
+    c->nparts = (c->nst + MM_WARPS - 1) / MM_WARPS;
+    c->nwords = ((F + 31) / 32 + 3) & ~3;          // multiple of 4 words: mask rows stay 16-byte aligned for cp.async.bulk
     c->num_sms = prop.multiProcessorCount;
-    const int st_total = (H + MM_ST_H - 1) / MM_ST_H;
+    if (F > 65535) { delete c; return fail(MM_E_UNSUPPORTED, "F=%d exceeds the 16-bit face ids of the soft-pass lists", F); }
     const size_t smem_max = prop.sharedMemPerBlockOptin;
-    int st_rows = 2;
-    if (const char* e = getenv("MM_ST_ROWS")) { const int v = atoi(e); if (v > 0) st_rows = v; }
-    if (st_rows > st_total) st_rows = st_total;
-    c->rec_in_smem = ((size_t)F * MM_REC_FLOATS * 4 <= 112 * 1024) ? 1 : 0;
-    if (const char* e = getenv("MM_REC_SMEM")) c->rec_in_smem = atoi(e) ? c->rec_in_smem : 0;
-    for (;;) {
-        c->st_rows = st_rows;
-        c->nbands = (st_total + st_rows - 1) / st_rows;
-        c->smem_raster = mm_raster_smem_bytes(c);
-        if (c->smem_raster <= smem_max) break;
-        if (st_rows > 1) { st_rows >>= 1; continue; }
-        if (c->rec_in_smem) { c->rec_in_smem = 0; continue; }
-        const size_t need = c->smem_raster;
-        delete c;
-        return fail(MM_E_UNSUPPORTED, "F=%d W=%d needs %zu B of shared memory per CTA (> %zu)", F, W, need, smem_max);
+    // vertex stage: sub-tile rows per CTA such that the two chunk masks fit in <= 96 KB and an image gets >= 4 CTAs
+    {
+        const size_t row_bytes = 2 * (size_t)c->nstx * c->nwords * 4;
+        int rows = (int)((96 * 1024) / row_bytes);
+        if (rows < 1) rows = 1;
+        const int want = (c->nsty + 3) / 4;
+        if (rows > want) rows = want;
+        if (const char* e = getenv("MM_CHUNK_ROWS")) { const int v = atoi(e); if (v > 0) rows = v; }
+        if (rows > c->nsty) rows = c->nsty;
+        c->chunk_rows = rows;
+        c->nchunks = (c->nsty + rows - 1) / rows;
     }
-    const size_t vs_f = mm_vertex_smem_fwd(V), vs_b = mm_vertex_smem_bwd(V);
-    if (vs_f > smem_max || vs_b > smem_max) {
+    c->smem_vertex_fwd = mm_vertex_smem_fwd(c);
+    c->smem_raster = mm_raster_smem_bytes(c);
+    const size_t vs_f = c->smem_vertex_fwd, vs_b = mm_vertex_smem_bwd(V);
+    if (vs_f > smem_max || vs_b > smem_max || c->smem_raster > smem_max) {
+        const size_t need = vs_f > vs_b ? (vs_f > c->smem_raster ? vs_f : c->smem_raster) : (vs_b > c->smem_raster ? vs_b : c->smem_raster);
         delete c;
-        return fail(MM_E_UNSUPPORTED, "V=%d needs %zu B of shared memory in the vertex stage (> %zu)", V, vs_b, smem_max);
+        return fail(MM_E_UNSUPPORTED, "V=%d F=%d W=%d needs %zu B of shared memory per CTA (> %zu)", V, F, W, need, smem_max);
     }
     mm_vertex_set_smem(vs_f, vs_b);
     cudaError_t e = mm_raster_configure(c);
@@ -182,12 +184,13 @@ int mm_render_forward(mm_ctx* c, int B, const float* vertices, const float* azim
     cudaStream_t s = (cudaStream_t)stream;
     const mm_ws_layout L = mm_ws_make(c, B);
     char* ws = (char*)workspace;
-    mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg),
-                         face_normals, nullptr, s);
+    mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (uint32_t*)(ws + L.maskS),
+                         (uint32_t*)(ws + L.maskH), (float*)(ws + L.vimg), face_normals, nullptr, s);
     if (int r = check_launch("vertex_fwd")) return r;
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, no_mask, p);
     p.frec = (const float*)(ws + L.frec);
+    p.maskS = (const uint32_t*)(ws + L.maskS); p.maskH = (const uint32_t*)(ws + L.maskH);
     p.tex = tex; p.lights = lights; p.bg = bg;
     p.rgba = rgba; p.imnormal = imnormal;
     p.face_idx_ws = (int32_t*)(ws + L.face_idx); p.face_idx_out = face_idx;
@@ -217,6 +220,7 @@ int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azi
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, no_mask, p);
     p.frec = (const float*)(ws + L.frec);
+    p.maskS = (const uint32_t*)(ws + L.maskS); p.maskH = (const uint32_t*)(ws + L.maskH);
     p.tex = tex; p.lights = lights; p.bg = bg;
     p.rgba = const_cast<float*>(rgba);
     p.face_idx_ws = (int32_t*)(ws + L.face_idx);
@@ -283,13 +287,14 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     MM_CUDA(cudaMemsetAsync(g_tex, 0, (size_t)B * 3 * Ht * Wt * 4, s));
     if (g_bg && !no_mask) MM_CUDA(cudaMemsetAsync(g_bg, 0, (size_t)B * 3 * HW * 4, s));
     if (c->timing) cudaEventRecord(c->ev[0], s);
-    mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg),
-                         face_normals, (float*)(ws + L.gfacc), s);
+    mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (uint32_t*)(ws + L.maskS),
+                         (uint32_t*)(ws + L.maskH), (float*)(ws + L.vimg), face_normals, (float*)(ws + L.gfacc), s);
     if (int r = check_launch("vertex_fwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[1], s);
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, no_mask, p);
     p.frec = (const float*)(ws + L.frec);
+    p.maskS = (const uint32_t*)(ws + L.maskS); p.maskH = (const uint32_t*)(ws + L.maskH);
     p.tex = tex; p.lights = lights; p.bg = bg; p.gt = gt;
     p.rgba = rgba;
     p.face_idx_ws = (int32_t*)(ws + L.face_idx);

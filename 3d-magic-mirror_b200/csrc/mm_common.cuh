@@ -12,11 +12,15 @@
 //                          n = unit face normal in camera space.  48 B / face, one
 //                          contiguous block per image so a CTA stages it with ONE
 //                          cp.async.bulk (TMA bulk copy) into shared memory.
+//     maskS/H    [B,NST,NW] per-sub-tile face BITMASKS written by the vertex stage (NST = sub-tiles per
+//                          image, NW = ceil(F/32)): bit f of sub-tile s is set iff face f's bbox enlarged by
+//                          `boxlen` (S) / front face f's tight bbox (H) can touch s.  A bitmask keeps faces in
+//                          index order, which DIB-R's "first knum faces" truncation needs.
 //     vimg       [B,V,2]   unscaled image-plane xy (debug export / parity tests)
 //     face_idx   [B,H,W]   int32 winner of the hard pass (-1 none); saved for backward
 //     gfacc      [B,F,9]   backward accumulators: d/d(fvi) (6, unscaled) + d/d(unit normal) (3)
-//     part_fwd   [B,NB,4]  per-CTA partial sums (L1, N, D, contour)  NB = bands per image
-//     part_bwd   [B,NB,12] per-CTA partials (contour sum, 9 light grads, -, -)
+//     part_fwd   [B,NP,4]  per-CTA partial sums (L1, N, D, contour)  NP = raster CTAs per image
+//     part_bwd   [B,NP,12] per-CTA partials (contour sum, 9 light grads, -, -)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -38,12 +42,13 @@ struct mm_ctx {
     // derived
     float sx, sy;            // multiplier / W, multiplier / H  (fp32 division, DIBR_SPEC A.1)
     float blen;              // boxlen * multiplier
-    int nstx;                // sub-tile columns  = ceil(W / 8)
-    int st_rows;             // sub-tile rows per CTA band
-    int nbands;              // CTAs per image    = ceil(ceil(H/4) / st_rows)
+    int nstx, nsty;          // sub-tile grid = ceil(W / 8) x ceil(H / 4)
+    int nst;                 // sub-tiles per image
+    int nparts;              // raster CTAs per image = ceil(nst / 8) (one warp per sub-tile); also #loss partials
     int nwords;              // bitmask words per sub-tile = ceil(F / 32)
-    int rec_in_smem;         // face records staged in shared memory (else read through L1)
-    size_t smem_raster;      // dynamic smem bytes of the raster kernels
+    int chunk_rows, nchunks; // vertex stage: sub-tile rows binned per CTA, CTAs per image
+    size_t smem_vertex_fwd;  // dynamic smem bytes of the vertex forward kernel
+    size_t smem_raster;      // dynamic smem bytes of the raster kernels (per-lane soft candidate lists)
     int num_sms;
     // device arrays
     int32_t* d_faces;        // [F,3]
@@ -55,7 +60,7 @@ struct mm_ctx {
 };
 
 struct mm_ws_layout {
-    size_t frec, vimg, face_idx, gfacc, part_fwd, part_bwd, total;
+    size_t frec, maskS, maskH, vimg, face_idx, gfacc, part_fwd, part_bwd, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -64,11 +69,13 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     mm_ws_layout L;
     size_t off = 0;
     L.frec = off;     off = mm_align_up(off + (size_t)B * c->F * MM_REC_FLOATS * 4, 256);
+    L.maskS = off;    off = mm_align_up(off + (size_t)B * c->nst * c->nwords * 4, 256);
+    L.maskH = off;    off = mm_align_up(off + (size_t)B * c->nst * c->nwords * 4, 256);
     L.vimg = off;     off = mm_align_up(off + (size_t)B * c->V * 2 * 4, 256);
     L.face_idx = off; off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.gfacc = off;    off = mm_align_up(off + (size_t)B * c->F * 9 * 4, 256);
-    L.part_fwd = off; off = mm_align_up(off + (size_t)B * c->nbands * 4 * 4, 256);
-    L.part_bwd = off; off = mm_align_up(off + (size_t)B * c->nbands * 12 * 4, 256);
+    L.part_fwd = off; off = mm_align_up(off + (size_t)B * c->nparts * 4 * 4, 256);
+    L.part_bwd = off; off = mm_align_up(off + (size_t)B * c->nparts * 12 * 4, 256);
     L.total = off;
     return L;
 }
@@ -76,10 +83,12 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
 // parameters shared by the raster kernels (passed by value)
 struct mm_raster_params {
     int B, V, F, H, W, Ht, Wt;
-    int nstx, st_rows, nbands, nwords, knum;
+    int nstx, nsty, nst, nparts, nwords, knum;
     float sx, sy, blen, multiplier, eps, sigmainv;
     int no_mask;
     const float* frec;       // [B,F,12]
+    const uint32_t* maskS;   // [B,NST,NW]
+    const uint32_t* maskH;   // [B,NST,NW]
     const float* face_uvs;   // [F,6]
     const float* tex;        // [B,3,Ht,Wt]
     const float* lights;     // [B,9]
@@ -90,22 +99,22 @@ struct mm_raster_params {
     float* imnormal;         // [B,H,W,3] or NULL
     int32_t* face_idx_ws;    // [B,H,W]
     int32_t* face_idx_out;   // [B,H,W] or NULL
-    float* part_fwd;         // [B,NB,4]
+    float* part_fwd;         // [B,NP,4]
     // backward
     const float* g_rgba;     // [B,4,H,W] or NULL
-    const float* part_fwd_in;// [B,NB,4] forward partials (IoU sums re-derived per CTA)
+    const float* part_fwd_in;// [B,NP,4] forward partials (IoU sums re-derived per CTA)
     float image_weight, contour, loss_scale;
     int analytic_loss;
     float* gfacc;            // [B,F,9]
     float* g_tex;            // [B,3,Ht,Wt]
     float* g_bg;             // [B,3,H,W] or NULL
-    float* part_bwd;         // [B,NB,12]
+    float* part_bwd;         // [B,NP,12]
 };
 
 // launchers (defined in the .cu files)
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
-                          const float* dist, const float* bias, float* frec, float* vimg, float* face_normals,
-                          float* gfacc_zero, cudaStream_t s);
+                          const float* dist, const float* bias, float* frec, uint32_t* maskS, uint32_t* maskH,
+                          float* vimg, float* face_normals, float* gfacc_zero, cudaStream_t s);
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,
                           const float* part_bwd, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
@@ -120,7 +129,7 @@ void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float*
                          float image_weight, float contour, float loss_scale, float* g_pred, cudaStream_t s);
 cudaError_t mm_raster_configure(const mm_ctx* c);
 size_t mm_raster_smem_bytes(const mm_ctx* c);
-size_t mm_vertex_smem_fwd(int V);
+size_t mm_vertex_smem_fwd(const mm_ctx* c);
 size_t mm_vertex_smem_bwd(int V);
 void mm_vertex_set_smem(size_t fwd, size_t bwd);
 void mm_launch_export_faces(const mm_ctx* c, int B, const float* frec, const float* vimg, float* fvi, float* fvz,

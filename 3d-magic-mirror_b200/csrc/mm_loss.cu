@@ -5,9 +5,9 @@
 
 namespace {
 
-// One CTA per (band of rows, image): partial sums (L1, N, D, contour) -> part_fwd[b][band][4]
+// One CTA per (contiguous pixel range, image): partial sums (L1, N, D, contour) -> part_fwd[b][band][4]
 __global__ void __launch_bounds__(MM_THREADS)
-k_recon_fwd(int H, int W, int band_rows, int nbands, float contour,
+k_recon_fwd(int H, int W, int nparts, float contour,
             const float* __restrict__ pred, const float* __restrict__ gt, const int32_t* __restrict__ tab,
             float* __restrict__ part_fwd)
 {
@@ -18,9 +18,10 @@ k_recon_fwd(int H, int W, int band_rows, int nbands, float contour,
     const float* gb = gt + (size_t)b * 4 * HW;
     const int32_t* refrow = tab;
     const int32_t* refcol = tab + 3 * H;
-    const int y0 = band * band_rows, y1 = min(H, y0 + band_rows);
+    const int per = (H * W + nparts - 1) / nparts;               // contiguous pixel range of this CTA
+    const int i0 = band * per, i1 = min(H * W, i0 + per);
     float a_l1 = 0.0f, a_n = 0.0f, a_d = 0.0f, a_c = 0.0f;
-    for (int i = y0 * W + threadIdx.x; i < y1 * W; i += MM_THREADS) {
+    for (int i = i0 + threadIdx.x; i < i1; i += MM_THREADS) {
         const float gm = gb[3 * HW + i], m = pb[3 * HW + i];
         #pragma unroll
         for (int c = 0; c < 3; ++c) a_l1 += fabsf(l1_term(pb[c * HW + i], gb[c * HW + i], gm));
@@ -36,13 +37,13 @@ k_recon_fwd(int H, int W, int band_rows, int nbands, float contour,
     }
     const float s0 = block_sum(a_l1, red), s1 = block_sum(a_n, red), s2 = block_sum(a_d, red), s3 = block_sum(a_c, red);
     if (threadIdx.x == 0) {
-        float* pf = part_fwd + ((size_t)b * nbands + band) * 4;
+        float* pf = part_fwd + ((size_t)b * nparts + band) * 4;
         pf[0] = s0; pf[1] = s1; pf[2] = s2; pf[3] = s3;
     }
 }
 
 __global__ void __launch_bounds__(MM_THREADS)
-k_recon_bwd(int B, int H, int W, int band_rows, int nbands, float image_weight, float contour, float loss_scale,
+k_recon_bwd(int B, int H, int W, int nparts, float image_weight, float contour, float loss_scale,
             const float* __restrict__ pred, const float* __restrict__ gt, const int32_t* __restrict__ tab,
             const float* __restrict__ part_fwd, float* __restrict__ g_pred)
 {
@@ -58,16 +59,17 @@ k_recon_bwd(int B, int H, int W, int band_rows, int nbands, float image_weight, 
     const int32_t* collo = tab + 3 * H + W;
     const int32_t* colhi = tab + 3 * H + 2 * W;
     float Nb = 0.0f, Db = 0.0f;
-    for (int k = 0; k < nbands; ++k) {
-        Nb += part_fwd[((size_t)b * nbands + k) * 4 + 1];
-        Db += part_fwd[((size_t)b * nbands + k) * 4 + 2];
+    for (int k = 0; k < nparts; ++k) {
+        Nb += part_fwd[((size_t)b * nparts + k) * 4 + 1];
+        Db += part_fwd[((size_t)b * nparts + k) * 4 + 2];
     }
     const float De = Db + 1e-10f;
     const float k_img = loss_scale * image_weight / ((float)B * 3.0f * (float)HW);
     const float k_iou = loss_scale / (float)B;
     const float k_cont = loss_scale * contour / ((float)B * (float)HW);
-    const int y0 = band * band_rows, y1 = min(H, y0 + band_rows);
-    for (int i = y0 * W + threadIdx.x; i < y1 * W; i += MM_THREADS) {
+    const int per = (H * W + nparts - 1) / nparts;
+    const int i0 = band * per, i1 = min(H * W, i0 + per);
+    for (int i = i0 + threadIdx.x; i < i1; i += MM_THREADS) {
         const float gm = gb[3 * HW + i], m = pb[3 * HW + i];
         #pragma unroll
         for (int c = 0; c < 3; ++c)
@@ -94,22 +96,22 @@ k_recon_bwd(int B, int H, int W, int band_rows, int nbands, float image_weight, 
 
 // loss[0..3] = data, image, mask (1 - mean IoU), contour term.  Single CTA, fixed summation order.
 __global__ void __launch_bounds__(MM_THREADS)
-k_loss_finalize(int B, int H, int W, int nbands, float image_weight, float contour,
+k_loss_finalize(int B, int H, int W, int nparts, float image_weight, float contour,
                 const float* __restrict__ part_fwd, const float* __restrict__ part_bwd,
                 float* __restrict__ loss, float* __restrict__ iou_out)
 {
     __shared__ float red[MM_WARPS];
     float a_l1 = 0.0f, a_c = 0.0f, a_iou = 0.0f;
-    for (int i = threadIdx.x; i < B * nbands; i += MM_THREADS) {
+    for (int i = threadIdx.x; i < B * nparts; i += MM_THREADS) {
         a_l1 += part_fwd[(size_t)i * 4 + 0];
         a_c += part_fwd[(size_t)i * 4 + 3];
         if (part_bwd) a_c += part_bwd[(size_t)i * 12 + 0];
     }
     for (int b = threadIdx.x; b < B; b += MM_THREADS) {
         float n = 0.0f, d = 0.0f;
-        for (int k = 0; k < nbands; ++k) {
-            n += part_fwd[((size_t)b * nbands + k) * 4 + 1];
-            d += part_fwd[((size_t)b * nbands + k) * 4 + 2];
+        for (int k = 0; k < nparts; ++k) {
+            n += part_fwd[((size_t)b * nparts + k) * 4 + 1];
+            d += part_fwd[((size_t)b * nparts + k) * 4 + 2];
         }
         a_iou += n / (d + 1e-10f);
         if (iou_out) { iou_out[b * 2] = n; iou_out[b * 2 + 1] = d; }
@@ -132,22 +134,21 @@ k_loss_finalize(int B, int H, int W, int nbands, float image_weight, float conto
 void mm_launch_recon_fwd(const mm_ctx* c, int B, const float* pred, const float* gt, float contour, float* part_fwd,
                          cudaStream_t s)
 {
-    const dim3 grid(c->nbands, B);
-    k_recon_fwd<<<grid, MM_THREADS, 0, s>>>(c->H, c->W, c->st_rows * MM_ST_H, c->nbands, contour, pred, gt, c->d_tab,
-                                            part_fwd);
+    const dim3 grid(c->nparts, B);
+    k_recon_fwd<<<grid, MM_THREADS, 0, s>>>(c->H, c->W, c->nparts, contour, pred, gt, c->d_tab, part_fwd);
 }
 
 void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float* gt, const float* part_fwd,
                          float image_weight, float contour, float loss_scale, float* g_pred, cudaStream_t s)
 {
-    const dim3 grid(c->nbands, B);
-    k_recon_bwd<<<grid, MM_THREADS, 0, s>>>(B, c->H, c->W, c->st_rows * MM_ST_H, c->nbands, image_weight, contour,
-                                            loss_scale, pred, gt, c->d_tab, part_fwd, g_pred);
+    const dim3 grid(c->nparts, B);
+    k_recon_bwd<<<grid, MM_THREADS, 0, s>>>(B, c->H, c->W, c->nparts, image_weight, contour, loss_scale, pred, gt,
+                                            c->d_tab, part_fwd, g_pred);
 }
 
 void mm_launch_loss_finalize(const mm_ctx* c, int B, const float* part_fwd, const float* part_bwd,
                              float image_weight, float contour, float* loss, float* iou_out, cudaStream_t s)
 {
-    k_loss_finalize<<<1, MM_THREADS, 0, s>>>(B, c->H, c->W, c->nbands, image_weight, contour, part_fwd, part_bwd,
+    k_loss_finalize<<<1, MM_THREADS, 0, s>>>(B, c->H, c->W, c->nparts, image_weight, contour, part_fwd, part_bwd,
                                              loss, iou_out);
 }

@@ -1,10 +1,11 @@
 // mm_vertex.cu -- vertex stage of the render path, forward and backward.
 //
-// Forward fuses, per image (one CTA each): camera_position_from_spherical_angles
+// Forward fuses, per image: camera_position_from_spherical_angles
 // (smr_utils.py:257-281), generate_transformation_matrix (smr_utils.py:284-311),
 // kaolin prepare_vertices (networks.py:284-287: [v,1]*T, perspective divide, gather
 // by faces, unit face normals) and the second face_normals call (networks.py:289),
-// and emits the 48-byte face records the raster kernels stage into shared memory.
+// emits the 48-byte face records the raster kernels read, and bins every face into
+// the per-sub-tile bitmasks (the "tile face lists").
 // The reference runs ~25 tiny kernels + a cuBLAS matmul for this.
 //
 // Backward consumes the per-face accumulators (d/d fvi, d/d unit normal) produced by
@@ -58,24 +59,39 @@ __device__ inline void transform_vertex(const float* T, float x, float y, float 
 }
 
 // ------------------------------------------------------------------ forward
+// grid = (nchunks, B).  Every CTA of an image recomputes the (tiny) vertex transform, writes the face
+// records of its contiguous 1/nchunks share of the faces, and bins ALL faces into the bitmasks of its own
+// `chunk_rows` sub-tile rows (built in shared memory with atomicOr, then streamed out coalesced).
+struct VertexFwdParams {
+    int V, F, H, W, nstx, nsty, nwords, chunk_rows, nchunks;
+    float proj_x, proj_y, multiplier, sx, sy, blen;
+};
+
 __global__ void __launch_bounds__(256)
-k_vertex_fwd(int V, int F, float proj_x, float proj_y, float multiplier,
+k_vertex_fwd(const VertexFwdParams q,
              const int32_t* __restrict__ faces, const float* __restrict__ vertices,
              const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
              const float* __restrict__ bias,
-             float* __restrict__ frec, float* __restrict__ vimg, float* __restrict__ face_normals,
-             float* __restrict__ gfacc_zero)
+             float* __restrict__ frec, uint32_t* __restrict__ maskS, uint32_t* __restrict__ maskH,
+             float* __restrict__ vimg, float* __restrict__ face_normals, float* __restrict__ gfacc_zero)
 {
     extern __shared__ float sm[];
-    float* sT = sm;                  // 12
-    float* svc = sm + 16;            // V*3 camera-space
+    const int V = q.V, F = q.F;
+    float* sT = sm;                    // 12
+    float* svc = sm + 16;              // V*3 camera-space
     float* svi = svc + (size_t)V * 3;  // V*2 image-plane (unscaled)
-    const int b = blockIdx.x;
+    uint32_t* smS = reinterpret_cast<uint32_t*>(svi + (size_t)V * 2);
+    const int chunk = blockIdx.x, b = blockIdx.y;
+    const int row0 = chunk * q.chunk_rows;
+    const int rows = min(q.chunk_rows, q.nsty - row0);
+    const int nmask = rows * q.nstx * q.nwords;
+    uint32_t* smH = smS + (size_t)q.chunk_rows * q.nstx * q.nwords;
     if (threadIdx.x == 0) {
         Cam c;
         camera_setup(azim[b], elev[b], dist[b], bias[b * 2], bias[b * 2 + 1], c);
         for (int i = 0; i < 12; ++i) sT[i] = c.T[i];
     }
+    for (int i = threadIdx.x; i < nmask; i += blockDim.x) { smS[i] = 0u; smH[i] = 0u; }
     __syncthreads();
     const float* vb = vertices + (size_t)b * V * 3;
     for (int v = threadIdx.x; v < V; v += blockDim.x) {
@@ -84,13 +100,18 @@ k_vertex_fwd(int V, int F, float proj_x, float proj_y, float multiplier,
         svc[v * 3] = cx; svc[v * 3 + 1] = cy; svc[v * 3 + 2] = cz;
         // kaolin perspective_camera: (x*px, y*py) / (z * -1)
         const float den = cz * -1.0f;
-        const float xi = (cx * proj_x) / den, yi = (cy * proj_y) / den;
+        const float xi = (cx * q.proj_x) / den, yi = (cy * q.proj_y) / den;
         svi[v * 2] = xi; svi[v * 2 + 1] = yi;
-        vimg[((size_t)b * V + v) * 2] = xi;
-        vimg[((size_t)b * V + v) * 2 + 1] = yi;
+        if (chunk == 0) {
+            vimg[((size_t)b * V + v) * 2] = xi;
+            vimg[((size_t)b * V + v) * 2 + 1] = yi;
+        }
     }
     __syncthreads();
     float4* rec = reinterpret_cast<float4*>(frec + (size_t)b * F * MM_REC_FLOATS);
+    const float inv_sx = 1.0f / q.sx, inv_sy = 1.0f / q.sy;
+    const int py0 = row0 * MM_ST_H, prow = rows * MM_ST_H;     // pixel rows covered by this chunk
+    const int per_chunk = (F + q.nchunks - 1) / q.nchunks;   // contiguous face range whose records this CTA writes
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
         const int i0 = faces[f * 3], i1 = faces[f * 3 + 1], i2 = faces[f * 3 + 2];
         const float ax = svc[i0 * 3], ay = svc[i0 * 3 + 1], az = svc[i0 * 3 + 2];
@@ -104,20 +125,58 @@ k_vertex_fwd(int V, int F, float proj_x, float proj_y, float multiplier,
         const float len = sqrtf(nx * nx + ny * ny + nz * nz);
         const float inv = len + 1e-10f;
         nx /= inv; ny /= inv; nz /= inv;
-        rec[f * 3 + 0] = make_float4(__fmul_rn(svi[i0 * 2], multiplier), __fmul_rn(svi[i0 * 2 + 1], multiplier),
-                                     __fmul_rn(svi[i1 * 2], multiplier), __fmul_rn(svi[i1 * 2 + 1], multiplier));
-        rec[f * 3 + 1] = make_float4(__fmul_rn(svi[i2 * 2], multiplier), __fmul_rn(svi[i2 * 2 + 1], multiplier), az, bz);
-        rec[f * 3 + 2] = make_float4(cz, nx, ny, nz);
-        if (face_normals) {
-            float* fn = face_normals + ((size_t)b * F + f) * 3;
-            fn[0] = nx; fn[1] = ny; fn[2] = nz;
+        // image-plane corners scaled by `multiplier` (DIBR_SPEC A.1), one rounding each
+        const float sax = __fmul_rn(svi[i0 * 2], q.multiplier), say = __fmul_rn(svi[i0 * 2 + 1], q.multiplier);
+        const float sbx = __fmul_rn(svi[i1 * 2], q.multiplier), sby = __fmul_rn(svi[i1 * 2 + 1], q.multiplier);
+        const float scx = __fmul_rn(svi[i2 * 2], q.multiplier), scy = __fmul_rn(svi[i2 * 2 + 1], q.multiplier);
+        if ((f / per_chunk) == chunk) {
+            rec[f * 3 + 0] = make_float4(sax, say, sbx, sby);
+            rec[f * 3 + 1] = make_float4(scx, scy, az, bz);
+            rec[f * 3 + 2] = make_float4(cz, nx, ny, nz);
+            if (face_normals) {
+                float* fn = face_normals + ((size_t)b * F + f) * 3;
+                fn[0] = nx; fn[1] = ny; fn[2] = nz;
+            }
+            if (gfacc_zero) {
+                float* g = gfacc_zero + ((size_t)b * F + f) * 9;
+                #pragma unroll
+                for (int i = 0; i < 9; ++i) g[i] = 0.0f;
+            }
         }
-        if (gfacc_zero) {
-            float* g = gfacc_zero + ((size_t)b * F + f) * 9;
-            #pragma unroll
-            for (int i = 0; i < 9; ++i) g[i] = 0.0f;
+        // ---- binning: conservative pixel ranges (exact tests are redone per pixel in the raster kernels)
+        const float xmin = fminf(fminf(sax, sbx), scx), xmax = fmaxf(fmaxf(sax, sbx), scx);
+        const float ymin = fminf(fminf(say, sby), scy), ymax = fmaxf(fmaxf(say, sby), scy);
+        const float xl = xmin - q.blen, xh = xmax + q.blen, yl = ymin - q.blen, yh = ymax + q.blen;
+        float fx_lo = (xl * inv_sx + (float)(q.W - 1)) * 0.5f;
+        float fx_hi = (xh * inv_sx + (float)(q.W - 1)) * 0.5f;
+        float fy_lo = ((float)(q.H - 1) - yh * inv_sy) * 0.5f;
+        float fy_hi = ((float)(q.H - 1) - yl * inv_sy) * 0.5f;
+        // NaN/Inf coordinates (vertex on the camera plane) must stay conservative: treat as "everywhere"
+        if (!(fx_lo == fx_lo) || !(fx_hi == fx_hi)) { fx_lo = -4.0f; fx_hi = 1.0e6f; }
+        if (!(fy_lo == fy_lo) || !(fy_hi == fy_hi)) { fy_lo = -4.0f; fy_hi = 1.0e6f; }
+        fx_lo = fminf(fmaxf(fx_lo, -4.0f), 1.0e6f); fx_hi = fminf(fmaxf(fx_hi, -4.0f), 1.0e6f);
+        fy_lo = fminf(fmaxf(fy_lo, -4.0f), 1.0e6f); fy_hi = fminf(fmaxf(fy_hi, -4.0f), 1.0e6f);
+        const int ix0 = max((int)floorf(fx_lo), 0), ix1 = min((int)ceilf(fx_hi), q.W - 1);
+        const int iy0 = max((int)floorf(fy_lo) - py0, 0), iy1 = min((int)ceilf(fy_hi) - py0, prow - 1);
+        if (ix0 > ix1 || iy0 > iy1) continue;
+        const bool front = nz >= 0.0f;
+        const float bpx = q.blen * inv_sx * 0.5f, bpy = q.blen * inv_sy * 0.5f;
+        const int hx0 = max((int)floorf(fx_lo + bpx), 0), hx1 = min((int)ceilf(fx_hi - bpx), q.W - 1);
+        const int hy0 = max((int)floorf(fy_lo + bpy) - py0, 0), hy1 = min((int)ceilf(fy_hi - bpy) - py0, prow - 1);
+        const uint32_t bit = 1u << (f & 31);
+        const int wd = f >> 5;
+        for (int sy = iy0 >> 2; sy <= (iy1 >> 2); ++sy) {
+            for (int sxi = ix0 >> 3; sxi <= (ix1 >> 3); ++sxi) {
+                const int st = sy * q.nstx + sxi;
+                atomicOr(&smS[st * q.nwords + wd], bit);
+                if (front && sxi >= (hx0 >> 3) && sxi <= (hx1 >> 3) && sy >= (hy0 >> 2) && sy <= (hy1 >> 2))
+                    atomicOr(&smH[st * q.nwords + wd], bit);
+            }
         }
     }
+    __syncthreads();
+    const size_t gbase = ((size_t)b * q.nsty * q.nstx + (size_t)row0 * q.nstx) * q.nwords;
+    for (int i = threadIdx.x; i < nmask; i += blockDim.x) { maskS[gbase + i] = smS[i]; maskH[gbase + i] = smH[i]; }
 }
 
 // ------------------------------------------------------------------ backward
@@ -134,7 +193,7 @@ __device__ inline float block_sum_256(float v, float* red /* >= 8 floats */) {
 }
 
 __global__ void __launch_bounds__(256)
-k_vertex_bwd(int V, int F, int nbands, float proj_x, float proj_y,
+k_vertex_bwd(int V, int F, int nparts, float proj_x, float proj_y,
              const int32_t* __restrict__ faces, const float* __restrict__ vertices,
              const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
              const float* __restrict__ bias,
@@ -271,7 +330,7 @@ k_vertex_bwd(int V, int F, int nbands, float proj_x, float proj_y,
     // (4) light gradient: deterministic sum of the per-CTA partials of the raster backward
     if (threadIdx.x < 9) {
         float s = 0.0f;
-        for (int k = 0; k < nbands; ++k) s += part_bwd[((size_t)b * nbands + k) * 12 + 1 + threadIdx.x];
+        for (int k = 0; k < nparts; ++k) s += part_bwd[((size_t)b * nparts + k) * 12 + 1 + threadIdx.x];
         g_lights[b * 9 + threadIdx.x] = s;
     }
 }
@@ -298,12 +357,16 @@ __global__ void k_export_faces(int V, int F, float multiplier, const int32_t* __
 }  // namespace
 
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
-                          const float* dist, const float* bias, float* frec, float* vimg, float* face_normals,
-                          float* gfacc_zero, cudaStream_t s)
+                          const float* dist, const float* bias, float* frec, uint32_t* maskS, uint32_t* maskH,
+                          float* vimg, float* face_normals, float* gfacc_zero, cudaStream_t s)
 {
-    const size_t smem = (16 + (size_t)c->V * 5) * sizeof(float);
-    k_vertex_fwd<<<B, 256, smem, s>>>(c->V, c->F, c->proj_x, c->proj_y, c->multiplier, c->d_faces, vertices,
-                                      azim, elev, dist, bias, frec, vimg, face_normals, gfacc_zero);
+    VertexFwdParams q;
+    q.V = c->V; q.F = c->F; q.H = c->H; q.W = c->W; q.nstx = c->nstx; q.nsty = c->nsty; q.nwords = c->nwords;
+    q.chunk_rows = c->chunk_rows; q.nchunks = c->nchunks;
+    q.proj_x = c->proj_x; q.proj_y = c->proj_y; q.multiplier = c->multiplier; q.sx = c->sx; q.sy = c->sy; q.blen = c->blen;
+    const dim3 grid(c->nchunks, B);
+    k_vertex_fwd<<<grid, 256, c->smem_vertex_fwd, s>>>(q, c->d_faces, vertices, azim, elev, dist, bias, frec, maskS,
+                                                       maskH, vimg, face_normals, gfacc_zero);
 }
 
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
@@ -312,7 +375,7 @@ void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const f
                           float* g_bias, float* g_lights, cudaStream_t s)
 {
     const size_t smem = ((size_t)c->V * 6) * sizeof(float);
-    k_vertex_bwd<<<B, 256, smem, s>>>(c->V, c->F, c->nbands, c->proj_x, c->proj_y, c->d_faces, vertices, azim, elev,
+    k_vertex_bwd<<<B, 256, smem, s>>>(c->V, c->F, c->nparts, c->proj_x, c->proj_y, c->d_faces, vertices, azim, elev,
                                       dist, bias, gfacc, g_face_normals, part_bwd, g_vertices, g_azim, g_elev,
                                       g_dist, g_bias, g_lights);
 }
@@ -325,7 +388,9 @@ void mm_launch_export_faces(const mm_ctx* c, int B, const float* frec, const flo
                                                        fnz, total);
 }
 
-size_t mm_vertex_smem_fwd(int V) { return (16 + (size_t)V * 5) * sizeof(float); }
+size_t mm_vertex_smem_fwd(const mm_ctx* c) {
+    return (16 + (size_t)c->V * 5) * sizeof(float) + 2 * (size_t)c->chunk_rows * c->nstx * c->nwords * sizeof(uint32_t);
+}
 size_t mm_vertex_smem_bwd(int V) { return ((size_t)V * 6) * sizeof(float); }
 void mm_vertex_set_smem(size_t fwd, size_t bwd) {
     cudaFuncSetAttribute(k_vertex_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd);
