@@ -70,6 +70,7 @@ void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int no_mask, mm_raster_
     p.no_mask = no_mask;
     p.face_uvs = c->d_face_uvs;
     p.tab = c->d_tab;
+    p.prof = c->d_prof;
 }
 
 }  // namespace
@@ -111,7 +112,8 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     c->nstx = (W + MM_ST_W - 1) / MM_ST_W;
     c->nsty = (H + MM_ST_H - 1) / MM_ST_H;
     c->nst = c->nstx * c->nsty;
-    c->nparts = (c->nst + MM_WARPS - 1) / MM_WARPS;
+    c->nparts = (c->nst + MM_RWARPS - 1) / MM_RWARPS;
+    c->nparts_recon = (H * W + 4095) / 4096 < 1 ? 1 : (H * W + 4095) / 4096;     // ~4096 pixels per recon CTA
     c->nwords = ((F + 31) / 32 + 3) & ~3;          // multiple of 4 words: mask rows stay 16-byte aligned for cp.async.bulk
     c->num_sms = prop.multiProcessorCount;
     if (F > 65535) { delete c; return fail(MM_E_UNSUPPORTED, "F=%d exceeds the 16-bit face ids of the soft-pass lists", F); }
@@ -185,7 +187,7 @@ int mm_render_forward(mm_ctx* c, int B, const float* vertices, const float* azim
     const mm_ws_layout L = mm_ws_make(c, B);
     char* ws = (char*)workspace;
     mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (uint32_t*)(ws + L.maskS),
-                         (uint32_t*)(ws + L.maskH), (float*)(ws + L.vimg), face_normals, nullptr, s);
+                         (uint32_t*)(ws + L.maskH), (float*)(ws + L.vimg), face_normals, nullptr, (uint32_t*)(ws + L.tickets), s);
     if (int r = check_launch("vertex_fwd")) return r;
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, no_mask, p);
@@ -195,6 +197,7 @@ int mm_render_forward(mm_ctx* c, int B, const float* vertices, const float* azim
     p.rgba = rgba; p.imnormal = imnormal;
     p.face_idx_ws = (int32_t*)(ws + L.face_idx); p.face_idx_out = face_idx;
     p.part_fwd = (float*)(ws + L.part_fwd);
+    p.img_fwd = (float*)(ws + L.img_fwd); p.img_bwd = (float*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
     mm_launch_raster_fwd(c, p, false, s);
     return check_launch("raster_fwd");
 }
@@ -229,9 +232,10 @@ int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azi
     p.gfacc = (float*)(ws + L.gfacc);
     p.g_tex = g_tex; p.g_bg = no_mask ? g_bg : nullptr;
     p.part_bwd = (float*)(ws + L.part_bwd);
+    p.img_fwd = (float*)(ws + L.img_fwd); p.img_bwd = (float*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
     mm_launch_raster_bwd(c, p, s);
     if (int r = check_launch("raster_bwd")) return r;
-    mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.part_bwd, g_vertices,
+    mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.img_bwd, g_vertices,
                          g_azim, g_elev, g_dist, g_bias, g_lights, s);
     return check_launch("vertex_bwd");
 }
@@ -246,7 +250,8 @@ int mm_recon_data_forward(mm_ctx* c, int B, const float* pred, const float* gt, 
     char* ws = (char*)workspace;
     mm_launch_recon_fwd(c, B, pred, gt, contour, (float*)(ws + L.part_fwd), s);
     if (int r = check_launch("recon_fwd")) return r;
-    mm_launch_loss_finalize(c, B, (const float*)(ws + L.part_fwd), nullptr, image_weight, contour, loss, iou_sums, s);
+    mm_launch_image_reduce(c, B, c->nparts_recon, (const float*)(ws + L.part_fwd), (float*)(ws + L.img_fwd), s);
+    mm_launch_loss_finalize(c, B, (const float*)(ws + L.img_fwd), nullptr, image_weight, contour, loss, iou_sums, s);
     return check_launch("loss_finalize");
 }
 
@@ -261,7 +266,8 @@ int mm_recon_data_backward(mm_ctx* c, int B, const float* pred, const float* gt,
     // the IoU sums are re-derived so that the call does not depend on workspace state of an earlier forward
     mm_launch_recon_fwd(c, B, pred, gt, 0.0f, (float*)(ws + L.part_fwd), s);
     if (int r = check_launch("recon_fwd")) return r;
-    mm_launch_recon_bwd(c, B, pred, gt, (const float*)(ws + L.part_fwd), image_weight, contour, loss_scale, g_pred, s);
+    mm_launch_image_reduce(c, B, c->nparts_recon, (const float*)(ws + L.part_fwd), (float*)(ws + L.img_fwd), s);
+    mm_launch_recon_bwd(c, B, pred, gt, (const float*)(ws + L.img_fwd), image_weight, contour, loss_scale, g_pred, s);
     return check_launch("recon_bwd");
 }
 
@@ -288,7 +294,8 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     if (g_bg && !no_mask) MM_CUDA(cudaMemsetAsync(g_bg, 0, (size_t)B * 3 * HW * 4, s));
     if (c->timing) cudaEventRecord(c->ev[0], s);
     mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (uint32_t*)(ws + L.maskS),
-                         (uint32_t*)(ws + L.maskH), (float*)(ws + L.vimg), face_normals, (float*)(ws + L.gfacc), s);
+                         (uint32_t*)(ws + L.maskH), (float*)(ws + L.vimg), face_normals, (float*)(ws + L.gfacc),
+                         (uint32_t*)(ws + L.tickets), s);
     if (int r = check_launch("vertex_fwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[1], s);
     mm_raster_params p;
@@ -299,11 +306,11 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     p.rgba = rgba;
     p.face_idx_ws = (int32_t*)(ws + L.face_idx);
     p.part_fwd = (float*)(ws + L.part_fwd);
+    p.img_fwd = (float*)(ws + L.img_fwd); p.img_bwd = (float*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
     mm_launch_raster_fwd(c, p, true, s);
     if (int r = check_launch("raster_fwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[2], s);
     p.g_rgba = g_rgba_extra;
-    p.part_fwd_in = p.part_fwd;
     p.image_weight = image_weight; p.contour = contour; p.loss_scale = loss_scale;
     p.analytic_loss = 1;
     p.gfacc = (float*)(ws + L.gfacc);
@@ -312,13 +319,19 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     mm_launch_raster_bwd(c, p, s);
     if (int r = check_launch("raster_bwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[3], s);
-    mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.part_bwd, g_vertices, g_azim,
+    mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.img_bwd, g_vertices, g_azim,
                          g_elev, g_dist, g_bias, g_lights, s);
     if (int r = check_launch("vertex_bwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[4], s);
-    mm_launch_loss_finalize(c, B, p.part_fwd, p.part_bwd, image_weight, contour, loss, nullptr, s);
+    mm_launch_loss_finalize(c, B, p.img_fwd, p.img_bwd, image_weight, contour, loss, nullptr, s);
     if (c->timing) cudaEventRecord(c->ev[5], s);
     return check_launch("loss_finalize");
+}
+
+int mm_debug_set_profile_buffer(mm_ctx* c, long long* device_buf) {
+    MM_REQUIRE(c, "ctx");
+    c->d_prof = device_buf;
+    return MM_OK;
 }
 
 int mm_ctx_set_timing(mm_ctx* c, int enable) {

@@ -21,13 +21,23 @@
 //     gfacc      [B,F,9]   backward accumulators: d/d(fvi) (6, unscaled) + d/d(unit normal) (3)
 //     part_fwd   [B,NP,4]  per-CTA partial sums (L1, N, D, contour)  NP = raster CTAs per image
 //     part_bwd   [B,NP,12] per-CTA partials (contour sum, 9 light grads, -, -)
+//     img_fwd    [B,4]     per-image sums (L1, N, D, contour), reduced in a FIXED order by the last CTA of the image
+//     img_bwd    [B,12]    per-image sums (contour, 9 light grads), same scheme
+//     tickets    [B,2]     u32 arrival counters of the forward / backward raster CTAs (self-resetting)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
 
-#define MM_THREADS      256          // threads per raster CTA (8 warps)
+#define MM_THREADS      256          // threads per CTA of the loss / vertex kernels
 #define MM_WARPS        (MM_THREADS / 32)
+#ifndef MM_RWARPS
+#define MM_RWARPS       1            // raster kernels: warps (= sub-tiles) per CTA.  1 => the hardware CTA scheduler
+#endif                               // balances sub-tiles individually (heavy silhouette tiles never park idle warps)
+#define MM_RTHREADS     (32 * MM_RWARPS)
+#ifndef MM_RMINB
+#define MM_RMINB        24           // min resident raster CTAs per SM (caps registers at 64/thread for 1-warp CTAs)
+#endif
 #define MM_ST_W         8            // sub-tile (one warp) = 8 x 4 pixels
 #define MM_ST_H         4
 #define MM_REC_FLOATS   12
@@ -44,7 +54,8 @@ struct mm_ctx {
     float blen;              // boxlen * multiplier
     int nstx, nsty;          // sub-tile grid = ceil(W / 8) x ceil(H / 4)
     int nst;                 // sub-tiles per image
-    int nparts;              // raster CTAs per image = ceil(nst / 8) (one warp per sub-tile); also #loss partials
+    int nparts;              // raster CTAs per image = ceil(nst / MM_RWARPS) (one warp per sub-tile); #partials of the fused path
+    int nparts_recon;        // CTAs per image of the stand-alone recon_data kernels
     int nwords;              // bitmask words per sub-tile = ceil(F / 32)
     int chunk_rows, nchunks; // vertex stage: sub-tile rows binned per CTA, CTAs per image
     size_t smem_vertex_fwd;  // dynamic smem bytes of the vertex forward kernel
@@ -55,12 +66,13 @@ struct mm_ctx {
     float*   d_face_uvs;     // [F,6]
     int32_t* d_tab;          // [3*H + 3*W] contour tables: refrow,rowlo,rowhi,refcol,collo,colhi
     // measurement hook (mm_ctx_set_timing)
+    long long* d_prof;       // optional per-sub-tile cycle counters (debug, NULL normally)
     int timing;
     cudaEvent_t ev[8];
 };
 
 struct mm_ws_layout {
-    size_t frec, maskS, maskH, vimg, face_idx, gfacc, part_fwd, part_bwd, total;
+    size_t frec, maskS, maskH, vimg, face_idx, gfacc, part_fwd, part_bwd, img_fwd, img_bwd, tickets, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -74,8 +86,12 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     L.vimg = off;     off = mm_align_up(off + (size_t)B * c->V * 2 * 4, 256);
     L.face_idx = off; off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.gfacc = off;    off = mm_align_up(off + (size_t)B * c->F * 9 * 4, 256);
-    L.part_fwd = off; off = mm_align_up(off + (size_t)B * c->nparts * 4 * 4, 256);
-    L.part_bwd = off; off = mm_align_up(off + (size_t)B * c->nparts * 12 * 4, 256);
+    const size_t np = (size_t)(c->nparts > c->nparts_recon ? c->nparts : c->nparts_recon);
+    L.part_fwd = off; off = mm_align_up(off + (size_t)B * np * 4 * 4, 256);
+    L.part_bwd = off; off = mm_align_up(off + (size_t)B * np * 12 * 4, 256);
+    L.img_fwd = off;  off = mm_align_up(off + (size_t)B * 4 * 4, 256);
+    L.img_bwd = off;  off = mm_align_up(off + (size_t)B * 12 * 4, 256);
+    L.tickets = off;  off = mm_align_up(off + (size_t)B * 2 * 4, 256);
     L.total = off;
     return L;
 }
@@ -100,32 +116,36 @@ struct mm_raster_params {
     int32_t* face_idx_ws;    // [B,H,W]
     int32_t* face_idx_out;   // [B,H,W] or NULL
     float* part_fwd;         // [B,NP,4]
+    float* img_fwd;          // [B,4]
+    float* img_bwd;          // [B,12]
+    uint32_t* tickets;       // [B,2]
     // backward
     const float* g_rgba;     // [B,4,H,W] or NULL
-    const float* part_fwd_in;// [B,NP,4] forward partials (IoU sums re-derived per CTA)
     float image_weight, contour, loss_scale;
     int analytic_loss;
     float* gfacc;            // [B,F,9]
     float* g_tex;            // [B,3,Ht,Wt]
     float* g_bg;             // [B,3,H,W] or NULL
     float* part_bwd;         // [B,NP,12]
+    long long* prof;         // debug: [B,NST,8] cycles fwd / bwd, popc(S), popc(H), hard, soft-mark, soft-pairs cycles, #pairs; NULL normally
 };
 
 // launchers (defined in the .cu files)
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec, uint32_t* maskS, uint32_t* maskH,
-                          float* vimg, float* face_normals, float* gfacc_zero, cudaStream_t s);
+                          float* vimg, float* face_normals, float* gfacc_zero, uint32_t* tickets, cudaStream_t s);
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,
-                          const float* part_bwd, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
+                          const float* img_bwd, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
                           float* g_bias, float* g_lights, cudaStream_t s);
 void mm_launch_raster_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_loss, cudaStream_t s);
 void mm_launch_raster_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
-void mm_launch_loss_finalize(const mm_ctx* c, int B, const float* part_fwd, const float* part_bwd,
+void mm_launch_loss_finalize(const mm_ctx* c, int B, const float* img_fwd, const float* img_bwd,
                              float image_weight, float contour, float* loss, float* iou_out, cudaStream_t s);
+void mm_launch_image_reduce(const mm_ctx* c, int B, int np, const float* part_fwd, float* img_fwd, cudaStream_t s);
 void mm_launch_recon_fwd(const mm_ctx* c, int B, const float* pred, const float* gt, float contour, float* part_fwd,
                          cudaStream_t s);
-void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float* gt, const float* part_fwd,
+void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float* gt, const float* img_fwd,
                          float image_weight, float contour, float loss_scale, float* g_pred, cudaStream_t s);
 cudaError_t mm_raster_configure(const mm_ctx* c);
 size_t mm_raster_smem_bytes(const mm_ctx* c);

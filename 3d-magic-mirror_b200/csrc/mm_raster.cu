@@ -5,21 +5,25 @@
 // networks.py:297-317, and their autograd.
 //
 // Work decomposition (B200: 148 SMs):
-//   grid = (nparts, B); one CTA = 8 warps = 8 consecutive sub-tiles of one image, one
-//   warp per sub-tile (8x4 pixels, one lane per pixel).
-//     1. The CTA stages the bitmask rows ("tile face lists") of its 8 sub-tiles -- one
+//   grid = (nparts, B); one CTA = MM_RWARPS warps (default 1), one warp per sub-tile (8x4 pixels, one lane per
+//   pixel).  Single-warp CTAs let the hardware scheduler balance sub-tiles individually: silhouette tiles cost
+//   100x an empty tile, and in a multi-warp CTA the finished warps would park at the final barrier.
+//     1. The CTA stages the bitmask rows ("tile face lists") of its sub-tiles -- one
 //        contiguous block per mask -- into shared memory with TMA bulk copies
 //        (cp.async.bulk + mbarrier).  The masks were produced by the vertex stage.
-//     2. Hard pass: the warp walks the set bits of its H mask in index order; all 32
-//        lanes visit the same face at the same time (the 48-byte face record is one
-//        broadcast load served by L1) and test their own pixel.  Bit-exact DIB-R
-//        arithmetic (see mm_device.cuh).
-//     3. Soft pass, only if some lane is uncovered: phase A walks the S mask and lets
-//        every uncovered lane append the faces whose enlarged bbox contains ITS pixel
-//        to a private list in shared memory (stops at knum, so DIB-R's order-dependent
-//        truncation falls out for free); phase B lets every lane evaluate only its own
-//        list -- the expensive distance/exp code runs on (pixel, face) pairs that
-//        matter instead of on every face of the sub-tile for every lane.
+//     2. Hard pass, FACE-parallel: the set bits of the H mask are compacted into dense
+//        batches of 32 faces; each lane loads ONE face record and rasterises it over the
+//        few pixels of the sub-tile its bbox touches, resolving visibility with a packed
+//        (depth, ~face) atomicMax per pixel in shared memory.  Work is proportional to
+//        sum |bbox ∩ sub-tile| instead of faces x 32 pixels, there is no serial
+//        load->test chain across faces, and far-camera images (all 1280 faces inside a
+//        handful of sub-tiles) stop being a critical path.  Bit-exact DIB-R arithmetic
+//        (see mm_device.cuh): max z / smallest index == the reference's ordered scan.
+//     3. Soft pass, only if some pixel is uncovered, also face-parallel over the S mask:
+//        lanes mark per-pixel hit words (exact half-open enlarged-bbox test); the rank of
+//        a (pixel, face) pair among the pixel's candidates (batch order == lane order ==
+//        face-index order) enforces DIB-R's "first knum faces" cap; accepted pairs
+//        evaluate the distance/exp code once each.
 //   Backward re-derives the same per-pixel state from `face_idx` (saved) and the same
 //   masks instead of storing Kaolin's knum-deep side buffers
 //   (B*H*W*30*(4+8+1) B = 307 MB at B=48,128^2).
@@ -29,20 +33,35 @@ namespace {
 
 #define FULL 0xffffffffu
 
+// per-warp scratch in shared memory (one sub-tile = one warp)
+struct WarpScratch {
+    uint32_t fq[64];               // face queue: set bits of the mask row compacted into dense batches of 32
+    uint32_t fid[32];              // face ids of the current batch (slot j = lane j's face)
+    uint32_t hit[32];              // per pixel: which slots (faces) of the current batch hit it
+    uint32_t cnt[32];              // per pixel: candidates seen so far (DIB-R's knum cap)
+    float gs[32];                  // bwd: upstream gradient of the silhouette per pixel
+    float oma[32];                 // bwd: 1 - soft per pixel
+    float rec[9][32];              // the batch's face records (ax ay bx by cx cy az bz cz), column j = slot j
+    float facc[6][32];             // bwd: per-face corner-gradient accumulators of the batch
+    uint32_t pr[1024];             // pair list: (slot << 5 | pixel), overwritten in place by the pair's result
+    long long dbg[4];              // debug cycle counters (mm_debug_set_profile_buffer)
+};
+
 struct CtaCtx {
     const uint32_t* mS;     // this warp's S mask row (shared memory)
     const uint32_t* mH;     // this warp's H mask row (shared memory)
-    uint16_t* slist;        // [knum][MM_THREADS] per-lane soft candidate lists
+    WarpScratch* ws;        // this warp's scratch
     float* lights;          // 9
-    float* red;             // MM_WARPS
+    float* red;             // MM_RWARPS
     const float* rec;       // face records of this image (global, read through L1)
-    int st, ix, iy;
+    int st, stx, sty, ix, iy;
     bool st_valid, active;
 };
 
-// dynamic smem: | mbarrier 16 B | maskS 8*nwords*4 | maskH 8*nwords*4 | slist knum*256*2 |
+// dynamic smem: | mbarrier 16 B | maskS 8*nwords*4 | maskH 8*nwords*4 | 8 x WarpScratch |
 __host__ __device__ inline size_t raster_smem(int nwords, int knum) {
-    return 16 + 2 * (size_t)MM_WARPS * nwords * 4 + (size_t)knum * MM_THREADS * 2;
+    (void)knum;
+    return 16 + 2 * (size_t)MM_RWARPS * nwords * 4 + MM_RWARPS * sizeof(WarpScratch);
 }
 
 __device__ __forceinline__ void cta_prologue(const mm_raster_params& p, unsigned char* smem, float* s_lights, float* s_red,
@@ -52,12 +71,12 @@ __device__ __forceinline__ void cta_prologue(const mm_raster_params& p, unsigned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     uint32_t* smS = reinterpret_cast<uint32_t*>(smem + 16);
-    uint32_t* smH = smS + MM_WARPS * p.nwords;
-    c.slist = reinterpret_cast<uint16_t*>(smH + MM_WARPS * p.nwords);
+    uint32_t* smH = smS + MM_RWARPS * p.nwords;
+    c.ws = reinterpret_cast<WarpScratch*>(smH + MM_RWARPS * p.nwords) + warp;
     c.lights = s_lights; c.red = s_red;
     c.rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
-    const int st0 = g * MM_WARPS;
-    const int nsub = min(MM_WARPS, p.nst - st0);
+    const int st0 = g * MM_RWARPS;
+    const int nsub = min(MM_RWARPS, p.nst - st0);
     if (threadIdx.x == 0) mbar_init(bar, 1);
     if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
     __syncthreads();
@@ -72,34 +91,97 @@ __device__ __forceinline__ void cta_prologue(const mm_raster_params& p, unsigned
     }
     c.st = st0 + warp;
     c.st_valid = c.st < p.nst;
-    const int sty = c.st / p.nstx, stx = c.st - sty * p.nstx;
-    c.ix = stx * MM_ST_W + (lane & 7);
-    c.iy = sty * MM_ST_H + (lane >> 3);
+    c.sty = c.st / p.nstx; c.stx = c.st - c.sty * p.nstx;
+    c.ix = c.stx * MM_ST_W + (lane & 7);
+    c.iy = c.sty * MM_ST_H + (lane >> 3);
     c.active = c.st_valid && (c.ix < p.W) && (c.iy < p.H);
     c.mS = smS + warp * p.nwords;
     c.mH = smH + warp * p.nwords;
     mbar_wait(bar, 0);
 }
 
-// Walks the set bits of one sub-tile mask row in face-index order; fn(f) is warp-uniform.
-template <typename Fn>
-__device__ __forceinline__ void for_each_face(const uint32_t* row, int nwords, int lane, Fn fn)
+// sum over the raster CTA (MM_RWARPS warps); a single-warp CTA needs no barrier at all
+__device__ __forceinline__ float rblock_sum(float v, float* red) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if (MM_RWARPS == 1) return v;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.0f;
+    #pragma unroll
+    for (int i = 0; i < MM_RWARPS; ++i) r += red[i];
+    return r;
+}
+
+// Per-image reduction without a second kernel and without float atomics: every CTA publishes its partial
+// sums, takes a ticket, and the LAST CTA of the image sums all partials in a fixed order (deterministic).
+// Returns true in the CTA that did the reduction.  The ticket resets itself so the workspace can be reused.
+template <int NV>
+__device__ __forceinline__ bool image_reduce_last(const float (&v)[NV], float* part /* [nparts][STRIDE] of this image */,
+                                                  int stride, int nparts, uint32_t* ticket, float* out, int lane)
 {
+    __shared__ uint32_t s_ticket;
+    if (threadIdx.x == 0) {
+        #pragma unroll
+        for (int i = 0; i < NV; ++i) part[(size_t)blockIdx.x * stride + i] = v[i];
+        __threadfence();
+        s_ticket = atomicAdd(ticket, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != (uint32_t)(nparts - 1)) return false;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        float acc[NV];
+        #pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
+        for (int k = lane; k < nparts; k += 32) {
+            #pragma unroll
+            for (int i = 0; i < NV; ++i) acc[i] += __ldcg(part + (size_t)k * stride + i);
+        }
+        #pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
+        }
+        if (lane == 0) {
+            #pragma unroll
+            for (int i = 0; i < NV; ++i) out[i] = acc[i];
+            *ticket = 0u;
+        }
+    }
+    return true;
+}
+
+// Compacts the set bits of one sub-tile mask row (face-index order) into dense batches of 32 faces and calls
+// fn(f) once per batch with ALL lanes converged: lane j gets the j-th face of the batch, or -1.
+template <typename Fn>
+__device__ __forceinline__ void for_each_batch(const uint32_t* row, int nwords, int lane, uint32_t* fq, Fn fn)
+{
+    int qn = 0;
+    const uint32_t lt = (1u << lane) - 1u;
     for (int wd0 = 0; wd0 < nwords; wd0 += 32) {
         const uint32_t w = (wd0 + lane < nwords) ? row[wd0 + lane] : 0u;
         uint32_t nz = __ballot_sync(FULL, w != 0u);
         while (nz) {
             const int src = __ffs(nz) - 1;
             nz &= nz - 1;
-            uint32_t m = __shfl_sync(FULL, w, src);
-            const int base = (wd0 + src) << 5;
-            while (m) {
-                const int f = base + __ffs(m) - 1;
-                m &= m - 1;
+            const uint32_t m = __shfl_sync(FULL, w, src);
+            if ((m >> lane) & 1u) fq[qn + __popc(m & lt)] = (uint32_t)(((wd0 + src) << 5) + lane);
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                const int f = (int)fq[lane];
+                const uint32_t carry = fq[32 + lane];
+                __syncwarp();
                 fn(f);
+                qn -= 32;
+                if (lane < qn) fq[lane] = carry;
+                __syncwarp();
             }
         }
     }
+    if (qn > 0) fn(lane < qn ? (int)fq[lane] : -1);
 }
 
 __device__ __forceinline__ bool mask_empty(const uint32_t* row, int nwords, int lane)
@@ -109,67 +191,223 @@ __device__ __forceinline__ bool mask_empty(const uint32_t* row, int nwords, int 
     return __ballot_sync(FULL, any != 0u) == 0u;
 }
 
-// Hard pass (DIBR_SPEC A.2)
+// Conservative pixel-index range, clipped to the sub-tile, of the scaled-NDC box [xl,xh) x [yl,yh)
+// (the exact half-open tests are redone per pixel).  Returns false if empty.
+struct PixRange { int ix0, ix1, iy0, iy1; };
+__device__ __forceinline__ bool pix_range(const mm_raster_params& p, const CtaCtx& c, float xl, float xh, float yl, float yh,
+                                          PixRange& r)
+{
+    const float inv_sx = 1.0f / p.sx, inv_sy = 1.0f / p.sy;
+    float fx_lo = (xl * inv_sx + (float)(p.W - 1)) * 0.5f;
+    float fx_hi = (xh * inv_sx + (float)(p.W - 1)) * 0.5f;
+    float fy_lo = ((float)(p.H - 1) - yh * inv_sy) * 0.5f;
+    float fy_hi = ((float)(p.H - 1) - yl * inv_sy) * 0.5f;
+    if (!(fx_lo == fx_lo) || !(fx_hi == fx_hi)) { fx_lo = -4.0f; fx_hi = 1.0e6f; }
+    if (!(fy_lo == fy_lo) || !(fy_hi == fy_hi)) { fy_lo = -4.0f; fy_hi = 1.0e6f; }
+    fx_lo = fminf(fmaxf(fx_lo, -4.0f), 1.0e6f); fx_hi = fminf(fmaxf(fx_hi, -4.0f), 1.0e6f);
+    fy_lo = fminf(fmaxf(fy_lo, -4.0f), 1.0e6f); fy_hi = fminf(fmaxf(fy_hi, -4.0f), 1.0e6f);
+    const int bx = c.stx * MM_ST_W, by = c.sty * MM_ST_H;
+    r.ix0 = max((int)floorf(fx_lo), bx);
+    r.ix1 = min(min((int)ceilf(fx_hi), bx + MM_ST_W - 1), p.W - 1);
+    r.iy0 = max((int)floorf(fy_lo), by);
+    r.iy1 = min(min((int)ceilf(fy_hi), by + MM_ST_H - 1), p.H - 1);
+    return r.ix0 <= r.ix1 && r.iy0 <= r.iy1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The pair engine: one batch of <= 32 faces against the 32 pixels of the sub-tile, in four warp-synchronous phases.
+//   ph1 (lanes = faces)  mark(f): the lane parks its face record in ws->rec and ORs bit `lane` into ws->hit[pixel]
+//                        for every pixel of the sub-tile inside the face's (tight or enlarged) bbox -- exact
+//                        half-open fp32 test, DIBR_SPEC A.2 / A.4.
+//   ph2 (lanes = pixels) batches arrive in face-index order and slots inside a batch are in face-index order, so
+//                        cnt[pixel] + rank-in-hit-word is the pair's position in the reference's ordered scan; pairs
+//                        beyond `cap` are dropped (DIB-R's order-dependent knum truncation).  Accepted pairs go to a
+//                        dense list; each pixel's pairs are CONTIGUOUS and in face order.
+//   ph3 (lanes = pairs)  eval(slot, pixel) -> float: the expensive arithmetic (barycentrics + 2 IEEE divisions, or
+//                        distance + exp) runs once per accepted pair with all 32 lanes busy, whatever the shape of
+//                        the face/pixel incidence.
+//   ph4 (lanes = pixels) scan(slot, value): every pixel folds ITS pairs in face order -- a strictly-greater depth
+//                        test or a running product -- i.e. exactly the reference's sequential loop over faces,
+//                        without atomics, so `face_idx` ties and the silhouette product keep the reference's order.
+template <typename MarkFn, typename EvalFn, typename ScanFn>
+__device__ __forceinline__ int pair_batch(const mm_raster_params& p, WarpScratch* ws, int lane, int f, int cap,
+                                          MarkFn mark, EvalFn eval, ScanFn scan)
+{
+    ws->fid[lane] = (uint32_t)f;
+    mark(f);
+    __syncwarp();
+    uint32_t keep = ws->hit[lane];
+    const int base = (int)ws->cnt[lane];
+    const int nh = __popc(keep);
+    ws->cnt[lane] = (uint32_t)(base + nh);
+    ws->hit[lane] = 0u;
+    int allowed = cap - base;
+    allowed = allowed < 0 ? 0 : allowed;
+    if (nh > allowed) {                          // keep only the `allowed` lowest set bits (rare: > knum candidates)
+        uint32_t k2 = 0u, h = keep;
+        for (int a = 0; a < allowed; ++a) { const uint32_t low = h & (0u - h); k2 |= low; h ^= low; }
+        keep = k2;
+    }
+    const int nk = __popc(keep);
+    int incl = nk;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    const int pos0 = incl - nk;
+    {
+        int pos = pos0;
+        uint32_t k2 = keep;
+        while (k2) { const int j = __ffs(k2) - 1; k2 &= k2 - 1; ws->pr[pos++] = (uint32_t)((j << 5) | lane); }
+    }
+    __syncwarp();
+    for (int i = lane; i < total; i += 32) {
+        const uint32_t e = ws->pr[i];
+        ws->pr[i] = __float_as_uint(eval((int)(e >> 5), (int)(e & 31u)));
+    }
+    __syncwarp();
+    {
+        int pos = pos0;
+        uint32_t k2 = keep;
+        while (k2) { const int j = __ffs(k2) - 1; k2 &= k2 - 1; scan(j, __uint_as_float(ws->pr[pos++])); }
+    }
+    __syncwarp();
+    (void)p;
+    return total;
+}
+
+// ph1 helper: park the record, then mark the pixels of the sub-tile whose centre lies in [xmin,xmax) x [ymin,ymax)
+__device__ __forceinline__ void mark_box(const mm_raster_params& p, const CtaCtx& c, int lane, const FaceRec& r,
+                                         float xmin, float xmax, float ymin, float ymax, uint32_t need)
+{
+    WarpScratch* ws = c.ws;
+    ws->rec[0][lane] = r.ax; ws->rec[1][lane] = r.ay; ws->rec[2][lane] = r.bx; ws->rec[3][lane] = r.by;
+    ws->rec[4][lane] = r.cx; ws->rec[5][lane] = r.cy; ws->rec[6][lane] = r.az; ws->rec[7][lane] = r.bz; ws->rec[8][lane] = r.cz;
+    PixRange pr;
+    if (!pix_range(p, c, xmin, xmax, ymin, ymax, pr)) return;
+    const int bx = c.stx * MM_ST_W, by = c.sty * MM_ST_H;
+    for (int iy = pr.iy0; iy <= pr.iy1; ++iy) {
+        const float py = pix_y(iy, p.H, p.sy);
+        if (py < ymin || py >= ymax) continue;
+        for (int ix = pr.ix0; ix <= pr.ix1; ++ix) {
+            const int pl = (iy - by) * MM_ST_W + (ix - bx);
+            const float px = pix_x(ix, p.W, p.sx);
+            if (((need >> pl) & 1u) && !(px < xmin || px >= xmax)) atomicOr(&ws->hit[pl], 1u << lane);
+        }
+    }
+}
+
+__device__ __forceinline__ FaceRec slot_rec(const WarpScratch* ws, int j) {
+    FaceRec r;
+    r.ax = ws->rec[0][j]; r.ay = ws->rec[1][j]; r.bx = ws->rec[2][j]; r.by = ws->rec[3][j];
+    r.cx = ws->rec[4][j]; r.cy = ws->rec[5][j]; r.az = ws->rec[6][j]; r.bz = ws->rec[7][j]; r.cz = ws->rec[8][j];
+    r.nx = r.ny = r.nz = 0.0f;
+    return r;
+}
+
+// Hard pass (DIBR_SPEC A.2): front faces, tight bbox, barycentric inside test, strictly-greater depth, first face wins
+// ties.  The winner's weights are recomputed at the end by the pixel's own lane (same instruction sequence).
 __device__ __forceinline__ void hard_pass(const mm_raster_params& p, const CtaCtx& c, int lane, float x0, float y0,
                                           int& best_f, float& bw0, float& bw1, float& bw2)
 {
+    WarpScratch* ws = c.ws;
+    ws->hit[lane] = 0u; ws->cnt[lane] = 0u;
+    __syncwarp();
+    const int bx = c.stx * MM_ST_W, by = c.sty * MM_ST_H;
     float best_z = -INFINITY;
-    best_f = -1; bw0 = bw1 = bw2 = 0.0f;
-    for_each_face(c.mH, p.nwords, lane, [&](int f) {
-        const FaceRec r = load_rec(c.rec, f);
-        float w0, w1, w2, zz;
-        if (hard_test(r, x0, y0, p.eps, w0, w1, w2, zz)) {
-            if (!(zz <= best_z)) { best_z = zz; best_f = f; bw0 = w0; bw1 = w1; bw2 = w2; }
-        }
+    int bf = -1;
+    for_each_batch(c.mH, p.nwords, lane, ws->fq, [&](int f) {
+        pair_batch(p, ws, lane, f, 0x7fffffff,
+            [&](int ff) {
+                if (ff < 0) return;
+                const FaceRec r = load_rec(c.rec, ff);
+                if (!(r.nz >= 0.0f)) return;
+                mark_box(p, c, lane, r, fminf(fminf(r.ax, r.bx), r.cx), fmaxf(fmaxf(r.ax, r.bx), r.cx),
+                         fminf(fminf(r.ay, r.by), r.cy), fmaxf(fmaxf(r.ay, r.by), r.cy), FULL);
+            },
+            [&](int j, int pl) -> float {
+                const FaceRec r = slot_rec(ws, j);
+                Bary b;
+                bary_eval(r, pix_x(bx + (pl & 7), p.W, p.sx), pix_y(by + (pl >> 3), p.H, p.sy), p.eps, b);
+                if (b.w0 < 0.0f || b.w1 < 0.0f || b.w2 < 0.0f) return -INFINITY;
+                return ADD(ADD(MUL(b.w0, r.az), MUL(b.w1, r.bz)), MUL(b.w2, r.cz));
+            },
+            [&](int j, float zz) {
+                if (!(zz <= best_z)) { best_z = zz; bf = (int)ws->fid[j]; }
+            });
     });
+    best_f = bf; bw0 = bw1 = bw2 = 0.0f;
+    if (bf >= 0) {
+        const FaceRec r = load_rec(c.rec, bf);
+        Bary b;
+        bary_eval(r, x0, y0, p.eps, b);
+        bw0 = b.w0; bw1 = b.w1; bw2 = b.w2;
+    }
 }
 
-// Soft pass phase A: per-lane candidate list (first knum faces, in index order, whose enlarged bbox holds the pixel)
-__device__ __forceinline__ int soft_collect(const mm_raster_params& p, const CtaCtx& c, int lane, bool need, float x0, float y0)
+// Soft pass skeleton shared by forward and backward (DIBR_SPEC A.4/A.5): all faces (no back-face test), bbox
+// enlarged by blen, first knum candidates per pixel in face order.  `need` = pixels that take part.
+template <typename EvalFn, typename ScanFn, typename EndFn>
+__device__ __forceinline__ void soft_pass(const mm_raster_params& p, const CtaCtx& c, int lane, uint32_t need,
+                                          EvalFn eval, ScanFn scan, EndFn end)
 {
-    int cnt = 0;
-    uint16_t* mine = c.slist + threadIdx.x;
-    for_each_face(c.mS, p.nwords, lane, [&](int f) {
-        const FaceRec r = load_rec(c.rec, f);
-        if (need && cnt < p.knum && soft_bbox_test(r, x0, y0, p.blen)) {
-            mine[cnt * MM_THREADS] = (uint16_t)f;
-            ++cnt;
-        }
+    WarpScratch* ws = c.ws;
+    ws->hit[lane] = 0u; ws->cnt[lane] = 0u;
+    __syncwarp();
+    for_each_batch(c.mS, p.nwords, lane, ws->fq, [&](int f) {
+        const long long t0 = p.prof ? clock64() : 0;
+        const int total = pair_batch(p, ws, lane, f, p.knum,
+            [&](int ff) {
+                if (ff < 0) return;
+                const FaceRec r = load_rec(c.rec, ff);
+                mark_box(p, c, lane, r, SUB(fminf(fminf(r.ax, r.bx), r.cx), p.blen), ADD(fmaxf(fmaxf(r.ax, r.bx), r.cx), p.blen),
+                         SUB(fminf(fminf(r.ay, r.by), r.cy), p.blen), ADD(fmaxf(fmaxf(r.ay, r.by), r.cy), p.blen), need);
+            },
+            eval, scan);
+        if (p.prof && lane == 0) { ws->dbg[1] += clock64() - t0; ws->dbg[3] += total; }
+        end(f);
+        __syncwarp();
     });
-    return cnt;
 }
 
 // ---------------------------------------------------------------------------------------------- forward
 template <bool WITH_LOSS>
-__global__ void __launch_bounds__(MM_THREADS)
+__global__ void __launch_bounds__(MM_RTHREADS, MM_RMINB)
 k_raster_fwd(const mm_raster_params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ float s_lights[16];
-    __shared__ float s_red[MM_WARPS];
+    __shared__ float s_red[MM_RWARPS];
     CtaCtx c;
     cta_prologue(p, smem, s_lights, s_red, c);
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const size_t HW = (size_t)p.H * p.W;
     float acc_l1 = 0.0f, acc_n = 0.0f, acc_d = 0.0f;
+    const long long t_start = p.prof ? clock64() : 0;
 
     if (c.st_valid) {
         const float x0 = pix_x(c.ix, p.W, p.sx), y0 = pix_y(c.iy, p.H, p.sy);
         int best_f = -1;
         float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, soft = 0.0f;
+        if (p.prof && lane == 0) { c.ws->dbg[0] = 0; c.ws->dbg[1] = 0; c.ws->dbg[2] = 0; c.ws->dbg[3] = 0; }
         if (!mask_empty(c.mS, p.nwords, lane)) {
+            const long long th = p.prof ? clock64() : 0;
             hard_pass(p, c, lane, x0, y0, best_f, w0, w1, w2);
-            const bool need_soft = c.active && (best_f < 0);
-            if (__any_sync(FULL, need_soft)) {
-                const int cnt = soft_collect(p, c, lane, need_soft, x0, y0);
+            if (p.prof && lane == 0) c.ws->dbg[0] = clock64() - th;
+            const uint32_t need = __ballot_sync(FULL, c.active && (best_f < 0));
+            if (need) {
+                const float kz = p.sigmainv / p.multiplier / p.multiplier;
+                const int bx = c.stx * MM_ST_W, by = c.sty * MM_ST_H;
                 float allprob = 1.0f;
-                const uint16_t* mine = c.slist + threadIdx.x;
-                for (int k = 0; k < cnt; ++k) {
-                    const FaceRec r = load_rec(c.rec, (int)mine[k * MM_THREADS]);
-                    int type;
-                    const float d2 = soft_d2(r, x0, y0, p.multiplier, type);
-                    allprob = allprob * (1.0f - soft_prob(d2, p.sigmainv, p.multiplier));
-                }
+                soft_pass(p, c, lane, need,
+                          [&](int j, int pl) -> float {
+                              int type;
+                              const FaceRec r = slot_rec(c.ws, j);
+                              const float d2 = soft_d2_fast(r, pix_x(bx + (pl & 7), p.W, p.sx), pix_y(by + (pl >> 3), p.H, p.sy),
+                                                            p.multiplier, type);
+                              return soft_prob_fast(d2, kz);
+                          },
+                          [&](int, float prob) { allprob = allprob * (1.0f - prob); },      // the reference's ordered product
+                          [&](int) {});
                 soft = 1.0f - allprob;
             }
             if (best_f >= 0) soft = 1.0f;
@@ -232,27 +470,28 @@ k_raster_fwd(const mm_raster_params p)
             }
         }
     }
+    if (p.prof && c.st_valid && lane == 0) {
+        long long* pr = p.prof + ((size_t)b * p.nst + c.st) * 8;
+        int ns = 0, nh = 0;
+        for (int i = 0; i < p.nwords; ++i) { ns += __popc(c.mS[i]); nh += __popc(c.mH[i]); }
+        pr[0] = clock64() - t_start; pr[2] = ns; pr[3] = nh;
+        pr[4] = c.ws->dbg[0]; pr[5] = c.ws->dbg[1]; pr[6] = 0; pr[7] = c.ws->dbg[3];
+    }
     if (WITH_LOSS) {
-        const float s0 = block_sum(acc_l1, c.red);
-        const float s1 = block_sum(acc_n, c.red);
-        const float s2 = block_sum(acc_d, c.red);
-        if (threadIdx.x == 0) {
-            float* pf = p.part_fwd + ((size_t)b * p.nparts + blockIdx.x) * 4;
-            pf[0] = s0; pf[1] = s1; pf[2] = s2; pf[3] = 0.0f;
-        }
+        const float v[4] = {rblock_sum(acc_l1, c.red), rblock_sum(acc_n, c.red), rblock_sum(acc_d, c.red), 0.0f};
+        image_reduce_last<4>(v, p.part_fwd + (size_t)b * p.nparts * 4, 4, p.nparts, p.tickets + b * 2, p.img_fwd + b * 4, lane);
     }
 }
 
 // ---------------------------------------------------------------------------------------------- backward
 __device__ __forceinline__ float contour_c(float m, float mref) { return fabsf(m - mref); }
 
-__global__ void __launch_bounds__(MM_THREADS)
+__global__ void __launch_bounds__(MM_RTHREADS, MM_RMINB)
 k_raster_bwd(const mm_raster_params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ float s_lights[16];
-    __shared__ float s_red[MM_WARPS];
-    __shared__ float s_iou[2];
+    __shared__ float s_red[MM_RWARPS];
     CtaCtx c;
     cta_prologue(p, smem, s_lights, s_red, c);
     const int b = blockIdx.y, lane = threadIdx.x & 31;
@@ -265,31 +504,20 @@ k_raster_bwd(const mm_raster_params p)
     const int32_t* collo = p.tab + 3 * H + W;
     const int32_t* colhi = p.tab + 3 * H + 2 * W;
 
+    const long long t_start = p.prof ? clock64() : 0;
     float acc_contour = 0.0f;
     float acc_l[9];
     #pragma unroll
     for (int i = 0; i < 9; ++i) acc_l[i] = 0.0f;
 
-    // loss-gradient constants; the per-image IoU sums are re-derived from the forward partials in a fixed
-    // order by warp 0 (every CTA of the image gets bit-identical sums)
+    // loss-gradient constants; the per-image IoU sums were reduced by the forward kernel (fixed order)
     float k_img = 0.0f, k_iou = 0.0f, k_cont = 0.0f, Nb = 0.0f, De = 1.0f;
     if (p.analytic_loss) {
-        if (threadIdx.x < 32) {
-            float n = 0.0f, d = 0.0f;
-            for (int k = lane; k < p.nparts; k += 32) {
-                n += p.part_fwd_in[((size_t)b * p.nparts + k) * 4 + 1];
-                d += p.part_fwd_in[((size_t)b * p.nparts + k) * 4 + 2];
-            }
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { n += __shfl_xor_sync(FULL, n, o); d += __shfl_xor_sync(FULL, d, o); }
-            if (lane == 0) { s_iou[0] = n; s_iou[1] = d; }
-        }
-        __syncthreads();
         k_img = p.loss_scale * p.image_weight / ((float)p.B * 3.0f * (float)HW);
         k_iou = p.loss_scale / (float)p.B;
         k_cont = p.loss_scale * p.contour / ((float)p.B * (float)HW);
-        Nb = s_iou[0];
-        De = s_iou[1] + 1e-10f;
+        Nb = p.img_fwd[b * 4 + 1];
+        De = p.img_fwd[b * 4 + 2] + 1e-10f;
     }
     const float* rg = p.rgba + (size_t)b * 4 * HW;         // forward output (silhouette re-read)
     const float* gtb = p.gt ? p.gt + (size_t)b * 4 * HW : nullptr;
@@ -338,47 +566,63 @@ k_raster_bwd(const mm_raster_params p)
             }
         }
 
-        // ---- soft silhouette backward (DIBR_SPEC A.5): uncovered pixels only
-        const bool need_soft = active && (best_f == -1) && (g_soft != 0.0f) && (soft > 0.0f);
-        if (__any_sync(FULL, need_soft)) {
-            const int cnt = soft_collect(p, c, lane, need_soft, x0, y0);
-            const float one_m_all = 1.0f - soft;
-            const uint16_t* mine = c.slist + threadIdx.x;
-            for (int k = 0; k < cnt; ++k) {
-                const int f = (int)mine[k * MM_THREADS];
-                const FaceRec r = load_rec(c.rec, f);
-                int type;
-                const float d2s = soft_d2(r, x0, y0, p.multiplier, type);
-                const float prob = soft_prob(d2s, p.sigmainv, p.multiplier);
-                // dLdz = -sigmainv * dLdp * (1-allprob) / (1-prob+1e-6) * prob
-                const float dLdz = MUL(DIV(MUL(MUL(MUL(-1.0f, p.sigmainv), g_soft), one_m_all),
-                                           ADD(SUB(1.0f, prob), 1e-6f)), prob);
-                float* g = gacc + (size_t)f * 9;
-                if (type >= 3) {
-                    const int i = type - 3;
-                    const float x1 = (i == 0) ? r.ax : ((i == 1) ? r.bx : r.cx);
-                    const float y1 = (i == 0) ? r.ay : ((i == 1) ? r.by : r.cy);
-                    atomicAdd(g + 2 * i,     DIV(MUL(MUL(dLdz, 2.0f), SUB(x1, x0)), p.multiplier));
-                    atomicAdd(g + 2 * i + 1, DIV(MUL(MUL(dLdz, 2.0f), SUB(y1, y0)), p.multiplier));
-                } else {
-                    const int i = type, j = (type + 1) % 3;
-                    const float x1 = (i == 0) ? r.ax : ((i == 1) ? r.bx : r.cx);
-                    const float y1 = (i == 0) ? r.ay : ((i == 1) ? r.by : r.cy);
-                    const float x2 = (j == 0) ? r.ax : ((j == 1) ? r.bx : r.cx);
-                    const float y2 = (j == 0) ? r.ay : ((j == 1) ? r.by : r.cy);
-                    const float A = SUB(y2, y1), Bc = SUB(x1, x2), C = SUB(MUL(x2, y1), MUL(x1, y2));
-                    const float up = ADD(ADD(MUL(A, x0), MUL(Bc, y0)), C);
-                    const float dn = ADD(ADD(MUL(A, A), MUL(Bc, Bc)), 1e-10f);
-                    const float d2 = DIV(MUL(up, up), dn);
-                    const float dzdA = DIV(MUL(2.0f, SUB(MUL(x0, up), MUL(d2, A))), dn);
-                    const float dzdB = DIV(MUL(2.0f, SUB(MUL(y0, up), MUL(d2, Bc))), dn);
-                    const float dzdC = DIV(MUL(2.0f, up), dn);
-                    atomicAdd(g + 2 * i,     DIV(MUL(dLdz, SUB(dzdB, MUL(y2, dzdC))), p.multiplier));
-                    atomicAdd(g + 2 * i + 1, DIV(MUL(dLdz, SUB(MUL(x2, dzdC), dzdA)), p.multiplier));
-                    atomicAdd(g + 2 * j,     DIV(MUL(dLdz, SUB(MUL(y1, dzdC), dzdB)), p.multiplier));
-                    atomicAdd(g + 2 * j + 1, DIV(MUL(dLdz, SUB(dzdA, MUL(x1, dzdC))), p.multiplier));
-                }
-            }
+        // ---- soft silhouette backward (DIBR_SPEC A.5): uncovered pixels only; face-parallel, so each lane owns ONE
+        // face per batch and accumulates that face's 6 corner gradients in registers -> 6 atomics per (face, sub-tile)
+        const uint32_t need = __ballot_sync(FULL, active && (best_f == -1) && (g_soft != 0.0f) && (soft > 0.0f));
+        if (need) {
+            c.ws->gs[lane] = g_soft;
+            c.ws->oma[lane] = 1.0f - soft;
+            #pragma unroll
+            for (int k = 0; k < 6; ++k) c.ws->facc[k][lane] = 0.0f;
+            const float kz = p.sigmainv / p.multiplier / p.multiplier;
+            const float inv_mult = 1.0f / p.multiplier;
+            const int bx = c.stx * MM_ST_W, by = c.sty * MM_ST_H;
+            soft_pass(p, c, lane, need,
+                      [&](int j, int pl) -> float {
+                          int type;
+                          const FaceRec r = slot_rec(c.ws, j);
+                          const float px = pix_x(bx + (pl & 7), W, p.sx), py = pix_y(by + (pl >> 3), H, p.sy);
+                          const float d2s = soft_d2_fast(r, px, py, p.multiplier, type);
+                          const float prob = soft_prob_fast(d2s, kz);
+                          // dLdz = -sigmainv * dLdp * (1-allprob) / (1-prob+1e-6) * prob   (DIBR_SPEC A.5)
+                          const float dLdz = __fdividef(-p.sigmainv * c.ws->gs[pl] * c.ws->oma[pl], (1.0f - prob) + 1e-6f) * prob * inv_mult;
+                          if (type >= 3) {
+                              const int i = type - 3;
+                              const float x1 = (i == 0) ? r.ax : ((i == 1) ? r.bx : r.cx);
+                              const float y1 = (i == 0) ? r.ay : ((i == 1) ? r.by : r.cy);
+                              atomicAdd(&c.ws->facc[2 * i][j], dLdz * 2.0f * (x1 - px));
+                              atomicAdd(&c.ws->facc[2 * i + 1][j], dLdz * 2.0f * (y1 - py));
+                          } else {
+                              const int i = type, i2 = (type == 2) ? 0 : type + 1;
+                              const float x1 = (i == 0) ? r.ax : ((i == 1) ? r.bx : r.cx);
+                              const float y1 = (i == 0) ? r.ay : ((i == 1) ? r.by : r.cy);
+                              const float x2 = (i2 == 0) ? r.ax : ((i2 == 1) ? r.bx : r.cx);
+                              const float y2 = (i2 == 0) ? r.ay : ((i2 == 1) ? r.by : r.cy);
+                              const float A = SUB(y2, y1), Bc = SUB(x1, x2), C = SUB(MUL(x2, y1), MUL(x1, y2));
+                              const float up = ADD(ADD(MUL(A, px), MUL(Bc, py)), C);
+                              const float rdn = __fdividef(1.0f, ADD(ADD(MUL(A, A), MUL(Bc, Bc)), 1e-10f));
+                              const float d2 = up * up * rdn;
+                              const float dzdA = 2.0f * (px * up - d2 * A) * rdn;
+                              const float dzdB = 2.0f * (py * up - d2 * Bc) * rdn;
+                              const float dzdC = 2.0f * up * rdn;
+                              atomicAdd(&c.ws->facc[2 * i][j], dLdz * (dzdB - y2 * dzdC));
+                              atomicAdd(&c.ws->facc[2 * i + 1][j], dLdz * (x2 * dzdC - dzdA));
+                              atomicAdd(&c.ws->facc[2 * i2][j], dLdz * (y1 * dzdC - dzdB));
+                              atomicAdd(&c.ws->facc[2 * i2 + 1][j], dLdz * (dzdA - x1 * dzdC));
+                          }
+                          return 0.0f;
+                      },
+                      [&](int, float) {},
+                      [&](int f) {
+                          if (f >= 0) {
+                              float* g = gacc + (size_t)f * 9;
+                              #pragma unroll
+                              for (int k = 0; k < 6; ++k) {
+                                  const float v = c.ws->facc[k][lane];
+                                  if (v != 0.0f) { atomicAdd(g + k, v); c.ws->facc[k][lane] = 0.0f; }
+                              }
+                          }
+                      });
         }
 
         if (active) {
@@ -504,17 +748,13 @@ k_raster_bwd(const mm_raster_params p)
         }
     }
 
-    // ---- per-CTA partials: contour sum + 9 light gradients (summed deterministically later)
-    float* pb = p.part_bwd + ((size_t)b * p.nparts + blockIdx.x) * 12;
-    {
-        const float s = block_sum(acc_contour, c.red);
-        if (threadIdx.x == 0) pb[0] = s;
-    }
+    if (p.prof && c.st_valid && lane == 0) p.prof[((size_t)b * p.nst + c.st) * 8 + 1] = clock64() - t_start;
+    // ---- per-CTA partials: contour sum + 9 light gradients, reduced per image by the last CTA (fixed order)
+    float v[10];
+    v[0] = rblock_sum(acc_contour, c.red);
     #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        const float s = block_sum(acc_l[i], c.red);
-        if (threadIdx.x == 0) pb[1 + i] = s;
-    }
+    for (int i = 0; i < 9; ++i) v[1 + i] = rblock_sum(acc_l[i], c.red);
+    image_reduce_last<10>(v, p.part_bwd + (size_t)b * p.nparts * 12, 12, p.nparts, p.tickets + b * 2 + 1, p.img_bwd + b * 12, lane);
 }
 
 }  // namespace
@@ -534,12 +774,12 @@ void mm_launch_raster_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_
 {
     const dim3 grid(c->nparts, p.B);
     const size_t smem = raster_smem(c->nwords, c->knum);
-    if (with_loss) k_raster_fwd<true><<<grid, MM_THREADS, smem, s>>>(p);
-    else           k_raster_fwd<false><<<grid, MM_THREADS, smem, s>>>(p);
+    if (with_loss) k_raster_fwd<true><<<grid, MM_RTHREADS, smem, s>>>(p);
+    else           k_raster_fwd<false><<<grid, MM_RTHREADS, smem, s>>>(p);
 }
 
 void mm_launch_raster_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
     const dim3 grid(c->nparts, p.B);
-    k_raster_bwd<<<grid, MM_THREADS, raster_smem(c->nwords, c->knum), s>>>(p);
+    k_raster_bwd<<<grid, MM_RTHREADS, raster_smem(c->nwords, c->knum), s>>>(p);
 }

@@ -73,7 +73,8 @@ k_vertex_fwd(const VertexFwdParams q,
              const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
              const float* __restrict__ bias,
              float* __restrict__ frec, uint32_t* __restrict__ maskS, uint32_t* __restrict__ maskH,
-             float* __restrict__ vimg, float* __restrict__ face_normals, float* __restrict__ gfacc_zero)
+             float* __restrict__ vimg, float* __restrict__ face_normals, float* __restrict__ gfacc_zero,
+             uint32_t* __restrict__ tickets)
 {
     extern __shared__ float sm[];
     const int V = q.V, F = q.F;
@@ -90,6 +91,7 @@ k_vertex_fwd(const VertexFwdParams q,
         Cam c;
         camera_setup(azim[b], elev[b], dist[b], bias[b * 2], bias[b * 2 + 1], c);
         for (int i = 0; i < 12; ++i) sT[i] = c.T[i];
+        if (chunk == 0) { tickets[b * 2] = 0u; tickets[b * 2 + 1] = 0u; }
     }
     for (int i = threadIdx.x; i < nmask; i += blockDim.x) { smS[i] = 0u; smH[i] = 0u; }
     __syncthreads();
@@ -193,12 +195,12 @@ __device__ inline float block_sum_256(float v, float* red /* >= 8 floats */) {
 }
 
 __global__ void __launch_bounds__(256)
-k_vertex_bwd(int V, int F, int nparts, float proj_x, float proj_y,
+k_vertex_bwd(int V, int F, float proj_x, float proj_y,
              const int32_t* __restrict__ faces, const float* __restrict__ vertices,
              const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
              const float* __restrict__ bias,
              const float* __restrict__ gfacc, const float* __restrict__ g_face_normals,
-             const float* __restrict__ part_bwd,
+             const float* __restrict__ img_bwd,
              float* __restrict__ g_vertices, float* __restrict__ g_azim, float* __restrict__ g_elev,
              float* __restrict__ g_dist, float* __restrict__ g_bias, float* __restrict__ g_lights)
 {
@@ -327,12 +329,8 @@ k_vertex_bwd(int V, int F, int nparts, float proj_x, float proj_y,
         g_elev[b] = k * (gcam[0] * (-sc.d * sc.se * sc.sa) + gcam[1] * (sc.d * sc.ce) + gcam[2] * (-sc.d * sc.se * sc.ca));
         g_azim[b] = k * (gcam[0] * (sc.d * sc.ce * sc.ca) + gcam[2] * (-sc.d * sc.ce * sc.sa));
     }
-    // (4) light gradient: deterministic sum of the per-CTA partials of the raster backward
-    if (threadIdx.x < 9) {
-        float s = 0.0f;
-        for (int k = 0; k < nparts; ++k) s += part_bwd[((size_t)b * nparts + k) * 12 + 1 + threadIdx.x];
-        g_lights[b * 9 + threadIdx.x] = s;
-    }
+    // (4) light gradient: per-image sums already reduced (fixed order) by the raster backward
+    if (threadIdx.x < 9) g_lights[b * 9 + threadIdx.x] = img_bwd[b * 12 + 1 + threadIdx.x];
 }
 
 __global__ void k_export_faces(int V, int F, float multiplier, const int32_t* __restrict__ faces,
@@ -358,7 +356,7 @@ __global__ void k_export_faces(int V, int F, float multiplier, const int32_t* __
 
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec, uint32_t* maskS, uint32_t* maskH,
-                          float* vimg, float* face_normals, float* gfacc_zero, cudaStream_t s)
+                          float* vimg, float* face_normals, float* gfacc_zero, uint32_t* tickets, cudaStream_t s)
 {
     VertexFwdParams q;
     q.V = c->V; q.F = c->F; q.H = c->H; q.W = c->W; q.nstx = c->nstx; q.nsty = c->nsty; q.nwords = c->nwords;
@@ -366,17 +364,17 @@ void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const f
     q.proj_x = c->proj_x; q.proj_y = c->proj_y; q.multiplier = c->multiplier; q.sx = c->sx; q.sy = c->sy; q.blen = c->blen;
     const dim3 grid(c->nchunks, B);
     k_vertex_fwd<<<grid, 256, c->smem_vertex_fwd, s>>>(q, c->d_faces, vertices, azim, elev, dist, bias, frec, maskS,
-                                                       maskH, vimg, face_normals, gfacc_zero);
+                                                       maskH, vimg, face_normals, gfacc_zero, tickets);
 }
 
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,
-                          const float* part_bwd, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
+                          const float* img_bwd, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
                           float* g_bias, float* g_lights, cudaStream_t s)
 {
     const size_t smem = ((size_t)c->V * 6) * sizeof(float);
-    k_vertex_bwd<<<B, 256, smem, s>>>(c->V, c->F, c->nparts, c->proj_x, c->proj_y, c->d_faces, vertices, azim, elev,
-                                      dist, bias, gfacc, g_face_normals, part_bwd, g_vertices, g_azim, g_elev,
+    k_vertex_bwd<<<B, 256, smem, s>>>(c->V, c->F, c->proj_x, c->proj_y, c->d_faces, vertices, azim, elev,
+                                      dist, bias, gfacc, g_face_normals, img_bwd, g_vertices, g_azim, g_elev,
                                       g_dist, g_bias, g_lights);
 }
 

@@ -3,7 +3,9 @@ usage: python tools/quick_bench.py [steps]"""
 import ctypes, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+t00 = time.time()
 import torch
+print('import torch %.1fs' % (time.time() - t00), flush=True)
 import __graft_entry__ as g
 import bench
 mm = g.load_package()
@@ -15,9 +17,11 @@ for c in (dict(mesh="ellipsoid", B=4, image_size=128, no_mask=True, contour=0.1,
     keys = ["face_idx_mismatch_staged", "face_idx_mismatch_e2e", "soft_staged_max_abs_err", "rgba_staged_max_abs_err",
             "loss_rel_err", "grad_vertices_rel_err", "grad_textures_rel_err", "grad_azimuths_rel_err", "grad_lights_rel_err"]
     print("parity", c["mesh"], {k: (r[k] if isinstance(r[k], int) else float("%.3g" % r[k])) for k in keys}, flush=True)
+print('parity done %.1fs' % (time.time() - t00), flush=True)
 dev = "cuda:0"
 dr, sets = bench.build_workload(mm, dev, 0)
 fr = bench.FusedRunner(mm, dr, sets, dev)
+print('workload built %.1fs' % (time.time() - t00), flush=True)
 for i in range(10): fr.step(i)
 ms = bench.timed(torch, 1, fr.step, steps) / steps
 L = mm.lib(); h = fr.h.handle
