@@ -31,6 +31,9 @@
 
 #define MM_THREADS      256          // threads per CTA of the loss / vertex kernels
 #define MM_WARPS        (MM_THREADS / 32)
+#ifndef MM_VTHREADS
+#define MM_VTHREADS     512          // threads per CTA of the vertex-stage kernels
+#endif
 #ifndef MM_RWARPS
 #define MM_RWARPS       1            // raster kernels: warps (= sub-tiles) per CTA.  1 => the hardware CTA scheduler
 #endif                               // balances sub-tiles individually (heavy silhouette tiles never park idle warps)

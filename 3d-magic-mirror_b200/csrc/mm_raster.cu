@@ -534,7 +534,8 @@ k_raster_bwd(const mm_raster_params p)
         const int best_f = active ? p.face_idx_ws[(size_t)b * HW + pix] : -2;   // -2: inactive lane
         // ---- upstream gradient of the 4 output channels
         float g_img[3] = {0.0f, 0.0f, 0.0f}, g_soft = 0.0f;
-        float soft = 0.0f;
+        float soft = 0.0f, gm_lane = 0.0f;
+        const bool fast4 = ((H & 3) == 0) && ((W & 3) == 0);
         if (active) {
             soft = rg[3 * HW + pix];
             if (gup) { g_img[0] = gup[pix]; g_img[1] = gup[HW + pix]; g_img[2] = gup[2 * HW + pix]; g_soft = gup[3 * HW + pix]; }
@@ -545,7 +546,7 @@ k_raster_bwd(const mm_raster_params p)
                     g_img[ch] += k_img * sgnf(l1_term(rg[ch * HW + pix], __ldg(gtb + ch * HW + pix), gm)) * gm;
                 // soft IoU: -(1/B) * (gm*De - Nb*(1-gm)) / De^2
                 g_soft += -k_iou * (gm * De - Nb * (1.0f - gm)) / (De * De);
-                if (p.contour > 0.0f) {
+                if (p.contour > 0.0f && !fast4) {
                     const int ry = refrow[iy], rx = refcol[ix];
                     const size_t rp = (size_t)ry * W + rx;
                     const float mref = rg[3 * HW + rp], gref = __ldg(gtb + 3 * HW + rp);
@@ -563,7 +564,22 @@ k_raster_bwd(const mm_raster_params p)
                         }
                     g_soft += k_cont * gc;
                 }
+                gm_lane = gm;
             }
+        }
+        // contour term, fast path: H and W are multiples of 4, so the 8x4 sub-tile holds two complete 4x4 contour
+        // blocks (lanes with lx < 4 / lx >= 4) whose reference pixels are lanes 0 and 4: everything is exchanged
+        // with shuffles instead of 2 + 32 dependent global loads per reference pixel.
+        if (p.analytic_loss && p.contour > 0.0f && fast4) {
+            const int ref_lane = lane & 4;
+            const float mref = __shfl_sync(FULL, soft, ref_lane), gref = __shfl_sync(FULL, gm_lane, ref_lane);
+            const float dlt = active ? contour_c(soft, mref) - contour_c(gm_lane, gref) : 0.0f;
+            acc_contour += dlt * dlt;
+            const float own = 2.0f * dlt * sgnf(soft - mref);
+            float t = -own;                                     // what this pixel contributes to its reference pixel
+            t += __shfl_xor_sync(FULL, t, 1); t += __shfl_xor_sync(FULL, t, 2);
+            t += __shfl_xor_sync(FULL, t, 8); t += __shfl_xor_sync(FULL, t, 16);
+            if (active) g_soft += k_cont * (own + ((lane == ref_lane) ? t : 0.0f));
         }
 
         // ---- soft silhouette backward (DIBR_SPEC A.5): uncovered pixels only; face-parallel, so each lane owns ONE

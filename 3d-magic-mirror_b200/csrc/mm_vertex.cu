@@ -67,7 +67,7 @@ struct VertexFwdParams {
     float proj_x, proj_y, multiplier, sx, sy, blen;
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(MM_VTHREADS)
 k_vertex_fwd(const VertexFwdParams q,
              const int32_t* __restrict__ faces, const float* __restrict__ vertices,
              const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
@@ -182,7 +182,7 @@ k_vertex_fwd(const VertexFwdParams q,
 }
 
 // ------------------------------------------------------------------ backward
-__device__ inline float block_sum_256(float v, float* red /* >= 8 floats */) {
+__device__ inline float block_sum_v(float v, float* red /* >= MM_VTHREADS/32 floats */) {
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
@@ -190,11 +190,11 @@ __device__ inline float block_sum_256(float v, float* red /* >= 8 floats */) {
     __syncthreads();
     float r = 0.0f;
     #pragma unroll
-    for (int i = 0; i < 8; ++i) r += red[i];
+    for (int i = 0; i < MM_VTHREADS / 32; ++i) r += red[i];
     return r;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(MM_VTHREADS)
 k_vertex_bwd(int V, int F, float proj_x, float proj_y,
              const int32_t* __restrict__ faces, const float* __restrict__ vertices,
              const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
@@ -206,7 +206,7 @@ k_vertex_bwd(int V, int F, float proj_x, float proj_y,
 {
     extern __shared__ float sm[];
     __shared__ Cam sc;
-    __shared__ float red[8];
+    __shared__ float red[MM_VTHREADS / 32];
     __shared__ float sacc[12];
     float* svc = sm;                      // V*3 camera-space positions
     float* sgv = sm + (size_t)V * 3;      // V*3 gradient w.r.t. camera-space positions
@@ -288,7 +288,7 @@ k_vertex_bwd(int V, int F, float proj_x, float proj_y,
     }
     #pragma unroll
     for (int i = 0; i < 12; ++i) {
-        const float r = block_sum_256(acc[i], red);
+        const float r = block_sum_v(acc[i], red);
         if (threadIdx.x == 0) sacc[i] = r;
     }
     __syncthreads();
@@ -363,7 +363,7 @@ void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const f
     q.chunk_rows = c->chunk_rows; q.nchunks = c->nchunks;
     q.proj_x = c->proj_x; q.proj_y = c->proj_y; q.multiplier = c->multiplier; q.sx = c->sx; q.sy = c->sy; q.blen = c->blen;
     const dim3 grid(c->nchunks, B);
-    k_vertex_fwd<<<grid, 256, c->smem_vertex_fwd, s>>>(q, c->d_faces, vertices, azim, elev, dist, bias, frec, maskS,
+    k_vertex_fwd<<<grid, MM_VTHREADS, c->smem_vertex_fwd, s>>>(q, c->d_faces, vertices, azim, elev, dist, bias, frec, maskS,
                                                        maskH, vimg, face_normals, gfacc_zero, tickets);
 }
 
@@ -373,7 +373,7 @@ void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const f
                           float* g_bias, float* g_lights, cudaStream_t s)
 {
     const size_t smem = ((size_t)c->V * 6) * sizeof(float);
-    k_vertex_bwd<<<B, 256, smem, s>>>(c->V, c->F, c->proj_x, c->proj_y, c->d_faces, vertices, azim, elev,
+    k_vertex_bwd<<<B, MM_VTHREADS, smem, s>>>(c->V, c->F, c->proj_x, c->proj_y, c->d_faces, vertices, azim, elev,
                                       dist, bias, gfacc, g_face_normals, img_bwd, g_vertices, g_azim, g_elev,
                                       g_dist, g_bias, g_lights);
 }
