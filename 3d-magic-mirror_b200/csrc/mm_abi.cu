@@ -65,7 +65,7 @@ int check_launch(const char* what) {
 void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int no_mask, mm_raster_params& p) {
     memset(&p, 0, sizeof(p));
     p.B = B; p.V = c->V; p.F = c->F; p.H = c->H; p.W = c->W; p.Ht = Ht; p.Wt = Wt;
-    p.nstx = c->nstx; p.nsty = c->nsty; p.nst = c->nst; p.nparts = c->nparts; p.nwords = c->nwords; p.knum = c->knum;
+    p.nstx = c->nstx; p.nsty = c->nsty; p.nst = c->nst; p.nwords = c->nwords; p.knum = c->knum;
     p.sx = c->sx; p.sy = c->sy; p.blen = c->blen; p.multiplier = c->multiplier; p.eps = c->eps; p.sigmainv = c->sigmainv;
     p.no_mask = no_mask;
     p.face_uvs = c->d_face_uvs;
@@ -112,7 +112,6 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     c->nstx = (W + MM_ST_W - 1) / MM_ST_W;
     c->nsty = (H + MM_ST_H - 1) / MM_ST_H;
     c->nst = c->nstx * c->nsty;
-    c->nparts = (c->nst + MM_RWARPS - 1) / MM_RWARPS;
     c->nparts_recon = (H * W + 4095) / 4096 < 1 ? 1 : (H * W + 4095) / 4096;     // ~4096 pixels per recon CTA
     c->nwords = ((F + 31) / 32 + 3) & ~3;          // multiple of 4 words: mask rows stay 16-byte aligned for cp.async.bulk
     c->num_sms = prop.multiProcessorCount;

@@ -23,7 +23,7 @@
 //     part_bwd   [B,NP,12] per-CTA partials (contour sum, 9 light grads, -, -)
 //     img_fwd    [B,4]     per-image sums (L1, N, D, contour), reduced in a FIXED order by the last CTA of the image
 //     img_bwd    [B,12]    per-image sums (contour, 9 light grads), same scheme
-//     tickets    [B,2]     u32 arrival counters of the forward / backward raster CTAs (self-resetting)
+//     tickets    [B,4]     u32 {fwd work queue, bwd work queue, fwd arrivals, bwd arrivals} (self-resetting)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -57,7 +57,6 @@ struct mm_ctx {
     float blen;              // boxlen * multiplier
     int nstx, nsty;          // sub-tile grid = ceil(W / 8) x ceil(H / 4)
     int nst;                 // sub-tiles per image
-    int nparts;              // raster CTAs per image = ceil(nst / MM_RWARPS) (one warp per sub-tile); #partials of the fused path
     int nparts_recon;        // CTAs per image of the stand-alone recon_data kernels
     int nwords;              // bitmask words per sub-tile = ceil(F / 32)
     int chunk_rows, nchunks; // vertex stage: sub-tile rows binned per CTA, CTAs per image
@@ -80,6 +79,14 @@ struct mm_ws_layout {
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// persistent raster warps per image: enough single-warp CTAs to fill every SM ~24 deep, at most one per sub-tile
+static inline int mm_raster_parts(const mm_ctx* c, int B) {
+    int g = (c->num_sms * 24 + B - 1) / B;
+    if (g < 1) g = 1;
+    if (g > c->nst) g = c->nst;
+    return g;
+}
+
 static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     mm_ws_layout L;
     size_t off = 0;
@@ -89,12 +96,13 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     L.vimg = off;     off = mm_align_up(off + (size_t)B * c->V * 2 * 4, 256);
     L.face_idx = off; off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.gfacc = off;    off = mm_align_up(off + (size_t)B * c->F * 9 * 4, 256);
-    const size_t np = (size_t)(c->nparts > c->nparts_recon ? c->nparts : c->nparts_recon);
+    const int rp = mm_raster_parts(c, B);
+    const size_t np = (size_t)(rp > c->nparts_recon ? rp : c->nparts_recon);
     L.part_fwd = off; off = mm_align_up(off + (size_t)B * np * 4 * 4, 256);
     L.part_bwd = off; off = mm_align_up(off + (size_t)B * np * 12 * 4, 256);
     L.img_fwd = off;  off = mm_align_up(off + (size_t)B * 4 * 4, 256);
     L.img_bwd = off;  off = mm_align_up(off + (size_t)B * 12 * 4, 256);
-    L.tickets = off;  off = mm_align_up(off + (size_t)B * 2 * 4, 256);
+    L.tickets = off;  off = mm_align_up(off + (size_t)B * 4 * 4, 256);
     L.total = off;
     return L;
 }
@@ -102,7 +110,7 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
 // parameters shared by the raster kernels (passed by value)
 struct mm_raster_params {
     int B, V, F, H, W, Ht, Wt;
-    int nstx, nsty, nst, nparts, nwords, knum;
+    int nstx, nsty, nst, nwords, knum;
     float sx, sy, blen, multiplier, eps, sigmainv;
     int no_mask;
     const float* frec;       // [B,F,12]
@@ -121,7 +129,7 @@ struct mm_raster_params {
     float* part_fwd;         // [B,NP,4]
     float* img_fwd;          // [B,4]
     float* img_bwd;          // [B,12]
-    uint32_t* tickets;       // [B,2]
+    uint32_t* tickets;       // [B,4]
     // backward
     const float* g_rgba;     // [B,4,H,W] or NULL
     float image_weight, contour, loss_scale;

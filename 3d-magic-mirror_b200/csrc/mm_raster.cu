@@ -48,56 +48,93 @@ struct WarpScratch {
 };
 
 struct CtaCtx {
-    const uint32_t* mS;     // this warp's S mask row (shared memory)
-    const uint32_t* mH;     // this warp's H mask row (shared memory)
+    const uint32_t* mS;     // current sub-tile's S mask row (shared memory, TMA-staged)
+    const uint32_t* mH;     // current sub-tile's H mask row
     WarpScratch* ws;        // this warp's scratch
     float* lights;          // 9
-    float* red;             // MM_RWARPS
+    float* red;             // unused with single-warp CTAs
     const float* rec;       // face records of this image (global, read through L1)
     int st, stx, sty, ix, iy;
     bool st_valid, active;
+    // persistent-warp state
+    uint64_t* bar;          // two mbarriers (double-buffered mask rows)
+    uint32_t* buf;          // [2][2*nwords]
+    uint32_t* queue;        // this image's sub-tile work counter
+    int nxt, k;
+    uint32_t phase0, phase1;
 };
 
-// dynamic smem: | mbarrier 16 B | maskS 8*nwords*4 | maskH 8*nwords*4 | 8 x WarpScratch |
+// dynamic smem: | 2 mbarriers 16 B | 2 x (S row + H row) | WarpScratch |
 __host__ __device__ inline size_t raster_smem(int nwords, int knum) {
     (void)knum;
-    return 16 + 2 * (size_t)MM_RWARPS * nwords * 4 + MM_RWARPS * sizeof(WarpScratch);
+    return 16 + 4 * (size_t)nwords * 4 + sizeof(WarpScratch);
 }
 
-__device__ __forceinline__ void cta_prologue(const mm_raster_params& p, unsigned char* smem, float* s_lights, float* s_red,
-                                             CtaCtx& c)
-{
-    const int b = blockIdx.y, g = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    uint32_t* smS = reinterpret_cast<uint32_t*>(smem + 16);
-    uint32_t* smH = smS + MM_RWARPS * p.nwords;
-    c.ws = reinterpret_cast<WarpScratch*>(smH + MM_RWARPS * p.nwords) + warp;
-    c.lights = s_lights; c.red = s_red;
-    c.rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
-    const int st0 = g * MM_RWARPS;
-    const int nsub = min(MM_RWARPS, p.nst - st0);
-    if (threadIdx.x == 0) mbar_init(bar, 1);
-    if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)nsub * p.nwords * 4;
-        const size_t off = ((size_t)b * p.nst + st0) * p.nwords;
+// The raster kernels run PERSISTENT single-warp CTAs: grid = (G, B), the G warps of image b pull 8x4-pixel sub-tiles
+// from a per-image atomic work counter.  Silhouette tiles cost ~100x an empty tile, so static tile->warp assignment
+// would leave most warps idle; the counter balances them, and the per-tile fixed cost (barrier set-up, light
+// vector, loss partials, image-level reduction ticket) is paid once per warp instead of once per tile.
+// While a tile is being processed the NEXT tile's two bitmask rows ("tile face lists") are already in flight:
+// a TMA bulk copy (cp.async.bulk) into the other half of a double buffer, completion tracked by an mbarrier.
+__device__ __forceinline__ int fetch_tile(CtaCtx& c, int lane) {
+    int t = 0;
+    if (lane == 0) t = (int)atomicAdd(c.queue, 1u);
+    return __shfl_sync(FULL, t, 0);
+}
+
+__device__ __forceinline__ void issue_masks(const mm_raster_params& p, CtaCtx& c, int st, int k, int lane) {
+    if (lane == 0) {
+        const uint32_t bytes = (uint32_t)p.nwords * 4;
+        const size_t off = ((size_t)blockIdx.y * p.nst + st) * p.nwords;
+        uint64_t* bar = c.bar + k;
+        uint32_t* dst = c.buf + (size_t)k * 2 * p.nwords;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(2 * bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(smS)), "l"(p.maskS + off), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+                     ::"r"(smem_u32(dst)), "l"(p.maskS + off), "r"(bytes), "r"(smem_u32(bar)) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(smH)), "l"(p.maskH + off), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+                     ::"r"(smem_u32(dst + p.nwords)), "l"(p.maskH + off), "r"(bytes), "r"(smem_u32(bar)) : "memory");
     }
-    c.st = st0 + warp;
-    c.st_valid = c.st < p.nst;
+}
+
+__device__ __forceinline__ void warp_init(const mm_raster_params& p, unsigned char* smem, float* s_lights, float* s_red,
+                                          CtaCtx& c, int which /* 0 fwd, 1 bwd */)
+{
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    c.bar = reinterpret_cast<uint64_t*>(smem);
+    c.buf = reinterpret_cast<uint32_t*>(smem + 16);
+    c.ws = reinterpret_cast<WarpScratch*>(c.buf + 4 * p.nwords);
+    c.lights = s_lights; c.red = s_red;
+    c.rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
+    c.queue = p.tickets + b * 4 + which;
+    if (lane == 0) { mbar_init(c.bar, 1); mbar_init(c.bar + 1, 1); }
+    if (lane < 9) s_lights[lane] = p.lights[b * 9 + lane];
+    __syncwarp();
+    c.k = 0; c.phase0 = 0u; c.phase1 = 0u;
+    c.st = fetch_tile(c, lane);
+    if (c.st < p.nst) issue_masks(p, c, c.st, 0, lane);
+}
+
+// Called at the top of every loop iteration: prefetch the next tile's masks, wait for the current ones.
+__device__ __forceinline__ void tile_begin(const mm_raster_params& p, CtaCtx& c, int lane)
+{
+    c.nxt = fetch_tile(c, lane);
+    if (c.nxt < p.nst) issue_masks(p, c, c.nxt, c.k ^ 1, lane);
+    if (c.k == 0) { mbar_wait(c.bar, c.phase0); c.phase0 ^= 1u; }
+    else          { mbar_wait(c.bar + 1, c.phase1); c.phase1 ^= 1u; }
+    c.mS = c.buf + (size_t)c.k * 2 * p.nwords;
+    c.mH = c.mS + p.nwords;
+    c.st_valid = true;
     c.sty = c.st / p.nstx; c.stx = c.st - c.sty * p.nstx;
     c.ix = c.stx * MM_ST_W + (lane & 7);
     c.iy = c.sty * MM_ST_H + (lane >> 3);
-    c.active = c.st_valid && (c.ix < p.W) && (c.iy < p.H);
-    c.mS = smS + warp * p.nwords;
-    c.mH = smH + warp * p.nwords;
-    mbar_wait(bar, 0);
+    c.active = (c.ix < p.W) && (c.iy < p.H);
+}
+
+__device__ __forceinline__ void tile_end(CtaCtx& c)
+{
+    __syncwarp();
+    c.st = c.nxt;
+    c.k ^= 1;
 }
 
 // sum over the raster CTA (MM_RWARPS warps); a single-warp CTA needs no barrier at all
@@ -147,7 +184,8 @@ __device__ __forceinline__ bool image_reduce_last(const float (&v)[NV], float* p
         if (lane == 0) {
             #pragma unroll
             for (int i = 0; i < NV; ++i) out[i] = acc[i];
-            *ticket = 0u;
+            *ticket = 0u;            // arrival counter
+            *(ticket - 2) = 0u;      // this pass's work queue (tickets[b] = {fwd queue, bwd queue, fwd arrivals, bwd arrivals})
         }
     }
     return true;
@@ -378,13 +416,14 @@ k_raster_fwd(const mm_raster_params p)
     __shared__ float s_lights[16];
     __shared__ float s_red[MM_RWARPS];
     CtaCtx c;
-    cta_prologue(p, smem, s_lights, s_red, c);
     const int b = blockIdx.y, lane = threadIdx.x & 31;
+    warp_init(p, smem, s_lights, s_red, c, 0);
     const size_t HW = (size_t)p.H * p.W;
     float acc_l1 = 0.0f, acc_n = 0.0f, acc_d = 0.0f;
-    const long long t_start = p.prof ? clock64() : 0;
 
-    if (c.st_valid) {
+    while (c.st < p.nst) {
+        const long long t_start = p.prof ? clock64() : 0;
+        tile_begin(p, c, lane);
         const float x0 = pix_x(c.ix, p.W, p.sx), y0 = pix_y(c.iy, p.H, p.sy);
         int best_f = -1;
         float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, soft = 0.0f;
@@ -469,32 +508,33 @@ k_raster_fwd(const mm_raster_params p)
                 acc_d += (soft + gm) - mul;
             }
         }
-    }
-    if (p.prof && c.st_valid && lane == 0) {
-        long long* pr = p.prof + ((size_t)b * p.nst + c.st) * 8;
-        int ns = 0, nh = 0;
-        for (int i = 0; i < p.nwords; ++i) { ns += __popc(c.mS[i]); nh += __popc(c.mH[i]); }
-        pr[0] = clock64() - t_start; pr[2] = ns; pr[3] = nh;
-        pr[4] = c.ws->dbg[0]; pr[5] = c.ws->dbg[1]; pr[6] = 0; pr[7] = c.ws->dbg[3];
+        if (p.prof && lane == 0) {
+            long long* pr = p.prof + ((size_t)b * p.nst + c.st) * 8;
+            int ns = 0, nh = 0;
+            for (int i = 0; i < p.nwords; ++i) { ns += __popc(c.mS[i]); nh += __popc(c.mH[i]); }
+            pr[0] = clock64() - t_start; pr[2] = ns; pr[3] = nh;
+            pr[4] = c.ws->dbg[0]; pr[5] = c.ws->dbg[1]; pr[6] = 0; pr[7] = c.ws->dbg[3];
+        }
+        tile_end(c);
     }
     if (WITH_LOSS) {
         const float v[4] = {rblock_sum(acc_l1, c.red), rblock_sum(acc_n, c.red), rblock_sum(acc_d, c.red), 0.0f};
-        image_reduce_last<4>(v, p.part_fwd + (size_t)b * p.nparts * 4, 4, p.nparts, p.tickets + b * 2, p.img_fwd + b * 4, lane);
+        image_reduce_last<4>(v, p.part_fwd + (size_t)b * gridDim.x * 4, 4, gridDim.x, p.tickets + b * 4 + 2, p.img_fwd + b * 4, lane);
     }
 }
 
 // ---------------------------------------------------------------------------------------------- backward
 __device__ __forceinline__ float contour_c(float m, float mref) { return fabsf(m - mref); }
 
-__global__ void __launch_bounds__(MM_RTHREADS, MM_RMINB)
+__global__ void __launch_bounds__(MM_RTHREADS, 16)
 k_raster_bwd(const mm_raster_params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ float s_lights[16];
     __shared__ float s_red[MM_RWARPS];
     CtaCtx c;
-    cta_prologue(p, smem, s_lights, s_red, c);
     const int b = blockIdx.y, lane = threadIdx.x & 31;
+    warp_init(p, smem, s_lights, s_red, c, 1);
     const size_t HW = (size_t)p.H * p.W;
     const int H = p.H, W = p.W;
     const int32_t* refrow = p.tab;
@@ -504,7 +544,6 @@ k_raster_bwd(const mm_raster_params p)
     const int32_t* collo = p.tab + 3 * H + W;
     const int32_t* colhi = p.tab + 3 * H + 2 * W;
 
-    const long long t_start = p.prof ? clock64() : 0;
     float acc_contour = 0.0f;
     float acc_l[9];
     #pragma unroll
@@ -525,7 +564,9 @@ k_raster_bwd(const mm_raster_params p)
     float* gacc = p.gfacc + (size_t)b * p.F * 9;
     float* gtex = p.g_tex + (size_t)b * 3 * p.Ht * p.Wt;
 
-    if (c.st_valid) {
+    while (c.st < p.nst) {
+        const long long t_start = p.prof ? clock64() : 0;
+        tile_begin(p, c, lane);
         const int ix = c.ix, iy = c.iy;
         const bool active = c.active;
         const float x0 = pix_x(ix, W, p.sx), y0 = pix_y(iy, H, p.sy);
@@ -762,15 +803,16 @@ k_raster_bwd(const mm_raster_params p)
                 }
             }
         }
+        if (p.prof && lane == 0) p.prof[((size_t)b * p.nst + c.st) * 8 + 1] = clock64() - t_start;
+        tile_end(c);
     }
 
-    if (p.prof && c.st_valid && lane == 0) p.prof[((size_t)b * p.nst + c.st) * 8 + 1] = clock64() - t_start;
     // ---- per-CTA partials: contour sum + 9 light gradients, reduced per image by the last CTA (fixed order)
     float v[10];
     v[0] = rblock_sum(acc_contour, c.red);
     #pragma unroll
     for (int i = 0; i < 9; ++i) v[1 + i] = rblock_sum(acc_l[i], c.red);
-    image_reduce_last<10>(v, p.part_bwd + (size_t)b * p.nparts * 12, 12, p.nparts, p.tickets + b * 2 + 1, p.img_bwd + b * 12, lane);
+    image_reduce_last<10>(v, p.part_bwd + (size_t)b * gridDim.x * 12, 12, gridDim.x, p.tickets + b * 4 + 3, p.img_bwd + b * 12, lane);
 }
 
 }  // namespace
@@ -788,7 +830,7 @@ cudaError_t mm_raster_configure(const mm_ctx* c) {
 
 void mm_launch_raster_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_loss, cudaStream_t s)
 {
-    const dim3 grid(c->nparts, p.B);
+    const dim3 grid(mm_raster_parts(c, p.B), p.B);
     const size_t smem = raster_smem(c->nwords, c->knum);
     if (with_loss) k_raster_fwd<true><<<grid, MM_RTHREADS, smem, s>>>(p);
     else           k_raster_fwd<false><<<grid, MM_RTHREADS, smem, s>>>(p);
@@ -796,6 +838,6 @@ void mm_launch_raster_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_
 
 void mm_launch_raster_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
-    const dim3 grid(c->nparts, p.B);
+    const dim3 grid(mm_raster_parts(c, p.B), p.B);
     k_raster_bwd<<<grid, MM_RTHREADS, raster_smem(c->nwords, c->knum), s>>>(p);
 }

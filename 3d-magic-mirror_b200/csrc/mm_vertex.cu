@@ -91,7 +91,7 @@ k_vertex_fwd(const VertexFwdParams q,
         Cam c;
         camera_setup(azim[b], elev[b], dist[b], bias[b * 2], bias[b * 2 + 1], c);
         for (int i = 0; i < 12; ++i) sT[i] = c.T[i];
-        if (chunk == 0) { tickets[b * 2] = 0u; tickets[b * 2 + 1] = 0u; }
+        if (chunk == 0) { tickets[b * 4] = 0u; tickets[b * 4 + 1] = 0u; tickets[b * 4 + 2] = 0u; tickets[b * 4 + 3] = 0u; }
     }
     for (int i = threadIdx.x; i < nmask; i += blockDim.x) { smS[i] = 0u; smH[i] = 0u; }
     __syncthreads();
