@@ -172,6 +172,7 @@ __device__ __forceinline__ bool image_reduce_last(const float (&v)[NV], float* p
         float acc[NV];
         #pragma unroll
         for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
+        #pragma unroll 1
         for (int k = lane; k < nparts; k += 32) {
             #pragma unroll
             for (int i = 0; i < NV; ++i) acc[i] += __ldcg(part + (size_t)k * stride + i);
@@ -198,9 +199,11 @@ __device__ __forceinline__ void for_each_batch(const uint32_t* row, int nwords, 
 {
     int qn = 0;
     const uint32_t lt = (1u << lane) - 1u;
+    #pragma unroll 1
     for (int wd0 = 0; wd0 < nwords; wd0 += 32) {
         const uint32_t w = (wd0 + lane < nwords) ? row[wd0 + lane] : 0u;
         uint32_t nz = __ballot_sync(FULL, w != 0u);
+        #pragma unroll 1
         while (nz) {
             const int src = __ffs(nz) - 1;
             nz &= nz - 1;
@@ -225,6 +228,7 @@ __device__ __forceinline__ void for_each_batch(const uint32_t* row, int nwords, 
 __device__ __forceinline__ bool mask_empty(const uint32_t* row, int nwords, int lane)
 {
     uint32_t any = 0u;
+    #pragma unroll 1
     for (int wd0 = 0; wd0 < nwords; wd0 += 32) any |= (wd0 + lane < nwords) ? row[wd0 + lane] : 0u;
     return __ballot_sync(FULL, any != 0u) == 0u;
 }
@@ -283,6 +287,7 @@ __device__ __forceinline__ int pair_batch(const mm_raster_params& p, WarpScratch
     allowed = allowed < 0 ? 0 : allowed;
     if (nh > allowed) {                          // keep only the `allowed` lowest set bits (rare: > knum candidates)
         uint32_t k2 = 0u, h = keep;
+        #pragma unroll 1
         for (int a = 0; a < allowed; ++a) { const uint32_t low = h & (0u - h); k2 |= low; h ^= low; }
         keep = k2;
     }
@@ -295,9 +300,11 @@ __device__ __forceinline__ int pair_batch(const mm_raster_params& p, WarpScratch
     {
         int pos = pos0;
         uint32_t k2 = keep;
+        #pragma unroll 1
         while (k2) { const int j = __ffs(k2) - 1; k2 &= k2 - 1; ws->pr[pos++] = (uint32_t)((j << 5) | lane); }
     }
     __syncwarp();
+    #pragma unroll 1
     for (int i = lane; i < total; i += 32) {
         const uint32_t e = ws->pr[i];
         ws->pr[i] = __float_as_uint(eval((int)(e >> 5), (int)(e & 31u)));
@@ -306,6 +313,7 @@ __device__ __forceinline__ int pair_batch(const mm_raster_params& p, WarpScratch
     {
         int pos = pos0;
         uint32_t k2 = keep;
+        #pragma unroll 1
         while (k2) { const int j = __ffs(k2) - 1; k2 &= k2 - 1; scan(j, __uint_as_float(ws->pr[pos++])); }
     }
     __syncwarp();
@@ -323,9 +331,11 @@ __device__ __forceinline__ void mark_box(const mm_raster_params& p, const CtaCtx
     PixRange pr;
     if (!pix_range(p, c, xmin, xmax, ymin, ymax, pr)) return;
     const int bx = c.stx * MM_ST_W, by = c.sty * MM_ST_H;
+    #pragma unroll 1
     for (int iy = pr.iy0; iy <= pr.iy1; ++iy) {
         const float py = pix_y(iy, p.H, p.sy);
         if (py < ymin || py >= ymax) continue;
+        #pragma unroll 1
         for (int ix = pr.ix0; ix <= pr.ix1; ++ix) {
             const int pl = (iy - by) * MM_ST_W + (ix - bx);
             const float px = pix_x(ix, p.W, p.sx);
@@ -511,6 +521,7 @@ k_raster_fwd(const mm_raster_params p)
         if (p.prof && lane == 0) {
             long long* pr = p.prof + ((size_t)b * p.nst + c.st) * 8;
             int ns = 0, nh = 0;
+            #pragma unroll 1
             for (int i = 0; i < p.nwords; ++i) { ns += __popc(c.mS[i]); nh += __popc(c.mH[i]); }
             pr[0] = clock64() - t_start; pr[2] = ns; pr[3] = nh;
             pr[4] = c.ws->dbg[0]; pr[5] = c.ws->dbg[1]; pr[6] = 0; pr[7] = c.ws->dbg[3];
