@@ -71,6 +71,27 @@ void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int no_mask, mm_raster_
     p.face_uvs = c->d_face_uvs;
     p.tab = c->d_tab;
     p.prof = c->d_prof;
+    p.nchunks = c->nchunks; p.chunk_tiles = c->chunk_rows * c->nstx;
+}
+
+void set_ws(const mm_ws_layout& L, char* ws, mm_raster_params& p) {
+    p.frec = (const float*)(ws + L.frec);
+    p.maskS = (const uint32_t*)(ws + L.maskS); p.maskH = (const uint32_t*)(ws + L.maskH);
+    p.tflag = (const unsigned char*)(ws + L.tflag); p.tlist = (const uint16_t*)(ws + L.tlist);
+    p.tcount = (const int32_t*)(ws + L.tcount); p.gsoft = (float*)(ws + L.gsoft);
+    p.face_idx_ws = (int32_t*)(ws + L.face_idx);
+    p.part_fwd = (float*)(ws + L.part_fwd); p.part_bwd = (float*)(ws + L.part_bwd);
+    p.img_fwd = (float*)(ws + L.img_fwd); p.img_bwd = (float*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
+    p.gfacc = (float*)(ws + L.gfacc);
+}
+
+void launch_vertex_fwd(const mm_ctx* c, int B, const mm_ws_layout& L, char* ws, const float* vertices, const float* azim,
+                       const float* elev, const float* dist, const float* bias, float* face_normals, bool zero_gfacc,
+                       cudaStream_t s) {
+    mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (uint32_t*)(ws + L.maskS),
+                         (uint32_t*)(ws + L.maskH), (unsigned char*)(ws + L.tflag), (uint16_t*)(ws + L.tlist),
+                         (int32_t*)(ws + L.tcount), (float*)(ws + L.vimg), face_normals,
+                         zero_gfacc ? (float*)(ws + L.gfacc) : nullptr, (uint32_t*)(ws + L.tickets), s);
 }
 
 }  // namespace
@@ -185,20 +206,17 @@ int mm_render_forward(mm_ctx* c, int B, const float* vertices, const float* azim
     cudaStream_t s = (cudaStream_t)stream;
     const mm_ws_layout L = mm_ws_make(c, B);
     char* ws = (char*)workspace;
-    mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (uint32_t*)(ws + L.maskS),
-                         (uint32_t*)(ws + L.maskH), (float*)(ws + L.vimg), face_normals, nullptr, (uint32_t*)(ws + L.tickets), s);
+    launch_vertex_fwd(c, B, L, ws, vertices, azim, elev, dist, bias, face_normals, false, s);
     if (int r = check_launch("vertex_fwd")) return r;
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, no_mask, p);
-    p.frec = (const float*)(ws + L.frec);
-    p.maskS = (const uint32_t*)(ws + L.maskS); p.maskH = (const uint32_t*)(ws + L.maskH);
+    set_ws(L, ws, p);
     p.tex = tex; p.lights = lights; p.bg = bg;
-    p.rgba = rgba; p.imnormal = imnormal;
-    p.face_idx_ws = (int32_t*)(ws + L.face_idx); p.face_idx_out = face_idx;
-    p.part_fwd = (float*)(ws + L.part_fwd);
-    p.img_fwd = (float*)(ws + L.img_fwd); p.img_bwd = (float*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
-    mm_launch_raster_fwd(c, p, false, s);
-    return check_launch("raster_fwd");
+    p.rgba = rgba; p.imnormal = imnormal; p.face_idx_out = face_idx;
+    mm_launch_geom_fwd(c, p, s);
+    if (int r = check_launch("geom_fwd")) return r;
+    mm_launch_shade_fwd(c, p, false, s);
+    return check_launch("shade_fwd");
 }
 
 int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev, const float* dist,
@@ -221,19 +239,16 @@ int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azi
     if (g_bg && !no_mask) MM_CUDA(cudaMemsetAsync(g_bg, 0, (size_t)B * 3 * HW * 4, s));
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, no_mask, p);
-    p.frec = (const float*)(ws + L.frec);
-    p.maskS = (const uint32_t*)(ws + L.maskS); p.maskH = (const uint32_t*)(ws + L.maskH);
+    set_ws(L, ws, p);
     p.tex = tex; p.lights = lights; p.bg = bg;
     p.rgba = const_cast<float*>(rgba);
-    p.face_idx_ws = (int32_t*)(ws + L.face_idx);
     p.g_rgba = g_rgba;
     p.analytic_loss = 0;
-    p.gfacc = (float*)(ws + L.gfacc);
     p.g_tex = g_tex; p.g_bg = no_mask ? g_bg : nullptr;
-    p.part_bwd = (float*)(ws + L.part_bwd);
-    p.img_fwd = (float*)(ws + L.img_fwd); p.img_bwd = (float*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
-    mm_launch_raster_bwd(c, p, s);
-    if (int r = check_launch("raster_bwd")) return r;
+    mm_launch_shade_bwd(c, p, s);
+    if (int r = check_launch("shade_bwd")) return r;
+    mm_launch_geom_bwd(c, p, s);
+    if (int r = check_launch("geom_bwd")) return r;
     mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.img_bwd, g_vertices,
                          g_azim, g_elev, g_dist, g_bias, g_lights, s);
     return check_launch("vertex_bwd");
@@ -292,38 +307,36 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     MM_CUDA(cudaMemsetAsync(g_tex, 0, (size_t)B * 3 * Ht * Wt * 4, s));
     if (g_bg && !no_mask) MM_CUDA(cudaMemsetAsync(g_bg, 0, (size_t)B * 3 * HW * 4, s));
     if (c->timing) cudaEventRecord(c->ev[0], s);
-    mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (uint32_t*)(ws + L.maskS),
-                         (uint32_t*)(ws + L.maskH), (float*)(ws + L.vimg), face_normals, (float*)(ws + L.gfacc),
-                         (uint32_t*)(ws + L.tickets), s);
+    launch_vertex_fwd(c, B, L, ws, vertices, azim, elev, dist, bias, face_normals, true, s);
     if (int r = check_launch("vertex_fwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[1], s);
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, no_mask, p);
-    p.frec = (const float*)(ws + L.frec);
-    p.maskS = (const uint32_t*)(ws + L.maskS); p.maskH = (const uint32_t*)(ws + L.maskH);
+    set_ws(L, ws, p);
     p.tex = tex; p.lights = lights; p.bg = bg; p.gt = gt;
     p.rgba = rgba;
-    p.face_idx_ws = (int32_t*)(ws + L.face_idx);
-    p.part_fwd = (float*)(ws + L.part_fwd);
-    p.img_fwd = (float*)(ws + L.img_fwd); p.img_bwd = (float*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
-    mm_launch_raster_fwd(c, p, true, s);
-    if (int r = check_launch("raster_fwd")) return r;
+    mm_launch_geom_fwd(c, p, s);
+    if (int r = check_launch("geom_fwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[2], s);
+    mm_launch_shade_fwd(c, p, true, s);
+    if (int r = check_launch("shade_fwd")) return r;
+    if (c->timing) cudaEventRecord(c->ev[3], s);
     p.g_rgba = g_rgba_extra;
     p.image_weight = image_weight; p.contour = contour; p.loss_scale = loss_scale;
     p.analytic_loss = 1;
-    p.gfacc = (float*)(ws + L.gfacc);
     p.g_tex = g_tex; p.g_bg = no_mask ? g_bg : nullptr;
-    p.part_bwd = (float*)(ws + L.part_bwd);
-    mm_launch_raster_bwd(c, p, s);
-    if (int r = check_launch("raster_bwd")) return r;
-    if (c->timing) cudaEventRecord(c->ev[3], s);
+    mm_launch_shade_bwd(c, p, s);
+    if (int r = check_launch("shade_bwd")) return r;
+    if (c->timing) cudaEventRecord(c->ev[4], s);
+    mm_launch_geom_bwd(c, p, s);
+    if (int r = check_launch("geom_bwd")) return r;
+    if (c->timing) cudaEventRecord(c->ev[5], s);
     mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.img_bwd, g_vertices, g_azim,
                          g_elev, g_dist, g_bias, g_lights, s);
     if (int r = check_launch("vertex_bwd")) return r;
-    if (c->timing) cudaEventRecord(c->ev[4], s);
+    if (c->timing) cudaEventRecord(c->ev[6], s);
     mm_launch_loss_finalize(c, B, p.img_fwd, p.img_bwd, image_weight, contour, loss, nullptr, s);
-    if (c->timing) cudaEventRecord(c->ev[5], s);
+    if (c->timing) cudaEventRecord(c->ev[7], s);
     return check_launch("loss_finalize");
 }
 
@@ -336,18 +349,18 @@ int mm_debug_set_profile_buffer(mm_ctx* c, long long* device_buf) {
 int mm_ctx_set_timing(mm_ctx* c, int enable) {
     MM_REQUIRE(c, "ctx");
     if (enable && !c->ev[0]) {
-        for (int i = 0; i < 6; ++i) MM_CUDA(cudaEventCreate(&c->ev[i]));
+        for (int i = 0; i < 8; ++i) MM_CUDA(cudaEventCreate(&c->ev[i]));
     }
     c->timing = enable ? 1 : 0;
     return MM_OK;
 }
 
 int mm_ctx_get_timing(mm_ctx* c, float* ms_host, int capacity) {
-    MM_REQUIRE(c && ms_host && capacity >= 5, "ctx / ms_host / capacity >= 5");
+    MM_REQUIRE(c && ms_host && capacity >= 7, "ctx / ms_host / capacity >= 7");
     MM_REQUIRE(c->timing && c->ev[0], "timing not enabled");
-    MM_CUDA(cudaEventSynchronize(c->ev[5]));
-    for (int i = 0; i < 5; ++i) MM_CUDA(cudaEventElapsedTime(&ms_host[i], c->ev[i], c->ev[i + 1]));
-    return 5;
+    MM_CUDA(cudaEventSynchronize(c->ev[7]));
+    for (int i = 0; i < 7; ++i) MM_CUDA(cudaEventElapsedTime(&ms_host[i], c->ev[i], c->ev[i + 1]));
+    return 7;
 }
 
 int mm_debug_export_faces(mm_ctx* c, int B, const void* workspace, float* fvi, float* fvz, float* fnz, void* stream)

@@ -16,6 +16,10 @@
 //                          image, NW = ceil(F/32)): bit f of sub-tile s is set iff face f's bbox enlarged by
 //                          `boxlen` (S) / front face f's tight bbox (H) can touch s.  A bitmask keeps faces in
 //                          index order, which DIB-R's "first knum faces" truncation needs.
+//     tflag      [B,NST] u8   1 iff the sub-tile's S mask has any bit (something can touch it)
+//     tlist      [B,NST] u16  non-empty sub-tiles, compacted per vertex-stage chunk (segment c starts at c*chunk_tiles)
+//     tcount     [B,NCH] i32  entries per segment
+//     gsoft      [B,H,W]      d(loss)/d(silhouette) per pixel, handed from the shading backward to the geometry backward
 //     vimg       [B,V,2]   unscaled image-plane xy (debug export / parity tests)
 //     face_idx   [B,H,W]   int32 winner of the hard pass (-1 none); saved for backward
 //     gfacc      [B,F,9]   backward accumulators: d/d(fvi) (6, unscaled) + d/d(unit normal) (3)
@@ -74,7 +78,7 @@ struct mm_ctx {
 };
 
 struct mm_ws_layout {
-    size_t frec, maskS, maskH, vimg, face_idx, gfacc, part_fwd, part_bwd, img_fwd, img_bwd, tickets, total;
+    size_t frec, maskS, maskH, tflag, tlist, tcount, gsoft, vimg, face_idx, gfacc, part_fwd, part_bwd, img_fwd, img_bwd, tickets, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -93,10 +97,14 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     L.frec = off;     off = mm_align_up(off + (size_t)B * c->F * MM_REC_FLOATS * 4, 256);
     L.maskS = off;    off = mm_align_up(off + (size_t)B * c->nst * c->nwords * 4, 256);
     L.maskH = off;    off = mm_align_up(off + (size_t)B * c->nst * c->nwords * 4, 256);
+    L.tflag = off;    off = mm_align_up(off + (size_t)B * c->nst, 256);
+    L.tlist = off;    off = mm_align_up(off + (size_t)B * c->nst * 2, 256);
+    L.tcount = off;   off = mm_align_up(off + (size_t)B * c->nchunks * 4, 256);
+    L.gsoft = off;    off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.vimg = off;     off = mm_align_up(off + (size_t)B * c->V * 2 * 4, 256);
     L.face_idx = off; off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.gfacc = off;    off = mm_align_up(off + (size_t)B * c->F * 9 * 4, 256);
-    const int rp = mm_raster_parts(c, B);
+    const int rp = (c->nst + MM_WARPS - 1) / MM_WARPS;          // shading CTAs per image (8 sub-tiles each)
     const size_t np = (size_t)(rp > c->nparts_recon ? rp : c->nparts_recon);
     L.part_fwd = off; off = mm_align_up(off + (size_t)B * np * 4 * 4, 256);
     L.part_bwd = off; off = mm_align_up(off + (size_t)B * np * 12 * 4, 256);
@@ -116,6 +124,11 @@ struct mm_raster_params {
     const float* frec;       // [B,F,12]
     const uint32_t* maskS;   // [B,NST,NW]
     const uint32_t* maskH;   // [B,NST,NW]
+    const unsigned char* tflag;   // [B,NST]
+    const uint16_t* tlist;   // [B,NST]
+    const int32_t* tcount;   // [B,NCH]
+    int nchunks, chunk_tiles;
+    float* gsoft;            // [B,H,W]
     const float* face_uvs;   // [F,6]
     const float* tex;        // [B,3,Ht,Wt]
     const float* lights;     // [B,9]
@@ -144,13 +157,16 @@ struct mm_raster_params {
 // launchers (defined in the .cu files)
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec, uint32_t* maskS, uint32_t* maskH,
+                          unsigned char* tflag, uint16_t* tlist, int32_t* tcount,
                           float* vimg, float* face_normals, float* gfacc_zero, uint32_t* tickets, cudaStream_t s);
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,
                           const float* img_bwd, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
                           float* g_bias, float* g_lights, cudaStream_t s);
-void mm_launch_raster_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_loss, cudaStream_t s);
-void mm_launch_raster_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
+void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
+void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
+void mm_launch_shade_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_loss, cudaStream_t s);
+void mm_launch_shade_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 void mm_launch_loss_finalize(const mm_ctx* c, int B, const float* img_fwd, const float* img_bwd,
                              float image_weight, float contour, float* loss, float* iou_out, cudaStream_t s);
 void mm_launch_image_reduce(const mm_ctx* c, int B, int np, const float* part_fwd, float* img_fwd, cudaStream_t s);

@@ -1,0 +1,394 @@
+// mm_shade.cu -- the STREAMING half of the per-pixel stage: shading (UV texture sampling, SH lighting, composite,
+// clamp), the recon_data loss terms, and their backward.  Replaces kaolin texture_mapping /
+// spherical_harmonic_lighting, the ~40 elementwise torch kernels of networks.py:303-317 and :364-390, and their
+// autograd.  Visibility (`face_idx`) and the soft silhouette come from the geometry kernels (mm_raster.cu); they are
+// only read for sub-tiles whose face list is non-empty (`tflag`), so the ~2/3 of the image that is plain background
+// never touches geometry at all.
+//
+// One thread per pixel, one warp per 8x4-pixel sub-tile (the layout of the geometry kernels: a warp's stores are
+// four 32-byte row segments, i.e. whole sectors), 8 sub-tiles per CTA, plain non-persistent grid = (ceil(NST/8), B):
+// this half is bandwidth/latency-bound and wants as many resident warps as possible, not work balancing.
+// Per-image sums (L1, IoU, contour, light gradients) are reduced per CTA and then, deterministically, by the last
+// CTA of the image to arrive (fixed summation order, no float atomics on scalars).
+#include "mm_device.cuh"
+
+namespace {
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ float contour_c(float m, float mref) { return fabsf(m - mref); }
+
+// Per-image reduction without a second kernel and without float atomics: every CTA publishes its partial sums,
+// takes a ticket, and the LAST CTA of the image sums all partials in a fixed order.  The ticket resets itself.
+template <int NV>
+__device__ __forceinline__ void image_reduce_last(const float (&v)[NV], float* part /* [nparts][stride] of this image */,
+                                                  int stride, int nparts, uint32_t* ticket, float* out, int lane)
+{
+    __shared__ uint32_t s_ticket;
+    if (threadIdx.x == 0) {
+        #pragma unroll
+        for (int i = 0; i < NV; ++i) part[(size_t)blockIdx.x * stride + i] = v[i];
+        __threadfence();
+        s_ticket = atomicAdd(ticket, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != (uint32_t)(nparts - 1)) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        float acc[NV];
+        #pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
+        #pragma unroll 1
+        for (int k = lane; k < nparts; k += 32) {
+            #pragma unroll
+            for (int i = 0; i < NV; ++i) acc[i] += __ldcg(part + (size_t)k * stride + i);
+        }
+        #pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
+        }
+        if (lane == 0) {
+            #pragma unroll
+            for (int i = 0; i < NV; ++i) out[i] = acc[i];
+            *ticket = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+template <bool WITH_LOSS>
+__global__ void __launch_bounds__(MM_THREADS)
+k_shade_fwd(const mm_raster_params p)
+{
+    __shared__ float s_lights[16];
+    __shared__ float s_red[MM_WARPS];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
+    __syncthreads();
+    const size_t HW = (size_t)p.H * p.W;
+    const float* rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
+    float acc_l1 = 0.0f, acc_n = 0.0f, acc_d = 0.0f;
+    const int st = blockIdx.x * MM_WARPS + warp;
+    if (st < p.nst) {
+        const int sty = st / p.nstx, stx = st - sty * p.nstx;
+        const int ix = stx * MM_ST_W + (lane & 7), iy = sty * MM_ST_H + (lane >> 3);
+        const bool active = (ix < p.W) && (iy < p.H);
+        const bool geom = p.tflag[(size_t)b * p.nst + st] != 0;      // warp-uniform: did the geometry kernel visit this tile?
+        int best_f = -1;
+        float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, soft = 0.0f;
+        if (geom && active) {
+            const size_t pix0 = (size_t)iy * p.W + ix;
+            best_f = p.face_idx_ws[(size_t)b * HW + pix0];
+            soft = p.rgba[(size_t)b * 4 * HW + 3 * HW + pix0];
+            if (best_f >= 0) {                                       // the winner's weights, same instruction sequence as the hard pass
+                const FaceRec r = load_rec(rec, best_f);
+                Bary bb;
+                bary_eval(r, pix_x(ix, p.W, p.sx), pix_y(iy, p.H, p.sy), p.eps, bb);
+                w0 = bb.w0; w1 = bb.w1; w2 = bb.w2;
+            }
+        }
+        if (active) {
+            const size_t pix = (size_t)iy * p.W + ix;
+            // ---- shading (networks.py:303-314)
+            float tm = 0.0f, nrm[3] = {0.0f, 0.0f, 0.0f}, tcol[3] = {0.0f, 0.0f, 0.0f};
+            if (best_f >= 0) {
+                const float* uvp = p.face_uvs + best_f * 6;
+                // interpolation in the rasteriser's operation order (w0*c0 + w1*c1) + w2*c2, uncontracted
+                const float u = interp3(w0, w1, w2, __ldg(uvp + 0), __ldg(uvp + 2), __ldg(uvp + 4));
+                const float v = interp3(w0, w1, w2, __ldg(uvp + 1), __ldg(uvp + 3), __ldg(uvp + 5));
+                const FaceRec r = load_rec(rec, best_f);
+                tm = ADD(ADD(w0, w1), w2);
+                nrm[0] = interp3(w0, w1, w2, r.nx, r.nx, r.nx);
+                nrm[1] = interp3(w0, w1, w2, r.ny, r.ny, r.ny);
+                nrm[2] = interp3(w0, w1, w2, r.nz, r.nz, r.nz);
+                Bilin bl;
+                bilin_setup(u, v, p.Ht, p.Wt, bl);
+                const float* tb = p.tex + (size_t)b * 3 * p.Ht * p.Wt;
+                #pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const TexFetch t = tex_fetch(tb + (size_t)ch * p.Ht * p.Wt, bl, p.Ht, p.Wt);
+                    tcol[ch] = t.nw * bl.nw + t.ne * bl.ne + t.sw * bl.sw + t.se * bl.se;
+                }
+            }
+            float bnd[9];
+            sh_bands(nrm[0], nrm[1], nrm[2], bnd);
+            const float coef = sh_coef(bnd, s_lights);
+            float img[3];
+            #pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float v;
+                if (p.no_mask) {
+                    const float bgc = __ldg(p.bg + ((size_t)b * 3 + ch) * HW + pix);
+                    v = (tcol[ch] * tm + bgc * (1.0f - tm)) * coef;
+                } else {
+                    v = tcol[ch] * tm * coef + (1.0f - tm);
+                }
+                img[ch] = clamp01(v);
+            }
+            float* out = p.rgba + (size_t)b * 4 * HW + pix;
+            out[0] = img[0]; out[HW] = img[1]; out[2 * HW] = img[2]; out[3 * HW] = soft;
+            if (p.face_idx_out) p.face_idx_out[(size_t)b * HW + pix] = best_f;
+            if (p.imnormal) {
+                float* no = p.imnormal + ((size_t)b * HW + pix) * 3;
+                no[0] = nrm[0]; no[1] = nrm[1]; no[2] = nrm[2];
+            }
+            if (WITH_LOSS) {
+                const float* g = p.gt + (size_t)b * 4 * HW + pix;
+                const float gm = __ldg(g + 3 * HW);
+                #pragma unroll
+                for (int ch = 0; ch < 3; ++ch) acc_l1 += fabsf(l1_term(img[ch], __ldg(g + ch * HW), gm));
+                const float mul = soft * gm;
+                acc_n += mul;
+                acc_d += (soft + gm) - mul;
+            }
+        }
+    }
+    if (WITH_LOSS) {
+        const float v[4] = {block_sum(acc_l1, s_red), block_sum(acc_n, s_red), block_sum(acc_d, s_red), 0.0f};
+        image_reduce_last<4>(v, p.part_fwd + (size_t)b * gridDim.x * 4, 4, gridDim.x, p.tickets + b * 4 + 2, p.img_fwd + b * 4, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- backward
+__global__ void __launch_bounds__(MM_THREADS)
+k_shade_bwd(const mm_raster_params p)
+{
+    __shared__ float s_lights[16];
+    __shared__ float s_red[MM_WARPS];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
+    __syncthreads();
+    const size_t HW = (size_t)p.H * p.W;
+    const int H = p.H, W = p.W;
+    const int32_t* refrow = p.tab;
+    const int32_t* rowlo = p.tab + H;
+    const int32_t* rowhi = p.tab + 2 * H;
+    const int32_t* refcol = p.tab + 3 * H;
+    const int32_t* collo = p.tab + 3 * H + W;
+    const int32_t* colhi = p.tab + 3 * H + 2 * W;
+    const float* rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
+    float acc_contour = 0.0f;
+    float acc_l[9];
+    #pragma unroll
+    for (int i = 0; i < 9; ++i) acc_l[i] = 0.0f;
+    // loss-gradient constants; the per-image IoU sums were reduced by the forward kernel (fixed order)
+    float k_img = 0.0f, k_iou = 0.0f, k_cont = 0.0f, Nb = 0.0f, De = 1.0f;
+    if (p.analytic_loss) {
+        k_img = p.loss_scale * p.image_weight / ((float)p.B * 3.0f * (float)HW);
+        k_iou = p.loss_scale / (float)p.B;
+        k_cont = p.loss_scale * p.contour / ((float)p.B * (float)HW);
+        Nb = p.img_fwd[b * 4 + 1];
+        De = p.img_fwd[b * 4 + 2] + 1e-10f;
+    }
+    const float* rg = p.rgba + (size_t)b * 4 * HW;         // forward output
+    const float* gtb = p.gt ? p.gt + (size_t)b * 4 * HW : nullptr;
+    const float* gup = p.g_rgba ? p.g_rgba + (size_t)b * 4 * HW : nullptr;
+    float* gacc = p.gfacc + (size_t)b * p.F * 9;
+    float* gtex = p.g_tex + (size_t)b * 3 * p.Ht * p.Wt;
+    const int st = blockIdx.x * MM_WARPS + warp;
+    if (st < p.nst) {
+        const int sty = st / p.nstx, stx = st - sty * p.nstx;
+        const int ix = stx * MM_ST_W + (lane & 7), iy = sty * MM_ST_H + (lane >> 3);
+        const bool active = (ix < W) && (iy < H);
+        const bool geom = p.tflag[(size_t)b * p.nst + st] != 0;
+        const float x0 = pix_x(ix, W, p.sx), y0 = pix_y(iy, H, p.sy);
+        const size_t pix = active ? (size_t)iy * W + ix : 0;
+        const int best_f = (active && geom) ? p.face_idx_ws[(size_t)b * HW + pix] : -1;
+        // ---- upstream gradient of the 4 output channels
+        float g_img[3] = {0.0f, 0.0f, 0.0f}, g_soft = 0.0f;
+        float soft = 0.0f, gm_lane = 0.0f;
+        const bool fast4 = ((H & 3) == 0) && ((W & 3) == 0);
+        if (active) {
+            soft = rg[3 * HW + pix];
+            if (gup) { g_img[0] = gup[pix]; g_img[1] = gup[HW + pix]; g_img[2] = gup[2 * HW + pix]; g_soft = gup[3 * HW + pix]; }
+            if (p.analytic_loss) {
+                const float gm = __ldg(gtb + 3 * HW + pix);
+                #pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+                    g_img[ch] += k_img * sgnf(l1_term(rg[ch * HW + pix], __ldg(gtb + ch * HW + pix), gm)) * gm;
+                // soft IoU: -(1/B) * (gm*De - Nb*(1-gm)) / De^2
+                g_soft += -k_iou * (gm * De - Nb * (1.0f - gm)) / (De * De);
+                if (p.contour > 0.0f && !fast4) {
+                    const int ry = refrow[iy], rx = refcol[ix];
+                    const size_t rp = (size_t)ry * W + rx;
+                    const float mref = rg[3 * HW + rp], gref = __ldg(gtb + 3 * HW + rp);
+                    const float dlt = contour_c(soft, mref) - contour_c(gm, gref);
+                    acc_contour += dlt * dlt;
+                    float gc = 2.0f * dlt * sgnf(soft - mref);
+                    // this pixel may itself be the reference of a block of pixels
+                    const int y_lo = rowlo[iy], y_hi = rowhi[iy], x_lo = collo[ix], x_hi = colhi[ix];
+                    for (int yy = y_lo; yy < y_hi; ++yy)
+                        for (int xx = x_lo; xx < x_hi; ++xx) {
+                            const size_t q = (size_t)yy * W + xx;
+                            const float mq = rg[3 * HW + q], gq = __ldg(gtb + 3 * HW + q);
+                            const float dq = contour_c(mq, soft) - contour_c(gq, gm);
+                            gc -= 2.0f * dq * sgnf(mq - soft);
+                        }
+                    g_soft += k_cont * gc;
+                }
+                gm_lane = gm;
+            }
+        }
+        // contour term, fast path: H and W are multiples of 4, so the 8x4 sub-tile holds two complete 4x4 contour
+        // blocks (lanes with lx < 4 / lx >= 4) whose reference pixels are lanes 0 and 4: everything is exchanged
+        // with shuffles instead of 2 + 32 dependent global loads per reference pixel.
+        if (p.analytic_loss && p.contour > 0.0f && fast4) {
+            const int ref_lane = lane & 4;
+            const float mref = __shfl_sync(FULL, soft, ref_lane), gref = __shfl_sync(FULL, gm_lane, ref_lane);
+            const float dlt = active ? contour_c(soft, mref) - contour_c(gm_lane, gref) : 0.0f;
+            acc_contour += dlt * dlt;
+            const float own = 2.0f * dlt * sgnf(soft - mref);
+            float t = -own;                                     // what this pixel contributes to its reference pixel
+            t += __shfl_xor_sync(FULL, t, 1); t += __shfl_xor_sync(FULL, t, 2);
+            t += __shfl_xor_sync(FULL, t, 8); t += __shfl_xor_sync(FULL, t, 16);
+            if (active) g_soft += k_cont * (own + ((lane == ref_lane) ? t : 0.0f));
+        }
+
+        // hand d(loss)/d(silhouette) to the geometry backward (only tiles with geometry can use it)
+        if (geom && active) p.gsoft[(size_t)b * HW + pix] = (best_f < 0) ? g_soft : 0.0f;
+
+        if (active) {
+            // ---- shading backward
+            float tm = 0.0f, nrm[3] = {0.0f, 0.0f, 0.0f}, tcol[3] = {0.0f, 0.0f, 0.0f};
+            FaceRec r;
+            Bary bar;
+            Bilin bl;
+            TexFetch tf[3];
+            float uv[6];
+            if (best_f >= 0) {
+                r = load_rec(rec, best_f);
+                bary_eval(r, x0, y0, p.eps, bar);
+                const float* uvp = p.face_uvs + best_f * 6;
+                #pragma unroll
+                for (int i = 0; i < 6; ++i) uv[i] = __ldg(uvp + i);
+                const float u = interp3(bar.w0, bar.w1, bar.w2, uv[0], uv[2], uv[4]);
+                const float v = interp3(bar.w0, bar.w1, bar.w2, uv[1], uv[3], uv[5]);
+                tm = ADD(ADD(bar.w0, bar.w1), bar.w2);
+                nrm[0] = interp3(bar.w0, bar.w1, bar.w2, r.nx, r.nx, r.nx);
+                nrm[1] = interp3(bar.w0, bar.w1, bar.w2, r.ny, r.ny, r.ny);
+                nrm[2] = interp3(bar.w0, bar.w1, bar.w2, r.nz, r.nz, r.nz);
+                bilin_setup(u, v, p.Ht, p.Wt, bl);
+                const float* tb = p.tex + (size_t)b * 3 * p.Ht * p.Wt;
+                #pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    tf[ch] = tex_fetch(tb + (size_t)ch * p.Ht * p.Wt, bl, p.Ht, p.Wt);
+                    tcol[ch] = tf[ch].nw * bl.nw + tf[ch].ne * bl.ne + tf[ch].sw * bl.sw + tf[ch].se * bl.se;
+                }
+            }
+            float bnd[9];
+            sh_bands(nrm[0], nrm[1], nrm[2], bnd);
+            const float coef = sh_coef(bnd, s_lights);
+            float g_coef = 0.0f, g_tcol[3];
+            #pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float pre, bgc = 0.0f;
+                if (p.no_mask) {
+                    bgc = __ldg(p.bg + ((size_t)b * 3 + ch) * HW + pix);
+                    pre = (tcol[ch] * tm + bgc * (1.0f - tm)) * coef;
+                } else {
+                    pre = tcol[ch] * tm * coef + (1.0f - tm);
+                }
+                const float g = (pre >= 0.0f && pre <= 1.0f) ? g_img[ch] : 0.0f;     // torch.clamp backward
+                g_tcol[ch] = g * tm * coef;
+                if (p.no_mask) {
+                    g_coef += g * (tcol[ch] * tm + bgc * (1.0f - tm));
+                    if (p.g_bg) p.g_bg[((size_t)b * 3 + ch) * HW + pix] = g * (1.0f - tm) * coef;
+                } else {
+                    g_coef += g * (tcol[ch] * tm);
+                }
+            }
+            #pragma unroll
+            for (int i = 0; i < 9; ++i) acc_l[i] += g_coef * bnd[i];
+
+            if (best_f >= 0) {
+                // texture gradient + d/d(u,v)
+                float gix = 0.0f, giy = 0.0f;
+                const bool xe = (bl.ix + 1) < p.Wt, ys = (bl.iy + 1) < p.Ht;
+                const float tx = bl.x - (float)bl.ix, ty = bl.y - (float)bl.iy;
+                #pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float g = g_tcol[ch];
+                    if (g != 0.0f) {
+                        float* gp = gtex + ((size_t)ch * p.Ht + bl.iy) * p.Wt + bl.ix;
+                        atomicAdd(gp, g * bl.nw);
+                        if (xe) atomicAdd(gp + 1, g * bl.ne);
+                        if (ys) atomicAdd(gp + p.Wt, g * bl.sw);
+                        if (xe && ys) atomicAdd(gp + p.Wt + 1, g * bl.se);
+                        gix += g * ((tf[ch].ne - tf[ch].nw) * (1.0f - ty) + (tf[ch].se - tf[ch].sw) * ty);
+                        giy += g * ((tf[ch].sw - tf[ch].nw) * (1.0f - tx) + (tf[ch].se - tf[ch].ne) * tx);
+                    }
+                }
+                const float g_gx = bl.in_x ? gix * ((float)p.Wt * 0.5f) : 0.0f;
+                const float g_gy = bl.in_y ? giy * ((float)p.Ht * 0.5f) : 0.0f;
+                const float g_u = 2.0f * g_gx, g_v = -2.0f * g_gy;
+
+                // d coef / d normal -> unit face normal (features are the same normal on 3 corners)
+                const float* l = s_lights;
+                const float nx = nrm[0], ny = nrm[1], nz = nrm[2];
+                const float dcx = l[1] * SH_C1 + l[4] * SH_C2 * ny + l[7] * SH_C4 * nz + l[8] * SH_C5 * 2.0f * nx;
+                const float dcy = l[3] * SH_C1 + l[4] * SH_C2 * nx + l[5] * SH_C2 * nz - l[8] * SH_C5 * 2.0f * ny;
+                const float dcz = l[2] * SH_C1 + l[5] * SH_C2 * ny + l[6] * SH_C3 * 2.0f * nz + l[7] * SH_C4 * nx;
+                float* g = gacc + (size_t)best_f * 9;
+                const float gn_scale = g_coef * tm;    // sum_i w_i * g_n
+                if (gn_scale != 0.0f) {
+                    atomicAdd(g + 6, gn_scale * dcx);
+                    atomicAdd(g + 7, gn_scale * dcy);
+                    atomicAdd(g + 8, gn_scale * dcz);
+                }
+                // hard rasteriser backward (DIBR_SPEC A.3) for the u,v channels
+                if (g_u != 0.0f || g_v != 0.0f) {
+                    const float k1 = bar.k1, k2 = bar.k2, k3 = bar.k3;
+                    const float m = bar.m, pp = bar.p, n = bar.n, q = bar.q, s = bar.s, t = bar.t;
+                    // numerators of dw1/d(.) and dw2/d(.) (common 1/k3^2 applied in dldI)
+                    const float dw1dm = SUB(MUL(0.0f, k3), MUL(q, k1)),   dw1dn = SUB(MUL(-t, k3), MUL(-pp, k1));
+                    const float dw1dp = SUB(MUL(0.0f, k3), MUL(-n, k1)),  dw1dq = SUB(MUL(s, k3), MUL(m, k1));
+                    const float dw1ds = SUB(MUL(q, k3), MUL(0.0f, k1)),   dw1dt = SUB(MUL(-n, k3), MUL(0.0f, k1));
+                    const float dw2dm = SUB(MUL(t, k3), MUL(q, k2)),      dw2dn = SUB(MUL(0.0f, k3), MUL(-pp, k2));
+                    const float dw2dp = SUB(MUL(-s, k3), MUL(-n, k2)),    dw2dq = SUB(MUL(0.0f, k3), MUL(m, k2));
+                    const float dw2ds = SUB(MUL(-pp, k3), MUL(0.0f, k2)), dw2dt = SUB(MUL(m, k3), MUL(0.0f, k2));
+                    const float dw1dax = -ADD(ADD(dw1dm, dw1dn), dw1ds), dw1day = -ADD(ADD(dw1dp, dw1dq), dw1dt);
+                    const float dw2dax = -ADD(ADD(dw2dm, dw2dn), dw2ds), dw2day = -ADD(ADD(dw2dp, dw2dq), dw2dt);
+                    const float den = ADD(MUL(k3, k3), p.eps);
+                    float gv[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+                    #pragma unroll
+                    for (int d = 0; d < 2; ++d) {
+                        const float gd = d == 0 ? g_u : g_v;
+                        const float c0 = uv[d], c1 = uv[2 + d], c2 = uv[4 + d];
+                        const float e1 = SUB(c1, c0), e2 = SUB(c2, c0);
+                        const float dldI = DIV(MUL(p.multiplier, gd), den);
+                        gv[0] += MUL(dldI, ADD(MUL(e1, dw1dax), MUL(e2, dw2dax)));
+                        gv[1] += MUL(dldI, ADD(MUL(e1, dw1day), MUL(e2, dw2day)));
+                        gv[2] += MUL(dldI, ADD(MUL(e1, dw1dm), MUL(e2, dw2dm)));
+                        gv[3] += MUL(dldI, ADD(MUL(e1, dw1dp), MUL(e2, dw2dp)));
+                        gv[4] += MUL(dldI, ADD(MUL(e1, dw1dn), MUL(e2, dw2dn)));
+                        gv[5] += MUL(dldI, ADD(MUL(e1, dw1dq), MUL(e2, dw2dq)));
+                    }
+                    #pragma unroll
+                    for (int i = 0; i < 6; ++i) atomicAdd(g + i, gv[i]);
+                }
+            }
+        }
+    }
+    // ---- per-CTA partials: contour sum + 9 light gradients, reduced per image by the last CTA (fixed order)
+    float v[10];
+    v[0] = block_sum(acc_contour, s_red);
+    #pragma unroll
+    for (int i = 0; i < 9; ++i) v[1 + i] = block_sum(acc_l[i], s_red);
+    image_reduce_last<10>(v, p.part_bwd + (size_t)b * gridDim.x * 12, 12, gridDim.x, p.tickets + b * 4 + 3, p.img_bwd + b * 12, lane);
+}
+
+}  // namespace
+
+void mm_launch_shade_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_loss, cudaStream_t s)
+{
+    const dim3 grid((c->nst + MM_WARPS - 1) / MM_WARPS, p.B);
+    if (with_loss) k_shade_fwd<true><<<grid, MM_THREADS, 0, s>>>(p);
+    else           k_shade_fwd<false><<<grid, MM_THREADS, 0, s>>>(p);
+}
+
+void mm_launch_shade_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
+{
+    const dim3 grid((c->nst + MM_WARPS - 1) / MM_WARPS, p.B);
+    k_shade_bwd<<<grid, MM_THREADS, 0, s>>>(p);
+}

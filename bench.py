@@ -25,7 +25,7 @@ UNIT = "images/s"
 B_PER_GPU = 48
 IMAGE_SIZE = 128
 NSETS = 4                     # rotating input/output sets: 4 x ~137 MB > 126 MB L2, so every step starts L2-cold
-KERNELS = ["vertex_fwd", "raster_fwd", "raster_bwd", "vertex_bwd", "loss_finalize"]
+KERNELS = ["vertex_fwd", "geom_fwd", "shade_fwd", "shade_bwd", "geom_bwd", "vertex_bwd", "loss_finalize"]
 
 
 def algorithmic_bytes(B, V, F, H, W, Ht, Wt, bg=True, extra=False):
@@ -374,14 +374,17 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         roof = {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": None}
         if kms:
-            dom = max(("raster_fwd", "raster_bwd"), key=lambda k: kms[k])
-            nbytes = bytes_bwd if dom == "raster_bwd" else bytes_fwd
-            ach = nbytes / (kms[dom] * 1e-3) / 1e9
-            roof.update({"kernel": "k_" + dom, "achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": nbytes,
-                         "avg_launch_ms": kms[dom], "kernel_ms": kms})
+            # the per-pixel stage is two launches per direction (geometry + shading); SURVEY 8(d) counts bytes per
+            # direction, so the roofline is taken over the slower direction's pair of launches
+            t_fwd, t_bwd = kms["geom_fwd"] + kms["shade_fwd"], kms["shade_bwd"] + kms["geom_bwd"]
+            dom = "bwd" if t_bwd >= t_fwd else "fwd"
+            nbytes, t_dom = (bytes_bwd, t_bwd) if dom == "bwd" else (bytes_fwd, t_fwd)
+            ach = nbytes / (t_dom * 1e-3) / 1e9
+            roof.update({"kernel": "k_shade_bwd+k_geom_bwd" if dom == "bwd" else "k_geom_fwd+k_shade_fwd", "achieved": ach,
+                         "frac": ach / peak, "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": t_dom, "kernel_ms": kms})
             try:
                 tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-                roof["traffic"] = tr.get("k_" + dom)
+                roof["traffic"] = tr.get(roof["kernel"])
             except Exception:
                 pass
         ach_step = bytes_step / (ms / K * 1e-3) / 1e9

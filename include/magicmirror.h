@@ -132,7 +132,7 @@ int mm_debug_set_profile_buffer(mm_ctx* ctx, long long* device_buf);
 /* Measurement hook (bench.py): when enabled, mm_render_compare_fwd_bwd records a CUDA event on
  * `stream` before each of its kernels and after the last one.  mm_ctx_get_timing waits for the last
  * call's final event and writes the per-kernel durations in milliseconds, in launch order
- * (vertex_fwd, raster_fwd, raster_bwd, vertex_bwd, loss_finalize); returns the count written. */
+ * (vertex_fwd, geom_fwd, shade_fwd, shade_bwd, geom_bwd, vertex_bwd, loss_finalize; capacity >= 7); returns the count written. */
 int mm_ctx_set_timing(mm_ctx* ctx, int enable);
 int mm_ctx_get_timing(mm_ctx* ctx, float* ms_host, int capacity);
 

@@ -26,10 +26,10 @@ for i in range(10): fr.step(i)
 ms = bench.timed(torch, 1, fr.step, steps) / steps
 L = mm.lib(); h = fr.h.handle
 L.mm_ctx_set_timing(h, 1)
-acc = [0.0] * 5; buf = (ctypes.c_float * 8)()
+acc = [0.0] * 7; buf = (ctypes.c_float * 8)()
 n = min(steps, 200)
 for i in range(n):
     fr.step(i); L.mm_ctx_get_timing(h, buf, 8)
-    for j in range(5): acc[j] += buf[j]
+    for j in range(7): acc[j] += buf[j]
 L.mm_ctx_set_timing(h, 0)
 print("ms_per_step %.4f  img/s %.0f  kernels_us %s" % (ms, 48 / ms * 1e3, {k: round(1e3 * a / n, 1) for k, a in zip(bench.KERNELS, acc)}), flush=True)
