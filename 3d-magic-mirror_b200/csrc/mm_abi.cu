@@ -71,14 +71,13 @@ void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int no_mask, mm_raster_
     p.face_uvs = c->d_face_uvs;
     p.tab = c->d_tab;
     p.prof = c->d_prof;
-    p.nchunks = c->nchunks; p.chunk_tiles = c->chunk_rows * c->nstx;
 }
 
 void set_ws(const mm_ws_layout& L, char* ws, mm_raster_params& p) {
     p.frec = (const float*)(ws + L.frec);
     p.maskS = (const uint32_t*)(ws + L.maskS); p.maskH = (const uint32_t*)(ws + L.maskH);
-    p.tflag = (const unsigned char*)(ws + L.tflag); p.tlist = (const uint16_t*)(ws + L.tlist);
-    p.tcount = (const int32_t*)(ws + L.tcount); p.gsoft = (float*)(ws + L.gsoft);
+    p.tflag = (const unsigned char*)(ws + L.tflag); p.glist = (const uint32_t*)(ws + L.glist);
+    p.gctr = (uint32_t*)(ws + L.gctr); p.gsoft = (float*)(ws + L.gsoft);
     p.face_idx_ws = (int32_t*)(ws + L.face_idx);
     p.part_fwd = (float*)(ws + L.part_fwd); p.part_bwd = (float*)(ws + L.part_bwd);
     p.img_fwd = (float*)(ws + L.img_fwd); p.img_bwd = (float*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
@@ -88,9 +87,10 @@ void set_ws(const mm_ws_layout& L, char* ws, mm_raster_params& p) {
 void launch_vertex_fwd(const mm_ctx* c, int B, const mm_ws_layout& L, char* ws, const float* vertices, const float* azim,
                        const float* elev, const float* dist, const float* bias, float* face_normals, bool zero_gfacc,
                        cudaStream_t s) {
+    cudaMemsetAsync(ws + L.gctr, 0, 16, s);          // work-list length + tickets of this forward/backward pair
     mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (uint32_t*)(ws + L.maskS),
-                         (uint32_t*)(ws + L.maskH), (unsigned char*)(ws + L.tflag), (uint16_t*)(ws + L.tlist),
-                         (int32_t*)(ws + L.tcount), (float*)(ws + L.vimg), face_normals,
+                         (uint32_t*)(ws + L.maskH), (unsigned char*)(ws + L.tflag), (uint32_t*)(ws + L.glist),
+                         (uint32_t*)(ws + L.gctr), (float*)(ws + L.vimg), face_normals,
                          zero_gfacc ? (float*)(ws + L.gfacc) : nullptr, (uint32_t*)(ws + L.tickets), s);
 }
 
@@ -136,6 +136,7 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     c->nparts_recon = (H * W + 4095) / 4096 < 1 ? 1 : (H * W + 4095) / 4096;     // ~4096 pixels per recon CTA
     c->nwords = ((F + 31) / 32 + 3) & ~3;          // multiple of 4 words: mask rows stay 16-byte aligned for cp.async.bulk
     c->num_sms = prop.multiProcessorCount;
+    if (c->nst > 65535) { delete c; return fail(MM_E_UNSUPPORTED, "image too large: %d sub-tiles exceed the 16-bit work-list ids", c->nst); }
     if (F > 65535) { delete c; return fail(MM_E_UNSUPPORTED, "F=%d exceeds the 16-bit face ids of the soft-pass lists", F); }
     const size_t smem_max = prop.sharedMemPerBlockOptin;
     // vertex stage: sub-tile rows per CTA such that the two chunk masks fit in <= 96 KB and an image gets >= 4 CTAs
@@ -198,7 +199,7 @@ int mm_render_forward(mm_ctx* c, int B, const float* vertices, const float* azim
                       int no_mask, float* rgba, float* face_normals, float* imnormal, int32_t* face_idx,
                       void* workspace, void* stream)
 {
-    MM_REQUIRE(c && B > 0, "ctx / B");
+    MM_REQUIRE(c && B > 0 && B <= 65535, "ctx / B (1..65535)");
     MM_REQUIRE(vertices && azim && elev && dist && bias && tex && lights, "NULL input");
     MM_REQUIRE(Ht > 0 && Wt > 0, "texture size");
     MM_REQUIRE(!no_mask || bg, "no_mask=1 requires bg");

@@ -17,8 +17,9 @@
 //                          `boxlen` (S) / front face f's tight bbox (H) can touch s.  A bitmask keeps faces in
 //                          index order, which DIB-R's "first knum faces" truncation needs.
 //     tflag      [B,NST] u8   1 iff the sub-tile's S mask has any bit (something can touch it)
-//     tlist      [B,NST] u16  non-empty sub-tiles, compacted per vertex-stage chunk (segment c starts at c*chunk_tiles)
-//     tcount     [B,NCH] i32  entries per segment
+//     glist      [B*NST] u32  all non-empty sub-tiles of the batch, (image << 16 | sub-tile), compacted by the vertex
+//                             stage through one atomic counter: the geometry kernels' global work list
+//     gctr       [4]     u32  {list length, forward ticket, backward ticket, -}
 //     gsoft      [B,H,W]      d(loss)/d(silhouette) per pixel, handed from the shading backward to the geometry backward
 //     vimg       [B,V,2]   unscaled image-plane xy (debug export / parity tests)
 //     face_idx   [B,H,W]   int32 winner of the hard pass (-1 none); saved for backward
@@ -78,17 +79,16 @@ struct mm_ctx {
 };
 
 struct mm_ws_layout {
-    size_t frec, maskS, maskH, tflag, tlist, tcount, gsoft, vimg, face_idx, gfacc, part_fwd, part_bwd, img_fwd, img_bwd, tickets, total;
+    size_t frec, maskS, maskH, tflag, glist, gctr, gsoft, vimg, face_idx, gfacc, part_fwd, part_bwd, img_fwd, img_bwd, tickets, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// persistent raster warps per image: enough single-warp CTAs to fill every SM ~24 deep, at most one per sub-tile
+// persistent geometry warps: enough single-warp CTAs to fill every SM ~24 deep, at most one per sub-tile of the batch
 static inline int mm_raster_parts(const mm_ctx* c, int B) {
-    int g = (c->num_sms * 24 + B - 1) / B;
-    if (g < 1) g = 1;
-    if (g > c->nst) g = c->nst;
-    return g;
+    long long g = (long long)c->num_sms * 24;
+    if (g > (long long)B * c->nst) g = (long long)B * c->nst;
+    return (int)(g < 1 ? 1 : g);
 }
 
 static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
@@ -98,8 +98,8 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     L.maskS = off;    off = mm_align_up(off + (size_t)B * c->nst * c->nwords * 4, 256);
     L.maskH = off;    off = mm_align_up(off + (size_t)B * c->nst * c->nwords * 4, 256);
     L.tflag = off;    off = mm_align_up(off + (size_t)B * c->nst, 256);
-    L.tlist = off;    off = mm_align_up(off + (size_t)B * c->nst * 2, 256);
-    L.tcount = off;   off = mm_align_up(off + (size_t)B * c->nchunks * 4, 256);
+    L.glist = off;    off = mm_align_up(off + (size_t)B * c->nst * 4, 256);
+    L.gctr = off;     off = mm_align_up(off + 16, 256);
     L.gsoft = off;    off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.vimg = off;     off = mm_align_up(off + (size_t)B * c->V * 2 * 4, 256);
     L.face_idx = off; off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
@@ -125,9 +125,8 @@ struct mm_raster_params {
     const uint32_t* maskS;   // [B,NST,NW]
     const uint32_t* maskH;   // [B,NST,NW]
     const unsigned char* tflag;   // [B,NST]
-    const uint16_t* tlist;   // [B,NST]
-    const int32_t* tcount;   // [B,NCH]
-    int nchunks, chunk_tiles;
+    const uint32_t* glist;   // [B*NST]
+    uint32_t* gctr;          // [4]
     float* gsoft;            // [B,H,W]
     const float* face_uvs;   // [F,6]
     const float* tex;        // [B,3,Ht,Wt]
@@ -157,7 +156,7 @@ struct mm_raster_params {
 // launchers (defined in the .cu files)
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec, uint32_t* maskS, uint32_t* maskH,
-                          unsigned char* tflag, uint16_t* tlist, int32_t* tcount,
+                          unsigned char* tflag, uint32_t* glist, uint32_t* gctr,
                           float* vimg, float* face_normals, float* gfacc_zero, uint32_t* tickets, cudaStream_t s);
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,

@@ -38,16 +38,16 @@ struct CtaCtx {
     const uint32_t* mS;     // current sub-tile's S mask row (shared memory, TMA-staged)
     const uint32_t* mH;     // current sub-tile's H mask row
     WarpScratch* ws;        // this warp's scratch
-    const float* rec;       // face records of this image (global, read through L1)
-    int st, stx, sty, ix, iy;
+    const float* rec;       // face records of the current tile's image (global, read through L1)
+    int b, st, stx, sty, ix, iy;   // current tile: image, sub-tile, pixel of this lane
     bool active;
     // persistent-warp state
     uint64_t* bar;          // two mbarriers (double-buffered mask rows)
     uint32_t* buf;          // [2][2*nwords]
-    uint32_t* queue;        // this image's ticket counter
-    int cum_excl, cum_incl; // lane k: tiles in list segments before / up to vertex-chunk k
-    int total;              // non-empty sub-tiles of this image
-    int nxt, k;
+    uint32_t* ticket;       // global ticket counter of this pass
+    int total;              // length of the batch-wide list of non-empty sub-tiles
+    int first;              // 1 until the warp has taken its static first tile
+    int nb, nxt, k;
     uint32_t phase0, phase1;
 };
 
@@ -57,24 +57,28 @@ __host__ __device__ inline size_t raster_smem(int nwords, int knum) {
     return 16 + 4 * (size_t)nwords * 4 + sizeof(WarpScratch);
 }
 
-// ticket -> sub-tile index through the per-chunk compacted lists of the vertex stage; -1 when the image is done
-__device__ __forceinline__ int fetch_tile(const mm_raster_params& p, CtaCtx& c, int lane) {
+// Next entry of the batch-wide work list: the first tile of every warp is static (its own index), the rest come from
+// one atomic ticket, so images with few non-empty tiles (far camera) cost nothing and warps never idle while any
+// image still has work.  Returns st = -1 when the list is exhausted.
+__device__ __forceinline__ void fetch_tile(const mm_raster_params& p, CtaCtx& c, int lane, int& ob, int& ost) {
     int t = 0;
-    if (lane == 0) t = (int)atomicAdd(c.queue, 1u);
-    t = __shfl_sync(FULL, t, 0);
-    if (t >= c.total) return -1;
-    const uint32_t before = __ballot_sync(FULL, lane < p.nchunks && c.cum_incl <= t);
-    const int chunk = __popc(before);
-    const int base = __shfl_sync(FULL, c.cum_excl, chunk);
-    int st = 0;
-    if (lane == 0) st = (int)p.tlist[(size_t)blockIdx.y * p.nst + (size_t)chunk * p.chunk_tiles + (t - base)];
-    return __shfl_sync(FULL, st, 0);
+    if (c.first) { t = (int)blockIdx.x; c.first = 0; }
+    else {
+        if (lane == 0) t = (int)atomicAdd(c.ticket, 1u) + (int)gridDim.x;
+        t = __shfl_sync(FULL, t, 0);
+    }
+    ob = 0; ost = -1;
+    if (t >= c.total) return;
+    uint32_t e = 0u;
+    if (lane == 0) e = p.glist[t];
+    e = __shfl_sync(FULL, e, 0);
+    ob = (int)(e >> 16); ost = (int)(e & 0xffffu);
 }
 
-__device__ __forceinline__ void issue_masks(const mm_raster_params& p, CtaCtx& c, int st, int k, int lane) {
+__device__ __forceinline__ void issue_masks(const mm_raster_params& p, CtaCtx& c, int b, int st, int k, int lane) {
     if (lane == 0) {
         const uint32_t bytes = (uint32_t)p.nwords * 4;
-        const size_t off = ((size_t)blockIdx.y * p.nst + st) * p.nwords;
+        const size_t off = ((size_t)b * p.nst + st) * p.nwords;
         uint64_t* bar = c.bar + k;
         uint32_t* dst = c.buf + (size_t)k * 2 * p.nwords;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(2 * bytes) : "memory");
@@ -87,35 +91,30 @@ __device__ __forceinline__ void issue_masks(const mm_raster_params& p, CtaCtx& c
 
 __device__ __forceinline__ void warp_init(const mm_raster_params& p, unsigned char* smem, CtaCtx& c, int which /* 0 fwd, 1 bwd */)
 {
-    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     c.bar = reinterpret_cast<uint64_t*>(smem);
     c.buf = reinterpret_cast<uint32_t*>(smem + 16);
     c.ws = reinterpret_cast<WarpScratch*>(c.buf + 4 * p.nwords);
-    c.rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
-    c.queue = p.tickets + b * 4 + which;
+    c.ticket = p.gctr + 1 + which;
+    c.total = (int)p.gctr[0];
+    c.first = 1;
     if (lane == 0) { mbar_init(c.bar, 1); mbar_init(c.bar + 1, 1); }
-    // per-chunk list sizes -> prefix sums (nchunks <= 32)
-    const int cnt = (lane < p.nchunks) ? p.tcount[b * p.nchunks + lane] : 0;
-    int incl = cnt;
-    #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-    c.cum_incl = incl; c.cum_excl = incl - cnt;
-    c.total = __shfl_sync(FULL, incl, 31);
     __syncwarp();
     c.k = 0; c.phase0 = 0u; c.phase1 = 0u;
-    c.st = fetch_tile(p, c, lane);
-    if (c.st >= 0) issue_masks(p, c, c.st, 0, lane);
+    fetch_tile(p, c, lane, c.b, c.st);
+    if (c.st >= 0) issue_masks(p, c, c.b, c.st, 0, lane);
 }
 
 // Called at the top of every loop iteration: prefetch the next tile's masks, wait for the current ones.
 __device__ __forceinline__ void tile_begin(const mm_raster_params& p, CtaCtx& c, int lane)
 {
-    c.nxt = fetch_tile(p, c, lane);
-    if (c.nxt >= 0) issue_masks(p, c, c.nxt, c.k ^ 1, lane);
+    fetch_tile(p, c, lane, c.nb, c.nxt);
+    if (c.nxt >= 0) issue_masks(p, c, c.nb, c.nxt, c.k ^ 1, lane);
     if (c.k == 0) { mbar_wait(c.bar, c.phase0); c.phase0 ^= 1u; }
     else          { mbar_wait(c.bar + 1, c.phase1); c.phase1 ^= 1u; }
     c.mS = c.buf + (size_t)c.k * 2 * p.nwords;
     c.mH = c.mS + p.nwords;
+    c.rec = p.frec + (size_t)c.b * p.F * MM_REC_FLOATS;
     c.sty = c.st / p.nstx; c.stx = c.st - c.sty * p.nstx;
     c.ix = c.stx * MM_ST_W + (lane & 7);
     c.iy = c.sty * MM_ST_H + (lane >> 3);
@@ -125,6 +124,7 @@ __device__ __forceinline__ void tile_begin(const mm_raster_params& p, CtaCtx& c,
 __device__ __forceinline__ void tile_end(CtaCtx& c)
 {
     __syncwarp();
+    c.b = c.nb;
     c.st = c.nxt;
     c.k ^= 1;
 }
@@ -361,7 +361,7 @@ k_geom_fwd(const mm_raster_params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     CtaCtx c;
-    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     warp_init(p, smem, c, 0);
     const size_t HW = (size_t)p.H * p.W;
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
@@ -369,6 +369,7 @@ k_geom_fwd(const mm_raster_params p)
     while (c.st >= 0) {
         const long long t_start = p.prof ? clock64() : 0;
         tile_begin(p, c, lane);
+        const int b = c.b;
         const float x0 = pix_x(c.ix, p.W, p.sx), y0 = pix_y(c.iy, p.H, p.sy);
         int best_f = -1;
         float w0, w1, w2, soft = 0.0f;
@@ -418,15 +419,16 @@ k_geom_bwd(const mm_raster_params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     CtaCtx c;
-    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     warp_init(p, smem, c, 1);
     const size_t HW = (size_t)p.H * p.W;
     const int H = p.H, W = p.W;
-    float* gacc = p.gfacc + (size_t)b * p.F * 9;
 
     while (c.st >= 0) {
         const long long t_start = p.prof ? clock64() : 0;
         tile_begin(p, c, lane);
+        const int b = c.b;
+        float* gacc = p.gfacc + (size_t)b * p.F * 9;
         const bool active = c.active;
         const size_t pix = active ? (size_t)c.iy * W + c.ix : 0;
         const int best_f = active ? p.face_idx_ws[(size_t)b * HW + pix] : -2;      // -2: inactive lane
@@ -495,11 +497,11 @@ k_geom_bwd(const mm_raster_params p)
         if (p.prof && lane == 0) p.prof[((size_t)b * p.nst + c.st) * 8 + 1] = clock64() - t_start;
         tile_end(c);
     }
-    // leave the workspace reusable: the last warp of the image to finish resets the ticket counter
+    // leave the workspace reusable for another backward on the same forward: the last warp to finish resets the ticket
     if (lane == 0) {
         __threadfence();
-        const uint32_t done = atomicAdd(p.tickets + b * 4 + 3, 1u);
-        if (done == gridDim.x - 1) { p.tickets[b * 4 + 1] = 0u; p.tickets[b * 4 + 3] = 0u; }
+        const uint32_t done = atomicAdd(p.gctr + 3, 1u);
+        if (done == gridDim.x - 1) { p.gctr[2] = 0u; p.gctr[3] = 0u; }
     }
 }
 
@@ -517,12 +519,12 @@ cudaError_t mm_raster_configure(const mm_ctx* c) {
 
 void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
-    const dim3 grid(mm_raster_parts(c, p.B), p.B);
+    const dim3 grid(mm_raster_parts(c, p.B));
     k_geom_fwd<<<grid, MM_RTHREADS, raster_smem(c->nwords, c->knum), s>>>(p);
 }
 
 void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
-    const dim3 grid(mm_raster_parts(c, p.B), p.B);
+    const dim3 grid(mm_raster_parts(c, p.B));
     k_geom_bwd<<<grid, MM_RTHREADS, raster_smem(c->nwords, c->knum), s>>>(p);
 }

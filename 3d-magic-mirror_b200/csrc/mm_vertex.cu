@@ -73,7 +73,7 @@ k_vertex_fwd(const VertexFwdParams q,
              const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
              const float* __restrict__ bias,
              float* __restrict__ frec, uint32_t* __restrict__ maskS, uint32_t* __restrict__ maskH,
-             unsigned char* __restrict__ tflag, uint16_t* __restrict__ tlist, int32_t* __restrict__ tcount,
+             unsigned char* __restrict__ tflag, uint32_t* __restrict__ glist, uint32_t* __restrict__ gctr,
              float* __restrict__ vimg, float* __restrict__ face_normals, float* __restrict__ gfacc_zero,
              uint32_t* __restrict__ tickets)
 {
@@ -180,15 +180,13 @@ k_vertex_fwd(const VertexFwdParams q,
     __syncthreads();
     const size_t gbase = ((size_t)b * q.nsty * q.nstx + (size_t)row0 * q.nstx) * q.nwords;
     for (int i = threadIdx.x; i < nmask; i += blockDim.x) { maskS[gbase + i] = smS[i]; maskH[gbase + i] = smH[i]; }
-    // ---- per-sub-tile "anything can touch it" flag + ordered compaction of the non-empty sub-tiles of this chunk
+    // ---- per-sub-tile "anything can touch it" flag; the non-empty sub-tiles of the whole batch are appended to ONE
+    // global work list (one atomicAdd per CTA reserves the range) that the geometry kernels consume
     __shared__ int s_wcount[MM_VTHREADS / 32];
-    __shared__ int s_base;
+    __shared__ uint32_t s_gbase;
     const int ntile = rows * q.nstx;
     const int nst = q.nsty * q.nstx;
     const int tile0 = row0 * q.nstx;
-    const int chunk_tiles = q.chunk_rows * q.nstx;
-    if (threadIdx.x == 0) s_base = 0;
-    __syncthreads();
     for (int t0 = 0; t0 < ntile; t0 += blockDim.x) {
         const int t = t0 + threadIdx.x;
         bool nonempty = false;
@@ -202,14 +200,17 @@ k_vertex_fwd(const VertexFwdParams q,
         const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
         if (ln == 0) s_wcount[wid] = __popc(bal);
         __syncthreads();
-        int off = s_base;
-        for (int w = 0; w < wid; ++w) off += s_wcount[w];
-        if (nonempty) tlist[(size_t)b * nst + (size_t)chunk * chunk_tiles + off + __popc(bal & ((1u << ln) - 1u))] = (uint16_t)(tile0 + t);
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_wcount[w];
+            s_gbase = tot ? atomicAdd(gctr, (uint32_t)tot) : 0u;
+        }
         __syncthreads();
-        if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_wcount[w]; s_base += tot; }
+        int off = 0;
+        for (int w = 0; w < wid; ++w) off += s_wcount[w];
+        if (nonempty) glist[s_gbase + off + __popc(bal & ((1u << ln) - 1u))] = ((uint32_t)b << 16) | (uint32_t)(tile0 + t);
         __syncthreads();
     }
-    if (threadIdx.x == 0) tcount[b * q.nchunks + chunk] = s_base;
 }
 
 // ------------------------------------------------------------------ backward
@@ -387,7 +388,7 @@ __global__ void k_export_faces(int V, int F, float multiplier, const int32_t* __
 
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec, uint32_t* maskS, uint32_t* maskH,
-                          unsigned char* tflag, uint16_t* tlist, int32_t* tcount,
+                          unsigned char* tflag, uint32_t* glist, uint32_t* gctr,
                           float* vimg, float* face_normals, float* gfacc_zero, uint32_t* tickets, cudaStream_t s)
 {
     VertexFwdParams q;
@@ -396,7 +397,7 @@ void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const f
     q.proj_x = c->proj_x; q.proj_y = c->proj_y; q.multiplier = c->multiplier; q.sx = c->sx; q.sy = c->sy; q.blen = c->blen;
     const dim3 grid(c->nchunks, B);
     k_vertex_fwd<<<grid, MM_VTHREADS, c->smem_vertex_fwd, s>>>(q, c->d_faces, vertices, azim, elev, dist, bias, frec, maskS,
-                                                       maskH, tflag, tlist, tcount, vimg, face_normals, gfacc_zero, tickets);
+                                                       maskH, tflag, glist, gctr, vimg, face_normals, gfacc_zero, tickets);
 }
 
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
