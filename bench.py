@@ -174,7 +174,10 @@ class FusedRunner(object):
 
 class E2ERunner(object):
     """The reference-facing path a trainer.py user takes -- DiffRender.render -> recon_data -> backward()
-    (trainer.py:276,441,509) -- fed from pinned HOST buffers every step, loss read back to the host."""
+    (trainer.py:276,441,509) -- fed from pinned HOST buffers every step, loss read back to the host.
+    The host->device copies of step i+1 are issued on a copy stream while step i computes (double-buffered device
+    staging, the same overlap the reference gets from its DataLoader + `.cuda(non_blocking=True)`, trainer.py:247);
+    every byte is still copied inside the timed region, every step."""
 
     def __init__(self, mm, dr, sets_cpu, device):
         import torch
@@ -191,15 +194,39 @@ class E2ERunner(object):
         self.h2d_bytes = sum(t.numel() * 4 for t in self.host[0].values())
         self.loss_host = torch.empty(1).pin_memory()
         self.d2h_bytes = 4
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.stage = [{k: torch.empty_like(v, device=device) for k, v in self.host[0].items()} for _ in range(2)]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]       # staging buffer filled
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]        # staging buffer consumed
+        self.primed = False
+
+    def _upload(self, i):
+        torch = self.torch
+        slot = i % 2
+        h = self.host[i % len(self.host)]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[slot])
+            for k, v in h.items():
+                self.stage[slot][k].copy_(v, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
 
     def step(self, i):
         torch = self.torch
-        h = self.host[i % len(self.host)]
-        A = {k: h[k].to(self.dev, non_blocking=True).requires_grad_(True) for k in self.keys}
-        gt = h['gt'].to(self.dev, non_blocking=True)
+        cur = torch.cuda.current_stream()
+        if not self.primed:
+            for e in self.free:
+                e.record(cur)
+            self._upload(i)
+            self.primed = True
+        self._upload(i + 1)                                   # next step's inputs, overlapped with this step's compute
+        slot = i % 2
+        cur.wait_event(self.ready[slot])
+        st = self.stage[slot]
+        A = {k: st[k].detach().requires_grad_(True) for k in self.keys}
         rgbs, _ = self.dr.render(no_mask=True, **A)
-        loss = self.dr.recon_data(rgbs, gt, no_mask=True, contour=0.1)
+        loss = self.dr.recon_data(rgbs, st['gt'], no_mask=True, contour=0.1)
         loss.backward()
+        self.free[slot].record(cur)
         self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         return loss
 
@@ -361,6 +388,8 @@ def main():
     Ke = max(3, min(K, 200))
     for i in range(3):
         e2e_runner.step(i)
+    torch.cuda.synchronize()
+    e2e_runner.primed = False                 # the timed region uploads its own first batch
     ms_e_local = timed(torch, world, e2e_runner.step, Ke)
     ms_e, units_e = aggregate(ms_e_local, B_PER_GPU * Ke, world)
 
@@ -400,7 +429,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": units_e / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e_runner.h2d_bytes,
                     "d2h_bytes_per_step": e2e_runner.d2h_bytes, "steps": Ke,
-                    "api": "DiffRender.render -> recon_data -> backward (pinned host inputs)"},
+                    "api": "DiffRender.render -> recon_data -> backward; pinned host inputs copied every step on a copy stream (double-buffered)"},
             "gpu_launches": len(KERNELS) * K,
             "roofline": roof,
         }
