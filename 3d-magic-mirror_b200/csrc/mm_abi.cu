@@ -75,23 +75,22 @@ void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int no_mask, mm_raster_
 
 void set_ws(const mm_ws_layout& L, char* ws, mm_raster_params& p) {
     p.frec = (const float*)(ws + L.frec);
-    p.maskS = (const uint32_t*)(ws + L.maskS); p.maskH = (const uint32_t*)(ws + L.maskH);
-    p.tflag = (const unsigned char*)(ws + L.tflag); p.glist = (const uint32_t*)(ws + L.glist);
-    p.gctr = (uint32_t*)(ws + L.gctr); p.gsoft = (float*)(ws + L.gsoft);
-    p.face_idx_ws = (int32_t*)(ws + L.face_idx);
+    p.zbuf = (unsigned long long*)(ws + L.zbuf); p.lacc = (unsigned long long*)(ws + L.lacc);
+    p.ovf_list = (uint32_t*)(ws + L.ovf_list); p.ovf_count = (uint32_t*)(ws + L.ovf_count);
+    p.gsoft = (float*)(ws + L.gsoft);
     p.part_fwd = (float*)(ws + L.part_fwd); p.part_bwd = (float*)(ws + L.part_bwd);
     p.img_fwd = (float*)(ws + L.img_fwd); p.img_bwd = (float*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
     p.gfacc = (float*)(ws + L.gfacc);
 }
 
-void launch_vertex_fwd(const mm_ctx* c, int B, const mm_ws_layout& L, char* ws, const float* vertices, const float* azim,
-                       const float* elev, const float* dist, const float* bias, float* face_normals, bool zero_gfacc,
-                       cudaStream_t s) {
-    cudaMemsetAsync(ws + L.gctr, 0, 16, s);          // work-list length + tickets of this forward/backward pair
-    mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (uint32_t*)(ws + L.maskS),
-                         (uint32_t*)(ws + L.maskH), (unsigned char*)(ws + L.tflag), (uint32_t*)(ws + L.glist),
-                         (uint32_t*)(ws + L.gctr), (float*)(ws + L.vimg), face_normals,
+// vertex stage + the single memset that clears the visibility buffer, the silhouette accumulators and the overflow counter
+int launch_vertex_fwd(const mm_ctx* c, int B, const mm_ws_layout& L, char* ws, const float* vertices, const float* azim,
+                      const float* elev, const float* dist, const float* bias, float* face_normals, bool zero_gfacc,
+                      cudaStream_t s) {
+    if (cudaMemsetAsync(ws + L.zbuf, 0, (L.ovf_count + 16) - L.zbuf, s) != cudaSuccess) return 1;
+    mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg), face_normals,
                          zero_gfacc ? (float*)(ws + L.gfacc) : nullptr, (uint32_t*)(ws + L.tickets), s);
+    return 0;
 }
 
 }  // namespace
@@ -139,18 +138,10 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     if (c->nst > 65535) { delete c; return fail(MM_E_UNSUPPORTED, "image too large: %d sub-tiles exceed the 16-bit work-list ids", c->nst); }
     if (F > 65535) { delete c; return fail(MM_E_UNSUPPORTED, "F=%d exceeds the 16-bit face ids of the soft-pass lists", F); }
     const size_t smem_max = prop.sharedMemPerBlockOptin;
-    // vertex stage: sub-tile rows per CTA such that the two chunk masks fit in <= 96 KB and an image gets >= 4 CTAs
-    {
-        const size_t row_bytes = 2 * (size_t)c->nstx * c->nwords * 4;
-        int rows = (int)((96 * 1024) / row_bytes);
-        if (rows < 1) rows = 1;
-        const int want = (c->nsty + 3) / 4;
-        if (rows > want) rows = want;
-        if (const char* e = getenv("MM_CHUNK_ROWS")) { const int v = atoi(e); if (v > 0) rows = v; }
-        if (rows > c->nsty) rows = c->nsty;
-        c->chunk_rows = rows;
-        c->nchunks = (c->nsty + rows - 1) / rows;
-    }
+    // vertex stage: CTAs per image (each recomputes the vertex transform and emits 1/nchunks of the face records)
+    c->nchunks = 4;
+    if (const char* e = getenv("MM_VCHUNKS")) { const int v = atoi(e); if (v > 0 && v <= 32) c->nchunks = v; }
+    c->chunk_rows = 0;
     c->smem_vertex_fwd = mm_vertex_smem_fwd(c);
     c->smem_raster = mm_raster_smem_bytes(c);
     const size_t vs_f = c->smem_vertex_fwd, vs_b = mm_vertex_smem_bwd(V);

@@ -12,14 +12,9 @@
 //                          n = unit face normal in camera space.  48 B / face, one
 //                          contiguous block per image so a CTA stages it with ONE
 //                          cp.async.bulk (TMA bulk copy) into shared memory.
-//     maskS/H    [B,NST,NW] per-sub-tile face BITMASKS written by the vertex stage (NST = sub-tiles per
-//                          image, NW = ceil(F/32)): bit f of sub-tile s is set iff face f's bbox enlarged by
-//                          `boxlen` (S) / front face f's tight bbox (H) can touch s.  A bitmask keeps faces in
-//                          index order, which DIB-R's "first knum faces" truncation needs.
-//     tflag      [B,NST] u8   1 iff the sub-tile's S mask has any bit (something can touch it)
-//     glist      [B*NST] u32  all non-empty sub-tiles of the batch, (image << 16 | sub-tile), compacted by the vertex
-//                             stage through one atomic counter: the geometry kernels' global work list
-//     gctr       [4]     u32  {list length, forward ticket, backward ticket, -}
+//     zbuf       [B,H,W] u64  visibility buffer: (order-preserving depth << 32 | ~face), atomicMax-resolved; 0 = uncovered
+//     lacc       [B,H,W] u64  soft-silhouette accumulator of uncovered pixels: fixed-point sum log(1-p) << 16 | count
+//     ovf_list   [B*H*W] u32  pixels that saw more than knum candidates (ordered re-scan), ovf_count [1] u32
 //     gsoft      [B,H,W]      d(loss)/d(silhouette) per pixel, handed from the shading backward to the geometry backward
 //     vimg       [B,V,2]   unscaled image-plane xy (debug export / parity tests)
 //     face_idx   [B,H,W]   int32 winner of the hard pass (-1 none); saved for backward
@@ -79,7 +74,7 @@ struct mm_ctx {
 };
 
 struct mm_ws_layout {
-    size_t frec, maskS, maskH, tflag, glist, gctr, gsoft, vimg, face_idx, gfacc, part_fwd, part_bwd, img_fwd, img_bwd, tickets, total;
+    size_t frec, zbuf, lacc, ovf_count, ovf_list, gsoft, vimg, gfacc, part_fwd, part_bwd, img_fwd, img_bwd, tickets, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -95,14 +90,13 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     mm_ws_layout L;
     size_t off = 0;
     L.frec = off;     off = mm_align_up(off + (size_t)B * c->F * MM_REC_FLOATS * 4, 256);
-    L.maskS = off;    off = mm_align_up(off + (size_t)B * c->nst * c->nwords * 4, 256);
-    L.maskH = off;    off = mm_align_up(off + (size_t)B * c->nst * c->nwords * 4, 256);
-    L.tflag = off;    off = mm_align_up(off + (size_t)B * c->nst, 256);
-    L.glist = off;    off = mm_align_up(off + (size_t)B * c->nst * 4, 256);
-    L.gctr = off;     off = mm_align_up(off + 16, 256);
+    // zbuf, lacc and ovf_count are contiguous: one memset clears them at the start of every forward
+    L.zbuf = off;     off = mm_align_up(off + (size_t)B * c->H * c->W * 8, 256);
+    L.lacc = off;     off = mm_align_up(off + (size_t)B * c->H * c->W * 8, 256);
+    L.ovf_count = off; off = mm_align_up(off + 16, 256);
+    L.ovf_list = off; off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.gsoft = off;    off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.vimg = off;     off = mm_align_up(off + (size_t)B * c->V * 2 * 4, 256);
-    L.face_idx = off; off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.gfacc = off;    off = mm_align_up(off + (size_t)B * c->F * 9 * 4, 256);
     const int rp = (c->nst + MM_WARPS - 1) / MM_WARPS;          // shading CTAs per image (8 sub-tiles each)
     const size_t np = (size_t)(rp > c->nparts_recon ? rp : c->nparts_recon);
@@ -122,11 +116,10 @@ struct mm_raster_params {
     float sx, sy, blen, multiplier, eps, sigmainv;
     int no_mask;
     const float* frec;       // [B,F,12]
-    const uint32_t* maskS;   // [B,NST,NW]
-    const uint32_t* maskH;   // [B,NST,NW]
-    const unsigned char* tflag;   // [B,NST]
-    const uint32_t* glist;   // [B*NST]
-    uint32_t* gctr;          // [4]
+    unsigned long long* zbuf;     // [B,H,W]
+    unsigned long long* lacc;     // [B,H,W]
+    uint32_t* ovf_list;      // [B*H*W]
+    uint32_t* ovf_count;     // [1]
     float* gsoft;            // [B,H,W]
     const float* face_uvs;   // [F,6]
     const float* tex;        // [B,3,Ht,Wt]
@@ -136,7 +129,6 @@ struct mm_raster_params {
     const int32_t* tab;      // contour tables
     float* rgba;             // [B,4,H,W]
     float* imnormal;         // [B,H,W,3] or NULL
-    int32_t* face_idx_ws;    // [B,H,W]
     int32_t* face_idx_out;   // [B,H,W] or NULL
     float* part_fwd;         // [B,NP,4]
     float* img_fwd;          // [B,4]
@@ -155,8 +147,7 @@ struct mm_raster_params {
 
 // launchers (defined in the .cu files)
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
-                          const float* dist, const float* bias, float* frec, uint32_t* maskS, uint32_t* maskH,
-                          unsigned char* tflag, uint32_t* glist, uint32_t* gctr,
+                          const float* dist, const float* bias, float* frec,
                           float* vimg, float* face_normals, float* gfacc_zero, uint32_t* tickets, cudaStream_t s);
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,

@@ -246,6 +246,36 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return r;
 }
 
+// ------------------------------------------------------------------ per-pixel soft-silhouette accumulator
+// One 64-bit word per pixel, updated with ONE integer atomicAdd per (pixel, face) candidate:
+//   bits 63..16  sum of log(1 - p_k) in fixed point (scale 2^32, two's complement; |sum| < 2^15)
+//   bits 15..0   number of candidates seen (0xFFFF = "truncated at knum: exact ordered value stored by the overflow pass")
+// Integer addition is associative, so the silhouette does not depend on the order in which face threads arrive
+// (a float atomicAdd would make the image differ from run to run in the last bit).
+#define MM_LACC_SCALE 4294967296.0
+#define MM_LACC_OVF   0xFFFFull
+__device__ __forceinline__ unsigned long long lacc_term(float log1m_p) {
+    const long long fx = __double2ll_rn((double)fmaxf(log1m_p, -80.0f) * MM_LACC_SCALE);
+    return ((unsigned long long)fx << 16) + 1ull;
+}
+__device__ __forceinline__ int lacc_count(unsigned long long a) { return (int)(a & 0xFFFFull); }
+__device__ __forceinline__ float lacc_logsum(unsigned long long a) { return (float)((double)((long long)a >> 16) / MM_LACC_SCALE); }
+__device__ __forceinline__ unsigned long long lacc_exact(float log_allprob) {
+    const long long fx = __double2ll_rn((double)fmaxf(log_allprob, -2400.0f) * MM_LACC_SCALE);
+    return ((unsigned long long)fx << 16) | MM_LACC_OVF;
+}
+// silhouette value of an uncovered pixel: 1 - prod(1 - p_k) = -expm1(sum log(1 - p_k))
+__device__ __forceinline__ float lacc_soft(unsigned long long a) { return (a == 0ull) ? 0.0f : -expm1f(lacc_logsum(a)); }
+
+// visibility buffer: (order-preserving depth << 32) | ~face ; atomicMax == "largest z, then smallest face index",
+// i.e. the reference's "strictly greater z replaces, first face wins ties" scan (DIBR_SPEC A.2).  0 = uncovered.
+__device__ __forceinline__ unsigned long long depth_key(float z, int f) {
+    const uint32_t b = __float_as_uint(z);
+    const uint32_t zo = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ((unsigned long long)zo << 32) | (unsigned long long)(0xffffffffu - (uint32_t)f);
+}
+__device__ __forceinline__ int key_face(unsigned long long key) { return key ? (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull)) : -1; }
+
 // ------------------------------------------------------------------ TMA bulk copy (global -> shared) helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

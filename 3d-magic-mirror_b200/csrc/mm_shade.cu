@@ -1,9 +1,8 @@
 // mm_shade.cu -- the STREAMING half of the per-pixel stage: shading (UV texture sampling, SH lighting, composite,
 // clamp), the recon_data loss terms, and their backward.  Replaces kaolin texture_mapping /
 // spherical_harmonic_lighting, the ~40 elementwise torch kernels of networks.py:303-317 and :364-390, and their
-// autograd.  Visibility (`face_idx`) and the soft silhouette come from the geometry kernels (mm_raster.cu); they are
-// only read for sub-tiles whose face list is non-empty (`tflag`), so the ~2/3 of the image that is plain background
-// never touches geometry at all.
+// autograd.  Visibility and the soft silhouette come from the geometry kernels (mm_raster.cu) as two 64-bit words
+// per pixel: the atomicMax-resolved (depth, face) key and the fixed-point log-product accumulator.
 //
 // One thread per pixel, one warp per 8x4-pixel sub-tile (the layout of the geometry kernels: a warp's stores are
 // four 32-byte row segments, i.e. whole sectors), 8 sub-tiles per CTA, plain non-persistent grid = (ceil(NST/8), B):
@@ -74,13 +73,12 @@ k_shade_fwd(const mm_raster_params p)
         const int sty = st / p.nstx, stx = st - sty * p.nstx;
         const int ix = stx * MM_ST_W + (lane & 7), iy = sty * MM_ST_H + (lane >> 3);
         const bool active = (ix < p.W) && (iy < p.H);
-        const bool geom = p.tflag[(size_t)b * p.nst + st] != 0;      // warp-uniform: did the geometry kernel visit this tile?
         int best_f = -1;
         float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, soft = 0.0f;
-        if (geom && active) {
+        if (active) {
             const size_t pix0 = (size_t)iy * p.W + ix;
-            best_f = p.face_idx_ws[(size_t)b * HW + pix0];
-            soft = p.rgba[(size_t)b * 4 * HW + 3 * HW + pix0];
+            best_f = key_face(p.zbuf[(size_t)b * HW + pix0]);
+            soft = (best_f >= 0) ? 1.0f : lacc_soft(p.lacc[(size_t)b * HW + pix0]);
             if (best_f >= 0) {                                       // the winner's weights, same instruction sequence as the hard pass
                 const FaceRec r = load_rec(rec, best_f);
                 Bary bb;
@@ -191,10 +189,9 @@ k_shade_bwd(const mm_raster_params p)
         const int sty = st / p.nstx, stx = st - sty * p.nstx;
         const int ix = stx * MM_ST_W + (lane & 7), iy = sty * MM_ST_H + (lane >> 3);
         const bool active = (ix < W) && (iy < H);
-        const bool geom = p.tflag[(size_t)b * p.nst + st] != 0;
         const float x0 = pix_x(ix, W, p.sx), y0 = pix_y(iy, H, p.sy);
         const size_t pix = active ? (size_t)iy * W + ix : 0;
-        const int best_f = (active && geom) ? p.face_idx_ws[(size_t)b * HW + pix] : -1;
+        const int best_f = active ? key_face(p.zbuf[(size_t)b * HW + pix]) : -1;
         // ---- upstream gradient of the 4 output channels
         float g_img[3] = {0.0f, 0.0f, 0.0f}, g_soft = 0.0f;
         float soft = 0.0f, gm_lane = 0.0f;
@@ -245,8 +242,8 @@ k_shade_bwd(const mm_raster_params p)
             if (active) g_soft += k_cont * (own + ((lane == ref_lane) ? t : 0.0f));
         }
 
-        // hand d(loss)/d(silhouette) to the geometry backward (only tiles with geometry can use it)
-        if (geom && active) p.gsoft[(size_t)b * HW + pix] = (best_f < 0) ? g_soft : 0.0f;
+        // hand d(loss)/d(silhouette) to the geometry backward (only uncovered pixels that saw a candidate can use it)
+        if (active && best_f < 0 && soft > 0.0f) p.gsoft[(size_t)b * HW + pix] = g_soft;
 
         if (active) {
             // ---- shading backward

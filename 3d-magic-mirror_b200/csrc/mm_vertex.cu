@@ -4,8 +4,7 @@
 // (smr_utils.py:257-281), generate_transformation_matrix (smr_utils.py:284-311),
 // kaolin prepare_vertices (networks.py:284-287: [v,1]*T, perspective divide, gather
 // by faces, unit face normals) and the second face_normals call (networks.py:289),
-// emits the 48-byte face records the raster kernels read, and bins every face into
-// the per-sub-tile bitmasks (the "tile face lists").
+// and emits the 48-byte face records the geometry kernels read.
 // The reference runs ~25 tiny kernels + a cuBLAS matmul for this.
 //
 // Backward consumes the per-face accumulators (d/d fvi, d/d unit normal) produced by
@@ -59,12 +58,11 @@ __device__ inline void transform_vertex(const float* T, float x, float y, float 
 }
 
 // ------------------------------------------------------------------ forward
-// grid = (nchunks, B).  Every CTA of an image recomputes the (tiny) vertex transform, writes the face
-// records of its contiguous 1/nchunks share of the faces, and bins ALL faces into the bitmasks of its own
-// `chunk_rows` sub-tile rows (built in shared memory with atomicOr, then streamed out coalesced).
+// grid = (nchunks, B): every CTA of an image recomputes the (tiny) vertex transform into shared memory and emits the
+// face records / normals of its contiguous 1/nchunks share of the faces.
 struct VertexFwdParams {
-    int V, F, H, W, nstx, nsty, nwords, chunk_rows, nchunks;
-    float proj_x, proj_y, multiplier, sx, sy, blen;
+    int V, F, nchunks;
+    float proj_x, proj_y, multiplier;
 };
 
 __global__ void __launch_bounds__(MM_VTHREADS)
@@ -72,29 +70,21 @@ k_vertex_fwd(const VertexFwdParams q,
              const int32_t* __restrict__ faces, const float* __restrict__ vertices,
              const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
              const float* __restrict__ bias,
-             float* __restrict__ frec, uint32_t* __restrict__ maskS, uint32_t* __restrict__ maskH,
-             unsigned char* __restrict__ tflag, uint32_t* __restrict__ glist, uint32_t* __restrict__ gctr,
-             float* __restrict__ vimg, float* __restrict__ face_normals, float* __restrict__ gfacc_zero,
-             uint32_t* __restrict__ tickets)
+             float* __restrict__ frec, float* __restrict__ vimg, float* __restrict__ face_normals,
+             float* __restrict__ gfacc_zero, uint32_t* __restrict__ tickets)
 {
     extern __shared__ float sm[];
     const int V = q.V, F = q.F;
     float* sT = sm;                    // 12
     float* svc = sm + 16;              // V*3 camera-space
     float* svi = svc + (size_t)V * 3;  // V*2 image-plane (unscaled)
-    uint32_t* smS = reinterpret_cast<uint32_t*>(svi + (size_t)V * 2);
     const int chunk = blockIdx.x, b = blockIdx.y;
-    const int row0 = chunk * q.chunk_rows;
-    const int rows = min(q.chunk_rows, q.nsty - row0);
-    const int nmask = rows * q.nstx * q.nwords;
-    uint32_t* smH = smS + (size_t)q.chunk_rows * q.nstx * q.nwords;
     if (threadIdx.x == 0) {
         Cam c;
         camera_setup(azim[b], elev[b], dist[b], bias[b * 2], bias[b * 2 + 1], c);
         for (int i = 0; i < 12; ++i) sT[i] = c.T[i];
         if (chunk == 0) { tickets[b * 4] = 0u; tickets[b * 4 + 1] = 0u; tickets[b * 4 + 2] = 0u; tickets[b * 4 + 3] = 0u; }
     }
-    for (int i = threadIdx.x; i < nmask; i += blockDim.x) { smS[i] = 0u; smH[i] = 0u; }
     __syncthreads();
     const float* vb = vertices + (size_t)b * V * 3;
     for (int v = threadIdx.x; v < V; v += blockDim.x) {
@@ -112,10 +102,9 @@ k_vertex_fwd(const VertexFwdParams q,
     }
     __syncthreads();
     float4* rec = reinterpret_cast<float4*>(frec + (size_t)b * F * MM_REC_FLOATS);
-    const float inv_sx = 1.0f / q.sx, inv_sy = 1.0f / q.sy;
-    const int py0 = row0 * MM_ST_H, prow = rows * MM_ST_H;     // pixel rows covered by this chunk
-    const int per_chunk = (F + q.nchunks - 1) / q.nchunks;   // contiguous face range whose records this CTA writes
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    const int per_chunk = (F + q.nchunks - 1) / q.nchunks;
+    const int f_end = min(F, (chunk + 1) * per_chunk);
+    for (int f = chunk * per_chunk + threadIdx.x; f < f_end; f += blockDim.x) {
         const int i0 = faces[f * 3], i1 = faces[f * 3 + 1], i2 = faces[f * 3 + 2];
         const float ax = svc[i0 * 3], ay = svc[i0 * 3 + 1], az = svc[i0 * 3 + 2];
         const float bx = svc[i1 * 3], by = svc[i1 * 3 + 1], bz = svc[i1 * 3 + 2];
@@ -129,87 +118,19 @@ k_vertex_fwd(const VertexFwdParams q,
         const float inv = len + 1e-10f;
         nx /= inv; ny /= inv; nz /= inv;
         // image-plane corners scaled by `multiplier` (DIBR_SPEC A.1), one rounding each
-        const float sax = __fmul_rn(svi[i0 * 2], q.multiplier), say = __fmul_rn(svi[i0 * 2 + 1], q.multiplier);
-        const float sbx = __fmul_rn(svi[i1 * 2], q.multiplier), sby = __fmul_rn(svi[i1 * 2 + 1], q.multiplier);
-        const float scx = __fmul_rn(svi[i2 * 2], q.multiplier), scy = __fmul_rn(svi[i2 * 2 + 1], q.multiplier);
-        if ((f / per_chunk) == chunk) {
-            rec[f * 3 + 0] = make_float4(sax, say, sbx, sby);
-            rec[f * 3 + 1] = make_float4(scx, scy, az, bz);
-            rec[f * 3 + 2] = make_float4(cz, nx, ny, nz);
-            if (face_normals) {
-                float* fn = face_normals + ((size_t)b * F + f) * 3;
-                fn[0] = nx; fn[1] = ny; fn[2] = nz;
-            }
-            if (gfacc_zero) {
-                float* g = gfacc_zero + ((size_t)b * F + f) * 9;
-                #pragma unroll
-                for (int i = 0; i < 9; ++i) g[i] = 0.0f;
-            }
+        rec[f * 3 + 0] = make_float4(__fmul_rn(svi[i0 * 2], q.multiplier), __fmul_rn(svi[i0 * 2 + 1], q.multiplier),
+                                     __fmul_rn(svi[i1 * 2], q.multiplier), __fmul_rn(svi[i1 * 2 + 1], q.multiplier));
+        rec[f * 3 + 1] = make_float4(__fmul_rn(svi[i2 * 2], q.multiplier), __fmul_rn(svi[i2 * 2 + 1], q.multiplier), az, bz);
+        rec[f * 3 + 2] = make_float4(cz, nx, ny, nz);
+        if (face_normals) {
+            float* fn = face_normals + ((size_t)b * F + f) * 3;
+            fn[0] = nx; fn[1] = ny; fn[2] = nz;
         }
-        // ---- binning: conservative pixel ranges (exact tests are redone per pixel in the raster kernels)
-        const float xmin = fminf(fminf(sax, sbx), scx), xmax = fmaxf(fmaxf(sax, sbx), scx);
-        const float ymin = fminf(fminf(say, sby), scy), ymax = fmaxf(fmaxf(say, sby), scy);
-        const float xl = xmin - q.blen, xh = xmax + q.blen, yl = ymin - q.blen, yh = ymax + q.blen;
-        float fx_lo = (xl * inv_sx + (float)(q.W - 1)) * 0.5f;
-        float fx_hi = (xh * inv_sx + (float)(q.W - 1)) * 0.5f;
-        float fy_lo = ((float)(q.H - 1) - yh * inv_sy) * 0.5f;
-        float fy_hi = ((float)(q.H - 1) - yl * inv_sy) * 0.5f;
-        // NaN/Inf coordinates (vertex on the camera plane) must stay conservative: treat as "everywhere"
-        if (!(fx_lo == fx_lo) || !(fx_hi == fx_hi)) { fx_lo = -4.0f; fx_hi = 1.0e6f; }
-        if (!(fy_lo == fy_lo) || !(fy_hi == fy_hi)) { fy_lo = -4.0f; fy_hi = 1.0e6f; }
-        fx_lo = fminf(fmaxf(fx_lo, -4.0f), 1.0e6f); fx_hi = fminf(fmaxf(fx_hi, -4.0f), 1.0e6f);
-        fy_lo = fminf(fmaxf(fy_lo, -4.0f), 1.0e6f); fy_hi = fminf(fmaxf(fy_hi, -4.0f), 1.0e6f);
-        const int ix0 = max((int)floorf(fx_lo), 0), ix1 = min((int)ceilf(fx_hi), q.W - 1);
-        const int iy0 = max((int)floorf(fy_lo) - py0, 0), iy1 = min((int)ceilf(fy_hi) - py0, prow - 1);
-        if (ix0 > ix1 || iy0 > iy1) continue;
-        const bool front = nz >= 0.0f;
-        const float bpx = q.blen * inv_sx * 0.5f, bpy = q.blen * inv_sy * 0.5f;
-        const int hx0 = max((int)floorf(fx_lo + bpx), 0), hx1 = min((int)ceilf(fx_hi - bpx), q.W - 1);
-        const int hy0 = max((int)floorf(fy_lo + bpy) - py0, 0), hy1 = min((int)ceilf(fy_hi - bpy) - py0, prow - 1);
-        const uint32_t bit = 1u << (f & 31);
-        const int wd = f >> 5;
-        for (int sy = iy0 >> 2; sy <= (iy1 >> 2); ++sy) {
-            for (int sxi = ix0 >> 3; sxi <= (ix1 >> 3); ++sxi) {
-                const int st = sy * q.nstx + sxi;
-                atomicOr(&smS[st * q.nwords + wd], bit);
-                if (front && sxi >= (hx0 >> 3) && sxi <= (hx1 >> 3) && sy >= (hy0 >> 2) && sy <= (hy1 >> 2))
-                    atomicOr(&smH[st * q.nwords + wd], bit);
-            }
+        if (gfacc_zero) {
+            float* g = gfacc_zero + ((size_t)b * F + f) * 9;
+            #pragma unroll
+            for (int i = 0; i < 9; ++i) g[i] = 0.0f;
         }
-    }
-    __syncthreads();
-    const size_t gbase = ((size_t)b * q.nsty * q.nstx + (size_t)row0 * q.nstx) * q.nwords;
-    for (int i = threadIdx.x; i < nmask; i += blockDim.x) { maskS[gbase + i] = smS[i]; maskH[gbase + i] = smH[i]; }
-    // ---- per-sub-tile "anything can touch it" flag; the non-empty sub-tiles of the whole batch are appended to ONE
-    // global work list (one atomicAdd per CTA reserves the range) that the geometry kernels consume
-    __shared__ int s_wcount[MM_VTHREADS / 32];
-    __shared__ uint32_t s_gbase;
-    const int ntile = rows * q.nstx;
-    const int nst = q.nsty * q.nstx;
-    const int tile0 = row0 * q.nstx;
-    for (int t0 = 0; t0 < ntile; t0 += blockDim.x) {
-        const int t = t0 + threadIdx.x;
-        bool nonempty = false;
-        if (t < ntile) {
-            uint32_t any = 0u;
-            for (int w = 0; w < q.nwords; ++w) any |= smS[t * q.nwords + w];
-            nonempty = any != 0u;
-            tflag[(size_t)b * nst + tile0 + t] = nonempty ? 1 : 0;
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, nonempty);
-        const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
-        if (ln == 0) s_wcount[wid] = __popc(bal);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int tot = 0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_wcount[w];
-            s_gbase = tot ? atomicAdd(gctr, (uint32_t)tot) : 0u;
-        }
-        __syncthreads();
-        int off = 0;
-        for (int w = 0; w < wid; ++w) off += s_wcount[w];
-        if (nonempty) glist[s_gbase + off + __popc(bal & ((1u << ln) - 1u))] = ((uint32_t)b << 16) | (uint32_t)(tile0 + t);
-        __syncthreads();
     }
 }
 
@@ -387,17 +308,15 @@ __global__ void k_export_faces(int V, int F, float multiplier, const int32_t* __
 }  // namespace
 
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
-                          const float* dist, const float* bias, float* frec, uint32_t* maskS, uint32_t* maskH,
-                          unsigned char* tflag, uint32_t* glist, uint32_t* gctr,
+                          const float* dist, const float* bias, float* frec,
                           float* vimg, float* face_normals, float* gfacc_zero, uint32_t* tickets, cudaStream_t s)
 {
     VertexFwdParams q;
-    q.V = c->V; q.F = c->F; q.H = c->H; q.W = c->W; q.nstx = c->nstx; q.nsty = c->nsty; q.nwords = c->nwords;
-    q.chunk_rows = c->chunk_rows; q.nchunks = c->nchunks;
-    q.proj_x = c->proj_x; q.proj_y = c->proj_y; q.multiplier = c->multiplier; q.sx = c->sx; q.sy = c->sy; q.blen = c->blen;
+    q.V = c->V; q.F = c->F; q.nchunks = c->nchunks;
+    q.proj_x = c->proj_x; q.proj_y = c->proj_y; q.multiplier = c->multiplier;
     const dim3 grid(c->nchunks, B);
-    k_vertex_fwd<<<grid, MM_VTHREADS, c->smem_vertex_fwd, s>>>(q, c->d_faces, vertices, azim, elev, dist, bias, frec, maskS,
-                                                       maskH, tflag, glist, gctr, vimg, face_normals, gfacc_zero, tickets);
+    k_vertex_fwd<<<grid, MM_VTHREADS, c->smem_vertex_fwd, s>>>(q, c->d_faces, vertices, azim, elev, dist, bias, frec,
+                                                               vimg, face_normals, gfacc_zero, tickets);
 }
 
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
@@ -419,9 +338,7 @@ void mm_launch_export_faces(const mm_ctx* c, int B, const float* frec, const flo
                                                        fnz, total);
 }
 
-size_t mm_vertex_smem_fwd(const mm_ctx* c) {
-    return (16 + (size_t)c->V * 5) * sizeof(float) + 2 * (size_t)c->chunk_rows * c->nstx * c->nwords * sizeof(uint32_t);
-}
+size_t mm_vertex_smem_fwd(const mm_ctx* c) { return (16 + (size_t)c->V * 5) * sizeof(float); }
 size_t mm_vertex_smem_bwd(int V) { return ((size_t)V * 6) * sizeof(float); }
 void mm_vertex_set_smem(size_t fwd, size_t bwd) {
     cudaFuncSetAttribute(k_vertex_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd);
