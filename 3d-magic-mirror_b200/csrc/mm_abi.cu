@@ -107,6 +107,7 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     MM_REQUIRE(out != nullptr, "out");
     *out = nullptr;
     MM_REQUIRE(V > 0 && F > 0 && H > 0 && W > 0, "V, F, H, W must be positive");
+    MM_REQUIRE(H <= 4095 && W <= 4095, "H, W must be <= 4095 (12-bit pixel coordinates in the scatter queue)");
     MM_REQUIRE(faces_host && face_uvs_host, "faces_host / face_uvs_host");
     MM_REQUIRE(knum > 0 && knum <= MM_MAX_KNUM, "knum out of range");
     MM_REQUIRE(multiplier > 0.0f, "multiplier");

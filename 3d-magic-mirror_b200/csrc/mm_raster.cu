@@ -7,22 +7,21 @@
 // bookkeeping: ncu showed ~4500 warp-instructions per 8x4-pixel tile for ~100 useful (pixel, face) pairs.  This file
 // SCATTERS instead: the unit of work is a face.
 //
-//   k_hard        4 lanes per (image, face): rasterise the face's tight bbox (rows interleaved over the 4 lanes), exact
-//                 DIB-R inside test + depth, resolve visibility with ONE 64-bit atomicMax per covered pixel on a packed
-//                 (order-preserving depth << 32 | ~face) key.  max == "largest z, then smallest face index" == the
-//                 reference's ordered scan with its strictly-greater test, so `face_idx` is bit-exact and independent
-//                 of thread order.  No binning, no face lists, no shared memory.
-//   k_soft_fwd    4 lanes per (image, face), all faces: walk the bbox enlarged by `boxlen`; for every UNCOVERED pixel
-//                 inside (exact half-open test) evaluate the DIB-R distance / probability once and fold
-//                 log(1 - p) and a candidate count into the pixel's 64-bit accumulator with ONE integer atomicAdd
-//                 (fixed point => order independent => deterministic).  A pixel whose count reaches knum + 1 is
-//                 appended to the overflow list.
+//   k_scatter<HARD>      4 lanes per (image, face): walk the face's tight bbox, exact DIB-R inside test + depth, resolve
+//                 visibility with ONE 64-bit atomicMax per covered pixel on a packed (order-preserving depth << 32 |
+//                 ~face) key.  max == "largest z, then smallest face index" == the reference's ordered scan with its
+//                 strictly-greater test, so `face_idx` is bit-exact and independent of thread order.  No binning, no
+//                 face lists.
+//   k_scatter<SOFT_FWD>  all faces: walk the bbox enlarged by `boxlen`; for every UNCOVERED pixel inside (exact
+//                 half-open test) evaluate the DIB-R distance / probability once and fold log(1 - p) and a candidate
+//                 count into the pixel's 64-bit accumulator with ONE integer atomicAdd (fixed point => order
+//                 independent => deterministic).  A pixel whose count reaches knum + 1 is appended to the overflow list.
+//   k_scatter<SOFT_BWD>  same walk; gradients are accumulated per face slot in shared memory and leave as <= 6 atomics
+//                 per face.
 //   k_soft_ovf    rare path (far cameras): DIB-R keeps only the FIRST knum candidates in face-index order.  One warp per
 //                 overflowed pixel replays the reference's ordered scan over all faces (32 faces per step, ballot keeps
 //                 the order) and stores the exact truncated product; the backward variant scatters the gradients of
 //                 exactly those knum candidates.
-//   k_soft_bwd    4 lanes per (image, face): same walk; the face's 6 corner gradients are accumulated in REGISTERS over
-//                 all its pixels, combined over the 4 lanes with shuffles, and leave as <= 6 atomics per face.
 //   Backward re-derives every probability from the face records instead of storing Kaolin's knum-deep side buffers
 //   (B*H*W*30*(4+8+1) B = 307 MB at B=48,128^2).
 #include "mm_device.cuh"
@@ -30,7 +29,6 @@
 namespace {
 
 #define FULL 0xffffffffu
-#define LANES_PER_FACE 4
 
 struct PixRange { int ix0, ix1, iy0, iy1; };
 
@@ -55,72 +53,38 @@ __device__ __forceinline__ bool pix_range(const mm_raster_params& p, float xl, f
     return r.ix0 <= r.ix1 && r.iy0 <= r.iy1;
 }
 
-// ---------------------------------------------------------------------------------------------- hard pass
-__global__ void __launch_bounds__(256)
-k_hard(const mm_raster_params p)
-{
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int q = gid & (LANES_PER_FACE - 1);
-    const int fid = gid / LANES_PER_FACE;
-    if (fid >= p.B * p.F) return;
-    const int b = fid / p.F, f = fid - b * p.F;
-    const FaceRec r = load_rec(p.frec + (size_t)b * p.F * MM_REC_FLOATS, f);
-    if (!(r.nz >= 0.0f)) return;                                   // DIBR_SPEC A.2: front faces only
-    const float xmin = fminf(fminf(r.ax, r.bx), r.cx), xmax = fmaxf(fmaxf(r.ax, r.bx), r.cx);
-    const float ymin = fminf(fminf(r.ay, r.by), r.cy), ymax = fmaxf(fmaxf(r.ay, r.by), r.cy);
-    PixRange pr;
-    if (!pix_range(p, xmin, xmax, ymin, ymax, pr)) return;
-    unsigned long long* zb = p.zbuf + (size_t)b * p.H * p.W;
-    for (int iy = pr.iy0 + q; iy <= pr.iy1; iy += LANES_PER_FACE) {
-        const float py = pix_y(iy, p.H, p.sy);
-        if (py < ymin || py >= ymax) continue;
-        for (int ix = pr.ix0; ix <= pr.ix1; ++ix) {
-            float w0, w1, w2, zz;
-            if (hard_test(r, pix_x(ix, p.W, p.sx), py, p.eps, w0, w1, w2, zz))
-                atomicMax(zb + (size_t)iy * p.W + ix, depth_key(zz, f));
-        }
-    }
+// ---------------------------------------------------------------------------------------------- the scatter engine
+// A warp owns FPW = 8 consecutive faces.  Set-up (8 lanes): load the record, compute the bbox (tight / enlarged) and
+// turn the half-open fp32 bbox test into an EXACT pixel rectangle (conservative float->int estimate, then <= 2
+// correction steps per side with the very comparison the reference uses; pixel centres are monotone in the index).
+// Every (face, pixel) pair of the 8 rectangles then gets a global number; the pairs are dealt to the 32 lanes
+// round-robin, so the warp is balanced whatever the face sizes, and no per-pixel bbox test is left.
+//   hard pass : every pair runs the inside test + depth (2 IEEE divisions) and, if inside, one atomicMax.
+//   soft pass : the expensive arithmetic applies only to UNCOVERED pixels, a sparse subset; running it inside the
+//               per-pair loop measured 80 warp-instructions per useful pair (~10 % lane utilisation).  So the loop
+//               only filters (one 8-byte load), ballot-compacts the qualifying pairs into a small shared-memory queue,
+//               and whenever 32 are waiting the whole warp evaluates them, one pair per lane.
+#define FPW 8
+
+struct WarpQ {
+    uint32_t q[64];          // pending pairs: slot << 24 | iy << 12 | ix
+    float rec[12][FPW];      // the warp's 8 face records
+    int img[FPW];            // image of each slot
+    int face[FPW];           // face index of each slot
+    int ix0[FPW], iy0[FPW], w[FPW];   // exact pixel rectangle of each slot's bbox (origin, width)
+    float facc[6][FPW];      // backward: corner-gradient accumulators per slot
+};
+
+enum { MODE_HARD = 0, MODE_SOFT_FWD = 1, MODE_SOFT_BWD = 2 };
+
+__device__ __forceinline__ FaceRec slot_rec(const WarpQ& wq, int slot) {
+    FaceRec r;
+    r.ax = wq.rec[0][slot]; r.ay = wq.rec[1][slot]; r.bx = wq.rec[2][slot]; r.by = wq.rec[3][slot];
+    r.cx = wq.rec[4][slot]; r.cy = wq.rec[5][slot]; r.az = wq.rec[6][slot]; r.bz = wq.rec[7][slot];
+    r.cz = wq.rec[8][slot]; r.nx = r.ny = r.nz = 0.0f;
+    return r;
 }
 
-// ---------------------------------------------------------------------------------------------- soft pass, forward
-__global__ void __launch_bounds__(256)
-k_soft_fwd(const mm_raster_params p)
-{
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int q = gid & (LANES_PER_FACE - 1);
-    const int fid = gid / LANES_PER_FACE;
-    if (fid >= p.B * p.F) return;
-    const int b = fid / p.F, f = fid - b * p.F;
-    const FaceRec r = load_rec(p.frec + (size_t)b * p.F * MM_REC_FLOATS, f);
-    const float xmin = SUB(fminf(fminf(r.ax, r.bx), r.cx), p.blen), xmax = ADD(fmaxf(fmaxf(r.ax, r.bx), r.cx), p.blen);
-    const float ymin = SUB(fminf(fminf(r.ay, r.by), r.cy), p.blen), ymax = ADD(fmaxf(fmaxf(r.ay, r.by), r.cy), p.blen);
-    PixRange pr;
-    if (!pix_range(p, xmin, xmax, ymin, ymax, pr)) return;
-    const size_t HW = (size_t)p.H * p.W;
-    const unsigned long long* zb = p.zbuf + (size_t)b * HW;
-    unsigned long long* la = p.lacc + (size_t)b * HW;
-    const float kz = p.sigmainv / p.multiplier / p.multiplier;
-    for (int iy = pr.iy0 + q; iy <= pr.iy1; iy += LANES_PER_FACE) {
-        const float py = pix_y(iy, p.H, p.sy);
-        if (py < ymin || py >= ymax) continue;
-        for (int ix = pr.ix0; ix <= pr.ix1; ++ix) {
-            const float px = pix_x(ix, p.W, p.sx);
-            if (px < xmin || px >= xmax) continue;
-            const size_t pix = (size_t)iy * p.W + ix;
-            if (zb[pix] != 0ull) continue;                          // covered pixels get soft = 1, no candidates
-            int type;
-            const float d2 = soft_d2_fast(r, px, py, p.multiplier, type);
-            const float prob = soft_prob_fast(d2, kz);
-            const unsigned long long old = atomicAdd(la + pix, lacc_term(log1pf(-prob)));
-            if (lacc_count(old) == p.knum) {                        // this is candidate knum+1: the pixel needs the ordered pass
-                const uint32_t slot = atomicAdd(p.ovf_count, 1u);
-                p.ovf_list[slot] = (uint32_t)((size_t)b * HW + pix);
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------- soft pass, backward
 // one (pixel, face) candidate's contribution to the face's 6 corner gradients (DIBR_SPEC A.5, fast tail)
 __device__ __forceinline__ void soft_pair_grad(const mm_raster_params& p, const FaceRec& r, float px, float py, float kz,
                                                float inv_mult, float g_soft, float one_m_all, float (&ga)[6])
@@ -163,55 +127,158 @@ __device__ __forceinline__ void soft_pair_grad(const mm_raster_params& p, const 
     for (int k = 0; k < 6; ++k) ga[k] += v[k];
 }
 
-__global__ void __launch_bounds__(256)
-k_soft_bwd(const mm_raster_params p)
+
+// one queued pair, evaluated by one lane (no warp collectives in here: the tail of the queue runs divergent)
+template <int MODE>
+__device__ __forceinline__ void eval_pair(const mm_raster_params& p, WarpQ& wq, uint32_t e, float kz, float inv_mult)
 {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int q = gid & (LANES_PER_FACE - 1);
-    const int fid = gid / LANES_PER_FACE;
-    const bool live = fid < p.B * p.F;
-    const int b = live ? fid / p.F : 0, f = live ? fid - b * p.F : 0;
-    float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    if (live) {
-        const FaceRec r = load_rec(p.frec + (size_t)b * p.F * MM_REC_FLOATS, f);
-        const float xmin = SUB(fminf(fminf(r.ax, r.bx), r.cx), p.blen), xmax = ADD(fmaxf(fmaxf(r.ax, r.bx), r.cx), p.blen);
-        const float ymin = SUB(fminf(fminf(r.ay, r.by), r.cy), p.blen), ymax = ADD(fmaxf(fmaxf(r.ay, r.by), r.cy), p.blen);
-        PixRange pr;
-        if (pix_range(p, xmin, xmax, ymin, ymax, pr)) {
-            const size_t HW = (size_t)p.H * p.W;
-            const unsigned long long* zb = p.zbuf + (size_t)b * HW;
-            const unsigned long long* la = p.lacc + (size_t)b * HW;
-            const float* gs = p.gsoft + (size_t)b * HW;
-            const float* alpha = p.rgba + (size_t)b * 4 * HW + 3 * HW;
-            const float kz = p.sigmainv / p.multiplier / p.multiplier;
-            const float inv_mult = 1.0f / p.multiplier;
-            for (int iy = pr.iy0 + q; iy <= pr.iy1; iy += LANES_PER_FACE) {
-                const float py = pix_y(iy, p.H, p.sy);
-                if (py < ymin || py >= ymax) continue;
-                for (int ix = pr.ix0; ix <= pr.ix1; ++ix) {
-                    const float px = pix_x(ix, p.W, p.sx);
-                    if (px < xmin || px >= xmax) continue;
-                    const size_t pix = (size_t)iy * p.W + ix;
-                    if (zb[pix] != 0ull) continue;
-                    if (lacc_count(la[pix]) == (int)MM_LACC_OVF) continue;       // truncated pixel: ordered pass owns it
-                    const float g = gs[pix];
-                    const float soft = alpha[pix];
-                    if (g == 0.0f || !(soft > 0.0f)) continue;
-                    soft_pair_grad(p, r, px, py, kz, inv_mult, g, 1.0f - soft, ga);
+    const int slot = (int)(e >> 24), iy = (int)((e >> 12) & 0xfffu), ix = (int)(e & 0xfffu);
+    const int b = wq.img[slot];
+    const size_t HW = (size_t)p.H * p.W;
+    const size_t pix = (size_t)iy * p.W + ix;
+    const float px = pix_x(ix, p.W, p.sx), py = pix_y(iy, p.H, p.sy);
+    const FaceRec r = slot_rec(wq, slot);
+    if (MODE == MODE_HARD) {
+        Bary bb;
+        bary_eval(r, px, py, p.eps, bb);
+        if (bb.w0 < 0.0f || bb.w1 < 0.0f || bb.w2 < 0.0f) return;
+        const float zz = ADD(ADD(MUL(bb.w0, r.az), MUL(bb.w1, r.bz)), MUL(bb.w2, r.cz));
+        atomicMax(p.zbuf + (size_t)b * HW + pix, depth_key(zz, wq.face[slot]));
+    } else if (MODE == MODE_SOFT_FWD) {
+        int type;
+        const float d2 = soft_d2_fast(r, px, py, p.multiplier, type);
+        const float prob = soft_prob_fast(d2, kz);
+        const unsigned long long old = atomicAdd(p.lacc + (size_t)b * HW + pix, lacc_term(log1pf(-prob)));
+        if (lacc_count(old) == p.knum) {                        // candidate knum+1: the pixel needs the ordered pass
+            const uint32_t s2 = atomicAdd(p.ovf_count, 1u);
+            p.ovf_list[s2] = (uint32_t)((size_t)b * HW + pix);
+        }
+    } else {
+        const float g = p.gsoft[(size_t)b * HW + pix];
+        const float soft = p.rgba[(size_t)b * 4 * HW + 3 * HW + pix];
+        if (g == 0.0f || !(soft > 0.0f)) return;
+        float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        soft_pair_grad(p, r, px, py, kz, inv_mult, g, 1.0f - soft, ga);
+        #pragma unroll
+        for (int k = 0; k < 6; ++k) if (ga[k] != 0.0f) atomicAdd(&wq.facc[k][slot], ga[k]);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_scatter(const mm_raster_params p)
+{
+    __shared__ WarpQ s_wq[8];
+    const int lane = threadIdx.x & 31;
+    WarpQ& wq = s_wq[threadIdx.x >> 5];
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t HW = (size_t)p.H * p.W;
+    const float kz = p.sigmainv / p.multiplier / p.multiplier;
+    const float inv_mult = 1.0f / p.multiplier;
+
+    // ---- set-up: lanes 0..7 each own one face of the warp: record -> smem, EXACT pixel rectangle of its bbox
+    int npx = 0;
+    if (lane < FPW) {
+        const int slot = lane;
+        const int fid = gwarp * FPW + slot;
+        int ix0 = 0, ix1 = -1, iy0 = 0, iy1 = -1;
+        if (fid < p.B * p.F) {
+            const int b = fid / p.F, f = fid - b * p.F;
+            const FaceRec r = load_rec(p.frec + (size_t)b * p.F * MM_REC_FLOATS, f);
+            wq.rec[0][slot] = r.ax; wq.rec[1][slot] = r.ay; wq.rec[2][slot] = r.bx; wq.rec[3][slot] = r.by;
+            wq.rec[4][slot] = r.cx; wq.rec[5][slot] = r.cy; wq.rec[6][slot] = r.az; wq.rec[7][slot] = r.bz;
+            wq.rec[8][slot] = r.cz; wq.img[slot] = b; wq.face[slot] = f;
+            if (MODE != MODE_HARD || r.nz >= 0.0f) {                 // DIBR_SPEC A.2: the hard pass sees front faces only
+                float xmin = fminf(fminf(r.ax, r.bx), r.cx), xmax = fmaxf(fmaxf(r.ax, r.bx), r.cx);
+                float ymin = fminf(fminf(r.ay, r.by), r.cy), ymax = fmaxf(fmaxf(r.ay, r.by), r.cy);
+                if (MODE != MODE_HARD) {                             // DIBR_SPEC A.4: bbox enlarged by boxlen
+                    xmin = SUB(xmin, p.blen); xmax = ADD(xmax, p.blen); ymin = SUB(ymin, p.blen); ymax = ADD(ymax, p.blen);
+                }
+                PixRange pr;
+                if (pix_range(p, xmin, xmax, ymin, ymax, pr)) {
+                    // tighten the conservative range to the exact half-open test  xmin <= px < xmax, ymin <= py < ymax
+                    // (pixel centres are monotone in the index, so the exact set is a rectangle; <= 2 steps per side)
+                    ix0 = pr.ix0; ix1 = pr.ix1; iy0 = pr.iy0; iy1 = pr.iy1;
+                    while (ix0 <= ix1 && pix_x(ix0, p.W, p.sx) < xmin) ++ix0;
+                    while (ix1 >= ix0 && pix_x(ix1, p.W, p.sx) >= xmax) --ix1;
+                    while (iy0 <= iy1 && pix_y(iy0, p.H, p.sy) >= ymax) ++iy0;      // y decreases with the row index
+                    while (iy1 >= iy0 && pix_y(iy1, p.H, p.sy) < ymin) --iy1;
                 }
             }
+        } else { wq.img[slot] = 0; wq.face[slot] = 0; }
+        const int w = ix1 - ix0 + 1, h = iy1 - iy0 + 1;
+        npx = (w > 0 && h > 0) ? w * h : 0;
+        wq.ix0[slot] = ix0; wq.iy0[slot] = iy0; wq.w[slot] = w > 0 ? w : 1;
+        if (MODE == MODE_SOFT_BWD) {
+            #pragma unroll
+            for (int k = 0; k < 6; ++k) wq.facc[k][slot] = 0.0f;
         }
     }
-    // combine the 4 lanes of the face, one set of atomics per face
+    // exclusive prefix of the 8 pixel counts (every lane keeps all of them: the slot search below is 8 compares)
+    int pre[FPW + 1];
+    pre[0] = 0;
     #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        ga[k] += __shfl_xor_sync(FULL, ga[k], 1);
-        ga[k] += __shfl_xor_sync(FULL, ga[k], 2);
+    for (int sl = 0; sl < FPW; ++sl) pre[sl + 1] = pre[sl] + __shfl_sync(FULL, npx, sl);
+    const int total = pre[FPW];
+    __syncwarp();
+
+    // ---- the warp's (face, pixel) pairs, dealt to the 32 lanes round-robin: perfectly balanced whatever the face sizes
+    int qn = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+    #pragma unroll 1
+    for (int k0 = 0; k0 < total; k0 += 32) {
+        const int k = k0 + lane;
+        bool cand = false;
+        uint32_t entry = 0u;
+        if (k < total) {
+            int slot = 0;
+            #pragma unroll
+            for (int sl = 1; sl < FPW; ++sl) slot += (k >= pre[sl]) ? 1 : 0;
+            int local = k;
+            #pragma unroll
+            for (int sl = 1; sl < FPW; ++sl) local = (slot == sl) ? k - pre[sl] : local;
+            const int w = wq.w[slot];
+            int dy = (int)(((float)local + 0.5f) * __frcp_rn((float)w));
+            int dx = local - dy * w;
+            if (dx < 0) { --dy; dx += w; } else if (dx >= w) { ++dy; dx -= w; }
+            const int ix = wq.ix0[slot] + dx, iy = wq.iy0[slot] + dy;
+            entry = ((uint32_t)slot << 24) | ((uint32_t)iy << 12) | (uint32_t)ix;
+            if (MODE == MODE_HARD) cand = true;
+            else {
+                const size_t pg = (size_t)wq.img[slot] * HW + (size_t)iy * p.W + ix;
+                cand = (p.zbuf[pg] == 0ull);                                        // covered pixels get soft = 1
+                if (MODE == MODE_SOFT_BWD && cand) cand = lacc_count(p.lacc[pg]) != (int)MM_LACC_OVF;
+            }
+        }
+        if (MODE == MODE_HARD) {                                   // every pair needs the inside test: no compaction
+            if (cand) eval_pair<MODE>(p, wq, entry, kz, inv_mult);
+            continue;
+        }
+        const uint32_t m = __ballot_sync(FULL, cand);
+        if (cand) wq.q[qn + __popc(m & lt)] = entry;
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+            const uint32_t e = wq.q[lane];
+            const uint32_t carry = wq.q[32 + lane];
+            __syncwarp();
+            eval_pair<MODE>(p, wq, e, kz, inv_mult);
+            qn -= 32;
+            if (lane < qn) wq.q[lane] = carry;
+            __syncwarp();
+        }
     }
-    if (live && q == 0) {
-        float* g = p.gfacc + ((size_t)b * p.F + f) * 9;
-        #pragma unroll
-        for (int k = 0; k < 6; ++k) if (ga[k] != 0.0f) atomicAdd(g + k, ga[k]);
+    if (MODE != MODE_HARD && lane < qn) eval_pair<MODE>(p, wq, wq.q[lane], kz, inv_mult);
+    if (MODE == MODE_SOFT_BWD) {
+        __syncwarp();
+        for (int idx = lane; idx < 6 * FPW; idx += 32) {
+            const int kk = idx / FPW, sl = idx - kk * FPW;
+            const int fg = gwarp * FPW + sl;
+            if (fg < p.B * p.F) {
+                const float v = wq.facc[kk][sl];
+                if (v != 0.0f) atomicAdd(p.gfacc + (size_t)fg * 9 + kk, v);
+            }
+        }
     }
 }
 
@@ -245,40 +312,55 @@ k_soft_ovf(const mm_raster_params p)
         }
         int kid = 0;
         float allprob = 1.0f;
-        for (int f0 = 0; f0 < p.F && kid < p.knum; f0 += 32) {
-            const int f = f0 + lane;
-            FaceRec r;
-            bool hit = false;
-            if (f < p.F) { r = load_rec(rec, f); hit = soft_bbox_test(r, px, py, p.blen); }
-            uint32_t m = __ballot_sync(FULL, hit);
-            const int room = p.knum - kid;
-            if (__popc(m) > room) {                              // keep the `room` lowest set bits
-                uint32_t k2 = 0u, h = m;
-                #pragma unroll 1
-                for (int a = 0; a < room; ++a) { const uint32_t low = h & (0u - h); k2 |= low; h ^= low; }
-                m = k2;
+        // 4 x 32 faces per step: the four bbox loads are independent, so one memory round trip covers 128 faces
+        for (int f0 = 0; f0 < p.F && kid < p.knum; f0 += 128) {
+            float4 c0[4], c1[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int f = f0 + u * 32 + lane;
+                if (f < p.F) {
+                    const float4* q4 = reinterpret_cast<const float4*>(rec) + (size_t)f * 3;
+                    c0[u] = __ldg(q4); c1[u] = __ldg(q4 + 1);
+                } else { c0[u] = make_float4(0.f, 0.f, 0.f, 0.f); c1[u] = c0[u]; }
             }
-            const bool mine = (m >> lane) & 1u;
-            if (BWD) {
-                if (mine) {
-                    float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-                    soft_pair_grad(p, r, px, py, kz, inv_mult, g, one_m_all, ga);
-                    float* gf = p.gfacc + ((size_t)b * p.F + f) * 9;
-                    #pragma unroll
-                    for (int k = 0; k < 6; ++k) if (ga[k] != 0.0f) atomicAdd(gf + k, ga[k]);
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (kid >= p.knum) break;
+                const int f = f0 + u * 32 + lane;
+                FaceRec r;
+                r.ax = c0[u].x; r.ay = c0[u].y; r.bx = c0[u].z; r.by = c0[u].w; r.cx = c1[u].x; r.cy = c1[u].y;
+                r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
+                const bool hit = (f < p.F) && soft_bbox_test(r, px, py, p.blen);
+                uint32_t m = __ballot_sync(FULL, hit);
+                const int room = p.knum - kid;
+                if (__popc(m) > room) {                          // keep the `room` lowest set bits
+                    uint32_t k2 = 0u, h = m;
+                    #pragma unroll 1
+                    for (int a = 0; a < room; ++a) { const uint32_t low = h & (0u - h); k2 |= low; h ^= low; }
+                    m = k2;
                 }
-            } else {
-                float prob = 0.0f;
-                if (mine) { int type; prob = soft_prob_fast(soft_d2_fast(r, px, py, p.multiplier, type), kz); }
-                uint32_t mm = m;
-                #pragma unroll 1
-                while (mm) {                                     // the reference's ordered product
-                    const int j = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    allprob = allprob * (1.0f - __shfl_sync(FULL, prob, j));
+                const bool mine = (m >> lane) & 1u;
+                if (BWD) {
+                    if (mine) {
+                        float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+                        soft_pair_grad(p, r, px, py, kz, inv_mult, g, one_m_all, ga);
+                        float* gf = p.gfacc + ((size_t)b * p.F + f) * 9;
+                        #pragma unroll
+                        for (int k = 0; k < 6; ++k) if (ga[k] != 0.0f) atomicAdd(gf + k, ga[k]);
+                    }
+                } else {
+                    float prob = 0.0f;
+                    if (mine) { int type; prob = soft_prob_fast(soft_d2_fast(r, px, py, p.multiplier, type), kz); }
+                    uint32_t mm = m;
+                    #pragma unroll 1
+                    while (mm) {                                 // the reference's ordered product
+                        const int j = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        allprob = allprob * (1.0f - __shfl_sync(FULL, prob, j));
+                    }
                 }
+                kid += __popc(m);
             }
-            kid += __popc(m);
         }
         if (!BWD && lane == 0) p.lacc[pg] = lacc_exact(allprob > 0.0f ? logf(allprob) : -2400.0f);
     }
@@ -288,18 +370,18 @@ k_soft_ovf(const mm_raster_params p)
 
 void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
-    const int threads = p.B * c->F * LANES_PER_FACE;
-    const int grid = (threads + 255) / 256;
-    k_hard<<<grid, 256, 0, s>>>(p);
-    k_soft_fwd<<<grid, 256, 0, s>>>(p);
+    const int warps = (p.B * c->F + FPW - 1) / FPW;
+    const int grid = (warps + 7) / 8;
+    k_scatter<MODE_HARD><<<grid, 256, 0, s>>>(p);
+    k_scatter<MODE_SOFT_FWD><<<grid, 256, 0, s>>>(p);
     k_soft_ovf<false><<<c->num_sms * 2, 256, 0, s>>>(p);
 }
 
 void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
-    const int threads = p.B * c->F * LANES_PER_FACE;
-    const int grid = (threads + 255) / 256;
-    k_soft_bwd<<<grid, 256, 0, s>>>(p);
+    const int warps = (p.B * c->F + FPW - 1) / FPW;
+    const int grid = (warps + 7) / 8;
+    k_scatter<MODE_SOFT_BWD><<<grid, 256, 0, s>>>(p);
     k_soft_ovf<true><<<c->num_sms * 2, 256, 0, s>>>(p);
 }
 
