@@ -78,6 +78,7 @@ void set_ws(const mm_ws_layout& L, char* ws, mm_raster_params& p) {
     p.zbuf = (unsigned long long*)(ws + L.zbuf); p.lacc = (unsigned long long*)(ws + L.lacc);
     p.ovf_list = (uint32_t*)(ws + L.ovf_list); p.ovf_count = (uint32_t*)(ws + L.ovf_count);
     p.gsoft = (float*)(ws + L.gsoft);
+    p.plist = (unsigned long long*)(ws + L.plist); p.plist_cap = (uint32_t)((L.gsoft - L.plist) / 8);
     p.part_fwd = (float*)(ws + L.part_fwd); p.part_bwd = (float*)(ws + L.part_bwd);
     p.img_fwd = (float*)(ws + L.img_fwd); p.img_bwd = (float*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
     p.gfacc = (float*)(ws + L.gfacc);

@@ -16,6 +16,9 @@
 //     lacc       [B,H,W] u64  soft-silhouette accumulator of uncovered pixels: fixed-point sum log(1-p) << 16 | count
 //     ovf_list   [B*H*W] u32  pixels that saw more than knum candidates (ordered re-scan), ovf_count [1] u32
 //     gsoft      [B,H,W]      d(loss)/d(silhouette) per pixel, handed from the shading backward to the geometry backward
+//     plist      [2*B*H*W] u64 the (face, pixel) candidate pairs the forward soft pass evaluated, (image*F+face) << 32 |
+//                             iy << 12 | ix: the backward soft pass replays this dense list instead of re-filtering
+//                             every bbox pixel; plist_count shares the cleared counter block
 //     vimg       [B,V,2]   unscaled image-plane xy (debug export / parity tests)
 //     face_idx   [B,H,W]   int32 winner of the hard pass (-1 none); saved for backward
 //     gfacc      [B,F,9]   backward accumulators: d/d(fvi) (6, unscaled) + d/d(unit normal) (3)
@@ -74,7 +77,7 @@ struct mm_ctx {
 };
 
 struct mm_ws_layout {
-    size_t frec, zbuf, lacc, ovf_count, ovf_list, gsoft, vimg, gfacc, part_fwd, part_bwd, img_fwd, img_bwd, tickets, total;
+    size_t frec, zbuf, lacc, ovf_count, ovf_list, plist, gsoft, vimg, gfacc, part_fwd, part_bwd, img_fwd, img_bwd, tickets, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -95,6 +98,7 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     L.lacc = off;     off = mm_align_up(off + (size_t)B * c->H * c->W * 8, 256);
     L.ovf_count = off; off = mm_align_up(off + 16, 256);
     L.ovf_list = off; off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
+    L.plist = off;    off = mm_align_up(off + (size_t)2 * B * c->H * c->W * 8, 256);
     L.gsoft = off;    off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.vimg = off;     off = mm_align_up(off + (size_t)B * c->V * 2 * 4, 256);
     L.gfacc = off;    off = mm_align_up(off + (size_t)B * c->F * 9 * 4, 256);
@@ -119,7 +123,9 @@ struct mm_raster_params {
     unsigned long long* zbuf;     // [B,H,W]
     unsigned long long* lacc;     // [B,H,W]
     uint32_t* ovf_list;      // [B*H*W]
-    uint32_t* ovf_count;     // [1]
+    uint32_t* ovf_count;     // [4]: {overflow pixels, candidate pairs recorded, -, -}
+    unsigned long long* plist;    // [plist_cap]
+    uint32_t plist_cap;
     float* gsoft;            // [B,H,W]
     const float* face_uvs;   // [F,6]
     const float* tex;        // [B,3,Ht,Wt]

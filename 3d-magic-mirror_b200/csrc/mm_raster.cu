@@ -164,6 +164,20 @@ __device__ __forceinline__ void eval_pair(const mm_raster_params& p, WarpQ& wq, 
     }
 }
 
+// forward soft pass: append the pairs this warp just evaluated to the global pair list (one atomicAdd per batch);
+// all 32 lanes must call it.  If the list is full the count still grows, which tells the backward to fall back.
+__device__ __forceinline__ void record_pairs(const mm_raster_params& p, const WarpQ& wq, uint32_t e, int n, int lane)
+{
+    uint32_t base = 0u;
+    if (lane == 0) base = atomicAdd(p.ovf_count + 1, (uint32_t)n);
+    base = __shfl_sync(FULL, base, 0);
+    if (lane < n && base + (uint32_t)lane < p.plist_cap) {
+        const int slot = (int)(e >> 24);
+        const unsigned long long fg = (unsigned long long)((size_t)wq.img[slot] * p.F + wq.face[slot]);
+        p.plist[base + lane] = (fg << 32) | (unsigned long long)(e & 0xffffffu);
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_scatter(const mm_raster_params p)
@@ -175,6 +189,7 @@ k_scatter(const mm_raster_params p)
     const size_t HW = (size_t)p.H * p.W;
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
     const float inv_mult = 1.0f / p.multiplier;
+    if (MODE == MODE_SOFT_BWD && p.ovf_count[1] <= p.plist_cap) return;      // the pair list is complete: k_soft_bwd_list did it
 
     // ---- set-up: lanes 0..7 each own one face of the warp: record -> smem, EXACT pixel rectangle of its bbox
     int npx = 0;
@@ -263,12 +278,14 @@ k_scatter(const mm_raster_params p)
             const uint32_t carry = wq.q[32 + lane];
             __syncwarp();
             eval_pair<MODE>(p, wq, e, kz, inv_mult);
+            if (MODE == MODE_SOFT_FWD) record_pairs(p, wq, e, 32, lane);
             qn -= 32;
             if (lane < qn) wq.q[lane] = carry;
             __syncwarp();
         }
     }
     if (MODE != MODE_HARD && lane < qn) eval_pair<MODE>(p, wq, wq.q[lane], kz, inv_mult);
+    if (MODE == MODE_SOFT_FWD && qn > 0) record_pairs(p, wq, lane < qn ? wq.q[lane] : 0u, qn, lane);
     if (MODE == MODE_SOFT_BWD) {
         __syncwarp();
         for (int idx = lane; idx < 6 * FPW; idx += 32) {
@@ -278,6 +295,49 @@ k_scatter(const mm_raster_params p)
                 const float v = wq.facc[kk][sl];
                 if (v != 0.0f) atomicAdd(p.gfacc + (size_t)fg * 9 + kk, v);
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- soft pass backward, list-driven
+// Replays the forward's dense candidate list: one pair per lane, no bbox walk, no filtering.
+__global__ void __launch_bounds__(256)
+k_soft_bwd_list(const mm_raster_params p)
+{
+    const uint32_t n = p.ovf_count[1];
+    if (n > p.plist_cap) return;                                   // list overflowed: the filter-based kernel runs instead
+    const int lane = threadIdx.x & 31;
+    const size_t HW = (size_t)p.H * p.W;
+    const float kz = p.sigmainv / p.multiplier / p.multiplier;
+    const float inv_mult = 1.0f / p.multiplier;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += stride) {
+        const uint32_t i = i0 + lane;
+        float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        uint32_t fg = 0xffffffffu;
+        if (i < n) {
+            const unsigned long long e = p.plist[i];
+            fg = (uint32_t)(e >> 32);
+            const int iy = (int)((e >> 12) & 0xfffu), ix = (int)(e & 0xfffu);
+            const int b = (int)(fg / (uint32_t)p.F);
+            const size_t pg = (size_t)b * HW + (size_t)iy * p.W + ix;
+            const float g = p.gsoft[pg];
+            const float soft = p.rgba[(size_t)b * 4 * HW + 3 * HW + (size_t)iy * p.W + ix];
+            if (g != 0.0f && soft > 0.0f && lacc_count(p.lacc[pg]) != (int)MM_LACC_OVF) {
+                const float4* q4 = reinterpret_cast<const float4*>(p.frec) + (size_t)fg * 3;
+                const float4 c0 = __ldg(q4), c1 = __ldg(q4 + 1);
+                FaceRec r;
+                r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
+                r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
+                soft_pair_grad(p, r, pix_x(ix, p.W, p.sx), pix_y(iy, p.H, p.sy), kz, inv_mult, g, 1.0f - soft, ga);
+            }
+        }
+        // one RED per non-zero component (vertex-type candidates touch 2 of the 6, edge-type 4); a warp-wide RED is ONE
+        // instruction, so pre-combining lanes that share a face with match_any + shuffles costs more than it saves
+        if (fg != 0xffffffffu) {
+            float* g = p.gfacc + (size_t)fg * 9;
+            #pragma unroll
+            for (int k = 0; k < 6; ++k) if (ga[k] != 0.0f) atomicAdd(g + k, ga[k]);
         }
     }
 }
@@ -312,11 +372,11 @@ k_soft_ovf(const mm_raster_params p)
         }
         int kid = 0;
         float allprob = 1.0f;
-        // 4 x 32 faces per step: the four bbox loads are independent, so one memory round trip covers 128 faces
-        for (int f0 = 0; f0 < p.F && kid < p.knum; f0 += 128) {
-            float4 c0[4], c1[4];
+        // 8 x 32 faces per step: the bbox loads are independent, so one memory round trip covers 256 faces
+        for (int f0 = 0; f0 < p.F && kid < p.knum; f0 += 256) {
+            float4 c0[8], c1[8];
             #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int f = f0 + u * 32 + lane;
                 if (f < p.F) {
                     const float4* q4 = reinterpret_cast<const float4*>(rec) + (size_t)f * 3;
@@ -324,7 +384,7 @@ k_soft_ovf(const mm_raster_params p)
                 } else { c0[u] = make_float4(0.f, 0.f, 0.f, 0.f); c1[u] = c0[u]; }
             }
             #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 if (kid >= p.knum) break;
                 const int f = f0 + u * 32 + lane;
                 FaceRec r;
@@ -381,7 +441,8 @@ void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t
 {
     const int warps = (p.B * c->F + FPW - 1) / FPW;
     const int grid = (warps + 7) / 8;
-    k_scatter<MODE_SOFT_BWD><<<grid, 256, 0, s>>>(p);
+    k_soft_bwd_list<<<c->num_sms * 4, 256, 0, s>>>(p);
+    k_scatter<MODE_SOFT_BWD><<<grid, 256, 0, s>>>(p);              // returns immediately unless the pair list overflowed
     k_soft_ovf<true><<<c->num_sms * 2, 256, 0, s>>>(p);
 }
 
