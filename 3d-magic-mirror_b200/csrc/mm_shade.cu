@@ -17,19 +17,35 @@ namespace {
 
 __device__ __forceinline__ float contour_c(float m, float mref) { return fabsf(m - mref); }
 
-// Per-image reduction without a second kernel and without float atomics: every CTA publishes its partial sums,
-// takes a ticket, and the LAST CTA of the image sums all partials in a fixed order.  The ticket resets itself.
+// Per-image reduction without a second kernel and without float atomics: the CTA reduces its NV partial sums with
+// ONE barrier (warp shuffles -> shared memory -> NV threads add the 8 warp results), publishes them, takes a ticket,
+// and the LAST CTA of the image sums all partials in a fixed order (deterministic).  The ticket resets itself.
 template <int NV>
-__device__ __forceinline__ void image_reduce_last(const float (&v)[NV], float* part /* [nparts][stride] of this image */,
+__device__ __forceinline__ void image_reduce_last(float (&v)[NV], float* part /* [nparts][stride] of this image */,
                                                   int stride, int nparts, uint32_t* ticket, float* out, int lane)
 {
+    __shared__ float s_part[MM_WARPS][NV];
     __shared__ uint32_t s_ticket;
-    if (threadIdx.x == 0) {
+    const int warp = threadIdx.x >> 5;
+    #pragma unroll
+    for (int i = 0; i < NV; ++i) {
         #pragma unroll
-        for (int i = 0; i < NV; ++i) part[(size_t)blockIdx.x * stride + i] = v[i];
-        __threadfence();
-        s_ticket = atomicAdd(ticket, 1u);
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(FULL, v[i], o);
     }
+    if (lane == 0) {
+        #pragma unroll
+        for (int i = 0; i < NV; ++i) s_part[warp][i] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        float r = 0.0f;
+        #pragma unroll
+        for (int w = 0; w < MM_WARPS; ++w) r += s_part[w][threadIdx.x];
+        part[(size_t)blockIdx.x * stride + threadIdx.x] = r;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
     __syncthreads();
     if (s_ticket != (uint32_t)(nparts - 1)) return;
     __threadfence();
@@ -61,7 +77,6 @@ __global__ void __launch_bounds__(MM_THREADS)
 k_shade_fwd(const mm_raster_params p)
 {
     __shared__ float s_lights[16];
-    __shared__ float s_red[MM_WARPS];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
     __syncthreads();
@@ -143,7 +158,7 @@ k_shade_fwd(const mm_raster_params p)
         }
     }
     if (WITH_LOSS) {
-        const float v[4] = {block_sum(acc_l1, s_red), block_sum(acc_n, s_red), block_sum(acc_d, s_red), 0.0f};
+        float v[4] = {acc_l1, acc_n, acc_d, 0.0f};
         image_reduce_last<4>(v, p.part_fwd + (size_t)b * gridDim.x * 4, 4, gridDim.x, p.tickets + b * 4 + 2, p.img_fwd + b * 4, lane);
     }
 }
@@ -153,7 +168,6 @@ __global__ void __launch_bounds__(MM_THREADS)
 k_shade_bwd(const mm_raster_params p)
 {
     __shared__ float s_lights[16];
-    __shared__ float s_red[MM_WARPS];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
     __syncthreads();
@@ -369,9 +383,9 @@ k_shade_bwd(const mm_raster_params p)
     }
     // ---- per-CTA partials: contour sum + 9 light gradients, reduced per image by the last CTA (fixed order)
     float v[10];
-    v[0] = block_sum(acc_contour, s_red);
+    v[0] = acc_contour;
     #pragma unroll
-    for (int i = 0; i < 9; ++i) v[1 + i] = block_sum(acc_l[i], s_red);
+    for (int i = 0; i < 9; ++i) v[1 + i] = acc_l[i];
     image_reduce_last<10>(v, p.part_bwd + (size_t)b * gridDim.x * 12, 12, gridDim.x, p.tickets + b * 4 + 3, p.img_bwd + b * 12, lane);
 }
 
