@@ -80,7 +80,7 @@ void set_ws(const mm_ws_layout& L, char* ws, mm_raster_params& p) {
     p.gsoft = (float*)(ws + L.gsoft);
     p.plist = (unsigned long long*)(ws + L.plist); p.plist_cap = (uint32_t)((L.gsoft - L.plist) / 8);
     p.part_fwd = (float*)(ws + L.part_fwd); p.part_bwd = (float*)(ws + L.part_bwd);
-    p.img_fwd = (float*)(ws + L.img_fwd); p.img_bwd = (float*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
+    p.img_fwd = (long long*)(ws + L.img_fwd); p.img_bwd = (long long*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
     p.gfacc = (float*)(ws + L.gfacc);
 }
 
@@ -90,7 +90,7 @@ int launch_vertex_fwd(const mm_ctx* c, int B, const mm_ws_layout& L, char* ws, c
                       cudaStream_t s) {
     if (cudaMemsetAsync(ws + L.zbuf, 0, (L.ovf_count + 16) - L.zbuf, s) != cudaSuccess) return 1;
     mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg), face_normals,
-                         zero_gfacc ? (float*)(ws + L.gfacc) : nullptr, (uint32_t*)(ws + L.tickets), s);
+                         zero_gfacc ? (float*)(ws + L.gfacc) : nullptr, (long long*)(ws + L.img_fwd), (long long*)(ws + L.img_bwd), s);
     return 0;
 }
 
@@ -243,7 +243,7 @@ int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azi
     if (int r = check_launch("shade_bwd")) return r;
     mm_launch_geom_bwd(c, p, s);
     if (int r = check_launch("geom_bwd")) return r;
-    mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.img_bwd, g_vertices,
+    mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.img_bwd, 1, g_vertices,
                          g_azim, g_elev, g_dist, g_bias, g_lights, s);
     return check_launch("vertex_bwd");
 }
@@ -258,8 +258,8 @@ int mm_recon_data_forward(mm_ctx* c, int B, const float* pred, const float* gt, 
     char* ws = (char*)workspace;
     mm_launch_recon_fwd(c, B, pred, gt, contour, (float*)(ws + L.part_fwd), s);
     if (int r = check_launch("recon_fwd")) return r;
-    mm_launch_image_reduce(c, B, c->nparts_recon, (const float*)(ws + L.part_fwd), (float*)(ws + L.img_fwd), s);
-    mm_launch_loss_finalize(c, B, (const float*)(ws + L.img_fwd), nullptr, image_weight, contour, loss, iou_sums, s);
+    mm_launch_image_reduce(c, B, c->nparts_recon, (const float*)(ws + L.part_fwd), (long long*)(ws + L.img_fwd), s);
+    mm_launch_loss_finalize(c, B, (const long long*)(ws + L.img_fwd), nullptr, image_weight, contour, loss, iou_sums, s);
     return check_launch("loss_finalize");
 }
 
@@ -274,8 +274,8 @@ int mm_recon_data_backward(mm_ctx* c, int B, const float* pred, const float* gt,
     // the IoU sums are re-derived so that the call does not depend on workspace state of an earlier forward
     mm_launch_recon_fwd(c, B, pred, gt, 0.0f, (float*)(ws + L.part_fwd), s);
     if (int r = check_launch("recon_fwd")) return r;
-    mm_launch_image_reduce(c, B, c->nparts_recon, (const float*)(ws + L.part_fwd), (float*)(ws + L.img_fwd), s);
-    mm_launch_recon_bwd(c, B, pred, gt, (const float*)(ws + L.img_fwd), image_weight, contour, loss_scale, g_pred, s);
+    mm_launch_image_reduce(c, B, c->nparts_recon, (const float*)(ws + L.part_fwd), (long long*)(ws + L.img_fwd), s);
+    mm_launch_recon_bwd(c, B, pred, gt, (const long long*)(ws + L.img_fwd), image_weight, contour, loss_scale, g_pred, s);
     return check_launch("recon_bwd");
 }
 
@@ -325,7 +325,7 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     mm_launch_geom_bwd(c, p, s);
     if (int r = check_launch("geom_bwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[5], s);
-    mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.img_bwd, g_vertices, g_azim,
+    mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.img_bwd, 0, g_vertices, g_azim,
                          g_elev, g_dist, g_bias, g_lights, s);
     if (int r = check_launch("vertex_bwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[6], s);

@@ -106,8 +106,8 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     const size_t np = (size_t)(rp > c->nparts_recon ? rp : c->nparts_recon);
     L.part_fwd = off; off = mm_align_up(off + (size_t)B * np * 4 * 4, 256);
     L.part_bwd = off; off = mm_align_up(off + (size_t)B * np * 12 * 4, 256);
-    L.img_fwd = off;  off = mm_align_up(off + (size_t)B * 4 * 4, 256);
-    L.img_bwd = off;  off = mm_align_up(off + (size_t)B * 12 * 4, 256);
+    L.img_fwd = off;  off = mm_align_up(off + (size_t)B * 4 * 8, 256);
+    L.img_bwd = off;  off = mm_align_up(off + (size_t)B * 12 * 8, 256);
     L.tickets = off;  off = mm_align_up(off + (size_t)B * 4 * 4, 256);
     L.total = off;
     return L;
@@ -137,8 +137,8 @@ struct mm_raster_params {
     float* imnormal;         // [B,H,W,3] or NULL
     int32_t* face_idx_out;   // [B,H,W] or NULL
     float* part_fwd;         // [B,NP,4]
-    float* img_fwd;          // [B,4]
-    float* img_bwd;          // [B,12]
+    long long* img_fwd;      // [B,4]  fixed-point (mm_device.cuh)
+    long long* img_bwd;      // [B,12] fixed-point
     uint32_t* tickets;       // [B,4]
     // backward
     const float* g_rgba;     // [B,4,H,W] or NULL
@@ -154,21 +154,22 @@ struct mm_raster_params {
 // launchers (defined in the .cu files)
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec,
-                          float* vimg, float* face_normals, float* gfacc_zero, uint32_t* tickets, cudaStream_t s);
+                          float* vimg, float* face_normals, float* gfacc_zero, long long* img_fwd, long long* img_bwd,
+                          cudaStream_t s);
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,
-                          const float* img_bwd, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
+                          long long* img_bwd, int reset, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
                           float* g_bias, float* g_lights, cudaStream_t s);
 void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 void mm_launch_shade_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_loss, cudaStream_t s);
 void mm_launch_shade_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
-void mm_launch_loss_finalize(const mm_ctx* c, int B, const float* img_fwd, const float* img_bwd,
+void mm_launch_loss_finalize(const mm_ctx* c, int B, const long long* img_fwd, long long* img_bwd,
                              float image_weight, float contour, float* loss, float* iou_out, cudaStream_t s);
-void mm_launch_image_reduce(const mm_ctx* c, int B, int np, const float* part_fwd, float* img_fwd, cudaStream_t s);
+void mm_launch_image_reduce(const mm_ctx* c, int B, int np, const float* part_fwd, long long* img_fwd, cudaStream_t s);
 void mm_launch_recon_fwd(const mm_ctx* c, int B, const float* pred, const float* gt, float contour, float* part_fwd,
                          cudaStream_t s);
-void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float* gt, const float* img_fwd,
+void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float* gt, const long long* img_fwd,
                          float image_weight, float contour, float loss_scale, float* g_pred, cudaStream_t s);
 cudaError_t mm_raster_configure(const mm_ctx* c);
 size_t mm_raster_smem_bytes(const mm_ctx* c);

@@ -246,6 +246,19 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return r;
 }
 
+// ------------------------------------------------------------------ order-independent (deterministic) per-image sums
+// Loss terms and light gradients are accumulated per image with 64-bit INTEGER atomics on fixed-point values: integer
+// addition is associative, so the sums do not depend on the order in which warps arrive (float atomics would make the
+// loss differ from run to run in the last bits) and no block barrier / last-CTA pass is needed.
+// Scales: 2^40 for sums of non-negative loss terms (range +-8.3e6, resolution 9e-13), 2^44 for gradient sums
+// (range +-5.2e5, resolution 6e-14).
+#define MM_FX_LOSS 1099511627776.0
+#define MM_FX_GRAD 17592186044416.0
+__device__ __forceinline__ void fx_add(long long* acc, float v, double scale) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)__double2ll_rn((double)v * scale));
+}
+__device__ __forceinline__ float fx_get(const long long* acc, double scale) { return (float)((double)(*acc) / scale); }
+
 // ------------------------------------------------------------------ per-pixel soft-silhouette accumulator
 // One 64-bit word per pixel, updated with ONE integer atomicAdd per (pixel, face) candidate:
 //   bits 63..16  sum of log(1 - p_k) in fixed point (scale 2^32, two's complement; |sum| < 2^15)

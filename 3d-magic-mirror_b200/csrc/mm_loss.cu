@@ -45,7 +45,7 @@ k_recon_fwd(int H, int W, int nparts, float contour,
 __global__ void __launch_bounds__(MM_THREADS)
 k_recon_bwd(int B, int H, int W, int nparts, float image_weight, float contour, float loss_scale,
             const float* __restrict__ pred, const float* __restrict__ gt, const int32_t* __restrict__ tab,
-            const float* __restrict__ img_fwd, float* __restrict__ g_pred)
+            const long long* __restrict__ img_fwd, float* __restrict__ g_pred)
 {
     const int b = blockIdx.y, band = blockIdx.x;
     const size_t HW = (size_t)H * W;
@@ -58,8 +58,8 @@ k_recon_bwd(int B, int H, int W, int nparts, float image_weight, float contour, 
     const int32_t* refcol = tab + 3 * H;
     const int32_t* collo = tab + 3 * H + W;
     const int32_t* colhi = tab + 3 * H + 2 * W;
-    const float Nb = img_fwd[b * 4 + 1];
-    const float De = img_fwd[b * 4 + 2] + 1e-10f;
+    const float Nb = fx_get(img_fwd + b * 4 + 1, MM_FX_LOSS);
+    const float De = fx_get(img_fwd + b * 4 + 2, MM_FX_LOSS) + 1e-10f;
     const float k_img = loss_scale * image_weight / ((float)B * 3.0f * (float)HW);
     const float k_iou = loss_scale / (float)B;
     const float k_cont = loss_scale * contour / ((float)B * (float)HW);
@@ -90,8 +90,8 @@ k_recon_bwd(int B, int H, int W, int nparts, float image_weight, float contour, 
     }
 }
 
-// part_fwd [B][np][4] -> img_fwd [B][4]; one warp per image, fixed order
-__global__ void k_image_reduce(int np, const float* __restrict__ part_fwd, float* __restrict__ img_fwd)
+// part_fwd [B][np][4] -> img_fwd [B][4] (fixed point); one warp per image, fixed order
+__global__ void k_image_reduce(int np, const float* __restrict__ part_fwd, long long* __restrict__ img_fwd)
 {
     const int b = blockIdx.x, lane = threadIdx.x;
     float a[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -102,23 +102,26 @@ __global__ void k_image_reduce(int np, const float* __restrict__ part_fwd, float
     for (int i = 0; i < 4; ++i) {
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
-        if (lane == 0) img_fwd[b * 4 + i] = a[i];
+        if (lane == 0) img_fwd[b * 4 + i] = __double2ll_rn((double)a[i] * MM_FX_LOSS);
     }
 }
 
 // loss[0..3] = data, image, mask (1 - mean IoU), contour term, from the per-image sums.  Single CTA, fixed order.
 __global__ void __launch_bounds__(MM_THREADS)
 k_loss_finalize(int B, int H, int W, float image_weight, float contour,
-                const float* __restrict__ img_fwd, const float* __restrict__ img_bwd,
+                const long long* __restrict__ img_fwd, long long* __restrict__ img_bwd,
                 float* __restrict__ loss, float* __restrict__ iou_out)
 {
     __shared__ float red[MM_WARPS];
     float a_l1 = 0.0f, a_c = 0.0f, a_iou = 0.0f;
     for (int b = threadIdx.x; b < B; b += MM_THREADS) {
-        a_l1 += img_fwd[b * 4 + 0];
-        a_c += img_fwd[b * 4 + 3];
-        if (img_bwd) a_c += img_bwd[b * 12 + 0];
-        const float n = img_fwd[b * 4 + 1], d = img_fwd[b * 4 + 2];
+        a_l1 += fx_get(img_fwd + b * 4 + 0, MM_FX_LOSS);
+        a_c += fx_get(img_fwd + b * 4 + 3, MM_FX_LOSS);
+        if (img_bwd) {          // fused path: the contour sum came from the shading backward; leave the workspace reusable
+            a_c += fx_get(img_bwd + b * 12 + 0, MM_FX_LOSS);
+            for (int i = 0; i < 12; ++i) img_bwd[b * 12 + i] = 0;
+        }
+        const float n = fx_get(img_fwd + b * 4 + 1, MM_FX_LOSS), d = fx_get(img_fwd + b * 4 + 2, MM_FX_LOSS);
         a_iou += n / (d + 1e-10f);
         if (iou_out) { iou_out[b * 2] = n; iou_out[b * 2 + 1] = d; }
     }
@@ -144,7 +147,7 @@ void mm_launch_recon_fwd(const mm_ctx* c, int B, const float* pred, const float*
     k_recon_fwd<<<grid, MM_THREADS, 0, s>>>(c->H, c->W, c->nparts_recon, contour, pred, gt, c->d_tab, part_fwd);
 }
 
-void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float* gt, const float* img_fwd,
+void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float* gt, const long long* img_fwd,
                          float image_weight, float contour, float loss_scale, float* g_pred, cudaStream_t s)
 {
     const dim3 grid(c->nparts_recon, B);
@@ -152,13 +155,13 @@ void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float*
                                             c->d_tab, img_fwd, g_pred);
 }
 
-void mm_launch_loss_finalize(const mm_ctx* c, int B, const float* img_fwd, const float* img_bwd,
+void mm_launch_loss_finalize(const mm_ctx* c, int B, const long long* img_fwd, long long* img_bwd,
                              float image_weight, float contour, float* loss, float* iou_out, cudaStream_t s)
 {
     k_loss_finalize<<<1, MM_THREADS, 0, s>>>(B, c->H, c->W, image_weight, contour, img_fwd, img_bwd, loss, iou_out);
 }
 
-void mm_launch_image_reduce(const mm_ctx* c, int B, int np, const float* part_fwd, float* img_fwd, cudaStream_t s)
+void mm_launch_image_reduce(const mm_ctx* c, int B, int np, const float* part_fwd, long long* img_fwd, cudaStream_t s)
 {
     (void)c;
     k_image_reduce<<<B, 32, 0, s>>>(np, part_fwd, img_fwd);

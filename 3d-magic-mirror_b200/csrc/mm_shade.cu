@@ -4,11 +4,11 @@
 // autograd.  Visibility and the soft silhouette come from the geometry kernels (mm_raster.cu) as two 64-bit words
 // per pixel: the atomicMax-resolved (depth, face) key and the fixed-point log-product accumulator.
 //
-// One thread per pixel, one warp per 8x4-pixel sub-tile (the layout of the geometry kernels: a warp's stores are
-// four 32-byte row segments, i.e. whole sectors), 8 sub-tiles per CTA, plain non-persistent grid = (ceil(NST/8), B):
-// this half is bandwidth/latency-bound and wants as many resident warps as possible, not work balancing.
-// Per-image sums (L1, IoU, contour, light gradients) are reduced per CTA and then, deterministically, by the last
-// CTA of the image to arrive (fixed summation order, no float atomics on scalars).
+// One thread per pixel, one warp per 8x4-pixel sub-tile (a warp's accesses are four 32-byte row segments, i.e. whole
+// sectors), ONE warp per CTA: covered tiles (texture gathers, gradient atomics) take ~10x longer than background
+// tiles, and in a multi-warp CTA the background warps would park at a barrier waiting for them (ncu: 47 % of the stall
+// samples of the 8-warp version).  Per-image sums (L1, IoU, contour, light gradients) leave each warp as fixed-point
+// 64-bit integer atomics: order-independent, hence deterministic, and barrier-free.
 #include "mm_device.cuh"
 
 namespace {
@@ -17,74 +17,26 @@ namespace {
 
 __device__ __forceinline__ float contour_c(float m, float mref) { return fabsf(m - mref); }
 
-// Per-image reduction without a second kernel and without float atomics: the CTA reduces its NV partial sums with
-// ONE barrier (warp shuffles -> shared memory -> NV threads add the 8 warp results), publishes them, takes a ticket,
-// and the LAST CTA of the image sums all partials in a fixed order (deterministic).  The ticket resets itself.
-template <int NV>
-__device__ __forceinline__ void image_reduce_last(float (&v)[NV], float* part /* [nparts][stride] of this image */,
-                                                  int stride, int nparts, uint32_t* ticket, float* out, int lane)
-{
-    __shared__ float s_part[MM_WARPS][NV];
-    __shared__ uint32_t s_ticket;
-    const int warp = threadIdx.x >> 5;
+__device__ __forceinline__ float warp_sum(float v) {
     #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(FULL, v[i], o);
-    }
-    if (lane == 0) {
-        #pragma unroll
-        for (int i = 0; i < NV; ++i) s_part[warp][i] = v[i];
-    }
-    __syncthreads();
-    if (threadIdx.x < NV) {
-        float r = 0.0f;
-        #pragma unroll
-        for (int w = 0; w < MM_WARPS; ++w) r += s_part[w][threadIdx.x];
-        part[(size_t)blockIdx.x * stride + threadIdx.x] = r;
-        __threadfence();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
-    __syncthreads();
-    if (s_ticket != (uint32_t)(nparts - 1)) return;
-    __threadfence();
-    if (threadIdx.x < 32) {
-        float acc[NV];
-        #pragma unroll
-        for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
-        #pragma unroll 1
-        for (int k = lane; k < nparts; k += 32) {
-            #pragma unroll
-            for (int i = 0; i < NV; ++i) acc[i] += __ldcg(part + (size_t)k * stride + i);
-        }
-        #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
-        }
-        if (lane == 0) {
-            #pragma unroll
-            for (int i = 0; i < NV; ++i) out[i] = acc[i];
-            *ticket = 0u;
-        }
-    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------- forward
 template <bool WITH_LOSS>
-__global__ void __launch_bounds__(MM_THREADS)
+__global__ void __launch_bounds__(32)
 k_shade_fwd(const mm_raster_params p)
 {
     __shared__ float s_lights[16];
-    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
-    __syncthreads();
+    const int b = blockIdx.y, lane = threadIdx.x;
+    if (lane < 9) s_lights[lane] = p.lights[b * 9 + lane];
+    __syncwarp();
     const size_t HW = (size_t)p.H * p.W;
     const float* rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
     float acc_l1 = 0.0f, acc_n = 0.0f, acc_d = 0.0f;
-    const int st = blockIdx.x * MM_WARPS + warp;
-    if (st < p.nst) {
+    const int st = blockIdx.x;
+    {
         const int sty = st / p.nstx, stx = st - sty * p.nstx;
         const int ix = stx * MM_ST_W + (lane & 7), iy = sty * MM_ST_H + (lane >> 3);
         const bool active = (ix < p.W) && (iy < p.H);
@@ -157,20 +109,24 @@ k_shade_fwd(const mm_raster_params p)
             }
         }
     }
-    if (WITH_LOSS) {
-        float v[4] = {acc_l1, acc_n, acc_d, 0.0f};
-        image_reduce_last<4>(v, p.part_fwd + (size_t)b * gridDim.x * 4, 4, gridDim.x, p.tickets + b * 4 + 2, p.img_fwd + b * 4, lane);
+    if (WITH_LOSS) {                     // per-image sums: fixed-point integer atomics (deterministic, no barrier)
+        const float s0 = warp_sum(acc_l1), s1 = warp_sum(acc_n), s2 = warp_sum(acc_d);
+        if (lane == 0) {
+            if (s0 != 0.0f) fx_add(p.img_fwd + b * 4 + 0, s0, MM_FX_LOSS);
+            if (s1 != 0.0f) fx_add(p.img_fwd + b * 4 + 1, s1, MM_FX_LOSS);
+            if (s2 != 0.0f) fx_add(p.img_fwd + b * 4 + 2, s2, MM_FX_LOSS);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------- backward
-__global__ void __launch_bounds__(MM_THREADS)
+__global__ void __launch_bounds__(32)
 k_shade_bwd(const mm_raster_params p)
 {
     __shared__ float s_lights[16];
-    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
-    __syncthreads();
+    const int b = blockIdx.y, lane = threadIdx.x;
+    if (lane < 9) s_lights[lane] = p.lights[b * 9 + lane];
+    __syncwarp();
     const size_t HW = (size_t)p.H * p.W;
     const int H = p.H, W = p.W;
     const int32_t* refrow = p.tab;
@@ -190,16 +146,16 @@ k_shade_bwd(const mm_raster_params p)
         k_img = p.loss_scale * p.image_weight / ((float)p.B * 3.0f * (float)HW);
         k_iou = p.loss_scale / (float)p.B;
         k_cont = p.loss_scale * p.contour / ((float)p.B * (float)HW);
-        Nb = p.img_fwd[b * 4 + 1];
-        De = p.img_fwd[b * 4 + 2] + 1e-10f;
+        Nb = fx_get(p.img_fwd + b * 4 + 1, MM_FX_LOSS);
+        De = fx_get(p.img_fwd + b * 4 + 2, MM_FX_LOSS) + 1e-10f;
     }
     const float* rg = p.rgba + (size_t)b * 4 * HW;         // forward output
     const float* gtb = p.gt ? p.gt + (size_t)b * 4 * HW : nullptr;
     const float* gup = p.g_rgba ? p.g_rgba + (size_t)b * 4 * HW : nullptr;
     float* gacc = p.gfacc + (size_t)b * p.F * 9;
     float* gtex = p.g_tex + (size_t)b * 3 * p.Ht * p.Wt;
-    const int st = blockIdx.x * MM_WARPS + warp;
-    if (st < p.nst) {
+    const int st = blockIdx.x;
+    {
         const int sty = st / p.nstx, stx = st - sty * p.nstx;
         const int ix = stx * MM_ST_W + (lane & 7), iy = sty * MM_ST_H + (lane >> 3);
         const bool active = (ix < W) && (iy < H);
@@ -381,25 +337,27 @@ k_shade_bwd(const mm_raster_params p)
             }
         }
     }
-    // ---- per-CTA partials: contour sum + 9 light gradients, reduced per image by the last CTA (fixed order)
-    float v[10];
-    v[0] = acc_contour;
+    // ---- per-image sums (contour, 9 light gradients): fixed-point integer atomics (deterministic, no barrier)
+    const float sc = warp_sum(acc_contour);
+    if (lane == 0 && sc != 0.0f) fx_add(p.img_bwd + b * 12, sc, MM_FX_LOSS);
     #pragma unroll
-    for (int i = 0; i < 9; ++i) v[1 + i] = acc_l[i];
-    image_reduce_last<10>(v, p.part_bwd + (size_t)b * gridDim.x * 12, 12, gridDim.x, p.tickets + b * 4 + 3, p.img_bwd + b * 12, lane);
+    for (int i = 0; i < 9; ++i) {
+        const float si = warp_sum(acc_l[i]);
+        if (lane == 0 && si != 0.0f) fx_add(p.img_bwd + b * 12 + 1 + i, si, MM_FX_GRAD);
+    }
 }
 
 }  // namespace
 
 void mm_launch_shade_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_loss, cudaStream_t s)
 {
-    const dim3 grid((c->nst + MM_WARPS - 1) / MM_WARPS, p.B);
-    if (with_loss) k_shade_fwd<true><<<grid, MM_THREADS, 0, s>>>(p);
-    else           k_shade_fwd<false><<<grid, MM_THREADS, 0, s>>>(p);
+    const dim3 grid(c->nst, p.B);
+    if (with_loss) k_shade_fwd<true><<<grid, 32, 0, s>>>(p);
+    else           k_shade_fwd<false><<<grid, 32, 0, s>>>(p);
 }
 
 void mm_launch_shade_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
-    const dim3 grid((c->nst + MM_WARPS - 1) / MM_WARPS, p.B);
-    k_shade_bwd<<<grid, MM_THREADS, 0, s>>>(p);
+    const dim3 grid(c->nst, p.B);
+    k_shade_bwd<<<grid, 32, 0, s>>>(p);
 }

@@ -71,7 +71,7 @@ k_vertex_fwd(const VertexFwdParams q,
              const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
              const float* __restrict__ bias,
              float* __restrict__ frec, float* __restrict__ vimg, float* __restrict__ face_normals,
-             float* __restrict__ gfacc_zero, uint32_t* __restrict__ tickets)
+             float* __restrict__ gfacc_zero, long long* __restrict__ img_fwd, long long* __restrict__ img_bwd)
 {
     extern __shared__ float sm[];
     const int V = q.V, F = q.F;
@@ -83,7 +83,10 @@ k_vertex_fwd(const VertexFwdParams q,
         Cam c;
         camera_setup(azim[b], elev[b], dist[b], bias[b * 2], bias[b * 2 + 1], c);
         for (int i = 0; i < 12; ++i) sT[i] = c.T[i];
-        if (chunk == 0) { tickets[b * 4] = 0u; tickets[b * 4 + 1] = 0u; tickets[b * 4 + 2] = 0u; tickets[b * 4 + 3] = 0u; }
+    }
+    if (chunk == 0 && threadIdx.x < 16) {          // the per-image fixed-point accumulators start at zero
+        if (threadIdx.x < 4) img_fwd[b * 4 + threadIdx.x] = 0;
+        if (threadIdx.x < 12) img_bwd[b * 12 + threadIdx.x] = 0;
     }
     __syncthreads();
     const float* vb = vertices + (size_t)b * V * 3;
@@ -153,7 +156,7 @@ k_vertex_bwd(int V, int F, float proj_x, float proj_y,
              const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
              const float* __restrict__ bias,
              const float* __restrict__ gfacc, const float* __restrict__ g_face_normals,
-             const float* __restrict__ img_bwd,
+             long long* __restrict__ img_bwd, int reset,
              float* __restrict__ g_vertices, float* __restrict__ g_azim, float* __restrict__ g_elev,
              float* __restrict__ g_dist, float* __restrict__ g_bias, float* __restrict__ g_lights)
 {
@@ -283,7 +286,11 @@ k_vertex_bwd(int V, int F, float proj_x, float proj_y,
         g_azim[b] = k * (gcam[0] * (sc.d * sc.ce * sc.ca) + gcam[2] * (-sc.d * sc.ce * sc.sa));
     }
     // (4) light gradient: per-image sums already reduced (fixed order) by the raster backward
-    if (threadIdx.x < 9) g_lights[b * 9 + threadIdx.x] = img_bwd[b * 12 + 1 + threadIdx.x];
+    if (threadIdx.x < 9) {
+        g_lights[b * 9 + threadIdx.x] = (float)((double)img_bwd[b * 12 + 1 + threadIdx.x] / 17592186044416.0);   // MM_FX_GRAD
+        if (reset) img_bwd[b * 12 + 1 + threadIdx.x] = 0;     // stand-alone backward: leave the workspace reusable
+    }
+    if (reset && threadIdx.x == 0) img_bwd[b * 12] = 0;
 }
 
 __global__ void k_export_faces(int V, int F, float multiplier, const int32_t* __restrict__ faces,
@@ -309,24 +316,25 @@ __global__ void k_export_faces(int V, int F, float multiplier, const int32_t* __
 
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec,
-                          float* vimg, float* face_normals, float* gfacc_zero, uint32_t* tickets, cudaStream_t s)
+                          float* vimg, float* face_normals, float* gfacc_zero, long long* img_fwd, long long* img_bwd,
+                          cudaStream_t s)
 {
     VertexFwdParams q;
     q.V = c->V; q.F = c->F; q.nchunks = c->nchunks;
     q.proj_x = c->proj_x; q.proj_y = c->proj_y; q.multiplier = c->multiplier;
     const dim3 grid(c->nchunks, B);
     k_vertex_fwd<<<grid, MM_VTHREADS, c->smem_vertex_fwd, s>>>(q, c->d_faces, vertices, azim, elev, dist, bias, frec,
-                                                               vimg, face_normals, gfacc_zero, tickets);
+                                                               vimg, face_normals, gfacc_zero, img_fwd, img_bwd);
 }
 
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,
-                          const float* img_bwd, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
+                          long long* img_bwd, int reset, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
                           float* g_bias, float* g_lights, cudaStream_t s)
 {
     const size_t smem = ((size_t)c->V * 6) * sizeof(float);
     k_vertex_bwd<<<B, MM_VTHREADS, smem, s>>>(c->V, c->F, c->proj_x, c->proj_y, c->d_faces, vertices, azim, elev,
-                                      dist, bias, gfacc, g_face_normals, img_bwd, g_vertices, g_azim, g_elev,
+                                      dist, bias, gfacc, g_face_normals, img_bwd, reset, g_vertices, g_azim, g_elev,
                                       g_dist, g_bias, g_lights);
 }
 
