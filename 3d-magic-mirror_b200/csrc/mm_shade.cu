@@ -120,7 +120,7 @@ k_shade_fwd(const mm_raster_params p)
 }
 
 // ---------------------------------------------------------------------------------------------- backward
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 28)
 k_shade_bwd(const mm_raster_params p)
 {
     __shared__ float s_lights[16];
@@ -136,10 +136,11 @@ k_shade_bwd(const mm_raster_params p)
     const int32_t* collo = p.tab + 3 * H + W;
     const int32_t* colhi = p.tab + 3 * H + 2 * W;
     const float* rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
-    float acc_contour = 0.0f;
+    float acc_contour = 0.0f, acc_gc = 0.0f;
     float acc_l[9];
     #pragma unroll
     for (int i = 0; i < 9; ++i) acc_l[i] = 0.0f;
+    bool tile_covered = false;
     // loss-gradient constants; the per-image IoU sums were reduced by the forward kernel (fixed order)
     float k_img = 0.0f, k_iou = 0.0f, k_cont = 0.0f, Nb = 0.0f, De = 1.0f;
     if (p.analytic_loss) {
@@ -162,6 +163,8 @@ k_shade_bwd(const mm_raster_params p)
         const float x0 = pix_x(ix, W, p.sx), y0 = pix_y(iy, H, p.sy);
         const size_t pix = active ? (size_t)iy * W + ix : 0;
         const int best_f = active ? key_face(p.zbuf[(size_t)b * HW + pix]) : -1;
+        const bool any_covered = __any_sync(FULL, best_f >= 0);
+        tile_covered = any_covered;
         // ---- upstream gradient of the 4 output channels
         float g_img[3] = {0.0f, 0.0f, 0.0f}, g_soft = 0.0f;
         float soft = 0.0f, gm_lane = 0.0f;
@@ -265,8 +268,12 @@ k_shade_bwd(const mm_raster_params p)
                     g_coef += g * (tcol[ch] * tm);
                 }
             }
-            #pragma unroll
-            for (int i = 0; i < 9; ++i) acc_l[i] += g_coef * bnd[i];
+            if (any_covered) {
+                #pragma unroll
+                for (int i = 0; i < 9; ++i) acc_l[i] += g_coef * bnd[i];
+            } else {
+                acc_gc += g_coef;                  // no normal anywhere in the tile: bands are the constants (C0,0,..,-C3B,0,0)
+            }
 
             if (best_f >= 0) {
                 // texture gradient + d/d(u,v)
@@ -340,10 +347,18 @@ k_shade_bwd(const mm_raster_params p)
     // ---- per-image sums (contour, 9 light gradients): fixed-point integer atomics (deterministic, no barrier)
     const float sc = warp_sum(acc_contour);
     if (lane == 0 && sc != 0.0f) fx_add(p.img_bwd + b * 12, sc, MM_FX_LOSS);
-    #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        const float si = warp_sum(acc_l[i]);
-        if (lane == 0 && si != 0.0f) fx_add(p.img_bwd + b * 12 + 1 + i, si, MM_FX_GRAD);
+    if (tile_covered) {
+        #pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const float si = warp_sum(acc_l[i]);
+            if (lane == 0 && si != 0.0f) fx_add(p.img_bwd + b * 12 + 1 + i, si, MM_FX_GRAD);
+        }
+    } else {                              // background tile: one reduction instead of nine
+        const float sg = warp_sum(acc_gc);
+        if (lane == 0 && sg != 0.0f) {
+            fx_add(p.img_bwd + b * 12 + 1 + 0, sg * SH_C0, MM_FX_GRAD);
+            fx_add(p.img_bwd + b * 12 + 1 + 6, sg * (-SH_C3B), MM_FX_GRAD);
+        }
     }
 }
 
