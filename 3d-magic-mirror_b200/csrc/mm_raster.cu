@@ -343,86 +343,124 @@ k_soft_bwd_list(const mm_raster_params p)
 }
 
 // ---------------------------------------------------------------------------------------------- overflow (ordered) pass
-// One warp per pixel that saw more than knum candidates: replay DIBR_SPEC A.4 literally -- faces in index order, first
-// knum whose enlarged bbox holds the pixel.  32 faces per step; the ballot keeps the order.
+// DIB-R keeps only the FIRST knum candidates in face-index order (DIBR_SPEC A.4).  Pixels that saw more are re-done
+// here literally.  One CTA per overflowed pixel: all F enlarged-bbox tests happen in ONE memory round trip (each thread
+// owns F/256 faces), the per-warp ballots land in shared memory as hit words in face order, warp 0 applies the knum cap
+// with a running count over the words, and the kept candidates (<= knum, wherever they are) are then evaluated by the
+// threads that own them.  Forward: per-word ordered products, multiplied in word order.  Backward: the gradients of
+// exactly those candidates.
+#define OVF_MAX_WORDS 2048          // F <= 65535
+
 template <bool BWD>
 __global__ void __launch_bounds__(256)
 k_soft_ovf(const mm_raster_params p)
 {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t n = *p.ovf_count;
+    __shared__ uint32_t s_mask[OVF_MAX_WORDS];
+    __shared__ float s_wprod[OVF_MAX_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n = p.ovf_count[0];
     const size_t HW = (size_t)p.H * p.W;
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
     const float inv_mult = 1.0f / p.multiplier;
-    for (uint32_t e = warp; e < n; e += nwarps) {
+    const int nw = (p.F + 31) >> 5;
+    const int niter = (p.F + 255) >> 8;                       // faces per thread
+    for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
         const uint32_t pg = p.ovf_list[e];
         const int b = (int)(pg / HW);
         const int pix = (int)(pg - (size_t)b * HW);
         const int iy = pix / p.W, ix = pix - iy * p.W;
         const float px = pix_x(ix, p.W, p.sx), py = pix_y(iy, p.H, p.sy);
-        const float* rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
+        const float4* rec4 = reinterpret_cast<const float4*>(p.frec + (size_t)b * p.F * MM_REC_FLOATS);
         float g = 0.0f, one_m_all = 0.0f;
         if (BWD) {
             g = p.gsoft[pg];
             const float soft = p.rgba[(size_t)b * 4 * HW + 3 * HW + pix];
             one_m_all = 1.0f - soft;
-            if (g == 0.0f || !(soft > 0.0f)) continue;          // warp-uniform
+            if (g == 0.0f || !(soft > 0.0f)) continue;          // block-uniform
         }
-        int kid = 0;
-        float allprob = 1.0f;
-        // 8 x 32 faces per step: the bbox loads are independent, so one memory round trip covers 256 faces
-        for (int f0 = 0; f0 < p.F && kid < p.knum; f0 += 256) {
-            float4 c0[8], c1[8];
-            #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int f = f0 + u * 32 + lane;
-                if (f < p.F) {
-                    const float4* q4 = reinterpret_cast<const float4*>(rec) + (size_t)f * 3;
-                    c0[u] = __ldg(q4); c1[u] = __ldg(q4 + 1);
-                } else { c0[u] = make_float4(0.f, 0.f, 0.f, 0.f); c1[u] = c0[u]; }
-            }
-            #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (kid >= p.knum) break;
-                const int f = f0 + u * 32 + lane;
+        // ---- phase 1: enlarged-bbox hit words, face order (word = f >> 5)
+        for (int j = 0; j < niter; ++j) {
+            const int f = (j << 8) + threadIdx.x;
+            bool hit = false;
+            if (f < p.F) {
+                const float4 c0 = __ldg(rec4 + (size_t)f * 3), c1 = __ldg(rec4 + (size_t)f * 3 + 1);
                 FaceRec r;
-                r.ax = c0[u].x; r.ay = c0[u].y; r.bx = c0[u].z; r.by = c0[u].w; r.cx = c1[u].x; r.cy = c1[u].y;
+                r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
                 r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
-                const bool hit = (f < p.F) && soft_bbox_test(r, px, py, p.blen);
-                uint32_t m = __ballot_sync(FULL, hit);
-                const int room = p.knum - kid;
-                if (__popc(m) > room) {                          // keep the `room` lowest set bits
+                hit = soft_bbox_test(r, px, py, p.blen);
+            }
+            const uint32_t m = __ballot_sync(FULL, hit);
+            const int word = (j << 3) + warp;
+            if (lane == 0 && word < nw) s_mask[word] = m;
+        }
+        __syncthreads();
+        // ---- phase 2 (warp 0): keep the first knum set bits over all words
+        if (warp == 0) {
+            int seen = 0;
+            for (int w0 = 0; w0 < nw; w0 += 32) {
+                const int wd = w0 + lane;
+                const uint32_t m = (wd < nw) ? s_mask[wd] : 0u;
+                const int c = __popc(m);
+                int incl = c;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+                const int before = seen + incl - c;
+                int room = p.knum - before;
+                room = room < 0 ? 0 : room;
+                uint32_t keep = m;
+                if (c > room) {
                     uint32_t k2 = 0u, h = m;
                     #pragma unroll 1
                     for (int a = 0; a < room; ++a) { const uint32_t low = h & (0u - h); k2 |= low; h ^= low; }
-                    m = k2;
+                    keep = k2;
                 }
-                const bool mine = (m >> lane) & 1u;
-                if (BWD) {
-                    if (mine) {
-                        float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-                        soft_pair_grad(p, r, px, py, kz, inv_mult, g, one_m_all, ga);
-                        float* gf = p.gfacc + ((size_t)b * p.F + f) * 9;
-                        #pragma unroll
-                        for (int k = 0; k < 6; ++k) if (ga[k] != 0.0f) atomicAdd(gf + k, ga[k]);
-                    }
-                } else {
-                    float prob = 0.0f;
-                    if (mine) { int type; prob = soft_prob_fast(soft_d2_fast(r, px, py, p.multiplier, type), kz); }
-                    uint32_t mm = m;
-                    #pragma unroll 1
-                    while (mm) {                                 // the reference's ordered product
-                        const int j = __ffs(mm) - 1;
-                        mm &= mm - 1;
-                        allprob = allprob * (1.0f - __shfl_sync(FULL, prob, j));
-                    }
-                }
-                kid += __popc(m);
+                if (wd < nw) { s_mask[wd] = keep; s_wprod[wd] = 1.0f; }
+                seen += __shfl_sync(FULL, incl, 31);
             }
         }
-        if (!BWD && lane == 0) p.lacc[pg] = lacc_exact(allprob > 0.0f ? logf(allprob) : -2400.0f);
+        __syncthreads();
+        // ---- phase 3: the owners of the kept candidates evaluate them
+        for (int j = 0; j < niter; ++j) {
+            const int f = (j << 8) + threadIdx.x;
+            const int word = (j << 3) + warp;
+            const uint32_t keep = (word < nw) ? s_mask[word] : 0u;
+            if (keep == 0u) continue;                           // warp-uniform
+            const bool mine = (keep >> lane) & 1u;
+            FaceRec r;
+            if (mine) {
+                const float4 c0 = __ldg(rec4 + (size_t)f * 3), c1 = __ldg(rec4 + (size_t)f * 3 + 1);
+                r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
+                r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
+            }
+            if (BWD) {
+                if (mine) {
+                    float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+                    soft_pair_grad(p, r, px, py, kz, inv_mult, g, one_m_all, ga);
+                    float* gf = p.gfacc + ((size_t)b * p.F + f) * 9;
+                    #pragma unroll
+                    for (int k = 0; k < 6; ++k) if (ga[k] != 0.0f) atomicAdd(gf + k, ga[k]);
+                }
+            } else {
+                float prob = 0.0f;
+                if (mine) { int type; prob = soft_prob_fast(soft_d2_fast(r, px, py, p.multiplier, type), kz); }
+                float wp = 1.0f;
+                uint32_t mm = keep;
+                #pragma unroll 1
+                while (mm) {                                     // the reference's ordered product within the word
+                    const int jj = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    wp = wp * (1.0f - __shfl_sync(FULL, prob, jj));
+                }
+                if (lane == 0) s_wprod[word] = wp;
+            }
+        }
+        __syncthreads();
+        if (!BWD && threadIdx.x == 0) {
+            float allprob = 1.0f;
+            for (int wd = 0; wd < nw; ++wd) if (s_mask[wd]) allprob = allprob * s_wprod[wd];     // word order = face order
+            p.lacc[pg] = lacc_exact(allprob > 0.0f ? logf(allprob) : -2400.0f);
+        }
+        __syncthreads();
     }
 }
 
@@ -434,7 +472,7 @@ void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t
     const int grid = (warps + 7) / 8;
     k_scatter<MODE_HARD><<<grid, 256, 0, s>>>(p);
     k_scatter<MODE_SOFT_FWD><<<grid, 256, 0, s>>>(p);
-    k_soft_ovf<false><<<c->num_sms * 2, 256, 0, s>>>(p);
+    k_soft_ovf<false><<<c->num_sms * 8, 256, 0, s>>>(p);
 }
 
 void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
@@ -443,7 +481,7 @@ void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t
     const int grid = (warps + 7) / 8;
     k_soft_bwd_list<<<c->num_sms * 4, 256, 0, s>>>(p);
     k_scatter<MODE_SOFT_BWD><<<grid, 256, 0, s>>>(p);              // returns immediately unless the pair list overflowed
-    k_soft_ovf<true><<<c->num_sms * 2, 256, 0, s>>>(p);
+    k_soft_ovf<true><<<c->num_sms * 8, 256, 0, s>>>(p);
 }
 
 size_t mm_raster_smem_bytes(const mm_ctx* c) { (void)c; return 0; }
