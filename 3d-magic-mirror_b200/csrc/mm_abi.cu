@@ -312,15 +312,15 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     mm_launch_geom_fwd(c, p, s);
     if (int r = check_launch("geom_fwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[2], s);
-    mm_launch_shade_fwd(c, p, true, s);
-    if (int r = check_launch("shade_fwd")) return r;
-    if (c->timing) cudaEventRecord(c->ev[3], s);
     p.g_rgba = g_rgba_extra;
     p.image_weight = image_weight; p.contour = contour; p.loss_scale = loss_scale;
     p.analytic_loss = 1;
     p.g_tex = g_tex; p.g_bg = no_mask ? g_bg : nullptr;
-    mm_launch_shade_bwd(c, p, s);
-    if (int r = check_launch("shade_bwd")) return r;
+    mm_launch_shade_fused(c, p, s);           // shading forward + loss sums + the whole RGB-side backward
+    if (int r = check_launch("shade_fused")) return r;
+    if (c->timing) cudaEventRecord(c->ev[3], s);
+    mm_launch_gsoft(c, p, s);                 // d(loss)/d(silhouette), needs the complete per-image IoU sums
+    if (int r = check_launch("gsoft")) return r;
     if (c->timing) cudaEventRecord(c->ev[4], s);
     mm_launch_geom_bwd(c, p, s);
     if (int r = check_launch("geom_bwd")) return r;

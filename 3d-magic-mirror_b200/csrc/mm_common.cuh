@@ -164,6 +164,8 @@ void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t
 void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 void mm_launch_shade_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_loss, cudaStream_t s);
 void mm_launch_shade_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
+void mm_launch_shade_fused(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
+void mm_launch_gsoft(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 void mm_launch_loss_finalize(const mm_ctx* c, int B, const long long* img_fwd, long long* img_bwd,
                              float image_weight, float contour, float* loss, float* iou_out, cudaStream_t s);
 void mm_launch_image_reduce(const mm_ctx* c, int B, int np, const float* part_fwd, long long* img_fwd, cudaStream_t s);

@@ -160,10 +160,12 @@ struct Bilin {
 };
 
 __device__ __forceinline__ void bilin_setup(float u, float v, int Ht, int Wt, Bilin& s) {
-    const float gx = u * 2.0f - 1.0f;
-    const float gy = -(v * 2.0f - 1.0f);
-    float x = ((gx + 1.0f) * (float)Wt - 1.0f) * 0.5f;
-    float y = ((gy + 1.0f) * (float)Ht - 1.0f) * 0.5f;
+    // explicit roundings: the fused and the unfused kernels must produce bit-identical images, so nothing here is left
+    // to the compiler's FMA-contraction choices
+    const float gx = SUB(MUL(u, 2.0f), 1.0f);
+    const float gy = -SUB(MUL(v, 2.0f), 1.0f);
+    float x = MUL(SUB(MUL(ADD(gx, 1.0f), (float)Wt), 1.0f), 0.5f);
+    float y = MUL(SUB(MUL(ADD(gy, 1.0f), (float)Ht), 1.0f), 0.5f);
     s.in_x = (x > 0.0f) && (x < (float)(Wt - 1));
     s.in_y = (y > 0.0f) && (y < (float)(Ht - 1));
     x = fminf((float)(Wt - 1), fmaxf(x, 0.0f));
@@ -171,11 +173,11 @@ __device__ __forceinline__ void bilin_setup(float u, float v, int Ht, int Wt, Bi
     const float fx = floorf(x), fy = floorf(y);
     s.ix = (int)fx; s.iy = (int)fy;
     s.x = x; s.y = y;
-    const float tx = x - fx, ty = y - fy;
-    s.nw = (1.0f - tx) * (1.0f - ty);
-    s.ne = tx * (1.0f - ty);
-    s.sw = (1.0f - tx) * ty;
-    s.se = tx * ty;
+    const float tx = SUB(x, fx), ty = SUB(y, fy);
+    s.nw = MUL(SUB(1.0f, tx), SUB(1.0f, ty));
+    s.ne = MUL(tx, SUB(1.0f, ty));
+    s.sw = MUL(SUB(1.0f, tx), ty);
+    s.se = MUL(tx, ty);
 }
 
 struct TexFetch {
@@ -193,6 +195,17 @@ __device__ __forceinline__ TexFetch tex_fetch(const float* __restrict__ plane, c
     return t;
 }
 
+// bilinear blend of the 4 fetched texels, fixed FMA chain
+__device__ __forceinline__ float tex_blend(const TexFetch& t, const Bilin& b) {
+    return __fmaf_rn(t.se, b.se, __fmaf_rn(t.sw, b.sw, __fmaf_rn(t.ne, b.ne, MUL(t.nw, b.nw))));
+}
+
+// networks.py:307-313 composite before the clamp, fixed operation order
+__device__ __forceinline__ float composite_pre(bool no_mask, float tcol, float tm, float bgc, float coef) {
+    return no_mask ? MUL(__fmaf_rn(tcol, tm, MUL(bgc, SUB(1.0f, tm))), coef)
+                   : __fmaf_rn(MUL(tcol, tm), coef, SUB(1.0f, tm));
+}
+
 // kaolin spherical_harmonic_lighting (9 bands)
 #define SH_C0 0.28209479177f
 #define SH_C1 0.4886025119f
@@ -204,20 +217,20 @@ __device__ __forceinline__ TexFetch tex_fetch(const float* __restrict__ plane, c
 
 __device__ __forceinline__ void sh_bands(float x, float y, float z, float* bnd) {
     bnd[0] = SH_C0;
-    bnd[1] = SH_C1 * x;
-    bnd[2] = SH_C1 * z;
-    bnd[3] = SH_C1 * y;
-    bnd[4] = SH_C2 * (x * y);
-    bnd[5] = SH_C2 * (y * z);
-    bnd[6] = SH_C3 * (z * z) - SH_C3B;
-    bnd[7] = SH_C4 * (x * z);
-    bnd[8] = SH_C5 * (x * x - y * y);
+    bnd[1] = MUL(SH_C1, x);
+    bnd[2] = MUL(SH_C1, z);
+    bnd[3] = MUL(SH_C1, y);
+    bnd[4] = MUL(SH_C2, MUL(x, y));
+    bnd[5] = MUL(SH_C2, MUL(y, z));
+    bnd[6] = __fmaf_rn(SH_C3, MUL(z, z), -SH_C3B);
+    bnd[7] = MUL(SH_C4, MUL(x, z));
+    bnd[8] = MUL(SH_C5, __fmaf_rn(x, x, -MUL(y, y)));
 }
 
 __device__ __forceinline__ float sh_coef(const float* bnd, const float* l) {
     float c = 0.0f;
     #pragma unroll
-    for (int i = 0; i < 9; ++i) c += bnd[i] * l[i];
+    for (int i = 0; i < 9; ++i) c = __fmaf_rn(bnd[i], l[i], c);
     return c;
 }
 

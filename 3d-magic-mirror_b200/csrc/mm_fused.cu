@@ -1,0 +1,407 @@
+// mm_fused.cu -- per-pixel kernels of the FUSED render-compare step (mm_render_compare_fwd_bwd).
+//
+// The unfused API (render, then recon_data, then autograd) needs a shading forward and, later, a shading backward
+// that re-reads everything (mm_shade.cu).  In the fused step the loss is known while the pixel is being shaded, and
+// of the whole backward only d(loss)/d(silhouette) depends on per-image sums (the IoU ratio): every RGB-side
+// gradient (texture, background, lights, face normals, hard-rasteriser uv term) is a function of the pixel alone.
+//
+//   k_shade_fused   one pass over the pixels: shading forward (networks.py:303-317), the L1/IoU partial sums
+//                   (networks.py:374-377) AND the complete RGB-side backward.  Every input plane is read once,
+//                   4 pixels per thread as float4 (16-byte) accesses issued up front; a warp owns a 16x8-pixel tile.
+//   k_gsoft         after the per-image sums are complete: d(loss)/d(silhouette) for every pixel (IoU + contour +
+//                   optional upstream gradient) and the contour loss sum.  Reads 2-3 planes, writes one.
+// The geometry backward (mm_raster.cu) then consumes `gsoft` exactly as in the unfused path.
+#include "mm_device.cuh"
+
+namespace {
+
+#define FULL 0xffffffffu
+#define FT_W 16           // tile of one warp: 16 x 8 pixels, lane = (ly = lane >> 2, lx = lane & 3), 4 pixels per lane
+#define FT_H 8
+#define FUSED_WARPS 4
+
+__device__ __forceinline__ float warp_sum(float v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// 4 consecutive floats of a plane row: one 16-byte access when the row start is 16-byte aligned (VEC), else guarded scalars
+template <bool VEC>
+__device__ __forceinline__ void load4(const float* __restrict__ p, int n, float (&v)[4]) {
+    if (VEC) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (j < n) ? __ldg(p + j) : 0.0f;
+    }
+}
+template <bool VEC>
+__device__ __forceinline__ void store4(float* __restrict__ p, int n, const float (&v)[4]) {
+    if (VEC) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < n) p[j] = v[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- fused shading
+template <bool VEC>
+__global__ void __launch_bounds__(32 * FUSED_WARPS)
+k_shade_fused(const mm_raster_params p)
+{
+    __shared__ float s_lights[16];
+    __shared__ float s_red[FUSED_WARPS][12];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
+    __syncthreads();
+    const int H = p.H, W = p.W;
+    const size_t HW = (size_t)H * W;
+    const int ntx = (W + FT_W - 1) / FT_W;
+    const int tile = blockIdx.x * FUSED_WARPS + warp;
+    const int ty = tile / ntx, tx = tile - ty * ntx;
+    const int iy = ty * FT_H + (lane >> 2), ix0 = tx * FT_W + (lane & 3) * 4;
+    const int n = (iy < H) ? min(4, W - ix0) : 0;                 // valid pixels of this lane (<= 0: none)
+    const bool active = n > 0;
+    const size_t pix0 = active ? (size_t)iy * W + ix0 : 0;
+
+    float acc_l1 = 0.0f, acc_n = 0.0f, acc_d = 0.0f, acc_gc = 0.0f;
+    float acc_l[9];
+    #pragma unroll
+    for (int i = 0; i < 9; ++i) acc_l[i] = 0.0f;
+    bool lane_covered = false;
+
+    if (active) {
+        // ---- every streamed input of the 4 pixels, issued up front
+        int face[4];
+        float soft[4];
+        {
+            const unsigned long long* zb = p.zbuf + (size_t)b * HW + pix0;
+            const unsigned long long* la = p.lacc + (size_t)b * HW + pix0;
+            unsigned long long z[4], l[4];
+            if (VEC) {
+                const ulonglong2 z0 = *reinterpret_cast<const ulonglong2*>(zb), z1 = *reinterpret_cast<const ulonglong2*>(zb + 2);
+                const ulonglong2 l0 = *reinterpret_cast<const ulonglong2*>(la), l1 = *reinterpret_cast<const ulonglong2*>(la + 2);
+                z[0] = z0.x; z[1] = z0.y; z[2] = z1.x; z[3] = z1.y;
+                l[0] = l0.x; l[1] = l0.y; l[2] = l1.x; l[3] = l1.y;
+            } else {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) { z[j] = (j < n) ? zb[j] : 0ull; l[j] = (j < n) ? la[j] : 0ull; }
+            }
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                face[j] = (j < n) ? key_face(z[j]) : -1;
+                soft[j] = (face[j] >= 0) ? 1.0f : lacc_soft(l[j]);
+            }
+        }
+        float bgv[3][4], gtv[4][4], gup[3][4];
+        const float* gtb = p.gt + (size_t)b * 4 * HW + pix0;
+        #pragma unroll
+        for (int ch = 0; ch < 4; ++ch) load4<VEC>(gtb + ch * HW, n, gtv[ch]);
+        #pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            if (p.no_mask) load4<VEC>(p.bg + ((size_t)b * 3 + ch) * HW + pix0, n, bgv[ch]);
+            else { bgv[ch][0] = bgv[ch][1] = bgv[ch][2] = bgv[ch][3] = 0.0f; }
+            if (p.g_rgba) load4<VEC>(p.g_rgba + ((size_t)b * 4 + ch) * HW + pix0, n, gup[ch]);
+            else { gup[ch][0] = gup[ch][1] = gup[ch][2] = gup[ch][3] = 0.0f; }
+        }
+        const float k_img = p.loss_scale * p.image_weight / ((float)p.B * 3.0f * (float)HW);
+        const float* rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
+        const float* tb = p.tex + (size_t)b * 3 * p.Ht * p.Wt;
+        float* gacc = p.gfacc + (size_t)b * p.F * 9;
+        float* gtex = p.g_tex + (size_t)b * 3 * p.Ht * p.Wt;
+        float img[3][4], gbg[3][4];
+        float coef_bg;                                                          // sh_coef of a zero normal, same op sequence
+        { float bnd0[9]; sh_bands(0.0f, 0.0f, 0.0f, bnd0); coef_bg = sh_coef(bnd0, s_lights); }
+
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gm = gtv[3][j];
+            if (face[j] < 0) {
+                // ---- background pixel: texmask = 0, normal = 0 (networks.py:307-314 with texmask 0)
+                float g_coef = 0.0f;
+                #pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    // the covered-path expression with tcol = tm = 0 (bit-identical to the unfused kernel)
+                    const float pre = composite_pre(p.no_mask, 0.0f, 0.0f, bgv[ch][j], coef_bg);
+                    const float v = clamp01(pre);
+                    img[ch][j] = v;
+                    const float lt = l1_term(v, gtv[ch][j], gm);
+                    acc_l1 += fabsf(lt);
+                    float g = gup[ch][j] + k_img * sgnf(lt) * gm;
+                    g = (pre >= 0.0f && pre <= 1.0f) ? g : 0.0f;
+                    gbg[ch][j] = g * coef_bg;
+                    if (p.no_mask) g_coef += g * bgv[ch][j];
+                }
+                if (j < n) acc_gc += g_coef;
+            } else {
+                // ---- covered pixel: shading forward + the whole RGB-side backward
+                lane_covered = true;
+                const int f = face[j];
+                const FaceRec r = load_rec(rec, f);
+                Bary bar;
+                bary_eval(r, pix_x(ix0 + j, W, p.sx), pix_y(iy, H, p.sy), p.eps, bar);
+                float uv[6];
+                const float* uvp = p.face_uvs + f * 6;
+                #pragma unroll
+                for (int i = 0; i < 6; ++i) uv[i] = __ldg(uvp + i);
+                const float u = interp3(bar.w0, bar.w1, bar.w2, uv[0], uv[2], uv[4]);
+                const float v = interp3(bar.w0, bar.w1, bar.w2, uv[1], uv[3], uv[5]);
+                const float tm = ADD(ADD(bar.w0, bar.w1), bar.w2);
+                const float nx = interp3(bar.w0, bar.w1, bar.w2, r.nx, r.nx, r.nx);
+                const float ny = interp3(bar.w0, bar.w1, bar.w2, r.ny, r.ny, r.ny);
+                const float nz = interp3(bar.w0, bar.w1, bar.w2, r.nz, r.nz, r.nz);
+                Bilin bl;
+                bilin_setup(u, v, p.Ht, p.Wt, bl);
+                TexFetch tf[3];
+                float tcol[3];
+                #pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    tf[ch] = tex_fetch(tb + (size_t)ch * p.Ht * p.Wt, bl, p.Ht, p.Wt);
+                    tcol[ch] = tex_blend(tf[ch], bl);
+                }
+                float bnd[9];
+                sh_bands(nx, ny, nz, bnd);
+                const float coef = sh_coef(bnd, s_lights);
+                float g_coef = 0.0f, g_tcol[3];
+                #pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float pre = composite_pre(p.no_mask, tcol[ch], tm, bgv[ch][j], coef);
+                    const float val = clamp01(pre);
+                    img[ch][j] = val;
+                    const float lt = l1_term(val, gtv[ch][j], gm);
+                    acc_l1 += fabsf(lt);
+                    float g = gup[ch][j] + k_img * sgnf(lt) * gm;
+                    g = (pre >= 0.0f && pre <= 1.0f) ? g : 0.0f;                     // torch.clamp backward
+                    g_tcol[ch] = g * tm * coef;
+                    gbg[ch][j] = g * (1.0f - tm) * coef;
+                    g_coef += p.no_mask ? g * (tcol[ch] * tm + bgv[ch][j] * (1.0f - tm)) : g * (tcol[ch] * tm);
+                }
+                #pragma unroll
+                for (int i = 0; i < 9; ++i) acc_l[i] += g_coef * bnd[i];
+
+                // texture gradient + d/d(u,v)
+                float gix = 0.0f, giy = 0.0f;
+                const bool xe = (bl.ix + 1) < p.Wt, ys = (bl.iy + 1) < p.Ht;
+                const float txf = bl.x - (float)bl.ix, tyf = bl.y - (float)bl.iy;
+                #pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float g = g_tcol[ch];
+                    if (g != 0.0f) {
+                        float* gp = gtex + ((size_t)ch * p.Ht + bl.iy) * p.Wt + bl.ix;
+                        atomicAdd(gp, g * bl.nw);
+                        if (xe) atomicAdd(gp + 1, g * bl.ne);
+                        if (ys) atomicAdd(gp + p.Wt, g * bl.sw);
+                        if (xe && ys) atomicAdd(gp + p.Wt + 1, g * bl.se);
+                        gix += g * ((tf[ch].ne - tf[ch].nw) * (1.0f - tyf) + (tf[ch].se - tf[ch].sw) * tyf);
+                        giy += g * ((tf[ch].sw - tf[ch].nw) * (1.0f - txf) + (tf[ch].se - tf[ch].ne) * txf);
+                    }
+                }
+                const float g_gx = bl.in_x ? gix * ((float)p.Wt * 0.5f) : 0.0f;
+                const float g_gy = bl.in_y ? giy * ((float)p.Ht * 0.5f) : 0.0f;
+                const float g_u = 2.0f * g_gx, g_v = -2.0f * g_gy;
+
+                // d coef / d normal -> unit face normal (the three corners carry the same normal)
+                const float* l = s_lights;
+                const float dcx = l[1] * SH_C1 + l[4] * SH_C2 * ny + l[7] * SH_C4 * nz + l[8] * SH_C5 * 2.0f * nx;
+                const float dcy = l[3] * SH_C1 + l[4] * SH_C2 * nx + l[5] * SH_C2 * nz - l[8] * SH_C5 * 2.0f * ny;
+                const float dcz = l[2] * SH_C1 + l[5] * SH_C2 * ny + l[6] * SH_C3 * 2.0f * nz + l[7] * SH_C4 * nx;
+                float* ga = gacc + (size_t)f * 9;
+                const float gn_scale = g_coef * tm;
+                if (gn_scale != 0.0f) {
+                    atomicAdd(ga + 6, gn_scale * dcx);
+                    atomicAdd(ga + 7, gn_scale * dcy);
+                    atomicAdd(ga + 8, gn_scale * dcz);
+                }
+                // hard rasteriser backward (DIBR_SPEC A.3) for the u,v channels
+                if (g_u != 0.0f || g_v != 0.0f) {
+                    const float k1 = bar.k1, k2 = bar.k2, k3 = bar.k3;
+                    const float m = bar.m, pp = bar.p, nn = bar.n, q = bar.q, s = bar.s, t = bar.t;
+                    const float dw1dm = SUB(MUL(0.0f, k3), MUL(q, k1)),   dw1dn = SUB(MUL(-t, k3), MUL(-pp, k1));
+                    const float dw1dp = SUB(MUL(0.0f, k3), MUL(-nn, k1)), dw1dq = SUB(MUL(s, k3), MUL(m, k1));
+                    const float dw1ds = SUB(MUL(q, k3), MUL(0.0f, k1)),   dw1dt = SUB(MUL(-nn, k3), MUL(0.0f, k1));
+                    const float dw2dm = SUB(MUL(t, k3), MUL(q, k2)),      dw2dn = SUB(MUL(0.0f, k3), MUL(-pp, k2));
+                    const float dw2dp = SUB(MUL(-s, k3), MUL(-nn, k2)),   dw2dq = SUB(MUL(0.0f, k3), MUL(m, k2));
+                    const float dw2ds = SUB(MUL(-pp, k3), MUL(0.0f, k2)), dw2dt = SUB(MUL(m, k3), MUL(0.0f, k2));
+                    const float dw1dax = -ADD(ADD(dw1dm, dw1dn), dw1ds), dw1day = -ADD(ADD(dw1dp, dw1dq), dw1dt);
+                    const float dw2dax = -ADD(ADD(dw2dm, dw2dn), dw2ds), dw2day = -ADD(ADD(dw2dp, dw2dq), dw2dt);
+                    const float den = ADD(MUL(k3, k3), p.eps);
+                    float gv[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+                    #pragma unroll
+                    for (int d = 0; d < 2; ++d) {
+                        const float gd = d == 0 ? g_u : g_v;
+                        const float c0 = uv[d], c1 = uv[2 + d], c2 = uv[4 + d];
+                        const float e1 = SUB(c1, c0), e2 = SUB(c2, c0);
+                        const float dldI = DIV(MUL(p.multiplier, gd), den);
+                        gv[0] += MUL(dldI, ADD(MUL(e1, dw1dax), MUL(e2, dw2dax)));
+                        gv[1] += MUL(dldI, ADD(MUL(e1, dw1day), MUL(e2, dw2day)));
+                        gv[2] += MUL(dldI, ADD(MUL(e1, dw1dm), MUL(e2, dw2dm)));
+                        gv[3] += MUL(dldI, ADD(MUL(e1, dw1dp), MUL(e2, dw2dp)));
+                        gv[4] += MUL(dldI, ADD(MUL(e1, dw1dn), MUL(e2, dw2dn)));
+                        gv[5] += MUL(dldI, ADD(MUL(e1, dw1dq), MUL(e2, dw2dq)));
+                    }
+                    #pragma unroll
+                    for (int i = 0; i < 6; ++i) atomicAdd(ga + i, gv[i]);
+                }
+            }
+            if (j < n) {                                   // IoU partial sums (kaolin mask_iou)
+                const float mul = soft[j] * gm;
+                acc_n += mul;
+                acc_d += (soft[j] + gm) - mul;
+            }
+        }
+        // ---- outputs, one 16-byte store per plane
+        float* out = p.rgba + (size_t)b * 4 * HW + pix0;
+        #pragma unroll
+        for (int ch = 0; ch < 3; ++ch) store4<VEC>(out + ch * HW, n, img[ch]);
+        store4<VEC>(out + 3 * HW, n, soft);
+        if (p.g_bg) {
+            #pragma unroll
+            for (int ch = 0; ch < 3; ++ch) store4<VEC>(p.g_bg + ((size_t)b * 3 + ch) * HW + pix0, n, gbg[ch]);
+        }
+    }
+
+    // ---- per-image sums: warp shuffle -> shared -> 12 fixed-point integer atomics per CTA (order-independent)
+    const bool warp_covered = __any_sync(FULL, lane_covered);
+    acc_l[0] += acc_gc * SH_C0;                  // background pixels: bands = (C0, 0, .., -C3B, 0, 0)
+    acc_l[6] += acc_gc * (-SH_C3B);
+    float sums[12];
+    sums[0] = warp_sum(acc_l1); sums[1] = warp_sum(acc_n); sums[2] = warp_sum(acc_d);
+    if (warp_covered) {
+        #pragma unroll
+        for (int i = 0; i < 9; ++i) sums[3 + i] = warp_sum(acc_l[i]);
+    } else {
+        #pragma unroll
+        for (int i = 0; i < 9; ++i) sums[3 + i] = 0.0f;
+        sums[3] = warp_sum(acc_l[0]);
+        sums[9] = warp_sum(acc_l[6]);
+    }
+    if (lane == 0) {
+        #pragma unroll
+        for (int i = 0; i < 12; ++i) s_red[warp][i] = sums[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        float v = 0.0f;
+        #pragma unroll
+        for (int w = 0; w < FUSED_WARPS; ++w) v += s_red[w][threadIdx.x];
+        if (v != 0.0f) {
+            if (threadIdx.x < 3) fx_add(p.img_fwd + b * 4 + threadIdx.x, v, MM_FX_LOSS);
+            else                 fx_add(p.img_bwd + b * 12 + 1 + (threadIdx.x - 3), v, MM_FX_GRAD);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- d(loss)/d(silhouette)
+// FAST4 (H, W multiples of 4): the contour term's nearest-down/nearest-up reference of a pixel is the top-left pixel of
+// its 4x4 block (DIBR_SPEC A.7).  4 consecutive lanes own the 4 rows of one block, each lane one float4 row segment.
+template <bool FAST4>
+__global__ void __launch_bounds__(128)
+k_gsoft(const mm_raster_params p)
+{
+    const int b = blockIdx.y;
+    const int H = p.H, W = p.W;
+    const size_t HW = (size_t)H * W;
+    const float* alpha = p.rgba + (size_t)b * 4 * HW + 3 * HW;
+    const float* gmask = p.gt + (size_t)b * 4 * HW + 3 * HW;
+    const float* gup = p.g_rgba ? p.g_rgba + (size_t)b * 4 * HW + 3 * HW : nullptr;
+    float* gs = p.gsoft + (size_t)b * HW;
+    const float Nb = fx_get(p.img_fwd + b * 4 + 1, MM_FX_LOSS);
+    const float De = fx_get(p.img_fwd + b * 4 + 2, MM_FX_LOSS) + 1e-10f;
+    const float k_iou = p.loss_scale / (float)p.B;
+    const float k_cont = p.loss_scale * p.contour / ((float)p.B * (float)HW);
+    const float inv_de2 = 1.0f / (De * De);
+    float acc_c = 0.0f;
+    if (FAST4) {
+        const int W4 = W >> 2;
+        const int t = blockIdx.x * blockDim.x + threadIdx.x;         // (block, row-in-block)
+        const int blk = t >> 2, r = t & 3;
+        const bool active = blk < (H >> 2) * W4;
+        const int by = blk / W4, bx = blk - by * W4;
+        const size_t pix0 = active ? (size_t)(by * 4 + r) * W + bx * 4 : 0;
+        float m[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0}, u[4] = {0, 0, 0, 0};
+        if (active) {
+            load4<true>(alpha + pix0, 4, m);
+            load4<true>(gmask + pix0, 4, g);
+            if (gup) load4<true>(gup + pix0, 4, u);
+        }
+        const int ref_lane = threadIdx.x & 28;                        // lane of row 0 of this block (warp-relative)
+        const float mref = __shfl_sync(FULL, m[0], ref_lane), gref = __shfl_sync(FULL, g[0], ref_lane);
+        float out[4];
+        float tsum = 0.0f;
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            out[j] = u[j] - k_iou * (g[j] * De - Nb * (1.0f - g[j])) * inv_de2;
+            if (p.contour > 0.0f) {
+                const float dlt = fabsf(m[j] - mref) - fabsf(g[j] - gref);
+                acc_c += active ? dlt * dlt : 0.0f;
+                const float own = 2.0f * dlt * sgnf(m[j] - mref);
+                out[j] += k_cont * own;
+                tsum -= own;                                          // what this pixel contributes to its reference pixel
+            }
+        }
+        if (p.contour > 0.0f) {
+            tsum += __shfl_xor_sync(FULL, tsum, 1);
+            tsum += __shfl_xor_sync(FULL, tsum, 2);
+            if (r == 0) out[0] += k_cont * tsum;
+        }
+        if (active) store4<true>(gs + pix0, 4, out);
+    } else {
+        const int32_t* refrow = p.tab;
+        const int32_t* rowlo = p.tab + H;
+        const int32_t* rowhi = p.tab + 2 * H;
+        const int32_t* refcol = p.tab + 3 * H;
+        const int32_t* collo = p.tab + 3 * H + W;
+        const int32_t* colhi = p.tab + 3 * H + 2 * W;
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < H * W) {
+            const float gm = gmask[i], m = alpha[i];
+            float g = (gup ? gup[i] : 0.0f) - k_iou * (gm * De - Nb * (1.0f - gm)) * inv_de2;
+            if (p.contour > 0.0f) {
+                const int iy = i / W, ix = i - iy * W;
+                const size_t rp = (size_t)refrow[iy] * W + refcol[ix];
+                const float mref = alpha[rp], gref = gmask[rp];
+                const float dlt = fabsf(m - mref) - fabsf(gm - gref);
+                acc_c += dlt * dlt;
+                float gc = 2.0f * dlt * sgnf(m - mref);
+                for (int yy = rowlo[iy]; yy < rowhi[iy]; ++yy)
+                    for (int xx = collo[ix]; xx < colhi[ix]; ++xx) {
+                        const size_t q = (size_t)yy * W + xx;
+                        const float mq = alpha[q], gq = gmask[q];
+                        const float dq = fabsf(mq - m) - fabsf(gq - gm);
+                        gc -= 2.0f * dq * sgnf(mq - m);
+                    }
+                g += k_cont * gc;
+            }
+            gs[i] = g;
+        }
+    }
+    if (p.contour > 0.0f) {
+        const float sc = warp_sum(acc_c);
+        if ((threadIdx.x & 31) == 0 && sc != 0.0f) fx_add(p.img_bwd + b * 12, sc, MM_FX_LOSS);
+    }
+}
+
+}  // namespace
+
+void mm_launch_shade_fused(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
+{
+    const int ntiles = ((p.W + FT_W - 1) / FT_W) * ((p.H + FT_H - 1) / FT_H);
+    const dim3 grid((ntiles + FUSED_WARPS - 1) / FUSED_WARPS, p.B);
+    (void)c;
+    if ((p.W & 3) == 0) k_shade_fused<true><<<grid, 32 * FUSED_WARPS, 0, s>>>(p);
+    else                k_shade_fused<false><<<grid, 32 * FUSED_WARPS, 0, s>>>(p);
+}
+
+void mm_launch_gsoft(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
+{
+    (void)c;
+    if ((p.W & 3) == 0 && (p.H & 3) == 0) {
+        const int threads = (p.H >> 2) * (p.W >> 2) * 4;
+        k_gsoft<true><<<dim3((threads + 127) / 128, p.B), 128, 0, s>>>(p);
+    } else {
+        k_gsoft<false><<<dim3((p.H * p.W + 127) / 128, p.B), 128, 0, s>>>(p);
+    }
+}

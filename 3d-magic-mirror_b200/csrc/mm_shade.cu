@@ -73,7 +73,7 @@ k_shade_fwd(const mm_raster_params p)
                 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     const TexFetch t = tex_fetch(tb + (size_t)ch * p.Ht * p.Wt, bl, p.Ht, p.Wt);
-                    tcol[ch] = t.nw * bl.nw + t.ne * bl.ne + t.sw * bl.sw + t.se * bl.se;
+                    tcol[ch] = tex_blend(t, bl);
                 }
             }
             float bnd[9];
@@ -82,14 +82,8 @@ k_shade_fwd(const mm_raster_params p)
             float img[3];
             #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                float v;
-                if (p.no_mask) {
-                    const float bgc = __ldg(p.bg + ((size_t)b * 3 + ch) * HW + pix);
-                    v = (tcol[ch] * tm + bgc * (1.0f - tm)) * coef;
-                } else {
-                    v = tcol[ch] * tm * coef + (1.0f - tm);
-                }
-                img[ch] = clamp01(v);
+                const float bgc = p.no_mask ? __ldg(p.bg + ((size_t)b * 3 + ch) * HW + pix) : 0.0f;
+                img[ch] = clamp01(composite_pre(p.no_mask, tcol[ch], tm, bgc, coef));
             }
             float* out = p.rgba + (size_t)b * 4 * HW + pix;
             out[0] = img[0]; out[HW] = img[1]; out[2 * HW] = img[2]; out[3 * HW] = soft;
@@ -243,7 +237,7 @@ k_shade_bwd(const mm_raster_params p)
                 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     tf[ch] = tex_fetch(tb + (size_t)ch * p.Ht * p.Wt, bl, p.Ht, p.Wt);
-                    tcol[ch] = tf[ch].nw * bl.nw + tf[ch].ne * bl.ne + tf[ch].sw * bl.sw + tf[ch].se * bl.se;
+                    tcol[ch] = tex_blend(tf[ch], bl);
                 }
             }
             float bnd[9];
@@ -252,13 +246,8 @@ k_shade_bwd(const mm_raster_params p)
             float g_coef = 0.0f, g_tcol[3];
             #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                float pre, bgc = 0.0f;
-                if (p.no_mask) {
-                    bgc = __ldg(p.bg + ((size_t)b * 3 + ch) * HW + pix);
-                    pre = (tcol[ch] * tm + bgc * (1.0f - tm)) * coef;
-                } else {
-                    pre = tcol[ch] * tm * coef + (1.0f - tm);
-                }
+                const float bgc = p.no_mask ? __ldg(p.bg + ((size_t)b * 3 + ch) * HW + pix) : 0.0f;
+                const float pre = composite_pre(p.no_mask, tcol[ch], tm, bgc, coef);
                 const float g = (pre >= 0.0f && pre <= 1.0f) ? g_img[ch] : 0.0f;     // torch.clamp backward
                 g_tcol[ch] = g * tm * coef;
                 if (p.no_mask) {

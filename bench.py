@@ -25,7 +25,10 @@ UNIT = "images/s"
 B_PER_GPU = 48
 IMAGE_SIZE = 128
 NSETS = 4                     # rotating input/output sets: 4 x ~137 MB > 126 MB L2, so every step starts L2-cold
-KERNELS = ["vertex_fwd", "geom_fwd", "shade_fwd", "shade_bwd", "geom_bwd", "vertex_bwd", "loss_finalize"]
+# intervals between the CUDA events the library records around its launches (mm_ctx_set_timing)
+KERNELS = ["vertex_fwd", "geom_fwd", "shade_fused", "gsoft", "geom_bwd", "vertex_bwd", "loss_finalize"]
+LAUNCHES_PER_STEP = 11       # k_vertex_fwd, k_scatter<hard>, k_scatter<soft>, k_soft_ovf<fwd>, k_shade_fused, k_gsoft, k_soft_bwd_list,
+                             # k_scatter<soft bwd fallback>, k_soft_ovf<bwd>, k_vertex_bwd, k_loss_finalize (+ memset nodes, not counted)
 
 
 def algorithmic_bytes(B, V, F, H, W, Ht, Wt, bg=True, extra=False):
@@ -403,14 +406,14 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         roof = {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": None}
         if kms:
-            # the per-pixel stage is two launches per direction (geometry + shading); SURVEY 8(d) counts bytes per
-            # direction, so the roofline is taken over the slower direction's pair of launches
-            t_fwd, t_bwd = kms["geom_fwd"] + kms["shade_fwd"], kms["shade_bwd"] + kms["geom_bwd"]
-            dom = "bwd" if t_bwd >= t_fwd else "fwd"
-            nbytes, t_dom = (bytes_bwd, t_bwd) if dom == "bwd" else (bytes_fwd, t_fwd)
+            # dominant kernel: k_shade_fused (shading forward + loss sums + the whole RGB-side backward).  Its algorithmic
+            # bytes are every image-sized tensor of the step touched once per direction (SURVEY 8(d) minus the V/F-sized
+            # vertex-stage terms): reads tex, bg, gt; writes rgba, g_bg, g_tex.
+            nbytes = bytes_step - B_PER_GPU * 4 * (3 * V + 3 * F + 3 * V + 3 * V + 14 * 3) - F * 36
+            t_dom = kms["shade_fused"]
             ach = nbytes / (t_dom * 1e-3) / 1e9
-            roof.update({"kernel": "k_shade_bwd+k_geom_bwd" if dom == "bwd" else "k_geom_fwd+k_shade_fwd", "achieved": ach,
-                         "frac": ach / peak, "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": t_dom, "kernel_ms": kms})
+            roof.update({"kernel": "k_shade_fused", "achieved": ach, "frac": ach / peak,
+                         "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": t_dom, "kernel_ms": kms})
             try:
                 tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
                 roof["traffic"] = tr.get(roof["kernel"])
@@ -430,7 +433,7 @@ def main():
             "e2e": {"value": units_e / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e_runner.h2d_bytes,
                     "d2h_bytes_per_step": e2e_runner.d2h_bytes, "steps": Ke,
                     "api": "DiffRender.render -> recon_data -> backward; pinned host inputs copied every step on a copy stream (double-buffered)"},
-            "gpu_launches": len(KERNELS) * K,
+            "gpu_launches": LAUNCHES_PER_STEP * K,
             "roofline": roof,
         }
         if world == 1 and not args.no_cpu_baseline:
