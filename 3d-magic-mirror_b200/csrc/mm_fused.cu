@@ -18,7 +18,6 @@ namespace {
 #define FULL 0xffffffffu
 #define FT_W 16           // tile of one warp: 16 x 8 pixels, lane = (ly = lane >> 2, lx = lane & 3), 4 pixels per lane
 #define FT_H 8
-#define FUSED_WARPS 4
 
 __device__ __forceinline__ float warp_sum(float v) {
     #pragma unroll
@@ -48,79 +47,89 @@ __device__ __forceinline__ void store4(float* __restrict__ p, int n, const float
 }
 
 // ---------------------------------------------------------------------------------------------- fused shading
-template <bool VEC>
-__global__ void __launch_bounds__(32 * FUSED_WARPS)
+// A CTA of FUSED_WARPS warps owns a strip of FUSED_WARPS 16x8-pixel tiles.
+//   pass 1 (streaming): every thread handles 4 consecutive pixels as float4 accesses issued up front, shades them AS
+//           BACKGROUND (texmask = 0, normal = 0), accumulates the loss sums and stores the outputs.  Covered pixels are
+//           appended to a shared-memory list.
+//   pass 2 (dense): the CTA's covered pixels, ONE PER LANE whatever their position: shading forward + the whole RGB-side
+//           backward; the pixel's outputs are overwritten with scalar stores.
+// The first version ran the covered path inside the 4-pixel loop of pass 1: 77 % lane utilisation, ~150 registers (8 resident
+// warps per SM) and ~840 dependent warp-instructions per pixel quad at 2 warps per scheduler -- 46 us, latency-bound
+// (profiles/r1_notes.md).  Splitting the passes lets pass 2 run compacted and at a smaller register footprint.
+#ifndef FUSED_WARPS
+#define FUSED_WARPS 4
+#endif
+#ifndef FUSED_MINB
+#define FUSED_MINB 4
+#endif
+#define FUSED_THREADS (32 * FUSED_WARPS)
+#define FUSED_TILE_PX (FT_W * FT_H)
+
+template <bool VEC, bool HAS_GUP>
+__global__ void __launch_bounds__(FUSED_THREADS, FUSED_MINB)
 k_shade_fused(const mm_raster_params p)
 {
     __shared__ float s_lights[16];
-    __shared__ float s_red[FUSED_WARPS][12];
+    __shared__ uint32_t s_list[FUSED_WARPS * FUSED_TILE_PX];      // face << 10 | warp << 7 | lane << 2 | j   (F <= 65535, <= 8 warps)
+    __shared__ int s_count;
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
+    if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
     const int H = p.H, W = p.W;
     const size_t HW = (size_t)H * W;
     const int ntx = (W + FT_W - 1) / FT_W;
-    const int tile = blockIdx.x * FUSED_WARPS + warp;
-    const int ty = tile / ntx, tx = tile - ty * ntx;
-    const int iy = ty * FT_H + (lane >> 2), ix0 = tx * FT_W + (lane & 3) * 4;
-    const int n = (iy < H) ? min(4, W - ix0) : 0;                 // valid pixels of this lane (<= 0: none)
-    const bool active = n > 0;
-    const size_t pix0 = active ? (size_t)iy * W + ix0 : 0;
+    const float k_img = p.loss_scale * p.image_weight / ((float)p.B * 3.0f * (float)HW);
+    float coef_bg;                                                          // sh_coef of a zero normal, same op sequence
+    { float bnd0[9]; sh_bands(0.0f, 0.0f, 0.0f, bnd0); coef_bg = sh_coef(bnd0, s_lights); }
 
     float acc_l1 = 0.0f, acc_n = 0.0f, acc_d = 0.0f, acc_gc = 0.0f;
-    float acc_l[9];
-    #pragma unroll
-    for (int i = 0; i < 9; ++i) acc_l[i] = 0.0f;
-    bool lane_covered = false;
-
-    if (active) {
-        // ---- every streamed input of the 4 pixels, issued up front
-        int face[4];
-        float soft[4];
-        {
-            const unsigned long long* zb = p.zbuf + (size_t)b * HW + pix0;
-            const unsigned long long* la = p.lacc + (size_t)b * HW + pix0;
-            unsigned long long z[4], l[4];
-            if (VEC) {
-                const ulonglong2 z0 = *reinterpret_cast<const ulonglong2*>(zb), z1 = *reinterpret_cast<const ulonglong2*>(zb + 2);
-                const ulonglong2 l0 = *reinterpret_cast<const ulonglong2*>(la), l1 = *reinterpret_cast<const ulonglong2*>(la + 2);
-                z[0] = z0.x; z[1] = z0.y; z[2] = z1.x; z[3] = z1.y;
-                l[0] = l0.x; l[1] = l0.y; l[2] = l1.x; l[3] = l1.y;
-            } else {
+    {
+        const int tile = blockIdx.x * FUSED_WARPS + warp;
+        const int ty = tile / ntx, tx = tile - ty * ntx;
+        const int iy = ty * FT_H + (lane >> 2), ix0 = tx * FT_W + (lane & 3) * 4;
+        const int n = (iy < H) ? min(4, W - ix0) : 0;             // valid pixels of this lane (<= 0: none)
+        const bool active = n > 0;
+        const size_t pix0 = active ? (size_t)iy * W + ix0 : 0;
+        int face[4] = {-1, -1, -1, -1};
+        if (active) {
+            // ---- every streamed input of the 4 pixels, issued up front
+            float soft[4];
+            {
+                const unsigned long long* zb = p.zbuf + (size_t)b * HW + pix0;
+                const unsigned long long* la = p.lacc + (size_t)b * HW + pix0;
+                unsigned long long z[4], l[4];
+                if (VEC) {
+                    const ulonglong2 z0 = *reinterpret_cast<const ulonglong2*>(zb), z1 = *reinterpret_cast<const ulonglong2*>(zb + 2);
+                    const ulonglong2 l0 = *reinterpret_cast<const ulonglong2*>(la), l1 = *reinterpret_cast<const ulonglong2*>(la + 2);
+                    z[0] = z0.x; z[1] = z0.y; z[2] = z1.x; z[3] = z1.y;
+                    l[0] = l0.x; l[1] = l0.y; l[2] = l1.x; l[3] = l1.y;
+                } else {
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) { z[j] = (j < n) ? zb[j] : 0ull; l[j] = (j < n) ? la[j] : 0ull; }
+                }
                 #pragma unroll
-                for (int j = 0; j < 4; ++j) { z[j] = (j < n) ? zb[j] : 0ull; l[j] = (j < n) ? la[j] : 0ull; }
+                for (int j = 0; j < 4; ++j) {
+                    face[j] = (j < n) ? key_face(z[j]) : -1;
+                    soft[j] = (face[j] >= 0) ? 1.0f : lacc_soft(l[j]);
+                }
             }
+            float bgv[3][4], gtv[4][4], gup[3][4];
+            const float* gtb = p.gt + (size_t)b * 4 * HW + pix0;
+            #pragma unroll
+            for (int ch = 0; ch < 4; ++ch) load4<VEC>(gtb + ch * HW, n, gtv[ch]);
+            #pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                if (p.no_mask) load4<VEC>(p.bg + ((size_t)b * 3 + ch) * HW + pix0, n, bgv[ch]);
+                else { bgv[ch][0] = bgv[ch][1] = bgv[ch][2] = bgv[ch][3] = 0.0f; }
+                if (HAS_GUP) load4<VEC>(p.g_rgba + ((size_t)b * 4 + ch) * HW + pix0, n, gup[ch]);
+                else { gup[ch][0] = gup[ch][1] = gup[ch][2] = gup[ch][3] = 0.0f; }
+            }
+            float img[3][4], gbg[3][4];
             #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                face[j] = (j < n) ? key_face(z[j]) : -1;
-                soft[j] = (face[j] >= 0) ? 1.0f : lacc_soft(l[j]);
-            }
-        }
-        float bgv[3][4], gtv[4][4], gup[3][4];
-        const float* gtb = p.gt + (size_t)b * 4 * HW + pix0;
-        #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) load4<VEC>(gtb + ch * HW, n, gtv[ch]);
-        #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            if (p.no_mask) load4<VEC>(p.bg + ((size_t)b * 3 + ch) * HW + pix0, n, bgv[ch]);
-            else { bgv[ch][0] = bgv[ch][1] = bgv[ch][2] = bgv[ch][3] = 0.0f; }
-            if (p.g_rgba) load4<VEC>(p.g_rgba + ((size_t)b * 4 + ch) * HW + pix0, n, gup[ch]);
-            else { gup[ch][0] = gup[ch][1] = gup[ch][2] = gup[ch][3] = 0.0f; }
-        }
-        const float k_img = p.loss_scale * p.image_weight / ((float)p.B * 3.0f * (float)HW);
-        const float* rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
-        const float* tb = p.tex + (size_t)b * 3 * p.Ht * p.Wt;
-        float* gacc = p.gfacc + (size_t)b * p.F * 9;
-        float* gtex = p.g_tex + (size_t)b * 3 * p.Ht * p.Wt;
-        float img[3][4], gbg[3][4];
-        float coef_bg;                                                          // sh_coef of a zero normal, same op sequence
-        { float bnd0[9]; sh_bands(0.0f, 0.0f, 0.0f, bnd0); coef_bg = sh_coef(bnd0, s_lights); }
-
-        #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float gm = gtv[3][j];
-            if (face[j] < 0) {
-                // ---- background pixel: texmask = 0, normal = 0 (networks.py:307-314 with texmask 0)
+                const float gm = gtv[3][j];
+                const bool is_bg = face[j] < 0;
                 float g_coef = 0.0f;
                 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
@@ -129,167 +138,194 @@ k_shade_fused(const mm_raster_params p)
                     const float v = clamp01(pre);
                     img[ch][j] = v;
                     const float lt = l1_term(v, gtv[ch][j], gm);
-                    acc_l1 += fabsf(lt);
+                    if (is_bg) acc_l1 += fabsf(lt);
                     float g = gup[ch][j] + k_img * sgnf(lt) * gm;
                     g = (pre >= 0.0f && pre <= 1.0f) ? g : 0.0f;
                     gbg[ch][j] = g * coef_bg;
                     if (p.no_mask) g_coef += g * bgv[ch][j];
                 }
-                if (j < n) acc_gc += g_coef;
-            } else {
-                // ---- covered pixel: shading forward + the whole RGB-side backward
-                lane_covered = true;
-                const int f = face[j];
-                const FaceRec r = load_rec(rec, f);
-                Bary bar;
-                bary_eval(r, pix_x(ix0 + j, W, p.sx), pix_y(iy, H, p.sy), p.eps, bar);
-                float uv[6];
-                const float* uvp = p.face_uvs + f * 6;
-                #pragma unroll
-                for (int i = 0; i < 6; ++i) uv[i] = __ldg(uvp + i);
-                const float u = interp3(bar.w0, bar.w1, bar.w2, uv[0], uv[2], uv[4]);
-                const float v = interp3(bar.w0, bar.w1, bar.w2, uv[1], uv[3], uv[5]);
-                const float tm = ADD(ADD(bar.w0, bar.w1), bar.w2);
-                const float nx = interp3(bar.w0, bar.w1, bar.w2, r.nx, r.nx, r.nx);
-                const float ny = interp3(bar.w0, bar.w1, bar.w2, r.ny, r.ny, r.ny);
-                const float nz = interp3(bar.w0, bar.w1, bar.w2, r.nz, r.nz, r.nz);
-                Bilin bl;
-                bilin_setup(u, v, p.Ht, p.Wt, bl);
-                TexFetch tf[3];
-                float tcol[3];
-                #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    tf[ch] = tex_fetch(tb + (size_t)ch * p.Ht * p.Wt, bl, p.Ht, p.Wt);
-                    tcol[ch] = tex_blend(tf[ch], bl);
-                }
-                float bnd[9];
-                sh_bands(nx, ny, nz, bnd);
-                const float coef = sh_coef(bnd, s_lights);
-                float g_coef = 0.0f, g_tcol[3];
-                #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float pre = composite_pre(p.no_mask, tcol[ch], tm, bgv[ch][j], coef);
-                    const float val = clamp01(pre);
-                    img[ch][j] = val;
-                    const float lt = l1_term(val, gtv[ch][j], gm);
-                    acc_l1 += fabsf(lt);
-                    float g = gup[ch][j] + k_img * sgnf(lt) * gm;
-                    g = (pre >= 0.0f && pre <= 1.0f) ? g : 0.0f;                     // torch.clamp backward
-                    g_tcol[ch] = g * tm * coef;
-                    gbg[ch][j] = g * (1.0f - tm) * coef;
-                    g_coef += p.no_mask ? g * (tcol[ch] * tm + bgv[ch][j] * (1.0f - tm)) : g * (tcol[ch] * tm);
-                }
-                #pragma unroll
-                for (int i = 0; i < 9; ++i) acc_l[i] += g_coef * bnd[i];
-
-                // texture gradient + d/d(u,v)
-                float gix = 0.0f, giy = 0.0f;
-                const bool xe = (bl.ix + 1) < p.Wt, ys = (bl.iy + 1) < p.Ht;
-                const float txf = bl.x - (float)bl.ix, tyf = bl.y - (float)bl.iy;
-                #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float g = g_tcol[ch];
-                    if (g != 0.0f) {
-                        float* gp = gtex + ((size_t)ch * p.Ht + bl.iy) * p.Wt + bl.ix;
-                        atomicAdd(gp, g * bl.nw);
-                        if (xe) atomicAdd(gp + 1, g * bl.ne);
-                        if (ys) atomicAdd(gp + p.Wt, g * bl.sw);
-                        if (xe && ys) atomicAdd(gp + p.Wt + 1, g * bl.se);
-                        gix += g * ((tf[ch].ne - tf[ch].nw) * (1.0f - tyf) + (tf[ch].se - tf[ch].sw) * tyf);
-                        giy += g * ((tf[ch].sw - tf[ch].nw) * (1.0f - txf) + (tf[ch].se - tf[ch].ne) * txf);
-                    }
-                }
-                const float g_gx = bl.in_x ? gix * ((float)p.Wt * 0.5f) : 0.0f;
-                const float g_gy = bl.in_y ? giy * ((float)p.Ht * 0.5f) : 0.0f;
-                const float g_u = 2.0f * g_gx, g_v = -2.0f * g_gy;
-
-                // d coef / d normal -> unit face normal (the three corners carry the same normal)
-                const float* l = s_lights;
-                const float dcx = l[1] * SH_C1 + l[4] * SH_C2 * ny + l[7] * SH_C4 * nz + l[8] * SH_C5 * 2.0f * nx;
-                const float dcy = l[3] * SH_C1 + l[4] * SH_C2 * nx + l[5] * SH_C2 * nz - l[8] * SH_C5 * 2.0f * ny;
-                const float dcz = l[2] * SH_C1 + l[5] * SH_C2 * ny + l[6] * SH_C3 * 2.0f * nz + l[7] * SH_C4 * nx;
-                float* ga = gacc + (size_t)f * 9;
-                const float gn_scale = g_coef * tm;
-                if (gn_scale != 0.0f) {
-                    atomicAdd(ga + 6, gn_scale * dcx);
-                    atomicAdd(ga + 7, gn_scale * dcy);
-                    atomicAdd(ga + 8, gn_scale * dcz);
-                }
-                // hard rasteriser backward (DIBR_SPEC A.3) for the u,v channels
-                if (g_u != 0.0f || g_v != 0.0f) {
-                    const float k1 = bar.k1, k2 = bar.k2, k3 = bar.k3;
-                    const float m = bar.m, pp = bar.p, nn = bar.n, q = bar.q, s = bar.s, t = bar.t;
-                    const float dw1dm = SUB(MUL(0.0f, k3), MUL(q, k1)),   dw1dn = SUB(MUL(-t, k3), MUL(-pp, k1));
-                    const float dw1dp = SUB(MUL(0.0f, k3), MUL(-nn, k1)), dw1dq = SUB(MUL(s, k3), MUL(m, k1));
-                    const float dw1ds = SUB(MUL(q, k3), MUL(0.0f, k1)),   dw1dt = SUB(MUL(-nn, k3), MUL(0.0f, k1));
-                    const float dw2dm = SUB(MUL(t, k3), MUL(q, k2)),      dw2dn = SUB(MUL(0.0f, k3), MUL(-pp, k2));
-                    const float dw2dp = SUB(MUL(-s, k3), MUL(-nn, k2)),   dw2dq = SUB(MUL(0.0f, k3), MUL(m, k2));
-                    const float dw2ds = SUB(MUL(-pp, k3), MUL(0.0f, k2)), dw2dt = SUB(MUL(m, k3), MUL(0.0f, k2));
-                    const float dw1dax = -ADD(ADD(dw1dm, dw1dn), dw1ds), dw1day = -ADD(ADD(dw1dp, dw1dq), dw1dt);
-                    const float dw2dax = -ADD(ADD(dw2dm, dw2dn), dw2ds), dw2day = -ADD(ADD(dw2dp, dw2dq), dw2dt);
-                    const float den = ADD(MUL(k3, k3), p.eps);
-                    float gv[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-                    #pragma unroll
-                    for (int d = 0; d < 2; ++d) {
-                        const float gd = d == 0 ? g_u : g_v;
-                        const float c0 = uv[d], c1 = uv[2 + d], c2 = uv[4 + d];
-                        const float e1 = SUB(c1, c0), e2 = SUB(c2, c0);
-                        const float dldI = DIV(MUL(p.multiplier, gd), den);
-                        gv[0] += MUL(dldI, ADD(MUL(e1, dw1dax), MUL(e2, dw2dax)));
-                        gv[1] += MUL(dldI, ADD(MUL(e1, dw1day), MUL(e2, dw2day)));
-                        gv[2] += MUL(dldI, ADD(MUL(e1, dw1dm), MUL(e2, dw2dm)));
-                        gv[3] += MUL(dldI, ADD(MUL(e1, dw1dp), MUL(e2, dw2dp)));
-                        gv[4] += MUL(dldI, ADD(MUL(e1, dw1dn), MUL(e2, dw2dn)));
-                        gv[5] += MUL(dldI, ADD(MUL(e1, dw1dq), MUL(e2, dw2dq)));
-                    }
-                    #pragma unroll
-                    for (int i = 0; i < 6; ++i) atomicAdd(ga + i, gv[i]);
+                if (is_bg && j < n) acc_gc += g_coef;
+                if (j < n) {                                   // IoU partial sums (kaolin mask_iou)
+                    const float mul = soft[j] * gm;
+                    acc_n += mul;
+                    acc_d += (soft[j] + gm) - mul;
                 }
             }
-            if (j < n) {                                   // IoU partial sums (kaolin mask_iou)
-                const float mul = soft[j] * gm;
-                acc_n += mul;
-                acc_d += (soft[j] + gm) - mul;
-            }
-        }
-        // ---- outputs, one 16-byte store per plane
-        float* out = p.rgba + (size_t)b * 4 * HW + pix0;
-        #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) store4<VEC>(out + ch * HW, n, img[ch]);
-        store4<VEC>(out + 3 * HW, n, soft);
-        if (p.g_bg) {
+            // ---- outputs, one 16-byte store per plane (covered pixels are overwritten by pass 2)
+            float* out = p.rgba + (size_t)b * 4 * HW + pix0;
             #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) store4<VEC>(p.g_bg + ((size_t)b * 3 + ch) * HW + pix0, n, gbg[ch]);
+            for (int ch = 0; ch < 3; ++ch) store4<VEC>(out + ch * HW, n, img[ch]);
+            store4<VEC>(out + 3 * HW, n, soft);
+            if (p.g_bg) {
+                #pragma unroll
+                for (int ch = 0; ch < 3; ++ch) store4<VEC>(p.g_bg + ((size_t)b * 3 + ch) * HW + pix0, n, gbg[ch]);
+            }
         }
-    }
-
-    // ---- per-image sums: warp shuffle -> shared -> 12 fixed-point integer atomics per CTA (order-independent)
-    const bool warp_covered = __any_sync(FULL, lane_covered);
-    acc_l[0] += acc_gc * SH_C0;                  // background pixels: bands = (C0, 0, .., -C3B, 0, 0)
-    acc_l[6] += acc_gc * (-SH_C3B);
-    float sums[12];
-    sums[0] = warp_sum(acc_l1); sums[1] = warp_sum(acc_n); sums[2] = warp_sum(acc_d);
-    if (warp_covered) {
+        // ---- covered pixels -> shared list (warp-aggregated append, 4 ballots)
         #pragma unroll
-        for (int i = 0; i < 9; ++i) sums[3 + i] = warp_sum(acc_l[i]);
-    } else {
-        #pragma unroll
-        for (int i = 0; i < 9; ++i) sums[3 + i] = 0.0f;
-        sums[3] = warp_sum(acc_l[0]);
-        sums[9] = warp_sum(acc_l[6]);
-    }
-    if (lane == 0) {
-        #pragma unroll
-        for (int i = 0; i < 12; ++i) s_red[warp][i] = sums[i];
+        for (int j = 0; j < 4; ++j) {
+            const bool cov = face[j] >= 0;
+            const uint32_t m = __ballot_sync(FULL, cov);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_count, __popc(m));
+                base = __shfl_sync(FULL, base, 0);
+                if (cov) s_list[base + __popc(m & ((1u << lane) - 1u))] =
+                    ((uint32_t)face[j] << 10) | ((uint32_t)warp << 7) | ((uint32_t)lane << 2) | (uint32_t)j;
+            }
+        }
     }
     __syncthreads();
-    if (threadIdx.x < 12) {
-        float v = 0.0f;
+
+    // ---- pass 2: the CTA's covered pixels, one per lane
+    const int count = s_count;
+    float acc_l[9];
+    #pragma unroll
+    for (int i = 0; i < 9; ++i) acc_l[i] = 0.0f;
+    const float* rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
+    const float* tb = p.tex + (size_t)b * 3 * p.Ht * p.Wt;
+    float* gacc = p.gfacc + (size_t)b * p.F * 9;
+    float* gtex = p.g_tex + (size_t)b * 3 * p.Ht * p.Wt;
+    #pragma unroll 1
+    for (int i = threadIdx.x; i < count; i += FUSED_THREADS) {
+        const uint32_t e = s_list[i];
+        const int f = (int)(e >> 10);
+        const int tile = blockIdx.x * FUSED_WARPS + (int)((e >> 7) & 7u);
+        const int el = (int)((e >> 2) & 31u);
+        const int ty = tile / ntx, tx = tile - ty * ntx;
+        const int iy = ty * FT_H + (el >> 2), ix = tx * FT_W + (el & 3) * 4 + (int)(e & 3u);
+        const size_t pix = (size_t)iy * W + ix;
+        const float* gtb = p.gt + (size_t)b * 4 * HW + pix;
+        const float gm = __ldg(gtb + 3 * HW);
+        float bgj[3], gtj[3], guj[3];
         #pragma unroll
-        for (int w = 0; w < FUSED_WARPS; ++w) v += s_red[w][threadIdx.x];
-        if (v != 0.0f) {
-            if (threadIdx.x < 3) fx_add(p.img_fwd + b * 4 + threadIdx.x, v, MM_FX_LOSS);
-            else                 fx_add(p.img_bwd + b * 12 + 1 + (threadIdx.x - 3), v, MM_FX_GRAD);
+        for (int ch = 0; ch < 3; ++ch) {
+            gtj[ch] = __ldg(gtb + ch * HW);
+            bgj[ch] = p.no_mask ? __ldg(p.bg + ((size_t)b * 3 + ch) * HW + pix) : 0.0f;
+            guj[ch] = HAS_GUP ? __ldg(p.g_rgba + ((size_t)b * 4 + ch) * HW + pix) : 0.0f;
+        }
+        const FaceRec r = load_rec(rec, f);
+        Bary bar;
+        bary_eval(r, pix_x(ix, W, p.sx), pix_y(iy, H, p.sy), p.eps, bar);
+        float uv[6];
+        const float* uvp = p.face_uvs + f * 6;
+        #pragma unroll
+        for (int k = 0; k < 6; ++k) uv[k] = __ldg(uvp + k);
+        const float u = interp3(bar.w0, bar.w1, bar.w2, uv[0], uv[2], uv[4]);
+        const float v = interp3(bar.w0, bar.w1, bar.w2, uv[1], uv[3], uv[5]);
+        const float tm = ADD(ADD(bar.w0, bar.w1), bar.w2);
+        const float nx = interp3(bar.w0, bar.w1, bar.w2, r.nx, r.nx, r.nx);
+        const float ny = interp3(bar.w0, bar.w1, bar.w2, r.ny, r.ny, r.ny);
+        const float nz = interp3(bar.w0, bar.w1, bar.w2, r.nz, r.nz, r.nz);
+        Bilin bl;
+        bilin_setup(u, v, p.Ht, p.Wt, bl);
+        TexFetch tf[3];
+        float tcol[3];
+        #pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            tf[ch] = tex_fetch(tb + (size_t)ch * p.Ht * p.Wt, bl, p.Ht, p.Wt);
+            tcol[ch] = tex_blend(tf[ch], bl);
+        }
+        float bnd[9];
+        sh_bands(nx, ny, nz, bnd);
+        const float coef = sh_coef(bnd, s_lights);
+        float g_coef = 0.0f, g_tcol[3];
+        float* out = p.rgba + (size_t)b * 4 * HW + pix;
+        #pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float pre = composite_pre(p.no_mask, tcol[ch], tm, bgj[ch], coef);
+            const float val = clamp01(pre);
+            out[ch * HW] = val;
+            const float lt = l1_term(val, gtj[ch], gm);
+            acc_l1 += fabsf(lt);
+            float g = guj[ch] + k_img * sgnf(lt) * gm;
+            g = (pre >= 0.0f && pre <= 1.0f) ? g : 0.0f;                     // torch.clamp backward
+            g_tcol[ch] = g * tm * coef;
+            if (p.g_bg) p.g_bg[((size_t)b * 3 + ch) * HW + pix] = g * (1.0f - tm) * coef;
+            g_coef += p.no_mask ? g * (tcol[ch] * tm + bgj[ch] * (1.0f - tm)) : g * (tcol[ch] * tm);
+        }
+        #pragma unroll
+        for (int k = 0; k < 9; ++k) acc_l[k] += g_coef * bnd[k];
+
+        // texture gradient + d/d(u,v)
+        float gix = 0.0f, giy = 0.0f;
+        const bool xe = (bl.ix + 1) < p.Wt, ys = (bl.iy + 1) < p.Ht;
+        const float txf = bl.x - (float)bl.ix, tyf = bl.y - (float)bl.iy;
+        #pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float g = g_tcol[ch];
+            if (g != 0.0f) {
+                float* gp = gtex + ((size_t)ch * p.Ht + bl.iy) * p.Wt + bl.ix;
+                atomicAdd(gp, g * bl.nw);
+                if (xe) atomicAdd(gp + 1, g * bl.ne);
+                if (ys) atomicAdd(gp + p.Wt, g * bl.sw);
+                if (xe && ys) atomicAdd(gp + p.Wt + 1, g * bl.se);
+                gix += g * ((tf[ch].ne - tf[ch].nw) * (1.0f - tyf) + (tf[ch].se - tf[ch].sw) * tyf);
+                giy += g * ((tf[ch].sw - tf[ch].nw) * (1.0f - txf) + (tf[ch].se - tf[ch].ne) * txf);
+            }
+        }
+        const float g_gx = bl.in_x ? gix * ((float)p.Wt * 0.5f) : 0.0f;
+        const float g_gy = bl.in_y ? giy * ((float)p.Ht * 0.5f) : 0.0f;
+        const float g_u = 2.0f * g_gx, g_v = -2.0f * g_gy;
+
+        // d coef / d normal -> unit face normal (the three corners carry the same normal)
+        const float* l = s_lights;
+        const float dcx = l[1] * SH_C1 + l[4] * SH_C2 * ny + l[7] * SH_C4 * nz + l[8] * SH_C5 * 2.0f * nx;
+        const float dcy = l[3] * SH_C1 + l[4] * SH_C2 * nx + l[5] * SH_C2 * nz - l[8] * SH_C5 * 2.0f * ny;
+        const float dcz = l[2] * SH_C1 + l[5] * SH_C2 * ny + l[6] * SH_C3 * 2.0f * nz + l[7] * SH_C4 * nx;
+        float* ga = gacc + (size_t)f * 9;
+        const float gn_scale = g_coef * tm;
+        if (gn_scale != 0.0f) {
+            atomicAdd(ga + 6, gn_scale * dcx);
+            atomicAdd(ga + 7, gn_scale * dcy);
+            atomicAdd(ga + 8, gn_scale * dcz);
+        }
+        // hard rasteriser backward (DIBR_SPEC A.3) for the u,v channels
+        if (g_u != 0.0f || g_v != 0.0f) {
+            const float k1 = bar.k1, k2 = bar.k2, k3 = bar.k3;
+            const float m = bar.m, pp = bar.p, nn = bar.n, q = bar.q, sb = bar.s, t = bar.t;
+            const float dw1dm = SUB(MUL(0.0f, k3), MUL(q, k1)),   dw1dn = SUB(MUL(-t, k3), MUL(-pp, k1));
+            const float dw1dp = SUB(MUL(0.0f, k3), MUL(-nn, k1)), dw1dq = SUB(MUL(sb, k3), MUL(m, k1));
+            const float dw1ds = SUB(MUL(q, k3), MUL(0.0f, k1)),   dw1dt = SUB(MUL(-nn, k3), MUL(0.0f, k1));
+            const float dw2dm = SUB(MUL(t, k3), MUL(q, k2)),      dw2dn = SUB(MUL(0.0f, k3), MUL(-pp, k2));
+            const float dw2dp = SUB(MUL(-sb, k3), MUL(-nn, k2)),  dw2dq = SUB(MUL(0.0f, k3), MUL(m, k2));
+            const float dw2ds = SUB(MUL(-pp, k3), MUL(0.0f, k2)), dw2dt = SUB(MUL(m, k3), MUL(0.0f, k2));
+            const float dw1dax = -ADD(ADD(dw1dm, dw1dn), dw1ds), dw1day = -ADD(ADD(dw1dp, dw1dq), dw1dt);
+            const float dw2dax = -ADD(ADD(dw2dm, dw2dn), dw2ds), dw2day = -ADD(ADD(dw2dp, dw2dq), dw2dt);
+            const float den = ADD(MUL(k3, k3), p.eps);
+            float gv[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            #pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const float gd = d == 0 ? g_u : g_v;
+                const float c0 = uv[d], c1 = uv[2 + d], c2 = uv[4 + d];
+                const float e1 = SUB(c1, c0), e2 = SUB(c2, c0);
+                const float dldI = DIV(MUL(p.multiplier, gd), den);
+                gv[0] += MUL(dldI, ADD(MUL(e1, dw1dax), MUL(e2, dw2dax)));
+                gv[1] += MUL(dldI, ADD(MUL(e1, dw1day), MUL(e2, dw2day)));
+                gv[2] += MUL(dldI, ADD(MUL(e1, dw1dm), MUL(e2, dw2dm)));
+                gv[3] += MUL(dldI, ADD(MUL(e1, dw1dp), MUL(e2, dw2dp)));
+                gv[4] += MUL(dldI, ADD(MUL(e1, dw1dn), MUL(e2, dw2dn)));
+                gv[5] += MUL(dldI, ADD(MUL(e1, dw1dq), MUL(e2, dw2dq)));
+            }
+            #pragma unroll
+            for (int k = 0; k < 6; ++k) atomicAdd(ga + k, gv[k]);
+        }
+    }
+
+    // ---- per-image sums: warp shuffle -> fixed-point integer atomics (order-independent, hence deterministic)
+    acc_l[0] += acc_gc * SH_C0;                  // background pixels: bands = (C0, 0, .., -C3B, 0, 0)
+    acc_l[6] += acc_gc * (-SH_C3B);
+    const float s0 = warp_sum(acc_l1), s1 = warp_sum(acc_n), s2 = warp_sum(acc_d);
+    if (lane == 0) {
+        if (s0 != 0.0f) fx_add(p.img_fwd + b * 4 + 0, s0, MM_FX_LOSS);
+        if (s1 != 0.0f) fx_add(p.img_fwd + b * 4 + 1, s1, MM_FX_LOSS);
+        if (s2 != 0.0f) fx_add(p.img_fwd + b * 4 + 2, s2, MM_FX_LOSS);
+    }
+    #pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        if (count > 0 || i == 0 || i == 6) {                // background strip: only bands 0 and 6 are non-zero
+            const float si = warp_sum(acc_l[i]);
+            if (lane == 0 && si != 0.0f) fx_add(p.img_bwd + b * 12 + 1 + i, si, MM_FX_GRAD);
         }
     }
 }
@@ -391,8 +427,9 @@ void mm_launch_shade_fused(const mm_ctx* c, const mm_raster_params& p, cudaStrea
     const int ntiles = ((p.W + FT_W - 1) / FT_W) * ((p.H + FT_H - 1) / FT_H);
     const dim3 grid((ntiles + FUSED_WARPS - 1) / FUSED_WARPS, p.B);
     (void)c;
-    if ((p.W & 3) == 0) k_shade_fused<true><<<grid, 32 * FUSED_WARPS, 0, s>>>(p);
-    else                k_shade_fused<false><<<grid, 32 * FUSED_WARPS, 0, s>>>(p);
+    const bool vec = (p.W & 3) == 0, gup = p.g_rgba != nullptr;
+    if (vec) { if (gup) k_shade_fused<true, true><<<grid, FUSED_THREADS, 0, s>>>(p); else k_shade_fused<true, false><<<grid, FUSED_THREADS, 0, s>>>(p); }
+    else     { if (gup) k_shade_fused<false, true><<<grid, FUSED_THREADS, 0, s>>>(p); else k_shade_fused<false, false><<<grid, FUSED_THREADS, 0, s>>>(p); }
 }
 
 void mm_launch_gsoft(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
