@@ -68,6 +68,7 @@ void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int no_mask, mm_raster_
     p.nstx = c->nstx; p.nsty = c->nsty; p.nst = c->nst; p.nwords = c->nwords; p.knum = c->knum;
     p.sx = c->sx; p.sy = c->sy; p.blen = c->blen; p.multiplier = c->multiplier; p.eps = c->eps; p.sigmainv = c->sigmainv;
     p.no_mask = no_mask;
+    p.covw = (c->W + 31) / 32;
     p.face_uvs = c->d_face_uvs;
     p.tab = c->d_tab;
     p.prof = c->d_prof;
@@ -76,6 +77,7 @@ void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int no_mask, mm_raster_
 void set_ws(const mm_ws_layout& L, char* ws, mm_raster_params& p) {
     p.frec = (const float*)(ws + L.frec);
     p.zbuf = (unsigned long long*)(ws + L.zbuf); p.lacc = (unsigned long long*)(ws + L.lacc);
+    p.cov = (uint32_t*)(ws + L.cov);
     p.ovf_list = (uint32_t*)(ws + L.ovf_list); p.ovf_count = (uint32_t*)(ws + L.ovf_count);
     p.gsoft = (float*)(ws + L.gsoft);
     p.plist = (unsigned long long*)(ws + L.plist); p.plist_cap = (uint32_t)((L.gsoft - L.plist) / 8);

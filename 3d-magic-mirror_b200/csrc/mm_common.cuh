@@ -13,6 +13,8 @@
 //                          contiguous block per image so a CTA stages it with ONE
 //                          cp.async.bulk (TMA bulk copy) into shared memory.
 //     zbuf       [B,H,W] u64  visibility buffer: (order-preserving depth << 32 | ~face), atomicMax-resolved; 0 = uncovered
+//     cov        [B,H,ceil(W/32)] u32 coverage bitmap written by the hard pass (atomicOr): the soft pass finds the UNCOVERED
+//                             pixels of a face's enlarged bbox with one word load per row instead of one zbuf load per pixel
 //     lacc       [B,H,W] u64  soft-silhouette accumulator of uncovered pixels: fixed-point sum log(1-p) << 16 | count
 //     ovf_list   [B*H*W] u32  pixels that saw more than knum candidates (ordered re-scan), ovf_count [1] u32
 //     gsoft      [B,H,W]      d(loss)/d(silhouette) per pixel, handed from the shading backward to the geometry backward
@@ -77,7 +79,7 @@ struct mm_ctx {
 };
 
 struct mm_ws_layout {
-    size_t frec, zbuf, lacc, ovf_count, ovf_list, plist, gsoft, vimg, gfacc, part_fwd, part_bwd, img_fwd, img_bwd, tickets, total;
+    size_t frec, zbuf, lacc, cov, ovf_count, ovf_list, plist, gsoft, vimg, gfacc, part_fwd, part_bwd, img_fwd, img_bwd, tickets, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -93,9 +95,10 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     mm_ws_layout L;
     size_t off = 0;
     L.frec = off;     off = mm_align_up(off + (size_t)B * c->F * MM_REC_FLOATS * 4, 256);
-    // zbuf, lacc and ovf_count are contiguous: one memset clears them at the start of every forward
+    // zbuf, lacc, cov and ovf_count are contiguous: one memset clears them at the start of every forward
     L.zbuf = off;     off = mm_align_up(off + (size_t)B * c->H * c->W * 8, 256);
     L.lacc = off;     off = mm_align_up(off + (size_t)B * c->H * c->W * 8, 256);
+    L.cov = off;      off = mm_align_up(off + (size_t)B * c->H * ((c->W + 31) / 32) * 4, 256);
     L.ovf_count = off; off = mm_align_up(off + 16, 256);
     L.ovf_list = off; off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.plist = off;    off = mm_align_up(off + (size_t)2 * B * c->H * c->W * 8, 256);
@@ -122,6 +125,8 @@ struct mm_raster_params {
     const float* frec;       // [B,F,12]
     unsigned long long* zbuf;     // [B,H,W]
     unsigned long long* lacc;     // [B,H,W]
+    uint32_t* cov;           // [B,H,ceil(W/32)] coverage bitmap: bit set = some front face covers the pixel (hard pass, atomicOr)
+    int covw;                // words per bitmap row
     uint32_t* ovf_list;      // [B*H*W]
     uint32_t* ovf_count;     // [4]: {overflow pixels, candidate pairs recorded, -, -}
     unsigned long long* plist;    // [plist_cap]

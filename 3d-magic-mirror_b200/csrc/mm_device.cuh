@@ -50,6 +50,28 @@ __device__ __forceinline__ void bary_eval(const FaceRec& r, float x0, float y0, 
     b.w0 = SUB(SUB(1.0f, b.w1), b.w2);
 }
 
+// bary_eval + the reference's inside test (all three weights >= 0), with the two IEEE divisions skipped when the SIGN
+// of a quotient already decides "outside": for finite k and den of opposite sign, k/den < 0 unless it underflows to -0
+// (which the reference's `w < 0` test would NOT reject) -- the magnitude guards exclude that, so the decision is exact.
+__device__ __forceinline__ bool bary_eval_inside(const FaceRec& r, float x0, float y0, float eps, Bary& b) {
+    b.m = SUB(r.bx, r.ax); b.p = SUB(r.by, r.ay);
+    b.n = SUB(r.cx, r.ax); b.q = SUB(r.cy, r.ay);
+    b.s = SUB(x0, r.ax);   b.t = SUB(y0, r.ay);
+    b.k1 = SUB(MUL(b.s, b.q), MUL(b.n, b.t));
+    b.k2 = SUB(MUL(b.m, b.t), MUL(b.s, b.p));
+    b.k3 = SUB(MUL(b.m, b.q), MUL(b.n, b.p));
+    const float den = ADD(b.k3, eps);
+    const float aden = fabsf(den);
+    if (aden > 1e-18f && aden < 1e18f) {                 // |k| > 1e-18 and |den| < 1e18  =>  |k/den| > 1e-36 > FLT_MIN
+        const float sg = den > 0.0f ? 1.0f : -1.0f;
+        if (b.k1 * sg < -1e-18f || b.k2 * sg < -1e-18f) return false;
+    }
+    b.w1 = DIV(b.k1, den);
+    b.w2 = DIV(b.k2, den);
+    b.w0 = SUB(SUB(1.0f, b.w1), b.w2);
+    return !(b.w0 < 0.0f || b.w1 < 0.0f || b.w2 < 0.0f);
+}
+
 // feature interpolation exactly as the rasteriser writes it: (w0*c0 + w1*c1) + w2*c2, no FMA contraction
 __device__ __forceinline__ float interp3(float w0, float w1, float w2, float c0, float c1, float c2) {
     return ADD(ADD(MUL(w0, c0), MUL(w1, c1)), MUL(w2, c2));

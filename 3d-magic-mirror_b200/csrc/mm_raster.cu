@@ -53,6 +53,26 @@ __device__ __forceinline__ bool pix_range(const mm_raster_params& p, float xl, f
     return r.ix0 <= r.ix1 && r.iy0 <= r.iy1;
 }
 
+// EXACT pixel rectangle of a face's bbox (tight, or enlarged by boxlen: DIBR_SPEC A.4) under the reference's half-open
+// fp32 test  xmin <= px < xmax, ymin <= py < ymax: conservative float->int estimate, then <= 2 correction steps per side
+// with the very comparison the reference uses (pixel centres are monotone in the index, so the exact set is a rectangle).
+__device__ __forceinline__ void exact_rect(const mm_raster_params& p, const FaceRec& r, bool enlarged,
+                                           int& ix0, int& ix1, int& iy0, int& iy1)
+{
+    float xmin = fminf(fminf(r.ax, r.bx), r.cx), xmax = fmaxf(fmaxf(r.ax, r.bx), r.cx);
+    float ymin = fminf(fminf(r.ay, r.by), r.cy), ymax = fmaxf(fmaxf(r.ay, r.by), r.cy);
+    if (enlarged) { xmin = SUB(xmin, p.blen); xmax = ADD(xmax, p.blen); ymin = SUB(ymin, p.blen); ymax = ADD(ymax, p.blen); }
+    PixRange pr;
+    ix0 = 0; ix1 = -1; iy0 = 0; iy1 = -1;
+    if (pix_range(p, xmin, xmax, ymin, ymax, pr)) {
+        ix0 = pr.ix0; ix1 = pr.ix1; iy0 = pr.iy0; iy1 = pr.iy1;
+        while (ix0 <= ix1 && pix_x(ix0, p.W, p.sx) < xmin) ++ix0;
+        while (ix1 >= ix0 && pix_x(ix1, p.W, p.sx) >= xmax) --ix1;
+        while (iy0 <= iy1 && pix_y(iy0, p.H, p.sy) >= ymax) ++iy0;      // y decreases with the row index
+        while (iy1 >= iy0 && pix_y(iy1, p.H, p.sy) < ymin) --iy1;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- the scatter engine
 // A warp owns FPW = 8 consecutive faces.  Set-up (8 lanes): load the record, compute the bbox (tight / enlarged) and
 // turn the half-open fp32 bbox test into an EXACT pixel rectangle (conservative float->int estimate, then <= 2
@@ -140,10 +160,10 @@ __device__ __forceinline__ void eval_pair(const mm_raster_params& p, WarpQ& wq, 
     const FaceRec r = slot_rec(wq, slot);
     if (MODE == MODE_HARD) {
         Bary bb;
-        bary_eval(r, px, py, p.eps, bb);
-        if (bb.w0 < 0.0f || bb.w1 < 0.0f || bb.w2 < 0.0f) return;
+        if (!bary_eval_inside(r, px, py, p.eps, bb)) return;
         const float zz = ADD(ADD(MUL(bb.w0, r.az), MUL(bb.w1, r.bz)), MUL(bb.w2, r.cz));
         atomicMax(p.zbuf + (size_t)b * HW + pix, depth_key(zz, wq.face[slot]));
+        atomicOr(p.cov + ((size_t)b * p.H + iy) * p.covw + (ix >> 5), 1u << (ix & 31));
     } else if (MODE == MODE_SOFT_FWD) {
         int type;
         const float d2 = soft_d2_fast(r, px, py, p.multiplier, type);
@@ -186,16 +206,20 @@ k_scatter(const mm_raster_params p)
     const int lane = threadIdx.x & 31;
     WarpQ& wq = s_wq[threadIdx.x >> 5];
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (p.B * p.F + FPW - 1) / FPW;
     const size_t HW = (size_t)p.H * p.W;
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
     const float inv_mult = 1.0f / p.multiplier;
+    if (gwarp >= nwarps) return;
     if (MODE == MODE_SOFT_BWD && p.ovf_count[1] <= p.plist_cap) return;      // the pair list is complete: k_soft_bwd_list did it
 
     // ---- set-up: lanes 0..7 each own one face of the warp: record -> smem, EXACT pixel rectangle of its bbox
     int npx = 0;
     if (lane < FPW) {
         const int slot = lane;
-        const int fid = gwarp * FPW + slot;
+        // faces are dealt to the warps with a stride of the warp count: a warp's 8 faces come from 8 different images,
+        // so near-camera images (faces ~30x larger) no longer load a few SMs (ncu r1c: busiest SM 1.7x the average)
+        const int fid = slot * nwarps + gwarp;
         int ix0 = 0, ix1 = -1, iy0 = 0, iy1 = -1;
         if (fid < p.B * p.F) {
             const int b = fid / p.F, f = fid - b * p.F;
@@ -203,23 +227,8 @@ k_scatter(const mm_raster_params p)
             wq.rec[0][slot] = r.ax; wq.rec[1][slot] = r.ay; wq.rec[2][slot] = r.bx; wq.rec[3][slot] = r.by;
             wq.rec[4][slot] = r.cx; wq.rec[5][slot] = r.cy; wq.rec[6][slot] = r.az; wq.rec[7][slot] = r.bz;
             wq.rec[8][slot] = r.cz; wq.img[slot] = b; wq.face[slot] = f;
-            if (MODE != MODE_HARD || r.nz >= 0.0f) {                 // DIBR_SPEC A.2: the hard pass sees front faces only
-                float xmin = fminf(fminf(r.ax, r.bx), r.cx), xmax = fmaxf(fmaxf(r.ax, r.bx), r.cx);
-                float ymin = fminf(fminf(r.ay, r.by), r.cy), ymax = fmaxf(fmaxf(r.ay, r.by), r.cy);
-                if (MODE != MODE_HARD) {                             // DIBR_SPEC A.4: bbox enlarged by boxlen
-                    xmin = SUB(xmin, p.blen); xmax = ADD(xmax, p.blen); ymin = SUB(ymin, p.blen); ymax = ADD(ymax, p.blen);
-                }
-                PixRange pr;
-                if (pix_range(p, xmin, xmax, ymin, ymax, pr)) {
-                    // tighten the conservative range to the exact half-open test  xmin <= px < xmax, ymin <= py < ymax
-                    // (pixel centres are monotone in the index, so the exact set is a rectangle; <= 2 steps per side)
-                    ix0 = pr.ix0; ix1 = pr.ix1; iy0 = pr.iy0; iy1 = pr.iy1;
-                    while (ix0 <= ix1 && pix_x(ix0, p.W, p.sx) < xmin) ++ix0;
-                    while (ix1 >= ix0 && pix_x(ix1, p.W, p.sx) >= xmax) --ix1;
-                    while (iy0 <= iy1 && pix_y(iy0, p.H, p.sy) >= ymax) ++iy0;      // y decreases with the row index
-                    while (iy1 >= iy0 && pix_y(iy1, p.H, p.sy) < ymin) --iy1;
-                }
-            }
+            if (MODE != MODE_HARD || r.nz >= 0.0f)                   // DIBR_SPEC A.2: the hard pass sees front faces only
+                exact_rect(p, r, MODE != MODE_HARD, ix0, ix1, iy0, iy1);
         } else { wq.img[slot] = 0; wq.face[slot] = 0; }
         const int w = ix1 - ix0 + 1, h = iy1 - iy0 + 1;
         npx = (w > 0 && h > 0) ? w * h : 0;
@@ -290,12 +299,136 @@ k_scatter(const mm_raster_params p)
         __syncwarp();
         for (int idx = lane; idx < 6 * FPW; idx += 32) {
             const int kk = idx / FPW, sl = idx - kk * FPW;
-            const int fg = gwarp * FPW + sl;
+            const int fg = sl * nwarps + gwarp;
             if (fg < p.B * p.F) {
                 const float v = wq.facc[kk][sl];
                 if (v != 0.0f) atomicAdd(p.gfacc + (size_t)fg * 9 + kk, v);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- soft pass forward
+// The candidates of the soft pass are the UNCOVERED pixels inside a face's enlarged bbox -- for most faces (the interior of
+// the object) there are none.  The pair engine above found that out with one 8-byte zbuf load + ~50 bookkeeping
+// instructions PER BBOX PIXEL (ncu r1c: 65 % of the kernel's 18.8 M warp-instructions).  Here every lane owns one face and
+// walks the rows of its rectangle against the coverage bitmap the hard pass left behind: one 32-bit word per (row, 32-pixel
+// column block) tells which of its pixels are uncovered.  The set bits become queue entries (warp scan + per-lane bit
+// loop); whenever 32 are waiting the whole warp evaluates them, one candidate per lane, exactly as before.
+#define SF_QCAP (1024 + 64)
+
+struct SoftQ {
+    uint32_t q[SF_QCAP];     // pending candidates: slot << 24 | iy << 12 | ix
+    float rec[6][32];        // the warp's 32 faces: image-plane corners
+    int img[32];
+    int face[32];
+};
+
+__device__ __forceinline__ void soft_fwd_eval(const mm_raster_params& p, const SoftQ& wq, uint32_t e, float kz)
+{
+    const int slot = (int)(e >> 24), iy = (int)((e >> 12) & 0xfffu), ix = (int)(e & 0xfffu);
+    const size_t pg = (size_t)wq.img[slot] * p.H * p.W + (size_t)iy * p.W + ix;
+    FaceRec r;
+    r.ax = wq.rec[0][slot]; r.ay = wq.rec[1][slot]; r.bx = wq.rec[2][slot]; r.by = wq.rec[3][slot];
+    r.cx = wq.rec[4][slot]; r.cy = wq.rec[5][slot];
+    r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
+    int type;
+    const float d2 = soft_d2_fast(r, pix_x(ix, p.W, p.sx), pix_y(iy, p.H, p.sy), p.multiplier, type);
+    const float prob = soft_prob_fast(d2, kz);
+    const unsigned long long old = atomicAdd(p.lacc + pg, lacc_term(log1pf(-prob)));
+    if (lacc_count(old) == p.knum) {                            // candidate knum+1: the pixel needs the ordered pass
+        const uint32_t s2 = atomicAdd(p.ovf_count, 1u);
+        p.ovf_list[s2] = (uint32_t)pg;
+    }
+}
+
+// append the candidates this warp just evaluated to the global pair list (one atomicAdd per batch); all lanes call it
+__device__ __forceinline__ void soft_fwd_record(const mm_raster_params& p, const SoftQ& wq, uint32_t e, int n, int lane)
+{
+    uint32_t base = 0u;
+    if (lane == 0) base = atomicAdd(p.ovf_count + 1, (uint32_t)n);
+    base = __shfl_sync(FULL, base, 0);
+    if (lane < n && base + (uint32_t)lane < p.plist_cap) {
+        const int slot = (int)(e >> 24);
+        const unsigned long long fg = (unsigned long long)((size_t)wq.img[slot] * p.F + wq.face[slot]);
+        p.plist[base + lane] = (fg << 32) | (unsigned long long)(e & 0xffffffu);
+    }
+}
+
+#define SF_WARPS 4
+__global__ void __launch_bounds__(32 * SF_WARPS)
+k_soft_fwd(const mm_raster_params p)
+{
+    __shared__ SoftQ s_wq[SF_WARPS];
+    const int lane = threadIdx.x & 31;
+    SoftQ& wq = s_wq[threadIdx.x >> 5];
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (p.B * p.F + 31) >> 5;
+    if (gwarp >= nwarps) return;
+    const float kz = p.sigmainv / p.multiplier / p.multiplier;
+
+    // ---- set-up: one face per lane (stride = warp count, so a warp mixes 32 images: balanced whatever the cameras)
+    const int fid = lane * nwarps + gwarp;
+    int ix0 = 0, ix1 = -1, iy0 = 0, iy1 = -1, b = 0;
+    if (fid < p.B * p.F) {
+        b = fid / p.F;
+        const int f = fid - b * p.F;
+        const float4* q4 = reinterpret_cast<const float4*>(p.frec) + (size_t)fid * 3;
+        const float4 c0 = __ldg(q4), c1 = __ldg(q4 + 1);
+        FaceRec r;
+        r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
+        r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
+        wq.rec[0][lane] = r.ax; wq.rec[1][lane] = r.ay; wq.rec[2][lane] = r.bx; wq.rec[3][lane] = r.by;
+        wq.rec[4][lane] = r.cx; wq.rec[5][lane] = r.cy; wq.img[lane] = b; wq.face[lane] = f;
+        exact_rect(p, r, true, ix0, ix1, iy0, iy1);
+    }
+    __syncwarp();
+    // ---- (row, 32-column block) segments of the lane's rectangle, walked row-major; idle lanes have none
+    const int wd0 = ix0 >> 5;
+    const int nwd = (ix1 >= ix0 && iy1 >= iy0) ? (ix1 >> 5) - wd0 + 1 : 0;
+    const int nseg = nwd * (iy1 - iy0 + 1);
+    const uint32_t* covb = p.cov + (size_t)b * p.H * p.covw;
+    int maxseg = nseg;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxseg = max(maxseg, __shfl_xor_sync(FULL, maxseg, o));
+    int qn = 0, row = iy0, wd = wd0;
+    #pragma unroll 1
+    for (int it = 0; it < maxseg; ++it) {
+        uint32_t bits = 0u;
+        if (it < nseg) {
+            const int lo = max(ix0 - (wd << 5), 0), hi = min(ix1 - (wd << 5), 31);         // column range inside this word
+            const uint32_t colmask = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+            bits = ~__ldg(covb + (size_t)row * p.covw + wd) & colmask;                       // uncovered pixels of the segment
+        }
+        if (__any_sync(FULL, bits != 0u)) {
+            // exclusive scan of the per-lane candidate counts -> queue offsets
+            const int c = __popc(bits);
+            int incl = c;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+            int pos = qn + incl - c;
+            const uint32_t hdr = ((uint32_t)lane << 24) | ((uint32_t)row << 12) | (uint32_t)(wd << 5);
+            while (bits) {
+                const int j = __ffs(bits) - 1;
+                bits &= bits - 1u;
+                wq.q[pos++] = hdr + (uint32_t)j;
+            }
+            qn += __shfl_sync(FULL, incl, 31);
+            __syncwarp();
+            while (qn >= 32) {                                   // evaluate from the top of the queue: no shifting
+                qn -= 32;
+                const uint32_t e = wq.q[qn + lane];
+                soft_fwd_eval(p, wq, e, kz);
+                soft_fwd_record(p, wq, e, 32, lane);
+            }
+            __syncwarp();
+        }
+        if (it < nseg) { if (++wd >= wd0 + nwd) { wd = wd0; ++row; } }
+    }
+    if (qn > 0) {
+        const uint32_t e = lane < qn ? wq.q[lane] : 0u;
+        if (lane < qn) soft_fwd_eval(p, wq, e, kz);
+        soft_fwd_record(p, wq, e, qn, lane);
     }
 }
 
@@ -471,7 +604,7 @@ void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t
     const int warps = (p.B * c->F + FPW - 1) / FPW;
     const int grid = (warps + 7) / 8;
     k_scatter<MODE_HARD><<<grid, 256, 0, s>>>(p);
-    k_scatter<MODE_SOFT_FWD><<<grid, 256, 0, s>>>(p);
+    { const int nw = (p.B * c->F + 31) / 32; k_soft_fwd<<<(nw + SF_WARPS - 1) / SF_WARPS, 32 * SF_WARPS, 0, s>>>(p); }
     k_soft_ovf<false><<<c->num_sms * 8, 256, 0, s>>>(p);
 }
 
