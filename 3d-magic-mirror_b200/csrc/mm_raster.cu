@@ -319,9 +319,9 @@ k_scatter(const mm_raster_params p)
 
 struct SoftQ {
     uint32_t q[SF_QCAP];     // pending candidates: slot << 24 | iy << 12 | ix
-    float rec[6][32];        // the warp's 32 faces: image-plane corners
-    int img[32];
-    int face[32];
+    float rec[6][8];         // the warp's 8 faces: image-plane corners
+    int img[8];
+    int face[8];
 };
 
 __device__ __forceinline__ void soft_fwd_eval(const mm_raster_params& p, const SoftQ& wq, uint32_t e, float kz)
@@ -356,6 +356,8 @@ __device__ __forceinline__ void soft_fwd_record(const mm_raster_params& p, const
 }
 
 #define SF_WARPS 4
+#define SF_FPW 8             // faces per warp: 4 lanes share a face and take its (row, column-block) segments round-robin, so the
+                             // dependent chain of bitmap loads per warp is 4x shorter and there are 4x more warps to overlap it
 __global__ void __launch_bounds__(32 * SF_WARPS)
 k_soft_fwd(const mm_raster_params p)
 {
@@ -363,12 +365,13 @@ k_soft_fwd(const mm_raster_params p)
     const int lane = threadIdx.x & 31;
     SoftQ& wq = s_wq[threadIdx.x >> 5];
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (p.B * p.F + 31) >> 5;
+    const int nwarps = (p.B * p.F + SF_FPW - 1) / SF_FPW;
     if (gwarp >= nwarps) return;
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
 
-    // ---- set-up: one face per lane (stride = warp count, so a warp mixes 32 images: balanced whatever the cameras)
-    const int fid = lane * nwarps + gwarp;
+    // ---- set-up: lane = (slot, sub); faces dealt with a stride of the warp count (a warp mixes 8 images: balanced)
+    const int slot = lane >> 2, sub = lane & 3;
+    const int fid = slot * nwarps + gwarp;
     int ix0 = 0, ix1 = -1, iy0 = 0, iy1 = -1, b = 0;
     if (fid < p.B * p.F) {
         b = fid / p.F;
@@ -378,24 +381,31 @@ k_soft_fwd(const mm_raster_params p)
         FaceRec r;
         r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
         r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
-        wq.rec[0][lane] = r.ax; wq.rec[1][lane] = r.ay; wq.rec[2][lane] = r.bx; wq.rec[3][lane] = r.by;
-        wq.rec[4][lane] = r.cx; wq.rec[5][lane] = r.cy; wq.img[lane] = b; wq.face[lane] = f;
+        if (sub == 0) {
+            wq.rec[0][slot] = r.ax; wq.rec[1][slot] = r.ay; wq.rec[2][slot] = r.bx; wq.rec[3][slot] = r.by;
+            wq.rec[4][slot] = r.cx; wq.rec[5][slot] = r.cy; wq.img[slot] = b; wq.face[slot] = f;
+        }
         exact_rect(p, r, true, ix0, ix1, iy0, iy1);
     }
     __syncwarp();
-    // ---- (row, 32-column block) segments of the lane's rectangle, walked row-major; idle lanes have none
+    // ---- (row, 32-column block) segments of the face's rectangle, row-major; this lane takes segments sub, sub+4, ..
     const int wd0 = ix0 >> 5;
     const int nwd = (ix1 >= ix0 && iy1 >= iy0) ? (ix1 >> 5) - wd0 + 1 : 0;
-    const int nseg = nwd * (iy1 - iy0 + 1);
+    const int nseg_face = nwd * (iy1 - iy0 + 1);
+    const int nseg = (nseg_face - sub + 3) >> 2;
     const uint32_t* covb = p.cov + (size_t)b * p.H * p.covw;
     int maxseg = nseg;
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxseg = max(maxseg, __shfl_xor_sync(FULL, maxseg, o));
-    int qn = 0, row = iy0, wd = wd0;
+    int qn = 0;
     #pragma unroll 1
     for (int it = 0; it < maxseg; ++it) {
         uint32_t bits = 0u;
+        int row = 0, wd = 0;
         if (it < nseg) {
+            const int sg = it * 4 + sub;
+            if (nwd == 1) { row = iy0 + sg; wd = wd0; }
+            else { const int rr = sg / nwd; row = iy0 + rr; wd = wd0 + (sg - rr * nwd); }
             const int lo = max(ix0 - (wd << 5), 0), hi = min(ix1 - (wd << 5), 31);         // column range inside this word
             const uint32_t colmask = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
             bits = ~__ldg(covb + (size_t)row * p.covw + wd) & colmask;                       // uncovered pixels of the segment
@@ -407,7 +417,7 @@ k_soft_fwd(const mm_raster_params p)
             #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
             int pos = qn + incl - c;
-            const uint32_t hdr = ((uint32_t)lane << 24) | ((uint32_t)row << 12) | (uint32_t)(wd << 5);
+            const uint32_t hdr = ((uint32_t)slot << 24) | ((uint32_t)row << 12) | (uint32_t)(wd << 5);
             while (bits) {
                 const int j = __ffs(bits) - 1;
                 bits &= bits - 1u;
@@ -423,7 +433,6 @@ k_soft_fwd(const mm_raster_params p)
             }
             __syncwarp();
         }
-        if (it < nseg) { if (++wd >= wd0 + nwd) { wd = wd0; ++row; } }
     }
     if (qn > 0) {
         const uint32_t e = lane < qn ? wq.q[lane] : 0u;
@@ -604,7 +613,7 @@ void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t
     const int warps = (p.B * c->F + FPW - 1) / FPW;
     const int grid = (warps + 7) / 8;
     k_scatter<MODE_HARD><<<grid, 256, 0, s>>>(p);
-    { const int nw = (p.B * c->F + 31) / 32; k_soft_fwd<<<(nw + SF_WARPS - 1) / SF_WARPS, 32 * SF_WARPS, 0, s>>>(p); }
+    { const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW; k_soft_fwd<<<(nw + SF_WARPS - 1) / SF_WARPS, 32 * SF_WARPS, 0, s>>>(p); }
     k_soft_ovf<false><<<c->num_sms * 8, 256, 0, s>>>(p);
 }
 
