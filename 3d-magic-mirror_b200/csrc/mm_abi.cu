@@ -98,6 +98,8 @@ int launch_vertex_fwd(const mm_ctx* c, int B, const mm_ws_layout& L, char* ws, c
 
 }  // namespace
 
+int g_mm_pdl = 1;
+
 extern "C" {
 
 int mm_abi_version(void) { return MM_ABI_VERSION; }
@@ -144,6 +146,7 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     const size_t smem_max = prop.sharedMemPerBlockOptin;
     // vertex stage: CTAs per image (each recomputes the vertex transform and emits 1/nchunks of the face records)
     c->nchunks = 4;
+    if (const char* e = getenv("MM_PDL")) g_mm_pdl = atoi(e) != 0;
     if (const char* e = getenv("MM_VCHUNKS")) { const int v = atoi(e); if (v > 0 && v <= 32) c->nchunks = v; }
     c->chunk_rows = 0;
     c->smem_vertex_fwd = mm_vertex_smem_fwd(c);

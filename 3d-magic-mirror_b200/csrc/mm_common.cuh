@@ -156,6 +156,31 @@ struct mm_raster_params {
     long long* prof;         // debug: [B,NST,8] cycles fwd / bwd, popc(S), popc(H), hard, soft-mark, soft-pairs cycles, #pairs; NULL normally
 };
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// A step is ~11 small dependent kernels; back to back in a stream each dependency costs ~2-3 us of launch latency + drain.
+// With programmatic stream serialization the next kernel's CTAs are scheduled while the previous kernel is still running and
+// park at `griddepcontrol.wait`, which returns once the previous grid has completed and its memory is visible.  EVERY kernel of
+// the library executes mm_pdl_prologue() first, in every thread, before any early return: that keeps the dependency transitive
+// (kernel N+1 waits for N, and N cannot finish before N-1 has) and makes the attribute safe on any launch.
+#ifdef __CUDACC__
+__device__ __forceinline__ void mm_pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                                    Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+extern int g_mm_pdl;          // 1 = launch dependent kernels with programmatic stream serialization (default; MM_PDL=0 disables)
+
 // launchers (defined in the .cu files)
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec,

@@ -69,6 +69,7 @@ template <bool VEC, bool HAS_GUP>
 __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MINB)
 k_shade_fused(const mm_raster_params p)
 {
+    mm_pdl_prologue();
     __shared__ float s_lights[16];
     __shared__ uint32_t s_list[FUSED_WARPS * FUSED_TILE_PX];      // face << 10 | warp << 7 | lane << 2 | j   (F <= 65535, <= 8 warps)
     __shared__ int s_count;
@@ -337,6 +338,7 @@ template <bool FAST4>
 __global__ void __launch_bounds__(128)
 k_gsoft(const mm_raster_params p)
 {
+    mm_pdl_prologue();
     const int b = blockIdx.y;
     const int H = p.H, W = p.W;
     const size_t HW = (size_t)H * W;
@@ -428,8 +430,9 @@ void mm_launch_shade_fused(const mm_ctx* c, const mm_raster_params& p, cudaStrea
     const dim3 grid((ntiles + FUSED_WARPS - 1) / FUSED_WARPS, p.B);
     (void)c;
     const bool vec = (p.W & 3) == 0, gup = p.g_rgba != nullptr;
-    if (vec) { if (gup) k_shade_fused<true, true><<<grid, FUSED_THREADS, 0, s>>>(p); else k_shade_fused<true, false><<<grid, FUSED_THREADS, 0, s>>>(p); }
-    else     { if (gup) k_shade_fused<false, true><<<grid, FUSED_THREADS, 0, s>>>(p); else k_shade_fused<false, false><<<grid, FUSED_THREADS, 0, s>>>(p); }
+    void (*k)(mm_raster_params) = vec ? (gup ? k_shade_fused<true, true> : k_shade_fused<true, false>)
+                                      : (gup ? k_shade_fused<false, true> : k_shade_fused<false, false>);
+    mm_launch(k, grid, dim3(FUSED_THREADS), 0, s, g_mm_pdl != 0, p);
 }
 
 void mm_launch_gsoft(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
@@ -437,8 +440,8 @@ void mm_launch_gsoft(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
     (void)c;
     if ((p.W & 3) == 0 && (p.H & 3) == 0) {
         const int threads = (p.H >> 2) * (p.W >> 2) * 4;
-        k_gsoft<true><<<dim3((threads + 127) / 128, p.B), 128, 0, s>>>(p);
+        mm_launch(k_gsoft<true>, dim3((threads + 127) / 128, p.B), dim3(128), 0, s, g_mm_pdl != 0, p);
     } else {
-        k_gsoft<false><<<dim3((p.H * p.W + 127) / 128, p.B), 128, 0, s>>>(p);
+        mm_launch(k_gsoft<false>, dim3((p.H * p.W + 127) / 128, p.B), dim3(128), 0, s, g_mm_pdl != 0, p);
     }
 }

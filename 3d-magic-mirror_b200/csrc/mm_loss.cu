@@ -11,6 +11,7 @@ k_recon_fwd(int H, int W, int nparts, float contour,
             const float* __restrict__ pred, const float* __restrict__ gt, const int32_t* __restrict__ tab,
             float* __restrict__ part_fwd)
 {
+    mm_pdl_prologue();
     __shared__ float red[MM_WARPS];
     const int b = blockIdx.y, band = blockIdx.x;
     const size_t HW = (size_t)H * W;
@@ -47,6 +48,7 @@ k_recon_bwd(int B, int H, int W, int nparts, float image_weight, float contour, 
             const float* __restrict__ pred, const float* __restrict__ gt, const int32_t* __restrict__ tab,
             const long long* __restrict__ img_fwd, float* __restrict__ g_pred)
 {
+    mm_pdl_prologue();
     const int b = blockIdx.y, band = blockIdx.x;
     const size_t HW = (size_t)H * W;
     const float* pb = pred + (size_t)b * 4 * HW;
@@ -93,6 +95,7 @@ k_recon_bwd(int B, int H, int W, int nparts, float image_weight, float contour, 
 // part_fwd [B][np][4] -> img_fwd [B][4] (fixed point); one warp per image, fixed order
 __global__ void k_image_reduce(int np, const float* __restrict__ part_fwd, long long* __restrict__ img_fwd)
 {
+    mm_pdl_prologue();
     const int b = blockIdx.x, lane = threadIdx.x;
     float a[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     for (int k = lane; k < np; k += 32)
@@ -112,6 +115,7 @@ k_loss_finalize(int B, int H, int W, float image_weight, float contour,
                 const long long* __restrict__ img_fwd, long long* __restrict__ img_bwd,
                 float* __restrict__ loss, float* __restrict__ iou_out)
 {
+    mm_pdl_prologue();
     __shared__ float red[MM_WARPS];
     float a_l1 = 0.0f, a_c = 0.0f, a_iou = 0.0f;
     for (int b = threadIdx.x; b < B; b += MM_THREADS) {
@@ -144,25 +148,25 @@ void mm_launch_recon_fwd(const mm_ctx* c, int B, const float* pred, const float*
                          cudaStream_t s)
 {
     const dim3 grid(c->nparts_recon, B);
-    k_recon_fwd<<<grid, MM_THREADS, 0, s>>>(c->H, c->W, c->nparts_recon, contour, pred, gt, c->d_tab, part_fwd);
+    mm_launch(k_recon_fwd, grid, dim3(MM_THREADS), 0, s, false, c->H, c->W, c->nparts_recon, contour, pred, gt, (const int32_t*)c->d_tab, part_fwd);
 }
 
 void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float* gt, const long long* img_fwd,
                          float image_weight, float contour, float loss_scale, float* g_pred, cudaStream_t s)
 {
     const dim3 grid(c->nparts_recon, B);
-    k_recon_bwd<<<grid, MM_THREADS, 0, s>>>(B, c->H, c->W, c->nparts_recon, image_weight, contour, loss_scale, pred, gt,
-                                            c->d_tab, img_fwd, g_pred);
+    mm_launch(k_recon_bwd, grid, dim3(MM_THREADS), 0, s, g_mm_pdl != 0, B, c->H, c->W, c->nparts_recon, image_weight, contour, loss_scale,
+              pred, gt, (const int32_t*)c->d_tab, img_fwd, g_pred);
 }
 
 void mm_launch_loss_finalize(const mm_ctx* c, int B, const long long* img_fwd, long long* img_bwd,
                              float image_weight, float contour, float* loss, float* iou_out, cudaStream_t s)
 {
-    k_loss_finalize<<<1, MM_THREADS, 0, s>>>(B, c->H, c->W, image_weight, contour, img_fwd, img_bwd, loss, iou_out);
+    mm_launch(k_loss_finalize, dim3(1), dim3(MM_THREADS), 0, s, g_mm_pdl != 0, B, c->H, c->W, image_weight, contour, img_fwd, img_bwd, loss, iou_out);
 }
 
 void mm_launch_image_reduce(const mm_ctx* c, int B, int np, const float* part_fwd, long long* img_fwd, cudaStream_t s)
 {
     (void)c;
-    k_image_reduce<<<B, 32, 0, s>>>(np, part_fwd, img_fwd);
+    mm_launch(k_image_reduce, dim3(B), dim3(32), 0, s, g_mm_pdl != 0, np, part_fwd, img_fwd);
 }

@@ -202,6 +202,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 k_scatter(const mm_raster_params p)
 {
+    mm_pdl_prologue();
     __shared__ WarpQ s_wq[8];
     const int lane = threadIdx.x & 31;
     WarpQ& wq = s_wq[threadIdx.x >> 5];
@@ -361,6 +362,7 @@ __device__ __forceinline__ void soft_fwd_record(const mm_raster_params& p, const
 __global__ void __launch_bounds__(32 * SF_WARPS)
 k_soft_fwd(const mm_raster_params p)
 {
+    mm_pdl_prologue();
     __shared__ SoftQ s_wq[SF_WARPS];
     const int lane = threadIdx.x & 31;
     SoftQ& wq = s_wq[threadIdx.x >> 5];
@@ -446,6 +448,7 @@ k_soft_fwd(const mm_raster_params p)
 __global__ void __launch_bounds__(256)
 k_soft_bwd_list(const mm_raster_params p)
 {
+    mm_pdl_prologue();
     const uint32_t n = p.ovf_count[1];
     if (n > p.plist_cap) return;                                   // list overflowed: the filter-based kernel runs instead
     const int lane = threadIdx.x & 31;
@@ -497,6 +500,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(256)
 k_soft_ovf(const mm_raster_params p)
 {
+    mm_pdl_prologue();
     __shared__ uint32_t s_mask[OVF_MAX_WORDS];
     __shared__ float s_wprod[OVF_MAX_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -612,18 +616,18 @@ void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t
 {
     const int warps = (p.B * c->F + FPW - 1) / FPW;
     const int grid = (warps + 7) / 8;
-    k_scatter<MODE_HARD><<<grid, 256, 0, s>>>(p);
-    { const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW; k_soft_fwd<<<(nw + SF_WARPS - 1) / SF_WARPS, 32 * SF_WARPS, 0, s>>>(p); }
-    k_soft_ovf<false><<<c->num_sms * 8, 256, 0, s>>>(p);
+    mm_launch(k_scatter<MODE_HARD>, dim3(grid), dim3(256), 0, s, g_mm_pdl != 0, p);
+    { const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW; mm_launch(k_soft_fwd, dim3((nw + SF_WARPS - 1) / SF_WARPS), dim3(32 * SF_WARPS), 0, s, g_mm_pdl != 0, p); }
+    mm_launch(k_soft_ovf<false>, dim3(c->num_sms * 8), dim3(256), 0, s, g_mm_pdl != 0, p);
 }
 
 void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
     const int warps = (p.B * c->F + FPW - 1) / FPW;
     const int grid = (warps + 7) / 8;
-    k_soft_bwd_list<<<c->num_sms * 4, 256, 0, s>>>(p);
-    k_scatter<MODE_SOFT_BWD><<<grid, 256, 0, s>>>(p);              // returns immediately unless the pair list overflowed
-    k_soft_ovf<true><<<c->num_sms * 8, 256, 0, s>>>(p);
+    mm_launch(k_soft_bwd_list, dim3(c->num_sms * 4), dim3(256), 0, s, g_mm_pdl != 0, p);
+    mm_launch(k_scatter<MODE_SOFT_BWD>, dim3(grid), dim3(256), 0, s, g_mm_pdl != 0, p);              // returns immediately unless the pair list overflowed
+    mm_launch(k_soft_ovf<true>, dim3(c->num_sms * 8), dim3(256), 0, s, g_mm_pdl != 0, p);
 }
 
 size_t mm_raster_smem_bytes(const mm_ctx* c) { (void)c; return 0; }

@@ -28,6 +28,7 @@ template <bool WITH_LOSS>
 __global__ void __launch_bounds__(32)
 k_shade_fwd(const mm_raster_params p)
 {
+    mm_pdl_prologue();
     __shared__ float s_lights[16];
     const int b = blockIdx.y, lane = threadIdx.x;
     if (lane < 9) s_lights[lane] = p.lights[b * 9 + lane];
@@ -117,6 +118,7 @@ k_shade_fwd(const mm_raster_params p)
 __global__ void __launch_bounds__(32, 28)
 k_shade_bwd(const mm_raster_params p)
 {
+    mm_pdl_prologue();
     __shared__ float s_lights[16];
     const int b = blockIdx.y, lane = threadIdx.x;
     if (lane < 9) s_lights[lane] = p.lights[b * 9 + lane];
@@ -356,12 +358,11 @@ k_shade_bwd(const mm_raster_params p)
 void mm_launch_shade_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_loss, cudaStream_t s)
 {
     const dim3 grid(c->nst, p.B);
-    if (with_loss) k_shade_fwd<true><<<grid, 32, 0, s>>>(p);
-    else           k_shade_fwd<false><<<grid, 32, 0, s>>>(p);
+    mm_launch(with_loss ? k_shade_fwd<true> : k_shade_fwd<false>, grid, dim3(32), 0, s, g_mm_pdl != 0, p);
 }
 
 void mm_launch_shade_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
     const dim3 grid(c->nst, p.B);
-    k_shade_bwd<<<grid, 32, 0, s>>>(p);
+    mm_launch(k_shade_bwd, grid, dim3(32), 0, s, false, p);      // first kernel after the memsets of the backward
 }

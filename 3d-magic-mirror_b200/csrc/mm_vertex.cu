@@ -73,6 +73,7 @@ k_vertex_fwd(const VertexFwdParams q,
              float* __restrict__ frec, float* __restrict__ vimg, float* __restrict__ face_normals,
              float* __restrict__ gfacc_zero, long long* __restrict__ img_fwd, long long* __restrict__ img_bwd)
 {
+    mm_pdl_prologue();
     extern __shared__ float sm[];
     const int V = q.V, F = q.F;
     float* sT = sm;                    // 12
@@ -160,6 +161,7 @@ k_vertex_bwd(int V, int F, float proj_x, float proj_y,
              float* __restrict__ g_vertices, float* __restrict__ g_azim, float* __restrict__ g_elev,
              float* __restrict__ g_dist, float* __restrict__ g_bias, float* __restrict__ g_lights)
 {
+    mm_pdl_prologue();
     extern __shared__ float sm[];
     __shared__ Cam sc;
     __shared__ float red[MM_VTHREADS / 32];
@@ -333,9 +335,9 @@ void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const f
                           float* g_bias, float* g_lights, cudaStream_t s)
 {
     const size_t smem = ((size_t)c->V * 6) * sizeof(float);
-    k_vertex_bwd<<<B, MM_VTHREADS, smem, s>>>(c->V, c->F, c->proj_x, c->proj_y, c->d_faces, vertices, azim, elev,
-                                      dist, bias, gfacc, g_face_normals, img_bwd, reset, g_vertices, g_azim, g_elev,
-                                      g_dist, g_bias, g_lights);
+    mm_launch(k_vertex_bwd, dim3(B), dim3(MM_VTHREADS), smem, s, g_mm_pdl != 0, c->V, c->F, c->proj_x, c->proj_y,
+              (const int32_t*)c->d_faces, vertices, azim, elev, dist, bias, gfacc, g_face_normals, img_bwd, reset, g_vertices,
+              g_azim, g_elev, g_dist, g_bias, g_lights);
 }
 
 void mm_launch_export_faces(const mm_ctx* c, int B, const float* frec, const float* vimg, float* fvi, float* fvz,
