@@ -89,10 +89,16 @@ void set_ws(const mm_ws_layout& L, char* ws, mm_raster_params& p) {
 // vertex stage + the single memset that clears the visibility buffer, the silhouette accumulators and the overflow counter
 int launch_vertex_fwd(const mm_ctx* c, int B, const mm_ws_layout& L, char* ws, const float* vertices, const float* azim,
                       const float* elev, const float* dist, const float* bias, float* face_normals, bool zero_gfacc,
-                      cudaStream_t s) {
-    if (cudaMemsetAsync(ws + L.zbuf, 0, (L.ovf_count + 16) - L.zbuf, s) != cudaSuccess) return 1;
+                      void* clr1, size_t bytes1, cudaStream_t s) {
+    // zbuf .. ovf_count are contiguous and 256-byte aligned: one clear range (16-byte units, tail padded inside the workspace)
+    const size_t bytes0 = mm_align_up((L.ovf_count + 16) - L.zbuf, 16);
+    if (clr1 && (((uintptr_t)clr1 & 15) != 0 || (bytes1 & 15) != 0)) {          // unaligned caller buffer: plain memset
+        if (cudaMemsetAsync(clr1, 0, bytes1, s) != cudaSuccess) return 1;
+        clr1 = nullptr; bytes1 = 0;
+    }
     mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg), face_normals,
-                         zero_gfacc ? (float*)(ws + L.gfacc) : nullptr, (long long*)(ws + L.img_fwd), (long long*)(ws + L.img_bwd), s);
+                         zero_gfacc ? (float*)(ws + L.gfacc) : nullptr, (long long*)(ws + L.img_fwd), (long long*)(ws + L.img_bwd),
+                         ws + L.zbuf, bytes0, clr1, bytes1, s);
     return 0;
 }
 
@@ -145,7 +151,7 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     if (F > 65535) { delete c; return fail(MM_E_UNSUPPORTED, "F=%d exceeds the 16-bit face ids of the soft-pass lists", F); }
     const size_t smem_max = prop.sharedMemPerBlockOptin;
     // vertex stage: CTAs per image (each recomputes the vertex transform and emits 1/nchunks of the face records)
-    c->nchunks = 4;
+    c->nchunks = 8;
     if (const char* e = getenv("MM_PDL")) g_mm_pdl = atoi(e) != 0;
     if (const char* e = getenv("MM_VCHUNKS")) { const int v = atoi(e); if (v > 0 && v <= 32) c->nchunks = v; }
     c->chunk_rows = 0;
@@ -205,7 +211,7 @@ int mm_render_forward(mm_ctx* c, int B, const float* vertices, const float* azim
     cudaStream_t s = (cudaStream_t)stream;
     const mm_ws_layout L = mm_ws_make(c, B);
     char* ws = (char*)workspace;
-    launch_vertex_fwd(c, B, L, ws, vertices, azim, elev, dist, bias, face_normals, false, s);
+    launch_vertex_fwd(c, B, L, ws, vertices, azim, elev, dist, bias, face_normals, false, nullptr, 0, s);
     if (int r = check_launch("vertex_fwd")) return r;
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, no_mask, p);
@@ -249,7 +255,7 @@ int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azi
     mm_launch_geom_bwd(c, p, s);
     if (int r = check_launch("geom_bwd")) return r;
     mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.img_bwd, 1, g_vertices,
-                         g_azim, g_elev, g_dist, g_bias, g_lights, s);
+                         g_azim, g_elev, g_dist, g_bias, g_lights, nullptr, nullptr, 0.0f, 0.0f, s);
     return check_launch("vertex_bwd");
 }
 
@@ -303,10 +309,9 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     const mm_ws_layout L = mm_ws_make(c, B);
     char* ws = (char*)workspace;
     const size_t HW = (size_t)c->H * c->W;
-    MM_CUDA(cudaMemsetAsync(g_tex, 0, (size_t)B * 3 * Ht * Wt * 4, s));
     if (g_bg && !no_mask) MM_CUDA(cudaMemsetAsync(g_bg, 0, (size_t)B * 3 * HW * 4, s));
     if (c->timing) cudaEventRecord(c->ev[0], s);
-    launch_vertex_fwd(c, B, L, ws, vertices, azim, elev, dist, bias, face_normals, true, s);
+    launch_vertex_fwd(c, B, L, ws, vertices, azim, elev, dist, bias, face_normals, true, g_tex, (size_t)B * 3 * Ht * Wt * 4, s);
     if (int r = check_launch("vertex_fwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[1], s);
     mm_raster_params p;
@@ -330,13 +335,11 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     mm_launch_geom_bwd(c, p, s);
     if (int r = check_launch("geom_bwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[5], s);
+    // vertex backward; its last CTA also finalises the loss scalars (img_fwd / img_bwd are re-zeroed by the next vertex_fwd)
     mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, p.gfacc, g_face_normals, p.img_bwd, 0, g_vertices, g_azim,
-                         g_elev, g_dist, g_bias, g_lights, s);
-    if (int r = check_launch("vertex_bwd")) return r;
-    if (c->timing) cudaEventRecord(c->ev[6], s);
-    mm_launch_loss_finalize(c, B, p.img_fwd, p.img_bwd, image_weight, contour, loss, nullptr, s);
-    if (c->timing) cudaEventRecord(c->ev[7], s);
-    return check_launch("loss_finalize");
+                         g_elev, g_dist, g_bias, g_lights, loss, p.img_fwd, image_weight, contour, s);
+    if (c->timing) { cudaEventRecord(c->ev[6], s); cudaEventRecord(c->ev[7], s); }
+    return check_launch("vertex_bwd");
 }
 
 int mm_debug_set_profile_buffer(mm_ctx* c, long long* device_buf) {

@@ -185,11 +185,12 @@ extern int g_mm_pdl;          // 1 = launch dependent kernels with programmatic 
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec,
                           float* vimg, float* face_normals, float* gfacc_zero, long long* img_fwd, long long* img_bwd,
-                          cudaStream_t s);
+                          void* clr0, size_t bytes0, void* clr1, size_t bytes1, cudaStream_t s);
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,
                           long long* img_bwd, int reset, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
-                          float* g_bias, float* g_lights, cudaStream_t s);
+                          float* g_bias, float* g_lights, float* loss, const long long* img_fwd, float image_weight,
+                          float contour, cudaStream_t s);
 void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 void mm_launch_shade_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_loss, cudaStream_t s);

@@ -13,6 +13,7 @@
 // to vertices, azimuth, elevation, distance and bias.
 #include "mm_common.cuh"
 #include <math_constants.h>
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -63,6 +64,12 @@ __device__ inline void transform_vertex(const float* T, float x, float y, float 
 struct VertexFwdParams {
     int V, F, nchunks;
     float proj_x, proj_y, multiplier;
+    // buffers this kernel clears for the rest of the step (16-byte units): visibility buffer + silhouette accumulators +
+    // coverage bitmap + counters, and (fused step) the texture-gradient output.  Folding the clears in here removes two
+    // memset nodes (~31 MB at cfg-2) from the head of the dependency chain: the stores drain while the CTAs do the
+    // latency-bound camera / vertex work.
+    uint4* clr0; size_t n0;
+    uint4* clr1; size_t n1;
 };
 
 __global__ void __launch_bounds__(MM_VTHREADS)
@@ -80,6 +87,13 @@ k_vertex_fwd(const VertexFwdParams q,
     float* svc = sm + 16;              // V*3 camera-space
     float* svi = svc + (size_t)V * 3;  // V*2 image-plane (unscaled)
     const int chunk = blockIdx.x, b = blockIdx.y;
+    {
+        const size_t nthreads = (size_t)gridDim.x * gridDim.y * blockDim.x;
+        const size_t t = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (size_t i = t; i < q.n0; i += nthreads) q.clr0[i] = z;
+        for (size_t i = t; i < q.n1; i += nthreads) q.clr1[i] = z;
+    }
     if (threadIdx.x == 0) {
         Cam c;
         camera_setup(azim[b], elev[b], dist[b], bias[b * 2], bias[b * 2 + 1], c);
@@ -139,36 +153,50 @@ k_vertex_fwd(const VertexFwdParams q,
 }
 
 // ------------------------------------------------------------------ backward
-__device__ inline float block_sum_v(float v, float* red /* >= MM_VTHREADS/32 floats */) {
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float r = 0.0f;
-    #pragma unroll
-    for (int i = 0; i < MM_VTHREADS / 32; ++i) r += red[i];
-    return r;
-}
+// One thread-block CLUSTER of VB_CLUSTER CTAs per image.  Every CTA scatters the per-face gradients of its quarter of the
+// faces into its own shared-memory copy of the per-vertex accumulator; after a cluster barrier each CTA reduces its quarter of
+// the VERTICES across the four copies through distributed shared memory, emits g_vertices and its partial camera sums; rank 0
+// finishes the camera chain.  (The first version was one 512-thread CTA per image: 48 busy SMs and ~26 block barriers, 20 us.)
+// The last CTA of image 0 also finalises the loss scalars of the fused step (was a separate single-CTA launch).
+#define VB_CLUSTER 4
+#define VB_THREADS 256
+#define VB_WARPS (VB_THREADS / 32)
 
-__global__ void __launch_bounds__(MM_VTHREADS)
-k_vertex_bwd(int V, int F, float proj_x, float proj_y,
+struct VertexBwdParams {
+    int B, V, F, H, W;
+    float proj_x, proj_y;
+    int reset;
+    // loss finalisation (fused step only; loss == NULL otherwise)
+    float* loss;
+    const long long* img_fwd;
+    float image_weight, contour;
+};
+
+__device__ __forceinline__ float fxv(const long long* a, double scale) { return (float)((double)(*a) / scale); }
+
+__global__ void __cluster_dims__(VB_CLUSTER, 1, 1) __launch_bounds__(VB_THREADS)
+k_vertex_bwd(const VertexBwdParams q,
              const int32_t* __restrict__ faces, const float* __restrict__ vertices,
              const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
              const float* __restrict__ bias,
              const float* __restrict__ gfacc, const float* __restrict__ g_face_normals,
-             long long* __restrict__ img_bwd, int reset,
+             long long* __restrict__ img_bwd,
              float* __restrict__ g_vertices, float* __restrict__ g_azim, float* __restrict__ g_elev,
              float* __restrict__ g_dist, float* __restrict__ g_bias, float* __restrict__ g_lights)
 {
     mm_pdl_prologue();
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ float sm[];
     __shared__ Cam sc;
-    __shared__ float red[MM_VTHREADS / 32];
-    __shared__ float sacc[12];
+    __shared__ float s_part[VB_WARPS][12];
+    __shared__ float s_cl[VB_CLUSTER][12];          // rank 0's copy collects the partial camera sums of the cluster
+    const int V = q.V, F = q.F;
     float* svc = sm;                      // V*3 camera-space positions
-    float* sgv = sm + (size_t)V * 3;      // V*3 gradient w.r.t. camera-space positions
-    const int b = blockIdx.x;
+    float* sgv = sm + (size_t)V * 3;      // V*3 gradient w.r.t. camera-space positions (this CTA's faces only)
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) camera_setup(azim[b], elev[b], dist[b], bias[b * 2], bias[b * 2 + 1], sc);
     __syncthreads();
     const float* vb = vertices + (size_t)b * V * 3;
@@ -179,7 +207,9 @@ k_vertex_bwd(int V, int F, float proj_x, float proj_y,
         sgv[v * 3] = 0.0f; sgv[v * 3 + 1] = 0.0f; sgv[v * 3 + 2] = 0.0f;
     }
     __syncthreads();
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    const int fper = (F + VB_CLUSTER - 1) / VB_CLUSTER;
+    const int f_end = min(F, (rank + 1) * fper);
+    for (int f = rank * fper + threadIdx.x; f < f_end; f += blockDim.x) {
         const int idx[3] = {faces[f * 3], faces[f * 3 + 1], faces[f * 3 + 2]};
         float P[3][3];
         #pragma unroll
@@ -192,9 +222,9 @@ k_vertex_bwd(int V, int F, float proj_x, float proj_y,
             const float gx = ga[i * 2], gy = ga[i * 2 + 1];
             const float z = P[i][2];
             const float den = z * -1.0f;
-            const float xi = (P[i][0] * proj_x) / den, yi = (P[i][1] * proj_y) / den;
-            G[i][0] += gx * proj_x / den;
-            G[i][1] += gy * proj_y / den;
+            const float xi = (P[i][0] * q.proj_x) / den, yi = (P[i][1] * q.proj_y) / den;
+            G[i][0] += gx * q.proj_x / den;
+            G[i][1] += gy * q.proj_y / den;
             G[i][2] += -(gx * xi + gy * yi) / z;
         }
         // (2) unit normal gradient (raster path + upstream face_normals gradient)
@@ -227,14 +257,22 @@ k_vertex_bwd(int V, int F, float proj_x, float proj_y,
             for (int k2 = 0; k2 < 3; ++k2)
                 if (G[i][k2] != 0.0f) atomicAdd(&sgv[idx[i] * 3 + k2], G[i][k2]);
     }
-    __syncthreads();
-    // (3) vcam = v*R + t : g_v = g_vcam * R^T ; g_R[i][j] = sum v_i g_j ; g_t[j] = sum g_j
+    cluster.sync();
+    // (3) vcam = v*R + t : g_v = g_vcam * R^T ; g_R[i][j] = sum v_i g_j ; g_t[j] = sum g_j.   This CTA's quarter of the
+    // vertices, summed over the cluster's four accumulator copies (distributed shared memory, fixed order)
+    const float* rsgv[VB_CLUSTER];
+    #pragma unroll
+    for (int r = 0; r < VB_CLUSTER; ++r) rsgv[r] = cluster.map_shared_rank(sgv, r);
     float acc[12];
     #pragma unroll
     for (int i = 0; i < 12; ++i) acc[i] = 0.0f;
     float* gvb = g_vertices + (size_t)b * V * 3;
-    for (int v = threadIdx.x; v < V; v += blockDim.x) {
-        const float g0 = sgv[v * 3], g1 = sgv[v * 3 + 1], g2 = sgv[v * 3 + 2];
+    const int vper = (V + VB_CLUSTER - 1) / VB_CLUSTER;
+    const int v_end = min(V, (rank + 1) * vper);
+    for (int v = rank * vper + threadIdx.x; v < v_end; v += blockDim.x) {
+        float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+        #pragma unroll
+        for (int r = 0; r < VB_CLUSTER; ++r) { g0 += rsgv[r][v * 3]; g1 += rsgv[r][v * 3 + 1]; g2 += rsgv[r][v * 3 + 2]; }
         const float x = vb[v * 3], y = vb[v * 3 + 1], z = vb[v * 3 + 2];
         gvb[v * 3 + 0] = g0 * sc.T[0] + g1 * sc.T[1] + g2 * sc.T[2];
         gvb[v * 3 + 1] = g0 * sc.T[3] + g1 * sc.T[4] + g2 * sc.T[5];
@@ -246,14 +284,24 @@ k_vertex_bwd(int V, int F, float proj_x, float proj_y,
     }
     #pragma unroll
     for (int i = 0; i < 12; ++i) {
-        const float r = block_sum_v(acc[i], red);
-        if (threadIdx.x == 0) sacc[i] = r;
+        float v = acc[i];
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[warp][i] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 12) {
+        float v = 0.0f;
+        #pragma unroll
+        for (int w = 0; w < VB_WARPS; ++w) v += s_part[w][threadIdx.x];
+        float* dst = cluster.map_shared_rank(&s_cl[0][0], 0);
+        dst[rank * 12 + threadIdx.x] = v;
+    }
+    cluster.sync();                        // partial sums visible to rank 0; nobody reads a remote sgv after this point
+    if (rank == 0 && threadIdx.x == 0) {
         float gR[9], gt[3], gcam[3];
-        for (int i = 0; i < 9; ++i) gR[i] = sacc[i];
-        for (int j = 0; j < 3; ++j) gt[j] = sacc[9 + j];
+        for (int i = 0; i < 9; ++i) { gR[i] = 0.0f; for (int r = 0; r < VB_CLUSTER; ++r) gR[i] += s_cl[r][i]; }
+        for (int j = 0; j < 3; ++j) { gt[j] = 0.0f; for (int r = 0; r < VB_CLUSTER; ++r) gt[j] += s_cl[r][9 + j]; }
         // t_j = -sum_i cam_i R_ij
         for (int i = 0; i < 3; ++i) {
             gcam[i] = -(gt[0] * sc.T[i * 3 + 0] + gt[1] * sc.T[i * 3 + 1] + gt[2] * sc.T[i * 3 + 2]);
@@ -287,12 +335,40 @@ k_vertex_bwd(int V, int F, float proj_x, float proj_y,
         g_elev[b] = k * (gcam[0] * (-sc.d * sc.se * sc.sa) + gcam[1] * (sc.d * sc.ce) + gcam[2] * (-sc.d * sc.se * sc.ca));
         g_azim[b] = k * (gcam[0] * (sc.d * sc.ce * sc.ca) + gcam[2] * (-sc.d * sc.ce * sc.sa));
     }
-    // (4) light gradient: per-image sums already reduced (fixed order) by the raster backward
-    if (threadIdx.x < 9) {
+    // (4) light gradient: per-image fixed-point sums accumulated by the shading backward
+    if (rank == 1 && threadIdx.x < 9) {
         g_lights[b * 9 + threadIdx.x] = (float)((double)img_bwd[b * 12 + 1 + threadIdx.x] / 17592186044416.0);   // MM_FX_GRAD
-        if (reset) img_bwd[b * 12 + 1 + threadIdx.x] = 0;     // stand-alone backward: leave the workspace reusable
+        if (q.reset) img_bwd[b * 12 + 1 + threadIdx.x] = 0;     // stand-alone backward: leave the workspace reusable
     }
-    if (reset && threadIdx.x == 0) img_bwd[b * 12] = 0;
+    if (q.reset && rank == 1 && threadIdx.x == 9) img_bwd[b * 12] = 0;
+    // (5) fused step: loss[0..3] = data, image, mask (1 - mean IoU), contour term (networks.py:364-390), one warp, fixed order
+    if (q.loss && b == 0 && rank == VB_CLUSTER - 1 && warp == 0) {
+        const double FXL = 1099511627776.0;                    // MM_FX_LOSS
+        float a_l1 = 0.0f, a_c = 0.0f, a_iou = 0.0f;
+        for (int i = lane; i < q.B; i += 32) {
+            a_l1 += fxv(q.img_fwd + i * 4 + 0, FXL);
+            a_c += fxv(q.img_fwd + i * 4 + 3, FXL) + fxv(img_bwd + i * 12 + 0, FXL);
+            const float n = fxv(q.img_fwd + i * 4 + 1, FXL), d = fxv(q.img_fwd + i * 4 + 2, FXL);
+            a_iou += n / (d + 1e-10f);
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a_l1 += __shfl_xor_sync(0xffffffffu, a_l1, o);
+            a_c += __shfl_xor_sync(0xffffffffu, a_c, o);
+            a_iou += __shfl_xor_sync(0xffffffffu, a_iou, o);
+        }
+        if (lane == 0) {
+            const float npx = (float)q.B * (float)q.H * (float)q.W;
+            const float l_img = a_l1 / (npx * 3.0f);
+            const float l_iou = 1.0f - a_iou / (float)q.B;
+            const float l_cont = (q.contour > 0.0f) ? a_c / npx : 0.0f;
+            const float l_mask = l_iou + ((q.contour > 0.0f) ? l_cont * q.contour : 0.0f);
+            q.loss[0] = q.image_weight * l_img + l_mask;
+            q.loss[1] = l_img;
+            q.loss[2] = l_iou;
+            q.loss[3] = l_cont;
+        }
+    }
 }
 
 __global__ void k_export_faces(int V, int F, float multiplier, const int32_t* __restrict__ faces,
@@ -319,9 +395,10 @@ __global__ void k_export_faces(int V, int F, float multiplier, const int32_t* __
 void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec,
                           float* vimg, float* face_normals, float* gfacc_zero, long long* img_fwd, long long* img_bwd,
-                          cudaStream_t s)
+                          void* clr0, size_t bytes0, void* clr1, size_t bytes1, cudaStream_t s)
 {
     VertexFwdParams q;
+    q.clr0 = (uint4*)clr0; q.n0 = bytes0 / 16; q.clr1 = (uint4*)clr1; q.n1 = bytes1 / 16;
     q.V = c->V; q.F = c->F; q.nchunks = c->nchunks;
     q.proj_x = c->proj_x; q.proj_y = c->proj_y; q.multiplier = c->multiplier;
     const dim3 grid(c->nchunks, B);
@@ -332,11 +409,15 @@ void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const f
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,
                           long long* img_bwd, int reset, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
-                          float* g_bias, float* g_lights, cudaStream_t s)
+                          float* g_bias, float* g_lights, float* loss, const long long* img_fwd, float image_weight,
+                          float contour, cudaStream_t s)
 {
     const size_t smem = ((size_t)c->V * 6) * sizeof(float);
-    mm_launch(k_vertex_bwd, dim3(B), dim3(MM_VTHREADS), smem, s, g_mm_pdl != 0, c->V, c->F, c->proj_x, c->proj_y,
-              (const int32_t*)c->d_faces, vertices, azim, elev, dist, bias, gfacc, g_face_normals, img_bwd, reset, g_vertices,
+    VertexBwdParams q;
+    q.B = B; q.V = c->V; q.F = c->F; q.H = c->H; q.W = c->W; q.proj_x = c->proj_x; q.proj_y = c->proj_y; q.reset = reset;
+    q.loss = loss; q.img_fwd = img_fwd; q.image_weight = image_weight; q.contour = contour;
+    mm_launch(k_vertex_bwd, dim3(VB_CLUSTER, B), dim3(VB_THREADS), smem, s, g_mm_pdl != 0, q,
+              (const int32_t*)c->d_faces, vertices, azim, elev, dist, bias, gfacc, g_face_normals, img_bwd, g_vertices,
               g_azim, g_elev, g_dist, g_bias, g_lights);
 }
 
