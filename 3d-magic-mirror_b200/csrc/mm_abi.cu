@@ -311,7 +311,10 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     const size_t HW = (size_t)c->H * c->W;
     if (g_bg && !no_mask) MM_CUDA(cudaMemsetAsync(g_bg, 0, (size_t)B * 3 * HW * 4, s));
     if (c->timing) cudaEventRecord(c->ev[0], s);
-    launch_vertex_fwd(c, B, L, ws, vertices, azim, elev, dist, bias, face_normals, true, g_tex, (size_t)B * 3 * Ht * Wt * 4, s);
+    const size_t gtex_bytes = (size_t)B * 3 * Ht * Wt * 4;
+    const bool gtex_side = (((uintptr_t)g_tex & 15) == 0) && ((gtex_bytes & 15) == 0);     // cleared by the hard pass on the side
+    if (!gtex_side) MM_CUDA(cudaMemsetAsync(g_tex, 0, gtex_bytes, s));
+    launch_vertex_fwd(c, B, L, ws, vertices, azim, elev, dist, bias, face_normals, true, nullptr, 0, s);
     if (int r = check_launch("vertex_fwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[1], s);
     mm_raster_params p;
@@ -319,7 +322,9 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     set_ws(L, ws, p);
     p.tex = tex; p.lights = lights; p.bg = bg; p.gt = gt;
     p.rgba = rgba;
+    if (gtex_side) { p.clr = (uint4*)g_tex; p.nclr = gtex_bytes / 16; }
     mm_launch_geom_fwd(c, p, s);
+    p.clr = nullptr; p.nclr = 0;
     if (int r = check_launch("geom_fwd")) return r;
     if (c->timing) cudaEventRecord(c->ev[2], s);
     p.g_rgba = g_rgba_extra;

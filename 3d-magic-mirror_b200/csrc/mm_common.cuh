@@ -153,6 +153,7 @@ struct mm_raster_params {
     float* g_tex;            // [B,3,Ht,Wt]
     float* g_bg;             // [B,3,H,W] or NULL
     float* part_bwd;         // [B,NP,12]
+    uint4* clr; size_t nclr;  // buffer the hard pass clears on the side (fused step: the texture-gradient output), 16-byte units
     long long* prof;         // debug: [B,NST,8] cycles fwd / bwd, popc(S), popc(H), hard, soft-mark, soft-pairs cycles, #pairs; NULL normally
 };
 

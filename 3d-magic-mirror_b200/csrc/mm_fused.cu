@@ -346,11 +346,16 @@ k_gsoft(const mm_raster_params p)
     const float* gmask = p.gt + (size_t)b * 4 * HW + 3 * HW;
     const float* gup = p.g_rgba ? p.g_rgba + (size_t)b * 4 * HW + 3 * HW : nullptr;
     float* gs = p.gsoft + (size_t)b * HW;
-    const float Nb = fx_get(p.img_fwd + b * 4 + 1, MM_FX_LOSS);
-    const float De = fx_get(p.img_fwd + b * 4 + 2, MM_FX_LOSS) + 1e-10f;
+    __shared__ float s_k[4];               // per-image constants (fixed-point -> float conversions are ~100 instructions: once per CTA)
+    if (threadIdx.x == 0) {
+        const float Nb0 = fx_get(p.img_fwd + b * 4 + 1, MM_FX_LOSS);
+        const float De0 = fx_get(p.img_fwd + b * 4 + 2, MM_FX_LOSS) + 1e-10f;
+        s_k[0] = Nb0; s_k[1] = De0; s_k[2] = 1.0f / (De0 * De0);
+    }
+    __syncthreads();
+    const float Nb = s_k[0], De = s_k[1], inv_de2 = s_k[2];
     const float k_iou = p.loss_scale / (float)p.B;
     const float k_cont = p.loss_scale * p.contour / ((float)p.B * (float)HW);
-    const float inv_de2 = 1.0f / (De * De);
     float acc_c = 0.0f;
     if (FAST4) {
         const int W4 = W >> 2;

@@ -211,6 +211,11 @@ k_scatter(const mm_raster_params p)
     const size_t HW = (size_t)p.H * p.W;
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
     const float inv_mult = 1.0f / p.multiplier;
+    if (MODE == MODE_HARD && p.nclr) {                 // the hard pass is issue-bound and leaves the memory system idle: clear
+        const size_t nthreads = (size_t)gridDim.x * blockDim.x;      // the step's texture-gradient buffer on the side
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nclr; i += nthreads) p.clr[i] = z;
+    }
     if (gwarp >= nwarps) return;
     if (MODE == MODE_SOFT_BWD && p.ovf_count[1] <= p.plist_cap) return;      // the pair list is complete: k_soft_bwd_list did it
 
@@ -625,7 +630,7 @@ void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t
 {
     const int warps = (p.B * c->F + FPW - 1) / FPW;
     const int grid = (warps + 7) / 8;
-    mm_launch(k_soft_bwd_list, dim3(c->num_sms * 4), dim3(256), 0, s, g_mm_pdl != 0, p);
+    mm_launch(k_soft_bwd_list, dim3(c->num_sms * 8), dim3(256), 0, s, g_mm_pdl != 0, p);
     mm_launch(k_scatter<MODE_SOFT_BWD>, dim3(grid), dim3(256), 0, s, g_mm_pdl != 0, p);              // returns immediately unless the pair list overflowed
     mm_launch(k_soft_ovf<true>, dim3(c->num_sms * 8), dim3(256), 0, s, g_mm_pdl != 0, p);
 }

@@ -158,8 +158,12 @@ k_vertex_fwd(const VertexFwdParams q,
 // the VERTICES across the four copies through distributed shared memory, emits g_vertices and its partial camera sums; rank 0
 // finishes the camera chain.  (The first version was one 512-thread CTA per image: 48 busy SMs and ~26 block barriers, 20 us.)
 // The last CTA of image 0 also finalises the loss scalars of the fused step (was a separate single-CTA launch).
+#ifndef VB_CLUSTER
 #define VB_CLUSTER 4
-#define VB_THREADS 256
+#endif
+#ifndef VB_THREADS
+#define VB_THREADS 384
+#endif
 #define VB_WARPS (VB_THREADS / 32)
 
 struct VertexBwdParams {
@@ -197,14 +201,15 @@ k_vertex_bwd(const VertexBwdParams q,
     const int rank = (int)cluster.block_rank();
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* vb = vertices + (size_t)b * V * 3;
+    // raw vertices -> shared while thread 0 builds the camera (the two latencies overlap), then transform in place
+    for (int i = threadIdx.x; i < V * 3; i += blockDim.x) { svc[i] = vb[i]; sgv[i] = 0.0f; }
     if (threadIdx.x == 0) camera_setup(azim[b], elev[b], dist[b], bias[b * 2], bias[b * 2 + 1], sc);
     __syncthreads();
-    const float* vb = vertices + (size_t)b * V * 3;
     for (int v = threadIdx.x; v < V; v += blockDim.x) {
         float cx, cy, cz;
-        transform_vertex(sc.T, vb[v * 3], vb[v * 3 + 1], vb[v * 3 + 2], cx, cy, cz);
+        transform_vertex(sc.T, svc[v * 3], svc[v * 3 + 1], svc[v * 3 + 2], cx, cy, cz);
         svc[v * 3] = cx; svc[v * 3 + 1] = cy; svc[v * 3 + 2] = cz;
-        sgv[v * 3] = 0.0f; sgv[v * 3 + 1] = 0.0f; sgv[v * 3 + 2] = 0.0f;
     }
     __syncthreads();
     const int fper = (F + VB_CLUSTER - 1) / VB_CLUSTER;
@@ -214,18 +219,26 @@ k_vertex_bwd(const VertexBwdParams q,
         float P[3][3];
         #pragma unroll
         for (int i = 0; i < 3; ++i) { P[i][0] = svc[idx[i] * 3]; P[i][1] = svc[idx[i] * 3 + 1]; P[i][2] = svc[idx[i] * 3 + 2]; }
-        const float* ga = gfacc + ((size_t)b * F + f) * 9;
+        float ga[9];
+        {
+            const float* gp = gfacc + ((size_t)b * F + f) * 9;
+            bool any = g_face_normals != nullptr;
+            #pragma unroll
+            for (int i = 0; i < 9; ++i) { ga[i] = gp[i]; any = any || (ga[i] != 0.0f); }
+            if (!any) continue;          // most faces (back-facing, interior, off-screen) received no gradient at all
+        }
         float G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        // (1) image-plane gradient -> camera space: xi = -px*x/z, yi = -py*y/z
+        // (1) image-plane gradient -> camera space: xi = -px*x/z, yi = -py*y/z.  One IEEE reciprocal per corner: the
+        // 15 divisions of the direct form mostly had zero numerators, which take the ~60-instruction slow path of the
+        // IEEE division (ncu: half of the kernel's instructions)
         #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const float gx = ga[i * 2], gy = ga[i * 2 + 1];
-            const float z = P[i][2];
-            const float den = z * -1.0f;
-            const float xi = (P[i][0] * q.proj_x) / den, yi = (P[i][1] * q.proj_y) / den;
-            G[i][0] += gx * q.proj_x / den;
-            G[i][1] += gy * q.proj_y / den;
-            G[i][2] += -(gx * xi + gy * yi) / z;
+            const float rz = 1.0f / P[i][2];
+            const float xi = -(P[i][0] * q.proj_x) * rz, yi = -(P[i][1] * q.proj_y) * rz;
+            G[i][0] += -(gx * q.proj_x) * rz;
+            G[i][1] += -(gy * q.proj_y) * rz;
+            G[i][2] += -(gx * xi + gy * yi) * rz;
         }
         // (2) unit normal gradient (raster path + upstream face_normals gradient)
         float gu[3] = {ga[6], ga[7], ga[8]};
