@@ -187,6 +187,7 @@ k_shade_fused(const mm_raster_params p)
     const float* tb = p.tex + (size_t)b * 3 * p.Ht * p.Wt;
     float* gacc = p.gfacc + (size_t)b * p.F * 9;
     float* gtex = p.g_tex + (size_t)b * 3 * p.Ht * p.Wt;
+    // (a texel-prefetch sub-pass ahead of this loop was measured: 43.7 -> 46.3 us, the kernel is not bound by that miss)
     #pragma unroll 1
     for (int i = threadIdx.x; i < count; i += FUSED_THREADS) {
         const uint32_t e = s_list[i];
