@@ -494,27 +494,32 @@ k_soft_bwd_list(const mm_raster_params p)
 
 // ---------------------------------------------------------------------------------------------- overflow (ordered) pass
 // DIB-R keeps only the FIRST knum candidates in face-index order (DIBR_SPEC A.4).  Pixels that saw more are re-done
-// here literally.  One CTA per overflowed pixel: all F enlarged-bbox tests happen in ONE memory round trip (each thread
-// owns F/256 faces), the per-warp ballots land in shared memory as hit words in face order, warp 0 applies the knum cap
-// with a running count over the words, and the kept candidates (<= knum, wherever they are) are then evaluated by the
-// threads that own them.  Forward: per-word ordered products, multiplied in word order.  Backward: the gradients of
-// exactly those candidates.
+// here literally.  One CTA per overflowed pixel:
+//   phase 1  all F enlarged-bbox tests in ONE memory round trip (each thread owns F/128 faces, loads issued back to back);
+//            the per-warp ballots land in shared memory as hit words in face order.
+//   phase 2  warp 0 keeps the first knum set bits (running count over the words) and writes the kept faces, in order, to a
+//            shared list; then -- still warp 0, no further block barrier -- lane k evaluates candidate k, and the ordered
+//            product (forward) is folded with shuffles exactly in the reference's order; backward: lane k scatters the
+//            gradient of candidate k.
+// A handful of pixels per step take this path (far cameras), so the kernel is pure latency: launch + ~2 round trips.
+#define OVF_THREADS 128
 #define OVF_MAX_WORDS 2048          // F <= 65535
+#define OVF_UNROLL 5
 
 template <bool BWD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(OVF_THREADS)
 k_soft_ovf(const mm_raster_params p)
 {
     mm_pdl_prologue();
     __shared__ uint32_t s_mask[OVF_MAX_WORDS];
-    __shared__ float s_wprod[OVF_MAX_WORDS];
+    __shared__ int s_kept[MM_MAX_KNUM];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n = p.ovf_count[0];
     const size_t HW = (size_t)p.H * p.W;
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
     const float inv_mult = 1.0f / p.multiplier;
     const int nw = (p.F + 31) >> 5;
-    const int niter = (p.F + 255) >> 8;                       // faces per thread
+    const int niter = (p.F + OVF_THREADS - 1) / OVF_THREADS;              // faces per thread
     for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
         const uint32_t pg = p.ovf_list[e];
         const int b = (int)(pg / HW);
@@ -529,87 +534,82 @@ k_soft_ovf(const mm_raster_params p)
             one_m_all = 1.0f - soft;
             if (g == 0.0f || !(soft > 0.0f)) continue;          // block-uniform
         }
-        // ---- phase 1: enlarged-bbox hit words, face order (word = f >> 5)
-        for (int j = 0; j < niter; ++j) {
-            const int f = (j << 8) + threadIdx.x;
-            bool hit = false;
-            if (f < p.F) {
-                const float4 c0 = __ldg(rec4 + (size_t)f * 3), c1 = __ldg(rec4 + (size_t)f * 3 + 1);
-                FaceRec r;
-                r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
-                r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
-                hit = soft_bbox_test(r, px, py, p.blen);
+        // ---- phase 1: enlarged-bbox hit words, face order (word = f >> 5); OVF_UNROLL independent record loads in flight
+        for (int j0 = 0; j0 < niter; j0 += OVF_UNROLL) {
+            float4 c0[OVF_UNROLL], c1[OVF_UNROLL];
+            #pragma unroll
+            for (int u = 0; u < OVF_UNROLL; ++u) {
+                const int f = (j0 + u) * OVF_THREADS + threadIdx.x;
+                if (j0 + u < niter && f < p.F) { c0[u] = __ldg(rec4 + (size_t)f * 3); c1[u] = __ldg(rec4 + (size_t)f * 3 + 1); }
+                else { c0[u] = make_float4(0.f, 0.f, 0.f, 0.f); c1[u] = c0[u]; }
             }
-            const uint32_t m = __ballot_sync(FULL, hit);
-            const int word = (j << 3) + warp;
-            if (lane == 0 && word < nw) s_mask[word] = m;
+            #pragma unroll
+            for (int u = 0; u < OVF_UNROLL; ++u) {
+                const int j = j0 + u;
+                const int f = j * OVF_THREADS + threadIdx.x;
+                bool hit = false;
+                if (j < niter && f < p.F) {
+                    FaceRec r;
+                    r.ax = c0[u].x; r.ay = c0[u].y; r.bx = c0[u].z; r.by = c0[u].w; r.cx = c1[u].x; r.cy = c1[u].y;
+                    r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
+                    hit = soft_bbox_test(r, px, py, p.blen);
+                }
+                const uint32_t m = __ballot_sync(FULL, hit);
+                const int word = j * (OVF_THREADS / 32) + warp;
+                if (lane == 0 && j < niter && word < nw) s_mask[word] = m;
+            }
         }
         __syncthreads();
-        // ---- phase 2 (warp 0): keep the first knum set bits over all words
+        // ---- phase 2 (warp 0): first knum set bits over all words -> ordered list of kept faces
         if (warp == 0) {
             int seen = 0;
-            for (int w0 = 0; w0 < nw; w0 += 32) {
+            for (int w0 = 0; w0 < nw && seen < p.knum; w0 += 32) {
                 const int wd = w0 + lane;
-                const uint32_t m = (wd < nw) ? s_mask[wd] : 0u;
+                uint32_t m = (wd < nw) ? s_mask[wd] : 0u;
                 const int c = __popc(m);
                 int incl = c;
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-                const int before = seen + incl - c;
-                int room = p.knum - before;
-                room = room < 0 ? 0 : room;
-                uint32_t keep = m;
-                if (c > room) {
-                    uint32_t k2 = 0u, h = m;
-                    #pragma unroll 1
-                    for (int a = 0; a < room; ++a) { const uint32_t low = h & (0u - h); k2 |= low; h ^= low; }
-                    keep = k2;
+                int pos = seen + incl - c;                       // candidates before this word
+                while (m && pos < p.knum) {                       // this word's bits, in face order
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1u;
+                    s_kept[pos++] = (wd << 5) + bit;
                 }
-                if (wd < nw) { s_mask[wd] = keep; s_wprod[wd] = 1.0f; }
                 seen += __shfl_sync(FULL, incl, 31);
             }
-        }
-        __syncthreads();
-        // ---- phase 3: the owners of the kept candidates evaluate them
-        for (int j = 0; j < niter; ++j) {
-            const int f = (j << 8) + threadIdx.x;
-            const int word = (j << 3) + warp;
-            const uint32_t keep = (word < nw) ? s_mask[word] : 0u;
-            if (keep == 0u) continue;                           // warp-uniform
-            const bool mine = (keep >> lane) & 1u;
-            FaceRec r;
-            if (mine) {
-                const float4 c0 = __ldg(rec4 + (size_t)f * 3), c1 = __ldg(rec4 + (size_t)f * 3 + 1);
-                r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
-                r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
-            }
-            if (BWD) {
-                if (mine) {
-                    float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-                    soft_pair_grad(p, r, px, py, kz, inv_mult, g, one_m_all, ga);
-                    float* gf = p.gfacc + ((size_t)b * p.F + f) * 9;
-                    #pragma unroll
-                    for (int k = 0; k < 6; ++k) if (ga[k] != 0.0f) atomicAdd(gf + k, ga[k]);
-                }
-            } else {
-                float prob = 0.0f;
-                if (mine) { int type; prob = soft_prob_fast(soft_d2_fast(r, px, py, p.multiplier, type), kz); }
-                float wp = 1.0f;
-                uint32_t mm = keep;
-                #pragma unroll 1
-                while (mm) {                                     // the reference's ordered product within the word
-                    const int jj = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    wp = wp * (1.0f - __shfl_sync(FULL, prob, jj));
-                }
-                if (lane == 0) s_wprod[word] = wp;
-            }
-        }
-        __syncthreads();
-        if (!BWD && threadIdx.x == 0) {
+            const int nk = min(seen, p.knum);
+            __syncwarp();
+            // ---- the kept candidates, one per lane (knum <= 64: two rounds at most)
             float allprob = 1.0f;
-            for (int wd = 0; wd < nw; ++wd) if (s_mask[wd]) allprob = allprob * s_wprod[wd];     // word order = face order
-            p.lacc[pg] = lacc_exact(allprob > 0.0f ? logf(allprob) : -2400.0f);
+            for (int k0 = 0; k0 < nk; k0 += 32) {
+                const int k = k0 + lane;
+                const bool mine = k < nk;
+                const int f = mine ? s_kept[k] : 0;
+                FaceRec r;
+                {
+                    const float4 c0 = __ldg(rec4 + (size_t)f * 3), c1 = __ldg(rec4 + (size_t)f * 3 + 1);
+                    r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
+                    r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
+                }
+                if (BWD) {
+                    if (mine) {
+                        float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+                        soft_pair_grad(p, r, px, py, kz, inv_mult, g, one_m_all, ga);
+                        float* gf = p.gfacc + ((size_t)b * p.F + f) * 9;
+                        #pragma unroll
+                        for (int q = 0; q < 6; ++q) if (ga[q] != 0.0f) atomicAdd(gf + q, ga[q]);
+                    }
+                } else {
+                    float prob = 0.0f;
+                    if (mine) { int type; prob = soft_prob_fast(soft_d2_fast(r, px, py, p.multiplier, type), kz); }
+                    const int cnt = min(32, nk - k0);
+                    #pragma unroll 1
+                    for (int q = 0; q < cnt; ++q)                // the reference's ordered product
+                        allprob = allprob * (1.0f - __shfl_sync(FULL, prob, q));
+                }
+            }
+            if (!BWD && lane == 0) p.lacc[pg] = lacc_exact(allprob > 0.0f ? logf(allprob) : -2400.0f);
         }
         __syncthreads();
     }
@@ -623,7 +623,7 @@ void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t
     const int grid = (warps + 7) / 8;
     mm_launch(k_scatter<MODE_HARD>, dim3(grid), dim3(256), 0, s, g_mm_pdl != 0, p);
     { const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW; mm_launch(k_soft_fwd, dim3((nw + SF_WARPS - 1) / SF_WARPS), dim3(32 * SF_WARPS), 0, s, g_mm_pdl != 0, p); }
-    mm_launch(k_soft_ovf<false>, dim3(c->num_sms * 8), dim3(256), 0, s, g_mm_pdl != 0, p);
+    mm_launch(k_soft_ovf<false>, dim3(c->num_sms * 16), dim3(OVF_THREADS), 0, s, g_mm_pdl != 0, p);
 }
 
 void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
@@ -632,7 +632,7 @@ void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t
     const int grid = (warps + 7) / 8;
     mm_launch(k_soft_bwd_list, dim3(c->num_sms * 8), dim3(256), 0, s, g_mm_pdl != 0, p);
     mm_launch(k_scatter<MODE_SOFT_BWD>, dim3(grid), dim3(256), 0, s, g_mm_pdl != 0, p);              // returns immediately unless the pair list overflowed
-    mm_launch(k_soft_ovf<true>, dim3(c->num_sms * 8), dim3(256), 0, s, g_mm_pdl != 0, p);
+    mm_launch(k_soft_ovf<true>, dim3(c->num_sms * 16), dim3(OVF_THREADS), 0, s, g_mm_pdl != 0, p);
 }
 
 size_t mm_raster_smem_bytes(const mm_ctx* c) { (void)c; return 0; }
