@@ -74,13 +74,14 @@ void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int no_mask, mm_raster_
     p.prof = c->d_prof;
 }
 
-void set_ws(const mm_ws_layout& L, char* ws, mm_raster_params& p) {
+void set_ws(const mm_ctx* c, const mm_ws_layout& L, char* ws, mm_raster_params& p) {
     p.frec = (const float*)(ws + L.frec);
     p.zbuf = (unsigned long long*)(ws + L.zbuf); p.lacc = (unsigned long long*)(ws + L.lacc);
     p.cov = (uint32_t*)(ws + L.cov);
     p.ovf_list = (uint32_t*)(ws + L.ovf_list); p.ovf_count = (uint32_t*)(ws + L.ovf_count);
     p.gsoft = (float*)(ws + L.gsoft);
     p.plist = (unsigned long long*)(ws + L.plist); p.plist_cap = (uint32_t)((L.gsoft - L.plist) / 8);
+    if (c->plist_cap_max && p.plist_cap > c->plist_cap_max) p.plist_cap = c->plist_cap_max;
     p.part_fwd = (float*)(ws + L.part_fwd); p.part_bwd = (float*)(ws + L.part_bwd);
     p.img_fwd = (long long*)(ws + L.img_fwd); p.img_bwd = (long long*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
     p.gfacc = (float*)(ws + L.gfacc);
@@ -153,6 +154,7 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     // vertex stage: CTAs per image (each recomputes the vertex transform and emits 1/nchunks of the face records)
     c->nchunks = 8;
     if (const char* e = getenv("MM_PDL")) g_mm_pdl = atoi(e) != 0;
+    if (const char* e = getenv("MM_PLIST_CAP")) c->plist_cap_max = (unsigned)atoi(e);
     if (const char* e = getenv("MM_VCHUNKS")) { const int v = atoi(e); if (v > 0 && v <= 32) c->nchunks = v; }
     c->chunk_rows = 0;
     c->smem_vertex_fwd = mm_vertex_smem_fwd(c);
@@ -215,7 +217,7 @@ int mm_render_forward(mm_ctx* c, int B, const float* vertices, const float* azim
     if (int r = check_launch("vertex_fwd")) return r;
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, no_mask, p);
-    set_ws(L, ws, p);
+    set_ws(c, L, ws, p);
     p.tex = tex; p.lights = lights; p.bg = bg;
     p.rgba = rgba; p.imnormal = imnormal; p.face_idx_out = face_idx;
     mm_launch_geom_fwd(c, p, s);
@@ -244,7 +246,7 @@ int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azi
     if (g_bg && !no_mask) MM_CUDA(cudaMemsetAsync(g_bg, 0, (size_t)B * 3 * HW * 4, s));
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, no_mask, p);
-    set_ws(L, ws, p);
+    set_ws(c, L, ws, p);
     p.tex = tex; p.lights = lights; p.bg = bg;
     p.rgba = const_cast<float*>(rgba);
     p.g_rgba = g_rgba;
@@ -319,7 +321,7 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     if (c->timing) cudaEventRecord(c->ev[1], s);
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, no_mask, p);
-    set_ws(L, ws, p);
+    set_ws(c, L, ws, p);
     p.tex = tex; p.lights = lights; p.bg = bg; p.gt = gt;
     p.rgba = rgba;
     if (gtex_side) { p.clr = (uint4*)g_tex; p.nclr = gtex_bytes / 16; }

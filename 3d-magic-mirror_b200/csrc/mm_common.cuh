@@ -68,6 +68,7 @@ struct mm_ctx {
     size_t smem_vertex_fwd;  // dynamic smem bytes of the vertex forward kernel
     size_t smem_raster;      // dynamic smem bytes of the raster kernels (per-lane soft candidate lists)
     int num_sms;
+    unsigned plist_cap_max;  // test hook (MM_PLIST_CAP): caps the forward's pair list so that the backward's fallback path runs
     // device arrays
     int32_t* d_faces;        // [F,3]
     float*   d_face_uvs;     // [F,6]

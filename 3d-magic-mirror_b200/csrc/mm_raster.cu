@@ -199,26 +199,12 @@ __device__ __forceinline__ void record_pairs(const mm_raster_params& p, const Wa
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256)
-k_scatter(const mm_raster_params p)
+__device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& wq, const int gwarp, const int nwarps)
 {
-    mm_pdl_prologue();
-    __shared__ WarpQ s_wq[8];
     const int lane = threadIdx.x & 31;
-    WarpQ& wq = s_wq[threadIdx.x >> 5];
-    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (p.B * p.F + FPW - 1) / FPW;
     const size_t HW = (size_t)p.H * p.W;
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
     const float inv_mult = 1.0f / p.multiplier;
-    if (MODE == MODE_HARD && p.nclr) {                 // the hard pass is issue-bound and leaves the memory system idle: clear
-        const size_t nthreads = (size_t)gridDim.x * blockDim.x;      // the step's texture-gradient buffer on the side
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nclr; i += nthreads) p.clr[i] = z;
-    }
-    if (gwarp >= nwarps) return;
-    if (MODE == MODE_SOFT_BWD && p.ovf_count[1] <= p.plist_cap) return;      // the pair list is complete: k_soft_bwd_list did it
-
     // ---- set-up: lanes 0..7 each own one face of the warp: record -> smem, EXACT pixel rectangle of its bbox
     int npx = 0;
     if (lane < FPW) {
@@ -312,6 +298,22 @@ k_scatter(const mm_raster_params p)
             }
         }
     }
+}
+
+// hard pass kernel: one warp per 8 faces
+__global__ void __launch_bounds__(256)
+k_scatter_hard(const mm_raster_params p)
+{
+    mm_pdl_prologue();
+    __shared__ WarpQ s_wq[8];
+    if (p.nclr) {                                      // the hard pass is issue-bound and leaves the memory system idle: clear
+        const size_t nthreads = (size_t)gridDim.x * blockDim.x;      // the step's texture-gradient buffer on the side
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nclr; i += nthreads) p.clr[i] = z;
+    }
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (p.B * p.F + FPW - 1) / FPW;
+    if (gwarp < nwarps) scatter_warp<MODE_HARD>(p, s_wq[threadIdx.x >> 5], gwarp, nwarps);
 }
 
 // ---------------------------------------------------------------------------------------------- soft pass forward
@@ -454,8 +456,17 @@ __global__ void __launch_bounds__(256)
 k_soft_bwd_list(const mm_raster_params p)
 {
     mm_pdl_prologue();
+    __shared__ WarpQ s_wq[8];
     const uint32_t n = p.ovf_count[1];
-    if (n > p.plist_cap) return;                                   // list overflowed: the filter-based kernel runs instead
+    if (n > p.plist_cap) {                  // the forward's pair list overflowed its buffer (never at the template meshes'
+        const int nwarps = (p.B * p.F + FPW - 1) / FPW;           // shapes): redo the bbox walk with the filtering pair engine
+        const int wstride = (gridDim.x * blockDim.x) >> 5;
+        for (int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gw < nwarps; gw += wstride) {
+            scatter_warp<MODE_SOFT_BWD>(p, s_wq[threadIdx.x >> 5], gw, nwarps);
+            __syncwarp();
+        }
+        return;
+    }
     const int lane = threadIdx.x & 31;
     const size_t HW = (size_t)p.H * p.W;
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
@@ -621,17 +632,14 @@ void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t
 {
     const int warps = (p.B * c->F + FPW - 1) / FPW;
     const int grid = (warps + 7) / 8;
-    mm_launch(k_scatter<MODE_HARD>, dim3(grid), dim3(256), 0, s, g_mm_pdl != 0, p);
+    mm_launch(k_scatter_hard, dim3(grid), dim3(256), 0, s, g_mm_pdl != 0, p);
     { const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW; mm_launch(k_soft_fwd, dim3((nw + SF_WARPS - 1) / SF_WARPS), dim3(32 * SF_WARPS), 0, s, g_mm_pdl != 0, p); }
     mm_launch(k_soft_ovf<false>, dim3(c->num_sms * 16), dim3(OVF_THREADS), 0, s, g_mm_pdl != 0, p);
 }
 
 void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
-    const int warps = (p.B * c->F + FPW - 1) / FPW;
-    const int grid = (warps + 7) / 8;
     mm_launch(k_soft_bwd_list, dim3(c->num_sms * 8), dim3(256), 0, s, g_mm_pdl != 0, p);
-    mm_launch(k_scatter<MODE_SOFT_BWD>, dim3(grid), dim3(256), 0, s, g_mm_pdl != 0, p);              // returns immediately unless the pair list overflowed
     mm_launch(k_soft_ovf<true>, dim3(c->num_sms * 16), dim3(OVF_THREADS), 0, s, g_mm_pdl != 0, p);
 }
 

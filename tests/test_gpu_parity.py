@@ -207,6 +207,15 @@ def test_error_behaviour(mm):
     assert rc == -1 and b"invalid argument" in L.mm_last_error()
 
 
+def test_soft_backward_fallback_when_pair_list_overflows(mm, monkeypatch):
+    """The backward replays the forward's (face, pixel) candidate list; if that list outgrows its buffer the backward
+    re-walks the bboxes instead.  MM_PLIST_CAP (read at ctx creation) shrinks the buffer so that path runs."""
+    monkeypatch.setenv("MM_PLIST_CAP", "257")
+    case = dict(mesh="sphere", B=2, image_size=64, no_mask=True, contour=0.1, seed=13, dist_range=(3.0, 7.0))
+    res = pu.run_parity_case(mm, **case)
+    _check(res, case["B"], 64, 64)
+
+
 def test_empty_scene_and_offscreen(mm):
     """Object entirely outside the frame: nothing covered, silhouette 0, gradients finite (zeros for geometry)."""
     dr = mm.DiffRender(mm.icosphere(3), 64)
