@@ -92,6 +92,8 @@ struct WarpQ {
     int img[FPW];            // image of each slot
     int face[FPW];           // face index of each slot
     int ix0[FPW], iy0[FPW], w[FPW];   // exact pixel rectangle of each slot's bbox (origin, width)
+    int pre[FPW];            // first pair number of each slot
+    float rw[FPW];           // 1 / width
     float facc[6][FPW];      // backward: corner-gradient accumulators per slot
 };
 
@@ -225,6 +227,7 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
         const int w = ix1 - ix0 + 1, h = iy1 - iy0 + 1;
         npx = (w > 0 && h > 0) ? w * h : 0;
         wq.ix0[slot] = ix0; wq.iy0[slot] = iy0; wq.w[slot] = w > 0 ? w : 1;
+        wq.rw[slot] = __frcp_rn((float)(w > 0 ? w : 1));
         if (MODE == MODE_SOFT_BWD) {
             #pragma unroll
             for (int k = 0; k < 6; ++k) wq.facc[k][slot] = 0.0f;
@@ -236,6 +239,12 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
     #pragma unroll
     for (int sl = 0; sl < FPW; ++sl) pre[sl + 1] = pre[sl] + __shfl_sync(FULL, npx, sl);
     const int total = pre[FPW];
+    if (lane < FPW) {
+        int mine = 0;
+        #pragma unroll
+        for (int sl = 1; sl < FPW; ++sl) mine = (lane == sl) ? pre[sl] : mine;
+        wq.pre[lane] = mine;
+    }
     __syncwarp();
 
     // ---- the warp's (face, pixel) pairs, dealt to the 32 lanes round-robin: perfectly balanced whatever the face sizes
@@ -250,11 +259,9 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
             int slot = 0;
             #pragma unroll
             for (int sl = 1; sl < FPW; ++sl) slot += (k >= pre[sl]) ? 1 : 0;
-            int local = k;
-            #pragma unroll
-            for (int sl = 1; sl < FPW; ++sl) local = (slot == sl) ? k - pre[sl] : local;
+            const int local = k - wq.pre[slot];
             const int w = wq.w[slot];
-            int dy = (int)(((float)local + 0.5f) * __frcp_rn((float)w));
+            int dy = (int)(((float)local + 0.5f) * wq.rw[slot]);
             int dx = local - dy * w;
             if (dx < 0) { --dy; dx += w; } else if (dx >= w) { ++dy; dx -= w; }
             const int ix = wq.ix0[slot] + dx, iy = wq.iy0[slot] + dy;
@@ -407,14 +414,13 @@ k_soft_fwd(const mm_raster_params p)
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxseg = max(maxseg, __shfl_xor_sync(FULL, maxseg, o));
     int qn = 0;
+    // running (row, word) of this lane's segment `it * 4 + sub`, advanced by 4 segments per iteration without a division
+    int row = iy0, wd = wd0 + sub;
+    if (nwd > 0) while (wd >= wd0 + nwd) { wd -= nwd; ++row; }
     #pragma unroll 1
     for (int it = 0; it < maxseg; ++it) {
         uint32_t bits = 0u;
-        int row = 0, wd = 0;
         if (it < nseg) {
-            const int sg = it * 4 + sub;
-            if (nwd == 1) { row = iy0 + sg; wd = wd0; }
-            else { const int rr = sg / nwd; row = iy0 + rr; wd = wd0 + (sg - rr * nwd); }
             const int lo = max(ix0 - (wd << 5), 0), hi = min(ix1 - (wd << 5), 31);         // column range inside this word
             const uint32_t colmask = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
             bits = ~__ldg(covb + (size_t)row * p.covw + wd) & colmask;                       // uncovered pixels of the segment
@@ -441,6 +447,10 @@ k_soft_fwd(const mm_raster_params p)
                 soft_fwd_record(p, wq, e, 32, lane);
             }
             __syncwarp();
+        }
+        if (it < nseg) {
+            if (nwd == 1) row += 4;
+            else { wd += 4; while (wd >= wd0 + nwd) { wd -= nwd; ++row; } }
         }
     }
     if (qn > 0) {
