@@ -288,7 +288,10 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all the host threads it can
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)
     import __graft_entry__ as g
     g.build_oracle()
     mm = g.load_package()
