@@ -333,11 +333,16 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     p.image_weight = image_weight; p.contour = contour; p.loss_scale = loss_scale;
     p.analytic_loss = 1;
     p.g_tex = g_tex; p.g_bg = no_mask ? g_bg : nullptr;
+    // H, W multiples of 4: the contour term is tile-local, so k_shade_fused also emits d(loss)/d(silhouette) minus its IoU term,
+    // which the geometry backward adds from the per-image sums on the fly -- no separate pass over the pixels
+    p.gsoft_iou_pending = ((c->H & 3) == 0 && (c->W & 3) == 0) ? 1 : 0;
     mm_launch_shade_fused(c, p, s);           // shading forward + loss sums + the whole RGB-side backward
     if (int r = check_launch("shade_fused")) return r;
     if (c->timing) cudaEventRecord(c->ev[3], s);
-    mm_launch_gsoft(c, p, s);                 // d(loss)/d(silhouette), needs the complete per-image IoU sums
-    if (int r = check_launch("gsoft")) return r;
+    if (!p.gsoft_iou_pending) {
+        mm_launch_gsoft(c, p, s);             // general sizes: d(loss)/d(silhouette) in its own pass (index tables)
+        if (int r = check_launch("gsoft")) return r;
+    }
     if (c->timing) cudaEventRecord(c->ev[4], s);
     mm_launch_geom_bwd(c, p, s);
     if (int r = check_launch("geom_bwd")) return r;

@@ -133,6 +133,7 @@ struct mm_raster_params {
     unsigned long long* plist;    // [plist_cap]
     uint32_t plist_cap;
     float* gsoft;            // [B,H,W]
+    int gsoft_iou_pending;   // 1: `gsoft` holds upstream + contour terms only; consumers add the IoU term (per-image sums) on the fly
     const float* face_uvs;   // [F,6]
     const float* tex;        // [B,3,Ht,Wt]
     const float* lights;     // [B,9]

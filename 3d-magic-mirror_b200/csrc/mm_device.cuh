@@ -294,6 +294,21 @@ __device__ __forceinline__ void fx_add(long long* acc, float v, double scale) {
 }
 __device__ __forceinline__ float fx_get(const long long* acc, double scale) { return (float)((double)(*acc) / scale); }
 
+// d(loss)/d(silhouette) of pixel `pix` of image b as the geometry backward consumes it.  In the fused step the shading kernel
+// stores the tile-local part (upstream gradient + contour term); the IoU term -(1/B) (gm De - Nb (1 - gm)) / De^2 needs the
+// complete per-image sums and is added here, by the consumer (DIBR_SPEC A.7).
+__device__ __forceinline__ float gsoft_at(const mm_raster_params& p, int b, size_t pix) {
+    const size_t HW = (size_t)p.H * p.W;
+    float g = p.gsoft[(size_t)b * HW + pix];
+    if (p.gsoft_iou_pending) {
+        const float gm = __ldg(p.gt + ((size_t)b * 4 + 3) * HW + pix);
+        const float Nb = fx_get(p.img_fwd + b * 4 + 1, MM_FX_LOSS);
+        const float De = fx_get(p.img_fwd + b * 4 + 2, MM_FX_LOSS) + 1e-10f;
+        g += -(p.loss_scale / (float)p.B) * (gm * De - Nb * (1.0f - gm)) / (De * De);
+    }
+    return g;
+}
+
 // ------------------------------------------------------------------ per-pixel soft-silhouette accumulator
 // One 64-bit word per pixel, updated with ONE integer atomicAdd per (pixel, face) candidate:
 //   bits 63..16  sum of log(1 - p_k) in fixed point (scale 2^32, two's complement; |sum| < 2^15)

@@ -84,7 +84,7 @@ k_shade_fused(const mm_raster_params p)
     float coef_bg;                                                          // sh_coef of a zero normal, same op sequence
     { float bnd0[9]; sh_bands(0.0f, 0.0f, 0.0f, bnd0); coef_bg = sh_coef(bnd0, s_lights); }
 
-    float acc_l1 = 0.0f, acc_n = 0.0f, acc_d = 0.0f, acc_gc = 0.0f;
+    float acc_l1 = 0.0f, acc_n = 0.0f, acc_d = 0.0f, acc_gc = 0.0f, acc_c = 0.0f;
     {
         const int tile = blockIdx.x * FUSED_WARPS + warp;
         const int ty = tile / ntx, tx = tile - ty * ntx;
@@ -93,9 +93,9 @@ k_shade_fused(const mm_raster_params p)
         const bool active = n > 0;
         const size_t pix0 = active ? (size_t)iy * W + ix0 : 0;
         int face[4] = {-1, -1, -1, -1};
+        float soft[4] = {0.0f, 0.0f, 0.0f, 0.0f}, gmv[4] = {0.0f, 0.0f, 0.0f, 0.0f}, gs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         if (active) {
             // ---- every streamed input of the 4 pixels, issued up front
-            float soft[4];
             {
                 const unsigned long long* zb = p.zbuf + (size_t)b * HW + pix0;
                 const unsigned long long* la = p.lacc + (size_t)b * HW + pix0;
@@ -126,6 +126,9 @@ k_shade_fused(const mm_raster_params p)
                 if (HAS_GUP) load4<VEC>(p.g_rgba + ((size_t)b * 4 + ch) * HW + pix0, n, gup[ch]);
                 else { gup[ch][0] = gup[ch][1] = gup[ch][2] = gup[ch][3] = 0.0f; }
             }
+            if (HAS_GUP) load4<VEC>(p.g_rgba + ((size_t)b * 4 + 3) * HW + pix0, n, gs);      // upstream d/d(silhouette)
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) gmv[j] = gtv[3][j];
             float img[3][4], gbg[3][4];
             #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -161,6 +164,29 @@ k_shade_fused(const mm_raster_params p)
                 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) store4<VEC>(p.g_bg + ((size_t)b * 3 + ch) * HW + pix0, n, gbg[ch]);
             }
+        }
+        // ---- tile-local part of d(loss)/d(silhouette): upstream + contour term (DIBR_SPEC A.7).  H and W are multiples of 4 here,
+        // so the 16x8 tile holds whole 4x4 contour blocks: a block = lanes differing in lane bits 2,3 (4 rows) with the same
+        // lx; its reference pixel is pixel 0 of the lane with (ly & 3) == 0.  The IoU term is added by the consumers (gsoft_at).
+        if (p.gsoft_iou_pending) {
+            if (p.contour > 0.0f) {
+                const float k_cont = p.loss_scale * p.contour / ((float)p.B * (float)HW);
+                const int ref_lane = lane & ~12;
+                const float mref = __shfl_sync(FULL, soft[0], ref_lane), gref = __shfl_sync(FULL, gmv[0], ref_lane);
+                float tsum = 0.0f;
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float dlt = fabsf(soft[j] - mref) - fabsf(gmv[j] - gref);
+                    acc_c += dlt * dlt;                       // lanes outside the image hold zeros
+                    const float own = 2.0f * dlt * sgnf(soft[j] - mref);
+                    gs[j] += k_cont * own;
+                    tsum -= own;                              // what this pixel contributes to its reference pixel
+                }
+                tsum += __shfl_xor_sync(FULL, tsum, 4);
+                tsum += __shfl_xor_sync(FULL, tsum, 8);
+                if ((lane & 12) == 0) gs[0] += k_cont * tsum;
+            }
+            if (active) store4<VEC>(p.gsoft + (size_t)b * HW + pix0, n, gs);
         }
         // ---- covered pixels -> shared list (warp-aggregated append, 4 ballots)
         #pragma unroll
@@ -318,6 +344,10 @@ k_shade_fused(const mm_raster_params p)
     acc_l[0] += acc_gc * SH_C0;                  // background pixels: bands = (C0, 0, .., -C3B, 0, 0)
     acc_l[6] += acc_gc * (-SH_C3B);
     const float s0 = warp_sum(acc_l1), s1 = warp_sum(acc_n), s2 = warp_sum(acc_d);
+    if (p.gsoft_iou_pending && p.contour > 0.0f) {
+        const float s3 = warp_sum(acc_c);
+        if (lane == 0 && s3 != 0.0f) fx_add(p.img_bwd + b * 12, s3, MM_FX_LOSS);
+    }
     if (lane == 0) {
         if (s0 != 0.0f) fx_add(p.img_fwd + b * 4 + 0, s0, MM_FX_LOSS);
         if (s1 != 0.0f) fx_add(p.img_fwd + b * 4 + 1, s1, MM_FX_LOSS);

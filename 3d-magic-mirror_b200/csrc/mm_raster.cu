@@ -176,7 +176,7 @@ __device__ __forceinline__ void eval_pair(const mm_raster_params& p, WarpQ& wq, 
             p.ovf_list[s2] = (uint32_t)((size_t)b * HW + pix);
         }
     } else {
-        const float g = p.gsoft[(size_t)b * HW + pix];
+        const float g = gsoft_at(p, b, pix);
         const float soft = p.rgba[(size_t)b * 4 * HW + 3 * HW + pix];
         if (g == 0.0f || !(soft > 0.0f)) return;
         float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
@@ -462,16 +462,14 @@ k_soft_fwd(const mm_raster_params p)
 
 // ---------------------------------------------------------------------------------------------- soft pass backward, list-driven
 // Replays the forward's dense candidate list: one pair per lane, no bbox walk, no filtering.
-__global__ void __launch_bounds__(256)
-k_soft_bwd_list(const mm_raster_params p)
+#define SB_THREADS 128
+__device__ __forceinline__ void soft_bwd_list_role(const mm_raster_params& p, WarpQ* s_wq, const int vblock, const int nvblocks)
 {
-    mm_pdl_prologue();
-    __shared__ WarpQ s_wq[8];
     const uint32_t n = p.ovf_count[1];
     if (n > p.plist_cap) {                  // the forward's pair list overflowed its buffer (never at the template meshes'
         const int nwarps = (p.B * p.F + FPW - 1) / FPW;           // shapes): redo the bbox walk with the filtering pair engine
-        const int wstride = (gridDim.x * blockDim.x) >> 5;
-        for (int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gw < nwarps; gw += wstride) {
+        const int wstride = (nvblocks * SB_THREADS) >> 5;
+        for (int gw = (vblock * SB_THREADS + threadIdx.x) >> 5; gw < nwarps; gw += wstride) {
             scatter_warp<MODE_SOFT_BWD>(p, s_wq[threadIdx.x >> 5], gw, nwarps);
             __syncwarp();
         }
@@ -481,8 +479,8 @@ k_soft_bwd_list(const mm_raster_params p)
     const size_t HW = (size_t)p.H * p.W;
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
     const float inv_mult = 1.0f / p.multiplier;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += stride) {
+    const uint32_t stride = (uint32_t)nvblocks * SB_THREADS;
+    for (uint32_t i0 = ((uint32_t)vblock * SB_THREADS + threadIdx.x) & ~31u; i0 < n; i0 += stride) {
         const uint32_t i = i0 + lane;
         float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
         uint32_t fg = 0xffffffffu;
@@ -492,7 +490,7 @@ k_soft_bwd_list(const mm_raster_params p)
             const int iy = (int)((e >> 12) & 0xfffu), ix = (int)(e & 0xfffu);
             const int b = (int)(fg / (uint32_t)p.F);
             const size_t pg = (size_t)b * HW + (size_t)iy * p.W + ix;
-            const float g = p.gsoft[pg];
+            const float g = gsoft_at(p, b, (size_t)iy * p.W + ix);
             const float soft = p.rgba[(size_t)b * 4 * HW + 3 * HW + (size_t)iy * p.W + ix];
             if (g != 0.0f && soft > 0.0f && lacc_count(p.lacc[pg]) != (int)MM_LACC_OVF) {
                 const float4* q4 = reinterpret_cast<const float4*>(p.frec) + (size_t)fg * 3;
@@ -528,12 +526,8 @@ k_soft_bwd_list(const mm_raster_params p)
 #define OVF_UNROLL 5
 
 template <bool BWD>
-__global__ void __launch_bounds__(OVF_THREADS)
-k_soft_ovf(const mm_raster_params p)
+__device__ __forceinline__ void soft_ovf_role(const mm_raster_params& p, uint32_t* s_mask, int* s_kept, const int vblock, const int nvblocks)
 {
-    mm_pdl_prologue();
-    __shared__ uint32_t s_mask[OVF_MAX_WORDS];
-    __shared__ int s_kept[MM_MAX_KNUM];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n = p.ovf_count[0];
     const size_t HW = (size_t)p.H * p.W;
@@ -541,7 +535,7 @@ k_soft_ovf(const mm_raster_params p)
     const float inv_mult = 1.0f / p.multiplier;
     const int nw = (p.F + 31) >> 5;
     const int niter = (p.F + OVF_THREADS - 1) / OVF_THREADS;              // faces per thread
-    for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
+    for (uint32_t e = (uint32_t)vblock; e < n; e += (uint32_t)nvblocks) {
         const uint32_t pg = p.ovf_list[e];
         const int b = (int)(pg / HW);
         const int pix = (int)(pg - (size_t)b * HW);
@@ -550,7 +544,7 @@ k_soft_ovf(const mm_raster_params p)
         const float4* rec4 = reinterpret_cast<const float4*>(p.frec + (size_t)b * p.F * MM_REC_FLOATS);
         float g = 0.0f, one_m_all = 0.0f;
         if (BWD) {
-            g = p.gsoft[pg];
+            g = gsoft_at(p, b, (size_t)pix);
             const float soft = p.rgba[(size_t)b * 4 * HW + 3 * HW + pix];
             one_m_all = 1.0f - soft;
             if (g == 0.0f || !(soft > 0.0f)) continue;          // block-uniform
@@ -636,6 +630,29 @@ k_soft_ovf(const mm_raster_params p)
     }
 }
 
+// forward: the overflow pass alone
+__global__ void __launch_bounds__(OVF_THREADS)
+k_soft_ovf_fwd(const mm_raster_params p)
+{
+    mm_pdl_prologue();
+    __shared__ uint32_t s_mask[OVF_MAX_WORDS];
+    __shared__ int s_kept[MM_MAX_KNUM];
+    soft_ovf_role<false>(p, s_mask, s_kept, blockIdx.x, gridDim.x);
+}
+
+// backward: ONE launch for the two independent halves of the soft-silhouette backward -- the first `nlist` CTAs replay the
+// pair list, the rest redo the truncated pixels (both only add into the per-face accumulators)
+__global__ void __launch_bounds__(SB_THREADS)
+k_soft_bwd(const mm_raster_params p, const int nlist)
+{
+    mm_pdl_prologue();
+    __shared__ WarpQ s_wq[SB_THREADS / 32];
+    __shared__ uint32_t s_mask[OVF_MAX_WORDS];
+    __shared__ int s_kept[MM_MAX_KNUM];
+    if ((int)blockIdx.x < nlist) soft_bwd_list_role(p, s_wq, blockIdx.x, nlist);
+    else                         soft_ovf_role<true>(p, s_mask, s_kept, blockIdx.x - nlist, gridDim.x - nlist);
+}
+
 }  // namespace
 
 void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
@@ -644,13 +661,14 @@ void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t
     const int grid = (warps + 7) / 8;
     mm_launch(k_scatter_hard, dim3(grid), dim3(256), 0, s, g_mm_pdl != 0, p);
     { const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW; mm_launch(k_soft_fwd, dim3((nw + SF_WARPS - 1) / SF_WARPS), dim3(32 * SF_WARPS), 0, s, g_mm_pdl != 0, p); }
-    mm_launch(k_soft_ovf<false>, dim3(c->num_sms * 16), dim3(OVF_THREADS), 0, s, g_mm_pdl != 0, p);
+    mm_launch(k_soft_ovf_fwd, dim3(c->num_sms * 16), dim3(OVF_THREADS), 0, s, g_mm_pdl != 0, p);
 }
 
 void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
-    mm_launch(k_soft_bwd_list, dim3(c->num_sms * 8), dim3(256), 0, s, g_mm_pdl != 0, p);
-    mm_launch(k_soft_ovf<true>, dim3(c->num_sms * 16), dim3(OVF_THREADS), 0, s, g_mm_pdl != 0, p);
+    static_assert(SB_THREADS == OVF_THREADS, "the merged backward kernel runs both roles with one CTA shape");
+    const int nlist = c->num_sms * 16, novf = c->num_sms * 8;
+    mm_launch(k_soft_bwd, dim3(nlist + novf), dim3(SB_THREADS), 0, s, g_mm_pdl != 0, p, nlist);
 }
 
 size_t mm_raster_smem_bytes(const mm_ctx* c) { (void)c; return 0; }

@@ -29,9 +29,9 @@ NSETS = 4                     # rotating input/output sets: 4 x ~137 MB > 126 MB
 # events switches programmatic dependent launch off across them, so these figures are a little above what the same
 # kernels cost inside the timed step; they are used for the roofline of the dominant kernel only.
 KERNELS = ["vertex_fwd", "geom_fwd", "shade_fused", "gsoft", "geom_bwd", "vertex_bwd", "tail"]
-# k_vertex_fwd, k_scatter<hard>, k_soft_fwd, k_soft_ovf<fwd>, k_shade_fused, k_gsoft, k_soft_bwd_list,
-# k_soft_ovf<bwd>, k_vertex_bwd (which also finalises the loss); no memset nodes
-LAUNCHES_PER_STEP = 9
+# k_vertex_fwd, k_scatter_hard, k_soft_fwd, k_soft_ovf_fwd, k_shade_fused, k_soft_bwd (pair list + truncated pixels),
+# k_vertex_bwd (which also finalises the loss); no memset nodes (k_gsoft only runs for H or W not a multiple of 4)
+LAUNCHES_PER_STEP = 7
 
 def algorithmic_bytes(B, V, F, H, W, Ht, Wt, bg=True, extra=False):
     """bytes each tensor contributes when touched once per direction (fp32)."""
