@@ -58,6 +58,9 @@ CASES = [
     dict(mesh="sphere", B=2, image_size=64, no_mask=True, contour=0.0, seed=13, dist_range=(6.5, 7.0)),  # knum truncation
     dict(mesh="sphere", B=2, image_size=48, no_mask=True, contour=0.1, seed=15, dist_range=(1.6, 2.0)),  # fills the frame
     dict(mesh="sphere2", B=2, image_size=64, no_mask=True, contour=0.1, seed=17),               # F=5120: records not in smem
+    dict(mesh="sphere", B=2, image_size=22, ratio=1.5, no_mask=True, contour=0.1, seed=19),     # 33x22: scalar (non-float4) rows,
+                                                                                                 # contour through index tables
+    dict(mesh="icosphere", B=2, image_size=30, ratio=1.2, no_mask=False, contour=0.1, seed=21), # 36x30: H % 4 == 0, W % 4 != 0
 ]
 
 
@@ -160,6 +163,37 @@ def test_cfg2_fused_equals_unfused_and_linearity(mm):
     rgb.backward(gx)            # accumulates into Ag grads: loss grad + extra
     for k, gk in names.items():
         assert pu.rel_err(out3[gk], Ag[k].grad) <= 5e-5, k
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(mesh="smpl_uv_642", B=8, image_size=128, ratio=2, init_ellipsoid=2, dist_range=(2.0, 6.0)),     # cfg-4 shape: 256x128, tex 512x128
+    dict(mesh="sphere2", B=4, image_size=256, ratio=1, init_ellipsoid=1, dist_range=(2.0, 7.0), Ht=512, Wt=512),  # cfg-5 shape: F=5120, 256^2, atlas 512^2
+], ids=["cfg4-market-256x128", "cfg5-sphere2-256x256-tex512"])
+def test_large_configs_fused_equals_unfused(mm, cfg):
+    """BASELINE configs[3] / configs[4] shapes: the fused step must reproduce render -> recon_data -> backward."""
+    B, S = cfg["B"], cfg["image_size"]
+    dr = mm.DiffRender(pu.get_mesh(mm, cfg["mesh"]), S, ratio=cfg["ratio"], init_ellipsoid=cfg["init_ellipsoid"], image_weight=1.0)
+    H, W = dr.height, dr.image_size
+    mk = lambda seed: pu.to_device(pu.make_attributes(dr.vertices_init, B, H, W, seed, Ht=cfg.get("Ht"), Wt=cfg.get("Wt"),  # noqa: E731
+                                                      dist_range=cfg["dist_range"]), DEV)
+    A = mk(31)
+    with torch.no_grad():
+        gt, _ = dr.render(no_mask=True, **mk(32))
+    Ag = {k: v.clone().requires_grad_(k != 'delta_vertices') for k, v in A.items()}
+    rgb, _ = dr.render(no_mask=True, **Ag)
+    loss = dr.recon_data(rgb, gt, no_mask=True, contour=0.1)
+    loss.backward()
+    out = dr.render_compare(gt, no_mask=True, contour=0.1, **A)
+    assert torch.equal(out['rgba'], rgb.detach())
+    assert bool(torch.isfinite(out['rgba']).all())
+    assert abs(float(out['loss'][0]) - float(loss)) <= 1e-6 * abs(float(loss))
+    names = dict(vertices='g_vertices', azimuths='g_azimuths', elevations='g_elevations', distances='g_distances',
+                 biases='g_biases', textures='g_textures', lights='g_lights', bg='g_bg')
+    for k, gk in names.items():
+        assert bool(torch.isfinite(out[gk]).all()), k
+        assert pu.rel_err(out[gk], Ag[k].grad) <= 5e-5, k            # same arithmetic, atomics order only
+    cov = (rgb[:, 3] == 1).float().mean().item()
+    assert 0.005 < cov < 0.98
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 32), (3, 30, 22), (2, 160, 96), (1, 7, 5)])
