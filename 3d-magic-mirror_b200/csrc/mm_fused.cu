@@ -308,35 +308,32 @@ k_shade_fused(const mm_raster_params p)
             atomicAdd(ga + 7, gn_scale * dcy);
             atomicAdd(ga + 8, gn_scale * dcz);
         }
-        // hard rasteriser backward (DIBR_SPEC A.3) for the u,v channels
+        // hard rasteriser backward (DIBR_SPEC A.3) for the u,v channels.  Gradients carry a tolerance (unlike the visibility
+        // decisions), so this block is written for instruction count, not for the reference's rounding sequence: the two
+        // channels are folded into A1 = sum_d dLdI_d (c1_d - c0_d), A2 = sum_d dLdI_d (c2_d - c0_d) first, and the
+        // structurally-zero partials are dropped.
         if (g_u != 0.0f || g_v != 0.0f) {
             const float k1 = bar.k1, k2 = bar.k2, k3 = bar.k3;
             const float m = bar.m, pp = bar.p, nn = bar.n, q = bar.q, sb = bar.s, t = bar.t;
-            const float dw1dm = SUB(MUL(0.0f, k3), MUL(q, k1)),   dw1dn = SUB(MUL(-t, k3), MUL(-pp, k1));
-            const float dw1dp = SUB(MUL(0.0f, k3), MUL(-nn, k1)), dw1dq = SUB(MUL(sb, k3), MUL(m, k1));
-            const float dw1ds = SUB(MUL(q, k3), MUL(0.0f, k1)),   dw1dt = SUB(MUL(-nn, k3), MUL(0.0f, k1));
-            const float dw2dm = SUB(MUL(t, k3), MUL(q, k2)),      dw2dn = SUB(MUL(0.0f, k3), MUL(-pp, k2));
-            const float dw2dp = SUB(MUL(-sb, k3), MUL(-nn, k2)),  dw2dq = SUB(MUL(0.0f, k3), MUL(m, k2));
-            const float dw2ds = SUB(MUL(-pp, k3), MUL(0.0f, k2)), dw2dt = SUB(MUL(m, k3), MUL(0.0f, k2));
-            const float dw1dax = -ADD(ADD(dw1dm, dw1dn), dw1ds), dw1day = -ADD(ADD(dw1dp, dw1dq), dw1dt);
-            const float dw2dax = -ADD(ADD(dw2dm, dw2dn), dw2ds), dw2day = -ADD(ADD(dw2dp, dw2dq), dw2dt);
-            const float den = ADD(MUL(k3, k3), p.eps);
-            float gv[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-            #pragma unroll
-            for (int d = 0; d < 2; ++d) {
-                const float gd = d == 0 ? g_u : g_v;
-                const float c0 = uv[d], c1 = uv[2 + d], c2 = uv[4 + d];
-                const float e1 = SUB(c1, c0), e2 = SUB(c2, c0);
-                const float dldI = DIV(MUL(p.multiplier, gd), den);
-                gv[0] += MUL(dldI, ADD(MUL(e1, dw1dax), MUL(e2, dw2dax)));
-                gv[1] += MUL(dldI, ADD(MUL(e1, dw1day), MUL(e2, dw2day)));
-                gv[2] += MUL(dldI, ADD(MUL(e1, dw1dm), MUL(e2, dw2dm)));
-                gv[3] += MUL(dldI, ADD(MUL(e1, dw1dp), MUL(e2, dw2dp)));
-                gv[4] += MUL(dldI, ADD(MUL(e1, dw1dn), MUL(e2, dw2dn)));
-                gv[5] += MUL(dldI, ADD(MUL(e1, dw1dq), MUL(e2, dw2dq)));
-            }
-            #pragma unroll
-            for (int k = 0; k < 6; ++k) atomicAdd(ga + k, gv[k]);
+            const float rden = __fdividef(p.multiplier, k3 * k3 + p.eps);
+            const float A1 = rden * (g_u * (uv[2] - uv[0]) + g_v * (uv[3] - uv[1]));
+            const float A2 = rden * (g_u * (uv[4] - uv[0]) + g_v * (uv[5] - uv[1]));
+            // numerators of dw1/d(.) and dw2/d(.):  w1 = k1/k3, w2 = k2/k3
+            const float d1m = -q * k1,          d2m = t * k3 - q * k2;
+            const float d1n = pp * k1 - t * k3, d2n = pp * k2;
+            const float d1p = nn * k1,          d2p = nn * k2 - sb * k3;
+            const float d1q = sb * k3 - m * k1, d2q = -m * k2;
+            const float d1s = q * k3,           d2s = -pp * k3;
+            const float d1t = -nn * k3,         d2t = m * k3;
+            const float gbx = A1 * d1m + A2 * d2m, gby = A1 * d1p + A2 * d2p;      // d/d(bx), d/d(by)
+            const float gcx = A1 * d1n + A2 * d2n, gcy = A1 * d1q + A2 * d2q;      // d/d(cx), d/d(cy)
+            const float gsx = A1 * d1s + A2 * d2s, gsy = A1 * d1t + A2 * d2t;      // d/d(s), d/d(t)
+            atomicAdd(ga + 0, -(gbx + gcx + gsx));
+            atomicAdd(ga + 1, -(gby + gcy + gsy));
+            atomicAdd(ga + 2, gbx);
+            atomicAdd(ga + 3, gby);
+            atomicAdd(ga + 4, gcx);
+            atomicAdd(ga + 5, gcy);
         }
     }
 
