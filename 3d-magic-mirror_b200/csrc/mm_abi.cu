@@ -155,6 +155,10 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     c->nchunks = 8;
     if (const char* e = getenv("MM_PDL")) g_mm_pdl = atoi(e) != 0;
     if (const char* e = getenv("MM_PLIST_CAP")) c->plist_cap_max = (unsigned)atoi(e);
+    // measured at cfg-2: 0.119 ms/step split vs 0.117 sequential -- both roles are latency-bound and share one register budget
+    // (128/thread from the shading role), so side by side they only trade warps; kept selectable for when shading slims down
+    c->split = 0;
+    if (const char* e = getenv("MM_SPLIT")) c->split = atoi(e) != 0;
     if (const char* e = getenv("MM_VCHUNKS")) { const int v = atoi(e); if (v > 0 && v <= 32) c->nchunks = v; }
     c->chunk_rows = 0;
     c->smem_vertex_fwd = mm_vertex_smem_fwd(c);
@@ -324,23 +328,37 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     set_ws(c, L, ws, p);
     p.tex = tex; p.lights = lights; p.bg = bg; p.gt = gt;
     p.rgba = rgba;
-    if (gtex_side) { p.clr = (uint4*)g_tex; p.nclr = gtex_bytes / 16; }
-    mm_launch_geom_fwd(c, p, s);
-    p.clr = nullptr; p.nclr = 0;
-    if (int r = check_launch("geom_fwd")) return r;
-    if (c->timing) cudaEventRecord(c->ev[2], s);
     p.g_rgba = g_rgba_extra;
     p.image_weight = image_weight; p.contour = contour; p.loss_scale = loss_scale;
     p.analytic_loss = 1;
     p.g_tex = g_tex; p.g_bg = no_mask ? g_bg : nullptr;
-    // H, W multiples of 4: the contour term is tile-local, so k_shade_fused also emits d(loss)/d(silhouette) minus its IoU term,
-    // which the geometry backward adds from the per-image sums on the fly -- no separate pass over the pixels
+    // H, W multiples of 4: the contour term is tile-local, so d(loss)/d(silhouette) minus its IoU term is emitted together with
+    // the alpha plane and the geometry backward adds the IoU term from the per-image sums on the fly
     p.gsoft_iou_pending = ((c->H & 3) == 0 && (c->W & 3) == 0) ? 1 : 0;
-    mm_launch_shade_fused(c, p, s);           // shading forward + loss sums + the whole RGB-side backward
-    if (int r = check_launch("shade_fused")) return r;
-    if (c->timing) cudaEventRecord(c->ev[3], s);
+    if (gtex_side) { p.clr = (uint4*)g_tex; p.nclr = gtex_bytes / 16; }
+    if (c->split) {
+        // hard pass | soft forward || RGB shading fwd+bwd (one launch) | overflow pass | final silhouette (alpha, IoU sums, gsoft)
+        mm_launch_hard(c, p, s);
+        p.clr = nullptr; p.nclr = 0;
+        if (int r = check_launch("hard")) return r;
+        if (c->timing) cudaEventRecord(c->ev[2], s);
+        mm_launch_soft_shade(c, p, s);
+        if (int r = check_launch("soft_shade")) return r;
+        if (c->timing) cudaEventRecord(c->ev[3], s);
+        mm_launch_soft_ovf_fwd(c, p, s);
+        mm_launch_alpha(c, p, s);
+        if (int r = check_launch("alpha")) return r;
+    } else {
+        mm_launch_geom_fwd(c, p, s);
+        p.clr = nullptr; p.nclr = 0;
+        if (int r = check_launch("geom_fwd")) return r;
+        if (c->timing) cudaEventRecord(c->ev[2], s);
+        mm_launch_shade_fused(c, p, s);           // shading forward + loss sums + the whole RGB-side backward
+        if (int r = check_launch("shade_fused")) return r;
+        if (c->timing) cudaEventRecord(c->ev[3], s);
+    }
     if (!p.gsoft_iou_pending) {
-        mm_launch_gsoft(c, p, s);             // general sizes: d(loss)/d(silhouette) in its own pass (index tables)
+        mm_launch_gsoft(c, p, s);                 // general sizes: d(loss)/d(silhouette) in its own pass (index tables)
         if (int r = check_launch("gsoft")) return r;
     }
     if (c->timing) cudaEventRecord(c->ev[4], s);

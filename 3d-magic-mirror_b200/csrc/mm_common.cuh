@@ -68,6 +68,7 @@ struct mm_ctx {
     size_t smem_vertex_fwd;  // dynamic smem bytes of the vertex forward kernel
     size_t smem_raster;      // dynamic smem bytes of the raster kernels (per-lane soft candidate lists)
     int num_sms;
+    int split;               // fused step: 1 = soft pass and RGB shading in one launch + k_alpha (MM_SPLIT=1), 0 = sequential (default)
     unsigned plist_cap_max;  // test hook (MM_PLIST_CAP): caps the forward's pair list so that the backward's fallback path runs
     // device arrays
     int32_t* d_faces;        // [F,3]
@@ -200,6 +201,10 @@ void mm_launch_shade_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_l
 void mm_launch_shade_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 void mm_launch_shade_fused(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 void mm_launch_gsoft(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
+void mm_launch_soft_shade(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
+void mm_launch_alpha(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
+void mm_launch_hard(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
+void mm_launch_soft_ovf_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 void mm_launch_loss_finalize(const mm_ctx* c, int B, const long long* img_fwd, long long* img_bwd,
                              float image_weight, float contour, float* loss, float* iou_out, cudaStream_t s);
 void mm_launch_image_reduce(const mm_ctx* c, int B, int np, const float* part_fwd, long long* img_fwd, cudaStream_t s);

@@ -12,10 +12,13 @@
 //                   optional upstream gradient) and the contour loss sum.  Reads 2-3 planes, writes one.
 // The geometry backward (mm_raster.cu) then consumes `gsoft` exactly as in the unfused path.
 #include "mm_device.cuh"
+#include "mm_soft_fwd.cuh"
 
 namespace {
 
+#ifndef FULL
 #define FULL 0xffffffffu
+#endif
 #define FT_W 16           // tile of one warp: 16 x 8 pixels, lane = (ly = lane >> 2, lx = lane & 3), 4 pixels per lane
 #define FT_H 8
 
@@ -65,15 +68,21 @@ __device__ __forceinline__ void store4(float* __restrict__ p, int n, const float
 #define FUSED_THREADS (32 * FUSED_WARPS)
 #define FUSED_TILE_PX (FT_W * FT_H)
 
-template <bool VEC, bool HAS_GUP>
-__global__ void __launch_bounds__(FUSED_THREADS, FUSED_MINB)
-k_shade_fused(const mm_raster_params p)
+struct ShadeSmem {
+    float lights[16];
+    uint32_t list[FUSED_WARPS * FUSED_TILE_PX];      // face << 10 | warp << 7 | lane << 2 | j   (F <= 65535, <= 8 warps)
+    int count;
+};
+
+// SPLIT: the silhouette is not final yet (the soft pass runs concurrently, in the same launch): the alpha plane, the IoU sums
+// and d(loss)/d(silhouette) are left to k_alpha; everything RGB-side is done here.
+template <bool VEC, bool HAS_GUP, bool SPLIT>
+__device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, ShadeSmem& sm, const int bx, const int b)
 {
-    mm_pdl_prologue();
-    __shared__ float s_lights[16];
-    __shared__ uint32_t s_list[FUSED_WARPS * FUSED_TILE_PX];      // face << 10 | warp << 7 | lane << 2 | j   (F <= 65535, <= 8 warps)
-    __shared__ int s_count;
-    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* s_lights = sm.lights;
+    uint32_t* s_list = sm.list;
+    int& s_count = sm.count;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
@@ -86,7 +95,7 @@ k_shade_fused(const mm_raster_params p)
 
     float acc_l1 = 0.0f, acc_n = 0.0f, acc_d = 0.0f, acc_gc = 0.0f, acc_c = 0.0f;
     {
-        const int tile = blockIdx.x * FUSED_WARPS + warp;
+        const int tile = bx * FUSED_WARPS + warp;
         const int ty = tile / ntx, tx = tile - ty * ntx;
         const int iy = ty * FT_H + (lane >> 2), ix0 = tx * FT_W + (lane & 3) * 4;
         const int n = (iy < H) ? min(4, W - ix0) : 0;             // valid pixels of this lane (<= 0: none)
@@ -99,20 +108,22 @@ k_shade_fused(const mm_raster_params p)
             {
                 const unsigned long long* zb = p.zbuf + (size_t)b * HW + pix0;
                 const unsigned long long* la = p.lacc + (size_t)b * HW + pix0;
-                unsigned long long z[4], l[4];
+                unsigned long long z[4], l[4] = {0ull, 0ull, 0ull, 0ull};
                 if (VEC) {
                     const ulonglong2 z0 = *reinterpret_cast<const ulonglong2*>(zb), z1 = *reinterpret_cast<const ulonglong2*>(zb + 2);
-                    const ulonglong2 l0 = *reinterpret_cast<const ulonglong2*>(la), l1 = *reinterpret_cast<const ulonglong2*>(la + 2);
                     z[0] = z0.x; z[1] = z0.y; z[2] = z1.x; z[3] = z1.y;
-                    l[0] = l0.x; l[1] = l0.y; l[2] = l1.x; l[3] = l1.y;
+                    if (!SPLIT) {
+                        const ulonglong2 l0 = *reinterpret_cast<const ulonglong2*>(la), l1 = *reinterpret_cast<const ulonglong2*>(la + 2);
+                        l[0] = l0.x; l[1] = l0.y; l[2] = l1.x; l[3] = l1.y;
+                    }
                 } else {
                     #pragma unroll
-                    for (int j = 0; j < 4; ++j) { z[j] = (j < n) ? zb[j] : 0ull; l[j] = (j < n) ? la[j] : 0ull; }
+                    for (int j = 0; j < 4; ++j) { z[j] = (j < n) ? zb[j] : 0ull; if (!SPLIT) l[j] = (j < n) ? la[j] : 0ull; }
                 }
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     face[j] = (j < n) ? key_face(z[j]) : -1;
-                    soft[j] = (face[j] >= 0) ? 1.0f : lacc_soft(l[j]);
+                    if (!SPLIT) soft[j] = (face[j] >= 0) ? 1.0f : lacc_soft(l[j]);
                 }
             }
             float bgv[3][4], gtv[4][4], gup[3][4];
@@ -126,7 +137,7 @@ k_shade_fused(const mm_raster_params p)
                 if (HAS_GUP) load4<VEC>(p.g_rgba + ((size_t)b * 4 + ch) * HW + pix0, n, gup[ch]);
                 else { gup[ch][0] = gup[ch][1] = gup[ch][2] = gup[ch][3] = 0.0f; }
             }
-            if (HAS_GUP) load4<VEC>(p.g_rgba + ((size_t)b * 4 + 3) * HW + pix0, n, gs);      // upstream d/d(silhouette)
+            if (HAS_GUP && !SPLIT) load4<VEC>(p.g_rgba + ((size_t)b * 4 + 3) * HW + pix0, n, gs);      // upstream d/d(silhouette)
             #pragma unroll
             for (int j = 0; j < 4; ++j) gmv[j] = gtv[3][j];
             float img[3][4], gbg[3][4];
@@ -149,7 +160,7 @@ k_shade_fused(const mm_raster_params p)
                     if (p.no_mask) g_coef += g * bgv[ch][j];
                 }
                 if (is_bg && j < n) acc_gc += g_coef;
-                if (j < n) {                                   // IoU partial sums (kaolin mask_iou)
+                if (!SPLIT && j < n) {                         // IoU partial sums (kaolin mask_iou)
                     const float mul = soft[j] * gm;
                     acc_n += mul;
                     acc_d += (soft[j] + gm) - mul;
@@ -159,7 +170,7 @@ k_shade_fused(const mm_raster_params p)
             float* out = p.rgba + (size_t)b * 4 * HW + pix0;
             #pragma unroll
             for (int ch = 0; ch < 3; ++ch) store4<VEC>(out + ch * HW, n, img[ch]);
-            store4<VEC>(out + 3 * HW, n, soft);
+            if (!SPLIT) store4<VEC>(out + 3 * HW, n, soft);
             if (p.g_bg) {
                 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) store4<VEC>(p.g_bg + ((size_t)b * 3 + ch) * HW + pix0, n, gbg[ch]);
@@ -168,7 +179,7 @@ k_shade_fused(const mm_raster_params p)
         // ---- tile-local part of d(loss)/d(silhouette): upstream + contour term (DIBR_SPEC A.7).  H and W are multiples of 4 here,
         // so the 16x8 tile holds whole 4x4 contour blocks: a block = lanes differing in lane bits 2,3 (4 rows) with the same
         // lx; its reference pixel is pixel 0 of the lane with (ly & 3) == 0.  The IoU term is added by the consumers (gsoft_at).
-        if (p.gsoft_iou_pending) {
+        if (!SPLIT && p.gsoft_iou_pending) {
             if (p.contour > 0.0f) {
                 const float k_cont = p.loss_scale * p.contour / ((float)p.B * (float)HW);
                 const int ref_lane = lane & ~12;
@@ -205,7 +216,11 @@ k_shade_fused(const mm_raster_params p)
     __syncthreads();
 
     // ---- pass 2: the CTA's covered pixels, one per lane
+#ifdef EXP_NO_HEAVY
+    const int count = 0;
+#else
     const int count = s_count;
+#endif
     float acc_l[9];
     #pragma unroll
     for (int i = 0; i < 9; ++i) acc_l[i] = 0.0f;
@@ -218,27 +233,44 @@ k_shade_fused(const mm_raster_params p)
     for (int i = threadIdx.x; i < count; i += FUSED_THREADS) {
         const uint32_t e = s_list[i];
         const int f = (int)(e >> 10);
-        const int tile = blockIdx.x * FUSED_WARPS + (int)((e >> 7) & 7u);
+        const int tile = bx * FUSED_WARPS + (int)((e >> 7) & 7u);
         const int el = (int)((e >> 2) & 31u);
         const int ty = tile / ntx, tx = tile - ty * ntx;
         const int iy = ty * FT_H + (el >> 2), ix = tx * FT_W + (el & 3) * 4 + (int)(e & 3u);
         const size_t pix = (size_t)iy * W + ix;
         const float* gtb = p.gt + (size_t)b * 4 * HW + pix;
+#ifdef EXP_NO_PIXLD
+        const float gm = 0.5f + 1e-9f * (float)pix;
+#else
         const float gm = __ldg(gtb + 3 * HW);
+#endif
         float bgj[3], gtj[3], guj[3];
         #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
+#ifdef EXP_NO_PIXLD
+            gtj[ch] = 0.25f * ch + 1e-9f * (float)pix; bgj[ch] = 0.3f * ch + 1e-9f * (float)pix;
+#else
             gtj[ch] = __ldg(gtb + ch * HW);
             bgj[ch] = p.no_mask ? __ldg(p.bg + ((size_t)b * 3 + ch) * HW + pix) : 0.0f;
+#endif
             guj[ch] = HAS_GUP ? __ldg(p.g_rgba + ((size_t)b * 4 + ch) * HW + pix) : 0.0f;
         }
+#ifdef EXP_NO_RECLD
+        FaceRec r; r.ax = 10.f * f; r.ay = 3.f * f; r.bx = r.ax + 40.f; r.by = r.ay + 3.f; r.cx = r.ax + 5.f; r.cy = r.ay + 45.f;
+        r.az = r.bz = r.cz = -3.f; r.nx = 0.1f; r.ny = 0.2f; r.nz = 0.97f;
+#else
         const FaceRec r = load_rec(rec, f);
+#endif
         Bary bar;
         bary_eval(r, pix_x(ix, W, p.sx), pix_y(iy, H, p.sy), p.eps, bar);
         float uv[6];
         const float* uvp = p.face_uvs + f * 6;
         #pragma unroll
+#ifdef EXP_NO_RECLD
+        for (int k = 0; k < 6; ++k) uv[k] = 0.1f * k + 1e-6f * f;
+#else
         for (int k = 0; k < 6; ++k) uv[k] = __ldg(uvp + k);
+#endif
         const float u = interp3(bar.w0, bar.w1, bar.w2, uv[0], uv[2], uv[4]);
         const float v = interp3(bar.w0, bar.w1, bar.w2, uv[1], uv[3], uv[5]);
         const float tm = ADD(ADD(bar.w0, bar.w1), bar.w2);
@@ -251,7 +283,11 @@ k_shade_fused(const mm_raster_params p)
         float tcol[3];
         #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
+#ifdef EXP_NO_TEXLD
+            tf[ch].nw = bl.nw + ch; tf[ch].ne = bl.ne; tf[ch].sw = bl.sw * 0.5f; tf[ch].se = bl.se + 0.1f;
+#else
             tf[ch] = tex_fetch(tb + (size_t)ch * p.Ht * p.Wt, bl, p.Ht, p.Wt);
+#endif
             tcol[ch] = tex_blend(tf[ch], bl);
         }
         float bnd[9];
@@ -263,13 +299,21 @@ k_shade_fused(const mm_raster_params p)
         for (int ch = 0; ch < 3; ++ch) {
             const float pre = composite_pre(p.no_mask, tcol[ch], tm, bgj[ch], coef);
             const float val = clamp01(pre);
+#ifndef EXP_NO_PIXST
             out[ch * HW] = val;
+#else
+            if (val == 12345.f) out[ch * HW] = val;
+#endif
             const float lt = l1_term(val, gtj[ch], gm);
             acc_l1 += fabsf(lt);
             float g = guj[ch] + k_img * sgnf(lt) * gm;
             g = (pre >= 0.0f && pre <= 1.0f) ? g : 0.0f;                     // torch.clamp backward
             g_tcol[ch] = g * tm * coef;
+#ifndef EXP_NO_PIXST
             if (p.g_bg) p.g_bg[((size_t)b * 3 + ch) * HW + pix] = g * (1.0f - tm) * coef;
+#else
+            if (g == 12345.f) p.g_bg[((size_t)b * 3 + ch) * HW + pix] = g * (1.0f - tm) * coef;
+#endif
             g_coef += p.no_mask ? g * (tcol[ch] * tm + bgj[ch] * (1.0f - tm)) : g * (tcol[ch] * tm);
         }
         #pragma unroll
@@ -282,7 +326,11 @@ k_shade_fused(const mm_raster_params p)
         #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
             const float g = g_tcol[ch];
+#ifdef EXP_NO_ATOM
+            if (g == 12345.0f) {
+#else
             if (g != 0.0f) {
+#endif
                 float* gp = gtex + ((size_t)ch * p.Ht + bl.iy) * p.Wt + bl.ix;
                 atomicAdd(gp, g * bl.nw);
                 if (xe) atomicAdd(gp + 1, g * bl.ne);
@@ -303,7 +351,11 @@ k_shade_fused(const mm_raster_params p)
         const float dcz = l[2] * SH_C1 + l[5] * SH_C2 * ny + l[6] * SH_C3 * 2.0f * nz + l[7] * SH_C4 * nx;
         float* ga = gacc + (size_t)f * 9;
         const float gn_scale = g_coef * tm;
+#ifdef EXP_NO_ATOM
+        if (gn_scale == 12345.0f) {
+#else
         if (gn_scale != 0.0f) {
+#endif
             atomicAdd(ga + 6, gn_scale * dcx);
             atomicAdd(ga + 7, gn_scale * dcy);
             atomicAdd(ga + 8, gn_scale * dcz);
@@ -312,7 +364,11 @@ k_shade_fused(const mm_raster_params p)
         // decisions), so this block is written for instruction count, not for the reference's rounding sequence: the two
         // channels are folded into A1 = sum_d dLdI_d (c1_d - c0_d), A2 = sum_d dLdI_d (c2_d - c0_d) first, and the
         // structurally-zero partials are dropped.
+#ifdef EXP_NO_ATOM
+        if (g_u == 12345.0f) {
+#else
         if (g_u != 0.0f || g_v != 0.0f) {
+#endif
             const float k1 = bar.k1, k2 = bar.k2, k3 = bar.k3;
             const float m = bar.m, pp = bar.p, nn = bar.n, q = bar.q, sb = bar.s, t = bar.t;
             const float rden = __fdividef(p.multiplier, k3 * k3 + p.eps);
@@ -341,7 +397,7 @@ k_shade_fused(const mm_raster_params p)
     acc_l[0] += acc_gc * SH_C0;                  // background pixels: bands = (C0, 0, .., -C3B, 0, 0)
     acc_l[6] += acc_gc * (-SH_C3B);
     const float s0 = warp_sum(acc_l1), s1 = warp_sum(acc_n), s2 = warp_sum(acc_d);
-    if (p.gsoft_iou_pending && p.contour > 0.0f) {
+    if (!SPLIT && p.gsoft_iou_pending && p.contour > 0.0f) {
         const float s3 = warp_sum(acc_c);
         if (lane == 0 && s3 != 0.0f) fx_add(p.img_bwd + b * 12, s3, MM_FX_LOSS);
     }
@@ -356,6 +412,125 @@ k_shade_fused(const mm_raster_params p)
             const float si = warp_sum(acc_l[i]);
             if (lane == 0 && si != 0.0f) fx_add(p.img_bwd + b * 12 + 1 + i, si, MM_FX_GRAD);
         }
+    }
+}
+
+// stand-alone fused shading (the silhouette is final: runs after the soft pass)
+template <bool VEC, bool HAS_GUP>
+__global__ void __launch_bounds__(FUSED_THREADS, FUSED_MINB)
+k_shade_fused(const mm_raster_params p)
+{
+    mm_pdl_prologue();
+    __shared__ ShadeSmem sm;
+    shade_fused_role<VEC, HAS_GUP, false>(p, sm, blockIdx.x, blockIdx.y);
+}
+
+// ---------------------------------------------------------------------------------------------- soft pass || shading, one launch
+// After the hard pass the soft-silhouette forward (latency-bound, ~40 % of the warp slots busy) and the RGB side of the shading
+// (latency-bound too) are independent: both only need the visibility buffer.  One launch runs them side by side -- CTAs are
+// dealt to the two roles interleaved in proportion (the block scheduler hands out CTAs in index order), so each SM holds a mix
+// and the idle issue slots of one role are filled by the other.  What needs the FINAL silhouette moves to k_alpha.
+#ifndef MERGED_MINB
+#define MERGED_MINB 4
+#endif
+template <bool VEC, bool HAS_GUP>
+__global__ void __launch_bounds__(FUSED_THREADS, MERGED_MINB)
+k_soft_shade(const mm_raster_params p, const int nshade, const int nshade_x, const int nsoft)
+{
+    mm_pdl_prologue();
+    __shared__ union { ShadeSmem shade; SoftQ soft[SF_WARPS]; } sm;
+    static_assert(FUSED_THREADS == 32 * SF_WARPS, "both roles share one CTA shape");
+    // role of CTA i: shade iff floor((i+1) * nshade / total) > floor(i * nshade / total); its index in the role = that floor
+    const unsigned long long total = (unsigned long long)nshade + (unsigned long long)nsoft;
+    const unsigned long long i = blockIdx.x;
+    const int s0 = (int)((i * (unsigned long long)nshade) / total), s1 = (int)(((i + 1) * (unsigned long long)nshade) / total);
+    if (s1 > s0) {
+        const int b = s0 / nshade_x;
+        shade_fused_role<VEC, HAS_GUP, true>(p, sm.shade, s0 - b * nshade_x, b);
+    } else {
+        const int vblock = (int)i - s0;                       // soft CTAs before this one
+        soft_fwd_role(p, sm.soft[threadIdx.x >> 5], vblock * SF_WARPS + (int)(threadIdx.x >> 5));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- final silhouette
+// Runs after the soft pass (and its overflow pass): alpha plane of the output, IoU partial sums (kaolin mask_iou), and -- when
+// H and W are multiples of 4 (FAST4: the contour term's 4x4 blocks are then aligned) -- the contour loss sum and the tile-local
+// part of d(loss)/d(silhouette) (upstream + contour; the IoU term is added by the consumers, gsoft_at).
+template <bool FAST4>
+__global__ void __launch_bounds__(128)
+k_alpha(const mm_raster_params p)
+{
+    mm_pdl_prologue();
+    const int b = blockIdx.y;
+    const int H = p.H, W = p.W;
+    const size_t HW = (size_t)H * W;
+    const unsigned long long* la = p.lacc + (size_t)b * HW;
+    const uint32_t* covb = p.cov + (size_t)b * H * p.covw;
+    const float* gmask = p.gt + (size_t)b * 4 * HW + 3 * HW;
+    float* alpha = p.rgba + (size_t)b * 4 * HW + 3 * HW;
+    float acc_n = 0.0f, acc_d = 0.0f, acc_c = 0.0f;
+    if (FAST4) {
+        const float* gup = p.g_rgba ? p.g_rgba + (size_t)b * 4 * HW + 3 * HW : nullptr;
+        const int W4 = W >> 2;
+        const int t = blockIdx.x * blockDim.x + threadIdx.x;         // (4x4 block, row-in-block): 4 consecutive lanes = one block
+        const int blk = t >> 2, r = t & 3;
+        const bool active = blk < (H >> 2) * W4;
+        const int by = blk / W4, bx = blk - by * W4;
+        const int iy = by * 4 + r, ix0 = bx * 4;
+        const size_t pix0 = active ? (size_t)iy * W + ix0 : 0;
+        float m[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0}, out[4] = {0, 0, 0, 0};
+        if (active) {
+            const ulonglong2 l0 = *reinterpret_cast<const ulonglong2*>(la + pix0), l1 = *reinterpret_cast<const ulonglong2*>(la + pix0 + 2);
+            const uint32_t cw = __ldg(covb + (size_t)iy * p.covw + (ix0 >> 5)) >> (ix0 & 31);
+            load4<true>(gmask + pix0, 4, g);
+            if (gup) load4<true>(gup + pix0, 4, out);
+            const unsigned long long l[4] = {l0.x, l0.y, l1.x, l1.y};
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                m[j] = ((cw >> j) & 1u) ? 1.0f : lacc_soft(l[j]);
+                const float mul = m[j] * g[j];
+                acc_n += mul;
+                acc_d += (m[j] + g[j]) - mul;
+            }
+            store4<true>(alpha + pix0, 4, m);
+        }
+        if (p.contour > 0.0f) {
+            const float k_cont = p.loss_scale * p.contour / ((float)p.B * (float)HW);
+            const int ref_lane = threadIdx.x & 28;                    // lane of row 0 of this block (warp-relative)
+            const float mref = __shfl_sync(FULL, m[0], ref_lane), gref = __shfl_sync(FULL, g[0], ref_lane);
+            float tsum = 0.0f;
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float dlt = fabsf(m[j] - mref) - fabsf(g[j] - gref);
+                acc_c += dlt * dlt;                                   // inactive lanes hold zeros
+                const float own = 2.0f * dlt * sgnf(m[j] - mref);
+                out[j] += k_cont * own;
+                tsum -= own;                                          // what this pixel contributes to its reference pixel
+            }
+            tsum += __shfl_xor_sync(FULL, tsum, 1);
+            tsum += __shfl_xor_sync(FULL, tsum, 2);
+            if (r == 0) out[0] += k_cont * tsum;
+        }
+        if (active) store4<true>(p.gsoft + (size_t)b * HW + pix0, 4, out);
+    } else {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < H * W) {
+            const int iy = i / W, ix = i - iy * W;
+            const bool covered = (__ldg(covb + (size_t)iy * p.covw + (ix >> 5)) >> (ix & 31)) & 1u;
+            const float m = covered ? 1.0f : lacc_soft(la[i]);
+            const float gm = gmask[i];
+            alpha[i] = m;
+            const float mul = m * gm;
+            acc_n += mul;
+            acc_d += (m + gm) - mul;
+        }
+    }
+    const float s1 = warp_sum(acc_n), s2 = warp_sum(acc_d), s3 = warp_sum(acc_c);
+    if ((threadIdx.x & 31) == 0) {
+        if (s1 != 0.0f) fx_add(p.img_fwd + b * 4 + 1, s1, MM_FX_LOSS);
+        if (s2 != 0.0f) fx_add(p.img_fwd + b * 4 + 2, s2, MM_FX_LOSS);
+        if (FAST4 && s3 != 0.0f) fx_add(p.img_bwd + b * 12, s3, MM_FX_LOSS);
     }
 }
 
@@ -466,6 +641,31 @@ void mm_launch_shade_fused(const mm_ctx* c, const mm_raster_params& p, cudaStrea
     void (*k)(mm_raster_params) = vec ? (gup ? k_shade_fused<true, true> : k_shade_fused<true, false>)
                                       : (gup ? k_shade_fused<false, true> : k_shade_fused<false, false>);
     mm_launch(k, grid, dim3(FUSED_THREADS), 0, s, g_mm_pdl != 0, p);
+}
+
+// soft-silhouette forward and RGB-side shading side by side (see k_soft_shade)
+void mm_launch_soft_shade(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
+{
+    const int ntiles = ((p.W + FT_W - 1) / FT_W) * ((p.H + FT_H - 1) / FT_H);
+    const int nshade_x = (ntiles + FUSED_WARPS - 1) / FUSED_WARPS;
+    const int nshade = nshade_x * p.B;
+    const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW;
+    const int nsoft = (nw + SF_WARPS - 1) / SF_WARPS;
+    const bool vec = (p.W & 3) == 0, gup = p.g_rgba != nullptr;
+    void (*k)(mm_raster_params, int, int, int) = vec ? (gup ? k_soft_shade<true, true> : k_soft_shade<true, false>)
+                                                     : (gup ? k_soft_shade<false, true> : k_soft_shade<false, false>);
+    mm_launch(k, dim3(nshade + nsoft), dim3(FUSED_THREADS), 0, s, g_mm_pdl != 0, p, nshade, nshade_x, nsoft);
+}
+
+void mm_launch_alpha(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
+{
+    (void)c;
+    if ((p.W & 3) == 0 && (p.H & 3) == 0) {
+        const int threads = (p.H >> 2) * (p.W >> 2) * 4;
+        mm_launch(k_alpha<true>, dim3((threads + 127) / 128, p.B), dim3(128), 0, s, g_mm_pdl != 0, p);
+    } else {
+        mm_launch(k_alpha<false>, dim3((p.H * p.W + 127) / 128, p.B), dim3(128), 0, s, g_mm_pdl != 0, p);
+    }
 }
 
 void mm_launch_gsoft(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)

@@ -25,53 +25,9 @@
 //   Backward re-derives every probability from the face records instead of storing Kaolin's knum-deep side buffers
 //   (B*H*W*30*(4+8+1) B = 307 MB at B=48,128^2).
 #include "mm_device.cuh"
+#include "mm_soft_fwd.cuh"
 
 namespace {
-
-#define FULL 0xffffffffu
-
-struct PixRange { int ix0, ix1, iy0, iy1; };
-
-// Conservative pixel-index range, clipped to the image, of the scaled-NDC box [xl,xh) x [yl,yh)
-// (the exact half-open tests are redone per pixel).  Returns false if empty.
-__device__ __forceinline__ bool pix_range(const mm_raster_params& p, float xl, float xh, float yl, float yh, PixRange& r)
-{
-    const float inv_sx = 1.0f / p.sx, inv_sy = 1.0f / p.sy;
-    float fx_lo = (xl * inv_sx + (float)(p.W - 1)) * 0.5f;
-    float fx_hi = (xh * inv_sx + (float)(p.W - 1)) * 0.5f;
-    float fy_lo = ((float)(p.H - 1) - yh * inv_sy) * 0.5f;
-    float fy_hi = ((float)(p.H - 1) - yl * inv_sy) * 0.5f;
-    // NaN/Inf coordinates (vertex on the camera plane) stay conservative: treat as "everywhere"
-    if (!(fx_lo == fx_lo) || !(fx_hi == fx_hi)) { fx_lo = -4.0f; fx_hi = 1.0e6f; }
-    if (!(fy_lo == fy_lo) || !(fy_hi == fy_hi)) { fy_lo = -4.0f; fy_hi = 1.0e6f; }
-    fx_lo = fminf(fmaxf(fx_lo, -4.0f), 1.0e6f); fx_hi = fminf(fmaxf(fx_hi, -4.0f), 1.0e6f);
-    fy_lo = fminf(fmaxf(fy_lo, -4.0f), 1.0e6f); fy_hi = fminf(fmaxf(fy_hi, -4.0f), 1.0e6f);
-    r.ix0 = max((int)floorf(fx_lo), 0);
-    r.ix1 = min((int)ceilf(fx_hi), p.W - 1);
-    r.iy0 = max((int)floorf(fy_lo), 0);
-    r.iy1 = min((int)ceilf(fy_hi), p.H - 1);
-    return r.ix0 <= r.ix1 && r.iy0 <= r.iy1;
-}
-
-// EXACT pixel rectangle of a face's bbox (tight, or enlarged by boxlen: DIBR_SPEC A.4) under the reference's half-open
-// fp32 test  xmin <= px < xmax, ymin <= py < ymax: conservative float->int estimate, then <= 2 correction steps per side
-// with the very comparison the reference uses (pixel centres are monotone in the index, so the exact set is a rectangle).
-__device__ __forceinline__ void exact_rect(const mm_raster_params& p, const FaceRec& r, bool enlarged,
-                                           int& ix0, int& ix1, int& iy0, int& iy1)
-{
-    float xmin = fminf(fminf(r.ax, r.bx), r.cx), xmax = fmaxf(fmaxf(r.ax, r.bx), r.cx);
-    float ymin = fminf(fminf(r.ay, r.by), r.cy), ymax = fmaxf(fmaxf(r.ay, r.by), r.cy);
-    if (enlarged) { xmin = SUB(xmin, p.blen); xmax = ADD(xmax, p.blen); ymin = SUB(ymin, p.blen); ymax = ADD(ymax, p.blen); }
-    PixRange pr;
-    ix0 = 0; ix1 = -1; iy0 = 0; iy1 = -1;
-    if (pix_range(p, xmin, xmax, ymin, ymax, pr)) {
-        ix0 = pr.ix0; ix1 = pr.ix1; iy0 = pr.iy0; iy1 = pr.iy1;
-        while (ix0 <= ix1 && pix_x(ix0, p.W, p.sx) < xmin) ++ix0;
-        while (ix1 >= ix0 && pix_x(ix1, p.W, p.sx) >= xmax) --ix1;
-        while (iy0 <= iy1 && pix_y(iy0, p.H, p.sy) >= ymax) ++iy0;      // y decreases with the row index
-        while (iy1 >= iy0 && pix_y(iy1, p.H, p.sy) < ymin) --iy1;
-    }
-}
 
 // ---------------------------------------------------------------------------------------------- the scatter engine
 // A warp owns FPW = 8 consecutive faces.  Set-up (8 lanes): load the record, compute the bbox (tight / enlarged) and
@@ -324,140 +280,14 @@ k_scatter_hard(const mm_raster_params p)
 }
 
 // ---------------------------------------------------------------------------------------------- soft pass forward
-// The candidates of the soft pass are the UNCOVERED pixels inside a face's enlarged bbox -- for most faces (the interior of
-// the object) there are none.  The pair engine above found that out with one 8-byte zbuf load + ~50 bookkeeping
-// instructions PER BBOX PIXEL (ncu r1c: 65 % of the kernel's 18.8 M warp-instructions).  Here every lane owns one face and
-// walks the rows of its rectangle against the coverage bitmap the hard pass left behind: one 32-bit word per (row, 32-pixel
-// column block) tells which of its pixels are uncovered.  The set bits become queue entries (warp scan + per-lane bit
-// loop); whenever 32 are waiting the whole warp evaluates them, one candidate per lane, exactly as before.
-#define SF_QCAP (1024 + 64)
-
-struct SoftQ {
-    uint32_t q[SF_QCAP];     // pending candidates: slot << 24 | iy << 12 | ix
-    float rec[6][8];         // the warp's 8 faces: image-plane corners
-    int img[8];
-    int face[8];
-};
-
-__device__ __forceinline__ void soft_fwd_eval(const mm_raster_params& p, const SoftQ& wq, uint32_t e, float kz)
-{
-    const int slot = (int)(e >> 24), iy = (int)((e >> 12) & 0xfffu), ix = (int)(e & 0xfffu);
-    const size_t pg = (size_t)wq.img[slot] * p.H * p.W + (size_t)iy * p.W + ix;
-    FaceRec r;
-    r.ax = wq.rec[0][slot]; r.ay = wq.rec[1][slot]; r.bx = wq.rec[2][slot]; r.by = wq.rec[3][slot];
-    r.cx = wq.rec[4][slot]; r.cy = wq.rec[5][slot];
-    r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
-    int type;
-    const float d2 = soft_d2_fast(r, pix_x(ix, p.W, p.sx), pix_y(iy, p.H, p.sy), p.multiplier, type);
-    const float prob = soft_prob_fast(d2, kz);
-    const unsigned long long old = atomicAdd(p.lacc + pg, lacc_term(log1pf(-prob)));
-    if (lacc_count(old) == p.knum) {                            // candidate knum+1: the pixel needs the ordered pass
-        const uint32_t s2 = atomicAdd(p.ovf_count, 1u);
-        p.ovf_list[s2] = (uint32_t)pg;
-    }
-}
-
-// append the candidates this warp just evaluated to the global pair list (one atomicAdd per batch); all lanes call it
-__device__ __forceinline__ void soft_fwd_record(const mm_raster_params& p, const SoftQ& wq, uint32_t e, int n, int lane)
-{
-    uint32_t base = 0u;
-    if (lane == 0) base = atomicAdd(p.ovf_count + 1, (uint32_t)n);
-    base = __shfl_sync(FULL, base, 0);
-    if (lane < n && base + (uint32_t)lane < p.plist_cap) {
-        const int slot = (int)(e >> 24);
-        const unsigned long long fg = (unsigned long long)((size_t)wq.img[slot] * p.F + wq.face[slot]);
-        p.plist[base + lane] = (fg << 32) | (unsigned long long)(e & 0xffffffu);
-    }
-}
-
-#define SF_WARPS 4
-#define SF_FPW 8             // faces per warp: 4 lanes share a face and take its (row, column-block) segments round-robin, so the
-                             // dependent chain of bitmap loads per warp is 4x shorter and there are 4x more warps to overlap it
+// (engine in mm_soft_fwd.cuh, shared with the fused step's merged soft + shading kernel)
 __global__ void __launch_bounds__(32 * SF_WARPS)
 k_soft_fwd(const mm_raster_params p)
 {
     mm_pdl_prologue();
     __shared__ SoftQ s_wq[SF_WARPS];
-    const int lane = threadIdx.x & 31;
-    SoftQ& wq = s_wq[threadIdx.x >> 5];
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (p.B * p.F + SF_FPW - 1) / SF_FPW;
-    if (gwarp >= nwarps) return;
-    const float kz = p.sigmainv / p.multiplier / p.multiplier;
-
-    // ---- set-up: lane = (slot, sub); faces dealt with a stride of the warp count (a warp mixes 8 images: balanced)
-    const int slot = lane >> 2, sub = lane & 3;
-    const int fid = slot * nwarps + gwarp;
-    int ix0 = 0, ix1 = -1, iy0 = 0, iy1 = -1, b = 0;
-    if (fid < p.B * p.F) {
-        b = fid / p.F;
-        const int f = fid - b * p.F;
-        const float4* q4 = reinterpret_cast<const float4*>(p.frec) + (size_t)fid * 3;
-        const float4 c0 = __ldg(q4), c1 = __ldg(q4 + 1);
-        FaceRec r;
-        r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
-        r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
-        if (sub == 0) {
-            wq.rec[0][slot] = r.ax; wq.rec[1][slot] = r.ay; wq.rec[2][slot] = r.bx; wq.rec[3][slot] = r.by;
-            wq.rec[4][slot] = r.cx; wq.rec[5][slot] = r.cy; wq.img[slot] = b; wq.face[slot] = f;
-        }
-        exact_rect(p, r, true, ix0, ix1, iy0, iy1);
-    }
-    __syncwarp();
-    // ---- (row, 32-column block) segments of the face's rectangle, row-major; this lane takes segments sub, sub+4, ..
-    const int wd0 = ix0 >> 5;
-    const int nwd = (ix1 >= ix0 && iy1 >= iy0) ? (ix1 >> 5) - wd0 + 1 : 0;
-    const int nseg_face = nwd * (iy1 - iy0 + 1);
-    const int nseg = (nseg_face - sub + 3) >> 2;
-    const uint32_t* covb = p.cov + (size_t)b * p.H * p.covw;
-    int maxseg = nseg;
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxseg = max(maxseg, __shfl_xor_sync(FULL, maxseg, o));
-    int qn = 0;
-    // running (row, word) of this lane's segment `it * 4 + sub`, advanced by 4 segments per iteration without a division
-    int row = iy0, wd = wd0 + sub;
-    if (nwd > 0) while (wd >= wd0 + nwd) { wd -= nwd; ++row; }
-    #pragma unroll 1
-    for (int it = 0; it < maxseg; ++it) {
-        uint32_t bits = 0u;
-        if (it < nseg) {
-            const int lo = max(ix0 - (wd << 5), 0), hi = min(ix1 - (wd << 5), 31);         // column range inside this word
-            const uint32_t colmask = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
-            bits = ~__ldg(covb + (size_t)row * p.covw + wd) & colmask;                       // uncovered pixels of the segment
-        }
-        if (__any_sync(FULL, bits != 0u)) {
-            // exclusive scan of the per-lane candidate counts -> queue offsets
-            const int c = __popc(bits);
-            int incl = c;
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-            int pos = qn + incl - c;
-            const uint32_t hdr = ((uint32_t)slot << 24) | ((uint32_t)row << 12) | (uint32_t)(wd << 5);
-            while (bits) {
-                const int j = __ffs(bits) - 1;
-                bits &= bits - 1u;
-                wq.q[pos++] = hdr + (uint32_t)j;
-            }
-            qn += __shfl_sync(FULL, incl, 31);
-            __syncwarp();
-            while (qn >= 32) {                                   // evaluate from the top of the queue: no shifting
-                qn -= 32;
-                const uint32_t e = wq.q[qn + lane];
-                soft_fwd_eval(p, wq, e, kz);
-                soft_fwd_record(p, wq, e, 32, lane);
-            }
-            __syncwarp();
-        }
-        if (it < nseg) {
-            if (nwd == 1) row += 4;
-            else { wd += 4; while (wd >= wd0 + nwd) { wd -= nwd; ++row; } }
-        }
-    }
-    if (qn > 0) {
-        const uint32_t e = lane < qn ? wq.q[lane] : 0u;
-        if (lane < qn) soft_fwd_eval(p, wq, e, kz);
-        soft_fwd_record(p, wq, e, qn, lane);
-    }
+    soft_fwd_role(p, s_wq[threadIdx.x >> 5], gwarp);
 }
 
 // ---------------------------------------------------------------------------------------------- soft pass backward, list-driven
@@ -655,13 +485,22 @@ k_soft_bwd(const mm_raster_params p, const int nlist)
 
 }  // namespace
 
-void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
+void mm_launch_hard(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
     const int warps = (p.B * c->F + FPW - 1) / FPW;
-    const int grid = (warps + 7) / 8;
-    mm_launch(k_scatter_hard, dim3(grid), dim3(256), 0, s, g_mm_pdl != 0, p);
-    { const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW; mm_launch(k_soft_fwd, dim3((nw + SF_WARPS - 1) / SF_WARPS), dim3(32 * SF_WARPS), 0, s, g_mm_pdl != 0, p); }
+    mm_launch(k_scatter_hard, dim3((warps + 7) / 8), dim3(256), 0, s, g_mm_pdl != 0, p);
+}
+
+void mm_launch_soft_ovf_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
+{
     mm_launch(k_soft_ovf_fwd, dim3(c->num_sms * 16), dim3(OVF_THREADS), 0, s, g_mm_pdl != 0, p);
+}
+
+void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
+{
+    mm_launch_hard(c, p, s);
+    { const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW; mm_launch(k_soft_fwd, dim3((nw + SF_WARPS - 1) / SF_WARPS), dim3(32 * SF_WARPS), 0, s, g_mm_pdl != 0, p); }
+    mm_launch_soft_ovf_fwd(c, p, s);
 }
 
 void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)

@@ -250,6 +250,18 @@ def test_soft_backward_fallback_when_pair_list_overflows(mm, monkeypatch):
     _check(res, case["B"], 64, 64)
 
 
+@pytest.mark.parametrize("case", [
+    dict(mesh="ellipsoid", B=3, image_size=64, no_mask=True, contour=0.1, seed=23),
+    dict(mesh="sphere", B=2, image_size=22, ratio=1.5, no_mask=True, contour=0.1, seed=19),
+], ids=["aligned", "ragged"])
+def test_split_step_variant(mm, monkeypatch, case):
+    """MM_SPLIT=1 runs the soft pass and the RGB shading in one launch and finishes the silhouette in k_alpha."""
+    monkeypatch.setenv("MM_SPLIT", "1")
+    res = pu.run_parity_case(mm, **case)
+    H = round(case.get("ratio", 1) * case["image_size"])
+    _check(res, case["B"], H, case["image_size"])
+
+
 def test_empty_scene_and_offscreen(mm):
     """Object entirely outside the frame: nothing covered, silhouette 0, gradients finite (zeros for geometry)."""
     dr = mm.DiffRender(mm.icosphere(3), 64)
