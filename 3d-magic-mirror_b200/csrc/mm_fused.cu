@@ -140,41 +140,41 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
             if (HAS_GUP && !SPLIT) load4<VEC>(p.g_rgba + ((size_t)b * 4 + 3) * HW + pix0, n, gs);      // upstream d/d(silhouette)
             #pragma unroll
             for (int j = 0; j < 4; ++j) gmv[j] = gtv[3][j];
-            float img[3][4], gbg[3][4];
+            // channel by channel, each plane stored as soon as it is complete (keeps the live register set small: the kernel's
+            // occupancy is register-bound); covered pixels are overwritten by pass 2
+            float* out = p.rgba + (size_t)b * 4 * HW + pix0;
+            float g_coef[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float gm = gtv[3][j];
-                const bool is_bg = face[j] < 0;
-                float g_coef = 0.0f;
+            for (int ch = 0; ch < 3; ++ch) {
+                float img[4], gbg[4];
                 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
+                for (int j = 0; j < 4; ++j) {
+                    const float gm = gtv[3][j];
                     // the covered-path expression with tcol = tm = 0 (bit-identical to the unfused kernel)
                     const float pre = composite_pre(p.no_mask, 0.0f, 0.0f, bgv[ch][j], coef_bg);
                     const float v = clamp01(pre);
-                    img[ch][j] = v;
+                    img[j] = v;
                     const float lt = l1_term(v, gtv[ch][j], gm);
-                    if (is_bg) acc_l1 += fabsf(lt);
+                    if (face[j] < 0) acc_l1 += fabsf(lt);
                     float g = gup[ch][j] + k_img * sgnf(lt) * gm;
                     g = (pre >= 0.0f && pre <= 1.0f) ? g : 0.0f;
-                    gbg[ch][j] = g * coef_bg;
-                    if (p.no_mask) g_coef += g * bgv[ch][j];
+                    gbg[j] = g * coef_bg;
+                    if (p.no_mask) g_coef[j] += g * bgv[ch][j];
                 }
-                if (is_bg && j < n) acc_gc += g_coef;
+                store4<VEC>(out + ch * HW, n, img);
+                if (p.g_bg) store4<VEC>(p.g_bg + ((size_t)b * 3 + ch) * HW + pix0, n, gbg);
+            }
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float gm = gtv[3][j];
+                if (face[j] < 0 && j < n) acc_gc += g_coef[j];
                 if (!SPLIT && j < n) {                         // IoU partial sums (kaolin mask_iou)
                     const float mul = soft[j] * gm;
                     acc_n += mul;
                     acc_d += (soft[j] + gm) - mul;
                 }
             }
-            // ---- outputs, one 16-byte store per plane (covered pixels are overwritten by pass 2)
-            float* out = p.rgba + (size_t)b * 4 * HW + pix0;
-            #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) store4<VEC>(out + ch * HW, n, img[ch]);
             if (!SPLIT) store4<VEC>(out + 3 * HW, n, soft);
-            if (p.g_bg) {
-                #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) store4<VEC>(p.g_bg + ((size_t)b * 3 + ch) * HW + pix0, n, gbg[ch]);
-            }
         }
         // ---- tile-local part of d(loss)/d(silhouette): upstream + contour term (DIBR_SPEC A.7).  H and W are multiples of 4 here,
         // so the 16x8 tile holds whole 4x4 contour blocks: a block = lanes differing in lane bits 2,3 (4 rows) with the same
@@ -255,24 +255,18 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
 #endif
             guj[ch] = HAS_GUP ? __ldg(p.g_rgba + ((size_t)b * 4 + ch) * HW + pix) : 0.0f;
         }
-#ifdef EXP_NO_RECLD
-        FaceRec r; r.ax = 10.f * f; r.ay = 3.f * f; r.bx = r.ax + 40.f; r.by = r.ay + 3.f; r.cx = r.ax + 5.f; r.cy = r.ay + 45.f;
-        r.az = r.bz = r.cz = -3.f; r.nx = 0.1f; r.ny = 0.2f; r.nz = 0.97f;
-#else
         const FaceRec r = load_rec(rec, f);
-#endif
         Bary bar;
         bary_eval(r, pix_x(ix, W, p.sx), pix_y(iy, H, p.sy), p.eps, bar);
-        float uv[6];
-        const float* uvp = p.face_uvs + f * 6;
-        #pragma unroll
-#ifdef EXP_NO_RECLD
-        for (int k = 0; k < 6; ++k) uv[k] = 0.1f * k + 1e-6f * f;
-#else
-        for (int k = 0; k < 6; ++k) uv[k] = __ldg(uvp + k);
-#endif
-        const float u = interp3(bar.w0, bar.w1, bar.w2, uv[0], uv[2], uv[4]);
-        const float v = interp3(bar.w0, bar.w1, bar.w2, uv[1], uv[3], uv[5]);
+        float u, v;
+        {
+            float uvf[6];
+            const float* uvp = p.face_uvs + f * 6;
+            #pragma unroll
+            for (int k = 0; k < 6; ++k) uvf[k] = __ldg(uvp + k);
+            u = interp3(bar.w0, bar.w1, bar.w2, uvf[0], uvf[2], uvf[4]);
+            v = interp3(bar.w0, bar.w1, bar.w2, uvf[1], uvf[3], uvf[5]);
+        }
         const float tm = ADD(ADD(bar.w0, bar.w1), bar.w2);
         const float nx = interp3(bar.w0, bar.w1, bar.w2, r.nx, r.nx, r.nx);
         const float ny = interp3(bar.w0, bar.w1, bar.w2, r.ny, r.ny, r.ny);
@@ -369,8 +363,15 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
 #else
         if (g_u != 0.0f || g_v != 0.0f) {
 #endif
-            const float k1 = bar.k1, k2 = bar.k2, k3 = bar.k3;
-            const float m = bar.m, pp = bar.p, nn = bar.n, q = bar.q, sb = bar.s, t = bar.t;
+            // the record, the barycentric set-up and the face's uvs are RE-derived here (L1 hits + ~15 flops) instead of being
+            // kept alive across the texture section: ~20 registers less at the kernel's widest point
+            const FaceRec r2 = load_rec(rec, f);
+            const float m = r2.bx - r2.ax, pp = r2.by - r2.ay, nn = r2.cx - r2.ax, q = r2.cy - r2.ay;
+            const float sb = pix_x(ix, W, p.sx) - r2.ax, t = pix_y(iy, H, p.sy) - r2.ay;
+            const float k1 = sb * q - nn * t, k2 = m * t - sb * pp, k3 = m * q - nn * pp;
+            float uv[6];
+            #pragma unroll
+            for (int k = 0; k < 6; ++k) uv[k] = __ldg(p.face_uvs + f * 6 + k);
             const float rden = __fdividef(p.multiplier, k3 * k3 + p.eps);
             const float A1 = rden * (g_u * (uv[2] - uv[0]) + g_v * (uv[3] - uv[1]));
             const float A2 = rden * (g_u * (uv[4] - uv[0]) + g_v * (uv[5] - uv[1]));
