@@ -37,7 +37,6 @@ SIGNATURES = {
                                   [c_int, c_void_p, c_float, c_float, c_float] + [c_void_p] * 2 + [c_void_p] * 3 +
                                   [c_void_p] * 8 + [c_void_p, c_void_p]),
     "mm_debug_export_faces": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mm_debug_set_profile_buffer": (c_int, [c_void_p, c_void_p]),
     "mm_ctx_set_timing": (c_int, [c_void_p, c_int]),
     "mm_ctx_get_timing": (c_int, [c_void_p, c_void_p, c_int]),
 }

@@ -65,13 +65,12 @@ int check_launch(const char* what) {
 void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int no_mask, mm_raster_params& p) {
     memset(&p, 0, sizeof(p));
     p.B = B; p.V = c->V; p.F = c->F; p.H = c->H; p.W = c->W; p.Ht = Ht; p.Wt = Wt;
-    p.nstx = c->nstx; p.nsty = c->nsty; p.nst = c->nst; p.nwords = c->nwords; p.knum = c->knum;
+    p.nstx = c->nstx; p.nsty = c->nsty; p.nst = c->nst; p.knum = c->knum;
     p.sx = c->sx; p.sy = c->sy; p.blen = c->blen; p.multiplier = c->multiplier; p.eps = c->eps; p.sigmainv = c->sigmainv;
     p.no_mask = no_mask;
     p.covw = (c->W + 31) / 32;
     p.face_uvs = c->d_face_uvs;
     p.tab = c->d_tab;
-    p.prof = c->d_prof;
 }
 
 void set_ws(const mm_ctx* c, const mm_ws_layout& L, char* ws, mm_raster_params& p) {
@@ -82,8 +81,7 @@ void set_ws(const mm_ctx* c, const mm_ws_layout& L, char* ws, mm_raster_params& 
     p.gsoft = (float*)(ws + L.gsoft);
     p.plist = (unsigned long long*)(ws + L.plist); p.plist_cap = (uint32_t)((L.gsoft - L.plist) / 8);
     if (c->plist_cap_max && p.plist_cap > c->plist_cap_max) p.plist_cap = c->plist_cap_max;
-    p.part_fwd = (float*)(ws + L.part_fwd); p.part_bwd = (float*)(ws + L.part_bwd);
-    p.img_fwd = (long long*)(ws + L.img_fwd); p.img_bwd = (long long*)(ws + L.img_bwd); p.tickets = (uint32_t*)(ws + L.tickets);
+    p.img_fwd = (long long*)(ws + L.img_fwd); p.img_bwd = (long long*)(ws + L.img_bwd);
     p.gfacc = (float*)(ws + L.gfacc);
 }
 
@@ -146,7 +144,6 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     c->nsty = (H + MM_ST_H - 1) / MM_ST_H;
     c->nst = c->nstx * c->nsty;
     c->nparts_recon = (H * W + 4095) / 4096 < 1 ? 1 : (H * W + 4095) / 4096;     // ~4096 pixels per recon CTA
-    c->nwords = ((F + 31) / 32 + 3) & ~3;          // multiple of 4 words: mask rows stay 16-byte aligned for cp.async.bulk
     c->num_sms = prop.multiProcessorCount;
     if (c->nst > 65535) { delete c; return fail(MM_E_UNSUPPORTED, "image too large: %d sub-tiles exceed the 16-bit work-list ids", c->nst); }
     if (F > 65535) { delete c; return fail(MM_E_UNSUPPORTED, "F=%d exceeds the 16-bit face ids of the soft-pass lists", F); }
@@ -160,18 +157,14 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     c->split = 0;
     if (const char* e = getenv("MM_SPLIT")) c->split = atoi(e) != 0;
     if (const char* e = getenv("MM_VCHUNKS")) { const int v = atoi(e); if (v > 0 && v <= 32) c->nchunks = v; }
-    c->chunk_rows = 0;
     c->smem_vertex_fwd = mm_vertex_smem_fwd(c);
-    c->smem_raster = mm_raster_smem_bytes(c);
     const size_t vs_f = c->smem_vertex_fwd, vs_b = mm_vertex_smem_bwd(V);
-    if (vs_f > smem_max || vs_b > smem_max || c->smem_raster > smem_max) {
-        const size_t need = vs_f > vs_b ? (vs_f > c->smem_raster ? vs_f : c->smem_raster) : (vs_b > c->smem_raster ? vs_b : c->smem_raster);
+    if (vs_f > smem_max || vs_b > smem_max) {
+        const size_t need = vs_f > vs_b ? vs_f : vs_b;
         delete c;
         return fail(MM_E_UNSUPPORTED, "V=%d F=%d W=%d needs %zu B of shared memory per CTA (> %zu)", V, F, W, need, smem_max);
     }
     mm_vertex_set_smem(vs_f, vs_b);
-    cudaError_t e = mm_raster_configure(c);
-    if (e != cudaSuccess) { delete c; return fail(MM_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
 
     std::vector<int32_t> tab(3 * (size_t)H + 3 * (size_t)W);
     contour_tables(H, tab.data(), tab.data() + H, tab.data() + 2 * H);
@@ -370,12 +363,6 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
                          g_elev, g_dist, g_bias, g_lights, loss, p.img_fwd, image_weight, contour, s);
     if (c->timing) { cudaEventRecord(c->ev[6], s); cudaEventRecord(c->ev[7], s); }
     return check_launch("vertex_bwd");
-}
-
-int mm_debug_set_profile_buffer(mm_ctx* c, long long* device_buf) {
-    MM_REQUIRE(c, "ctx");
-    c->d_prof = device_buf;
-    return MM_OK;
 }
 
 int mm_ctx_set_timing(mm_ctx* c, int enable) {

@@ -6,29 +6,24 @@
 //     face_uvs   [F,3,2]              (DiffRender.face_uvs, networks.py:201,254)
 //     refrow/rowlo/rowhi [H], refcol/collo/colhi [W] int32: nearest-down/nearest-up
 //                index tables of the contour term (networks.py:381-382)
-//   workspace (caller-owned, per call):
-//     frec       [B,F,12]  face records: (ax,ay,bx,by | cx,cy,az,bz | cz,nx,ny,nz),
-//                          xy already multiplied by `multiplier`, z camera-space,
-//                          n = unit face normal in camera space.  48 B / face, one
-//                          contiguous block per image so a CTA stages it with ONE
-//                          cp.async.bulk (TMA bulk copy) into shared memory.
+//   workspace (caller-owned, per call; mm_ws_make):
+//     frec       [B,F,12]  face records: (ax,ay,bx,by | cx,cy,az,bz | cz,nx,ny,nz), xy already multiplied by `multiplier`,
+//                          z camera-space, n = unit face normal in camera space.  48 B = 3 x float4 per face.
 //     zbuf       [B,H,W] u64  visibility buffer: (order-preserving depth << 32 | ~face), atomicMax-resolved; 0 = uncovered
+//     lacc       [B,H,W] u64  soft-silhouette accumulator of uncovered pixels: fixed-point sum log(1-p) << 16 | count
 //     cov        [B,H,ceil(W/32)] u32 coverage bitmap written by the hard pass (atomicOr): the soft pass finds the UNCOVERED
 //                             pixels of a face's enlarged bbox with one word load per row instead of one zbuf load per pixel
-//     lacc       [B,H,W] u64  soft-silhouette accumulator of uncovered pixels: fixed-point sum log(1-p) << 16 | count
-//     ovf_list   [B*H*W] u32  pixels that saw more than knum candidates (ordered re-scan), ovf_count [1] u32
-//     gsoft      [B,H,W]      d(loss)/d(silhouette) per pixel, handed from the shading backward to the geometry backward
+//     ovf_count  [4] u32   {pixels that saw more than knum candidates, candidate pairs recorded, -, -}
+//                          (zbuf, lacc, cov and ovf_count are contiguous: k_vertex_fwd clears them in one range)
+//     ovf_list   [B*H*W] u32  the truncated pixels (exact ordered re-scan by the overflow pass)
 //     plist      [2*B*H*W] u64 the (face, pixel) candidate pairs the forward soft pass evaluated, (image*F+face) << 32 |
-//                             iy << 12 | ix: the backward soft pass replays this dense list instead of re-filtering
-//                             every bbox pixel; plist_count shares the cleared counter block
+//                             iy << 12 | ix: the backward soft pass replays this dense list
+//     gsoft      [B,H,W]      d(loss)/d(silhouette) per pixel, handed from the shading stage to the geometry backward
 //     vimg       [B,V,2]   unscaled image-plane xy (debug export / parity tests)
-//     face_idx   [B,H,W]   int32 winner of the hard pass (-1 none); saved for backward
 //     gfacc      [B,F,9]   backward accumulators: d/d(fvi) (6, unscaled) + d/d(unit normal) (3)
-//     part_fwd   [B,NP,4]  per-CTA partial sums (L1, N, D, contour)  NP = raster CTAs per image
-//     part_bwd   [B,NP,12] per-CTA partials (contour sum, 9 light grads, -, -)
-//     img_fwd    [B,4]     per-image sums (L1, N, D, contour), reduced in a FIXED order by the last CTA of the image
-//     img_bwd    [B,12]    per-image sums (contour, 9 light grads), same scheme
-//     tickets    [B,4]     u32 {fwd work queue, bwd work queue, fwd arrivals, bwd arrivals} (self-resetting)
+//     part_fwd   [B,NP,4]  per-CTA partial sums of the stand-alone recon_data kernels (L1, N, D, contour)
+//     img_fwd    [B,4]     per-image sums (L1, N, D, contour) as fixed-point 64-bit integers (order-independent atomics)
+//     img_bwd    [B,12]    per-image sums (contour, 9 light gradients, -, -), same scheme
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,14 +34,7 @@
 #ifndef MM_VTHREADS
 #define MM_VTHREADS     512          // threads per CTA of the vertex-stage kernels
 #endif
-#ifndef MM_RWARPS
-#define MM_RWARPS       1            // raster kernels: warps (= sub-tiles) per CTA.  1 => the hardware CTA scheduler
-#endif                               // balances sub-tiles individually (heavy silhouette tiles never park idle warps)
-#define MM_RTHREADS     (32 * MM_RWARPS)
-#ifndef MM_RMINB
-#define MM_RMINB        24           // min resident raster CTAs per SM (caps registers at 64/thread for 1-warp CTAs)
-#endif
-#define MM_ST_W         8            // sub-tile (one warp) = 8 x 4 pixels
+#define MM_ST_W         8            // unfused shading kernels: one warp = one 8 x 4 pixel sub-tile
 #define MM_ST_H         4
 #define MM_REC_FLOATS   12
 #define MM_MAX_KNUM     64
@@ -63,10 +51,8 @@ struct mm_ctx {
     int nstx, nsty;          // sub-tile grid = ceil(W / 8) x ceil(H / 4)
     int nst;                 // sub-tiles per image
     int nparts_recon;        // CTAs per image of the stand-alone recon_data kernels
-    int nwords;              // bitmask words per sub-tile = ceil(F / 32)
-    int chunk_rows, nchunks; // vertex stage: sub-tile rows binned per CTA, CTAs per image
+    int nchunks;             // vertex forward: CTAs per image (each emits 1/nchunks of the face records)
     size_t smem_vertex_fwd;  // dynamic smem bytes of the vertex forward kernel
-    size_t smem_raster;      // dynamic smem bytes of the raster kernels (per-lane soft candidate lists)
     int num_sms;
     int split;               // fused step: 1 = soft pass and RGB shading in one launch + k_alpha (MM_SPLIT=1), 0 = sequential (default)
     unsigned plist_cap_max;  // test hook (MM_PLIST_CAP): caps the forward's pair list so that the backward's fallback path runs
@@ -75,23 +61,15 @@ struct mm_ctx {
     float*   d_face_uvs;     // [F,6]
     int32_t* d_tab;          // [3*H + 3*W] contour tables: refrow,rowlo,rowhi,refcol,collo,colhi
     // measurement hook (mm_ctx_set_timing)
-    long long* d_prof;       // optional per-sub-tile cycle counters (debug, NULL normally)
     int timing;
     cudaEvent_t ev[8];
 };
 
 struct mm_ws_layout {
-    size_t frec, zbuf, lacc, cov, ovf_count, ovf_list, plist, gsoft, vimg, gfacc, part_fwd, part_bwd, img_fwd, img_bwd, tickets, total;
+    size_t frec, zbuf, lacc, cov, ovf_count, ovf_list, plist, gsoft, vimg, gfacc, part_fwd, img_fwd, img_bwd, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-// persistent geometry warps: enough single-warp CTAs to fill every SM ~24 deep, at most one per sub-tile of the batch
-static inline int mm_raster_parts(const mm_ctx* c, int B) {
-    long long g = (long long)c->num_sms * 24;
-    if (g > (long long)B * c->nst) g = (long long)B * c->nst;
-    return (int)(g < 1 ? 1 : g);
-}
 
 static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     mm_ws_layout L;
@@ -110,10 +88,8 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     const int rp = (c->nst + MM_WARPS - 1) / MM_WARPS;          // shading CTAs per image (8 sub-tiles each)
     const size_t np = (size_t)(rp > c->nparts_recon ? rp : c->nparts_recon);
     L.part_fwd = off; off = mm_align_up(off + (size_t)B * np * 4 * 4, 256);
-    L.part_bwd = off; off = mm_align_up(off + (size_t)B * np * 12 * 4, 256);
     L.img_fwd = off;  off = mm_align_up(off + (size_t)B * 4 * 8, 256);
     L.img_bwd = off;  off = mm_align_up(off + (size_t)B * 12 * 8, 256);
-    L.tickets = off;  off = mm_align_up(off + (size_t)B * 4 * 4, 256);
     L.total = off;
     return L;
 }
@@ -121,7 +97,7 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
 // parameters shared by the raster kernels (passed by value)
 struct mm_raster_params {
     int B, V, F, H, W, Ht, Wt;
-    int nstx, nsty, nst, nwords, knum;
+    int nstx, nsty, nst, knum;
     float sx, sy, blen, multiplier, eps, sigmainv;
     int no_mask;
     const float* frec;       // [B,F,12]
@@ -144,10 +120,8 @@ struct mm_raster_params {
     float* rgba;             // [B,4,H,W]
     float* imnormal;         // [B,H,W,3] or NULL
     int32_t* face_idx_out;   // [B,H,W] or NULL
-    float* part_fwd;         // [B,NP,4]
     long long* img_fwd;      // [B,4]  fixed-point (mm_device.cuh)
     long long* img_bwd;      // [B,12] fixed-point
-    uint32_t* tickets;       // [B,4]
     // backward
     const float* g_rgba;     // [B,4,H,W] or NULL
     float image_weight, contour, loss_scale;
@@ -155,9 +129,7 @@ struct mm_raster_params {
     float* gfacc;            // [B,F,9]
     float* g_tex;            // [B,3,Ht,Wt]
     float* g_bg;             // [B,3,H,W] or NULL
-    float* part_bwd;         // [B,NP,12]
     uint4* clr; size_t nclr;  // buffer the hard pass clears on the side (fused step: the texture-gradient output), 16-byte units
-    long long* prof;         // debug: [B,NST,8] cycles fwd / bwd, popc(S), popc(H), hard, soft-mark, soft-pairs cycles, #pairs; NULL normally
 };
 
 // ------------------------------------------------------------------ programmatic dependent launch (PDL)
@@ -212,8 +184,6 @@ void mm_launch_recon_fwd(const mm_ctx* c, int B, const float* pred, const float*
                          cudaStream_t s);
 void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float* gt, const long long* img_fwd,
                          float image_weight, float contour, float loss_scale, float* g_pred, cudaStream_t s);
-cudaError_t mm_raster_configure(const mm_ctx* c);
-size_t mm_raster_smem_bytes(const mm_ctx* c);
 size_t mm_vertex_smem_fwd(const mm_ctx* c);
 size_t mm_vertex_smem_bwd(int V);
 void mm_vertex_set_smem(size_t fwd, size_t bwd);

@@ -510,5 +510,3 @@ void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t
     mm_launch(k_soft_bwd, dim3(nlist + novf), dim3(SB_THREADS), 0, s, g_mm_pdl != 0, p, nlist);
 }
 
-size_t mm_raster_smem_bytes(const mm_ctx* c) { (void)c; return 0; }
-cudaError_t mm_raster_configure(const mm_ctx* c) { (void)c; return cudaSuccess; }

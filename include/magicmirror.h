@@ -125,14 +125,12 @@ int mm_render_compare_fwd_bwd(mm_ctx* ctx, int B,
 int mm_debug_export_faces(mm_ctx* ctx, int B, const void* workspace,
                           float* fvi, float* fvz, float* fnz, void* stream);
 
-/* Debug hook: when `device_buf` (int64 [B,NST,8], NST = ceil(W/8)*ceil(H/4)) is non-NULL the raster kernels record,
- * per 8x4-pixel sub-tile, SM cycles spent in forward / backward and the sizes of its two face lists. */
-int mm_debug_set_profile_buffer(mm_ctx* ctx, long long* device_buf);
-
 /* Measurement hook (bench.py): when enabled, mm_render_compare_fwd_bwd records a CUDA event on
- * `stream` before each of its kernels and after the last one.  mm_ctx_get_timing waits for the last
- * call's final event and writes the per-kernel durations in milliseconds, in launch order
- * (vertex_fwd, geom_fwd, shade_fwd, shade_bwd, geom_bwd, vertex_bwd, loss_finalize; capacity >= 7); returns the count written. */
+ * `stream` around each of its launch groups.  mm_ctx_get_timing waits for the last call's final event
+ * and writes the group durations in milliseconds, in launch order (vertex_fwd, geometry forward [hard + soft +
+ * overflow], fused shading, d/d-silhouette pass [only for H or W not a multiple of 4], geometry backward,
+ * vertex_bwd + loss finalisation, -; capacity >= 7); returns the count written.  Event records switch
+ * programmatic dependent launch off across them, so the figures are slightly above the in-step cost. */
 int mm_ctx_set_timing(mm_ctx* ctx, int enable);
 int mm_ctx_get_timing(mm_ctx* ctx, float* ms_host, int capacity);
 
