@@ -18,6 +18,12 @@
  *   - gradient outputs are OVERWRITTEN (the library zero-fills), never accumulated.
  *   - `workspace` written by a forward call must be passed unmodified to the
  *     matching backward call.
+ *
+ * Environment switches read at mm_ctx_create (diagnostics; defaults are the measured best):
+ *   MM_PDL=0        no programmatic dependent launch between the library's kernels
+ *   MM_SPLIT=1      fused step: soft pass and RGB shading in one launch + a final silhouette pass
+ *   MM_VCHUNKS=n    CTAs per image of the vertex forward kernel (default 8)
+ *   MM_PLIST_CAP=n  test hook: caps the forward's candidate list so the backward's fallback path runs
  */
 #ifndef MAGICMIRROR_H_
 #define MAGICMIRROR_H_
