@@ -37,6 +37,12 @@ SIGNATURES = {
                                   [c_int, c_void_p, c_float, c_float, c_float] + [c_void_p] * 2 + [c_void_p] * 3 +
                                   [c_void_p] * 8 + [c_void_p, c_void_p]),
     "mm_debug_export_faces": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mm_ctx_set_regularizer_topology": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                                c_void_p, c_void_p, c_float]),
+    "mm_mesh_reg_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, ctypes.c_uint,
+                                    c_void_p, c_void_p, c_void_p]),
+    "mm_mesh_reg_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, ctypes.c_uint,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mm_ctx_set_timing": (c_int, [c_void_p, c_int]),
     "mm_ctx_get_timing": (c_int, [c_void_p, c_void_p, c_int]),
 }

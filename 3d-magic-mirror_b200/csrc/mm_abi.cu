@@ -184,6 +184,8 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
 
 int mm_ctx_destroy(mm_ctx* c) {
     if (!c) return MM_OK;
+    cudaFree(c->d_edges); cudaFree(c->d_edge2faces); cudaFree(c->d_flip); cudaFree(c->d_sign_init);
+    cudaFree(c->d_lap_off); cudaFree(c->d_lap_col); cudaFree(c->d_lap_val); cudaFree(c->d_reg_ticket);
     cudaFree(c->d_faces);
     cudaFree(c->d_face_uvs);
     cudaFree(c->d_tab);
@@ -363,6 +365,79 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
                          g_elev, g_dist, g_bias, g_lights, loss, p.img_fwd, image_weight, contour, s);
     if (c->timing) { cudaEventRecord(c->ev[6], s); cudaEventRecord(c->ev[7], s); }
     return check_launch("vertex_bwd");
+}
+
+int mm_ctx_set_regularizer_topology(mm_ctx* c, int E, const int32_t* edges_host, const int32_t* edge2faces_host,
+                                    const int32_t* flip_index_host, const float* sign_init_host, int nnz,
+                                    const int32_t* lap_row_off_host, const int32_t* lap_col_host, const float* lap_val_host,
+                                    float ratio)
+{
+    MM_REQUIRE(c, "ctx");
+    MM_REQUIRE(E > 0 && nnz > 0 && ratio > 0.0f, "E, nnz, ratio must be positive");
+    MM_REQUIRE(edges_host && edge2faces_host && flip_index_host && sign_init_host && lap_row_off_host && lap_col_host && lap_val_host,
+               "NULL topology array");
+    for (int i = 0; i < E * 2; ++i) {
+        if (edges_host[i] < 0 || edges_host[i] >= c->V) return fail(MM_E_INVALID, "edges[%d] = %d out of [0,%d)", i, edges_host[i], c->V);
+        if (edge2faces_host[i] < 0 || edge2faces_host[i] >= c->F) return fail(MM_E_INVALID, "edge2faces[%d] = %d out of [0,%d)", i, edge2faces_host[i], c->F);
+    }
+    for (int i = 0; i < c->V; ++i)
+        if (flip_index_host[i] < 0 || flip_index_host[i] >= c->V) return fail(MM_E_INVALID, "flip_index[%d] out of range", i);
+    MM_REQUIRE(lap_row_off_host[0] == 0 && lap_row_off_host[c->V] == nnz, "laplacian row offsets");
+    for (int i = 0; i < nnz; ++i)
+        if (lap_col_host[i] < 0 || lap_col_host[i] >= c->V) return fail(MM_E_INVALID, "laplacian column %d out of range", i);
+    MM_CUDA(cudaSetDevice(c->device));
+    cudaFree(c->d_edges); cudaFree(c->d_edge2faces); cudaFree(c->d_flip); cudaFree(c->d_sign_init);
+    cudaFree(c->d_lap_off); cudaFree(c->d_lap_col); cudaFree(c->d_lap_val); cudaFree(c->d_reg_ticket);
+    c->d_edges = c->d_edge2faces = c->d_flip = c->d_lap_off = c->d_lap_col = nullptr;
+    c->d_sign_init = c->d_lap_val = nullptr; c->d_reg_ticket = nullptr;
+    MM_CUDA(cudaMalloc(&c->d_edges, (size_t)E * 2 * 4));
+    MM_CUDA(cudaMalloc(&c->d_edge2faces, (size_t)E * 2 * 4));
+    MM_CUDA(cudaMalloc(&c->d_flip, (size_t)c->V * 4));
+    MM_CUDA(cudaMalloc(&c->d_sign_init, (size_t)c->V * 4));
+    MM_CUDA(cudaMalloc(&c->d_lap_off, (size_t)(c->V + 1) * 4));
+    MM_CUDA(cudaMalloc(&c->d_lap_col, (size_t)nnz * 4));
+    MM_CUDA(cudaMalloc(&c->d_lap_val, (size_t)nnz * 4));
+    MM_CUDA(cudaMalloc(&c->d_reg_ticket, 4));
+    MM_CUDA(cudaMemcpy(c->d_edges, edges_host, (size_t)E * 2 * 4, cudaMemcpyHostToDevice));
+    MM_CUDA(cudaMemcpy(c->d_edge2faces, edge2faces_host, (size_t)E * 2 * 4, cudaMemcpyHostToDevice));
+    MM_CUDA(cudaMemcpy(c->d_flip, flip_index_host, (size_t)c->V * 4, cudaMemcpyHostToDevice));
+    MM_CUDA(cudaMemcpy(c->d_sign_init, sign_init_host, (size_t)c->V * 4, cudaMemcpyHostToDevice));
+    MM_CUDA(cudaMemcpy(c->d_lap_off, lap_row_off_host, (size_t)(c->V + 1) * 4, cudaMemcpyHostToDevice));
+    MM_CUDA(cudaMemcpy(c->d_lap_col, lap_col_host, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+    MM_CUDA(cudaMemcpy(c->d_lap_val, lap_val_host, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+    MM_CUDA(cudaMemset(c->d_reg_ticket, 0, 4));
+    c->reg_E = E; c->reg_ratio = ratio;
+    return MM_OK;
+}
+
+int mm_mesh_reg_forward(mm_ctx* c, int B, const float* delta_vertices, const float* vertices, const float* face_normals,
+                        float temp, float eps, int flip_l1, unsigned term_mask, float* terms, void* workspace, void* stream)
+{
+    MM_REQUIRE(c && B > 0, "ctx / B");
+    MM_REQUIRE(c->d_edges, "mm_ctx_set_regularizer_topology has not been called");
+    MM_REQUIRE(terms && workspace, "terms / workspace");
+    MM_REQUIRE(!(term_mask & (1u | 64u | 128u)) || delta_vertices, "laplacian / deform / flip terms need delta_vertices");
+    MM_REQUIRE(!(term_mask & (4u | 8u | 16u | 32u)) || vertices, "edge / depth terms need vertices");
+    MM_REQUIRE(!(term_mask & 2u) || face_normals, "flat term needs face_normals");
+    const mm_ws_layout L = mm_ws_make(c, B);
+    mm_launch_meshreg_fwd(c, B, delta_vertices, vertices, face_normals, temp, eps, flip_l1, term_mask,
+                          (float*)((char*)workspace + L.reg_part), terms, (cudaStream_t)stream);
+    return check_launch("meshreg_fwd");
+}
+
+int mm_mesh_reg_backward(mm_ctx* c, int B, const float* delta_vertices, const float* vertices, const float* face_normals,
+                         float temp, float eps, int flip_l1, unsigned term_mask, const float* g_terms, float* g_delta,
+                         float* g_vertices, float* g_face_normals, void* stream)
+{
+    MM_REQUIRE(c && B > 0, "ctx / B");
+    MM_REQUIRE(c->d_edges, "mm_ctx_set_regularizer_topology has not been called");
+    MM_REQUIRE(g_terms, "g_terms");
+    MM_REQUIRE(!(term_mask & (1u | 64u | 128u)) || (delta_vertices && g_delta), "laplacian / deform / flip terms need delta_vertices and g_delta");
+    MM_REQUIRE(!(term_mask & (4u | 8u | 16u | 32u)) || (vertices && g_vertices), "edge / depth terms need vertices and g_vertices");
+    MM_REQUIRE(!(term_mask & 2u) || (face_normals && g_face_normals), "flat term needs face_normals and g_face_normals");
+    mm_launch_meshreg_bwd(c, B, delta_vertices, vertices, face_normals, temp, eps, flip_l1, term_mask, g_terms, g_delta,
+                          g_vertices, g_face_normals, (cudaStream_t)stream);
+    return check_launch("meshreg_bwd");
 }
 
 int mm_ctx_set_timing(mm_ctx* c, int enable) {

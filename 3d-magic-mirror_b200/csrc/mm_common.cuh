@@ -60,13 +60,18 @@ struct mm_ctx {
     int32_t* d_faces;        // [F,3]
     float*   d_face_uvs;     // [F,6]
     int32_t* d_tab;          // [3*H + 3*W] contour tables: refrow,rowlo,rowhi,refcol,collo,colhi
+    // mesh-regulariser topology (mm_ctx_set_regularizer_topology; NULL until set)
+    int reg_E; float reg_ratio;
+    int32_t *d_edges, *d_edge2faces, *d_flip, *d_lap_off, *d_lap_col;
+    float *d_sign_init, *d_lap_val;
+    unsigned* d_reg_ticket;
     // measurement hook (mm_ctx_set_timing)
     int timing;
     cudaEvent_t ev[8];
 };
 
 struct mm_ws_layout {
-    size_t frec, zbuf, lacc, cov, ovf_count, ovf_list, plist, gsoft, vimg, gfacc, part_fwd, img_fwd, img_bwd, total;
+    size_t frec, zbuf, lacc, cov, ovf_count, ovf_list, plist, gsoft, vimg, gfacc, part_fwd, reg_part, img_fwd, img_bwd, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -88,6 +93,7 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     const int rp = (c->nst + MM_WARPS - 1) / MM_WARPS;          // shading CTAs per image (8 sub-tiles each)
     const size_t np = (size_t)(rp > c->nparts_recon ? rp : c->nparts_recon);
     L.part_fwd = off; off = mm_align_up(off + (size_t)B * np * 4 * 4, 256);
+    L.reg_part = off; off = mm_align_up(off + (size_t)B * 8 * 4, 256);
     L.img_fwd = off;  off = mm_align_up(off + (size_t)B * 4 * 8, 256);
     L.img_bwd = off;  off = mm_align_up(off + (size_t)B * 12 * 8, 256);
     L.total = off;
@@ -187,5 +193,10 @@ void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float*
 size_t mm_vertex_smem_fwd(const mm_ctx* c);
 size_t mm_vertex_smem_bwd(int V);
 void mm_vertex_set_smem(size_t fwd, size_t bwd);
+void mm_launch_meshreg_fwd(const mm_ctx* c, int B, const float* delta, const float* vertices, const float* fn, float temp,
+                           float eps, int flip_l1, unsigned mask, float* partials, float* terms, cudaStream_t s);
+void mm_launch_meshreg_bwd(const mm_ctx* c, int B, const float* delta, const float* vertices, const float* fn, float temp,
+                           float eps, int flip_l1, unsigned mask, const float* g_terms, float* g_delta, float* g_vertices,
+                           float* g_fn, cudaStream_t s);
 void mm_launch_export_faces(const mm_ctx* c, int B, const float* frec, const float* vimg, float* fvi, float* fvz,
                             float* fnz, cudaStream_t s);

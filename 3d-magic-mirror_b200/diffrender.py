@@ -57,6 +57,21 @@ class _CtxHandle(object):
         _lib.check(rc, "mm_ctx_create")
         self.handle = handle
         self.device_index = device_index
+        # topology of the mesh regularisers (networks.py:197-252): edges, edge -> face pairs, mirror index, depth signs and
+        # the uniform Laplacian in CSR form (the reference multiplies by the dense V x V matrix, 6-7 non-zeros per row)
+        i32 = lambda t: t.to(torch.int32).contiguous().cpu()          # noqa: E731
+        edges, e2f, flip = i32(dr.edges), i32(dr.edge2faces), i32(dr.flip_index)
+        sign = dr.sign_init.to(torch.float32).contiguous().cpu()
+        lap = dr.vertices_laplacian_matrix.to(torch.float32).cpu()
+        nzr, nzc = torch.nonzero(lap, as_tuple=True)
+        row_off = torch.zeros(dr.num_vertices + 1, dtype=torch.int32)
+        row_off[1:] = torch.cumsum(torch.bincount(nzr, minlength=dr.num_vertices), 0).to(torch.int32)
+        col = nzc.to(torch.int32).contiguous()
+        val = lap[nzr, nzc].contiguous()
+        with torch.cuda.device(device_index):
+            rc = L.mm_ctx_set_regularizer_topology(handle, edges.shape[0], _ptr(edges), _ptr(e2f), _ptr(flip), _ptr(sign),
+                                                   int(col.numel()), _ptr(row_off), _ptr(col), _ptr(val), float(dr.ratio))
+        _lib.check(rc, "mm_ctx_set_regularizer_topology")
 
     def workspace(self, B):
         n = _lib.lib().mm_workspace_bytes(self.handle, B)
@@ -186,6 +201,56 @@ class _ReconFn(torch.autograd.Function):
                                                    _ptr(g_pred), _ptr(ws), _stream())
         _lib.check(rc, "mm_recon_data_backward")
         return None, None, None, g_pred * g_loss, None
+
+
+TERMS = ("laplacian", "flat", "edge", "depth", "depthR", "depthC", "deform", "flip")
+
+
+class _MeshRegFn(torch.autograd.Function):
+    """All mesh regularisers of networks.py:392-491 in one launch per direction (csrc/mm_meshreg.cu).
+    Returns the 8 terms of TERMS (un-weighted, each exactly what the corresponding reference method returns;
+    `laplacian` and `flat` are the two summands of calc_reg_loss before their lambdas)."""
+
+    @staticmethod
+    def forward(ctx, dr, mask, temp, eps, flip_l1, delta, vertices, fn):
+        ref = delta if delta is not None else (vertices if vertices is not None else fn)
+        dev = ref.device
+        B = ref.shape[0]
+        delta = _f32c(delta) if delta is not None else None
+        vertices = _f32c(vertices) if vertices is not None else None
+        fn = _f32c(fn) if fn is not None else None
+        h = dr._ctx(dev)
+        with torch.cuda.device(dev):
+            terms = torch.zeros(8, device=dev, dtype=torch.float32)
+            ws = h.workspace(B)
+            rc = _lib.lib().mm_mesh_reg_forward(h.handle, B, _ptr(delta), _ptr(vertices), _ptr(fn), float(temp), float(eps),
+                                                1 if flip_l1 else 0, int(mask), _ptr(terms), _ptr(ws), _stream())
+        _lib.check(rc, "mm_mesh_reg_forward")
+        ctx.dr, ctx.h, ctx.args = dr, h, (int(mask), float(temp), float(eps), 1 if flip_l1 else 0, B)
+        ctx.present = (delta is not None, vertices is not None, fn is not None)
+        e = torch.empty(0, device=dev)
+        ctx.save_for_backward(delta if delta is not None else e, vertices if vertices is not None else e,
+                              fn if fn is not None else e)
+        return terms
+
+    @staticmethod
+    def backward(ctx, g_terms):
+        delta, vertices, fn = ctx.saved_tensors
+        mask, temp, eps, flip_l1, B = ctx.args
+        has_d, has_v, has_n = ctx.present
+        delta = delta if has_d else None
+        vertices = vertices if has_v else None
+        fn = fn if has_n else None
+        dev = g_terms.device
+        with torch.cuda.device(dev):
+            g_terms = _f32c(g_terms)
+            gd = torch.empty_like(delta) if has_d else None
+            gv = torch.empty_like(vertices) if has_v else None
+            gn = torch.empty_like(fn) if has_n else None
+            rc = _lib.lib().mm_mesh_reg_backward(ctx.h.handle, B, _ptr(delta), _ptr(vertices), _ptr(fn), temp, eps, flip_l1,
+                                                 mask, _ptr(g_terms), _ptr(gd), _ptr(gv), _ptr(gn), _stream())
+        _lib.check(rc, "mm_mesh_reg_backward")
+        return None, None, None, None, None, gd, gv, gn
 
 
 class DiffRender(object):
@@ -324,9 +389,23 @@ class DiffRender(object):
         loss_light = 0.1 * dist_fn(pred_att['lights'], target_att['lights'])
         return loss_cam, loss_shape, loss_texture, loss_light, loss_bias
 
+    # The mesh regularisers follow the device of their inputs, as in the reference.  On CUDA tensors the fused kernel
+    # (mm_mesh_reg_forward / _backward, one launch per direction) is the only path; the torch expressions below are the
+    # host-side statement of the same formulas for CPU tensors (checked against the reference in tests/test_host_setup.py).
+    def _reg_terms(self, mask, delta=None, vertices=None, face_normals=None, temp=2.0, eps=0.001, flip_l1=False):
+        return _MeshRegFn.apply(self, mask, temp, eps, flip_l1, delta, vertices, face_normals)
+
+    def regularizer_terms(self, att, temp=2.0, eps=0.001, flip_l1=False):
+        """All eight terms (dict keyed by TERMS) of the reference's `regularization()` inputs in ONE launch
+        (trainer.py:54-68 evaluates them with ~10 calls and ~80 kernels per attribute set)."""
+        t = self._reg_terms(255, att['delta_vertices'], att['vertices'], att['face_normals'], temp, eps, flip_l1)
+        return {k: t[i] for i, k in enumerate(TERMS)}
+
     def recon_flip(self, att, L1):
         """networks.py:392-410: z-mirror symmetry of delta_vertices, masked where the depth sign flipped."""
         Na = att['delta_vertices']
+        if Na.is_cuda:
+            return self._reg_terms(128, delta=Na, flip_l1=bool(L1))[7]
         idx = self.flip_index.to(Na.device)
         Nf = Na.index_select(1, idx)
         Nf = Nf * Nf.new_tensor([1.0, 1.0, -1.0])
@@ -342,6 +421,9 @@ class DiffRender(object):
     def calc_reg_loss(self, att):
         """networks.py:412-451: lambda_lpl * uniform-Laplacian energy + lambda_flat * dihedral flatness."""
         delta = att['delta_vertices']
+        if delta.is_cuda:
+            t = self._reg_terms(3, delta=delta, face_normals=att['face_normals'])
+            return self.lambda_lpl * t[0] + self.lambda_flat * t[1]
         dev = delta.device
         lap = self.vertices_laplacian_matrix.to(dev)
         e2f = self.edge2faces.to(dev)
@@ -354,6 +436,8 @@ class DiffRender(object):
 
     def calc_reg_edge(self, pred):
         """networks.py:453-461: 0.1 * mean_b || edge_len - mean(edge_len) ||_2."""
+        if pred.is_cuda:
+            return self._reg_terms(4, vertices=pred)[2]
         e = self.edges.to(pred.device)
         length = torch.norm(pred[:, e[:, 0]] - pred[:, e[:, 1]], p=2, dim=2)
         bias = length - torch.mean(length, dim=1, keepdim=True)
@@ -361,6 +445,8 @@ class DiffRender(object):
 
     def calc_reg_depth(self, pred):
         """networks.py:463-466."""
+        if pred.is_cuda:
+            return self._reg_terms(8, vertices=pred)[3]
         return torch.mean(pred[:, :, 2] ** 2)
 
     def _depth_weighted(self, pred, weight, eps):
@@ -370,17 +456,23 @@ class DiffRender(object):
 
     def calc_reg_depthR(self, pred, temp=2, eps=0.001):
         """networks.py:468-475: depth^2 weighted by exp(temp * r^2), sign-preserving."""
+        if pred.is_cuda:
+            return self._reg_terms(16, vertices=pred, temp=temp, eps=eps)[4]
         x = pred[:, :, 0].detach()
         y = pred[:, :, 1].detach()
         return self._depth_weighted(pred, torch.exp(temp * (x ** 2 + (y / self.ratio) ** 2)), eps)
 
     def calc_reg_depthC(self, pred, eps=0.001):
         """networks.py:477-485: depth^2 weighted by r^2, sign-preserving."""
+        if pred.is_cuda:
+            return self._reg_terms(32, vertices=pred, eps=eps)[5]
         x = pred[:, :, 0].detach()
         y = pred[:, :, 1].detach()
         return self._depth_weighted(pred, x ** 2 + (y / self.ratio) ** 2, eps)
 
     def calc_reg_deform(self, pred):
         """networks.py:487-491: mean per-vertex displacement norm."""
+        if pred.is_cuda:
+            return self._reg_terms(64, delta=pred)[6]
         b = pred.shape[0]
         return torch.mean(torch.norm(pred.reshape(-1, pred.size(2)), p=2, dim=1).reshape(b, -1))

@@ -124,6 +124,28 @@ int mm_render_compare_fwd_bwd(mm_ctx* ctx, int B,
                               float* g_tex, float* g_lights, float* g_bg,
                               void* workspace, void* stream);
 
+/* ---- the mesh regularisers next to the render path (networks.py:392-491), one launch per direction.
+ * Topology they need beyond mm_ctx_create's (DiffRender.__init__, networks.py:197-252): edges [E,2], edge2faces [E,2]
+ * (faces sharing each edge), flip_index [V] (z-mirror partner), sign_init [V] (sign of the template depth) and the uniform
+ * Laplacian (kaolin uniform_laplacian, networks.py:249) in CSR form.  All HOST pointers; copied into the ctx. */
+int mm_ctx_set_regularizer_topology(mm_ctx* ctx, int E, const int32_t* edges_host, const int32_t* edge2faces_host,
+                                    const int32_t* flip_index_host, const float* sign_init_host, int nnz,
+                                    const int32_t* lap_row_off_host /* V+1 */, const int32_t* lap_col_host,
+                                    const float* lap_val_host, float ratio);
+
+/* terms[8] (device, out) = laplacian, flat (the two summands of calc_reg_loss :412-451, before lambda_lpl / lambda_flat),
+ * calc_reg_edge (:453), calc_reg_depth (:463), calc_reg_depthR (:468), calc_reg_depthC (:477), calc_reg_deform (:487),
+ * recon_flip (:392; flip_l1 selects its L1 form).  term_mask bit k selects term k; an input a selected term does not need may
+ * be NULL (delta_vertices [B,V,3]: terms 0,6,7; vertices [B,V,3]: 2-5; face_normals [B,F,3]: 1). */
+int mm_mesh_reg_forward(mm_ctx* ctx, int B, const float* delta_vertices, const float* vertices, const float* face_normals,
+                        float temp, float eps, int flip_l1, unsigned term_mask, float* terms, void* workspace, void* stream);
+
+/* Gradient of sum_k g_terms[k] * term_k (g_terms: device [8]) w.r.t. the three inputs; outputs overwritten; a NULL input
+ * goes with a NULL output. */
+int mm_mesh_reg_backward(mm_ctx* ctx, int B, const float* delta_vertices, const float* vertices, const float* face_normals,
+                         float temp, float eps, int flip_l1, unsigned term_mask, const float* g_terms,
+                         float* g_delta_vertices, float* g_vertices, float* g_face_normals, void* stream);
+
 /* Test hook: copies the vertex-stage products of the last forward on `workspace`
  * (what kaolin prepare_vertices returns, networks.py:284-287) so that the oracle's
  * rasteriser can be run on bit-identical inputs.  Any pointer may be NULL.

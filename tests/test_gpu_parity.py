@@ -278,3 +278,52 @@ def test_empty_scene_and_offscreen(mm):
     for k in ('vertices', 'azimuths', 'textures'):
         assert bool(torch.isfinite(Ag[k].grad).all()) and float(Ag[k].grad.abs().max()) == 0.0
     assert float(Ag['bg'].grad.abs().max()) > 0
+
+
+# ------------------------------------------------------------------ fused mesh regularisers
+@pytest.mark.parametrize("mesh,ratio,ell", [("sphere", 1, 1), ("smpl_uv_642", 2, 2), ("sphere2", 1, 1)])
+def test_mesh_regularisers_fused_kernel_vs_torch_statement(mm, mesh, ratio, ell):
+    """mm_mesh_reg_forward/backward (CUDA tensors) against the torch statement of networks.py:392-491 (CPU tensors; that
+    statement is checked against the unmodified reference in tests/test_host_setup.py).  fp32: values 2e-5 rel, grads 2e-4."""
+    dr = mm.DiffRender(pu.get_mesh(mm, mesh), 64, ratio=ratio, init_ellipsoid=ell)
+    g = torch.Generator().manual_seed(5)
+    B, V, F = 5, dr.num_vertices, dr.num_faces
+    delta = 0.05 * torch.randn(B, V, 3, generator=g)
+    delta[0, :7] = 0.0                                   # zero displacements: norm sub-gradient, sign(0)
+    fn = torch.nn.functional.normalize(torch.randn(B, F, 3, generator=g), dim=2)
+
+    def run(dev):
+        d = delta.clone().to(dev).requires_grad_(True)
+        n = fn.clone().to(dev).requires_grad_(True)
+        att = {'delta_vertices': d, 'face_normals': n, 'vertices': dr.vertices_init.to(dev)[None] + d}
+        vals = [dr.calc_reg_loss(att), dr.calc_reg_edge(att['vertices']), dr.calc_reg_depth(att['vertices']),
+                dr.calc_reg_depthR(att['vertices'], temp=1.5), dr.calc_reg_depthC(att['vertices']),
+                dr.calc_reg_deform(att['delta_vertices']), dr.recon_flip(att, False), dr.recon_flip(att, True)]
+        w = torch.tensor([1.0, 0.7, 1.3, 0.9, 1.1, 0.5, 2.0, 0.3], device=dev)
+        (torch.stack(vals) * w).sum().backward()
+        return torch.stack(vals).detach().cpu(), d.grad.cpu(), n.grad.cpu()
+
+    v_ref, gd_ref, gn_ref = run("cpu")
+    v_cu, gd_cu, gn_cu = run(DEV)
+    assert torch.allclose(v_cu, v_ref, rtol=2e-5, atol=1e-8), (v_cu, v_ref)
+    assert pu.rel_err(gd_cu, gd_ref) <= 2e-4 and pu.rel_err(gn_cu, gn_ref) <= 2e-4
+    # all eight terms in one launch == the individual calls; deterministic
+    att = {'delta_vertices': delta.to(DEV), 'face_normals': fn.to(DEV), 'vertices': dr.vertices_init.to(DEV)[None] + delta.to(DEV)}
+    t1, t2 = dr.regularizer_terms(att, temp=1.5), dr.regularizer_terms(att, temp=1.5)
+    assert all(torch.equal(t1[k], t2[k]) for k in t1)
+    lam = dr.lambda_lpl * t1['laplacian'] + dr.lambda_flat * t1['flat']
+    assert torch.allclose(lam.cpu(), v_ref[0], rtol=2e-5)
+    for k, i in (('edge', 1), ('depth', 2), ('depthR', 3), ('depthC', 4), ('deform', 5), ('flip', 6)):
+        assert torch.allclose(t1[k].cpu(), v_ref[i], rtol=2e-5, atol=1e-8), k
+
+
+def test_mesh_regularisers_gradient_reaches_render_inputs(mm):
+    """calc_reg_loss consumes the `face_normals` the render returns (trainer.py:56): its gradient must flow back through
+    mm_render_backward's g_face_normals input into the vertices."""
+    dr, A = _cfg2(mm, B=4, seed=3)
+    Ag = {k: v.clone().requires_grad_(k == 'vertices') for k, v in A.items()}
+    _, out = dr.render(no_mask=True, **Ag)
+    att = {'delta_vertices': Ag['vertices'] - dr.vertices_init.to(DEV)[None], 'face_normals': out['face_normals']}
+    dr.calc_reg_loss(att).backward()
+    g = Ag['vertices'].grad
+    assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
