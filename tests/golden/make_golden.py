@@ -12,6 +12,9 @@ What is real reference code here and what is not:
                          inside is our C restatement (parity unpinned, docs/DIBR_SPEC.md); everything
                          around it is the reference's own code executing.
   * templates/<mesh>.npz -- the reference template meshes (data, not code) parsed into arrays.
+  * reg_<mesh>.npz    -- the UNMODIFIED reference's mesh regularisers (networks.py:392-491: calc_reg_loss, calc_reg_edge,
+                         calc_reg_depth/R/C, calc_reg_deform, recon_flip) on seeded inputs: values and the gradients of a
+                         fixed weighted sum.  Pure torch in the reference: no shim arithmetic involved.
 
 Usage:  python tests/golden/make_golden.py
 """
@@ -62,10 +65,27 @@ def cfg1_gt(H, W, seed):
     return torch.cat([torch.rand(1, 3, H, W, generator=g), disc[None, None]], dim=1)
 
 
+REG_CASES = {"sphere": (1, 1), "smpl_uv_642": (2, 2)}          # mesh -> (ratio, init_ellipsoid)
+
+
+def make_reg(net):
+    for mesh, (ratio, ell) in REG_CASES.items():
+        dr = net.DiffRender(os.path.join(REF, "template", mesh + ".obj"), 64, ratio=ratio, init_ellipsoid=ell)
+        dr.sign_init = dr.sign_init.cpu()
+        delta, fn = pu.reg_inputs(dr.num_vertices, dr.num_faces)
+        vals, gd, gn = pu.reg_values(dr, delta, fn)
+        np.savez_compressed(os.path.join(HERE, "reg_%s.npz" % mesh), ratio=ratio, init_ellipsoid=ell, values=vals.numpy(),
+                            grad_delta=gd.numpy(), grad_face_normals=gn.numpy())
+        print("reg", mesh, vals.numpy())
+
+
 def main():
     net, smr = ref_import.import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "reg":
+        return make_reg(net)
     mm = pu.load_mm()
     os.makedirs(os.path.join(HERE, "templates"), exist_ok=True)
+    make_reg(net)
 
     # ---- templates
     for name in TEMPLATES:

@@ -185,3 +185,27 @@ def run_parity_case(mm, mesh="icosphere", B=2, image_size=32, ratio=1, no_mask=T
         res["fused_loss_rel_err"] = abs(float(out['loss'][0]) - float(loss_o)) / max(abs(float(loss_o)), 1e-12)
         res["fused_rgba_max_abs_vs_unfused"] = float((out['rgba'] - rgb_c.detach()).abs().max())
     return res
+
+
+# ------------------------------------------------------------------ mesh regularisers fixtures
+REG_WEIGHTS = [1.0, 0.7, 1.3, 0.9, 1.1, 0.5, 2.0]                # calc_reg_loss, edge, depth, depthR, depthC, deform, flip
+
+
+def reg_inputs(V, F, seed=5, B=3):
+    g = torch.Generator().manual_seed(seed)
+    delta = 0.05 * torch.randn(B, V, 3, generator=g)
+    delta[0, :7] = 0.0
+    fn = torch.nn.functional.normalize(torch.randn(B, F, 3, generator=g), dim=2)
+    return delta, fn
+
+
+def reg_values(dr, delta, fn, temp=1.5):
+    """The seven reference calls of trainer.py:54-68 on one attribute set -> (values[7], d/d delta, d/d face_normals)."""
+    d = delta.clone().requires_grad_(True)
+    n = fn.clone().requires_grad_(True)
+    att = {'delta_vertices': d, 'face_normals': n, 'vertices': dr.vertices_init.to(d.device)[None] + d}
+    vals = torch.stack([dr.calc_reg_loss(att), dr.calc_reg_edge(att['vertices']), dr.calc_reg_depth(att['vertices']),
+                        dr.calc_reg_depthR(att['vertices'], temp=temp), dr.calc_reg_depthC(att['vertices']),
+                        dr.calc_reg_deform(att['delta_vertices']), dr.recon_flip(att, False)])
+    (vals * torch.tensor(REG_WEIGHTS, device=vals.device)).sum().backward()
+    return vals.detach(), d.grad, n.grad

@@ -327,3 +327,15 @@ def test_mesh_regularisers_gradient_reaches_render_inputs(mm):
     dr.calc_reg_loss(att).backward()
     g = Ag['vertices'].grad
     assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
+
+
+@pytest.mark.parametrize("mesh", ["sphere", "smpl_uv_642"])
+def test_mesh_regularisers_fused_kernel_vs_reference_golden(mm, mesh):
+    """The fused kernel against values + gradients produced by the UNMODIFIED reference (tests/golden/reg_<mesh>.npz)."""
+    z = np.load(os.path.join(pu.GOLDEN, "reg_%s.npz" % mesh))
+    dr = mm.DiffRender(pu.get_mesh(mm, mesh), 64, ratio=int(z["ratio"]), init_ellipsoid=int(z["init_ellipsoid"]))
+    delta, fn = pu.reg_inputs(dr.num_vertices, dr.num_faces)
+    vals, gd, gn = pu.reg_values(dr, delta.to(DEV), fn.to(DEV))
+    assert np.allclose(vals.cpu().numpy(), z["values"], rtol=2e-5, atol=1e-8)
+    assert pu.rel_err(gd.cpu(), torch.from_numpy(z["grad_delta"])) <= 2e-4
+    assert pu.rel_err(gn.cpu(), torch.from_numpy(z["grad_face_normals"])) <= 2e-4

@@ -3,6 +3,7 @@ the C-ABI library's exported symbols, and the loud-failure rules of the product 
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -123,3 +124,16 @@ def test_regularisers_match_reference_when_available(mm):
     for L1 in (False, True):
         for a, b in zip(dr.recon_att(p, q, L1=L1), ref.recon_att(p, q, L1=L1)):
             assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("mesh", ["sphere", "smpl_uv_642"])
+def test_regulariser_statement_reproduces_reference_golden(mm, mesh):
+    """tests/golden/reg_<mesh>.npz holds values + gradients computed by the UNMODIFIED reference's regularisers
+    (make_golden.py, networks.py:392-491).  The host-side torch statement must reproduce them on CPU."""
+    z = np.load(os.path.join(pu.GOLDEN, "reg_%s.npz" % mesh))
+    dr = mm.DiffRender(pu.get_mesh(mm, mesh), 64, ratio=int(z["ratio"]), init_ellipsoid=int(z["init_ellipsoid"]))
+    delta, fn = pu.reg_inputs(dr.num_vertices, dr.num_faces)
+    vals, gd, gn = pu.reg_values(dr, delta, fn)
+    assert np.allclose(vals.numpy(), z["values"], rtol=1e-6, atol=1e-9)
+    assert np.allclose(gd.numpy(), z["grad_delta"], rtol=1e-5, atol=1e-9)
+    assert np.allclose(gn.numpy(), z["grad_face_normals"], rtol=1e-5, atol=1e-9)
