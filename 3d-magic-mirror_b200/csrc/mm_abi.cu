@@ -411,17 +411,16 @@ int mm_ctx_set_regularizer_topology(mm_ctx* c, int E, const int32_t* edges_host,
 }
 
 int mm_mesh_reg_forward(mm_ctx* c, int B, const float* delta_vertices, const float* vertices, const float* face_normals,
-                        float temp, float eps, int flip_l1, unsigned term_mask, float* terms, void* workspace, void* stream)
+                        float temp, float eps, int flip_l1, unsigned term_mask, float* terms, float* scratch, void* stream)
 {
     MM_REQUIRE(c && B > 0, "ctx / B");
     MM_REQUIRE(c->d_edges, "mm_ctx_set_regularizer_topology has not been called");
-    MM_REQUIRE(terms && workspace, "terms / workspace");
+    MM_REQUIRE(terms && scratch, "terms / scratch");
     MM_REQUIRE(!(term_mask & (1u | 64u | 128u)) || delta_vertices, "laplacian / deform / flip terms need delta_vertices");
     MM_REQUIRE(!(term_mask & (4u | 8u | 16u | 32u)) || vertices, "edge / depth terms need vertices");
     MM_REQUIRE(!(term_mask & 2u) || face_normals, "flat term needs face_normals");
-    const mm_ws_layout L = mm_ws_make(c, B);
-    mm_launch_meshreg_fwd(c, B, delta_vertices, vertices, face_normals, temp, eps, flip_l1, term_mask,
-                          (float*)((char*)workspace + L.reg_part), terms, (cudaStream_t)stream);
+    mm_launch_meshreg_fwd(c, B, delta_vertices, vertices, face_normals, temp, eps, flip_l1, term_mask, scratch, terms,
+                          (cudaStream_t)stream);
     return check_launch("meshreg_fwd");
 }
 

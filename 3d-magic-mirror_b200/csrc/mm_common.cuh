@@ -71,7 +71,7 @@ struct mm_ctx {
 };
 
 struct mm_ws_layout {
-    size_t frec, zbuf, lacc, cov, ovf_count, ovf_list, plist, gsoft, vimg, gfacc, part_fwd, reg_part, img_fwd, img_bwd, total;
+    size_t frec, zbuf, lacc, cov, ovf_count, ovf_list, plist, gsoft, vimg, gfacc, part_fwd, img_fwd, img_bwd, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -93,7 +93,6 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     const int rp = (c->nst + MM_WARPS - 1) / MM_WARPS;          // shading CTAs per image (8 sub-tiles each)
     const size_t np = (size_t)(rp > c->nparts_recon ? rp : c->nparts_recon);
     L.part_fwd = off; off = mm_align_up(off + (size_t)B * np * 4 * 4, 256);
-    L.reg_part = off; off = mm_align_up(off + (size_t)B * 8 * 4, 256);
     L.img_fwd = off;  off = mm_align_up(off + (size_t)B * 4 * 8, 256);
     L.img_bwd = off;  off = mm_align_up(off + (size_t)B * 12 * 8, 256);
     L.total = off;

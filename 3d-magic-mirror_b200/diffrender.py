@@ -222,7 +222,7 @@ class _MeshRegFn(torch.autograd.Function):
         h = dr._ctx(dev)
         with torch.cuda.device(dev):
             terms = torch.zeros(8, device=dev, dtype=torch.float32)
-            ws = h.workspace(B)
+            ws = torch.empty(B * 8, device=dev, dtype=torch.float32)
             rc = _lib.lib().mm_mesh_reg_forward(h.handle, B, _ptr(delta), _ptr(vertices), _ptr(fn), float(temp), float(eps),
                                                 1 if flip_l1 else 0, int(mask), _ptr(terms), _ptr(ws), _stream())
         _lib.check(rc, "mm_mesh_reg_forward")

@@ -136,9 +136,10 @@ int mm_ctx_set_regularizer_topology(mm_ctx* ctx, int E, const int32_t* edges_hos
 /* terms[8] (device, out) = laplacian, flat (the two summands of calc_reg_loss :412-451, before lambda_lpl / lambda_flat),
  * calc_reg_edge (:453), calc_reg_depth (:463), calc_reg_depthR (:468), calc_reg_depthC (:477), calc_reg_deform (:487),
  * recon_flip (:392; flip_l1 selects its L1 form).  term_mask bit k selects term k; an input a selected term does not need may
- * be NULL (delta_vertices [B,V,3]: terms 0,6,7; vertices [B,V,3]: 2-5; face_normals [B,F,3]: 1). */
+ * be NULL (delta_vertices [B,V,3]: terms 0,6,7; vertices [B,V,3]: 2-5; face_normals [B,F,3]: 1).
+ * scratch: caller-owned device floats [B,8] (per-image partial sums; reduced over the batch in image order). */
 int mm_mesh_reg_forward(mm_ctx* ctx, int B, const float* delta_vertices, const float* vertices, const float* face_normals,
-                        float temp, float eps, int flip_l1, unsigned term_mask, float* terms, void* workspace, void* stream);
+                        float temp, float eps, int flip_l1, unsigned term_mask, float* terms, float* scratch, void* stream);
 
 /* Gradient of sum_k g_terms[k] * term_k (g_terms: device [8]) w.r.t. the three inputs; outputs overwritten; a NULL input
  * goes with a NULL output. */
