@@ -37,6 +37,8 @@ SIGNATURES = {
                                   [c_int, c_void_p, c_float, c_float, c_float] + [c_void_p] * 2 + [c_void_p] * 3 +
                                   [c_void_p] * 8 + [c_void_p, c_void_p]),
     "mm_debug_export_faces": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mm_face_normals_forward": (c_int, [c_void_p, c_int] + [c_void_p] * 8),
+    "mm_face_normals_backward": (c_int, [c_void_p, c_int] + [c_void_p] * 13),
     "mm_ctx_set_regularizer_topology": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                                 c_void_p, c_void_p, c_float]),
     "mm_mesh_reg_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, ctypes.c_uint,

@@ -260,6 +260,36 @@ int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azi
     return check_launch("vertex_bwd");
 }
 
+int mm_face_normals_forward(mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev, const float* dist,
+                            const float* bias, float* face_normals, void* workspace, void* stream)
+{
+    MM_REQUIRE(c && B > 0 && B <= 65535, "ctx / B (1..65535)");
+    MM_REQUIRE(vertices && azim && elev && dist && bias && face_normals && workspace, "NULL argument");
+    const mm_ws_layout L = mm_ws_make(c, B);
+    char* ws = (char*)workspace;
+    mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg), face_normals,
+                         nullptr, (long long*)(ws + L.img_fwd), (long long*)(ws + L.img_bwd), nullptr, 0, nullptr, 0,
+                         (cudaStream_t)stream);
+    return check_launch("vertex_fwd");
+}
+
+int mm_face_normals_backward(mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev, const float* dist,
+                             const float* bias, const float* g_face_normals, float* g_vertices, float* g_azim, float* g_elev,
+                             float* g_dist, float* g_bias, void* workspace, void* stream)
+{
+    MM_REQUIRE(c && B > 0, "ctx / B");
+    MM_REQUIRE(vertices && azim && elev && dist && bias && g_face_normals && workspace, "NULL argument");
+    MM_REQUIRE(g_vertices && g_azim && g_elev && g_dist && g_bias, "NULL gradient output");
+    cudaStream_t s = (cudaStream_t)stream;
+    const mm_ws_layout L = mm_ws_make(c, B);
+    char* ws = (char*)workspace;
+    MM_CUDA(cudaMemsetAsync(ws + L.gfacc, 0, (size_t)B * c->F * 9 * 4, s));
+    mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, (const float*)(ws + L.gfacc), g_face_normals,
+                         (long long*)(ws + L.img_bwd), 0, g_vertices, g_azim, g_elev, g_dist, g_bias, nullptr, nullptr, nullptr,
+                         0.0f, 0.0f, s);
+    return check_launch("vertex_bwd");
+}
+
 int mm_recon_data_forward(mm_ctx* c, int B, const float* pred, const float* gt, float image_weight, float contour,
                           float* loss, float* iou_sums, void* workspace, void* stream)
 {

@@ -349,7 +349,7 @@ k_vertex_bwd(const VertexBwdParams q,
         g_azim[b] = k * (gcam[0] * (sc.d * sc.ce * sc.ca) + gcam[2] * (-sc.d * sc.ce * sc.sa));
     }
     // (4) light gradient: per-image fixed-point sums accumulated by the shading backward
-    if (rank == 1 && threadIdx.x < 9) {
+    if (rank == 1 && threadIdx.x < 9 && g_lights) {
         g_lights[b * 9 + threadIdx.x] = (float)((double)img_bwd[b * 12 + 1 + threadIdx.x] / 17592186044416.0);   // MM_FX_GRAD
         if (q.reset) img_bwd[b * 12 + 1 + threadIdx.x] = 0;     // stand-alone backward: leave the workspace reusable
     }

@@ -167,6 +167,47 @@ class _RenderFn(torch.autograd.Function):
         return None, None, None, g_v, g_az, g_el, g_di, g_bi, g_tex, g_li, g_bg
 
 
+class _FaceNormalsFn(torch.autograd.Function):
+    """Vertex stage alone: attributes['face_normals'] without rasterising (trainer.py:367 discards the image)."""
+
+    @staticmethod
+    def forward(ctx, dr, vertices, azim, elev, dist, biases):
+        for n, t in (("vertices", vertices), ("azimuths", azim), ("elevations", elev), ("distances", dist), ("biases", biases)):
+            _require_cuda(t, n)
+        dev = vertices.device
+        B = azim.shape[0]
+        vertices, azim, elev, dist = _f32c(vertices), _f32c(azim).reshape(-1), _f32c(elev).reshape(-1), _f32c(dist).reshape(-1)
+        biases = _f32c(biases)
+        if vertices.shape != (B, dr.num_vertices, 3):
+            raise ValueError("vertices must be (B,%d,3), got %s" % (dr.num_vertices, tuple(vertices.shape)))
+        h = dr._ctx(dev)
+        with torch.cuda.device(dev):
+            fn = torch.empty(B, dr.num_faces, 3, device=dev, dtype=torch.float32)
+            ws = h.workspace(B)
+            rc = _lib.lib().mm_face_normals_forward(h.handle, B, _ptr(vertices), _ptr(azim), _ptr(elev), _ptr(dist), _ptr(biases),
+                                                    _ptr(fn), _ptr(ws), _stream())
+        _lib.check(rc, "mm_face_normals_forward")
+        ctx.h = h
+        ctx.save_for_backward(vertices, azim, elev, dist, biases, ws)
+        return fn
+
+    @staticmethod
+    def backward(ctx, g_fn):
+        vertices, azim, elev, dist, biases, ws = ctx.saved_tensors
+        dev = vertices.device
+        B = azim.shape[0]
+        with torch.cuda.device(dev):
+            g_fn = _f32c(g_fn)
+            gv = torch.empty_like(vertices)
+            ga, ge, gd = torch.empty_like(azim), torch.empty_like(elev), torch.empty_like(dist)
+            gb = torch.empty_like(biases)
+            rc = _lib.lib().mm_face_normals_backward(ctx.h.handle, B, _ptr(vertices), _ptr(azim), _ptr(elev), _ptr(dist),
+                                                     _ptr(biases), _ptr(g_fn), _ptr(gv), _ptr(ga), _ptr(ge), _ptr(gd), _ptr(gb),
+                                                     _ptr(ws), _stream())
+        _lib.check(rc, "mm_face_normals_backward")
+        return None, gv, ga, ge, gd, gb
+
+
 class _ReconFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dr, image_weight, contour, pred, gt):
@@ -310,6 +351,12 @@ class DiffRender(object):
         textures = attributes['textures']
         lights = attributes['lights']
         want_idx = bool(attributes.get('_want_face_idx', False))
+        if not attributes.get('_need_image', True):
+            # the caller only wants the refreshed attributes (trainer.py:367 discards the image): vertex stage
+            # alone, no rasterisation.  Returns (None, attributes) with a differentiable 'face_normals'.
+            attributes['face_normals'] = _FaceNormalsFn.apply(self, vertices, azimuths, elevations, distances, biases)
+            attributes['imnormal'] = None
+            return None, attributes
         rgbs, face_normals, imnormal, face_idx = _RenderFn.apply(
             self, bool(no_mask), want_idx, vertices, azimuths, elevations, distances, biases, textures, lights,
             bg if no_mask else None)

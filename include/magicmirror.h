@@ -124,6 +124,15 @@ int mm_render_compare_fwd_bwd(mm_ctx* ctx, int B,
                               float* g_tex, float* g_lights, float* g_bg,
                               void* workspace, void* stream);
 
+/* ---- render de-duplication.  trainer.py:367 renders only to refresh attributes['face_normals'] (the image
+ * is discarded): these two calls run the vertex stage alone (prepare_vertices + face_normals, networks.py:284-290) and its
+ * backward from an upstream gradient of the face normals.  Same argument conventions as mm_render_forward / _backward. */
+int mm_face_normals_forward(mm_ctx* ctx, int B, const float* vertices, const float* azim, const float* elev, const float* dist,
+                            const float* bias, float* face_normals /* B,F,3 out */, void* workspace, void* stream);
+int mm_face_normals_backward(mm_ctx* ctx, int B, const float* vertices, const float* azim, const float* elev, const float* dist,
+                             const float* bias, const float* g_face_normals /* B,F,3 */, float* g_vertices, float* g_azim,
+                             float* g_elev, float* g_dist, float* g_bias, void* workspace, void* stream);
+
 /* ---- the mesh regularisers next to the render path (networks.py:392-491), one launch per direction.
  * Topology they need beyond mm_ctx_create's (DiffRender.__init__, networks.py:197-252): edges [E,2], edge2faces [E,2]
  * (faces sharing each edge), flip_index [V] (z-mirror partner), sign_init [V] (sign of the template depth) and the uniform

@@ -339,3 +339,21 @@ def test_mesh_regularisers_fused_kernel_vs_reference_golden(mm, mesh):
     assert np.allclose(vals.cpu().numpy(), z["values"], rtol=2e-5, atol=1e-8)
     assert pu.rel_err(gd.cpu(), torch.from_numpy(z["grad_delta"])) <= 2e-4
     assert pu.rel_err(gn.cpu(), torch.from_numpy(z["grad_face_normals"])) <= 2e-4
+
+
+def test_render_without_image_matches_full_render(mm):
+    """render(_need_image=False) = vertex stage only; face_normals and their gradient path must equal the
+    full render's (bitwise forward; backward through g_face_normals only)."""
+    dr, A = _cfg2(mm, B=6, seed=11)
+    keys = ('vertices', 'azimuths', 'elevations', 'distances', 'biases')
+    w = torch.randn(6, dr.num_faces, 3, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2))
+    grads = []
+    for need in (True, False):
+        Ag = {k: (v.clone().requires_grad_(k in keys) if torch.is_tensor(v) else v) for k, v in A.items()}
+        img, out = dr.render(no_mask=True, _need_image=need, **Ag)
+        assert (img is None) == (not need)
+        (out['face_normals'] * w).sum().backward()
+        grads.append((out['face_normals'].detach(), {k: Ag[k].grad.clone() for k in keys}))
+    assert torch.equal(grads[0][0], grads[1][0])
+    for k in keys:
+        assert pu.rel_err(grads[1][1][k], grads[0][1][k]) <= 1e-5, k
