@@ -356,4 +356,4 @@ def test_render_without_image_matches_full_render(mm):
         grads.append((out['face_normals'].detach(), {k: Ag[k].grad.clone() for k in keys}))
     assert torch.equal(grads[0][0], grads[1][0])
     for k in keys:
-        assert pu.rel_err(grads[1][1][k], grads[0][1][k]) <= 1e-5, k
+        assert pu.rel_err(grads[1][1][k], grads[0][1][k]) <= TOL_GRAD, k      # smem float atomics order; camera terms cancel
