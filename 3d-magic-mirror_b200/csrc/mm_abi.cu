@@ -240,7 +240,7 @@ int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azi
     const mm_ws_layout L = mm_ws_make(c, B);
     char* ws = (char*)workspace;
     const size_t HW = (size_t)c->H * c->W;
-    MM_CUDA(cudaMemsetAsync(ws + L.gfacc, 0, (size_t)B * c->F * 9 * 4, s));
+    MM_CUDA(cudaMemsetAsync(ws + L.gfacc, 0, (size_t)B * c->F * MM_GF * 4, s));
     MM_CUDA(cudaMemsetAsync(g_tex, 0, (size_t)B * 3 * Ht * Wt * 4, s));
     if (g_bg && !no_mask) MM_CUDA(cudaMemsetAsync(g_bg, 0, (size_t)B * 3 * HW * 4, s));
     mm_raster_params p;
@@ -283,7 +283,7 @@ int mm_face_normals_backward(mm_ctx* c, int B, const float* vertices, const floa
     cudaStream_t s = (cudaStream_t)stream;
     const mm_ws_layout L = mm_ws_make(c, B);
     char* ws = (char*)workspace;
-    MM_CUDA(cudaMemsetAsync(ws + L.gfacc, 0, (size_t)B * c->F * 9 * 4, s));
+    MM_CUDA(cudaMemsetAsync(ws + L.gfacc, 0, (size_t)B * c->F * MM_GF * 4, s));
     mm_launch_vertex_bwd(c, B, vertices, azim, elev, dist, bias, (const float*)(ws + L.gfacc), g_face_normals,
                          (long long*)(ws + L.img_bwd), 0, g_vertices, g_azim, g_elev, g_dist, g_bias, nullptr, nullptr, nullptr,
                          0.0f, 0.0f, s);

@@ -20,7 +20,7 @@
 //                             iy << 12 | ix: the backward soft pass replays this dense list
 //     gsoft      [B,H,W]      d(loss)/d(silhouette) per pixel, handed from the shading stage to the geometry backward
 //     vimg       [B,V,2]   unscaled image-plane xy (debug export / parity tests)
-//     gfacc      [B,F,9]   backward accumulators: d/d(fvi) (6, unscaled) + d/d(unit normal) (3)
+//     gfacc      [B,F,12]  backward accumulators: d/d(fvi) (6, unscaled) | pad (2) | d/d(unit normal) (3) | pad (1)
 //     part_fwd   [B,NP,4]  per-CTA partial sums of the stand-alone recon_data kernels (L1, N, D, contour)
 //     img_fwd    [B,4]     per-image sums (L1, N, D, contour) as fixed-point 64-bit integers (order-independent atomics)
 //     img_bwd    [B,12]    per-image sums (contour, 9 light gradients, -, -), same scheme
@@ -37,6 +37,8 @@
 #define MM_ST_W         8            // unfused shading kernels: one warp = one 8 x 4 pixel sub-tile
 #define MM_ST_H         4
 #define MM_REC_FLOATS   12
+#define MM_GF           12           // floats per face of the backward accumulator `gfacc`: d/d corners (6), pad (2), d/d unit
+                                     // normal (3), pad (1) -- 48 B, so the three groups are 16/8/16-byte aligned for vector REDs
 #define MM_MAX_KNUM     64
 
 struct mm_ctx {
@@ -89,7 +91,7 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     L.plist = off;    off = mm_align_up(off + (size_t)2 * B * c->H * c->W * 8, 256);
     L.gsoft = off;    off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.vimg = off;     off = mm_align_up(off + (size_t)B * c->V * 2 * 4, 256);
-    L.gfacc = off;    off = mm_align_up(off + (size_t)B * c->F * 9 * 4, 256);
+    L.gfacc = off;    off = mm_align_up(off + (size_t)B * c->F * MM_GF * 4, 256);
     const int rp = (c->nst + MM_WARPS - 1) / MM_WARPS;          // shading CTAs per image (8 sub-tiles each)
     const size_t np = (size_t)(rp > c->nparts_recon ? rp : c->nparts_recon);
     L.part_fwd = off; off = mm_align_up(off + (size_t)B * np * 4 * 4, 256);
@@ -131,7 +133,7 @@ struct mm_raster_params {
     const float* g_rgba;     // [B,4,H,W] or NULL
     float image_weight, contour, loss_scale;
     int analytic_loss;
-    float* gfacc;            // [B,F,9]
+    float* gfacc;            // [B,F,MM_GF]
     float* g_tex;            // [B,3,Ht,Wt]
     float* g_bg;             // [B,3,H,W] or NULL
     uint4* clr; size_t nclr;  // buffer the hard pass clears on the side (fused step: the texture-gradient output), 16-byte units

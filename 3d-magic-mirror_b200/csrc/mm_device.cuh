@@ -339,6 +339,21 @@ __device__ __forceinline__ unsigned long long depth_key(float z, int f) {
 }
 __device__ __forceinline__ int key_face(unsigned long long key) { return key ? (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull)) : -1; }
 
+// ------------------------------------------------------------------ vector reductions into the per-face accumulators
+// sm_90+: red.global.add.v4.f32 / .v2.f32 (SASS REDG.E.ADD.F32x4 / x2) -- one L2 reduction for a 16 / 8-byte aligned group
+// instead of one per float.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+// d/d(the six image-plane corner coordinates) of face record `g` (gfacc + face * MM_GF)
+__device__ __forceinline__ void red_add_corners(float* g, const float (&v)[6]) {
+    red_add_v4(g, v[0], v[1], v[2], v[3]);
+    red_add_v2(g + 4, v[4], v[5]);
+}
+
 // ------------------------------------------------------------------ TMA bulk copy (global -> shared) helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -226,7 +226,7 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
     for (int i = 0; i < 9; ++i) acc_l[i] = 0.0f;
     const float* rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
     const float* tb = p.tex + (size_t)b * 3 * p.Ht * p.Wt;
-    float* gacc = p.gfacc + (size_t)b * p.F * 9;
+    float* gacc = p.gfacc + (size_t)b * p.F * MM_GF;
     float* gtex = p.g_tex + (size_t)b * 3 * p.Ht * p.Wt;
     // (a texel-prefetch sub-pass ahead of this loop was measured: 43.7 -> 46.3 us, the kernel is not bound by that miss)
     #pragma unroll 1
@@ -343,16 +343,14 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
         const float dcx = l[1] * SH_C1 + l[4] * SH_C2 * ny + l[7] * SH_C4 * nz + l[8] * SH_C5 * 2.0f * nx;
         const float dcy = l[3] * SH_C1 + l[4] * SH_C2 * nx + l[5] * SH_C2 * nz - l[8] * SH_C5 * 2.0f * ny;
         const float dcz = l[2] * SH_C1 + l[5] * SH_C2 * ny + l[6] * SH_C3 * 2.0f * nz + l[7] * SH_C4 * nx;
-        float* ga = gacc + (size_t)f * 9;
+        float* ga = gacc + (size_t)f * MM_GF;
         const float gn_scale = g_coef * tm;
 #ifdef EXP_NO_ATOM
         if (gn_scale == 12345.0f) {
 #else
         if (gn_scale != 0.0f) {
 #endif
-            atomicAdd(ga + 6, gn_scale * dcx);
-            atomicAdd(ga + 7, gn_scale * dcy);
-            atomicAdd(ga + 8, gn_scale * dcz);
+            red_add_v4(ga + 8, gn_scale * dcx, gn_scale * dcy, gn_scale * dcz, 0.0f);
         }
         // hard rasteriser backward (DIBR_SPEC A.3) for the u,v channels.  Gradients carry a tolerance (unlike the visibility
         // decisions), so this block is written for instruction count, not for the reference's rounding sequence: the two
@@ -385,12 +383,8 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
             const float gbx = A1 * d1m + A2 * d2m, gby = A1 * d1p + A2 * d2p;      // d/d(bx), d/d(by)
             const float gcx = A1 * d1n + A2 * d2n, gcy = A1 * d1q + A2 * d2q;      // d/d(cx), d/d(cy)
             const float gsx = A1 * d1s + A2 * d2s, gsy = A1 * d1t + A2 * d2t;      // d/d(s), d/d(t)
-            atomicAdd(ga + 0, -(gbx + gcx + gsx));
-            atomicAdd(ga + 1, -(gby + gcy + gsy));
-            atomicAdd(ga + 2, gbx);
-            atomicAdd(ga + 3, gby);
-            atomicAdd(ga + 4, gcx);
-            atomicAdd(ga + 5, gcy);
+            red_add_v4(ga, -(gbx + gcx + gsx), -(gby + gcy + gsy), gbx, gby);
+            red_add_v2(ga + 4, gcx, gcy);
         }
     }
 

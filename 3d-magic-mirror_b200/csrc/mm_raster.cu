@@ -257,7 +257,7 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
             const int fg = sl * nwarps + gwarp;
             if (fg < p.B * p.F) {
                 const float v = wq.facc[kk][sl];
-                if (v != 0.0f) atomicAdd(p.gfacc + (size_t)fg * 9 + kk, v);
+                if (v != 0.0f) atomicAdd(p.gfacc + (size_t)fg * MM_GF + kk, v);
             }
         }
     }
@@ -313,7 +313,8 @@ __device__ __forceinline__ void soft_bwd_list_role(const mm_raster_params& p, Wa
     for (uint32_t i0 = ((uint32_t)vblock * SB_THREADS + threadIdx.x) & ~31u; i0 < n; i0 += stride) {
         const uint32_t i = i0 + lane;
         float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-        uint32_t fg = 0xffffffffu;
+        uint32_t fg = 0u;
+        bool live = false;
         if (i < n) {
             const unsigned long long e = p.plist[i];
             fg = (uint32_t)(e >> 32);
@@ -329,15 +330,12 @@ __device__ __forceinline__ void soft_bwd_list_role(const mm_raster_params& p, Wa
                 r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
                 r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
                 soft_pair_grad(p, r, pix_x(ix, p.W, p.sx), pix_y(iy, p.H, p.sy), kz, inv_mult, g, 1.0f - soft, ga);
+                live = true;
             }
         }
-        // one RED per non-zero component (vertex-type candidates touch 2 of the 6, edge-type 4); a warp-wide RED is ONE
-        // instruction, so pre-combining lanes that share a face with match_any + shuffles costs more than it saves
-        if (fg != 0xffffffffu) {
-            float* g = p.gfacc + (size_t)fg * 9;
-            #pragma unroll
-            for (int k = 0; k < 6; ++k) if (ga[k] != 0.0f) atomicAdd(g + k, ga[k]);
-        }
+        // the six corner gradients of the pair's face leave as one 16-byte + one 8-byte vector RED (a warp-wide RED is ONE
+        // instruction: pre-combining lanes that share a face with match_any + shuffles costs more than it saves)
+        if (live) red_add_corners(p.gfacc + (size_t)fg * MM_GF, ga);
     }
 }
 
@@ -441,9 +439,7 @@ __device__ __forceinline__ void soft_ovf_role(const mm_raster_params& p, uint32_
                     if (mine) {
                         float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
                         soft_pair_grad(p, r, px, py, kz, inv_mult, g, one_m_all, ga);
-                        float* gf = p.gfacc + ((size_t)b * p.F + f) * 9;
-                        #pragma unroll
-                        for (int q = 0; q < 6; ++q) if (ga[q] != 0.0f) atomicAdd(gf + q, ga[q]);
+                        red_add_corners(p.gfacc + ((size_t)b * p.F + f) * MM_GF, ga);
                     }
                 } else {
                     float prob = 0.0f;

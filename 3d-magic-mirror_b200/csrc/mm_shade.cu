@@ -149,7 +149,7 @@ k_shade_bwd(const mm_raster_params p)
     const float* rg = p.rgba + (size_t)b * 4 * HW;         // forward output
     const float* gtb = p.gt ? p.gt + (size_t)b * 4 * HW : nullptr;
     const float* gup = p.g_rgba ? p.g_rgba + (size_t)b * 4 * HW : nullptr;
-    float* gacc = p.gfacc + (size_t)b * p.F * 9;
+    float* gacc = p.gfacc + (size_t)b * p.F * MM_GF;
     float* gtex = p.g_tex + (size_t)b * 3 * p.Ht * p.Wt;
     const int st = blockIdx.x;
     {
@@ -294,12 +294,10 @@ k_shade_bwd(const mm_raster_params p)
                 const float dcx = l[1] * SH_C1 + l[4] * SH_C2 * ny + l[7] * SH_C4 * nz + l[8] * SH_C5 * 2.0f * nx;
                 const float dcy = l[3] * SH_C1 + l[4] * SH_C2 * nx + l[5] * SH_C2 * nz - l[8] * SH_C5 * 2.0f * ny;
                 const float dcz = l[2] * SH_C1 + l[5] * SH_C2 * ny + l[6] * SH_C3 * 2.0f * nz + l[7] * SH_C4 * nx;
-                float* g = gacc + (size_t)best_f * 9;
+                float* g = gacc + (size_t)best_f * MM_GF;
                 const float gn_scale = g_coef * tm;    // sum_i w_i * g_n
                 if (gn_scale != 0.0f) {
-                    atomicAdd(g + 6, gn_scale * dcx);
-                    atomicAdd(g + 7, gn_scale * dcy);
-                    atomicAdd(g + 8, gn_scale * dcz);
+                    red_add_v4(g + 8, gn_scale * dcx, gn_scale * dcy, gn_scale * dcz, 0.0f);
                 }
                 // hard rasteriser backward (DIBR_SPEC A.3) for the u,v channels
                 if (g_u != 0.0f || g_v != 0.0f) {
@@ -329,8 +327,7 @@ k_shade_bwd(const mm_raster_params p)
                         gv[4] += MUL(dldI, ADD(MUL(e1, dw1dn), MUL(e2, dw2dn)));
                         gv[5] += MUL(dldI, ADD(MUL(e1, dw1dq), MUL(e2, dw2dq)));
                     }
-                    #pragma unroll
-                    for (int i = 0; i < 6; ++i) atomicAdd(g + i, gv[i]);
+                    red_add_corners(g, gv);
                 }
             }
         }

@@ -145,9 +145,8 @@ k_vertex_fwd(const VertexFwdParams q,
             fn[0] = nx; fn[1] = ny; fn[2] = nz;
         }
         if (gfacc_zero) {
-            float* g = gfacc_zero + ((size_t)b * F + f) * 9;
-            #pragma unroll
-            for (int i = 0; i < 9; ++i) g[i] = 0.0f;
+            float4* g = reinterpret_cast<float4*>(gfacc_zero + ((size_t)b * F + f) * MM_GF);
+            g[0] = g[1] = g[2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
     }
 }
@@ -221,10 +220,12 @@ k_vertex_bwd(const VertexBwdParams q,
         for (int i = 0; i < 3; ++i) { P[i][0] = svc[idx[i] * 3]; P[i][1] = svc[idx[i] * 3 + 1]; P[i][2] = svc[idx[i] * 3 + 2]; }
         float ga[9];
         {
-            const float* gp = gfacc + ((size_t)b * F + f) * 9;
+            const float4* gp = reinterpret_cast<const float4*>(gfacc + ((size_t)b * F + f) * MM_GF);
+            const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
+            ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g2.x; ga[7] = g2.y; ga[8] = g2.z;
             bool any = g_face_normals != nullptr;
             #pragma unroll
-            for (int i = 0; i < 9; ++i) { ga[i] = gp[i]; any = any || (ga[i] != 0.0f); }
+            for (int i = 0; i < 9; ++i) any = any || (ga[i] != 0.0f);
             if (!any) continue;          // most faces (back-facing, interior, off-screen) received no gradient at all
         }
         float G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
