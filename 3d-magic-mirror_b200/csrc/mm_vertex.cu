@@ -416,8 +416,10 @@ void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const f
     q.V = c->V; q.F = c->F; q.nchunks = c->nchunks;
     q.proj_x = c->proj_x; q.proj_y = c->proj_y; q.multiplier = c->multiplier;
     const dim3 grid(c->nchunks, B);
-    k_vertex_fwd<<<grid, MM_VTHREADS, c->smem_vertex_fwd, s>>>(q, c->d_faces, vertices, azim, elev, dist, bias, frec,
-                                                               vimg, face_normals, gfacc_zero, img_fwd, img_bwd);
+    // programmatic launch here too: in a loop of steps the launch latency of this first kernel hides under the tail of whatever
+    // ran before on the stream (the prologue still waits for that work to complete before touching memory)
+    mm_launch(k_vertex_fwd, grid, dim3(MM_VTHREADS), c->smem_vertex_fwd, s, g_mm_pdl != 0, q, (const int32_t*)c->d_faces, vertices,
+              azim, elev, dist, bias, frec, vimg, face_normals, gfacc_zero, img_fwd, img_bwd);
 }
 
 void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
