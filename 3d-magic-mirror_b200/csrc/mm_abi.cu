@@ -65,6 +65,7 @@ int check_launch(const char* what) {
 void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int no_mask, mm_raster_params& p) {
     memset(&p, 0, sizeof(p));
     p.B = B; p.V = c->V; p.F = c->F; p.H = c->H; p.W = c->W; p.Ht = Ht; p.Wt = Wt;
+    p.Htp = c->tex_mirror ? Ht / 2 : Ht;
     p.nstx = c->nstx; p.nsty = c->nsty; p.nst = c->nst; p.knum = c->knum;
     p.sx = c->sx; p.sy = c->sy; p.blen = c->blen; p.multiplier = c->multiplier; p.eps = c->eps; p.sigmainv = c->sigmainv;
     p.no_mask = no_mask;
@@ -207,6 +208,7 @@ int mm_render_forward(mm_ctx* c, int B, const float* vertices, const float* azim
     MM_REQUIRE(c && B > 0 && B <= 65535, "ctx / B (1..65535)");
     MM_REQUIRE(vertices && azim && elev && dist && bias && tex && lights, "NULL input");
     MM_REQUIRE(Ht > 0 && Wt > 0, "texture size");
+    MM_REQUIRE(!c->tex_mirror || (Ht & 1) == 0, "a mirrored texture needs an even logical height Ht");
     MM_REQUIRE(!no_mask || bg, "no_mask=1 requires bg");
     MM_REQUIRE(rgba && workspace, "rgba / workspace");
     cudaStream_t s = (cudaStream_t)stream;
@@ -235,13 +237,14 @@ int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azi
     MM_REQUIRE(vertices && azim && elev && dist && bias && tex && lights, "NULL input");
     MM_REQUIRE(!no_mask || bg, "no_mask=1 requires bg");
     MM_REQUIRE(rgba && g_rgba && workspace, "rgba / g_rgba / workspace");
+    MM_REQUIRE(Ht > 0 && Wt > 0 && (!c->tex_mirror || (Ht & 1) == 0), "texture size (even Ht for a mirrored texture)");
     MM_REQUIRE(g_vertices && g_azim && g_elev && g_dist && g_bias && g_tex && g_lights, "NULL gradient output");
     cudaStream_t s = (cudaStream_t)stream;
     const mm_ws_layout L = mm_ws_make(c, B);
     char* ws = (char*)workspace;
     const size_t HW = (size_t)c->H * c->W;
     MM_CUDA(cudaMemsetAsync(ws + L.gfacc, 0, (size_t)B * c->F * MM_GF * 4, s));
-    MM_CUDA(cudaMemsetAsync(g_tex, 0, (size_t)B * 3 * Ht * Wt * 4, s));
+    MM_CUDA(cudaMemsetAsync(g_tex, 0, (size_t)B * 3 * (c->tex_mirror ? Ht / 2 : Ht) * Wt * 4, s));
     if (g_bg && !no_mask) MM_CUDA(cudaMemsetAsync(g_bg, 0, (size_t)B * 3 * HW * 4, s));
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, no_mask, p);
@@ -333,6 +336,7 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     MM_REQUIRE(c && B > 0, "ctx / B");
     MM_REQUIRE(vertices && azim && elev && dist && bias && tex && lights && gt, "NULL input");
     MM_REQUIRE(Ht > 0 && Wt > 0, "texture size");
+    MM_REQUIRE(!c->tex_mirror || (Ht & 1) == 0, "a mirrored texture needs an even logical height Ht");
     MM_REQUIRE(!no_mask || bg, "no_mask=1 requires bg");
     MM_REQUIRE(rgba && loss && workspace, "rgba / loss / workspace");
     MM_REQUIRE(g_vertices && g_azim && g_elev && g_dist && g_bias && g_tex && g_lights, "NULL gradient output");
@@ -342,7 +346,7 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     const size_t HW = (size_t)c->H * c->W;
     if (g_bg && !no_mask) MM_CUDA(cudaMemsetAsync(g_bg, 0, (size_t)B * 3 * HW * 4, s));
     if (c->timing) cudaEventRecord(c->ev[0], s);
-    const size_t gtex_bytes = (size_t)B * 3 * Ht * Wt * 4;
+    const size_t gtex_bytes = (size_t)B * 3 * (c->tex_mirror ? Ht / 2 : Ht) * Wt * 4;
     const bool gtex_side = (((uintptr_t)g_tex & 15) == 0) && ((gtex_bytes & 15) == 0);     // cleared by the hard pass on the side
     if (!gtex_side) MM_CUDA(cudaMemsetAsync(g_tex, 0, gtex_bytes, s));
     launch_vertex_fwd(c, B, L, ws, vertices, azim, elev, dist, bias, face_normals, true, nullptr, 0, s);
@@ -467,6 +471,12 @@ int mm_mesh_reg_backward(mm_ctx* c, int B, const float* delta_vertices, const fl
     mm_launch_meshreg_bwd(c, B, delta_vertices, vertices, face_normals, temp, eps, flip_l1, term_mask, g_terms, g_delta,
                           g_vertices, g_face_normals, (cudaStream_t)stream);
     return check_launch("meshreg_bwd");
+}
+
+int mm_ctx_set_texture_mirror(mm_ctx* c, int enable) {
+    MM_REQUIRE(c, "ctx");
+    c->tex_mirror = enable ? 1 : 0;
+    return MM_OK;
 }
 
 int mm_ctx_set_timing(mm_ctx* c, int enable) {

@@ -57,6 +57,7 @@ struct mm_ctx {
     size_t smem_vertex_fwd;  // dynamic smem bytes of the vertex forward kernel
     int num_sms;
     int split;               // fused step: 1 = soft pass and RGB shading in one launch + k_alpha (MM_SPLIT=1), 0 = sequential (default)
+    int tex_mirror;          // 1: tex / g_tex hold the top half of a vertically mirrored atlas (mm_ctx_set_texture_mirror)
     unsigned plist_cap_max;  // test hook (MM_PLIST_CAP): caps the forward's pair list so that the backward's fallback path runs
     // device arrays
     int32_t* d_faces;        // [F,3]
@@ -104,6 +105,7 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
 // parameters shared by the raster kernels (passed by value)
 struct mm_raster_params {
     int B, V, F, H, W, Ht, Wt;
+    int Htp;                 // physical texture rows: Ht, or Ht/2 for a mirrored texture (mm_ctx_set_texture_mirror)
     int nstx, nsty, nst, knum;
     float sx, sy, blen, multiplier, eps, sigmainv;
     int no_mask;
@@ -119,7 +121,7 @@ struct mm_raster_params {
     float* gsoft;            // [B,H,W]
     int gsoft_iou_pending;   // 1: `gsoft` holds upstream + contour terms only; consumers add the IoU term (per-image sums) on the fly
     const float* face_uvs;   // [F,6]
-    const float* tex;        // [B,3,Ht,Wt]
+    const float* tex;        // [B,3,Htp,Wt]
     const float* lights;     // [B,9]
     const float* bg;         // [B,3,H,W] or NULL
     const float* gt;         // [B,4,H,W] or NULL
@@ -134,7 +136,7 @@ struct mm_raster_params {
     float image_weight, contour, loss_scale;
     int analytic_loss;
     float* gfacc;            // [B,F,MM_GF]
-    float* g_tex;            // [B,3,Ht,Wt]
+    float* g_tex;            // [B,3,Htp,Wt]
     float* g_bg;             // [B,3,H,W] or NULL
     uint4* clr; size_t nclr;  // buffer the hard pass clears on the side (fused step: the texture-gradient output), 16-byte units
 };

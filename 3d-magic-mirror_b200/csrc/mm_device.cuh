@@ -206,14 +206,20 @@ struct TexFetch {
     float nw, ne, sw, se;
 };
 
-__device__ __forceinline__ TexFetch tex_fetch(const float* __restrict__ plane, const Bilin& s, int Ht, int Wt) {
+// the reference's TextureEncoder emits cat([t, t.flip(2)], dim=2) (model_res.py:609-610).  With a mirrored
+// texture the caller hands over t alone ([B,3,Htp,Wt], Htp = Ht/2) and logical atlas row r lives in physical row
+// r < Htp ? r : Ht-1-r; same texels, same weights, half the texture bytes.  Htp == Ht for a plain atlas (identity map).
+__device__ __forceinline__ int tex_row(int r, int Ht, int Htp) { return r < Htp ? r : Ht - 1 - r; }
+
+__device__ __forceinline__ TexFetch tex_fetch(const float* __restrict__ plane, const Bilin& s, int Ht, int Wt, int Htp) {
     TexFetch t;
     const bool xe = (s.ix + 1) < Wt, ys = (s.iy + 1) < Ht;
-    const float* p = plane + (size_t)s.iy * Wt + s.ix;
-    t.nw = __ldg(p);
-    t.ne = xe ? __ldg(p + 1) : 0.0f;
-    t.sw = ys ? __ldg(p + Wt) : 0.0f;
-    t.se = (xe && ys) ? __ldg(p + Wt + 1) : 0.0f;
+    const float* p0 = plane + (size_t)tex_row(s.iy, Ht, Htp) * Wt + s.ix;
+    const float* p1 = plane + (size_t)tex_row(ys ? s.iy + 1 : s.iy, Ht, Htp) * Wt + s.ix;
+    t.nw = __ldg(p0);
+    t.ne = xe ? __ldg(p0 + 1) : 0.0f;
+    t.sw = ys ? __ldg(p1) : 0.0f;
+    t.se = (xe && ys) ? __ldg(p1 + 1) : 0.0f;
     return t;
 }
 

@@ -225,9 +225,9 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
     #pragma unroll
     for (int i = 0; i < 9; ++i) acc_l[i] = 0.0f;
     const float* rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
-    const float* tb = p.tex + (size_t)b * 3 * p.Ht * p.Wt;
+    const float* tb = p.tex + (size_t)b * 3 * p.Htp * p.Wt;
     float* gacc = p.gfacc + (size_t)b * p.F * MM_GF;
-    float* gtex = p.g_tex + (size_t)b * 3 * p.Ht * p.Wt;
+    float* gtex = p.g_tex + (size_t)b * 3 * p.Htp * p.Wt;
     // (a texel-prefetch sub-pass ahead of this loop was measured: 43.7 -> 46.3 us, the kernel is not bound by that miss)
     #pragma unroll 1
     for (int i = threadIdx.x; i < count; i += FUSED_THREADS) {
@@ -280,7 +280,7 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
 #ifdef EXP_NO_TEXLD
             tf[ch].nw = bl.nw + ch; tf[ch].ne = bl.ne; tf[ch].sw = bl.sw * 0.5f; tf[ch].se = bl.se + 0.1f;
 #else
-            tf[ch] = tex_fetch(tb + (size_t)ch * p.Ht * p.Wt, bl, p.Ht, p.Wt);
+            tf[ch] = tex_fetch(tb + (size_t)ch * p.Htp * p.Wt, bl, p.Ht, p.Wt, p.Htp);
 #endif
             tcol[ch] = tex_blend(tf[ch], bl);
         }
@@ -316,6 +316,7 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
         // texture gradient + d/d(u,v)
         float gix = 0.0f, giy = 0.0f;
         const bool xe = (bl.ix + 1) < p.Wt, ys = (bl.iy + 1) < p.Ht;
+        const int tr0 = tex_row(bl.iy, p.Ht, p.Htp), tr1 = tex_row(ys ? bl.iy + 1 : bl.iy, p.Ht, p.Htp);
         const float txf = bl.x - (float)bl.ix, tyf = bl.y - (float)bl.iy;
         #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
@@ -325,11 +326,12 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
 #else
             if (g != 0.0f) {
 #endif
-                float* gp = gtex + ((size_t)ch * p.Ht + bl.iy) * p.Wt + bl.ix;
+                float* gp = gtex + ((size_t)ch * p.Htp + tr0) * p.Wt + bl.ix;
+                float* gq = gtex + ((size_t)ch * p.Htp + tr1) * p.Wt + bl.ix;
                 atomicAdd(gp, g * bl.nw);
                 if (xe) atomicAdd(gp + 1, g * bl.ne);
-                if (ys) atomicAdd(gp + p.Wt, g * bl.sw);
-                if (xe && ys) atomicAdd(gp + p.Wt + 1, g * bl.se);
+                if (ys) atomicAdd(gq, g * bl.sw);
+                if (xe && ys) atomicAdd(gq + 1, g * bl.se);
                 gix += g * ((tf[ch].ne - tf[ch].nw) * (1.0f - tyf) + (tf[ch].se - tf[ch].sw) * tyf);
                 giy += g * ((tf[ch].sw - tf[ch].nw) * (1.0f - txf) + (tf[ch].se - tf[ch].ne) * txf);
             }

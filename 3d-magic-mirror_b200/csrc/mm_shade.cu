@@ -70,10 +70,10 @@ k_shade_fwd(const mm_raster_params p)
                 nrm[2] = interp3(w0, w1, w2, r.nz, r.nz, r.nz);
                 Bilin bl;
                 bilin_setup(u, v, p.Ht, p.Wt, bl);
-                const float* tb = p.tex + (size_t)b * 3 * p.Ht * p.Wt;
+                const float* tb = p.tex + (size_t)b * 3 * p.Htp * p.Wt;
                 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    const TexFetch t = tex_fetch(tb + (size_t)ch * p.Ht * p.Wt, bl, p.Ht, p.Wt);
+                    const TexFetch t = tex_fetch(tb + (size_t)ch * p.Htp * p.Wt, bl, p.Ht, p.Wt, p.Htp);
                     tcol[ch] = tex_blend(t, bl);
                 }
             }
@@ -150,7 +150,7 @@ k_shade_bwd(const mm_raster_params p)
     const float* gtb = p.gt ? p.gt + (size_t)b * 4 * HW : nullptr;
     const float* gup = p.g_rgba ? p.g_rgba + (size_t)b * 4 * HW : nullptr;
     float* gacc = p.gfacc + (size_t)b * p.F * MM_GF;
-    float* gtex = p.g_tex + (size_t)b * 3 * p.Ht * p.Wt;
+    float* gtex = p.g_tex + (size_t)b * 3 * p.Htp * p.Wt;
     const int st = blockIdx.x;
     {
         const int sty = st / p.nstx, stx = st - sty * p.nstx;
@@ -235,10 +235,10 @@ k_shade_bwd(const mm_raster_params p)
                 nrm[1] = interp3(bar.w0, bar.w1, bar.w2, r.ny, r.ny, r.ny);
                 nrm[2] = interp3(bar.w0, bar.w1, bar.w2, r.nz, r.nz, r.nz);
                 bilin_setup(u, v, p.Ht, p.Wt, bl);
-                const float* tb = p.tex + (size_t)b * 3 * p.Ht * p.Wt;
+                const float* tb = p.tex + (size_t)b * 3 * p.Htp * p.Wt;
                 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    tf[ch] = tex_fetch(tb + (size_t)ch * p.Ht * p.Wt, bl, p.Ht, p.Wt);
+                    tf[ch] = tex_fetch(tb + (size_t)ch * p.Htp * p.Wt, bl, p.Ht, p.Wt, p.Htp);
                     tcol[ch] = tex_blend(tf[ch], bl);
                 }
             }
@@ -270,16 +270,18 @@ k_shade_bwd(const mm_raster_params p)
                 // texture gradient + d/d(u,v)
                 float gix = 0.0f, giy = 0.0f;
                 const bool xe = (bl.ix + 1) < p.Wt, ys = (bl.iy + 1) < p.Ht;
+                const int tr0 = tex_row(bl.iy, p.Ht, p.Htp), tr1 = tex_row(ys ? bl.iy + 1 : bl.iy, p.Ht, p.Htp);
                 const float tx = bl.x - (float)bl.ix, ty = bl.y - (float)bl.iy;
                 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     const float g = g_tcol[ch];
                     if (g != 0.0f) {
-                        float* gp = gtex + ((size_t)ch * p.Ht + bl.iy) * p.Wt + bl.ix;
+                        float* gp = gtex + ((size_t)ch * p.Htp + tr0) * p.Wt + bl.ix;
+                        float* gq = gtex + ((size_t)ch * p.Htp + tr1) * p.Wt + bl.ix;
                         atomicAdd(gp, g * bl.nw);
                         if (xe) atomicAdd(gp + 1, g * bl.ne);
-                        if (ys) atomicAdd(gp + p.Wt, g * bl.sw);
-                        if (xe && ys) atomicAdd(gp + p.Wt + 1, g * bl.se);
+                        if (ys) atomicAdd(gq, g * bl.sw);
+                        if (xe && ys) atomicAdd(gq + 1, g * bl.se);
                         gix += g * ((tf[ch].ne - tf[ch].nw) * (1.0f - ty) + (tf[ch].se - tf[ch].sw) * ty);
                         giy += g * ((tf[ch].sw - tf[ch].nw) * (1.0f - tx) + (tf[ch].se - tf[ch].ne) * tx);
                     }

@@ -85,6 +85,23 @@ class _CtxHandle(object):
             pass
 
 
+class _TexMirror(object):
+    """Scope in which the ctx reads `textures` as the upper half of a vertically mirrored atlas (SURVEY 8f-3,
+    mm_ctx_set_texture_mirror); the switch is put back on exit so the ctx stays stateless between calls."""
+
+    def __init__(self, h, on):
+        self.h, self.on = h, bool(on)
+
+    def __enter__(self):
+        if self.on:
+            _lib.check(_lib.lib().mm_ctx_set_texture_mirror(self.h.handle, 1), "mm_ctx_set_texture_mirror")
+
+    def __exit__(self, *exc):
+        if self.on:
+            _lib.lib().mm_ctx_set_texture_mirror(self.h.handle, 0)
+        return False
+
+
 def _require_cuda(t, name):
     if not t.is_cuda:
         raise _lib.MagicMirrorError(
@@ -94,7 +111,7 @@ def _require_cuda(t, name):
 
 class _RenderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, dr, no_mask, want_face_idx, vertices, azim, elev, dist, biases, textures, lights, bg):
+    def forward(ctx, dr, no_mask, want_face_idx, tex_mirror, vertices, azim, elev, dist, biases, textures, lights, bg):
         for n, t in (("vertices", vertices), ("azimuths", azim), ("elevations", elev), ("distances", dist),
                      ("biases", biases), ("textures", textures), ("lights", lights)):
             _require_cuda(t, n)
@@ -118,9 +135,9 @@ class _RenderFn(torch.autograd.Function):
                 raise ValueError("bg must be (B,3,%d,%d), got %s" % (H, W, tuple(bg.shape)))
         else:
             bg = None
-        Ht, Wt = textures.shape[2], textures.shape[3]
+        Ht, Wt = textures.shape[2] * (2 if tex_mirror else 1), textures.shape[3]
         h = dr._ctx(dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _TexMirror(h, tex_mirror):
             rgba = torch.empty(B, 4, H, W, device=dev, dtype=torch.float32)
             fn = torch.empty(B, F, 3, device=dev, dtype=torch.float32)
             imn = torch.empty(B, H, W, 3, device=dev, dtype=torch.float32)
@@ -131,7 +148,7 @@ class _RenderFn(torch.autograd.Function):
                                               1 if no_mask else 0, _ptr(rgba), _ptr(fn), _ptr(imn), _ptr(fidx),
                                               _ptr(ws), _stream())
         _lib.check(rc, "mm_render_forward")
-        ctx.dr, ctx.no_mask, ctx.h = dr, bool(no_mask), h
+        ctx.dr, ctx.no_mask, ctx.h, ctx.tex_mirror = dr, bool(no_mask), h, bool(tex_mirror)
         ctx.has_bg = bg is not None
         ctx.save_for_backward(vertices, azim, elev, dist, biases, textures, lights,
                               bg if bg is not None else torch.empty(0, device=dev), rgba, ws)
@@ -148,12 +165,12 @@ class _RenderFn(torch.autograd.Function):
         dev = vertices.device
         B = azim.shape[0]
         bg_t = bg if ctx.has_bg else None
-        Ht, Wt = textures.shape[2], textures.shape[3]
+        Ht, Wt = textures.shape[2] * (2 if ctx.tex_mirror else 1), textures.shape[3]
         if g_rgba is None:
             g_rgba = torch.zeros_like(rgba)
         g_rgba = _f32c(g_rgba)
         g_fn = _f32c(g_fn) if g_fn is not None else None
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _TexMirror(h, ctx.tex_mirror):
             g_v = torch.empty_like(vertices)
             g_az, g_el, g_di = torch.empty_like(azim), torch.empty_like(elev), torch.empty_like(dist)
             g_bi, g_tex, g_li = torch.empty_like(biases), torch.empty_like(textures), torch.empty_like(lights)
@@ -164,7 +181,7 @@ class _RenderFn(torch.autograd.Function):
                                                _ptr(g_v), _ptr(g_az), _ptr(g_el), _ptr(g_di), _ptr(g_bi),
                                                _ptr(g_tex), _ptr(g_li), _ptr(g_bg), _ptr(ws), _stream())
         _lib.check(rc, "mm_render_backward")
-        return None, None, None, g_v, g_az, g_el, g_di, g_bi, g_tex, g_li, g_bg
+        return None, None, None, None, g_v, g_az, g_el, g_di, g_bi, g_tex, g_li, g_bg
 
 
 class _FaceNormalsFn(torch.autograd.Function):
@@ -351,6 +368,9 @@ class DiffRender(object):
         textures = attributes['textures']
         lights = attributes['lights']
         want_idx = bool(attributes.get('_want_face_idx', False))
+        # TextureEncoder emits cat([t, t.flip(2)], 2) (model_res.py:609-610).  With _tex_mirror=True pass t itself
+        # as 'textures' ((B,3,Ht/2,Wt)): same image bit for bit, d/dt = the sum over both halves, half the texture traffic.
+        tex_mirror = bool(attributes.get('_tex_mirror', False))
         if not attributes.get('_need_image', True):
             # the caller only wants the refreshed attributes (trainer.py:367 discards the image): vertex stage
             # alone, no rasterisation.  Returns (None, attributes) with a differentiable 'face_normals'.
@@ -358,7 +378,7 @@ class DiffRender(object):
             attributes['imnormal'] = None
             return None, attributes
         rgbs, face_normals, imnormal, face_idx = _RenderFn.apply(
-            self, bool(no_mask), want_idx, vertices, azimuths, elevations, distances, biases, textures, lights,
+            self, bool(no_mask), want_idx, tex_mirror, vertices, azimuths, elevations, distances, biases, textures, lights,
             bg if no_mask else None)
         attributes['face_normals'] = face_normals
         attributes['imnormal'] = imnormal          # visualisation only
@@ -374,7 +394,7 @@ class DiffRender(object):
         return loss
 
     def render_compare(self, gt_data, no_mask=False, contour=0, loss_scale=1.0, g_rgba_extra=None,
-                       g_face_normals=None, **attributes):
+                       g_face_normals=None, tex_mirror=False, **attributes):
         """Fused render -> recon_data -> backward (mm_render_compare_fwd_bwd): one call returns the loss
         parts, the rendered RGBA and d(loss_scale*loss_data [+ <g_rgba_extra, rgba>])/d(every attribute).
         Equivalent to trainer.py:276 + :441 + the autograd walk of :509 for the data term."""
@@ -388,9 +408,9 @@ class DiffRender(object):
         gt = _f32c(gt_data)
         B = azim.shape[0]
         H, W, F = self.height, self.image_size, self.num_faces
-        Ht, Wt = textures.shape[2], textures.shape[3]
+        Ht, Wt = textures.shape[2] * (2 if tex_mirror else 1), textures.shape[3]
         h = self._ctx(dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _TexMirror(h, tex_mirror):
             out = {
                 'rgba': torch.empty(B, 4, H, W, device=dev), 'face_normals': torch.empty(B, F, 3, device=dev),
                 'loss': torch.empty(4, device=dev),

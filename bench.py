@@ -137,9 +137,10 @@ def build_workload(mm, device, rank, nsets=NSETS, B=B_PER_GPU):
 class FusedRunner(object):
     """Pre-allocates everything and calls mm_render_compare_fwd_bwd directly (inputs resident in HBM)."""
 
-    def __init__(self, mm, dr, sets_cpu, device):
+    def __init__(self, mm, dr, sets_cpu, device, tex_mirror=False):
         import torch
         self.torch, self.mm, self.dr, self.dev = torch, mm, dr, device
+        self.tex_mirror = tex_mirror      # SURVEY 8(f)-3 variant: the texture's upper half only (not the headline workload)
         self.L = mm.lib()
         self.h = dr._ctx(torch.device(device))
         self.sets = []
@@ -148,6 +149,8 @@ class FusedRunner(object):
         H, W, F = dr.height, dr.image_size, dr.num_faces
         for A, G in sets_cpu:
             d = {k: v.to(device).contiguous() for k, v in A.items()}
+            if tex_mirror:
+                d['textures'] = d['textures'][:, :, :d['textures'].shape[2] // 2].contiguous()
             with torch.no_grad():
                 gt, _ = dr.render(no_mask=True, **{k: v.to(device) for k, v in G.items()})
             d['gt'] = gt.contiguous()
@@ -165,13 +168,17 @@ class FusedRunner(object):
         d = self.sets[i % len(self.sets)]
         o = d['out']
         p = lambda t: ctypes.c_void_p(t.data_ptr())     # noqa: E731
-        Ht, Wt = d['textures'].shape[2], d['textures'].shape[3]
+        Ht, Wt = d['textures'].shape[2] * (2 if self.tex_mirror else 1), d['textures'].shape[3]
+        if self.tex_mirror:
+            self.L.mm_ctx_set_texture_mirror(self.h.handle, 1)
         rc = self.L.mm_render_compare_fwd_bwd(
             self.h.handle, self.B, p(d['vertices']), p(d['azimuths']), p(d['elevations']), p(d['distances']),
             p(d['biases']), p(d['textures']), Ht, Wt, p(d['lights']), p(d['bg']), 1, p(d['gt']),
             1.0, contour, 1.0, ctypes.c_void_p(0), ctypes.c_void_p(0), p(o['rgba']), p(o['fn']), p(o['loss']),
             p(o['g_v']), p(o['g_az']), p(o['g_el']), p(o['g_di']), p(o['g_bi']), p(o['g_tex']), p(o['g_li']),
             p(o['g_bg']), p(o['ws']), ctypes.c_void_p(self.stream.cuda_stream))
+        if self.tex_mirror:
+            self.L.mm_ctx_set_texture_mirror(self.h.handle, 0)
         if rc != 0:
             raise RuntimeError(self.L.mm_last_error().decode())
         return o

@@ -156,6 +156,14 @@ int mm_mesh_reg_backward(mm_ctx* ctx, int B, const float* delta_vertices, const 
                          float temp, float eps, int flip_l1, unsigned term_mask, const float* g_terms,
                          float* g_delta_vertices, float* g_vertices, float* g_face_normals, void* stream);
 
+/* ---- the atlas the renderer reads is produced as cat([t, t.flip(2)], dim=2) (TextureEncoder.forward,
+ * network/model_res.py:609-610): its lower half is the upper half upside down.  With the mirror switch on, every call on
+ * `ctx` takes `tex` / `g_tex` as the UPPER HALF alone, [B,3,Ht/2,Wt], while `Ht` stays the logical atlas height (even):
+ * logical row r >= Ht/2 is read from (and its gradient accumulated into) physical row Ht-1-r.  Same texels, same weights
+ * as rendering the concatenated atlas -- the image is bit-identical, g_tex equals the sum of the two halves' gradients --
+ * with half the texture bytes read, cleared and written.  Host-side switch; takes effect on the next call. */
+int mm_ctx_set_texture_mirror(mm_ctx* ctx, int enable);
+
 /* Test hook: copies the vertex-stage products of the last forward on `workspace`
  * (what kaolin prepare_vertices returns, networks.py:284-287) so that the oracle's
  * rasteriser can be run on bit-identical inputs.  Any pointer may be NULL.

@@ -357,3 +357,51 @@ def test_render_without_image_matches_full_render(mm):
     assert torch.equal(grads[0][0], grads[1][0])
     for k in keys:
         assert pu.rel_err(grads[1][1][k], grads[0][1][k]) <= TOL_GRAD, k      # smem float atomics order; camera terms cancel
+
+
+@pytest.mark.parametrize("size,ratio,mesh", [(128, 1, "ellipsoid"), (64, 2, "smpl_uv_642"), (30, 1.2, "icosphere")])
+def test_mirrored_texture_equals_concatenated_atlas(mm, size, ratio, mesh):
+    """TextureEncoder hands the renderer cat([t, t.flip(2)], 2) (model_res.py:609-610).  render(_tex_mirror=True)
+    on t alone must give the SAME image bit for bit (same texels, same weights), and d/dt must equal autograd's sum over the two
+    halves of the atlas gradient (float atomics order only); same through the unfused and the fused entry points."""
+    B = 4
+    dr = mm.DiffRender(pu.get_mesh(mm, mesh), size, ratio=ratio, init_ellipsoid=2 if ratio == 2 else 1, image_weight=1.0)
+    H, W = dr.height, dr.image_size
+    A = pu.to_device(pu.make_attributes(dr.vertices_init, B, H, W, 77, Ht=H, Wt=W), DEV)          # 'textures' = the half t
+    G = pu.to_device(pu.make_attributes(dr.vertices_init, B, H, W, 78), DEV)
+    with torch.no_grad():
+        gt, _ = dr.render(no_mask=True, **G)
+    half = A['textures']
+    keys = ('vertices', 'azimuths', 'elevations', 'distances', 'biases', 'lights', 'bg')
+    res = []
+    for mirror in (False, True):
+        Ag = {k: (v.clone().requires_grad_(k in keys) if torch.is_tensor(v) else v) for k, v in A.items()}
+        t = half.clone().requires_grad_(True)
+        Ag['textures'] = t if mirror else torch.cat([t, t.flip([2])], dim=2)
+        rgb, _ = dr.render(no_mask=True, _tex_mirror=mirror, **Ag)
+        loss = dr.recon_data(rgb, gt, no_mask=True, contour=0.1)
+        loss.backward()
+        res.append((rgb.detach(), loss.detach(), t.grad.clone(), {k: Ag[k].grad.clone() for k in keys}))
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
+    assert float(res[0][2].abs().max()) > 0
+    assert pu.rel_err(res[1][2], res[0][2]) <= 1e-5
+    for k in keys:
+        assert pu.rel_err(res[1][3][k], res[0][3][k]) <= TOL_GRAD, k
+    # fused entry point: mirrored half vs concatenated atlas
+    full = torch.cat([half, half.flip([2])], dim=2)
+    Af = {k: v for k, v in A.items() if k != 'textures'}
+    o0 = dr.render_compare(gt, no_mask=True, contour=0.1, textures=full, **Af)
+    o1 = dr.render_compare(gt, no_mask=True, contour=0.1, tex_mirror=True, textures=half, **Af)
+    assert torch.equal(o0['rgba'], o1['rgba']) and torch.equal(o0['rgba'], res[0][0])
+    assert torch.equal(o0['loss'], o1['loss'])
+    g_full = o0['g_textures']
+    assert o1['g_textures'].shape == half.shape
+    assert pu.rel_err(o1['g_textures'], g_full[:, :, :H] + g_full[:, :, H:].flip([2])) <= 1e-5
+    assert pu.rel_err(o1['g_textures'], res[0][2]) <= 1e-5
+    for k in ('vertices', 'azimuths', 'lights', 'bg'):
+        assert pu.rel_err(o1['g_' + k], o0['g_' + k]) <= TOL_GRAD, k
+    # the switch does not leak into the next call on the same ctx
+    with torch.no_grad():
+        again, _ = dr.render(no_mask=True, **{**Af, 'textures': full})
+    assert torch.equal(again, res[0][0])

@@ -33,3 +33,9 @@ for i in range(n):
     for j in range(7): acc[j] += buf[j]
 L.mm_ctx_set_timing(h, 0)
 print("ms_per_step %.4f  img/s %.0f  kernels_us %s" % (ms, 48 / ms * 1e3, {k: round(1e3 * a / n, 1) for k, a in zip(bench.KERNELS, acc)}), flush=True)
+
+# SURVEY 8(f)-3 variant: mirrored texture (the upper half of the atlas only); informational, not the headline workload
+fm = bench.FusedRunner(mm, dr, sets, dev, tex_mirror=True)
+for i in range(10): fm.step(i)
+msm = bench.timed(torch, 1, fm.step, steps) / steps
+print("mirrored-texture variant: ms_per_step %.4f  img/s %.0f" % (msm, 48 / msm * 1e3), flush=True)
