@@ -355,6 +355,8 @@ def main():
     device = "cuda:%d" % local_rank
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its version banner (and NCCL_DEBUG output) to stdout by default: stdout carries the ONE JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(device))
     if not os.path.exists(os.path.join(g.PKG_DIR, "libmagicmirror.so")):
         g.build_cuda()
