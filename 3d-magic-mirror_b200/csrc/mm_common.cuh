@@ -41,6 +41,8 @@
                                      // normal (3), pad (1) -- 48 B, so the three groups are 16/8/16-byte aligned for vector REDs
 #define MM_MAX_KNUM     64
 
+#define MM_MAX_PARTS 4
+
 struct mm_ctx {
     int device;
     int V, F, H, W;
@@ -71,6 +73,10 @@ struct mm_ctx {
     // measurement hook (mm_ctx_set_timing)
     int timing;
     cudaEvent_t ev[8];
+    // fused step as `parts` concurrent sub-batches (mm_ctx_set_parts / MM_PARTS): side streams + fork / join events, created lazily
+    int parts;
+    cudaStream_t part_stream[MM_MAX_PARTS - 1];
+    cudaEvent_t part_fork, part_join[MM_MAX_PARTS - 1];
 };
 
 struct mm_ws_layout {

@@ -22,6 +22,7 @@
  * Environment switches read at mm_ctx_create (diagnostics; defaults are the measured best):
  *   MM_PDL=0        no programmatic dependent launch between the library's kernels
  *   MM_SPLIT=1      fused step: soft pass and RGB shading in one launch + a final silhouette pass
+ *   MM_PARTS=n      fused step as n concurrent sub-batches (1..4; see mm_ctx_set_parts)
  *   MM_VCHUNKS=n    CTAs per image of the vertex forward kernel (default 8)
  *   MM_PLIST_CAP=n  test hook: caps the forward's candidate list so the backward's fallback path runs
  */
@@ -163,6 +164,14 @@ int mm_mesh_reg_backward(mm_ctx* ctx, int B, const float* delta_vertices, const 
  * as rendering the concatenated atlas -- the image is bit-identical, g_tex equals the sum of the two halves' gradients --
  * with half the texture bytes read, cleared and written.  Host-side switch; takes effect on the next call. */
 int mm_ctx_set_texture_mirror(mm_ctx* ctx, int enable);
+
+/* Tuning switch of mm_render_compare_fwd_bwd: run the batch as `parts` (1..4) sub-batches, each a complete kernel chain on its
+ * own stream (the caller's + ctx-owned side streams, forked from and joined back into `stream` with events inside the call).
+ * Images are independent through render and loss, so the outputs are those of the unsplit call (the loss scalars are the
+ * image-count-weighted mean of the parts').  The workspace layout of a split call is private: mm_debug_export_faces reads
+ * unsplit layouts only.  Sub-batches below 8 images are not split further; the timing hook measures the unsplit chain. */
+int mm_ctx_set_parts(mm_ctx* ctx, int parts);
+int mm_ctx_get_parts(const mm_ctx* ctx);
 
 /* Test hook: copies the vertex-stage products of the last forward on `workspace`
  * (what kaolin prepare_vertices returns, networks.py:284-287) so that the oracle's

@@ -130,10 +130,13 @@ def run_parity_case(mm, mesh="icosphere", B=2, image_size=32, ratio=1, no_mask=T
     fvi = torch.empty(B, F, 3, 2, device=device)
     fvz = torch.empty(B, F, 3, device=device)
     fnz = torch.empty(B, F, device=device)
-    # re-run the forward to get a workspace we own
+    # re-run the forward to get a workspace we own (unsplit: mm_debug_export_faces reads the unsplit workspace layout)
+    parts = mm.lib().mm_ctx_get_parts(h.handle)
+    mm.lib().mm_ctx_set_parts(h.handle, 1)
     with torch.no_grad():
         out = dr.render_compare(gt_dev, no_mask=no_mask, contour=contour, **{k: v.detach() for k, v in Ac.items()
                                                                              if k != '_want_face_idx'})
+    mm.lib().mm_ctx_set_parts(h.handle, parts)
     ws = out['_workspace']
     rc = mm.lib().mm_debug_export_faces(h.handle, B, ctypes.c_void_p(ws.data_ptr()), ctypes.c_void_p(fvi.data_ptr()),
                                         ctypes.c_void_p(fvz.data_ptr()), ctypes.c_void_p(fnz.data_ptr()),

@@ -405,3 +405,38 @@ def test_mirrored_texture_equals_concatenated_atlas(mm, size, ratio, mesh):
     with torch.no_grad():
         again, _ = dr.render(no_mask=True, **{**Af, 'textures': full})
     assert torch.equal(again, res[0][0])
+
+
+@pytest.mark.parametrize("B,parts", [(48, 2), (48, 3), (48, 4), (19, 2), (33, 4), (9, 4)])
+def test_split_batch_fused_step_equals_unsplit(mm, B, parts):
+    """mm_ctx_set_parts: the fused step as `parts` concurrent sub-batches (own streams, own workspace slices) must return what
+    the unsplit call returns: image bit-identical (images are independent), gradients up to float-atomics order, loss scalars
+    up to the re-association of the batch mean.  Uneven splits, upstream gradients (offset per part) and sub-batches too small
+    to split (B=9) included."""
+    dr, A = _cfg2(mm, B=B, seed=31)
+    G = pu.to_device(pu.make_attributes(dr.vertices_init, B, 128, 128, 32), DEV)
+    with torch.no_grad():
+        gt, _ = dr.render(no_mask=True, **G)
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    g_extra = 1e-4 * torch.randn(B, 4, 128, 128, device=DEV, generator=gen)
+    g_fn = 1e-3 * torch.randn(B, dr.num_faces, 3, device=DEV, generator=gen)
+    h = dr._ctx(torch.device(DEV))
+    L = mm.lib()
+    keep = L.mm_ctx_get_parts(h.handle)
+    outs = []
+    try:
+        for n in (1, parts):
+            assert L.mm_ctx_set_parts(h.handle, n) == 0
+            outs.append(dr.render_compare(gt, no_mask=True, contour=0.1, loss_scale=1.7, g_rgba_extra=g_extra,
+                                          g_face_normals=g_fn, **A))
+            torch.cuda.synchronize()
+    finally:
+        L.mm_ctx_set_parts(h.handle, keep)
+    o1, on = outs
+    assert torch.equal(o1['rgba'], on['rgba'])
+    assert torch.equal(o1['face_normals'], on['face_normals'])
+    assert pu.rel_err(on['loss'], o1['loss']) <= 2e-6
+    for k in ('g_vertices', 'g_azimuths', 'g_elevations', 'g_distances', 'g_biases', 'g_textures', 'g_lights', 'g_bg'):
+        assert pu.rel_err(on[k], o1[k]) <= 2e-5, k
+    assert L.mm_ctx_set_parts(h.handle, 9) != 0            # out of range
+    L.mm_ctx_set_parts(h.handle, keep)
