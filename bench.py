@@ -355,7 +355,10 @@ def main():
     device = "cuda:%d" % local_rank
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version banner (and NCCL_DEBUG output) to stdout by default: stdout carries the ONE JSON line only
+        # stdout carries the ONE JSON line only: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION (the log file
+        # setting is honoured above that level only), and its INFO / WARN output to stdout unless a file is named
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(device))
     if not os.path.exists(os.path.join(g.PKG_DIR, "libmagicmirror.so")):
