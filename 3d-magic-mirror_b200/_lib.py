@@ -46,6 +46,8 @@ SIGNATURES = {
     "mm_mesh_reg_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, ctypes.c_uint,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mm_ctx_set_texture_mirror": (c_int, [c_void_p, c_int]),
+    "mm_template_features_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mm_template_features_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mm_ctx_set_parts": (c_int, [c_void_p, c_int]),
     "mm_ctx_get_parts": (c_int, [c_void_p]),
     "mm_ctx_set_timing": (c_int, [c_void_p, c_int]),

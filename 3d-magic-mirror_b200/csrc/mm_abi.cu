@@ -189,6 +189,7 @@ int mm_ctx_destroy(mm_ctx* c) {
     if (!c) return MM_OK;
     cudaFree(c->d_edges); cudaFree(c->d_edge2faces); cudaFree(c->d_flip); cudaFree(c->d_sign_init);
     cudaFree(c->d_lap_off); cudaFree(c->d_lap_col); cudaFree(c->d_lap_val); cudaFree(c->d_reg_ticket);
+    cudaFree(c->d_lapT_off); cudaFree(c->d_lapT_row); cudaFree(c->d_lapT_val);
     cudaFree(c->d_faces);
     cudaFree(c->d_face_uvs);
     cudaFree(c->d_tab);
@@ -523,11 +524,14 @@ int mm_ctx_set_regularizer_topology(mm_ctx* c, int E, const int32_t* edges_host,
     for (int i = 0; i < c->V; ++i)
         if (flip_index_host[i] < 0 || flip_index_host[i] >= c->V) return fail(MM_E_INVALID, "flip_index[%d] out of range", i);
     MM_REQUIRE(lap_row_off_host[0] == 0 && lap_row_off_host[c->V] == nnz, "laplacian row offsets");
+    for (int i = 0; i < c->V; ++i) MM_REQUIRE(lap_row_off_host[i] <= lap_row_off_host[i + 1], "laplacian row offsets must be non-decreasing");
     for (int i = 0; i < nnz; ++i)
         if (lap_col_host[i] < 0 || lap_col_host[i] >= c->V) return fail(MM_E_INVALID, "laplacian column %d out of range", i);
     MM_CUDA(cudaSetDevice(c->device));
     cudaFree(c->d_edges); cudaFree(c->d_edge2faces); cudaFree(c->d_flip); cudaFree(c->d_sign_init);
     cudaFree(c->d_lap_off); cudaFree(c->d_lap_col); cudaFree(c->d_lap_val); cudaFree(c->d_reg_ticket);
+    cudaFree(c->d_lapT_off); cudaFree(c->d_lapT_row); cudaFree(c->d_lapT_val);
+    c->d_lapT_off = c->d_lapT_row = nullptr; c->d_lapT_val = nullptr;
     c->d_edges = c->d_edge2faces = c->d_flip = c->d_lap_off = c->d_lap_col = nullptr;
     c->d_sign_init = c->d_lap_val = nullptr; c->d_reg_ticket = nullptr;
     MM_CUDA(cudaMalloc(&c->d_edges, (size_t)E * 2 * 4));
@@ -546,6 +550,24 @@ int mm_ctx_set_regularizer_topology(mm_ctx* c, int E, const int32_t* edges_host,
     MM_CUDA(cudaMemcpy(c->d_lap_col, lap_col_host, (size_t)nnz * 4, cudaMemcpyHostToDevice));
     MM_CUDA(cudaMemcpy(c->d_lap_val, lap_val_host, (size_t)nnz * 4, cudaMemcpyHostToDevice));
     MM_CUDA(cudaMemset(c->d_reg_ticket, 0, 4));
+    {   // transpose (counting sort by column; rows stay ascending inside a column): x @ lpl walks columns (mm_template.cu)
+        std::vector<int32_t> toff(c->V + 1, 0), trow(nnz);
+        std::vector<float> tval(nnz);
+        for (int k = 0; k < nnz; ++k) ++toff[lap_col_host[k] + 1];
+        for (int j = 0; j < c->V; ++j) toff[j + 1] += toff[j];
+        std::vector<int32_t> fill(toff.begin(), toff.end() - 1);
+        for (int i = 0; i < c->V; ++i)
+            for (int k = lap_row_off_host[i]; k < lap_row_off_host[i + 1]; ++k) {
+                const int d = fill[lap_col_host[k]]++;
+                trow[d] = i; tval[d] = lap_val_host[k];
+            }
+        MM_CUDA(cudaMalloc(&c->d_lapT_off, (size_t)(c->V + 1) * 4));
+        MM_CUDA(cudaMalloc(&c->d_lapT_row, (size_t)nnz * 4));
+        MM_CUDA(cudaMalloc(&c->d_lapT_val, (size_t)nnz * 4));
+        MM_CUDA(cudaMemcpy(c->d_lapT_off, toff.data(), (size_t)(c->V + 1) * 4, cudaMemcpyHostToDevice));
+        MM_CUDA(cudaMemcpy(c->d_lapT_row, trow.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice));
+        MM_CUDA(cudaMemcpy(c->d_lapT_val, tval.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice));
+    }
     c->reg_E = E; c->reg_ratio = ratio;
     return MM_OK;
 }
@@ -583,6 +605,31 @@ int mm_ctx_set_texture_mirror(mm_ctx* c, int enable) {
     MM_REQUIRE(c, "ctx");
     c->tex_mirror = enable ? 1 : 0;
     return MM_OK;
+}
+
+int mm_template_features_forward(mm_ctx* c, int N, int h, int w, const float* x, const float* template_xyz, float* local,
+                                 float* neighbor_diff, void* stream)
+{
+    MM_REQUIRE(c && N > 0 && h > 0 && w > 0, "ctx / N / h / w");
+    MM_REQUIRE(x && template_xyz && local, "NULL argument");
+    MM_REQUIRE(!neighbor_diff || c->d_lapT_off, "neighbor_diff needs mm_ctx_set_regularizer_topology (the Laplacian)");
+    if (cudaError_t e = mm_launch_template_fwd(c, N, h, w, x, template_xyz, local, neighbor_diff, (cudaStream_t)stream))
+        return fail(MM_E_CUDA, "template_features_fwd: %s", cudaGetErrorString(e));
+    return check_launch("template_features_fwd");
+}
+
+int mm_template_features_backward(mm_ctx* c, int N, int h, int w, const float* template_xyz, const float* g_local,
+                                  const float* g_neighbor_diff, float* g_x, void* stream)
+{
+    MM_REQUIRE(c && N > 0 && h > 0 && w > 0, "ctx / N / h / w");
+    MM_REQUIRE(template_xyz && g_x && (g_local || g_neighbor_diff), "NULL argument");
+    MM_REQUIRE(!g_neighbor_diff || c->d_lap_off, "g_neighbor_diff needs mm_ctx_set_regularizer_topology (the Laplacian)");
+    if ((long long)h * w > mm_template_max_plane())
+        return fail(MM_E_UNSUPPORTED, "feature plane %dx%d exceeds %d elements (shared-memory accumulator of the backward)", h, w,
+                    mm_template_max_plane());
+    if (cudaError_t e = mm_launch_template_bwd(c, N, h, w, template_xyz, g_local, g_neighbor_diff, g_x, (cudaStream_t)stream))
+        return fail(MM_E_CUDA, "template_features_bwd: %s", cudaGetErrorString(e));
+    return check_launch("template_features_bwd");
 }
 
 int mm_ctx_set_parts(mm_ctx* c, int parts) {

@@ -70,6 +70,8 @@ struct mm_ctx {
     int32_t *d_edges, *d_edge2faces, *d_flip, *d_lap_off, *d_lap_col;
     float *d_sign_init, *d_lap_val;
     unsigned* d_reg_ticket;
+    int32_t *d_lapT_off, *d_lapT_row;   // the same Laplacian transposed (column j -> rows i), for x @ lpl (mm_template.cu)
+    float* d_lapT_val;
     // measurement hook (mm_ctx_set_timing)
     int timing;
     cudaEvent_t ev[8];
@@ -182,6 +184,11 @@ void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const f
                           long long* img_bwd, int reset, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
                           float* g_bias, float* g_lights, float* loss, const long long* img_fwd, float image_weight,
                           float contour, cudaStream_t s);
+cudaError_t mm_launch_template_fwd(const mm_ctx* c, int N, int h, int w, const float* x, const float* tmpl, float* local,
+                                   float* ndiff, cudaStream_t s);
+cudaError_t mm_launch_template_bwd(const mm_ctx* c, int N, int h, int w, const float* tmpl, const float* g_local,
+                                   const float* g_ndiff, float* g_x, cudaStream_t s);
+int mm_template_max_plane(void);
 void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 void mm_launch_shade_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_loss, cudaStream_t s);

@@ -311,6 +311,50 @@ class _MeshRegFn(torch.autograd.Function):
         return None, None, None, None, None, gd, gv, gn
 
 
+class _TemplateFeaturesFn(torch.autograd.Function):
+    """ShapeEncoder.forward's template conditioning (network/model_res.py:317-325) in one kernel per direction:
+    bilinear gather of the feature map at the template's (x, y) + right-multiplication by the sparse Laplacian."""
+
+    @staticmethod
+    def forward(ctx, dr, x, template):
+        _require_cuda(x, "x")
+        dev = x.device
+        x = _f32c(x)
+        if x.dim() != 4:
+            raise ValueError("x must be (B,C,h,w), got %s" % (tuple(x.shape),))
+        B, C, h, w = x.shape
+        V = dr.num_vertices
+        tmpl = _f32c(template.detach().to(dev)).reshape(-1, 3)
+        if tmpl.shape[0] != V:
+            raise ValueError("template must hold %d vertices (one template for the whole batch), got %s" % (V, tuple(template.shape)))
+        hnd = dr._ctx(dev)
+        with torch.cuda.device(dev):
+            local = torch.empty(B, C, V, 1, device=dev, dtype=torch.float32)
+            ndiff = torch.empty(B, C, V, 1, device=dev, dtype=torch.float32)
+            rc = _lib.lib().mm_template_features_forward(hnd.handle, B * C, h, w, _ptr(x), _ptr(tmpl), _ptr(local), _ptr(ndiff),
+                                                         _stream())
+        _lib.check(rc, "mm_template_features_forward")
+        ctx.h, ctx.shape = hnd, (B, C, h, w)
+        ctx.save_for_backward(tmpl)
+        return local, ndiff
+
+    @staticmethod
+    def backward(ctx, g_local, g_ndiff):
+        tmpl, = ctx.saved_tensors
+        B, C, h, w = ctx.shape
+        dev = tmpl.device
+        with torch.cuda.device(dev):
+            g_local = _f32c(g_local) if g_local is not None else None
+            g_ndiff = _f32c(g_ndiff) if g_ndiff is not None else None
+            if g_local is None and g_ndiff is None:
+                return None, torch.zeros(B, C, h, w, device=dev), None
+            g_x = torch.empty(B, C, h, w, device=dev, dtype=torch.float32)
+            rc = _lib.lib().mm_template_features_backward(ctx.h.handle, B * C, h, w, _ptr(tmpl), _ptr(g_local), _ptr(g_ndiff),
+                                                          _ptr(g_x), _stream())
+        _lib.check(rc, "mm_template_features_backward")
+        return None, g_x, None
+
+
 class DiffRender(object):
     # kaolin dibr_rasterization defaults (call site networks.py:297-299 passes none of them)
     sigmainv = 7000.0
@@ -432,6 +476,14 @@ class DiffRender(object):
         _lib.check(rc, "mm_render_compare_fwd_bwd")
         out['_workspace'] = ws
         return out
+
+    def template_features(self, x, template):
+        """SURVEY 8(f)-3 (encoder side).  Drop-in for network/model_res.py:317-325 inside ShapeEncoder.forward:
+            local         = F.grid_sample(x, template[..., 0:2], 'bilinear', align_corners=True, padding_mode='zeros')  (B,C,V,1)
+            neighbor_diff = torch.mm(local.view(-1, V), lpl).view(B, C, V, 1),  lpl = self.vertices_laplacian_matrix
+        x: (B,C,h,w) CUDA features; template: (1,V,3) or (V,3) (detached, as in the reference).  One kernel per direction;
+        the dense V x V product uses the mesh's sparse Laplacian."""
+        return _TemplateFeaturesFn.apply(self, x, template)
 
     # ------------------------------------------------------------------ regularisers (networks.py:326-491)
     def recon_att(self, pred_att, target_att, L1=False, chamfer=False, azim=1):

@@ -165,6 +165,17 @@ int mm_mesh_reg_backward(mm_ctx* ctx, int B, const float* delta_vertices, const 
  * with half the texture bytes read, cleared and written.  Host-side switch; takes effect on the next call. */
 int mm_ctx_set_texture_mirror(mm_ctx* ctx, int enable);
 
+/* ---- SURVEY 8(f)-3, encoder side: ShapeEncoder.forward's template conditioning (network/model_res.py:317-325):
+ *   local         = F.grid_sample(x, template[..., 0:2], 'bilinear', align_corners=True, padding_mode='zeros')   [N,V]
+ *   neighbor_diff = torch.mm(local.view(-1, V), lpl)   with lpl = vertices_laplacian_matrix (trainer.py:91)       [N,V]
+ * for the N = B*C feature planes x [N,h,w]; one kernel, the dense V x V GEMM replaced by the sparse Laplacian set with
+ * mm_ctx_set_regularizer_topology.  template_xyz: device [V,3] (x, y used; the reference detaches them).  neighbor_diff may
+ * be NULL.  Backward: g_x [N,h,w] (overwritten) from g_local and / or g_neighbor_diff (either may be NULL); h*w <= 2048. */
+int mm_template_features_forward(mm_ctx* ctx, int N, int h, int w, const float* x, const float* template_xyz,
+                                 float* local, float* neighbor_diff, void* stream);
+int mm_template_features_backward(mm_ctx* ctx, int N, int h, int w, const float* template_xyz, const float* g_local,
+                                  const float* g_neighbor_diff, float* g_x, void* stream);
+
 /* Tuning switch of mm_render_compare_fwd_bwd: run the batch as `parts` (1..4) sub-batches, each a complete kernel chain on its
  * own stream (the caller's + ctx-owned side streams, forked from and joined back into `stream` with events inside the call).
  * Images are independent through render and loss, so the outputs are those of the unsplit call (the loss scalars are the

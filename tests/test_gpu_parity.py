@@ -440,3 +440,57 @@ def test_split_batch_fused_step_equals_unsplit(mm, B, parts):
         assert pu.rel_err(on[k], o1[k]) <= 2e-5, k
     assert L.mm_ctx_set_parts(h.handle, 9) != 0            # out of range
     L.mm_ctx_set_parts(h.handle, keep)
+
+
+@pytest.mark.parametrize("mesh,shape", [("sphere", (3, 16, 8, 4)), ("smpl_uv_642", (2, 8, 4, 4)), ("icosphere", (2, 5, 7, 9)),
+                                         ("sphere", (48, 288, 8, 4))])
+def test_template_features_vs_reference_torch_ops(mm, mesh, shape):
+    """SURVEY 8(f)-3, encoder side: DiffRender.template_features == the reference's own statement, network/model_res.py:317-325
+    (F.grid_sample(align_corners=True, zeros) at the template's (x, y), then torch.mm with the dense V x V Laplacian),
+    forward and d/dx, fp32 tolerance 1e-5 of the tensor's scale (sparse 7-term rows vs a 642-term dense dot product).
+    A stretched template puts some vertices outside [-1,1]: zero padding."""
+    import torch.nn.functional as F
+    B, C, h, w = shape
+    dr = mm.DiffRender(pu.get_mesh(mm, mesh), 64, image_weight=1.0)
+    V = dr.num_vertices
+    gen = torch.Generator().manual_seed(B * 1000 + C)
+    x = torch.randn(B, C, h, w, generator=gen).to(DEV).requires_grad_(True)
+    template = (dr.vertices_init * torch.tensor([1.3, 1.1, 1.0]))[None].to(DEV)
+    wl = torch.randn(B, C, V, 1, generator=gen).to(DEV)
+    wn = torch.randn(B, C, V, 1, generator=gen).to(DEV)
+    local, ndiff = dr.template_features(x, template)
+    ((local * wl).sum() + (ndiff * wn).sum()).backward()
+    gx = x.grad.clone()
+    # the reference's lines, verbatim in form
+    x2 = x.detach().clone().requires_grad_(True)
+    current_position = template.repeat(B, 1, 1).view(B, V, 1, 3).detach()
+    uv_sampler = current_position[:, :, :, 0:2].detach()
+    local_r = F.grid_sample(x2, uv_sampler, mode='bilinear', align_corners=True, padding_mode="zeros")
+    lpl = dr.vertices_laplacian_matrix.to(DEV)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    nd_r = torch.mm(local_r.view(-1, V), lpl).view(B, -1, V, 1)
+    ((local_r * wl).sum() + (nd_r * wn).sum()).backward()
+    assert local.shape == local_r.shape and ndiff.shape == nd_r.shape
+    assert pu.rel_err(local, local_r) <= 1e-5
+    assert pu.rel_err(ndiff, nd_r) <= 1e-5
+    assert pu.rel_err(gx, x2.grad) <= 1e-5
+    # only one of the two outputs used downstream
+    x3 = x.detach().clone().requires_grad_(True)
+    l3, n3 = dr.template_features(x3, template)
+    (n3 * wn).sum().backward()
+    x4 = x.detach().clone().requires_grad_(True)
+    l4 = F.grid_sample(x4, uv_sampler, mode='bilinear', align_corners=True, padding_mode="zeros")
+    (torch.mm(l4.view(-1, V), lpl).view(B, -1, V, 1) * wn).sum().backward()
+    assert pu.rel_err(x3.grad, x4.grad) <= 1e-5
+
+
+def test_template_features_errors(mm):
+    dr = mm.DiffRender(pu.get_mesh(mm, "icosphere"), 32)
+    with pytest.raises(mm.MagicMirrorError):
+        dr.template_features(torch.zeros(1, 2, 4, 4), dr.vertices_init)                     # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        dr.template_features(torch.zeros(1, 2, 4, 4, device=DEV), dr.vertices_init[:10])    # wrong vertex count
+    x = torch.zeros(1, 1, 64, 64, device=DEV, requires_grad=True)                           # plane too large for the backward
+    l, n = dr.template_features(x, dr.vertices_init)
+    with pytest.raises(mm.MagicMirrorError):
+        (l.sum() + n.sum()).backward()
