@@ -430,6 +430,36 @@ class DiffRender(object):
             attributes['face_idx'] = face_idx
         return rgbs, attributes
 
+    def render_many(self, attribute_sets, no_mask=False):
+        """SURVEY 8(f)-2, second half: several independent renders of one iteration in ONE pass.  trainer.py:345-347 renders the
+        interpolated attributes and the rotated copy back to back (`Xir, Ai = render(**Ai)`; `Xer90, Ae90 = render(**Ae90)`);
+        images are independent through the whole path, so the sets are concatenated along the batch, rendered once (the
+        kernels see 2B-3B images: fewer, fuller launches) and split again.  Returns [(rgbs_k, attributes_k), ...] exactly as
+        the separate calls would (bit-identical images; autograd flows through the cat / split)."""
+        sets = list(attribute_sets)
+        if len(sets) == 1:
+            return [self.render(no_mask=no_mask, **sets[0])]
+        keys = ['azimuths', 'elevations', 'distances', 'biases', 'vertices', 'textures', 'lights']
+        sizes = [A['azimuths'].shape[0] for A in sets]
+        merged = {k: torch.cat([A[k] for A in sets], dim=0) for k in keys}
+        merged['bg'] = torch.cat([A['bg'] for A in sets], dim=0) if no_mask else None
+        for flag in ('_want_face_idx', '_tex_mirror'):
+            vals = {bool(A.get(flag, False)) for A in sets}
+            if len(vals) != 1:
+                raise ValueError("render_many: '%s' must agree across the attribute sets" % flag)
+            merged[flag] = vals.pop()
+        rgbs, out = self.render(no_mask=no_mask, **merged)
+        res = []
+        parts = {k: torch.split(out[k], sizes, dim=0) for k in ('face_normals', 'imnormal')}
+        if merged['_want_face_idx']:
+            parts['face_idx'] = torch.split(out['face_idx'], sizes, dim=0)
+        for i, (A, img) in enumerate(zip(sets, torch.split(rgbs, sizes, dim=0))):
+            A = dict(A)
+            for k, v in parts.items():
+                A[k] = v[i]
+            res.append((img, A))
+        return res
+
     def recon_data(self, pred_data, gt_data, no_mask=False, contour=0):
         """networks.py:364-390: image_weight * masked-L1 + (1 - soft IoU) + contour * contour-MSE."""
         loss, parts = _ReconFn.apply(self, self.image_weight, contour, pred_data, gt_data)

@@ -273,7 +273,7 @@ def timed(torch, world, fn, steps):
     return e0.elapsed_time(e1)
 
 
-def cpu_baseline(mm, dr, sets_cpu, budget_s=12.0):
+def cpu_baseline(mm, dr, sets_cpu, budget_s=15.0):
     """Oracle port (our CPU restatement of the Kaolin DIB-R path + torch-CPU glue) on a bounded sample."""
     import torch
     import parity_utils as pu
@@ -292,7 +292,7 @@ def cpu_baseline(mm, dr, sets_cpu, budget_s=12.0):
     t0 = time.perf_counter()
     once()
     one = time.perf_counter() - t0
-    reps = max(1, min(50, int(budget_s / max(one, 1e-3))))
+    reps = max(1, min(200, int(budget_s / max(one, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(reps):
         once()

@@ -494,3 +494,28 @@ def test_template_features_errors(mm):
     l, n = dr.template_features(x, dr.vertices_init)
     with pytest.raises(mm.MagicMirrorError):
         (l.sum() + n.sum()).backward()
+
+
+def test_render_many_equals_separate_renders(mm):
+    """render_many([A1, A2, A3]) == three render calls (trainer.py:276,345,347), images bit-identical, gradients
+    of a loss over all three equal up to float-atomics order; uneven batch sizes."""
+    dr = mm.DiffRender(pu.get_mesh(mm, "ellipsoid"), 128, image_weight=1.0)
+    sizes = (6, 3, 5)
+    sets = [pu.to_device(pu.make_attributes(dr.vertices_init, b, 128, 128, 60 + i), DEV) for i, b in enumerate(sizes)]
+    keys = ('vertices', 'azimuths', 'distances', 'textures', 'lights', 'bg')
+    w = [torch.randn(b, 4, 128, 128, device=DEV, generator=torch.Generator(device=DEV).manual_seed(i)) for i, b in enumerate(sizes)]
+
+    def run(many):
+        As = [{k: (v.clone().requires_grad_(k in keys) if torch.is_tensor(v) else v) for k, v in A.items()} for A in sets]
+        outs = dr.render_many(As, no_mask=True) if many else [dr.render(no_mask=True, **A) for A in As]
+        loss = sum((img * wi).sum() + out['face_normals'].sum() for (img, out), wi in zip(outs, w))
+        loss.backward()
+        return [img.detach() for img, _ in outs], [{k: A[k].grad.clone() for k in keys} for A in As], outs
+
+    img_s, g_s, _ = run(False)
+    img_m, g_m, outs = run(True)
+    for i, b in enumerate(sizes):
+        assert img_m[i].shape == (b, 4, 128, 128) and torch.equal(img_m[i], img_s[i])
+        assert outs[i][1]['face_normals'].shape == (b, dr.num_faces, 3) and outs[i][1]['imnormal'].shape == (b, 128, 128, 3)
+        for k in keys:
+            assert pu.rel_err(g_m[i][k], g_s[i][k]) <= TOL_GRAD, (i, k)
