@@ -367,6 +367,15 @@ def main():
     torch.cuda.set_device(local_rank)
     device = "cuda:%d" % local_rank
     if world > 1:
+        # one process per GPU: keep this rank's threads (and the first touch of its pinned host buffers) on the CPUs next to
+        # its GPU, so that N ranks do not pull their e2e uploads across the socket interconnect
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception:
+            pass
+    if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries the ONE JSON line only: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION (the log file
         # setting is honoured above that level only), and its INFO / WARN output to stdout unless a file is named
