@@ -132,3 +132,43 @@ def test_recon_data_identity():
     m = x[:, 3].reshape(3, -1)
     want = 1 - ((m * m).sum(1) / ((2 * m - m * m).sum(1) + 1e-10)).mean()
     assert abs(float(got) - float(want)) < 1e-6
+
+
+def test_full_pipeline_gradients_match_f64_central_differences(mm):
+    """the oracle's analytic backward (autograd glue + the C DIB-R backward kernels) against fp64 central
+    differences of loss = recon_data(render(A), gt) on EVERY input of the path: vertices, the five camera scalars, texture,
+    lights, background.  The loss is piecewise smooth (visibility is discrete), so a probe that straddles a visibility change
+    is allowed to disagree: at most one of the probes per input may."""
+    dt = torch.float64
+    dr = mm.DiffRender(mm.icosphere(1), 16, image_weight=1.0)
+    orc = pu.oracle_for(dr, dtype=dt)
+    A = {k: v.to(dt) for k, v in pu.make_attributes(dr.vertices_init, 1, 16, 16, 5, dist_range=(2.5, 3.0)).items()}
+    G = {k: v.to(dt) for k, v in pu.make_attributes(dr.vertices_init, 1, 16, 16, 6, dist_range=(2.5, 3.0)).items()}
+    with torch.no_grad():
+        gt = orc.render(no_mask=True, **G)[0]
+
+    def loss_of(Ax):
+        return orc.recon_data(orc.render(no_mask=True, **Ax)[0], gt, no_mask=True, contour=0.1)
+
+    keys = ['vertices', 'azimuths', 'elevations', 'distances', 'biases', 'textures', 'lights', 'bg']
+    Ag = {k: (v.clone().requires_grad_(k in keys)) for k, v in A.items()}
+    loss_of(Ag).backward()
+    gen = torch.Generator().manual_seed(0)
+    for k in keys:
+        g = Ag[k].grad.reshape(-1)
+        n = g.numel()
+        # probe where the analytic gradient is largest (informative) plus random entries
+        cand = torch.unique(torch.cat([g.abs().topk(min(4, n)).indices, torch.randint(0, n, (4,), generator=gen)]))
+        eps = 1e-6 if k not in ('azimuths', 'elevations') else 1e-5          # degrees
+        bad = 0
+        for i in cand.tolist():
+            vals = []
+            for sgn in (1.0, -1.0):
+                Ax = {kk: vv.clone() for kk, vv in A.items()}
+                Ax[k].view(-1)[i] += sgn * eps
+                with torch.no_grad():
+                    vals.append(float(loss_of(Ax)))
+            fd = (vals[0] - vals[1]) / (2 * eps)
+            if abs(fd - float(g[i])) > 2e-5 * max(1e-3, abs(fd), abs(float(g[i]))) + 1e-9:      # 2e-5 relative
+                bad += 1
+        assert bad <= 1 and float(g.abs().max()) > 0, (k, bad, len(cand))
