@@ -59,7 +59,8 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F,
                   float sigmainv, float boxlen, int knum, float multiplier, float eps);
 int mm_ctx_destroy(mm_ctx* ctx);
 
-/* Bytes of caller-owned scratch needed by any call on `ctx` with batch B. */
+/* Bytes of caller-owned scratch needed by any call on `ctx` with batch B (covers the unsplit layout and every split of the
+ * fused step into sub-batches, mm_ctx_set_parts). */
 size_t mm_workspace_bytes(const mm_ctx* ctx, int B);
 
 /* Replaces DiffRender.render (networks.py:258-324): camera_position_from_spherical_angles
