@@ -18,41 +18,39 @@ c_float = ctypes.c_float
 c_void_p = ctypes.c_void_p
 
 # name -> (restype, argtypes); mirrors include/magicmirror.h one to one
+c_size_t = ctypes.c_size_t
+_P = c_void_p
+
+# name -> (restype, argtypes); mirrors include/magicmirror.h one to one
+_RENDER_IN = [_P] * 6 + [c_int, c_int, c_int] + [_P] * 2 + [c_int]      # vertices..tex, Ht, Wt, tex_mirror, lights, bg, no_mask
 SIGNATURES = {
     "mm_abi_version": (c_int, []),
     "mm_last_error": (ctypes.c_char_p, []),
-    "mm_ctx_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+    "mm_ctx_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, _P, _P, c_int, c_int,
                               c_float, c_float, c_float, c_float, c_int, c_float, c_float]),
-    "mm_ctx_destroy": (c_int, [c_void_p]),
-    "mm_workspace_bytes": (ctypes.c_size_t, [c_void_p, c_int]),
-    "mm_render_forward": (c_int, [c_void_p, c_int] + [c_void_p] * 6 + [c_int, c_int] + [c_void_p] * 2 + [c_int] +
-                          [c_void_p] * 4 + [c_void_p, c_void_p]),
-    "mm_render_backward": (c_int, [c_void_p, c_int] + [c_void_p] * 6 + [c_int, c_int] + [c_void_p] * 2 + [c_int] +
-                           [c_void_p] * 3 + [c_void_p] * 8 + [c_void_p, c_void_p]),
-    "mm_recon_data_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
-                                      c_void_p, c_void_p]),
-    "mm_recon_data_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
-                                       c_void_p, c_void_p]),
-    "mm_render_compare_fwd_bwd": (c_int, [c_void_p, c_int] + [c_void_p] * 6 + [c_int, c_int] + [c_void_p] * 2 +
-                                  [c_int, c_void_p, c_float, c_float, c_float] + [c_void_p] * 2 + [c_void_p] * 3 +
-                                  [c_void_p] * 8 + [c_void_p, c_void_p]),
-    "mm_debug_export_faces": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mm_face_normals_forward": (c_int, [c_void_p, c_int] + [c_void_p] * 8),
-    "mm_face_normals_backward": (c_int, [c_void_p, c_int] + [c_void_p] * 13),
-    "mm_ctx_set_regularizer_topology": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
-                                                c_void_p, c_void_p, c_float]),
-    "mm_mesh_reg_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, ctypes.c_uint,
-                                    c_void_p, c_void_p, c_void_p]),
-    "mm_mesh_reg_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, ctypes.c_uint,
-                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mm_ctx_set_texture_mirror": (c_int, [c_void_p, c_int]),
-    "mm_template_features_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mm_template_features_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mm_ctx_set_parts": (c_int, [c_void_p, c_int]),
-    "mm_ctx_get_parts": (c_int, [c_void_p]),
-    "mm_ctx_set_timing": (c_int, [c_void_p, c_int]),
-    "mm_ctx_get_timing": (c_int, [c_void_p, c_void_p, c_int]),
+    "mm_ctx_destroy": (c_int, [_P]),
+    "mm_workspace_bytes": (c_size_t, [_P, c_int]),
+    "mm_render_forward": (c_int, [_P, c_int] + _RENDER_IN + [_P] * 4 + [_P, c_size_t, _P]),
+    "mm_render_backward": (c_int, [_P, c_int] + _RENDER_IN + [_P] * 3 + [_P, c_float, c_float, c_float, _P] + [_P] * 8 +
+                           [_P, c_size_t, _P]),
+    "mm_recon_data_forward": (c_int, [_P, c_int, _P, _P, c_float, c_float, _P, _P, _P, c_size_t, _P]),
+    "mm_recon_data_backward": (c_int, [_P, c_int, _P, _P, c_float, c_float, c_float, _P, _P, _P, c_size_t, _P]),
+    "mm_render_compare_fwd_bwd": (c_int, [_P, c_int] + _RENDER_IN + [_P, c_float, c_float, c_float] + [_P] * 2 + [_P] * 3 +
+                                  [_P] * 8 + [_P, c_size_t, _P]),
+    "mm_debug_export_faces": (c_int, [_P, c_int, _P, c_size_t, _P, _P, _P, _P]),
+    "mm_face_normals_forward": (c_int, [_P, c_int] + [_P] * 6 + [_P, c_size_t, _P]),
+    "mm_face_normals_backward": (c_int, [_P, c_int] + [_P] * 11 + [_P, c_size_t, _P]),
+    "mm_ctx_set_regularizer_topology": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, c_float]),
+    "mm_mesh_reg_forward": (c_int, [_P, c_int, _P, _P, _P, c_float, c_float, c_int, ctypes.c_uint, _P, _P, _P]),
+    "mm_mesh_reg_backward": (c_int, [_P, c_int, _P, _P, _P, c_float, c_float, c_int, ctypes.c_uint, _P, _P, _P, _P, _P]),
+    "mm_template_features_forward": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "mm_template_features_backward": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "mm_texture_flow_forward": (c_int, [_P] + [c_int] * 7 + [_P, _P, _P, _P]),
+    "mm_texture_flow_backward": (c_int, [_P] + [c_int] * 7 + [_P, _P, _P, _P, _P, _P]),
+    "mm_ctx_set_timing": (c_int, [_P, c_int]),
+    "mm_ctx_get_timing": (c_int, [_P, _P, c_int]),
 }
+ABI_VERSION = 2
 
 
 class MagicMirrorError(RuntimeError):
@@ -72,7 +70,7 @@ def lib():
             fn = getattr(handle, name)     # AttributeError here == header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        if handle.mm_abi_version() != 1:
+        if handle.mm_abi_version() != ABI_VERSION:
             raise MagicMirrorError("libmagicmirror ABI version mismatch")
         _lib = handle
     return _lib

@@ -21,8 +21,8 @@
 //     gsoft      [B,H,W]      d(loss)/d(silhouette) per pixel, handed from the shading stage to the geometry backward
 //     vimg       [B,V,2]   unscaled image-plane xy (debug export / parity tests)
 //     gfacc      [B,F,12]  backward accumulators: d/d(fvi) (6, unscaled) | pad (2) | d/d(unit normal) (3) | pad (1)
-//     part_fwd   [B,NP,4]  per-CTA partial sums of the stand-alone recon_data kernels (L1, N, D, contour)
 //     img_fwd    [B,4]     per-image sums (L1, N, D, contour) as fixed-point 64-bit integers (order-independent atomics)
+//     ticket     [4] u32   last-CTA ticket of the stand-alone recon_data forward (cleared together with img_fwd)
 //     img_bwd    [B,12]    per-image sums (contour, 9 light gradients, -, -), same scheme
 #pragma once
 #include <cuda_runtime.h>
@@ -41,8 +41,6 @@
                                      // normal (3), pad (1) -- 48 B, so the three groups are 16/8/16-byte aligned for vector REDs
 #define MM_MAX_KNUM     64
 
-#define MM_MAX_PARTS 4
-
 struct mm_ctx {
     int device;
     int V, F, H, W;
@@ -58,8 +56,7 @@ struct mm_ctx {
     int nchunks;             // vertex forward: CTAs per image (each emits 1/nchunks of the face records)
     size_t smem_vertex_fwd;  // dynamic smem bytes of the vertex forward kernel
     int num_sms;
-    int split;               // fused step: 1 = soft pass and RGB shading in one launch + k_alpha (MM_SPLIT=1), 0 = sequential (default)
-    int tex_mirror;          // 1: tex / g_tex hold the top half of a vertically mirrored atlas (mm_ctx_set_texture_mirror)
+    int pdl;                 // 1 = dependent kernels are launched with programmatic stream serialization (default; MM_PDL=0 disables)
     unsigned plist_cap_max;  // test hook (MM_PLIST_CAP): caps the forward's pair list so that the backward's fallback path runs
     // device arrays
     int32_t* d_faces;        // [F,3]
@@ -69,20 +66,15 @@ struct mm_ctx {
     int reg_E; float reg_ratio;
     int32_t *d_edges, *d_edge2faces, *d_flip, *d_lap_off, *d_lap_col;
     float *d_sign_init, *d_lap_val;
-    unsigned* d_reg_ticket;
     int32_t *d_lapT_off, *d_lapT_row;   // the same Laplacian transposed (column j -> rows i), for x @ lpl (mm_template.cu)
     float* d_lapT_val;
     // measurement hook (mm_ctx_set_timing)
     int timing;
     cudaEvent_t ev[8];
-    // fused step as `parts` concurrent sub-batches (mm_ctx_set_parts / MM_PARTS): side streams + fork / join events, created lazily
-    int parts;
-    cudaStream_t part_stream[MM_MAX_PARTS - 1];
-    cudaEvent_t part_fork, part_join[MM_MAX_PARTS - 1];
 };
 
 struct mm_ws_layout {
-    size_t frec, zbuf, lacc, cov, ovf_count, ovf_list, plist, gsoft, vimg, gfacc, part_fwd, img_fwd, img_bwd, total;
+    size_t frec, zbuf, lacc, cov, ovf_count, ovf_list, plist, gsoft, vimg, gfacc, img_fwd, ticket, img_bwd, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -101,10 +93,9 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     L.gsoft = off;    off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.vimg = off;     off = mm_align_up(off + (size_t)B * c->V * 2 * 4, 256);
     L.gfacc = off;    off = mm_align_up(off + (size_t)B * c->F * MM_GF * 4, 256);
-    const int rp = (c->nst + MM_WARPS - 1) / MM_WARPS;          // shading CTAs per image (8 sub-tiles each)
-    const size_t np = (size_t)(rp > c->nparts_recon ? rp : c->nparts_recon);
-    L.part_fwd = off; off = mm_align_up(off + (size_t)B * np * 4 * 4, 256);
-    L.img_fwd = off;  off = mm_align_up(off + (size_t)B * 4 * 8, 256);
+    // img_fwd and ticket are contiguous: the stand-alone recon_data forward clears them with one memset
+    L.img_fwd = off;  off = off + (size_t)B * 4 * 8;
+    L.ticket = off;   off = mm_align_up(off + 16, 256);
     L.img_bwd = off;  off = mm_align_up(off + (size_t)B * 12 * 8, 256);
     L.total = off;
     return L;
@@ -142,6 +133,7 @@ struct mm_raster_params {
     // backward
     const float* g_rgba;     // [B,4,H,W] or NULL
     float image_weight, contour, loss_scale;
+    const float* loss_scale_dev;  // optional DEVICE scalar multiplied into loss_scale (the upstream gradient of the loss, lazy fusion)
     int analytic_loss;
     float* gfacc;            // [B,F,MM_GF]
     float* g_tex;            // [B,3,Htp,Wt]
@@ -172,16 +164,14 @@ static inline cudaError_t mm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 bl
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #endif
-extern int g_mm_pdl;          // 1 = launch dependent kernels with programmatic stream serialization (default; MM_PDL=0 disables)
-
-// launchers (defined in the .cu files)
-void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
+// launchers (defined in the .cu files); every one returns the launch's cudaError_t
+cudaError_t mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec,
                           float* vimg, float* face_normals, float* gfacc_zero, long long* img_fwd, long long* img_bwd,
                           void* clr0, size_t bytes0, void* clr1, size_t bytes1, cudaStream_t s);
-void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
-                          const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,
-                          long long* img_bwd, int reset, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
+cudaError_t mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
+                          const float* dist, const float* bias, float* gfacc, const float* g_face_normals,
+                          long long* img_bwd, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
                           float* g_bias, float* g_lights, float* loss, const long long* img_fwd, float image_weight,
                           float contour, cudaStream_t s);
 cudaError_t mm_launch_template_fwd(const mm_ctx* c, int N, int h, int w, const float* x, const float* tmpl, float* local,
@@ -189,30 +179,27 @@ cudaError_t mm_launch_template_fwd(const mm_ctx* c, int N, int h, int w, const f
 cudaError_t mm_launch_template_bwd(const mm_ctx* c, int N, int h, int w, const float* tmpl, const float* g_local,
                                    const float* g_ndiff, float* g_x, cudaStream_t s);
 int mm_template_max_plane(void);
-void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
-void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
-void mm_launch_shade_fwd(const mm_ctx* c, const mm_raster_params& p, bool with_loss, cudaStream_t s);
-void mm_launch_shade_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
-void mm_launch_shade_fused(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
-void mm_launch_gsoft(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
-void mm_launch_soft_shade(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
-void mm_launch_alpha(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
-void mm_launch_hard(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
-void mm_launch_soft_ovf_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
-void mm_launch_loss_finalize(const mm_ctx* c, int B, const long long* img_fwd, long long* img_bwd,
-                             float image_weight, float contour, float* loss, float* iou_out, cudaStream_t s);
-void mm_launch_image_reduce(const mm_ctx* c, int B, int np, const float* part_fwd, long long* img_fwd, cudaStream_t s);
-void mm_launch_recon_fwd(const mm_ctx* c, int B, const float* pred, const float* gt, float contour, float* part_fwd,
+cudaError_t mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
+cudaError_t mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
+// shading: mode 0 = fused (forward + loss sums + RGB-side backward), 1 = forward only, 2 = backward only
+cudaError_t mm_launch_shade(const mm_ctx* c, const mm_raster_params& p, int mode, cudaStream_t s);
+cudaError_t mm_launch_gsoft(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
+cudaError_t mm_launch_recon_fwd(const mm_ctx* c, int B, const float* pred, const float* gt, float image_weight, float contour,
+                         long long* img_fwd, unsigned* ticket, float* loss, float* iou_out, cudaStream_t s);
+cudaError_t mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float* gt, const long long* img_fwd,
+                         float image_weight, float contour, float loss_scale, const float* loss_scale_dev, float* g_pred,
                          cudaStream_t s);
-void mm_launch_recon_bwd(const mm_ctx* c, int B, const float* pred, const float* gt, const long long* img_fwd,
-                         float image_weight, float contour, float loss_scale, float* g_pred, cudaStream_t s);
 size_t mm_vertex_smem_fwd(const mm_ctx* c);
 size_t mm_vertex_smem_bwd(int V);
-void mm_vertex_set_smem(size_t fwd, size_t bwd);
-void mm_launch_meshreg_fwd(const mm_ctx* c, int B, const float* delta, const float* vertices, const float* fn, float temp,
-                           float eps, int flip_l1, unsigned mask, float* partials, float* terms, cudaStream_t s);
-void mm_launch_meshreg_bwd(const mm_ctx* c, int B, const float* delta, const float* vertices, const float* fn, float temp,
+cudaError_t mm_vertex_set_smem(int device, size_t fwd, size_t bwd);
+cudaError_t mm_launch_meshreg_fwd(const mm_ctx* c, int B, const float* delta, const float* vertices, const float* fn, float temp,
+                           float eps, int flip_l1, unsigned mask, float* partials, unsigned* ticket, float* terms, cudaStream_t s);
+cudaError_t mm_launch_meshreg_bwd(const mm_ctx* c, int B, const float* delta, const float* vertices, const float* fn, float temp,
                            float eps, int flip_l1, unsigned mask, const float* g_terms, float* g_delta, float* g_vertices,
                            float* g_fn, cudaStream_t s);
-void mm_launch_export_faces(const mm_ctx* c, int B, const float* frec, const float* vimg, float* fvi, float* fvz,
+cudaError_t mm_launch_export_faces(const mm_ctx* c, int B, const float* frec, const float* vimg, float* fvi, float* fvz,
                             float* fnz, cudaStream_t s);
+cudaError_t mm_launch_texflow_fwd(const mm_ctx* c, int B, int C, int Hi, int Wi, int Ho, int Wo, int concat, const float* img,
+                                  const float* flow, float* out, cudaStream_t s);
+cudaError_t mm_launch_texflow_bwd(const mm_ctx* c, int B, int C, int Hi, int Wi, int Ho, int Wo, int concat, const float* img,
+                                  const float* flow, const float* g_out, float* g_img, float* g_flow, cudaStream_t s);

@@ -303,6 +303,12 @@ __device__ __forceinline__ float fx_get(const long long* acc, double scale) { re
 // d(loss)/d(silhouette) of pixel `pix` of image b as the geometry backward consumes it.  In the fused step the shading kernel
 // stores the tile-local part (upstream gradient + contour term); the IoU term -(1/B) (gm De - Nb (1 - gm)) / De^2 needs the
 // complete per-image sums and is added here, by the consumer (DIBR_SPEC A.7).
+// loss_scale of the analytic loss gradient: the host-side factor times, when given, a DEVICE scalar (the upstream gradient
+// of the loss that autograd hands to recon_data's backward -- lazy fusion, no host round trip)
+__device__ __forceinline__ float eff_loss_scale(const mm_raster_params& p) {
+    return p.loss_scale_dev ? p.loss_scale * __ldg(p.loss_scale_dev) : p.loss_scale;
+}
+
 __device__ __forceinline__ float gsoft_at(const mm_raster_params& p, int b, size_t pix) {
     const size_t HW = (size_t)p.H * p.W;
     float g = p.gsoft[(size_t)b * HW + pix];
@@ -310,7 +316,7 @@ __device__ __forceinline__ float gsoft_at(const mm_raster_params& p, int b, size
         const float gm = __ldg(p.gt + ((size_t)b * 4 + 3) * HW + pix);
         const float Nb = fx_get(p.img_fwd + b * 4 + 1, MM_FX_LOSS);
         const float De = fx_get(p.img_fwd + b * 4 + 2, MM_FX_LOSS) + 1e-10f;
-        g += -(p.loss_scale / (float)p.B) * (gm * De - Nb * (1.0f - gm)) / (De * De);
+        g += -(eff_loss_scale(p) / (float)p.B) * (gm * De - Nb * (1.0f - gm)) / (De * De);
     }
     return g;
 }
@@ -358,30 +364,4 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
 __device__ __forceinline__ void red_add_corners(float* g, const float (&v)[6]) {
     red_add_v4(g, v[0], v[1], v[2], v[3]);
     red_add_v2(g + 4, v[4], v[5]);
-}
-
-// ------------------------------------------------------------------ TMA bulk copy (global -> shared) helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra.uni WAIT_DONE;\n"
-        "bra.uni WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
 }

@@ -1,18 +1,19 @@
-// mm_fused.cu -- per-pixel kernels of the FUSED render-compare step (mm_render_compare_fwd_bwd).
+// mm_fused.cu -- the per-pixel SHADING stage of every entry point: UV texture sampling, SH lighting, composite, clamp
+// (kaolin texture_mapping / spherical_harmonic_lighting + networks.py:303-317), the recon_data loss terms
+// (networks.py:364-390) and their backward.  ONE kernel body, three modes:
 //
-// The unfused API (render, then recon_data, then autograd) needs a shading forward and, later, a shading backward
-// that re-reads everything (mm_shade.cu).  In the fused step the loss is known while the pixel is being shaded, and
-// of the whole backward only d(loss)/d(silhouette) depends on per-image sums (the IoU ratio): every RGB-side
-// gradient (texture, background, lights, face normals, hard-rasteriser uv term) is a function of the pixel alone.
-//
-//   k_shade_fused   one pass over the pixels: shading forward (networks.py:303-317), the L1/IoU partial sums
-//                   (networks.py:374-377) AND the complete RGB-side backward.  Every input plane is read once,
-//                   4 pixels per thread as float4 (16-byte) accesses issued up front; a warp owns a 16x8-pixel tile.
-//   k_gsoft         after the per-image sums are complete: d(loss)/d(silhouette) for every pixel (IoU + contour +
-//                   optional upstream gradient) and the contour loss sum.  Reads 2-3 planes, writes one.
-// The geometry backward (mm_raster.cu) then consumes `gsoft` exactly as in the unfused path.
+//   SHADE_FUSED  mm_render_compare_fwd_bwd: shading forward, the L1 / IoU / contour partial sums AND the complete RGB-side
+//                backward in one pass.  Of the whole backward only d(loss)/d(silhouette) depends on per-image sums (the IoU
+//                ratio): every RGB-side gradient (texture, background, lights, face normals, hard-rasteriser uv term) is
+//                a function of the pixel alone, so it is formed while the pixel is being shaded.
+//   SHADE_FWD    mm_render_forward: the forward alone (+ the optional imnormal / face_idx outputs).
+//   SHADE_BWD    mm_render_backward: the backward alone, re-deriving the forward per pixel.  The upstream gradient is any
+//                mix of a materialised g_rgba and the ANALYTIC recon_data gradient (lazy fusion: recon_data's backward hands
+//                over (gt, weights, a device scalar) instead of a (B,4,H,W) tensor; the IoU sums are in the workspace).
+// Sharing the body makes the images of the three entry points bit-identical by construction.
+//   k_gsoft      H or W not a multiple of 4 only: d(loss)/d(silhouette) in its own pass (contour term through index tables).
+// The geometry backward (mm_raster.cu) consumes `gsoft`.
 #include "mm_device.cuh"
-#include "mm_soft_fwd.cuh"
 
 namespace {
 
@@ -74,11 +75,15 @@ struct ShadeSmem {
     int count;
 };
 
-// SPLIT: the silhouette is not final yet (the soft pass runs concurrently, in the same launch): the alpha plane, the IoU sums
-// and d(loss)/d(silhouette) are left to k_alpha; everything RGB-side is done here.
-template <bool VEC, bool HAS_GUP, bool SPLIT>
-__device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, ShadeSmem& sm, const int bx, const int b)
+enum { SHADE_FUSED = 0, SHADE_FWD = 1, SHADE_BWD = 2 };
+
+template <bool VEC, bool HAS_GUP, int MODE>
+__device__ __forceinline__ void shade_role(const mm_raster_params& p, ShadeSmem& sm, const int bx, const int b)
 {
+    constexpr bool OUT = MODE != SHADE_BWD;        // stores the image (rgba [+ imnormal, face_idx])
+    constexpr bool SUMS = MODE == SHADE_FUSED;     // accumulates the loss sums (L1, IoU, contour)
+    constexpr bool GRAD = MODE != SHADE_FWD;       // forms the RGB-side backward and d(loss)/d(silhouette)
+    const bool analytic = GRAD && p.analytic_loss; // the recon_data gradient is formed in-kernel from gt
     float* s_lights = sm.lights;
     uint32_t* s_list = sm.list;
     int& s_count = sm.count;
@@ -89,7 +94,8 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
     const int H = p.H, W = p.W;
     const size_t HW = (size_t)H * W;
     const int ntx = (W + FT_W - 1) / FT_W;
-    const float k_img = p.loss_scale * p.image_weight / ((float)p.B * 3.0f * (float)HW);
+    const float lscale = analytic ? eff_loss_scale(p) : 0.0f;
+    const float k_img = lscale * p.image_weight / ((float)p.B * 3.0f * (float)HW);
     float coef_bg;                                                          // sh_coef of a zero normal, same op sequence
     { float bnd0[9]; sh_bands(0.0f, 0.0f, 0.0f, bnd0); coef_bg = sh_coef(bnd0, s_lights); }
 
@@ -112,24 +118,24 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
                 if (VEC) {
                     const ulonglong2 z0 = *reinterpret_cast<const ulonglong2*>(zb), z1 = *reinterpret_cast<const ulonglong2*>(zb + 2);
                     z[0] = z0.x; z[1] = z0.y; z[2] = z1.x; z[3] = z1.y;
-                    if (!SPLIT) {
-                        const ulonglong2 l0 = *reinterpret_cast<const ulonglong2*>(la), l1 = *reinterpret_cast<const ulonglong2*>(la + 2);
-                        l[0] = l0.x; l[1] = l0.y; l[2] = l1.x; l[3] = l1.y;
-                    }
+                    const ulonglong2 l0 = *reinterpret_cast<const ulonglong2*>(la), l1 = *reinterpret_cast<const ulonglong2*>(la + 2);
+                    l[0] = l0.x; l[1] = l0.y; l[2] = l1.x; l[3] = l1.y;
                 } else {
                     #pragma unroll
-                    for (int j = 0; j < 4; ++j) { z[j] = (j < n) ? zb[j] : 0ull; if (!SPLIT) l[j] = (j < n) ? la[j] : 0ull; }
+                    for (int j = 0; j < 4; ++j) { z[j] = (j < n) ? zb[j] : 0ull; l[j] = (j < n) ? la[j] : 0ull; }
                 }
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     face[j] = (j < n) ? key_face(z[j]) : -1;
-                    if (!SPLIT) soft[j] = (face[j] >= 0) ? 1.0f : lacc_soft(l[j]);
+                    soft[j] = (face[j] >= 0) ? 1.0f : lacc_soft(l[j]);
                 }
             }
             float bgv[3][4], gtv[4][4], gup[3][4];
-            const float* gtb = p.gt + (size_t)b * 4 * HW + pix0;
             #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) load4<VEC>(gtb + ch * HW, n, gtv[ch]);
+            for (int ch = 0; ch < 4; ++ch) {
+                if (analytic || SUMS) load4<VEC>(p.gt + ((size_t)b * 4 + ch) * HW + pix0, n, gtv[ch]);
+                else { gtv[ch][0] = gtv[ch][1] = gtv[ch][2] = gtv[ch][3] = 0.0f; }
+            }
             #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 if (p.no_mask) load4<VEC>(p.bg + ((size_t)b * 3 + ch) * HW + pix0, n, bgv[ch]);
@@ -137,7 +143,7 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
                 if (HAS_GUP) load4<VEC>(p.g_rgba + ((size_t)b * 4 + ch) * HW + pix0, n, gup[ch]);
                 else { gup[ch][0] = gup[ch][1] = gup[ch][2] = gup[ch][3] = 0.0f; }
             }
-            if (HAS_GUP && !SPLIT) load4<VEC>(p.g_rgba + ((size_t)b * 4 + 3) * HW + pix0, n, gs);      // upstream d/d(silhouette)
+            if (HAS_GUP) load4<VEC>(p.g_rgba + ((size_t)b * 4 + 3) * HW + pix0, n, gs);      // upstream d/d(silhouette)
             #pragma unroll
             for (int j = 0; j < 4; ++j) gmv[j] = gtv[3][j];
             // channel by channel, each plane stored as soon as it is complete (keeps the live register set small: the kernel's
@@ -150,38 +156,55 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float gm = gtv[3][j];
-                    // the covered-path expression with tcol = tm = 0 (bit-identical to the unfused kernel)
+                    // the covered-path expression with tcol = tm = 0 (every mode runs the same operation sequence)
                     const float pre = composite_pre(p.no_mask, 0.0f, 0.0f, bgv[ch][j], coef_bg);
                     const float v = clamp01(pre);
                     img[j] = v;
                     const float lt = l1_term(v, gtv[ch][j], gm);
-                    if (face[j] < 0) acc_l1 += fabsf(lt);
+                    if (SUMS && face[j] < 0) acc_l1 += fabsf(lt);
                     float g = gup[ch][j] + k_img * sgnf(lt) * gm;
                     g = (pre >= 0.0f && pre <= 1.0f) ? g : 0.0f;
                     gbg[j] = g * coef_bg;
                     if (p.no_mask) g_coef[j] += g * bgv[ch][j];
                 }
-                store4<VEC>(out + ch * HW, n, img);
-                if (p.g_bg) store4<VEC>(p.g_bg + ((size_t)b * 3 + ch) * HW + pix0, n, gbg);
+                if (OUT) store4<VEC>(out + ch * HW, n, img);
+                if (GRAD && p.g_bg) store4<VEC>(p.g_bg + ((size_t)b * 3 + ch) * HW + pix0, n, gbg);
             }
             #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float gm = gtv[3][j];
-                if (face[j] < 0 && j < n) acc_gc += g_coef[j];
-                if (!SPLIT && j < n) {                         // IoU partial sums (kaolin mask_iou)
+                if (GRAD && face[j] < 0 && j < n) acc_gc += g_coef[j];
+                if (SUMS && j < n) {                           // IoU partial sums (kaolin mask_iou)
                     const float mul = soft[j] * gm;
                     acc_n += mul;
                     acc_d += (soft[j] + gm) - mul;
                 }
             }
-            if (!SPLIT) store4<VEC>(out + 3 * HW, n, soft);
+            if (OUT) store4<VEC>(out + 3 * HW, n, soft);
+            if (MODE == SHADE_FWD) {
+                if (p.face_idx_out) {
+                    int32_t* fo = p.face_idx_out + (size_t)b * HW + pix0;
+                    if (VEC) *reinterpret_cast<int4*>(fo) = make_int4(face[0], face[1], face[2], face[3]);
+                    else { for (int j = 0; j < 4; ++j) if (j < n) fo[j] = face[j]; }
+                }
+                if (p.imnormal) {                              // background: zero normal; covered pixels overwritten by pass 2
+                    float* no = p.imnormal + ((size_t)b * HW + pix0) * 3;
+                    if (VEC) {
+                        const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        float4* n4 = reinterpret_cast<float4*>(no);
+                        n4[0] = z4; n4[1] = z4; n4[2] = z4;
+                    } else { for (int j = 0; j < 3 * n; ++j) no[j] = 0.0f; }
+                }
+            }
         }
-        // ---- tile-local part of d(loss)/d(silhouette): upstream + contour term (DIBR_SPEC A.7).  H and W are multiples of 4 here,
-        // so the 16x8 tile holds whole 4x4 contour blocks: a block = lanes differing in lane bits 2,3 (4 rows) with the same
-        // lx; its reference pixel is pixel 0 of the lane with (ly & 3) == 0.  The IoU term is added by the consumers (gsoft_at).
-        if (!SPLIT && p.gsoft_iou_pending) {
-            if (p.contour > 0.0f) {
-                const float k_cont = p.loss_scale * p.contour / ((float)p.B * (float)HW);
+        // ---- d(loss)/d(silhouette) handed to the geometry backward: upstream + (analytic loss) the contour term (DIBR_SPEC A.7).
+        // H and W are multiples of 4 whenever the contour term is formed here (gsoft_iou_pending), so the 16x8 tile holds whole
+        // 4x4 contour blocks: a block = lanes differing in lane bits 2,3 (4 rows) with the same lx; its reference pixel is pixel 0
+        // of the lane with (ly & 3) == 0.  The IoU term is added by the consumers (gsoft_at).  Without an analytic loss the
+        // upstream gradient alone is stored, whatever the image size.
+        if (GRAD && (p.gsoft_iou_pending || !analytic)) {
+            if (analytic && p.contour > 0.0f) {
+                const float k_cont = lscale * p.contour / ((float)p.B * (float)HW);
                 const int ref_lane = lane & ~12;
                 const float mref = __shfl_sync(FULL, soft[0], ref_lane), gref = __shfl_sync(FULL, gmv[0], ref_lane);
                 float tsum = 0.0f;
@@ -216,18 +239,14 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
     __syncthreads();
 
     // ---- pass 2: the CTA's covered pixels, one per lane
-#ifdef EXP_NO_HEAVY
-    const int count = 0;
-#else
     const int count = s_count;
-#endif
     float acc_l[9];
     #pragma unroll
     for (int i = 0; i < 9; ++i) acc_l[i] = 0.0f;
     const float* rec = p.frec + (size_t)b * p.F * MM_REC_FLOATS;
     const float* tb = p.tex + (size_t)b * 3 * p.Htp * p.Wt;
-    float* gacc = p.gfacc + (size_t)b * p.F * MM_GF;
-    float* gtex = p.g_tex + (size_t)b * 3 * p.Htp * p.Wt;
+    float* gacc = GRAD ? p.gfacc + (size_t)b * p.F * MM_GF : nullptr;
+    float* gtex = GRAD ? p.g_tex + (size_t)b * 3 * p.Htp * p.Wt : nullptr;
     // (a texel-prefetch sub-pass ahead of this loop was measured: 43.7 -> 46.3 us, the kernel is not bound by that miss)
     #pragma unroll 1
     for (int i = threadIdx.x; i < count; i += FUSED_THREADS) {
@@ -238,21 +257,12 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
         const int ty = tile / ntx, tx = tile - ty * ntx;
         const int iy = ty * FT_H + (el >> 2), ix = tx * FT_W + (el & 3) * 4 + (int)(e & 3u);
         const size_t pix = (size_t)iy * W + ix;
-        const float* gtb = p.gt + (size_t)b * 4 * HW + pix;
-#ifdef EXP_NO_PIXLD
-        const float gm = 0.5f + 1e-9f * (float)pix;
-#else
-        const float gm = __ldg(gtb + 3 * HW);
-#endif
-        float bgj[3], gtj[3], guj[3];
+        float gm = 0.0f, bgj[3], gtj[3], guj[3];
+        if (analytic || SUMS) gm = __ldg(p.gt + ((size_t)b * 4 + 3) * HW + pix);
         #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-#ifdef EXP_NO_PIXLD
-            gtj[ch] = 0.25f * ch + 1e-9f * (float)pix; bgj[ch] = 0.3f * ch + 1e-9f * (float)pix;
-#else
-            gtj[ch] = __ldg(gtb + ch * HW);
+            gtj[ch] = (analytic || SUMS) ? __ldg(p.gt + ((size_t)b * 4 + ch) * HW + pix) : 0.0f;
             bgj[ch] = p.no_mask ? __ldg(p.bg + ((size_t)b * 3 + ch) * HW + pix) : 0.0f;
-#endif
             guj[ch] = HAS_GUP ? __ldg(p.g_rgba + ((size_t)b * 4 + ch) * HW + pix) : 0.0f;
         }
         const FaceRec r = load_rec(rec, f);
@@ -277,11 +287,7 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
         float tcol[3];
         #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-#ifdef EXP_NO_TEXLD
-            tf[ch].nw = bl.nw + ch; tf[ch].ne = bl.ne; tf[ch].sw = bl.sw * 0.5f; tf[ch].se = bl.se + 0.1f;
-#else
             tf[ch] = tex_fetch(tb + (size_t)ch * p.Htp * p.Wt, bl, p.Ht, p.Wt, p.Htp);
-#endif
             tcol[ch] = tex_blend(tf[ch], bl);
         }
         float bnd[9];
@@ -293,23 +299,22 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
         for (int ch = 0; ch < 3; ++ch) {
             const float pre = composite_pre(p.no_mask, tcol[ch], tm, bgj[ch], coef);
             const float val = clamp01(pre);
-#ifndef EXP_NO_PIXST
-            out[ch * HW] = val;
-#else
-            if (val == 12345.f) out[ch * HW] = val;
-#endif
-            const float lt = l1_term(val, gtj[ch], gm);
-            acc_l1 += fabsf(lt);
-            float g = guj[ch] + k_img * sgnf(lt) * gm;
-            g = (pre >= 0.0f && pre <= 1.0f) ? g : 0.0f;                     // torch.clamp backward
-            g_tcol[ch] = g * tm * coef;
-#ifndef EXP_NO_PIXST
-            if (p.g_bg) p.g_bg[((size_t)b * 3 + ch) * HW + pix] = g * (1.0f - tm) * coef;
-#else
-            if (g == 12345.f) p.g_bg[((size_t)b * 3 + ch) * HW + pix] = g * (1.0f - tm) * coef;
-#endif
-            g_coef += p.no_mask ? g * (tcol[ch] * tm + bgj[ch] * (1.0f - tm)) : g * (tcol[ch] * tm);
+            if (OUT) out[ch * HW] = val;
+            if (GRAD) {
+                const float lt = l1_term(val, gtj[ch], gm);
+                if (SUMS) acc_l1 += fabsf(lt);
+                float g = guj[ch] + k_img * sgnf(lt) * gm;
+                g = (pre >= 0.0f && pre <= 1.0f) ? g : 0.0f;                     // torch.clamp backward
+                g_tcol[ch] = g * tm * coef;
+                if (p.g_bg) p.g_bg[((size_t)b * 3 + ch) * HW + pix] = g * (1.0f - tm) * coef;
+                g_coef += p.no_mask ? g * (tcol[ch] * tm + bgj[ch] * (1.0f - tm)) : g * (tcol[ch] * tm);
+            }
         }
+        if (MODE == SHADE_FWD && p.imnormal) {
+            float* no = p.imnormal + ((size_t)b * HW + pix) * 3;
+            no[0] = nx; no[1] = ny; no[2] = nz;
+        }
+        if (!GRAD) continue;
         #pragma unroll
         for (int k = 0; k < 9; ++k) acc_l[k] += g_coef * bnd[k];
 
@@ -321,11 +326,7 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
         #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
             const float g = g_tcol[ch];
-#ifdef EXP_NO_ATOM
-            if (g == 12345.0f) {
-#else
             if (g != 0.0f) {
-#endif
                 float* gp = gtex + ((size_t)ch * p.Htp + tr0) * p.Wt + bl.ix;
                 float* gq = gtex + ((size_t)ch * p.Htp + tr1) * p.Wt + bl.ix;
                 atomicAdd(gp, g * bl.nw);
@@ -347,22 +348,12 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
         const float dcz = l[2] * SH_C1 + l[5] * SH_C2 * ny + l[6] * SH_C3 * 2.0f * nz + l[7] * SH_C4 * nx;
         float* ga = gacc + (size_t)f * MM_GF;
         const float gn_scale = g_coef * tm;
-#ifdef EXP_NO_ATOM
-        if (gn_scale == 12345.0f) {
-#else
-        if (gn_scale != 0.0f) {
-#endif
-            red_add_v4(ga + 8, gn_scale * dcx, gn_scale * dcy, gn_scale * dcz, 0.0f);
-        }
+        if (gn_scale != 0.0f) red_add_v4(ga + 8, gn_scale * dcx, gn_scale * dcy, gn_scale * dcz, 0.0f);
         // hard rasteriser backward (DIBR_SPEC A.3) for the u,v channels.  Gradients carry a tolerance (unlike the visibility
         // decisions), so this block is written for instruction count, not for the reference's rounding sequence: the two
         // channels are folded into A1 = sum_d dLdI_d (c1_d - c0_d), A2 = sum_d dLdI_d (c2_d - c0_d) first, and the
         // structurally-zero partials are dropped.
-#ifdef EXP_NO_ATOM
-        if (g_u == 12345.0f) {
-#else
         if (g_u != 0.0f || g_v != 0.0f) {
-#endif
             // the record, the barycentric set-up and the face's uvs are RE-derived here (L1 hits + ~15 flops) instead of being
             // kept alive across the texture section: ~20 registers less at the kernel's widest point
             const FaceRec r2 = load_rec(rec, f);
@@ -389,152 +380,47 @@ __device__ __forceinline__ void shade_fused_role(const mm_raster_params& p, Shad
             red_add_v2(ga + 4, gcx, gcy);
         }
     }
+    if (!GRAD && !SUMS) return;
 
     // ---- per-image sums: warp shuffle -> fixed-point integer atomics (order-independent, hence deterministic)
-    acc_l[0] += acc_gc * SH_C0;                  // background pixels: bands = (C0, 0, .., -C3B, 0, 0)
-    acc_l[6] += acc_gc * (-SH_C3B);
-    const float s0 = warp_sum(acc_l1), s1 = warp_sum(acc_n), s2 = warp_sum(acc_d);
-    if (!SPLIT && p.gsoft_iou_pending && p.contour > 0.0f) {
-        const float s3 = warp_sum(acc_c);
-        if (lane == 0 && s3 != 0.0f) fx_add(p.img_bwd + b * 12, s3, MM_FX_LOSS);
+    if (SUMS) {
+        const float s0 = warp_sum(acc_l1), s1 = warp_sum(acc_n), s2 = warp_sum(acc_d);
+        if (p.gsoft_iou_pending && p.contour > 0.0f) {
+            const float s3 = warp_sum(acc_c);
+            if (lane == 0 && s3 != 0.0f) fx_add(p.img_bwd + b * 12, s3, MM_FX_LOSS);
+        }
+        if (lane == 0) {
+            if (s0 != 0.0f) fx_add(p.img_fwd + b * 4 + 0, s0, MM_FX_LOSS);
+            if (s1 != 0.0f) fx_add(p.img_fwd + b * 4 + 1, s1, MM_FX_LOSS);
+            if (s2 != 0.0f) fx_add(p.img_fwd + b * 4 + 2, s2, MM_FX_LOSS);
+        }
     }
-    if (lane == 0) {
-        if (s0 != 0.0f) fx_add(p.img_fwd + b * 4 + 0, s0, MM_FX_LOSS);
-        if (s1 != 0.0f) fx_add(p.img_fwd + b * 4 + 1, s1, MM_FX_LOSS);
-        if (s2 != 0.0f) fx_add(p.img_fwd + b * 4 + 2, s2, MM_FX_LOSS);
-    }
-    #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        if (count > 0 || i == 0 || i == 6) {                // background strip: only bands 0 and 6 are non-zero
-            const float si = warp_sum(acc_l[i]);
-            if (lane == 0 && si != 0.0f) fx_add(p.img_bwd + b * 12 + 1 + i, si, MM_FX_GRAD);
+    if (GRAD) {
+        acc_l[0] += acc_gc * SH_C0;                  // background pixels: bands = (C0, 0, .., -C3B, 0, 0)
+        acc_l[6] += acc_gc * (-SH_C3B);
+        #pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            if (count > 0 || i == 0 || i == 6) {                // background strip: only bands 0 and 6 are non-zero
+                const float si = warp_sum(acc_l[i]);
+                if (lane == 0 && si != 0.0f) fx_add(p.img_bwd + b * 12 + 1 + i, si, MM_FX_GRAD);
+            }
         }
     }
 }
 
-// stand-alone fused shading (the silhouette is final: runs after the soft pass)
-template <bool VEC, bool HAS_GUP>
+template <bool VEC, bool HAS_GUP, int MODE>
 __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MINB)
-k_shade_fused(const mm_raster_params p)
+k_shade(const mm_raster_params p)
 {
     mm_pdl_prologue();
     __shared__ ShadeSmem sm;
-    shade_fused_role<VEC, HAS_GUP, false>(p, sm, blockIdx.x, blockIdx.y);
-}
-
-// ---------------------------------------------------------------------------------------------- soft pass || shading, one launch
-// After the hard pass the soft-silhouette forward (latency-bound, ~40 % of the warp slots busy) and the RGB side of the shading
-// (latency-bound too) are independent: both only need the visibility buffer.  One launch runs them side by side -- CTAs are
-// dealt to the two roles interleaved in proportion (the block scheduler hands out CTAs in index order), so each SM holds a mix
-// and the idle issue slots of one role are filled by the other.  What needs the FINAL silhouette moves to k_alpha.
-#ifndef MERGED_MINB
-#define MERGED_MINB 4
-#endif
-template <bool VEC, bool HAS_GUP>
-__global__ void __launch_bounds__(FUSED_THREADS, MERGED_MINB)
-k_soft_shade(const mm_raster_params p, const int nshade, const int nshade_x, const int nsoft)
-{
-    mm_pdl_prologue();
-    __shared__ union { ShadeSmem shade; SoftQ soft[SF_WARPS]; } sm;
-    static_assert(FUSED_THREADS == 32 * SF_WARPS, "both roles share one CTA shape");
-    // role of CTA i: shade iff floor((i+1) * nshade / total) > floor(i * nshade / total); its index in the role = that floor
-    const unsigned long long total = (unsigned long long)nshade + (unsigned long long)nsoft;
-    const unsigned long long i = blockIdx.x;
-    const int s0 = (int)((i * (unsigned long long)nshade) / total), s1 = (int)(((i + 1) * (unsigned long long)nshade) / total);
-    if (s1 > s0) {
-        const int b = s0 / nshade_x;
-        shade_fused_role<VEC, HAS_GUP, true>(p, sm.shade, s0 - b * nshade_x, b);
-    } else {
-        const int vblock = (int)i - s0;                       // soft CTAs before this one
-        soft_fwd_role(p, sm.soft[threadIdx.x >> 5], vblock * SF_WARPS + (int)(threadIdx.x >> 5));
-    }
-}
-
-// ---------------------------------------------------------------------------------------------- final silhouette
-// Runs after the soft pass (and its overflow pass): alpha plane of the output, IoU partial sums (kaolin mask_iou), and -- when
-// H and W are multiples of 4 (FAST4: the contour term's 4x4 blocks are then aligned) -- the contour loss sum and the tile-local
-// part of d(loss)/d(silhouette) (upstream + contour; the IoU term is added by the consumers, gsoft_at).
-template <bool FAST4>
-__global__ void __launch_bounds__(128)
-k_alpha(const mm_raster_params p)
-{
-    mm_pdl_prologue();
-    const int b = blockIdx.y;
-    const int H = p.H, W = p.W;
-    const size_t HW = (size_t)H * W;
-    const unsigned long long* la = p.lacc + (size_t)b * HW;
-    const uint32_t* covb = p.cov + (size_t)b * H * p.covw;
-    const float* gmask = p.gt + (size_t)b * 4 * HW + 3 * HW;
-    float* alpha = p.rgba + (size_t)b * 4 * HW + 3 * HW;
-    float acc_n = 0.0f, acc_d = 0.0f, acc_c = 0.0f;
-    if (FAST4) {
-        const float* gup = p.g_rgba ? p.g_rgba + (size_t)b * 4 * HW + 3 * HW : nullptr;
-        const int W4 = W >> 2;
-        const int t = blockIdx.x * blockDim.x + threadIdx.x;         // (4x4 block, row-in-block): 4 consecutive lanes = one block
-        const int blk = t >> 2, r = t & 3;
-        const bool active = blk < (H >> 2) * W4;
-        const int by = blk / W4, bx = blk - by * W4;
-        const int iy = by * 4 + r, ix0 = bx * 4;
-        const size_t pix0 = active ? (size_t)iy * W + ix0 : 0;
-        float m[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0}, out[4] = {0, 0, 0, 0};
-        if (active) {
-            const ulonglong2 l0 = *reinterpret_cast<const ulonglong2*>(la + pix0), l1 = *reinterpret_cast<const ulonglong2*>(la + pix0 + 2);
-            const uint32_t cw = __ldg(covb + (size_t)iy * p.covw + (ix0 >> 5)) >> (ix0 & 31);
-            load4<true>(gmask + pix0, 4, g);
-            if (gup) load4<true>(gup + pix0, 4, out);
-            const unsigned long long l[4] = {l0.x, l0.y, l1.x, l1.y};
-            #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                m[j] = ((cw >> j) & 1u) ? 1.0f : lacc_soft(l[j]);
-                const float mul = m[j] * g[j];
-                acc_n += mul;
-                acc_d += (m[j] + g[j]) - mul;
-            }
-            store4<true>(alpha + pix0, 4, m);
-        }
-        if (p.contour > 0.0f) {
-            const float k_cont = p.loss_scale * p.contour / ((float)p.B * (float)HW);
-            const int ref_lane = threadIdx.x & 28;                    // lane of row 0 of this block (warp-relative)
-            const float mref = __shfl_sync(FULL, m[0], ref_lane), gref = __shfl_sync(FULL, g[0], ref_lane);
-            float tsum = 0.0f;
-            #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float dlt = fabsf(m[j] - mref) - fabsf(g[j] - gref);
-                acc_c += dlt * dlt;                                   // inactive lanes hold zeros
-                const float own = 2.0f * dlt * sgnf(m[j] - mref);
-                out[j] += k_cont * own;
-                tsum -= own;                                          // what this pixel contributes to its reference pixel
-            }
-            tsum += __shfl_xor_sync(FULL, tsum, 1);
-            tsum += __shfl_xor_sync(FULL, tsum, 2);
-            if (r == 0) out[0] += k_cont * tsum;
-        }
-        if (active) store4<true>(p.gsoft + (size_t)b * HW + pix0, 4, out);
-    } else {
-        const int i = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i < H * W) {
-            const int iy = i / W, ix = i - iy * W;
-            const bool covered = (__ldg(covb + (size_t)iy * p.covw + (ix >> 5)) >> (ix & 31)) & 1u;
-            const float m = covered ? 1.0f : lacc_soft(la[i]);
-            const float gm = gmask[i];
-            alpha[i] = m;
-            const float mul = m * gm;
-            acc_n += mul;
-            acc_d += (m + gm) - mul;
-        }
-    }
-    const float s1 = warp_sum(acc_n), s2 = warp_sum(acc_d), s3 = warp_sum(acc_c);
-    if ((threadIdx.x & 31) == 0) {
-        if (s1 != 0.0f) fx_add(p.img_fwd + b * 4 + 1, s1, MM_FX_LOSS);
-        if (s2 != 0.0f) fx_add(p.img_fwd + b * 4 + 2, s2, MM_FX_LOSS);
-        if (FAST4 && s3 != 0.0f) fx_add(p.img_bwd + b * 12, s3, MM_FX_LOSS);
-    }
+    shade_role<VEC, HAS_GUP, MODE>(p, sm, blockIdx.x, blockIdx.y);
 }
 
 // ---------------------------------------------------------------------------------------------- d(loss)/d(silhouette)
-// FAST4 (H, W multiples of 4): the contour term's nearest-down/nearest-up reference of a pixel is the top-left pixel of
-// its 4x4 block (DIBR_SPEC A.7).  4 consecutive lanes own the 4 rows of one block, each lane one float4 row segment.
-template <bool FAST4>
+// H or W not a multiple of 4: the contour term's nearest-down / nearest-up reference of a pixel (DIBR_SPEC A.7) is not
+// tile-local; this pass forms d(loss)/d(silhouette) (upstream + IoU + contour) per pixel through the ctx's index tables and,
+// in the fused step, the contour loss sum.  (Multiples of 4 never come here: the shading kernel does it on the fly.)
 __global__ void __launch_bounds__(128)
 k_gsoft(const mm_raster_params p)
 {
@@ -550,78 +436,42 @@ k_gsoft(const mm_raster_params p)
     if (threadIdx.x == 0) {
         const float Nb0 = fx_get(p.img_fwd + b * 4 + 1, MM_FX_LOSS);
         const float De0 = fx_get(p.img_fwd + b * 4 + 2, MM_FX_LOSS) + 1e-10f;
-        s_k[0] = Nb0; s_k[1] = De0; s_k[2] = 1.0f / (De0 * De0);
+        s_k[0] = Nb0; s_k[1] = De0; s_k[2] = 1.0f / (De0 * De0); s_k[3] = eff_loss_scale(p);
     }
     __syncthreads();
-    const float Nb = s_k[0], De = s_k[1], inv_de2 = s_k[2];
-    const float k_iou = p.loss_scale / (float)p.B;
-    const float k_cont = p.loss_scale * p.contour / ((float)p.B * (float)HW);
+    const float Nb = s_k[0], De = s_k[1], inv_de2 = s_k[2], lscale = s_k[3];
+    const float k_iou = lscale / (float)p.B;
+    const float k_cont = lscale * p.contour / ((float)p.B * (float)HW);
     float acc_c = 0.0f;
-    if (FAST4) {
-        const int W4 = W >> 2;
-        const int t = blockIdx.x * blockDim.x + threadIdx.x;         // (block, row-in-block)
-        const int blk = t >> 2, r = t & 3;
-        const bool active = blk < (H >> 2) * W4;
-        const int by = blk / W4, bx = blk - by * W4;
-        const size_t pix0 = active ? (size_t)(by * 4 + r) * W + bx * 4 : 0;
-        float m[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0}, u[4] = {0, 0, 0, 0};
-        if (active) {
-            load4<true>(alpha + pix0, 4, m);
-            load4<true>(gmask + pix0, 4, g);
-            if (gup) load4<true>(gup + pix0, 4, u);
-        }
-        const int ref_lane = threadIdx.x & 28;                        // lane of row 0 of this block (warp-relative)
-        const float mref = __shfl_sync(FULL, m[0], ref_lane), gref = __shfl_sync(FULL, g[0], ref_lane);
-        float out[4];
-        float tsum = 0.0f;
-        #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            out[j] = u[j] - k_iou * (g[j] * De - Nb * (1.0f - g[j])) * inv_de2;
-            if (p.contour > 0.0f) {
-                const float dlt = fabsf(m[j] - mref) - fabsf(g[j] - gref);
-                acc_c += active ? dlt * dlt : 0.0f;
-                const float own = 2.0f * dlt * sgnf(m[j] - mref);
-                out[j] += k_cont * own;
-                tsum -= own;                                          // what this pixel contributes to its reference pixel
-            }
-        }
+    const int32_t* refrow = p.tab;
+    const int32_t* rowlo = p.tab + H;
+    const int32_t* rowhi = p.tab + 2 * H;
+    const int32_t* refcol = p.tab + 3 * H;
+    const int32_t* collo = p.tab + 3 * H + W;
+    const int32_t* colhi = p.tab + 3 * H + 2 * W;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < H * W) {
+        const float gm = gmask[i], m = alpha[i];
+        float g = (gup ? gup[i] : 0.0f) - k_iou * (gm * De - Nb * (1.0f - gm)) * inv_de2;
         if (p.contour > 0.0f) {
-            tsum += __shfl_xor_sync(FULL, tsum, 1);
-            tsum += __shfl_xor_sync(FULL, tsum, 2);
-            if (r == 0) out[0] += k_cont * tsum;
+            const int iy = i / W, ix = i - iy * W;
+            const size_t rp = (size_t)refrow[iy] * W + refcol[ix];
+            const float mref = alpha[rp], gref = gmask[rp];
+            const float dlt = fabsf(m - mref) - fabsf(gm - gref);
+            acc_c += dlt * dlt;
+            float gc = 2.0f * dlt * sgnf(m - mref);
+            for (int yy = rowlo[iy]; yy < rowhi[iy]; ++yy)
+                for (int xx = collo[ix]; xx < colhi[ix]; ++xx) {
+                    const size_t q = (size_t)yy * W + xx;
+                    const float mq = alpha[q], gq = gmask[q];
+                    const float dq = fabsf(mq - m) - fabsf(gq - gm);
+                    gc -= 2.0f * dq * sgnf(mq - m);
+                }
+            g += k_cont * gc;
         }
-        if (active) store4<true>(gs + pix0, 4, out);
-    } else {
-        const int32_t* refrow = p.tab;
-        const int32_t* rowlo = p.tab + H;
-        const int32_t* rowhi = p.tab + 2 * H;
-        const int32_t* refcol = p.tab + 3 * H;
-        const int32_t* collo = p.tab + 3 * H + W;
-        const int32_t* colhi = p.tab + 3 * H + 2 * W;
-        const int i = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i < H * W) {
-            const float gm = gmask[i], m = alpha[i];
-            float g = (gup ? gup[i] : 0.0f) - k_iou * (gm * De - Nb * (1.0f - gm)) * inv_de2;
-            if (p.contour > 0.0f) {
-                const int iy = i / W, ix = i - iy * W;
-                const size_t rp = (size_t)refrow[iy] * W + refcol[ix];
-                const float mref = alpha[rp], gref = gmask[rp];
-                const float dlt = fabsf(m - mref) - fabsf(gm - gref);
-                acc_c += dlt * dlt;
-                float gc = 2.0f * dlt * sgnf(m - mref);
-                for (int yy = rowlo[iy]; yy < rowhi[iy]; ++yy)
-                    for (int xx = collo[ix]; xx < colhi[ix]; ++xx) {
-                        const size_t q = (size_t)yy * W + xx;
-                        const float mq = alpha[q], gq = gmask[q];
-                        const float dq = fabsf(mq - m) - fabsf(gq - gm);
-                        gc -= 2.0f * dq * sgnf(mq - m);
-                    }
-                g += k_cont * gc;
-            }
-            gs[i] = g;
-        }
+        gs[i] = g;
     }
-    if (p.contour > 0.0f) {
+    if (p.contour > 0.0f && p.analytic_loss == 1) {           // fused step only (== 1): the contour LOSS sum is formed here too
         const float sc = warp_sum(acc_c);
         if ((threadIdx.x & 31) == 0 && sc != 0.0f) fx_add(p.img_bwd + b * 12, sc, MM_FX_LOSS);
     }
@@ -629,49 +479,31 @@ k_gsoft(const mm_raster_params p)
 
 }  // namespace
 
-void mm_launch_shade_fused(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
+// VEC (16-byte accesses) needs rows that start 16-byte aligned: W a multiple of 4 AND every plane pointer 16-byte aligned
+// (a torch view with an odd storage offset, or any other ABI client, may hand over less: scalar template then)
+static bool aligned16(const void* q) { return (((uintptr_t)q) & 15) == 0; }
+
+cudaError_t mm_launch_shade(const mm_ctx* c, const mm_raster_params& p, int mode, cudaStream_t s)
 {
     const int ntiles = ((p.W + FT_W - 1) / FT_W) * ((p.H + FT_H - 1) / FT_H);
     const dim3 grid((ntiles + FUSED_WARPS - 1) / FUSED_WARPS, p.B);
-    (void)c;
-    const bool vec = (p.W & 3) == 0, gup = p.g_rgba != nullptr;
-    void (*k)(mm_raster_params) = vec ? (gup ? k_shade_fused<true, true> : k_shade_fused<true, false>)
-                                      : (gup ? k_shade_fused<false, true> : k_shade_fused<false, false>);
-    mm_launch(k, grid, dim3(FUSED_THREADS), 0, s, g_mm_pdl != 0, p);
+    const bool vec = (p.W & 3) == 0 && aligned16(p.zbuf) && aligned16(p.lacc) && aligned16(p.gt) && aligned16(p.bg) &&
+                     aligned16(p.g_rgba) && aligned16(p.rgba) && aligned16(p.g_bg) && aligned16(p.gsoft) &&
+                     aligned16(p.imnormal) && aligned16(p.face_idx_out);
+    const bool gup = p.g_rgba != nullptr;
+    void (*k)(mm_raster_params) = nullptr;
+    if (mode == SHADE_FUSED)
+        k = vec ? (gup ? k_shade<true, true, SHADE_FUSED> : k_shade<true, false, SHADE_FUSED>)
+                : (gup ? k_shade<false, true, SHADE_FUSED> : k_shade<false, false, SHADE_FUSED>);
+    else if (mode == SHADE_FWD)
+        k = vec ? k_shade<true, false, SHADE_FWD> : k_shade<false, false, SHADE_FWD>;
+    else
+        k = vec ? (gup ? k_shade<true, true, SHADE_BWD> : k_shade<true, false, SHADE_BWD>)
+                : (gup ? k_shade<false, true, SHADE_BWD> : k_shade<false, false, SHADE_BWD>);
+    return mm_launch(k, grid, dim3(FUSED_THREADS), 0, s, c->pdl != 0, p);
 }
 
-// soft-silhouette forward and RGB-side shading side by side (see k_soft_shade)
-void mm_launch_soft_shade(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
+cudaError_t mm_launch_gsoft(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
-    const int ntiles = ((p.W + FT_W - 1) / FT_W) * ((p.H + FT_H - 1) / FT_H);
-    const int nshade_x = (ntiles + FUSED_WARPS - 1) / FUSED_WARPS;
-    const int nshade = nshade_x * p.B;
-    const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW;
-    const int nsoft = (nw + SF_WARPS - 1) / SF_WARPS;
-    const bool vec = (p.W & 3) == 0, gup = p.g_rgba != nullptr;
-    void (*k)(mm_raster_params, int, int, int) = vec ? (gup ? k_soft_shade<true, true> : k_soft_shade<true, false>)
-                                                     : (gup ? k_soft_shade<false, true> : k_soft_shade<false, false>);
-    mm_launch(k, dim3(nshade + nsoft), dim3(FUSED_THREADS), 0, s, g_mm_pdl != 0, p, nshade, nshade_x, nsoft);
-}
-
-void mm_launch_alpha(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
-{
-    (void)c;
-    if ((p.W & 3) == 0 && (p.H & 3) == 0) {
-        const int threads = (p.H >> 2) * (p.W >> 2) * 4;
-        mm_launch(k_alpha<true>, dim3((threads + 127) / 128, p.B), dim3(128), 0, s, g_mm_pdl != 0, p);
-    } else {
-        mm_launch(k_alpha<false>, dim3((p.H * p.W + 127) / 128, p.B), dim3(128), 0, s, g_mm_pdl != 0, p);
-    }
-}
-
-void mm_launch_gsoft(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
-{
-    (void)c;
-    if ((p.W & 3) == 0 && (p.H & 3) == 0) {
-        const int threads = (p.H >> 2) * (p.W >> 2) * 4;
-        mm_launch(k_gsoft<true>, dim3((threads + 127) / 128, p.B), dim3(128), 0, s, g_mm_pdl != 0, p);
-    } else {
-        mm_launch(k_gsoft<false>, dim3((p.H * p.W + 127) / 128, p.B), dim3(128), 0, s, g_mm_pdl != 0, p);
-    }
+    return mm_launch(k_gsoft, dim3((p.H * p.W + 127) / 128, p.B), dim3(128), 0, s, c->pdl != 0, p);
 }

@@ -284,19 +284,19 @@ static void fill_reg(const mm_ctx* c, int B, const float* delta, const float* ve
     q.delta = delta; q.vertices = vertices; q.fn = fn;
 }
 
-void mm_launch_meshreg_fwd(const mm_ctx* c, int B, const float* delta, const float* vertices, const float* fn, float temp,
-                           float eps, int flip_l1, unsigned mask, float* partials, float* terms, cudaStream_t s)
+cudaError_t mm_launch_meshreg_fwd(const mm_ctx* c, int B, const float* delta, const float* vertices, const float* fn, float temp,
+                           float eps, int flip_l1, unsigned mask, float* partials, unsigned* ticket, float* terms, cudaStream_t s)
 {
     RegParams q;
     fill_reg(c, B, delta, vertices, fn, temp, eps, flip_l1, mask, q);
-    mm_launch(k_meshreg_fwd, dim3(B), dim3(REG_THREADS), 0, s, false, q, partials, c->d_reg_ticket, terms);
+    return mm_launch(k_meshreg_fwd, dim3(B), dim3(REG_THREADS), 0, s, false, q, partials, ticket, terms);
 }
 
-void mm_launch_meshreg_bwd(const mm_ctx* c, int B, const float* delta, const float* vertices, const float* fn, float temp,
+cudaError_t mm_launch_meshreg_bwd(const mm_ctx* c, int B, const float* delta, const float* vertices, const float* fn, float temp,
                            float eps, int flip_l1, unsigned mask, const float* g_terms, float* g_delta, float* g_vertices,
                            float* g_fn, cudaStream_t s)
 {
     RegParams q;
     fill_reg(c, B, delta, vertices, fn, temp, eps, flip_l1, mask, q);
-    mm_launch(k_meshreg_bwd, dim3(B), dim3(REG_THREADS), 0, s, false, q, g_terms, g_delta, g_vertices, g_fn);
+    return mm_launch(k_meshreg_bwd, dim3(B), dim3(REG_THREADS), 0, s, false, q, g_terms, g_delta, g_vertices, g_fn);
 }

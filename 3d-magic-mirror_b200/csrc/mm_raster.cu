@@ -481,28 +481,22 @@ k_soft_bwd(const mm_raster_params p, const int nlist)
 
 }  // namespace
 
-void mm_launch_hard(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
+cudaError_t mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
+    const bool pdl = c->pdl != 0;
     const int warps = (p.B * c->F + FPW - 1) / FPW;
-    mm_launch(k_scatter_hard, dim3((warps + 7) / 8), dim3(256), 0, s, g_mm_pdl != 0, p);
+    cudaError_t e = mm_launch(k_scatter_hard, dim3((warps + 7) / 8), dim3(256), 0, s, pdl, p);
+    if (e != cudaSuccess) return e;
+    const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW;
+    e = mm_launch(k_soft_fwd, dim3((nw + SF_WARPS - 1) / SF_WARPS), dim3(32 * SF_WARPS), 0, s, pdl, p);
+    if (e != cudaSuccess) return e;
+    return mm_launch(k_soft_ovf_fwd, dim3(c->num_sms * 16), dim3(OVF_THREADS), 0, s, pdl, p);
 }
 
-void mm_launch_soft_ovf_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
-{
-    mm_launch(k_soft_ovf_fwd, dim3(c->num_sms * 16), dim3(OVF_THREADS), 0, s, g_mm_pdl != 0, p);
-}
-
-void mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
-{
-    mm_launch_hard(c, p, s);
-    { const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW; mm_launch(k_soft_fwd, dim3((nw + SF_WARPS - 1) / SF_WARPS), dim3(32 * SF_WARPS), 0, s, g_mm_pdl != 0, p); }
-    mm_launch_soft_ovf_fwd(c, p, s);
-}
-
-void mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
+cudaError_t mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
     static_assert(SB_THREADS == OVF_THREADS, "the merged backward kernel runs both roles with one CTA shape");
     const int nlist = c->num_sms * 16, novf = c->num_sms * 8;
-    mm_launch(k_soft_bwd, dim3(nlist + novf), dim3(SB_THREADS), 0, s, g_mm_pdl != 0, p, nlist);
+    return mm_launch(k_soft_bwd, dim3(nlist + novf), dim3(SB_THREADS), 0, s, c->pdl != 0, p, nlist);
 }
 

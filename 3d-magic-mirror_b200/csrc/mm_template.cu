@@ -173,7 +173,7 @@ cudaError_t mm_launch_template_fwd(const mm_ctx* c, int N, int h, int w, const f
     int grid = (N + TF_WARPS - 1) / TF_WARPS;
     const int cap = c->num_sms * 16;                      // persistent over rows: the per-CTA table is built once
     if (grid > cap) grid = cap;
-    return mm_launch(k_template_features_fwd, dim3(grid), dim3(TF_THREADS), smem, s, g_mm_pdl != 0, q, x, local, ndiff);
+    return mm_launch(k_template_features_fwd, dim3(grid), dim3(TF_THREADS), smem, s, c->pdl != 0, q, x, local, ndiff);
 }
 
 cudaError_t mm_launch_template_bwd(const mm_ctx* c, int N, int h, int w, const float* tmpl, const float* g_local,
@@ -188,5 +188,5 @@ cudaError_t mm_launch_template_bwd(const mm_ctx* c, int N, int h, int w, const f
     int grid = (N + TF_WARPS - 1) / TF_WARPS;
     const int cap = c->num_sms * 8;
     if (grid > cap) grid = cap;
-    return mm_launch(k_template_features_bwd, dim3(grid), dim3(TF_THREADS), smem, s, g_mm_pdl != 0, q, g_local, g_ndiff, g_x);
+    return mm_launch(k_template_features_bwd, dim3(grid), dim3(TF_THREADS), smem, s, c->pdl != 0, q, g_local, g_ndiff, g_x);
 }

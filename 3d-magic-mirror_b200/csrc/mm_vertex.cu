@@ -14,6 +14,7 @@
 #include "mm_common.cuh"
 #include <math_constants.h>
 #include <cooperative_groups.h>
+#include <mutex>
 
 namespace {
 
@@ -168,7 +169,6 @@ k_vertex_fwd(const VertexFwdParams q,
 struct VertexBwdParams {
     int B, V, F, H, W;
     float proj_x, proj_y;
-    int reset;
     // loss finalisation (fused step only; loss == NULL otherwise)
     float* loss;
     const long long* img_fwd;
@@ -182,7 +182,7 @@ k_vertex_bwd(const VertexBwdParams q,
              const int32_t* __restrict__ faces, const float* __restrict__ vertices,
              const float* __restrict__ azim, const float* __restrict__ elev, const float* __restrict__ dist,
              const float* __restrict__ bias,
-             const float* __restrict__ gfacc, const float* __restrict__ g_face_normals,
+             float* __restrict__ gfacc, const float* __restrict__ g_face_normals,
              long long* __restrict__ img_bwd,
              float* __restrict__ g_vertices, float* __restrict__ g_azim, float* __restrict__ g_elev,
              float* __restrict__ g_dist, float* __restrict__ g_bias, float* __restrict__ g_lights)
@@ -220,8 +220,16 @@ k_vertex_bwd(const VertexBwdParams q,
         for (int i = 0; i < 3; ++i) { P[i][0] = svc[idx[i] * 3]; P[i][1] = svc[idx[i] * 3 + 1]; P[i][2] = svc[idx[i] * 3 + 2]; }
         float ga[9];
         {
-            const float4* gp = reinterpret_cast<const float4*>(gfacc + ((size_t)b * F + f) * MM_GF);
+            // consume and clear: the accumulators are left zeroed for the next backward on this workspace (the vertex forward
+            // zeroes them for the first one), so no call needs a memset node for them
+            float4* gp = reinterpret_cast<float4*>(gfacc + ((size_t)b * F + f) * MM_GF);
             const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
+            {
+                const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (g0.x != 0.0f || g0.y != 0.0f || g0.z != 0.0f || g0.w != 0.0f) gp[0] = z4;
+                if (g1.x != 0.0f || g1.y != 0.0f) gp[1] = z4;
+                if (g2.x != 0.0f || g2.y != 0.0f || g2.z != 0.0f) gp[2] = z4;
+            }
             ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g2.x; ga[7] = g2.y; ga[8] = g2.z;
             bool any = g_face_normals != nullptr;
             #pragma unroll
@@ -352,9 +360,8 @@ k_vertex_bwd(const VertexBwdParams q,
     // (4) light gradient: per-image fixed-point sums accumulated by the shading backward
     if (rank == 1 && threadIdx.x < 9 && g_lights) {
         g_lights[b * 9 + threadIdx.x] = (float)((double)img_bwd[b * 12 + 1 + threadIdx.x] / 17592186044416.0);   // MM_FX_GRAD
-        if (q.reset) img_bwd[b * 12 + 1 + threadIdx.x] = 0;     // stand-alone backward: leave the workspace reusable
-    }
-    if (q.reset && rank == 1 && threadIdx.x == 9) img_bwd[b * 12] = 0;
+        img_bwd[b * 12 + 1 + threadIdx.x] = 0;                  // consume and clear (entry 0, the contour sum, belongs to the
+    }                                                           // loss finalisation below and to the next vertex forward)
     // (5) fused step: loss[0..3] = data, image, mask (1 - mean IoU), contour term (networks.py:364-390), one warp, fixed order
     if (q.loss && b == 0 && rank == VB_CLUSTER - 1 && warp == 0) {
         const double FXL = 1099511627776.0;                    // MM_FX_LOSS
@@ -406,7 +413,7 @@ __global__ void k_export_faces(int V, int F, float multiplier, const int32_t* __
 
 }  // namespace
 
-void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
+cudaError_t mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec,
                           float* vimg, float* face_normals, float* gfacc_zero, long long* img_fwd, long long* img_bwd,
                           void* clr0, size_t bytes0, void* clr1, size_t bytes1, cudaStream_t s)
@@ -418,36 +425,53 @@ void mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const f
     const dim3 grid(c->nchunks, B);
     // programmatic launch here too: in a loop of steps the launch latency of this first kernel hides under the tail of whatever
     // ran before on the stream (the prologue still waits for that work to complete before touching memory)
-    mm_launch(k_vertex_fwd, grid, dim3(MM_VTHREADS), c->smem_vertex_fwd, s, g_mm_pdl != 0, q, (const int32_t*)c->d_faces, vertices,
+    return mm_launch(k_vertex_fwd, grid, dim3(MM_VTHREADS), c->smem_vertex_fwd, s, c->pdl != 0, q, (const int32_t*)c->d_faces, vertices,
               azim, elev, dist, bias, frec, vimg, face_normals, gfacc_zero, img_fwd, img_bwd);
 }
 
-void mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
-                          const float* dist, const float* bias, const float* gfacc, const float* g_face_normals,
-                          long long* img_bwd, int reset, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
+cudaError_t mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
+                          const float* dist, const float* bias, float* gfacc, const float* g_face_normals,
+                          long long* img_bwd, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,
                           float* g_bias, float* g_lights, float* loss, const long long* img_fwd, float image_weight,
                           float contour, cudaStream_t s)
 {
     const size_t smem = ((size_t)c->V * 6) * sizeof(float);
     VertexBwdParams q;
-    q.B = B; q.V = c->V; q.F = c->F; q.H = c->H; q.W = c->W; q.proj_x = c->proj_x; q.proj_y = c->proj_y; q.reset = reset;
+    q.B = B; q.V = c->V; q.F = c->F; q.H = c->H; q.W = c->W; q.proj_x = c->proj_x; q.proj_y = c->proj_y;
     q.loss = loss; q.img_fwd = img_fwd; q.image_weight = image_weight; q.contour = contour;
-    mm_launch(k_vertex_bwd, dim3(VB_CLUSTER, B), dim3(VB_THREADS), smem, s, g_mm_pdl != 0, q,
+    return mm_launch(k_vertex_bwd, dim3(VB_CLUSTER, B), dim3(VB_THREADS), smem, s, c->pdl != 0, q,
               (const int32_t*)c->d_faces, vertices, azim, elev, dist, bias, gfacc, g_face_normals, img_bwd, g_vertices,
               g_azim, g_elev, g_dist, g_bias, g_lights);
 }
 
-void mm_launch_export_faces(const mm_ctx* c, int B, const float* frec, const float* vimg, float* fvi, float* fvz,
+cudaError_t mm_launch_export_faces(const mm_ctx* c, int B, const float* frec, const float* vimg, float* fvi, float* fvz,
                             float* fnz, cudaStream_t s)
 {
     const int total = B * c->F;
     k_export_faces<<<(total + 255) / 256, 256, 0, s>>>(c->V, c->F, c->multiplier, c->d_faces, frec, vimg, fvi, fvz,
                                                        fnz, total);
+    return cudaPeekAtLastError();
 }
 
 size_t mm_vertex_smem_fwd(const mm_ctx* c) { return (16 + (size_t)c->V * 5) * sizeof(float); }
 size_t mm_vertex_smem_bwd(int V) { return ((size_t)V * 6) * sizeof(float); }
-void mm_vertex_set_smem(size_t fwd, size_t bwd) {
-    cudaFuncSetAttribute(k_vertex_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd);
-    cudaFuncSetAttribute(k_vertex_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd);
+// The opt-in dynamic shared memory limit is a per-device attribute of the KERNEL, shared by every ctx of the process: keep the
+// largest requirement seen per device and only ever raise it (a second ctx with a smaller mesh must not lower the limit
+// under a first one with a larger mesh).
+cudaError_t mm_vertex_set_smem(int device, size_t fwd, size_t bwd) {
+    static std::mutex mu;
+    static size_t cur_fwd[64] = {0}, cur_bwd[64] = {0};
+    std::lock_guard<std::mutex> lock(mu);
+    const int d = (device >= 0 && device < 64) ? device : 0;
+    if (fwd > cur_fwd[d]) {
+        cudaError_t e = cudaFuncSetAttribute(k_vertex_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd);
+        if (e != cudaSuccess) return e;
+        cur_fwd[d] = fwd;
+    }
+    if (bwd > cur_bwd[d]) {
+        cudaError_t e = cudaFuncSetAttribute(k_vertex_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd);
+        if (e != cudaSuccess) return e;
+        cur_bwd[d] = bwd;
+    }
+    return cudaSuccess;
 }

@@ -8,11 +8,12 @@ Same constructor, attributes and method signatures as the reference:
     .render(no_mask=False, **attributes) -> (rgbs[B,4,H,W], attributes)   networks.py:258
     .recon_data(pred_data, gt_data, no_mask=False, contour=0) -> 0-d      networks.py:364
     .recon_att / .recon_flip / .calc_reg_* (mesh regularisers)           networks.py:326-491
-`render` and `recon_data` are the hot path and run entirely in the CUDA library
-(one vertex-stage kernel + one raster kernel forward; raster-backward +
-vertex-backward kernels for autograd).  There is no CPU / PyTorch fallback: CPU
-tensors raise.  `render_compare` additionally exposes the fused
-render -> recon_data -> backward call (mm_render_compare_fwd_bwd).
+`render` and `recon_data` are the hot path and run entirely in the CUDA library.  The
+trainer's three calls -- render (trainer.py:276), recon_data (:441), backward (:509) --
+are lazily fused: recon_data's gradient w.r.t. the image is never materialised, the render
+backward forms it in-kernel.  There is no CPU / PyTorch fallback anywhere in this package:
+CPU tensors raise.  `render_compare` additionally exposes the one-call fused
+render -> recon_data -> backward (mm_render_compare_fwd_bwd).
 """
 import ctypes
 import math
@@ -40,7 +41,10 @@ def _stream():
 
 
 class _CtxHandle(object):
-    """Owns one mm_ctx (one per DiffRender per device)."""
+    """Owns one mm_ctx (one per DiffRender per device) and a pool of workspaces: a render keeps its workspace until its
+    backward has run (or its graph is dropped), then the buffer goes back to the pool -- no per-call 40 MB allocation."""
+
+    POOL_MAX = 8
 
     def __init__(self, dr, device_index):
         L = _lib.lib()
@@ -57,6 +61,7 @@ class _CtxHandle(object):
         _lib.check(rc, "mm_ctx_create")
         self.handle = handle
         self.device_index = device_index
+        self.device = torch.device("cuda", device_index)
         # topology of the mesh regularisers (networks.py:197-252): edges, edge -> face pairs, mirror index, depth signs and
         # the uniform Laplacian in CSR form (the reference multiplies by the dense V x V matrix, 6-7 non-zeros per row)
         i32 = lambda t: t.to(torch.int32).contiguous().cpu()          # noqa: E731
@@ -71,11 +76,39 @@ class _CtxHandle(object):
         with torch.cuda.device(device_index):
             rc = L.mm_ctx_set_regularizer_topology(handle, edges.shape[0], _ptr(edges), _ptr(e2f), _ptr(flip), _ptr(sign),
                                                    int(col.numel()), _ptr(row_off), _ptr(col), _ptr(val), float(dr.ratio))
+            # what recon_data's lazy backward returns as "d(loss)/d(pred)": a zero-stride view of this one float (the real
+            # gradient is formed inside the render backward); recognised there by its address
+            self.zero = torch.zeros(1, device=self.device, dtype=torch.float32)
         _lib.check(rc, "mm_ctx_set_regularizer_topology")
+        self._ws_bytes = {}
+        self._pool = {}
+
+    def ws_bytes(self, B):
+        n = self._ws_bytes.get(B)
+        if n is None:
+            n = int(_lib.lib().mm_workspace_bytes(self.handle, B))
+            self._ws_bytes[B] = n
+        return n
+
+    def acquire(self, B):
+        """A workspace for batch B on the current stream: (tensor, pool key)."""
+        key = (B, torch.cuda.current_stream(self.device).cuda_stream)
+        free = self._pool.get(key)
+        if free:
+            return free.pop(), key
+        return torch.empty(self.ws_bytes(B), dtype=torch.uint8, device=self.device), key
+
+    def release(self, ws, key):
+        # buffers allocated while a CUDA graph is being captured belong to that graph's memory pool: never recycle them
+        if ws is None or torch.cuda.is_current_stream_capturing():
+            return
+        free = self._pool.setdefault(key, [])
+        if len(free) < self.POOL_MAX:
+            free.append(ws)
 
     def workspace(self, B):
-        n = _lib.lib().mm_workspace_bytes(self.handle, B)
-        return torch.empty(n, dtype=torch.uint8, device=torch.device("cuda", self.device_index))
+        """A private (un-pooled) workspace, for callers that keep it (tests, bench)."""
+        return torch.empty(self.ws_bytes(B), dtype=torch.uint8, device=self.device)
 
     def __del__(self):
         try:
@@ -85,101 +118,131 @@ class _CtxHandle(object):
             pass
 
 
-class _TexMirror(object):
-    """Scope in which the ctx reads `textures` as the upper half of a vertically mirrored atlas (SURVEY 8f-3,
-    mm_ctx_set_texture_mirror); the switch is put back on exit so the ctx stays stateless between calls."""
+class _Record(object):
+    """One render call: its workspace (vertex-stage products, visibility buffer, candidate list, per-image sums) and what
+    recon_data's lazy backward handed over for the render backward."""
+    _next = [0]
 
-    def __init__(self, h, on):
-        self.h, self.on = h, bool(on)
+    def __init__(self, h, B):
+        self.h, self.B = h, B
+        self.ws, self.key = h.acquire(B)
+        self.pending = None          # (gt, image_weight, contour, g_loss) set by _ReconLazyFn.backward
+        self.recon_used = False      # the workspace holds the IoU sums of ONE recon_data call
+        self.rgba_ptr, self.version = 0, 0
+        _Record._next[0] += 1
+        self.token = _Record._next[0]
 
-    def __enter__(self):
-        if self.on:
-            _lib.check(_lib.lib().mm_ctx_set_texture_mirror(self.h.handle, 1), "mm_ctx_set_texture_mirror")
-
-    def __exit__(self, *exc):
-        if self.on:
-            _lib.lib().mm_ctx_set_texture_mirror(self.h.handle, 0)
-        return False
+    def __del__(self):
+        try:
+            self.h.release(self.ws, self.key)
+        except Exception:
+            pass
 
 
-def _require_cuda(t, name):
+def _require_cuda(t, name, what="render"):
     if not t.is_cuda:
         raise _lib.MagicMirrorError(
-            "DiffRender.%s: tensor '%s' is on %s; the render path is CUDA (sm_100a) only and has no CPU fallback"
-            % ("render", name, t.device))
+            "DiffRender.%s: tensor '%s' is on %s; this path is CUDA (sm_100a) only and has no CPU fallback"
+            % (what, name, t.device))
+
+
+def _check_render_inputs(dr, no_mask, tex_mirror, vertices, azim, elev, dist, biases, textures, lights, bg):
+    """Shape / device validation shared by render and render_compare; returns the contiguous fp32 tensors."""
+    for n, t in (("vertices", vertices), ("azimuths", azim), ("elevations", elev), ("distances", dist),
+                 ("biases", biases), ("textures", textures), ("lights", lights)):
+        _require_cuda(t, n)
+    B = azim.shape[0]
+    H, W, V = dr.height, dr.image_size, dr.num_vertices
+    vertices, azim, elev, dist = _f32c(vertices), _f32c(azim).reshape(-1), _f32c(elev).reshape(-1), _f32c(dist).reshape(-1)
+    biases, textures, lights = _f32c(biases), _f32c(textures), _f32c(lights)
+    if vertices.shape != (B, V, 3):
+        raise ValueError("vertices must be (B,%d,3), got %s" % (V, tuple(vertices.shape)))
+    if elev.shape[0] != B or dist.shape[0] != B:
+        raise ValueError("azimuths, elevations and distances must all hold B=%d values" % B)
+    if textures.dim() != 4 or textures.shape[0] != B or textures.shape[1] != 3:
+        raise ValueError("textures must be (B,3,Ht,Wt), got %s" % (tuple(textures.shape),))
+    if lights.shape != (B, 9) or biases.shape != (B, 2):
+        raise ValueError("lights must be (B,9) and biases (B,2)")
+    if no_mask:
+        if bg is None:
+            raise TypeError("render(no_mask=True) needs attributes['bg'] (B,3,H,W)")
+        _require_cuda(bg, "bg")
+        bg = _f32c(bg)
+        if bg.shape != (B, 3, H, W):
+            raise ValueError("bg must be (B,3,%d,%d), got %s" % (H, W, tuple(bg.shape)))
+    else:
+        bg = None
+    Ht, Wt = textures.shape[2] * (2 if tex_mirror else 1), textures.shape[3]
+    return B, Ht, Wt, vertices, azim, elev, dist, biases, textures, lights, bg
+
+
+def _check_plane(t, name, shape, dev):
+    _require_cuda(t, name)
+    t = _f32c(t)
+    if tuple(t.shape) != tuple(shape) or t.device != dev:
+        raise ValueError("%s must be %s on %s, got %s on %s" % (name, tuple(shape), dev, tuple(t.shape), t.device))
+    return t
 
 
 class _RenderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dr, no_mask, want_face_idx, tex_mirror, vertices, azim, elev, dist, biases, textures, lights, bg):
-        for n, t in (("vertices", vertices), ("azimuths", azim), ("elevations", elev), ("distances", dist),
-                     ("biases", biases), ("textures", textures), ("lights", lights)):
-            _require_cuda(t, n)
+        B, Ht, Wt, vertices, azim, elev, dist, biases, textures, lights, bg = _check_render_inputs(
+            dr, no_mask, tex_mirror, vertices, azim, elev, dist, biases, textures, lights, bg)
         dev = vertices.device
-        B = azim.shape[0]
-        H, W, V, F = dr.height, dr.image_size, dr.num_vertices, dr.num_faces
-        vertices, azim, elev, dist = _f32c(vertices), _f32c(azim).reshape(-1), _f32c(elev).reshape(-1), _f32c(dist).reshape(-1)
-        biases, textures, lights = _f32c(biases), _f32c(textures), _f32c(lights)
-        if vertices.shape != (B, V, 3):
-            raise ValueError("vertices must be (B,%d,3), got %s" % (V, tuple(vertices.shape)))
-        if textures.dim() != 4 or textures.shape[0] != B or textures.shape[1] != 3:
-            raise ValueError("textures must be (B,3,Ht,Wt), got %s" % (tuple(textures.shape),))
-        if lights.shape != (B, 9) or biases.shape != (B, 2):
-            raise ValueError("lights must be (B,9) and biases (B,2)")
-        if no_mask:
-            if bg is None:
-                raise TypeError("render(no_mask=True) needs attributes['bg'] (B,3,H,W)")
-            _require_cuda(bg, "bg")
-            bg = _f32c(bg)
-            if bg.shape != (B, 3, H, W):
-                raise ValueError("bg must be (B,3,%d,%d), got %s" % (H, W, tuple(bg.shape)))
-        else:
-            bg = None
-        Ht, Wt = textures.shape[2] * (2 if tex_mirror else 1), textures.shape[3]
+        H, W, F = dr.height, dr.image_size, dr.num_faces
         h = dr._ctx(dev)
-        with torch.cuda.device(dev), _TexMirror(h, tex_mirror):
+        with torch.cuda.device(dev):
             rgba = torch.empty(B, 4, H, W, device=dev, dtype=torch.float32)
             fn = torch.empty(B, F, 3, device=dev, dtype=torch.float32)
             imn = torch.empty(B, H, W, 3, device=dev, dtype=torch.float32)
             fidx = torch.empty(B, H, W, device=dev, dtype=torch.int32) if want_face_idx else None
-            ws = h.workspace(B)
+            rec = _Record(h, B)
             rc = _lib.lib().mm_render_forward(h.handle, B, _ptr(vertices), _ptr(azim), _ptr(elev), _ptr(dist),
-                                              _ptr(biases), _ptr(textures), Ht, Wt, _ptr(lights), _ptr(bg),
-                                              1 if no_mask else 0, _ptr(rgba), _ptr(fn), _ptr(imn), _ptr(fidx),
-                                              _ptr(ws), _stream())
+                                              _ptr(biases), _ptr(textures), Ht, Wt, 1 if tex_mirror else 0, _ptr(lights),
+                                              _ptr(bg), 1 if no_mask else 0, _ptr(rgba), _ptr(fn), _ptr(imn), _ptr(fidx),
+                                              _ptr(rec.ws), rec.ws.numel(), _stream())
         _lib.check(rc, "mm_render_forward")
-        ctx.dr, ctx.no_mask, ctx.h, ctx.tex_mirror = dr, bool(no_mask), h, bool(tex_mirror)
+        rec.rgba_ptr, rec.version = rgba.data_ptr(), rgba._version
+        ctx.set_materialize_grads(False)
+        ctx.dr, ctx.no_mask, ctx.h, ctx.tex_mirror, ctx.rec = dr, bool(no_mask), h, bool(tex_mirror), rec
+        ctx._mm_token = rec.token
         ctx.has_bg = bg is not None
         ctx.save_for_backward(vertices, azim, elev, dist, biases, textures, lights,
-                              bg if bg is not None else torch.empty(0, device=dev), rgba, ws)
+                              bg if bg is not None else torch.empty(0, device=dev), rgba)
         ctx.mark_non_differentiable(imn)
         if fidx is None:
             fidx = torch.empty(0, device=dev, dtype=torch.int32)
         ctx.mark_non_differentiable(fidx)
+        dr._last_rec = rec
         return rgba, fn, imn, fidx
 
     @staticmethod
     def backward(ctx, g_rgba, g_fn, _g_imn, _g_fidx):
-        vertices, azim, elev, dist, biases, textures, lights, bg, rgba, ws = ctx.saved_tensors
-        dr, h = ctx.dr, ctx.h
+        vertices, azim, elev, dist, biases, textures, lights, bg, rgba = ctx.saved_tensors
+        h, rec = ctx.h, ctx.rec
         dev = vertices.device
         B = azim.shape[0]
         bg_t = bg if ctx.has_bg else None
         Ht, Wt = textures.shape[2] * (2 if ctx.tex_mirror else 1), textures.shape[3]
-        if g_rgba is None:
-            g_rgba = torch.zeros_like(rgba)
-        g_rgba = _f32c(g_rgba)
+        # lazy fusion: recon_data's backward left (gt, weights, upstream scalar) here and returned a zero-stride dummy
+        pend, rec.pending = rec.pending, None
+        if g_rgba is not None and g_rgba.data_ptr() == h.zero.data_ptr():
+            g_rgba = None                              # the dummy alone: no other consumer contributed a gradient
+        g_rgba = _f32c(g_rgba) if g_rgba is not None else None
         g_fn = _f32c(g_fn) if g_fn is not None else None
-        with torch.cuda.device(dev), _TexMirror(h, ctx.tex_mirror):
+        gt, iw, contour, g_loss = pend if pend is not None else (None, 0.0, 0.0, None)
+        with torch.cuda.device(dev):
             g_v = torch.empty_like(vertices)
             g_az, g_el, g_di = torch.empty_like(azim), torch.empty_like(elev), torch.empty_like(dist)
             g_bi, g_tex, g_li = torch.empty_like(biases), torch.empty_like(textures), torch.empty_like(lights)
             g_bg = torch.empty_like(bg_t) if bg_t is not None else None
             rc = _lib.lib().mm_render_backward(h.handle, B, _ptr(vertices), _ptr(azim), _ptr(elev), _ptr(dist),
-                                               _ptr(biases), _ptr(textures), Ht, Wt, _ptr(lights), _ptr(bg_t),
-                                               1 if ctx.no_mask else 0, _ptr(rgba), _ptr(g_rgba), _ptr(g_fn),
+                                               _ptr(biases), _ptr(textures), Ht, Wt, 1 if ctx.tex_mirror else 0,
+                                               _ptr(lights), _ptr(bg_t), 1 if ctx.no_mask else 0, _ptr(rgba),
+                                               _ptr(g_rgba), _ptr(g_fn), _ptr(gt), iw, contour, 1.0, _ptr(g_loss),
                                                _ptr(g_v), _ptr(g_az), _ptr(g_el), _ptr(g_di), _ptr(g_bi),
-                                               _ptr(g_tex), _ptr(g_li), _ptr(g_bg), _ptr(ws), _stream())
+                                               _ptr(g_tex), _ptr(g_li), _ptr(g_bg), _ptr(rec.ws), rec.ws.numel(), _stream())
         _lib.check(rc, "mm_render_backward")
         return None, None, None, None, g_v, g_az, g_el, g_di, g_bi, g_tex, g_li, g_bg
 
@@ -200,19 +263,20 @@ class _FaceNormalsFn(torch.autograd.Function):
         h = dr._ctx(dev)
         with torch.cuda.device(dev):
             fn = torch.empty(B, dr.num_faces, 3, device=dev, dtype=torch.float32)
-            ws = h.workspace(B)
+            rec = _Record(h, B)
             rc = _lib.lib().mm_face_normals_forward(h.handle, B, _ptr(vertices), _ptr(azim), _ptr(elev), _ptr(dist), _ptr(biases),
-                                                    _ptr(fn), _ptr(ws), _stream())
+                                                    _ptr(fn), _ptr(rec.ws), rec.ws.numel(), _stream())
         _lib.check(rc, "mm_face_normals_forward")
-        ctx.h = h
-        ctx.save_for_backward(vertices, azim, elev, dist, biases, ws)
+        ctx.h, ctx.rec = h, rec
+        ctx.save_for_backward(vertices, azim, elev, dist, biases)
         return fn
 
     @staticmethod
     def backward(ctx, g_fn):
-        vertices, azim, elev, dist, biases, ws = ctx.saved_tensors
+        vertices, azim, elev, dist, biases = ctx.saved_tensors
         dev = vertices.device
         B = azim.shape[0]
+        ws = ctx.rec.ws
         with torch.cuda.device(dev):
             g_fn = _f32c(g_fn)
             gv = torch.empty_like(vertices)
@@ -220,45 +284,84 @@ class _FaceNormalsFn(torch.autograd.Function):
             gb = torch.empty_like(biases)
             rc = _lib.lib().mm_face_normals_backward(ctx.h.handle, B, _ptr(vertices), _ptr(azim), _ptr(elev), _ptr(dist),
                                                      _ptr(biases), _ptr(g_fn), _ptr(gv), _ptr(ga), _ptr(ge), _ptr(gd), _ptr(gb),
-                                                     _ptr(ws), _stream())
+                                                     _ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "mm_face_normals_backward")
         return None, gv, ga, ge, gd, gb
 
 
+def _check_recon_inputs(dr, pred, gt):
+    _require_cuda(pred, "pred_data", "recon_data")
+    _require_cuda(gt, "gt_data", "recon_data")
+    pred, gt = _f32c(pred), _f32c(gt)
+    B = pred.shape[0]
+    if pred.shape != (B, 4, dr.height, dr.image_size) or gt.shape != pred.shape:
+        raise ValueError("recon_data expects (B,4,%d,%d) tensors, got %s and %s"
+                         % (dr.height, dr.image_size, tuple(pred.shape), tuple(gt.shape)))
+    return B, pred, gt
+
+
 class _ReconFn(torch.autograd.Function):
+    """recon_data on a `pred` that is NOT an untouched render output: stand-alone kernels, materialised gradient."""
+
     @staticmethod
     def forward(ctx, dr, image_weight, contour, pred, gt):
-        _require_cuda(pred, "pred_data")
-        _require_cuda(gt, "gt_data")
-        pred, gt = _f32c(pred), _f32c(gt)
-        B = pred.shape[0]
-        if pred.shape != (B, 4, dr.height, dr.image_size) or gt.shape != pred.shape:
-            raise ValueError("recon_data expects (B,4,%d,%d) tensors, got %s and %s"
-                             % (dr.height, dr.image_size, tuple(pred.shape), tuple(gt.shape)))
+        B, pred, gt = _check_recon_inputs(dr, pred, gt)
         dev = pred.device
         h = dr._ctx(dev)
         with torch.cuda.device(dev):
             loss = torch.empty(4, device=dev, dtype=torch.float32)
-            ws = h.workspace(B)
+            rec = _Record(h, B)
             rc = _lib.lib().mm_recon_data_forward(h.handle, B, _ptr(pred), _ptr(gt), float(image_weight),
-                                                  float(contour), _ptr(loss), _ptr(None), _ptr(ws), _stream())
+                                                  float(contour), _ptr(loss), _ptr(None), _ptr(rec.ws), rec.ws.numel(), _stream())
         _lib.check(rc, "mm_recon_data_forward")
-        ctx.dr, ctx.h, ctx.iw, ctx.contour = dr, h, float(image_weight), float(contour)
-        ctx.save_for_backward(pred, gt, ws)
+        ctx.h, ctx.iw, ctx.contour, ctx.rec = h, float(image_weight), float(contour), rec
+        ctx.save_for_backward(pred, gt)
         ctx.mark_non_differentiable(loss)
-        return loss[0].clone(), loss
+        return torch.as_strided(loss, (), (), 0), loss
 
     @staticmethod
     def backward(ctx, g_loss, _g_parts):
-        pred, gt, ws = ctx.saved_tensors
+        pred, gt = ctx.saved_tensors
         B = pred.shape[0]
         dev = pred.device
+        ws = ctx.rec.ws
         with torch.cuda.device(dev):
+            g_loss = _f32c(g_loss)
             g_pred = torch.empty_like(pred)
             rc = _lib.lib().mm_recon_data_backward(ctx.h.handle, B, _ptr(pred), _ptr(gt), ctx.iw, ctx.contour, 1.0,
-                                                   _ptr(g_pred), _ptr(ws), _stream())
+                                                   _ptr(g_loss), _ptr(g_pred), _ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "mm_recon_data_backward")
-        return None, None, None, g_pred * g_loss, None
+        return None, None, None, g_pred, None
+
+
+class _ReconLazyFn(torch.autograd.Function):
+    """recon_data on the untouched output of `render` (trainer.py:276 -> :441): the loss sums are computed into THAT render's
+    workspace, and the backward does not materialise d(loss)/d(pred) -- it leaves (gt, weights, the upstream scalar as a device
+    pointer) with the render record and returns a zero-stride dummy; the render backward forms the gradient in-kernel
+    (mm_render_backward's recon_gt; SURVEY 8b "lazy fusion").  Other consumers of the image still work: autograd sums their
+    gradient with the dummy (zeros) and the render backward receives it as its materialised part."""
+
+    @staticmethod
+    def forward(ctx, dr, rec, image_weight, contour, pred, gt):
+        B, pred, gt = _check_recon_inputs(dr, pred, gt)
+        dev = pred.device
+        h = rec.h
+        with torch.cuda.device(dev):
+            loss = torch.empty(4, device=dev, dtype=torch.float32)
+            rc = _lib.lib().mm_recon_data_forward(h.handle, B, _ptr(pred), _ptr(gt), float(image_weight),
+                                                  float(contour), _ptr(loss), _ptr(None), _ptr(rec.ws), rec.ws.numel(), _stream())
+        _lib.check(rc, "mm_recon_data_forward")
+        ctx.rec, ctx.iw, ctx.contour, ctx.shape = rec, float(image_weight), float(contour), tuple(pred.shape)
+        ctx.save_for_backward(gt)
+        ctx.mark_non_differentiable(loss)
+        return torch.as_strided(loss, (), (), 0), loss
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_parts):
+        gt, = ctx.saved_tensors
+        rec = ctx.rec
+        rec.pending = (gt, ctx.iw, ctx.contour, _f32c(g_loss).reshape(1))
+        return None, None, None, None, rec.h.zero.expand(ctx.shape), None
 
 
 TERMS = ("laplacian", "flat", "edge", "depth", "depthR", "depthC", "deform", "flip")
@@ -280,7 +383,7 @@ class _MeshRegFn(torch.autograd.Function):
         h = dr._ctx(dev)
         with torch.cuda.device(dev):
             terms = torch.zeros(8, device=dev, dtype=torch.float32)
-            ws = torch.empty(B * 8, device=dev, dtype=torch.float32)
+            ws = torch.empty(B * 8 + 8, device=dev, dtype=torch.float32)
             rc = _lib.lib().mm_mesh_reg_forward(h.handle, B, _ptr(delta), _ptr(vertices), _ptr(fn), float(temp), float(eps),
                                                 1 if flip_l1 else 0, int(mask), _ptr(terms), _ptr(ws), _stream())
         _lib.check(rc, "mm_mesh_reg_forward")
@@ -355,6 +458,45 @@ class _TemplateFeaturesFn(torch.autograd.Function):
         return None, g_x, None
 
 
+class _TextureFlowFn(torch.autograd.Function):
+    """Tail of TextureEncoder.forward (network/model_res.py:598-611): bicubic grid_sample of the input image at the predicted
+    texture flow (align_corners=True, zero padding) [+ the flip-concat that builds the atlas], one kernel per direction."""
+
+    @staticmethod
+    def forward(ctx, dr, img, flow, concat):
+        _require_cuda(img, "img", "texture_flow")
+        _require_cuda(flow, "texture_flow", "texture_flow")
+        img, flow = _f32c(img), _f32c(flow)
+        if img.dim() != 4 or flow.dim() != 4 or flow.shape[1] != 2 or flow.shape[0] != img.shape[0]:
+            raise ValueError("texture_flow expects img (B,C,Hi,Wi) and flow (B,2,Ho,Wo), got %s and %s"
+                             % (tuple(img.shape), tuple(flow.shape)))
+        B, C, Hi, Wi = img.shape
+        Ho, Wo = flow.shape[2:]
+        dev = img.device
+        h = dr._ctx(dev)
+        with torch.cuda.device(dev):
+            out = torch.empty(B, C, Ho * (2 if concat else 1), Wo, device=dev, dtype=torch.float32)
+            rc = _lib.lib().mm_texture_flow_forward(h.handle, B, C, Hi, Wi, Ho, Wo, 1 if concat else 0, _ptr(img), _ptr(flow),
+                                                    _ptr(out), _stream())
+        _lib.check(rc, "mm_texture_flow_forward")
+        ctx.h, ctx.concat = h, bool(concat)
+        ctx.save_for_backward(img, flow)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        img, flow = ctx.saved_tensors
+        B, C, Hi, Wi = img.shape
+        Ho, Wo = flow.shape[2:]
+        with torch.cuda.device(img.device):
+            g_out = _f32c(g_out)
+            g_img, g_flow = torch.empty_like(img), torch.empty_like(flow)
+            rc = _lib.lib().mm_texture_flow_backward(ctx.h.handle, B, C, Hi, Wi, Ho, Wo, 1 if ctx.concat else 0, _ptr(img),
+                                                     _ptr(flow), _ptr(g_out), _ptr(g_img), _ptr(g_flow), _stream())
+        _lib.check(rc, "mm_texture_flow_backward")
+        return None, g_img, g_flow, None
+
+
 class DiffRender(object):
     # kaolin dibr_rasterization defaults (call site networks.py:297-299 passes none of them)
     sigmainv = 7000.0
@@ -388,6 +530,8 @@ class DiffRender(object):
         sign = torch.sign(self.vertices_init[:, 2])
         self.sign_init = sign.cuda() if torch.cuda.is_available() else sign      # networks.py:252
         self.print_contour = False      # the reference prints loss_contour on every call (a device sync)
+        self.lazy_fusion = True         # recon_data on a render output defers its gradient to the render backward
+        self._last_rec = None
         self._ctxs = {}
 
     # ------------------------------------------------------------------ plumbing
@@ -424,6 +568,9 @@ class DiffRender(object):
         rgbs, face_normals, imnormal, face_idx = _RenderFn.apply(
             self, bool(no_mask), want_idx, tex_mirror, vertices, azimuths, elevations, distances, biases, textures, lights,
             bg if no_mask else None)
+        rec, self._last_rec = self._last_rec, None
+        if rec is not None and rec.rgba_ptr == rgbs.data_ptr():
+            rgbs._mm_rec = rec                     # lets recon_data find this render's workspace (lazy fusion)
         attributes['face_normals'] = face_normals
         attributes['imnormal'] = imnormal          # visualisation only
         if want_idx:
@@ -461,30 +608,42 @@ class DiffRender(object):
         return res
 
     def recon_data(self, pred_data, gt_data, no_mask=False, contour=0):
-        """networks.py:364-390: image_weight * masked-L1 + (1 - soft IoU) + contour * contour-MSE."""
-        loss, parts = _ReconFn.apply(self, self.image_weight, contour, pred_data, gt_data)
+        """networks.py:364-390: image_weight * masked-L1 + (1 - soft IoU) + contour * contour-MSE.
+
+        When `pred_data` is the untouched tensor `render` returned (trainer.py:276 -> :441) the call is LAZILY FUSED with
+        that render's backward: one loss kernel now; at `backward()` the gradient w.r.t. the image is never materialised
+        (see _ReconLazyFn).  Consequence: `torch.autograd.grad(loss, pred_data)` -- the gradient with respect to the image
+        ITSELF -- returns the zero placeholder in that mode; set `dr.lazy_fusion = False` if you need it."""
+        rec = getattr(pred_data, '_mm_rec', None) if self.lazy_fusion else None
+        lazy = (rec is not None and not rec.recon_used and rec.ws is not None
+                and pred_data.data_ptr() == rec.rgba_ptr and pred_data._version == rec.version
+                and getattr(pred_data.grad_fn, '_mm_token', None) == rec.token
+                and not (torch.is_tensor(gt_data) and gt_data.requires_grad))
+        if lazy:
+            rec.recon_used = True
+            loss, parts = _ReconLazyFn.apply(self, rec, self.image_weight, contour, pred_data, gt_data)
+        else:
+            loss, parts = _ReconFn.apply(self, self.image_weight, contour, pred_data, gt_data)
         if contour > 0 and self.print_contour:
             print('loss_contour: %f' % parts[3].item())
         return loss
 
     def render_compare(self, gt_data, no_mask=False, contour=0, loss_scale=1.0, g_rgba_extra=None,
-                       g_face_normals=None, tex_mirror=False, **attributes):
+                       g_face_normals=None, tex_mirror=False, workspace=None, **attributes):
         """Fused render -> recon_data -> backward (mm_render_compare_fwd_bwd): one call returns the loss
         parts, the rendered RGBA and d(loss_scale*loss_data [+ <g_rgba_extra, rgba>])/d(every attribute).
         Equivalent to trainer.py:276 + :441 + the autograd walk of :509 for the data term."""
         A = attributes
-        dev = A['vertices'].device
-        for n in ('vertices', 'azimuths', 'elevations', 'distances', 'biases', 'textures', 'lights'):
-            _require_cuda(A[n], n)
-        vertices, textures, lights, biases = _f32c(A['vertices']), _f32c(A['textures']), _f32c(A['lights']), _f32c(A['biases'])
-        azim, elev, dist = _f32c(A['azimuths']).reshape(-1), _f32c(A['elevations']).reshape(-1), _f32c(A['distances']).reshape(-1)
-        bg = _f32c(A['bg']) if no_mask else None
-        gt = _f32c(gt_data)
-        B = azim.shape[0]
+        B, Ht, Wt, vertices, azim, elev, dist, biases, textures, lights, bg = _check_render_inputs(
+            self, no_mask, tex_mirror, A['vertices'], A['azimuths'], A['elevations'], A['distances'], A['biases'],
+            A['textures'], A['lights'], A.get('bg'))
+        dev = vertices.device
         H, W, F = self.height, self.image_size, self.num_faces
-        Ht, Wt = textures.shape[2] * (2 if tex_mirror else 1), textures.shape[3]
+        gt = _check_plane(gt_data, "gt_data", (B, 4, H, W), dev)
+        gx = _check_plane(g_rgba_extra, "g_rgba_extra", (B, 4, H, W), dev) if g_rgba_extra is not None else None
+        gfn = _check_plane(g_face_normals, "g_face_normals", (B, F, 3), dev) if g_face_normals is not None else None
         h = self._ctx(dev)
-        with torch.cuda.device(dev), _TexMirror(h, tex_mirror):
+        with torch.cuda.device(dev):
             out = {
                 'rgba': torch.empty(B, 4, H, W, device=dev), 'face_normals': torch.empty(B, F, 3, device=dev),
                 'loss': torch.empty(4, device=dev),
@@ -493,16 +652,15 @@ class DiffRender(object):
                 'g_biases': torch.empty_like(biases), 'g_textures': torch.empty_like(textures),
                 'g_lights': torch.empty_like(lights), 'g_bg': torch.empty_like(bg) if bg is not None else None,
             }
-            ws = h.workspace(B)
+            ws = workspace if workspace is not None else h.workspace(B)
             rc = _lib.lib().mm_render_compare_fwd_bwd(
                 h.handle, B, _ptr(vertices), _ptr(azim), _ptr(elev), _ptr(dist), _ptr(biases), _ptr(textures), Ht, Wt,
-                _ptr(lights), _ptr(bg), 1 if no_mask else 0, _ptr(gt), float(self.image_weight), float(contour),
-                float(loss_scale), _ptr(_f32c(g_rgba_extra) if g_rgba_extra is not None else None),
-                _ptr(_f32c(g_face_normals) if g_face_normals is not None else None),
+                1 if tex_mirror else 0, _ptr(lights), _ptr(bg), 1 if no_mask else 0, _ptr(gt), float(self.image_weight),
+                float(contour), float(loss_scale), _ptr(gx), _ptr(gfn),
                 _ptr(out['rgba']), _ptr(out['face_normals']), _ptr(out['loss']),
                 _ptr(out['g_vertices']), _ptr(out['g_azimuths']), _ptr(out['g_elevations']), _ptr(out['g_distances']),
                 _ptr(out['g_biases']), _ptr(out['g_textures']), _ptr(out['g_lights']), _ptr(out['g_bg']),
-                _ptr(ws), _stream())
+                _ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "mm_render_compare_fwd_bwd")
         out['_workspace'] = ws
         return out
@@ -538,10 +696,21 @@ class DiffRender(object):
         loss_light = 0.1 * dist_fn(pred_att['lights'], target_att['lights'])
         return loss_cam, loss_shape, loss_texture, loss_light, loss_bias
 
-    # The mesh regularisers follow the device of their inputs, as in the reference.  On CUDA tensors the fused kernel
-    # (mm_mesh_reg_forward / _backward, one launch per direction) is the only path; the torch expressions below are the
-    # host-side statement of the same formulas for CPU tensors (checked against the reference in tests/test_host_setup.py).
+    def texture_flow(self, img, flow, concat=True):
+        """SURVEY 8(f)-3 (texture side).  Drop-in for network/model_res.py:598-599,609-610 inside TextureEncoder.forward:
+            textures = F.grid_sample(img, texture_flow.permute(0, 2, 3, 1), mode='bicubic', align_corners=True)
+            textures = torch.cat([textures, textures.flip([2])], dim=2)            # concat=True (no `makeup` network in between)
+        img (B,C,Hi,Wi), flow = texture_flow (B,2,Ho,Wo) exactly as the decoder emits it (no permute); returns (B,C,2Ho,Wo)
+        (or (B,C,Ho,Wo) with concat=False -- pass that half to render(_tex_mirror=True) and the concatenated atlas never exists)."""
+        return _TextureFlowFn.apply(self, img, flow, bool(concat))
+
+    # The mesh regularisers run in the fused kernel (mm_mesh_reg_forward / _backward, one launch per direction) and nowhere
+    # else: CPU tensors raise, like the render path.  (The plain-torch statement of the same formulas lives in
+    # tests/reg_torch.py, where it is checked against the unmodified reference and used as the kernel's checker.)
     def _reg_terms(self, mask, delta=None, vertices=None, face_normals=None, temp=2.0, eps=0.001, flip_l1=False):
+        for n, t in (("delta_vertices", delta), ("vertices", vertices), ("face_normals", face_normals)):
+            if t is not None:
+                _require_cuda(t, n, "calc_reg_* / recon_flip")
         return _MeshRegFn.apply(self, mask, temp, eps, flip_l1, delta, vertices, face_normals)
 
     def regularizer_terms(self, att, temp=2.0, eps=0.001, flip_l1=False):
@@ -551,77 +720,31 @@ class DiffRender(object):
         return {k: t[i] for i, k in enumerate(TERMS)}
 
     def recon_flip(self, att, L1):
-        """networks.py:392-410: z-mirror symmetry of delta_vertices, masked where the depth sign flipped."""
-        Na = att['delta_vertices']
-        if Na.is_cuda:
-            return self._reg_terms(128, delta=Na, flip_l1=bool(L1))[7]
-        idx = self.flip_index.to(Na.device)
-        Nf = Na.index_select(1, idx)
-        Nf = Nf * Nf.new_tensor([1.0, 1.0, -1.0])
-        diff = Na - Nf
-        loss_norm = torch.abs(diff) if L1 else diff.norm(dim=2)
-        mask_a = torch.relu(torch.sign(Na[:, :, 2]) * self.sign_init.to(Na.device))
-        mask_f = mask_a.index_select(1, idx)
-        if L1:
-            # reference broadcasting: (B,V,3) * (B,V) is only valid when V == 3; mirror its intent per vertex
-            return torch.mean(loss_norm * mask_f.unsqueeze(-1))
-        return torch.mean(loss_norm * mask_f)
+        """networks.py:392-410: z-mirror symmetry of delta_vertices, masked where the depth sign flipped.  (L1=True: the
+        reference's (B,V,3) * (B,V) product is shape-invalid for V != 3; its per-vertex intent is implemented.)"""
+        return self._reg_terms(128, delta=att['delta_vertices'], flip_l1=bool(L1))[7]
 
     def calc_reg_loss(self, att):
         """networks.py:412-451: lambda_lpl * uniform-Laplacian energy + lambda_flat * dihedral flatness."""
-        delta = att['delta_vertices']
-        if delta.is_cuda:
-            t = self._reg_terms(3, delta=delta, face_normals=att['face_normals'])
-            return self.lambda_lpl * t[0] + self.lambda_flat * t[1]
-        dev = delta.device
-        lap = self.vertices_laplacian_matrix.to(dev)
-        e2f = self.edge2faces.to(dev)
-        fn = att['face_normals']
-        nb_vertices = delta.shape[1]
-        loss_laplacian = torch.mean(torch.matmul(lap, delta) ** 2) * nb_vertices * 3
-        cos = torch.sum(fn[:, e2f[:, 0]] * fn[:, e2f[:, 1]], dim=2)
-        loss_flat = torch.mean((cos - 1) ** 2) * e2f.shape[0]
-        return self.lambda_lpl * loss_laplacian + self.lambda_flat * loss_flat
+        t = self._reg_terms(3, delta=att['delta_vertices'], face_normals=att['face_normals'])
+        return self.lambda_lpl * t[0] + self.lambda_flat * t[1]
 
     def calc_reg_edge(self, pred):
         """networks.py:453-461: 0.1 * mean_b || edge_len - mean(edge_len) ||_2."""
-        if pred.is_cuda:
-            return self._reg_terms(4, vertices=pred)[2]
-        e = self.edges.to(pred.device)
-        length = torch.norm(pred[:, e[:, 0]] - pred[:, e[:, 1]], p=2, dim=2)
-        bias = length - torch.mean(length, dim=1, keepdim=True)
-        return 0.1 * torch.mean(torch.norm(bias, p=2, dim=1))
+        return self._reg_terms(4, vertices=pred)[2]
 
     def calc_reg_depth(self, pred):
         """networks.py:463-466."""
-        if pred.is_cuda:
-            return self._reg_terms(8, vertices=pred)[3]
-        return torch.mean(pred[:, :, 2] ** 2)
-
-    def _depth_weighted(self, pred, weight, eps):
-        s = self.sign_init.to(pred.device)
-        z = pred[:, :, 2]
-        return torch.mean((s >= 0) * (z - eps) ** 2 * weight + (s < 0) * (z + eps) ** 2 * weight)
+        return self._reg_terms(8, vertices=pred)[3]
 
     def calc_reg_depthR(self, pred, temp=2, eps=0.001):
         """networks.py:468-475: depth^2 weighted by exp(temp * r^2), sign-preserving."""
-        if pred.is_cuda:
-            return self._reg_terms(16, vertices=pred, temp=temp, eps=eps)[4]
-        x = pred[:, :, 0].detach()
-        y = pred[:, :, 1].detach()
-        return self._depth_weighted(pred, torch.exp(temp * (x ** 2 + (y / self.ratio) ** 2)), eps)
+        return self._reg_terms(16, vertices=pred, temp=temp, eps=eps)[4]
 
     def calc_reg_depthC(self, pred, eps=0.001):
         """networks.py:477-485: depth^2 weighted by r^2, sign-preserving."""
-        if pred.is_cuda:
-            return self._reg_terms(32, vertices=pred, eps=eps)[5]
-        x = pred[:, :, 0].detach()
-        y = pred[:, :, 1].detach()
-        return self._depth_weighted(pred, x ** 2 + (y / self.ratio) ** 2, eps)
+        return self._reg_terms(32, vertices=pred, eps=eps)[5]
 
     def calc_reg_deform(self, pred):
         """networks.py:487-491: mean per-vertex displacement norm."""
-        if pred.is_cuda:
-            return self._reg_terms(64, delta=pred)[6]
-        b = pred.shape[0]
-        return torch.mean(torch.norm(pred.reshape(-1, pred.size(2)), p=2, dim=1).reshape(b, -1))
+        return self._reg_terms(64, delta=pred)[6]

@@ -169,16 +169,12 @@ class FusedRunner(object):
         o = d['out']
         p = lambda t: ctypes.c_void_p(t.data_ptr())     # noqa: E731
         Ht, Wt = d['textures'].shape[2] * (2 if self.tex_mirror else 1), d['textures'].shape[3]
-        if self.tex_mirror:
-            self.L.mm_ctx_set_texture_mirror(self.h.handle, 1)
         rc = self.L.mm_render_compare_fwd_bwd(
             self.h.handle, self.B, p(d['vertices']), p(d['azimuths']), p(d['elevations']), p(d['distances']),
-            p(d['biases']), p(d['textures']), Ht, Wt, p(d['lights']), p(d['bg']), 1, p(d['gt']),
+            p(d['biases']), p(d['textures']), Ht, Wt, 1 if self.tex_mirror else 0, p(d['lights']), p(d['bg']), 1, p(d['gt']),
             1.0, contour, 1.0, ctypes.c_void_p(0), ctypes.c_void_p(0), p(o['rgba']), p(o['fn']), p(o['loss']),
             p(o['g_v']), p(o['g_az']), p(o['g_el']), p(o['g_di']), p(o['g_bi']), p(o['g_tex']), p(o['g_li']),
-            p(o['g_bg']), p(o['ws']), ctypes.c_void_p(self.stream.cuda_stream))
-        if self.tex_mirror:
-            self.L.mm_ctx_set_texture_mirror(self.h.handle, 0)
+            p(o['g_bg']), p(o['ws']), o['ws'].numel(), ctypes.c_void_p(self.stream.cuda_stream))
         if rc != 0:
             raise RuntimeError(self.L.mm_last_error().decode())
         return o

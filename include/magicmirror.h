@@ -11,18 +11,30 @@
  *     stated otherwise; the caller owns all buffers, including `workspace`.
  *   - the library owns only `mm_ctx` (mesh topology, per-face UVs, raster params).
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
- *     never synchronises and never allocates device memory.
+ *     never synchronises and never allocates device memory: every call can be
+ *     captured into a CUDA graph.
  *   - return value 0 = ok, < 0 = error (MM_E_*); mm_last_error() returns a
  *     thread-local message for the last failing call.
- *   - a ctx is bound to one device; calls on one ctx must be serialised by the caller.
+ *   - a ctx is bound to one device, which must be the CURRENT device of the calling
+ *     thread (checked); calls on one ctx may come from any thread; two calls that
+ *     share a workspace must be stream-ordered.  The ctx holds no per-call state.
+ *   - `workspace` / `workspace_bytes`: caller-owned scratch of at least
+ *     mm_workspace_bytes(ctx, B) bytes, 256-byte aligned (checked).  A workspace
+ *     written by a forward call must be passed unmodified to the matching backward
+ *     call (and to mm_recon_data_forward for lazy fusion, below).
  *   - gradient outputs are OVERWRITTEN (the library zero-fills), never accumulated.
- *   - `workspace` written by a forward call must be passed unmodified to the
- *     matching backward call.
+ *   - image-sized planes (rgba, gt, bg, g_rgba, g_bg, imnormal, face_idx) may have any
+ *     alignment; 16-byte aligned planes with W % 4 == 0 take the vectorised kernels.
+ *   - `tex_mirror`: the atlas the renderer reads is produced as
+ *     cat([t, t.flip(2)], dim=2) (TextureEncoder.forward, network/model_res.py:609-610):
+ *     its lower half is the upper half upside down.  With tex_mirror = 1, `tex` / `g_tex`
+ *     are the UPPER HALF alone, [B,3,Ht/2,Wt], while `Ht` stays the logical atlas height
+ *     (even): logical row r >= Ht/2 is read from (and its gradient accumulated into)
+ *     physical row Ht-1-r.  Same texels, same weights: the image is bit-identical, g_tex
+ *     equals the sum of the two halves' gradients, half the texture bytes move.
  *
  * Environment switches read at mm_ctx_create (diagnostics; defaults are the measured best):
  *   MM_PDL=0        no programmatic dependent launch between the library's kernels
- *   MM_SPLIT=1      fused step: soft pass and RGB shading in one launch + a final silhouette pass
- *   MM_PARTS=n      fused step as n concurrent sub-batches (1..4; see mm_ctx_set_parts)
  *   MM_VCHUNKS=n    CTAs per image of the vertex forward kernel (default 8)
  *   MM_PLIST_CAP=n  test hook: caps the forward's candidate list so the backward's fallback path runs
  */
@@ -36,10 +48,10 @@
 extern "C" {
 #endif
 
-#define MM_ABI_VERSION 1
+#define MM_ABI_VERSION 2
 
 #define MM_OK            0
-#define MM_E_INVALID    -1   /* bad argument (NULL pointer, non-positive size, ...) */
+#define MM_E_INVALID    -1   /* bad argument (NULL pointer, non-positive size, undersized workspace, wrong device, ...) */
 #define MM_E_CUDA       -2   /* a CUDA runtime call failed; message has the cudaError string */
 #define MM_E_UNSUPPORTED -3  /* configuration outside what the kernels support */
 
@@ -59,8 +71,7 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F,
                   float sigmainv, float boxlen, int knum, float multiplier, float eps);
 int mm_ctx_destroy(mm_ctx* ctx);
 
-/* Bytes of caller-owned scratch needed by any call on `ctx` with batch B (covers the unsplit layout and every split of the
- * fused step into sub-batches, mm_ctx_set_parts). */
+/* Bytes of caller-owned scratch needed by any call on `ctx` with batch B. */
 size_t mm_workspace_bytes(const mm_ctx* ctx, int B);
 
 /* Replaces DiffRender.render (networks.py:258-324): camera_position_from_spherical_angles
@@ -68,48 +79,57 @@ size_t mm_workspace_bytes(const mm_ctx* ctx, int B);
  * (:284), face_normals (:289), dibr_rasterization (:297), texture_mapping (:305),
  * spherical_harmonic_lighting (:306), composite + clamp + pack (:307-317).
  *   rgba          [B,4,H,W]   out
- *   face_normals  [B,F,3]     out  (attributes['face_normals'], networks.py:319)
+ *   face_normals  [B,F,3]     out  (attributes['face_normals'], networks.py:319), may be NULL
  *   imnormal      [B,H,W,3]   out, may be NULL (attributes['imnormal'], :320)
  *   face_idx      [B,H,W]     out int32, may be NULL (-1 = no face) */
 int mm_render_forward(mm_ctx* ctx, int B,
                       const float* vertices /* B,V,3 */, const float* azim /* B */,
                       const float* elev /* B */, const float* dist /* B */, const float* bias /* B,2 */,
-                      const float* tex /* B,3,Ht,Wt */, int Ht, int Wt,
+                      const float* tex /* B,3,Ht,Wt */, int Ht, int Wt, int tex_mirror,
                       const float* lights /* B,9 */, const float* bg /* B,3,H,W or NULL */, int no_mask,
                       float* rgba, float* face_normals, float* imnormal, int32_t* face_idx,
-                      void* workspace, void* stream);
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of mm_render_forward (replaces autograd through the same Kaolin calls:
  * rasterize_backward + dibr_soft_mask_backward + grid_sample backward + ...).
- *   g_rgba          [B,4,H,W]  upstream gradient
+ * The upstream gradient of the image is the SUM of two optional parts:
+ *   g_rgba          [B,4,H,W]  a materialised upstream gradient, or NULL
+ *   recon_gt        [B,4,H,W]  or NULL.  LAZY FUSION of trainer.py:441 + :509: when DiffRender.recon_data was evaluated on
+ *                   this render's output with mm_recon_data_forward ON THIS WORKSPACE, its backward does not materialise
+ *                   d(loss)/d(rgba): it hands over (recon_gt, image_weight, contour, loss_scale, loss_scale_dev) and the
+ *                   gradient loss_scale * [*loss_scale_dev] * d(recon_data)/d(rgba) is formed inside the shading kernel
+ *                   (the per-image IoU sums are in the workspace).  loss_scale_dev: DEVICE scalar or NULL (= 1).
  *   g_face_normals  [B,F,3]    upstream gradient of the face_normals output, may be NULL
  * All g_* outputs are overwritten; g_bg may be NULL (and must be when bg is NULL). */
 int mm_render_backward(mm_ctx* ctx, int B,
                        const float* vertices, const float* azim, const float* elev, const float* dist,
-                       const float* bias, const float* tex, int Ht, int Wt, const float* lights,
+                       const float* bias, const float* tex, int Ht, int Wt, int tex_mirror, const float* lights,
                        const float* bg, int no_mask,
                        const float* rgba /* forward output */,
                        const float* g_rgba, const float* g_face_normals,
+                       const float* recon_gt, float image_weight, float contour, float loss_scale,
+                       const float* loss_scale_dev,
                        float* g_vertices /* B,V,3 */, float* g_azim, float* g_elev, float* g_dist,
                        float* g_bias /* B,2 */, float* g_tex /* B,3,Ht,Wt */, float* g_lights /* B,9 */,
                        float* g_bg /* B,3,H,W or NULL */,
-                       void* workspace, void* stream);
+                       void* workspace, size_t workspace_bytes, void* stream);
 
-/* Replaces DiffRender.recon_data (networks.py:364-390) incl. kaolin mask_iou (:377).
+/* Replaces DiffRender.recon_data (networks.py:364-390) incl. kaolin mask_iou (:377).  One kernel (+ a 1 KB memset).
  *   loss      [4] out: data (= image_weight*image + mask + contour*contour_term), image, mask(1-IoU), contour_term
- *   iou_sums  [B,2] out: N_b = sum(p*g), D_b = sum(p+g-p*g); may be NULL */
+ *   iou_sums  [B,2] out: N_b = sum(p*g), D_b = sum(p+g-p*g); may be NULL
+ * The per-image sums are left in `workspace` (see mm_render_backward's recon_gt). */
 int mm_recon_data_forward(mm_ctx* ctx, int B, const float* pred /* B,4,H,W */, const float* gt /* B,4,H,W */,
                           float image_weight, float contour,
-                          float* loss, float* iou_sums, void* workspace, void* stream);
+                          float* loss, float* iou_sums, void* workspace, size_t workspace_bytes, void* stream);
 
-/* d(loss_scale * loss_data)/d(pred) -> g_pred [B,4,H,W] (overwritten). */
+/* d(loss_scale * [*loss_scale_dev] * loss_data)/d(pred) -> g_pred [B,4,H,W] (overwritten), for a `pred` that is not a
+ * render output of this library; needs the per-image sums mm_recon_data_forward left in `workspace`. */
 int mm_recon_data_backward(mm_ctx* ctx, int B, const float* pred, const float* gt,
-                           float image_weight, float contour, float loss_scale,
-                           float* g_pred, void* workspace, void* stream);
+                           float image_weight, float contour, float loss_scale, const float* loss_scale_dev,
+                           float* g_pred, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Fused benchmark path: render -> recon_data -> backward of (loss_scale*loss_data +
- * <g_rgba_extra, rgba>) in one call; the loss gradient is formed in-kernel and
- * never materialised.  Replaces trainer.py:276 + :441 + the autograd walk at :509.
+/* Fused path: render -> recon_data -> backward of (loss_scale*loss_data + <g_rgba_extra, rgba>) in one call; the loss
+ * gradient is formed in-kernel and never materialised.  Replaces trainer.py:276 + :441 + the autograd walk at :509.
  *   gt            [B,4,H,W]
  *   g_rgba_extra  [B,4,H,W] or NULL  (upstream gradient from another consumer, e.g. the GAN)
  *   g_face_normals [B,F,3] or NULL   (upstream gradient of face_normals, e.g. from calc_reg_loss, networks.py:422)
@@ -117,23 +137,24 @@ int mm_recon_data_backward(mm_ctx* ctx, int B, const float* pred, const float* g
  *   loss          [4] out, as mm_recon_data_forward */
 int mm_render_compare_fwd_bwd(mm_ctx* ctx, int B,
                               const float* vertices, const float* azim, const float* elev, const float* dist,
-                              const float* bias, const float* tex, int Ht, int Wt, const float* lights,
+                              const float* bias, const float* tex, int Ht, int Wt, int tex_mirror, const float* lights,
                               const float* bg, int no_mask,
                               const float* gt, float image_weight, float contour, float loss_scale,
                               const float* g_rgba_extra, const float* g_face_normals,
                               float* rgba, float* face_normals, float* loss,
                               float* g_vertices, float* g_azim, float* g_elev, float* g_dist, float* g_bias,
                               float* g_tex, float* g_lights, float* g_bg,
-                              void* workspace, void* stream);
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- render de-duplication.  trainer.py:367 renders only to refresh attributes['face_normals'] (the image
  * is discarded): these two calls run the vertex stage alone (prepare_vertices + face_normals, networks.py:284-290) and its
  * backward from an upstream gradient of the face normals.  Same argument conventions as mm_render_forward / _backward. */
 int mm_face_normals_forward(mm_ctx* ctx, int B, const float* vertices, const float* azim, const float* elev, const float* dist,
-                            const float* bias, float* face_normals /* B,F,3 out */, void* workspace, void* stream);
+                            const float* bias, float* face_normals /* B,F,3 out */, void* workspace, size_t workspace_bytes,
+                            void* stream);
 int mm_face_normals_backward(mm_ctx* ctx, int B, const float* vertices, const float* azim, const float* elev, const float* dist,
                              const float* bias, const float* g_face_normals /* B,F,3 */, float* g_vertices, float* g_azim,
-                             float* g_elev, float* g_dist, float* g_bias, void* workspace, void* stream);
+                             float* g_elev, float* g_dist, float* g_bias, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- the mesh regularisers next to the render path (networks.py:392-491), one launch per direction.
  * Topology they need beyond mm_ctx_create's (DiffRender.__init__, networks.py:197-252): edges [E,2], edge2faces [E,2]
@@ -148,7 +169,8 @@ int mm_ctx_set_regularizer_topology(mm_ctx* ctx, int E, const int32_t* edges_hos
  * calc_reg_edge (:453), calc_reg_depth (:463), calc_reg_depthR (:468), calc_reg_depthC (:477), calc_reg_deform (:487),
  * recon_flip (:392; flip_l1 selects its L1 form).  term_mask bit k selects term k; an input a selected term does not need may
  * be NULL (delta_vertices [B,V,3]: terms 0,6,7; vertices [B,V,3]: 2-5; face_normals [B,F,3]: 1).
- * scratch: caller-owned device floats [B,8] (per-image partial sums; reduced over the batch in image order). */
+ * scratch: caller-owned device floats [B*8 + 8] (per-image partial sums, reduced over the batch in image order, + the
+ * last-CTA ticket; per call, so concurrent calls on different streams do not share state). */
 int mm_mesh_reg_forward(mm_ctx* ctx, int B, const float* delta_vertices, const float* vertices, const float* face_normals,
                         float temp, float eps, int flip_l1, unsigned term_mask, float* terms, float* scratch, void* stream);
 
@@ -157,14 +179,6 @@ int mm_mesh_reg_forward(mm_ctx* ctx, int B, const float* delta_vertices, const f
 int mm_mesh_reg_backward(mm_ctx* ctx, int B, const float* delta_vertices, const float* vertices, const float* face_normals,
                          float temp, float eps, int flip_l1, unsigned term_mask, const float* g_terms,
                          float* g_delta_vertices, float* g_vertices, float* g_face_normals, void* stream);
-
-/* ---- the atlas the renderer reads is produced as cat([t, t.flip(2)], dim=2) (TextureEncoder.forward,
- * network/model_res.py:609-610): its lower half is the upper half upside down.  With the mirror switch on, every call on
- * `ctx` takes `tex` / `g_tex` as the UPPER HALF alone, [B,3,Ht/2,Wt], while `Ht` stays the logical atlas height (even):
- * logical row r >= Ht/2 is read from (and its gradient accumulated into) physical row Ht-1-r.  Same texels, same weights
- * as rendering the concatenated atlas -- the image is bit-identical, g_tex equals the sum of the two halves' gradients --
- * with half the texture bytes read, cleared and written.  Host-side switch; takes effect on the next call. */
-int mm_ctx_set_texture_mirror(mm_ctx* ctx, int enable);
 
 /* ---- SURVEY 8(f)-3, encoder side: ShapeEncoder.forward's template conditioning (network/model_res.py:317-325):
  *   local         = F.grid_sample(x, template[..., 0:2], 'bilinear', align_corners=True, padding_mode='zeros')   [N,V]
@@ -177,19 +191,24 @@ int mm_template_features_forward(mm_ctx* ctx, int N, int h, int w, const float* 
 int mm_template_features_backward(mm_ctx* ctx, int N, int h, int w, const float* template_xyz, const float* g_local,
                                   const float* g_neighbor_diff, float* g_x, void* stream);
 
-/* Tuning switch of mm_render_compare_fwd_bwd: run the batch as `parts` (1..4) sub-batches, each a complete kernel chain on its
- * own stream (the caller's + ctx-owned side streams, forked from and joined back into `stream` with events inside the call).
- * Images are independent through render and loss, so the outputs are those of the unsplit call (the loss scalars are the
- * image-count-weighted mean of the parts').  The workspace layout of a split call is private: mm_debug_export_faces reads
- * unsplit layouts only.  Sub-batches below 8 images are not split further; the timing hook measures the unsplit chain. */
-int mm_ctx_set_parts(mm_ctx* ctx, int parts);
-int mm_ctx_get_parts(const mm_ctx* ctx);
+/* ---- SURVEY 8(f)-3, texture side: TextureEncoder.forward's tail (network/model_res.py:598-611):
+ *   textures = F.grid_sample(img, flow.permute(0,2,3,1), mode='bicubic', align_corners=True)      (padding_mode 'zeros')
+ *   [textures = cat([textures, textures.flip(2)], dim=2)   when concat != 0; the reference's optional `makeup` network sits
+ *    between the two lines, so the concat is a switch]
+ * img [B,C,Hi,Wi], flow [B,2,Ho,Wo] (channel 0 = x, 1 = y in [-1,1], exactly the tensor the reference permutes);
+ * out [B,C,Ho*(concat?2:1),Wo].  Backward: g_img (overwritten) and g_flow (overwritten) from g_out (the two halves of a
+ * concatenated g_out are summed on the fly). */
+int mm_texture_flow_forward(mm_ctx* ctx, int B, int C, int Hi, int Wi, int Ho, int Wo, int concat,
+                            const float* img, const float* flow, float* out, void* stream);
+int mm_texture_flow_backward(mm_ctx* ctx, int B, int C, int Hi, int Wi, int Ho, int Wo, int concat,
+                             const float* img, const float* flow, const float* g_out, float* g_img, float* g_flow,
+                             void* stream);
 
 /* Test hook: copies the vertex-stage products of the last forward on `workspace`
  * (what kaolin prepare_vertices returns, networks.py:284-287) so that the oracle's
  * rasteriser can be run on bit-identical inputs.  Any pointer may be NULL.
  *   fvi [B,F,3,2] image-plane xy (unscaled), fvz [B,F,3] camera z, fnz [B,F] unit-normal z */
-int mm_debug_export_faces(mm_ctx* ctx, int B, const void* workspace,
+int mm_debug_export_faces(mm_ctx* ctx, int B, const void* workspace, size_t workspace_bytes,
                           float* fvi, float* fvz, float* fnz, void* stream);
 
 /* Measurement hook (bench.py): when enabled, mm_render_compare_fwd_bwd records a CUDA event on
@@ -197,7 +216,8 @@ int mm_debug_export_faces(mm_ctx* ctx, int B, const void* workspace,
  * and writes the group durations in milliseconds, in launch order (vertex_fwd, geometry forward [hard + soft +
  * overflow], fused shading, d/d-silhouette pass [only for H or W not a multiple of 4], geometry backward,
  * vertex_bwd + loss finalisation, -; capacity >= 7); returns the count written.  Event records switch
- * programmatic dependent launch off across them, so the figures are slightly above the in-step cost. */
+ * programmatic dependent launch off across them, so the figures are slightly above the in-step cost.
+ * (The one piece of per-call state in a ctx: do not enable it on a ctx shared between threads.) */
 int mm_ctx_set_timing(mm_ctx* ctx, int enable);
 int mm_ctx_get_timing(mm_ctx* ctx, float* ms_host, int capacity);
 

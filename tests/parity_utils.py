@@ -82,22 +82,60 @@ def rel_err(a, b):
     return (a - b).abs().max().item() / (scale if scale > 0 else 1.0)
 
 
-def oracle_for(dr, dtype=torch.float32):
+def oracle_for(dr, dtype=torch.float32, **variant):
     import ref_pipeline
     return ref_pipeline.OracleRender(dr.faces.cpu().numpy(), dr.face_uvs.cpu().numpy(), dr.image_size, dr.ratio,
                                      dr.image_weight, dtype=dtype)
 
 
+def boundary_check(orc64, A64, fidx_a, fidx_b, H, W, tol=2e-4):
+    """For every pixel where the two fp32 pipelines picked different faces: how close is that pixel, IN THE FP64 ORACLE, to
+    flipping?  margin = the smallest |barycentric weight| of the two faces at the pixel (an edge passes through the pixel
+    centre), or their relative depth gap when both contain it.  Returns (#pixels with margin > tol, worst margin).
+    A flip with a large margin is a real disagreement; a flip inside fp32 rounding of a boundary is the reference algorithm's
+    own ill-conditioning (two fp32 vertex stages differ by ~2e-7)."""
+    diff = (fidx_a != fidx_b).nonzero()
+    if diff.numel() == 0:
+        return 0, 0.0
+    with torch.no_grad():
+        fvc, fvi, _ = orc64.vertex_stage({k: v.detach() for k, v in A64.items()})
+    worst, bad = 0.0, 0
+    for b, iy, ix in diff.tolist():
+        x0 = (2 * ix + 1 - W) / W
+        y0 = (H - 2 * iy - 1) / H
+        margins, depths = [], []
+        for f in (int(fidx_a[b, iy, ix]), int(fidx_b[b, iy, ix])):
+            if f < 0:
+                continue
+            (ax, ay), (bx, by), (cx, cy) = fvi[b, f].tolist()
+            m, p, n, q, s_, t = bx - ax, by - ay, cx - ax, cy - ay, x0 - ax, y0 - ay
+            k3 = m * q - n * p
+            w1, w2 = (s_ * q - n * t) / (k3 + 1e-14), (m * t - s_ * p) / (k3 + 1e-14)
+            w0 = 1 - w1 - w2
+            margins.append(min(abs(w0), abs(w1), abs(w2)))
+            z = fvc[b, f, :, 2].tolist()
+            depths.append((min(w0, w1, w2), w0 * z[0] + w1 * z[1] + w2 * z[2]))
+        margin = min(margins) if margins else 1.0
+        if len(depths) == 2 and depths[0][0] >= 0 and depths[1][0] >= 0:          # both contain the pixel: a depth tie?
+            margin = min(margin, abs(depths[0][1] - depths[1][1]) / max(abs(depths[0][1]), 1e-12))
+        worst = max(worst, margin)
+        bad += margin > tol
+    return bad, worst
+
+
 def run_parity_case(mm, mesh="icosphere", B=2, image_size=32, ratio=1, no_mask=True, contour=0.1, seed=0,
-                    device="cuda:0", init_ellipsoid=1, dist_range=(2.0, 7.0), image_weight=1.0, fused=True):
+                    device="cuda:0", init_ellipsoid=1, dist_range=(2.0, 7.0), image_weight=1.0, fused=True, tex=None,
+                    elev_range=(0.0, 30.0), bias_range=0.3):
     """CUDA product vs CPU oracle on one seeded case.  Returns a dict of error figures."""
     import ctypes
     import kaolin_shim as kal
     tm = get_mesh(mm, mesh)
     dr = mm.DiffRender(tm, image_size, ratio=ratio, init_ellipsoid=init_ellipsoid, image_weight=image_weight)
     H, W = dr.height, dr.image_size
-    A_cpu = make_attributes(dr.vertices_init, B, H, W, seed, dist_range=dist_range)
-    gt_src = make_attributes(dr.vertices_init, B, H, W, seed + 1000, dist_range=dist_range)
+    Ht, Wt = tex if tex is not None else (None, None)
+    kw = dict(dist_range=dist_range, elev_range=elev_range, bias_range=bias_range, Ht=Ht, Wt=Wt)
+    A_cpu = make_attributes(dr.vertices_init, B, H, W, seed, **kw)
+    gt_src = make_attributes(dr.vertices_init, B, H, W, seed + 1000, **kw)
     orc = oracle_for(dr)
 
     # ---------------- oracle (CPU): GT image = render of an independent sample (SURVEY 8d)
@@ -130,15 +168,12 @@ def run_parity_case(mm, mesh="icosphere", B=2, image_size=32, ratio=1, no_mask=T
     fvi = torch.empty(B, F, 3, 2, device=device)
     fvz = torch.empty(B, F, 3, device=device)
     fnz = torch.empty(B, F, device=device)
-    # re-run the forward to get a workspace we own (unsplit: mm_debug_export_faces reads the unsplit workspace layout)
-    parts = mm.lib().mm_ctx_get_parts(h.handle)
-    mm.lib().mm_ctx_set_parts(h.handle, 1)
+    # re-run the forward through the fused entry point to get a workspace we own
     with torch.no_grad():
         out = dr.render_compare(gt_dev, no_mask=no_mask, contour=contour, **{k: v.detach() for k, v in Ac.items()
                                                                              if k != '_want_face_idx'})
-    mm.lib().mm_ctx_set_parts(h.handle, parts)
     ws = out['_workspace']
-    rc = mm.lib().mm_debug_export_faces(h.handle, B, ctypes.c_void_p(ws.data_ptr()), ctypes.c_void_p(fvi.data_ptr()),
+    rc = mm.lib().mm_debug_export_faces(h.handle, B, ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctypes.c_void_p(fvi.data_ptr()),
                                         ctypes.c_void_p(fvz.data_ptr()), ctypes.c_void_p(fnz.data_ptr()),
                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0
@@ -170,23 +205,45 @@ def run_parity_case(mm, mesh="icosphere", B=2, image_size=32, ratio=1, no_mask=T
     res["face_normals_rel_err"] = rel_err(Aout['face_normals'], fn_o)
     # fp32 noise floor of the reference algorithm itself: the same oracle in fp64 is the arbiter.  Sliver faces at
     # the silhouette (k3 -> 0) and small faces far from the camera amplify the ~2e-7 difference between two fp32
-    # vertex stages; whatever the fp32 oracle loses against fp64, the product may lose too (x2), never more.
+    # vertex stages; whatever the fp32 oracle loses against fp64, the product may lose too (x4), never more.
     orc64 = oracle_for(dr, torch.float64)
-    with torch.no_grad():
-        rgb64, fn64, _, fidx64 = orc64.render(no_mask=no_mask, **{k: v.double() for k, v in A_cpu.items()})
+    A64 = {k: v.double().requires_grad_(k != 'delta_vertices') for k, v in A_cpu.items()}
+    rgb64, fn64, _, fidx64 = orc64.render(no_mask=no_mask, **A64)
+    loss64 = orc64.recon_data(rgb64, gt_cpu.double(), no_mask=no_mask, contour=contour)
+    (loss64 + (fn64 * wfn.double()).sum()).backward()
+    rgb64, fn64 = rgb64.detach(), fn64.detach()
     agree = ((fidx_c == fidx_o) & (fidx_o == fidx64))[:, None].expand(-1, 4, -1, -1)
     res["rgba_noise_f32_oracle_vs_f64"] = float((rgb_o.detach().double() - rgb64).abs()[agree].max())
     res["rgba_err_vs_f64"] = float((rgb_c.detach().cpu().double() - rgb64).abs()[agree].max())
     res["face_normals_noise_f32_oracle_vs_f64"] = rel_err(fn_o, fn64)
     res["face_normals_err_vs_f64"] = rel_err(Aout['face_normals'], fn64)
+    res["loss_noise_f32_oracle_vs_f64"] = abs(float(loss_o) - float(loss64)) / max(abs(float(loss64)), 1e-12)
+    # every pixel whose winner differs end to end must sit on a decision boundary of the fp64 oracle (an edge of one of the two
+    # faces within fp32 rounding of the pixel centre, or a depth tie): `face_idx_unexcused` counts the ones that do not
+    res["face_idx_unexcused"], res["face_idx_worst_margin"] = boundary_check(orc64, A64, fidx_c, fidx_o, H, W)
+    only32 = (fidx_c == fidx_o) & (fidx_o != fidx64)
+    res["face_idx_f32_oracle_vs_f64"] = int((fidx_o != fidx64).sum())
+    res["face_idx_both_f32_differ_from_f64"] = int(only32.sum())
     for k in GRAD_KEYS:
         if k == 'bg' and not no_mask:
             continue
         res["grad_" + k + "_rel_err"] = rel_err(Ac[k].grad, Ao[k].grad)
+        res["gnoise_" + k] = rel_err(Ao[k].grad, A64[k].grad)              # fp32 oracle vs fp64 oracle
+        res["gerr64_" + k] = rel_err(Ac[k].grad, A64[k].grad)              # product vs fp64 oracle
     # fused entry point vs the two-call path
     if fused:
         res["fused_loss_rel_err"] = abs(float(out['loss'][0]) - float(loss_o)) / max(abs(float(loss_o)), 1e-12)
         res["fused_rgba_max_abs_vs_unfused"] = float((out['rgba'] - rgb_c.detach()).abs().max())
+    # the same step with lazy fusion off (recon_data materialises its gradient, the render backward takes it as g_rgba)
+    dr.lazy_fusion = False
+    An = to_device(A_cpu, device, requires_grad=True)
+    rgb_n, Aout_n = dr.render(no_mask=no_mask, **An)
+    loss_n = dr.recon_data(rgb_n, gt_dev, no_mask=no_mask, contour=contour)
+    (loss_n + (Aout_n['face_normals'] * wfn.to(device)).sum()).backward()
+    dr.lazy_fusion = True
+    res["lazy_vs_materialised_rgba"] = float((rgb_n.detach() - rgb_c.detach()).abs().max())
+    res["lazy_vs_materialised_loss"] = abs(float(loss_n) - float(loss_c))
+    res["lazy_vs_materialised_grad"] = max(rel_err(Ac[k].grad, An[k].grad) for k in GRAD_KEYS if not (k == 'bg' and not no_mask))
     return res
 
 
@@ -203,10 +260,12 @@ def reg_inputs(V, F, seed=5, B=3):
 
 
 def reg_values(dr, delta, fn, temp=1.5):
-    """The seven reference calls of trainer.py:54-68 on one attribute set -> (values[7], d/d delta, d/d face_normals)."""
+    """The seven reference calls of trainer.py:54-68 on one attribute set -> (values[7], d/d delta, d/d face_normals).
+    `dr`: the product's DiffRender (CUDA tensors: the fused kernel) or tests/reg_torch.TorchRegularisers (the torch checker)."""
+    vinit = (dr.dr if hasattr(dr, 'dr') else dr).vertices_init
     d = delta.clone().requires_grad_(True)
     n = fn.clone().requires_grad_(True)
-    att = {'delta_vertices': d, 'face_normals': n, 'vertices': dr.vertices_init.to(d.device)[None] + d}
+    att = {'delta_vertices': d, 'face_normals': n, 'vertices': vinit.to(d.device)[None] + d}
     vals = torch.stack([dr.calc_reg_loss(att), dr.calc_reg_edge(att['vertices']), dr.calc_reg_depth(att['vertices']),
                         dr.calc_reg_depthR(att['vertices'], temp=temp), dr.calc_reg_depthC(att['vertices']),
                         dr.calc_reg_deform(att['delta_vertices']), dr.recon_flip(att, False)])

@@ -1,17 +1,21 @@
 """GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every compute call goes through the
 C ABI of libmagicmirror.so via the reference-shaped Python DiffRender; the CPU oracle is the checker.
 
-Tolerances (fp32 path, stated per BASELINE.json north_star):
-  * face_idx: bit-exact against the oracle rasteriser fed the product's own vertex-stage output
-    ("staged"); end-to-end (two different fp32 vertex stages: torch-CPU vs our kernel, ~2e-7 rel apart)
-    at most a handful of silhouette pixels may flip and are counted.
-  * RGBA: staged <= 5e-5 abs (values in [0,1]; bilinear texel coordinates reach 255, 1 ulp there = 1.5e-5);
-    end-to-end the arbiter is the SAME oracle run in fp64: |cuda - f64| <= max(1e-4, 4 x |f32 oracle - f64|) on
-    pixels where all three agree on the winner (sliver faces at the silhouette amplify the 2e-7 difference
-    between two fp32 vertex stages for the reference algorithm itself), mean abs <= 2e-6.
-  * face_normals: same rule, relative to the tensor's max.
-  * loss: 1e-5 rel.  Gradients: max|a-b| / max|b| <= 5e-4 end-to-end (atomics order + the same
-    conditioning); typical figures are 1e-5 (see profiles/ parity summaries).
+PARITY IS UNPINNED for the Kaolin part: the oracle restates Kaolin's DIB-R kernels from the published algorithm (Kaolin is
+not installable offline); docs/DIBR_SPEC.md lists the assumptions, docs/DIBR_SENSITIVITY.md what each alternative would change.
+
+Bars (fp32 path; BASELINE.json north_star: "bit-exact face indices / visibility, RGBA and loss / grad within 1e-4 rel"):
+  * face_idx: BIT-EXACT against the oracle rasteriser fed the product's own vertex-stage output ("staged").  End to end the
+    two pipelines have different fp32 vertex stages (torch-CPU vs our kernel, ~2e-7 rel apart): a pixel may only flip if it
+    sits on a decision boundary of the SAME oracle run in fp64 (an edge through the pixel centre within 2e-4 barycentric
+    units, or a depth tie) -- `face_idx_unexcused` must be 0.
+  * RGBA: staged <= 5e-5 abs (values in [0,1]; bilinear texel coordinates reach 511, 1 ulp there = 3e-5); end to end
+    <= 1e-4 on pixels with the same winner, unless the fp32 ORACLE itself is further than 2.5e-5 from the fp64 oracle there
+    (sliver faces at the silhouette: the reference algorithm's own conditioning) -- then 4 x that noise.
+  * loss: 1e-5 rel.  Gradients: max|a-b| / max|b| <= 1e-4, same noise rule against the fp64 oracle's gradients
+    (`gnoise_*` = fp32 oracle vs fp64 oracle is reported for every tensor).
+  * lazy fusion (recon_data's gradient formed inside the render backward) == the materialised path: image and loss bit-equal,
+    gradients to float-atomics order (2e-5).
 """
 import glob
 import os
@@ -25,27 +29,34 @@ import parity_utils as pu
 pytestmark = pytest.mark.gpu
 
 TOL_STAGED_RGBA = 5e-5
-TOL_E2E_RGBA = 1e-3
+TOL_E2E_RGBA = 1e-4
 TOL_LOSS = 1e-5
-TOL_GRAD = 5e-4
+TOL_GRAD = 1e-4
 DEV = "cuda:0"
 
 
 def _check(res, B, H, W):
     assert res["face_idx_mismatch_staged"] == 0, res
+    assert res["face_idx_unexcused"] == 0, res
     assert res["face_idx_mismatch_e2e"] <= max(2, int(2e-4 * B * H * W)), res
     assert res["soft_staged_max_abs_err"] <= 2e-6, res
     assert res["rgba_staged_max_abs_err"] <= TOL_STAGED_RGBA, res
     assert res["imnormal_staged_max_abs_err"] <= 2e-6, res
-    assert res["rgba_err_vs_f64"] <= max(1e-4, 4.0 * res["rgba_noise_f32_oracle_vs_f64"]), res
-    assert res["rgba_max_abs_err"] <= max(TOL_E2E_RGBA, 4.0 * res["rgba_noise_f32_oracle_vs_f64"]), res
+    noise = res["rgba_noise_f32_oracle_vs_f64"]
+    assert res["rgba_err_vs_f64"] <= max(TOL_E2E_RGBA, 4.0 * noise), res
+    assert res["rgba_max_abs_err"] <= max(TOL_E2E_RGBA, 4.0 * noise), res
     assert res["rgba_mean_abs_err"] <= 2e-6 + 2.0 * res["face_idx_mismatch_e2e"] / (B * H * W), res
     assert res["loss_rel_err"] <= TOL_LOSS and res["fused_loss_rel_err"] <= TOL_LOSS, res
     assert res["fused_rgba_max_abs_vs_unfused"] == 0.0, res
     assert res["face_normals_err_vs_f64"] <= max(1e-4, 4.0 * res["face_normals_noise_f32_oracle_vs_f64"]), res
+    assert res["lazy_vs_materialised_rgba"] == 0.0 and res["lazy_vs_materialised_loss"] == 0.0, res
+    assert res["lazy_vs_materialised_grad"] <= 2e-5, res
     for k, v in res.items():
         if k.startswith("grad_"):
-            assert v <= TOL_GRAD, (k, res)
+            name = k[5:-8]
+            bar = max(TOL_GRAD, 4.0 * res["gnoise_" + name])
+            assert v <= bar, (k, v, bar, res)
+            assert res["gerr64_" + name] <= bar, (k, res)
 
 
 CASES = [
@@ -71,6 +82,36 @@ def test_parity_against_oracle(mm, case):
     _check(res, case["B"], H, case["image_size"])
 
 
+# BASELINE.json configs at their REAL sizes, against the oracle (not fused-vs-unfused): the bench workload itself (cfg-2, B=48,
+# seed 1234), the Market shape (cfg-4: 256x128, smpl_uv_642, ratio 2, train_market.py:126-130 camera ranges) and the high-res
+# shape (cfg-5: 256x256, 512x512 atlas; sphere and the 5120-face sphere2).  The C/OpenMP oracle needs a few seconds per case.
+FULL_SIZE = [
+    dict(mesh="ellipsoid", B=48, image_size=128, no_mask=True, contour=0.1, seed=1234),
+    dict(mesh="smpl_uv_642", B=8, image_size=128, ratio=2, init_ellipsoid=2, no_mask=True, contour=0.1, seed=4321,
+         dist_range=(2.0, 6.0), elev_range=(-15.0, 15.0), bias_range=0.5),
+    dict(mesh="sphere", B=2, image_size=256, no_mask=True, contour=0.1, seed=55, tex=(512, 512)),
+    dict(mesh="sphere2", B=2, image_size=256, no_mask=True, contour=0.1, seed=56, tex=(512, 512)),
+]
+
+
+@pytest.mark.parametrize("case", FULL_SIZE, ids=["cfg2-B48-128", "cfg4-B8-256x128", "cfg5-sphere-256-tex512", "cfg5-sphere2-256-tex512"])
+def test_parity_against_oracle_full_size(mm, case):
+    res = pu.run_parity_case(mm, device=DEV, **case)
+    H = int(round(case.get("ratio", 1) * case["image_size"]))
+    print("parity", case["mesh"], {k: (float("%.3g" % v) if isinstance(v, float) else v) for k, v in res.items()})
+    _check(res, case["B"], H, case["image_size"])
+
+
+def test_seed23_sliver_winner_is_the_reference_algorithms_conditioning(mm):
+    """Round 1 skipped this input ('sliver winner: flat grad tolerance fails').  It is re-admitted under the noise rule: the
+    test prints how far the fp32 ORACLE's own gradients are from the fp64 oracle's on it, and the product must stay within
+    4 x that (or 1e-4, whichever is larger) of BOTH -- i.e. it may be as ill-conditioned as the reference algorithm, not more."""
+    case = dict(mesh="ellipsoid", B=3, image_size=64, no_mask=True, contour=0.1, seed=23)
+    res = pu.run_parity_case(mm, device=DEV, **case)
+    print("seed23", {k: float("%.3g" % v) for k, v in res.items() if k.startswith(("grad_", "gnoise_", "gerr64_"))})
+    _check(res, 3, 64, 64)
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(pu.GOLDEN, "render_*.npz"))),
                          ids=lambda p: os.path.basename(p)[7:-4])
 def test_against_committed_golden(mm, path):
@@ -87,7 +128,7 @@ def test_against_committed_golden(mm, path):
     loss.backward()
     want = torch.from_numpy(z["rgbs"])
     diff = (rgbs.detach().cpu() - want).abs()
-    assert float(diff.mean()) <= 5e-6 and float((diff > TOL_E2E_RGBA).float().mean()) <= 2e-4
+    assert float(diff.mean()) <= 5e-6 and float((diff > 1e-3).float().mean()) <= 2e-4
     assert abs(float(loss) - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))
     assert pu.rel_err(Aout['face_normals'], torch.from_numpy(z["face_normals"])) <= 1e-4
     for k in pu.GRAD_KEYS:
@@ -236,9 +277,31 @@ def test_error_behaviour(mm):
     import ctypes
     L = mm.lib()
     h = dr._ctx(torch.device(DEV))
-    rc = L.mm_render_forward(h.handle, 2, *([ctypes.c_void_p(0)] * 6), 64, 32, ctypes.c_void_p(0), ctypes.c_void_p(0), 0,
-                             *([ctypes.c_void_p(0)] * 4), ctypes.c_void_p(0), ctypes.c_void_p(0))
+    ws = h.workspace(2)
+    nul = ctypes.c_void_p(0)
+    rc = L.mm_render_forward(h.handle, 2, *([nul] * 6), 64, 32, 0, nul, nul, 0, *([nul] * 4), ctypes.c_void_p(ws.data_ptr()),
+                             ws.numel(), nul)
     assert rc == -1 and b"invalid argument" in L.mm_last_error()
+    # an undersized / missing / misaligned workspace is detected, not overrun
+    good = [ctypes.c_void_p(A[k].data_ptr()) for k in ('vertices', 'azimuths', 'elevations', 'distances', 'biases', 'textures')]
+    rgba = torch.empty(2, 4, 32, 32, device=DEV)
+    tail = [64, 32, 0, ctypes.c_void_p(A['lights'].data_ptr()), nul, 0, ctypes.c_void_p(rgba.data_ptr()), nul, nul, nul]
+    rc = L.mm_render_forward(h.handle, 2, *good, *tail, ctypes.c_void_p(ws.data_ptr()), ws.numel() - 1, nul)
+    assert rc == -1 and b"workspace holds" in L.mm_last_error()
+    rc = L.mm_render_forward(h.handle, 2, *good, *tail, nul, ws.numel(), nul)
+    assert rc == -1 and b"workspace is NULL" in L.mm_last_error()
+    rc = L.mm_render_forward(h.handle, 2, *good, *tail, ctypes.c_void_p(ws.data_ptr() + 4), ws.numel(), nul)
+    assert rc == -1 and b"256-byte aligned" in L.mm_last_error()
+    rc = L.mm_render_forward(h.handle, 70000, *good, *tail, ctypes.c_void_p(ws.data_ptr()), ws.numel(), nul)
+    assert rc == -1
+    # render_compare validates like render does (shapes, devices) instead of handing bad pointers to the kernels
+    gt = torch.rand(2, 4, 32, 32, device=DEV)
+    with pytest.raises(ValueError):
+        dr.render_compare(gt[:, :3], no_mask=True, **A)
+    with pytest.raises(mm.MagicMirrorError):
+        dr.render_compare(gt.cpu(), no_mask=True, **A)
+    with pytest.raises(ValueError):
+        dr.render_compare(gt, no_mask=True, g_rgba_extra=torch.zeros(2, 4, 16, 16, device=DEV), **A)
 
 
 def test_soft_backward_fallback_when_pair_list_overflows(mm, monkeypatch):
@@ -248,18 +311,6 @@ def test_soft_backward_fallback_when_pair_list_overflows(mm, monkeypatch):
     case = dict(mesh="sphere", B=2, image_size=64, no_mask=True, contour=0.1, seed=13, dist_range=(3.0, 7.0))
     res = pu.run_parity_case(mm, **case)
     _check(res, case["B"], 64, 64)
-
-
-@pytest.mark.parametrize("case", [
-    dict(mesh="ellipsoid", B=3, image_size=64, no_mask=True, contour=0.1, seed=24),   # (seed 23 has a sliver winner: flat grad tolerance fails in every variant)
-    dict(mesh="sphere", B=2, image_size=22, ratio=1.5, no_mask=True, contour=0.1, seed=19),
-], ids=["aligned", "ragged"])
-def test_split_step_variant(mm, monkeypatch, case):
-    """MM_SPLIT=1 runs the soft pass and the RGB shading in one launch and finishes the silhouette in k_alpha."""
-    monkeypatch.setenv("MM_SPLIT", "1")
-    res = pu.run_parity_case(mm, **case)
-    H = round(case.get("ratio", 1) * case["image_size"])
-    _check(res, case["B"], H, case["image_size"])
 
 
 def test_empty_scene_and_offscreen(mm):
@@ -283,8 +334,8 @@ def test_empty_scene_and_offscreen(mm):
 # ------------------------------------------------------------------ fused mesh regularisers
 @pytest.mark.parametrize("mesh,ratio,ell", [("sphere", 1, 1), ("smpl_uv_642", 2, 2), ("sphere2", 1, 1)])
 def test_mesh_regularisers_fused_kernel_vs_torch_statement(mm, mesh, ratio, ell):
-    """mm_mesh_reg_forward/backward (CUDA tensors) against the torch statement of networks.py:392-491 (CPU tensors; that
-    statement is checked against the unmodified reference in tests/test_host_setup.py).  fp32: values 2e-5 rel, grads 2e-4."""
+    """mm_mesh_reg_forward/backward (the product) against the torch statement of networks.py:392-491 in tests/reg_torch.py
+    (itself checked against the unmodified reference in tests/test_host_setup.py).  fp32: values 2e-5 rel, grads 2e-4."""
     dr = mm.DiffRender(pu.get_mesh(mm, mesh), 64, ratio=ratio, init_ellipsoid=ell)
     g = torch.Generator().manual_seed(5)
     B, V, F = 5, dr.num_vertices, dr.num_faces
@@ -292,13 +343,17 @@ def test_mesh_regularisers_fused_kernel_vs_torch_statement(mm, mesh, ratio, ell)
     delta[0, :7] = 0.0                                   # zero displacements: norm sub-gradient, sign(0)
     fn = torch.nn.functional.normalize(torch.randn(B, F, 3, generator=g), dim=2)
 
+    import reg_torch
+    chk = reg_torch.TorchRegularisers(dr)
+
     def run(dev):
         d = delta.clone().to(dev).requires_grad_(True)
         n = fn.clone().to(dev).requires_grad_(True)
         att = {'delta_vertices': d, 'face_normals': n, 'vertices': dr.vertices_init.to(dev)[None] + d}
-        vals = [dr.calc_reg_loss(att), dr.calc_reg_edge(att['vertices']), dr.calc_reg_depth(att['vertices']),
-                dr.calc_reg_depthR(att['vertices'], temp=1.5), dr.calc_reg_depthC(att['vertices']),
-                dr.calc_reg_deform(att['delta_vertices']), dr.recon_flip(att, False), dr.recon_flip(att, True)]
+        R = chk if dev == "cpu" else dr              # CPU: the torch checker; CUDA: the product's fused kernel
+        vals = [R.calc_reg_loss(att), R.calc_reg_edge(att['vertices']), R.calc_reg_depth(att['vertices']),
+                R.calc_reg_depthR(att['vertices'], temp=1.5), R.calc_reg_depthC(att['vertices']),
+                R.calc_reg_deform(att['delta_vertices']), R.recon_flip(att, False), R.recon_flip(att, True)]
         w = torch.tensor([1.0, 0.7, 1.3, 0.9, 1.1, 0.5, 2.0, 0.3], device=dev)
         (torch.stack(vals) * w).sum().backward()
         return torch.stack(vals).detach().cpu(), d.grad.cpu(), n.grad.cpu()
@@ -407,41 +462,6 @@ def test_mirrored_texture_equals_concatenated_atlas(mm, size, ratio, mesh):
     assert torch.equal(again, res[0][0])
 
 
-@pytest.mark.parametrize("B,parts", [(48, 2), (48, 3), (48, 4), (19, 2), (33, 4), (9, 4)])
-def test_split_batch_fused_step_equals_unsplit(mm, B, parts):
-    """mm_ctx_set_parts: the fused step as `parts` concurrent sub-batches (own streams, own workspace slices) must return what
-    the unsplit call returns: image bit-identical (images are independent), gradients up to float-atomics order, loss scalars
-    up to the re-association of the batch mean.  Uneven splits, upstream gradients (offset per part) and sub-batches too small
-    to split (B=9) included."""
-    dr, A = _cfg2(mm, B=B, seed=31)
-    G = pu.to_device(pu.make_attributes(dr.vertices_init, B, 128, 128, 32), DEV)
-    with torch.no_grad():
-        gt, _ = dr.render(no_mask=True, **G)
-    gen = torch.Generator(device=DEV).manual_seed(5)
-    g_extra = 1e-4 * torch.randn(B, 4, 128, 128, device=DEV, generator=gen)
-    g_fn = 1e-3 * torch.randn(B, dr.num_faces, 3, device=DEV, generator=gen)
-    h = dr._ctx(torch.device(DEV))
-    L = mm.lib()
-    keep = L.mm_ctx_get_parts(h.handle)
-    outs = []
-    try:
-        for n in (1, parts):
-            assert L.mm_ctx_set_parts(h.handle, n) == 0
-            outs.append(dr.render_compare(gt, no_mask=True, contour=0.1, loss_scale=1.7, g_rgba_extra=g_extra,
-                                          g_face_normals=g_fn, **A))
-            torch.cuda.synchronize()
-    finally:
-        L.mm_ctx_set_parts(h.handle, keep)
-    o1, on = outs
-    assert torch.equal(o1['rgba'], on['rgba'])
-    assert torch.equal(o1['face_normals'], on['face_normals'])
-    assert pu.rel_err(on['loss'], o1['loss']) <= 2e-6
-    for k in ('g_vertices', 'g_azimuths', 'g_elevations', 'g_distances', 'g_biases', 'g_textures', 'g_lights', 'g_bg'):
-        assert pu.rel_err(on[k], o1[k]) <= 2e-5, k
-    assert L.mm_ctx_set_parts(h.handle, 9) != 0            # out of range
-    L.mm_ctx_set_parts(h.handle, keep)
-
-
 @pytest.mark.parametrize("mesh,shape", [("sphere", (3, 16, 8, 4)), ("smpl_uv_642", (2, 8, 4, 4)), ("icosphere", (2, 5, 7, 9)),
                                          ("sphere", (48, 288, 8, 4))])
 def test_template_features_vs_reference_torch_ops(mm, mesh, shape):
@@ -519,3 +539,44 @@ def test_render_many_equals_separate_renders(mm):
         assert outs[i][1]['face_normals'].shape == (b, dr.num_faces, 3) and outs[i][1]['imnormal'].shape == (b, 128, 128, 3)
         for k in keys:
             assert pu.rel_err(g_m[i][k], g_s[i][k]) <= TOL_GRAD, (i, k)
+
+
+@pytest.mark.parametrize("shape,concat", [((4, 3, 128, 128, 128, 128), True), ((2, 3, 40, 24, 33, 17), False),
+                                          ((48, 3, 128, 128, 128, 128), True)])
+def test_texture_flow_vs_reference_torch_ops(mm, shape, concat):
+    """SURVEY 8(f)-3, texture side: DiffRender.texture_flow == the reference's own lines, network/model_res.py:598-599,609-610
+    (bicubic F.grid_sample with align_corners=True at the predicted flow, then cat([t, t.flip([2])], 2)), forward and the
+    gradients w.r.t. the image and the flow.  A flow reaching outside [-1,1] exercises the zero padding of the 4x4 taps."""
+    import torch.nn.functional as F
+    B, C, Hi, Wi, Ho, Wo = shape
+    dr = mm.DiffRender(mm.icosphere(1), 32)
+    gen = torch.Generator().manual_seed(B * 7 + Ho)
+    img = torch.rand(B, C, Hi, Wi, generator=gen).to(DEV).requires_grad_(True)
+    flow = (torch.rand(B, 2, Ho, Wo, generator=gen) * 2.3 - 1.15).to(DEV).requires_grad_(True)
+    w = torch.randn(B, C, Ho * (2 if concat else 1), Wo, generator=gen).to(DEV)
+    out = dr.texture_flow(img, flow, concat=concat)
+    (out * w).sum().backward()
+    gi, gf = img.grad.clone(), flow.grad.clone()
+    # the reference's lines, verbatim in form
+    img2, flow2 = img.detach().clone().requires_grad_(True), flow.detach().clone().requires_grad_(True)
+    uv_sampler = flow2.permute(0, 2, 3, 1)
+    textures = F.grid_sample(img2, uv_sampler, mode='bicubic', align_corners=True)
+    if concat:
+        textures_flip = textures.flip([2])
+        textures = torch.cat([textures, textures_flip], dim=2)
+    (textures * w).sum().backward()
+    assert out.shape == textures.shape
+    assert pu.rel_err(out, textures) <= 2e-6
+    assert pu.rel_err(gi, img2.grad) <= 2e-5          # float atomics order
+    assert pu.rel_err(gf, flow2.grad) <= 2e-5
+    # the un-concatenated half feeds render(_tex_mirror=True): same image as rendering the concatenated atlas
+    if concat and Ho == 128:
+        dr2 = mm.DiffRender(pu.get_mesh(mm, "ellipsoid"), 128, image_weight=1.0)
+        A = pu.to_device(pu.make_attributes(dr2.vertices_init, B, 128, 128, 5), DEV)
+        with torch.no_grad():
+            half = dr2.texture_flow(img, flow, concat=False)
+            full, _ = dr2.render(no_mask=True, **{**A, 'textures': out.detach()})
+            mirr, _ = dr2.render(no_mask=True, _tex_mirror=True, **{**A, 'textures': half})
+        assert torch.equal(full, mirr)
+    with pytest.raises(mm.MagicMirrorError):
+        dr.texture_flow(img.detach().cpu(), flow.detach().cpu())

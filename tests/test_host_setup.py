@@ -76,7 +76,7 @@ def test_abi_library_exports_every_declared_symbol(mm):
     from magic_mirror_b200 import _lib
     assert set(_lib.SIGNATURES) == declared
     h.mm_abi_version.restype = ctypes.c_int
-    assert h.mm_abi_version() == 1
+    assert h.mm_abi_version() == 2
 
 
 def test_cpu_tensors_fail_loudly(mm):
@@ -88,6 +88,13 @@ def test_cpu_tensors_fail_loudly(mm):
         dr.recon_data(torch.rand(1, 4, 32, 32), torch.rand(1, 4, 32, 32))
     with pytest.raises(KeyError):
         dr.render(no_mask=False, azimuths=A['azimuths'])
+    # the mesh regularisers have no torch / CPU branch either
+    with pytest.raises(mm.MagicMirrorError):
+        dr.calc_reg_edge(A['vertices'])
+    with pytest.raises(mm.MagicMirrorError):
+        dr.recon_flip({'delta_vertices': A['delta_vertices']}, False)
+    src = open(os.path.join(ROOT, "3d-magic-mirror_b200", "diffrender.py")).read()
+    assert ".is_cuda:" not in src.replace("if not t.is_cuda:", "")       # no device-dispatch branches in the product
 
 
 def test_product_never_imports_oracle():
@@ -108,6 +115,8 @@ def test_regularisers_match_reference_when_available(mm):
     path = os.path.join(ref_import.REFERENCE_ROOT, "template", "sphere.obj")
     ref = net.DiffRender(path, 64, ratio=2, init_ellipsoid=2)
     dr = mm.DiffRender(path, 64, ratio=2, init_ellipsoid=2)
+    import reg_torch
+    chk = reg_torch.TorchRegularisers(dr)
     g = torch.Generator().manual_seed(5)
     B, V, F = 3, dr.num_vertices, dr.num_faces
     att = {'delta_vertices': 0.05 * torch.randn(B, V, 3, generator=g),
@@ -117,7 +126,7 @@ def test_regularisers_match_reference_when_available(mm):
                        ("calc_reg_depth", (att['vertices'],)), ("calc_reg_depthR", (att['vertices'],)),
                        ("calc_reg_depthC", (att['vertices'],)), ("calc_reg_deform", (att['delta_vertices'],)),
                        ("recon_flip", (att, False))):
-        a, b = getattr(dr, name)(*args), getattr(ref, name)(*args)
+        a, b = getattr(chk, name)(*args), getattr(ref, name)(*args)
         assert torch.allclose(a, b, rtol=1e-6, atol=1e-8), name
     p = pu.make_attributes(dr.vertices_init, 2, 128, 64, 1)
     q = pu.make_attributes(dr.vertices_init, 2, 128, 64, 2)
@@ -129,11 +138,13 @@ def test_regularisers_match_reference_when_available(mm):
 @pytest.mark.parametrize("mesh", ["sphere", "smpl_uv_642"])
 def test_regulariser_statement_reproduces_reference_golden(mm, mesh):
     """tests/golden/reg_<mesh>.npz holds values + gradients computed by the UNMODIFIED reference's regularisers
-    (make_golden.py, networks.py:392-491).  The host-side torch statement must reproduce them on CPU."""
+    (make_golden.py, networks.py:392-491).  The torch checker (tests/reg_torch.py) must reproduce them on CPU; the GPU
+    tests then hold the fused kernel against the checker and against the same fixtures."""
+    import reg_torch
     z = np.load(os.path.join(pu.GOLDEN, "reg_%s.npz" % mesh))
     dr = mm.DiffRender(pu.get_mesh(mm, mesh), 64, ratio=int(z["ratio"]), init_ellipsoid=int(z["init_ellipsoid"]))
     delta, fn = pu.reg_inputs(dr.num_vertices, dr.num_faces)
-    vals, gd, gn = pu.reg_values(dr, delta, fn)
+    vals, gd, gn = pu.reg_values(reg_torch.TorchRegularisers(dr), delta, fn)
     assert np.allclose(vals.numpy(), z["values"], rtol=1e-6, atol=1e-9)
     assert np.allclose(gd.numpy(), z["grad_delta"], rtol=1e-5, atol=1e-9)
     assert np.allclose(gn.numpy(), z["grad_face_normals"], rtol=1e-5, atol=1e-9)
