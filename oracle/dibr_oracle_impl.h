@@ -22,9 +22,40 @@
 #error "define REAL and FN() before including"
 #endif
 
-/* pixel centre in multiplier-scaled NDC (DIBR_SPEC A.1) */
-static inline REAL FN(px_x)(int ix, int W, REAL mult) { return (mult / (REAL)W) * (REAL)(2 * ix + 1 - W); }
-static inline REAL FN(px_y)(int iy, int H, REAL mult) { return (mult / (REAL)H) * (REAL)(H - 2 * iy - 1); }
+/* pixel centre in multiplier-scaled NDC (DIBR_SPEC A.1).  MMO_V_PIXEL_ORDER: the other plausible expression order. */
+static inline REAL FN(px_x)(int ix, int W, REAL mult) {
+    if (g_mmo_variant & MMO_V_PIXEL_ORDER) return ((REAL)(2 * ix + 1 - W) / (REAL)W) * mult;
+    return (mult / (REAL)W) * (REAL)(2 * ix + 1 - W);
+}
+static inline REAL FN(px_y)(int iy, int H, REAL mult) {
+    if (g_mmo_variant & MMO_V_PIXEL_ORDER) return ((REAL)(H - 2 * iy - 1) / (REAL)H) * mult;
+    return (mult / (REAL)H) * (REAL)(H - 2 * iy - 1);
+}
+
+/* barycentric weights of (x0,y0) in triangle a,b,c.  Default: DIB-R's k1/k2/k3 form with k/(k3+eps) (DIBR_SPEC A.2).
+ * MMO_V_EDGE_BARY: the edge-function form (w0, w1 from the sub-triangle areas opposite a and b, w2 = 1-w0-w1), which a newer
+ * Kaolin may use; MMO_V_EPS_ZERO: no eps in the denominator. */
+static inline void FN(bary)(REAL ax, REAL ay, REAL bx, REAL by, REAL cx, REAL cy, REAL x0, REAL y0, REAL eps,
+                            REAL* w0, REAL* w1, REAL* w2)
+{
+    if (g_mmo_variant & MMO_V_EPS_ZERO) eps = 0;
+    if (g_mmo_variant & MMO_V_EDGE_BARY) {
+        const REAL det = (by - cy) * (ax - cx) + (cx - bx) * (ay - cy);
+        *w0 = ((by - cy) * (x0 - cx) + (cx - bx) * (y0 - cy)) / (det + eps);
+        *w1 = ((cy - ay) * (x0 - cx) + (ax - cx) * (y0 - cy)) / (det + eps);
+        *w2 = (REAL)1 - *w0 - *w1;
+        return;
+    }
+    const REAL m = bx - ax, p = by - ay;
+    const REAL n = cx - ax, q = cy - ay;
+    const REAL s = x0 - ax, t = y0 - ay;
+    const REAL k1 = s * q - n * t;
+    const REAL k2 = m * t - s * p;
+    const REAL k3 = m * q - n * p;
+    *w1 = k1 / (k3 + eps);
+    *w2 = k2 / (k3 + eps);
+    *w0 = (REAL)1 - *w1 - *w2;
+}
 
 /* ------------------------------------------------------------------------
  * Hard rasterisation forward  (Kaolin packed_rasterize_forward_cuda_kernel)
@@ -60,19 +91,16 @@ void FN(mmo_rasterize_forward)(int B, int H, int W, int F, int D,
                     const REAL cx = p_b[f * 6 + 4] * multiplier, cy = p_b[f * 6 + 5] * multiplier;
                     const REAL xmin = fmin(fmin(ax, bx), cx), xmax = fmax(fmax(ax, bx), cx);
                     const REAL ymin = fmin(fmin(ay, by), cy), ymax = fmax(fmax(ay, by), cy);
-                    if (x0 < xmin || x0 >= xmax || y0 < ymin || y0 >= ymax) continue;
-                    const REAL m = bx - ax, p = by - ay;
-                    const REAL n = cx - ax, q = cy - ay;
-                    const REAL s = x0 - ax, t = y0 - ay;
-                    const REAL k1 = s * q - n * t;
-                    const REAL k2 = m * t - s * p;
-                    const REAL k3 = m * q - n * p;
-                    const REAL w1 = k1 / (k3 + eps);
-                    const REAL w2 = k2 / (k3 + eps);
-                    const REAL w0 = (REAL)1 - w1 - w2;
-                    if (w0 < 0 || w1 < 0 || w2 < 0) continue;
+                    if (g_mmo_variant & MMO_V_BBOX_CLOSED) {         /* closed instead of half-open bbox test */
+                        if (x0 < xmin || x0 > xmax || y0 < ymin || y0 > ymax) continue;
+                    } else if (x0 < xmin || x0 >= xmax || y0 < ymin || y0 >= ymax) continue;
+                    REAL w0, w1, w2;
+                    FN(bary)(ax, ay, bx, by, cx, cy, x0, y0, eps, &w0, &w1, &w2);
+                    if (g_mmo_variant & MMO_V_INSIDE_STRICT) { if (w0 <= 0 || w1 <= 0 || w2 <= 0) continue; }
+                    else if (w0 < 0 || w1 < 0 || w2 < 0) continue;
                     const REAL zz = w0 * z_b[f * 3 + 0] + w1 * z_b[f * 3 + 1] + w2 * z_b[f * 3 + 2];
-                    if (zz <= best_z) continue;      /* strict >: first face wins exact ties */
+                    if (g_mmo_variant & MMO_V_DEPTH_GE) { if (zz < best_z) continue; }     /* >=: LAST face wins exact ties */
+                    else if (zz <= best_z) continue;     /* strict >: first face wins exact ties */
                     best_z = zz; best_f = f; bw0 = w0; bw1 = w1; bw2 = w2;
                 }
                 const size_t pix = ((size_t)b * H + iy) * W + ix;
@@ -208,7 +236,9 @@ void FN(mmo_soft_mask_forward)(int B, int H, int W, int F, int knum,
                     const REAL xmax = fmax(fmax(X[0], X[1]), X[2]) + blen;
                     const REAL ymin = fmin(fmin(Y[0], Y[1]), Y[2]) - blen;
                     const REAL ymax = fmax(fmax(Y[0], Y[1]), Y[2]) + blen;
-                    if (x0 < xmin || x0 >= xmax || y0 < ymin || y0 >= ymax) continue;
+                    if (g_mmo_variant & MMO_V_SOFT_BBOX_CLOSED) {
+                        if (x0 < xmin || x0 > xmax || y0 < ymin || y0 > ymax) continue;
+                    } else if (x0 < xmin || x0 >= xmax || y0 < ymin || y0 >= ymax) continue;
                     REAL pdis[6];
                     for (int i = 0; i < 3; ++i) {
                         const REAL x1 = X[i], y1 = Y[i];

@@ -53,6 +53,20 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+# ---- variant switches (ORACLE ONLY; tools/dibr_sensitivity.py): bits of mmo_set_variant in dibr_oracle.c, plus the one
+# assumption that lives at the Python level of Kaolin (valid faces: normal_z >= 0 vs > 0)
+VARIANTS = {"bbox_closed": 1, "soft_bbox_closed": 2, "depth_ge": 4, "pixel_order": 8, "edge_bary": 16, "eps_zero": 32,
+            "inside_strict": 64}
+NZ_STRICT = False
+
+
+def set_variant(name=None):
+    """name: None (the spec), a key of VARIANTS, or 'nz_strict'."""
+    global NZ_STRICT
+    NZ_STRICT = (name == "nz_strict")
+    lib().mmo_set_variant(VARIANTS.get(name, 0) if name else 0)
+
+
 def _real(dtype):
     if dtype == torch.float32:
         return "f32", ctypes.c_float
@@ -262,7 +276,7 @@ def dibr_rasterization(height, width, face_vertices_z, face_vertices_image, face
         feats = torch.cat(list(face_features), dim=-1)
     else:
         feats = face_features
-    valid_faces = face_normals_z >= 0
+    valid_faces = (face_normals_z > 0) if NZ_STRICT else (face_normals_z >= 0)
     interp, face_idx = rasterize(height, width, face_vertices_z, face_vertices_image, feats,
                                  valid_faces, multiplier, eps)
     if is_list:

@@ -35,7 +35,12 @@ TOL_GRAD = 1e-4
 DEV = "cuda:0"
 
 
+def _fmt(res):
+    return {k: (float("%.3g" % v) if isinstance(v, float) else v) for k, v in res.items()}
+
+
 def _check(res, B, H, W):
+    print("PARITY", B, H, W, _fmt(res))
     assert res["face_idx_mismatch_staged"] == 0, res
     assert res["face_idx_unexcused"] == 0, res
     assert res["face_idx_mismatch_e2e"] <= max(2, int(2e-4 * B * H * W)), res
