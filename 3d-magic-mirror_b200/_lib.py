@@ -30,6 +30,7 @@ SIGNATURES = {
                               c_float, c_float, c_float, c_float, c_int, c_float, c_float]),
     "mm_ctx_destroy": (c_int, [_P]),
     "mm_workspace_bytes": (c_size_t, [_P, c_int]),
+    "mm_ctx_get_int": (c_int, [_P, ctypes.c_char_p]),
     "mm_render_forward": (c_int, [_P, c_int] + _RENDER_IN + [_P] * 4 + [_P, c_size_t, _P]),
     "mm_render_backward": (c_int, [_P, c_int] + _RENDER_IN + [_P] * 3 + [_P, c_float, c_float, c_float, _P] + [_P] * 8 +
                            [_P, c_size_t, _P]),

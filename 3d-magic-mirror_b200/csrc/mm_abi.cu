@@ -126,6 +126,25 @@ cudaError_t launch_vertex_fwd(const mm_ctx* c, int B, const mm_ws_layout& L, cha
                                 ws + L.zbuf, bytes0, nullptr, 0, s);
 }
 
+// forward geometry of a batch: face records + visibility buffer + soft-silhouette accumulators + candidate lists.  ONE kernel
+// over shared-memory row bands when the ctx's configuration fits (mm_band.cu), else vertex stage -> hard pass -> soft pass ->
+// overflow pass.  p.clr / p.nclr (fused step) name a buffer that is cleared on the side.
+int launch_geometry_forward(const mm_ctx* c, int B, const mm_ws_layout& L, char* ws, const mm_raster_params& p,
+                            const float* vertices, const float* azim, const float* elev, const float* dist, const float* bias,
+                            float* face_normals, cudaStream_t s) {
+    if (c->band_on) {
+        MM_CUDA(cudaMemsetAsync(ws + L.ovf_count, 0, 16, s));          // the two list counters (global atomics)
+        if (c->timing) cudaEventRecord(c->ev[1], s);
+        MM_LAUNCH(mm_launch_band_fwd(c, p, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg),
+                                     face_normals, (float*)(ws + L.gfacc), s), "raster_band");
+        return MM_OK;
+    }
+    MM_LAUNCH(launch_vertex_fwd(c, B, L, ws, vertices, azim, elev, dist, bias, face_normals, s), "vertex_fwd");
+    if (c->timing) cudaEventRecord(c->ev[1], s);
+    MM_LAUNCH(mm_launch_geom_fwd(c, p, s), "geom_fwd");
+    return MM_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -190,6 +209,18 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
         delete c;
         return fail(MM_E_CUDA, "cudaFuncSetAttribute(vertex kernels) failed: %s", cudaGetErrorString(e));
     }
+    {   // forward geometry in shared-memory row bands when the configuration fits (default), else the four-kernel chain
+        int want = 1;
+        if (const char* e = getenv("MM_BAND")) want = atoi(e) != 0;
+        c->band_on = 0;
+        if (want && mm_band_config(c, smem_max, &c->band_shift, &c->band_rows, &c->band_smem)) {
+            if (cudaError_t e = mm_band_set_smem(device, c->band_smem)) {
+                delete c;
+                return fail(MM_E_CUDA, "cudaFuncSetAttribute(band kernel) failed: %s", cudaGetErrorString(e));
+            }
+            c->band_on = 1;
+        }
+    }
 
     std::vector<int32_t> tab(3 * (size_t)H + 3 * (size_t)W);
     contour_tables(H, tab.data(), tab.data() + H, tab.data() + 2 * H);
@@ -225,6 +256,17 @@ int mm_ctx_destroy(mm_ctx* c) {
     return MM_OK;
 }
 
+int mm_ctx_get_int(const mm_ctx* c, const char* key) {
+    if (!c || !key) return -1;
+    const int geom = c->band_on ? 1 : 4;                    // band kernel | vertex + hard + soft + overflow
+    if (!strcmp(key, "band")) return c->band_on;
+    if (!strcmp(key, "band_count")) return c->band_on ? (1 << c->band_shift) : 0;
+    if (!strcmp(key, "band_rows")) return c->band_on ? c->band_rows : 0;
+    if (!strcmp(key, "fused_kernels")) return geom + 3;     // + shading, soft backward, vertex backward
+    if (!strcmp(key, "api_kernels")) return geom + 1 + 1 + 3;   // + shade fwd | recon | shade bwd, soft bwd, vertex bwd
+    return -1;
+}
+
 size_t mm_workspace_bytes(const mm_ctx* c, int B) {
     if (!c || B <= 0) return 0;
     return mm_ws_make(c, B).total;
@@ -244,13 +286,12 @@ int mm_render_forward(mm_ctx* c, int B, const float* vertices, const float* azim
     cudaStream_t s = (cudaStream_t)stream;
     const mm_ws_layout L = mm_ws_make(c, B);
     char* ws = (char*)workspace;
-    MM_LAUNCH(launch_vertex_fwd(c, B, L, ws, vertices, azim, elev, dist, bias, face_normals, s), "vertex_fwd");
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, tex_mirror, no_mask, p);
     set_ws(c, L, ws, p);
     p.tex = tex; p.lights = lights; p.bg = bg;
     p.rgba = rgba; p.imnormal = imnormal; p.face_idx_out = face_idx;
-    MM_LAUNCH(mm_launch_geom_fwd(c, p, s), "geom_fwd");
+    if (int r = launch_geometry_forward(c, B, L, ws, p, vertices, azim, elev, dist, bias, face_normals, s)) return r;
     MM_LAUNCH(mm_launch_shade(c, p, 1, s), "shade_fwd");
     return MM_OK;
 }
@@ -381,8 +422,6 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     const size_t gtex_bytes = (size_t)B * 3 * (tex_mirror ? Ht / 2 : Ht) * Wt * 4;
     const bool gtex_side = (((uintptr_t)g_tex & 15) == 0) && ((gtex_bytes & 15) == 0);     // cleared by the hard pass on the side
     if (!gtex_side) MM_CUDA(cudaMemsetAsync(g_tex, 0, gtex_bytes, s));
-    MM_LAUNCH(launch_vertex_fwd(c, B, L, ws, vertices, azim, elev, dist, bias, face_normals, s), "vertex_fwd");
-    if (c->timing) cudaEventRecord(c->ev[1], s);
     mm_raster_params p;
     fill_params(c, B, Ht, Wt, tex_mirror, no_mask, p);
     set_ws(c, L, ws, p);
@@ -396,7 +435,7 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     // shading kernel and the geometry backward adds the IoU term from the per-image sums on the fly
     p.gsoft_iou_pending = ((c->H & 3) == 0 && (c->W & 3) == 0) ? 1 : 0;
     if (gtex_side) { p.clr = (uint4*)g_tex; p.nclr = gtex_bytes / 16; }
-    MM_LAUNCH(mm_launch_geom_fwd(c, p, s), "geom_fwd");
+    if (int r = launch_geometry_forward(c, B, L, ws, p, vertices, azim, elev, dist, bias, face_normals, s)) return r;
     p.clr = nullptr; p.nclr = 0;
     if (c->timing) cudaEventRecord(c->ev[2], s);
     MM_LAUNCH(mm_launch_shade(c, p, 0, s), "shade_fused");       // shading forward + loss sums + the whole RGB-side backward

@@ -57,6 +57,9 @@ struct mm_ctx {
     size_t smem_vertex_fwd;  // dynamic smem bytes of the vertex forward kernel
     int num_sms;
     int pdl;                 // 1 = dependent kernels are launched with programmatic stream serialization (default; MM_PDL=0 disables)
+    // forward geometry as ONE kernel over row bands held in shared memory (mm_band.cu; MM_BAND=0 selects the four-kernel chain)
+    int band_on, band_shift, band_rows;
+    size_t band_smem;
     unsigned plist_cap_max;  // test hook (MM_PLIST_CAP): caps the forward's pair list so that the backward's fallback path runs
     // device arrays
     int32_t* d_faces;        // [F,3]
@@ -203,3 +206,8 @@ cudaError_t mm_launch_texflow_fwd(const mm_ctx* c, int B, int C, int Hi, int Wi,
                                   const float* flow, float* out, cudaStream_t s);
 cudaError_t mm_launch_texflow_bwd(const mm_ctx* c, int B, int C, int Hi, int Wi, int Ho, int Wo, int concat, const float* img,
                                   const float* flow, const float* g_out, float* g_img, float* g_flow, cudaStream_t s);
+bool mm_band_config(const mm_ctx* c, size_t smem_optin, int* nb_shift, int* R, size_t* smem);
+cudaError_t mm_band_set_smem(int device, size_t bytes);
+cudaError_t mm_launch_band_fwd(const mm_ctx* c, const mm_raster_params& p, const float* vertices, const float* azim,
+                               const float* elev, const float* dist, const float* bias, float* frec, float* vimg,
+                               float* face_normals, float* gfacc_zero, cudaStream_t s);

@@ -125,6 +125,7 @@ class _Record(object):
 
     def __init__(self, h, B):
         self.h, self.B = h, B
+        self.captured = torch.cuda.is_current_stream_capturing()     # graph-pool memory: never recycled through our pool
         self.ws, self.key = h.acquire(B)
         self.pending = None          # (gt, image_weight, contour, g_loss) set by _ReconLazyFn.backward
         self.recon_used = False      # the workspace holds the IoU sums of ONE recon_data call
@@ -134,7 +135,8 @@ class _Record(object):
 
     def __del__(self):
         try:
-            self.h.release(self.ws, self.key)
+            if not self.captured:
+                self.h.release(self.ws, self.key)
         except Exception:
             pass
 

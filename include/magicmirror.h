@@ -35,6 +35,8 @@
  *
  * Environment switches read at mm_ctx_create (diagnostics; defaults are the measured best):
  *   MM_PDL=0        no programmatic dependent launch between the library's kernels
+ *   MM_BAND=0       forward geometry as the four-kernel chain (vertex -> hard -> soft -> overflow) instead of the one-kernel
+ *                   shared-memory band rasteriser (the chain is also the fallback for sizes whose band does not fit)
  *   MM_VCHUNKS=n    CTAs per image of the vertex forward kernel (default 8)
  *   MM_PLIST_CAP=n  test hook: caps the forward's candidate list so the backward's fallback path runs
  */
@@ -70,6 +72,12 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F,
                   int H, int W, float proj_x, float proj_y,
                   float sigmainv, float boxlen, int knum, float multiplier, float eps);
 int mm_ctx_destroy(mm_ctx* ctx);
+
+/* Introspection (tests, bench): "band" (1: the forward geometry runs as one kernel over shared-memory row bands, 0: the
+ * four-kernel chain), "band_count" (bands per image), "band_rows", "fused_kernels" (kernel launches of one
+ * mm_render_compare_fwd_bwd for H, W multiples of 4), "api_kernels" (render_forward + recon_data_forward + render_backward).
+ * Returns -1 for an unknown key. */
+int mm_ctx_get_int(const mm_ctx* ctx, const char* key);
 
 /* Bytes of caller-owned scratch needed by any call on `ctx` with batch B. */
 size_t mm_workspace_bytes(const mm_ctx* ctx, int B);

@@ -141,6 +141,16 @@ def run_parity_case(mm, mesh="icosphere", B=2, image_size=32, ratio=1, no_mask=T
     # ---------------- oracle (CPU): GT image = render of an independent sample
     with torch.no_grad():
         gt_cpu, _, _, _ = orc.render(no_mask=no_mask, **gt_src)
+        # The masked-L1 term has a KINK at pred == gt: d|x|/dx = sign(x).  Where |pred - gt| is below the fp32 noise of pred
+        # (up to ~3e-3 at sliver / grazing faces) two equally valid fp32 renderings take opposite signs, and at a pixel whose
+        # colour is very sensitive to the geometry (a grazing face less than a pixel high: measured 1.7e4 per unit of colour)
+        # that ONE sign moves the camera gradients by tens of per cent (found on sphere2 @ 256^2, seed 56: gt_R - pred_R =
+        # 3.8e-4 with the fp32 oracle, -6.4e-5 with the product).  A gradient comparison is only meaningful away from the
+        # kink, so the synthetic GT is moved to at least 5e-3 from the (fp32 oracle's) prediction; the count is reported.
+        pred0 = orc.render(no_mask=no_mask, **A_cpu)[0]
+        d = gt_cpu[:, :3] - pred0[:, :3]
+        near = d.abs() < 5e-3
+        gt_cpu[:, :3] = torch.where(near, (pred0[:, :3] + torch.where(d >= 0, 5e-3, -5e-3)).clamp(0, 1), gt_cpu[:, :3])
     Ao = to_device(A_cpu, "cpu", requires_grad=True)
     rgb_o, fn_o, imn_o, fidx_o = orc.render(no_mask=no_mask, **Ao)
     loss_o, parts_o = orc.recon_data(rgb_o, gt_cpu, no_mask=no_mask, contour=contour, return_parts=True)
@@ -157,7 +167,7 @@ def run_parity_case(mm, mesh="icosphere", B=2, image_size=32, ratio=1, no_mask=T
     (loss_c + (Aout['face_normals'] * wfn.to(device)).sum()).backward()
     torch.cuda.synchronize()
 
-    res = {}
+    res = {"l1_kink_pixels_moved": int(near.sum())}
     fidx_c = Aout['face_idx'].cpu().long()
     res["face_idx_mismatch_e2e"] = int((fidx_c != fidx_o).sum())
     res["covered_frac"] = float((fidx_o >= 0).float().mean())
@@ -215,6 +225,11 @@ def run_parity_case(mm, mesh="icosphere", B=2, image_size=32, ratio=1, no_mask=T
     agree = ((fidx_c == fidx_o) & (fidx_o == fidx64))[:, None].expand(-1, 4, -1, -1)
     res["rgba_noise_f32_oracle_vs_f64"] = float((rgb_o.detach().double() - rgb64).abs()[agree].max())
     res["rgba_err_vs_f64"] = float((rgb_c.detach().cpu().double() - rgb64).abs()[agree].max())
+    # distribution-level figure: which fraction of the (agreeing) pixels is further than 1e-4 from the fp64 oracle -- for the
+    # product and for the fp32 oracle itself (random U[0,1] texels on a 256..512-row atlas amplify a 1e-7 error of u,v to 1e-4)
+    npx = max(int(agree.sum()), 1)
+    res["rgba_frac_gt_1e-4_cuda_vs_f64"] = float(((rgb_c.detach().cpu().double() - rgb64).abs()[agree] > 1e-4).sum()) / npx
+    res["rgba_frac_gt_1e-4_f32_oracle_vs_f64"] = float(((rgb_o.detach().double() - rgb64).abs()[agree] > 1e-4).sum()) / npx
     res["face_normals_noise_f32_oracle_vs_f64"] = rel_err(fn_o, fn64)
     res["face_normals_err_vs_f64"] = rel_err(Aout['face_normals'], fn64)
     res["loss_noise_f32_oracle_vs_f64"] = abs(float(loss_o) - float(loss64)) / max(abs(float(loss64)), 1e-12)

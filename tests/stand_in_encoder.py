@@ -76,7 +76,7 @@ def make_images(B, H, W, seed):
     return torch.cat([rgb, disc.float().unsqueeze(1)], dim=1)
 
 
-def trainer_step_loss(dr, enc, images, contour=0.1, lambda_reg=0.1, render=None, recon=None):
+def trainer_step_loss(dr, enc, images, contour=0.1, lambda_reg=0.1, render=None, recon=None, regs=None):
     """The data + regularisation part of one trainer.py iteration (trainer.py:271-276, 441, 54-72, 505-509):
     encode -> render -> recon_data + mesh regularisers.  `render` / `recon` default to the DiffRender under test; the CPU
     oracle arm passes its own (same signature)."""
@@ -87,6 +87,7 @@ def trainer_step_loss(dr, enc, images, contour=0.1, lambda_reg=0.1, render=None,
     else:
         Xer, Ae = render(Ae)
     loss_data = (recon or (lambda p, g: dr.recon_data(p, g, no_mask=True, contour=contour)))(Xer, images)
-    reg = dr.calc_reg_loss(Ae) + 0.1 * dr.calc_reg_deform(Ae['delta_vertices']) + 0.01 * dr.calc_reg_depth(Ae['vertices']) \
-        + 0.1 * dr.calc_reg_edge(Ae['vertices'])
+    R = regs if regs is not None else dr          # the CPU oracle arm passes tests/reg_torch.TorchRegularisers (the product has no CPU path)
+    reg = R.calc_reg_loss(Ae) + 0.1 * R.calc_reg_deform(Ae['delta_vertices']) + 0.01 * R.calc_reg_depth(Ae['vertices']) \
+        + 0.1 * R.calc_reg_edge(Ae['vertices'])
     return loss_data + lambda_reg * reg, Xer

@@ -40,8 +40,10 @@ def test_trainer_step_gradients_match_oracle_pipeline(mm):
         Ae['face_normals'] = fn
         return rgb, Ae
 
+    import reg_torch
     loss_c, Xc = se.trainer_step_loss(dr, enc_c, images, render=render_cpu,
-                                      recon=lambda p, g: orc.recon_data(p, g, no_mask=True, contour=0.1))
+                                      recon=lambda p, g: orc.recon_data(p, g, no_mask=True, contour=0.1),
+                                      regs=reg_torch.TorchRegularisers(dr))
     loss_c.backward()
     assert abs(float(loss_g) - float(loss_c)) <= 1e-4 * abs(float(loss_c))
     assert float((Xg.detach().cpu() - Xc.detach()).abs().mean()) <= 1e-5
