@@ -8,6 +8,8 @@ from .diffrender import DiffRender                                            # 
 from .camera import camera_position_from_spherical_angles, generate_transformation_matrix   # noqa: F401
 from .mesh import TemplateMesh, load_obj, save_obj, icosphere                # noqa: F401
 from ._lib import MagicMirrorError, LIB_PATH, lib                            # noqa: F401
+from .template_em import template_update, sharded_template_update          # noqa: F401
 
 __all__ = ["DiffRender", "camera_position_from_spherical_angles", "generate_transformation_matrix",
-           "TemplateMesh", "load_obj", "save_obj", "icosphere", "MagicMirrorError", "LIB_PATH", "lib"]
+           "TemplateMesh", "load_obj", "save_obj", "icosphere", "MagicMirrorError", "LIB_PATH", "lib",
+           "template_update", "sharded_template_update"]

@@ -210,7 +210,9 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
         return fail(MM_E_CUDA, "cudaFuncSetAttribute(vertex kernels) failed: %s", cudaGetErrorString(e));
     }
     {   // forward geometry in shared-memory row bands when the configuration fits (default), else the four-kernel chain
-        int want = 1;
+        // measured at cfg-2 (profiles/r2_notes.md): 76 us vs 57 us for the chain -- every band re-does the vertex stage and the
+        // face selection, and the near-camera images' bands set the kernel time; off unless asked for
+        int want = 0;
         if (const char* e = getenv("MM_BAND")) want = atoi(e) != 0;
         c->band_on = 0;
         if (want && mm_band_config(c, smem_max, &c->band_shift, &c->band_rows, &c->band_smem)) {
@@ -219,6 +221,10 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
                 return fail(MM_E_CUDA, "cudaFuncSetAttribute(band kernel) failed: %s", cudaGetErrorString(e));
             }
             c->band_on = 1;
+            if (const char* e = getenv("MM_BAND_PROF")) {
+                if (atoi(e) != 0 && cudaMalloc(&c->band_prof, 8192 * 8 * sizeof(long long)) != cudaSuccess) c->band_prof = nullptr;
+                if (c->band_prof) cudaMemset(c->band_prof, 0, 8192 * 8 * sizeof(long long));
+            }
         }
     }
 
@@ -248,6 +254,7 @@ int mm_ctx_destroy(mm_ctx* c) {
     cudaFree(c->d_edges); cudaFree(c->d_edge2faces); cudaFree(c->d_flip); cudaFree(c->d_sign_init);
     cudaFree(c->d_lap_off); cudaFree(c->d_lap_col); cudaFree(c->d_lap_val);
     cudaFree(c->d_lapT_off); cudaFree(c->d_lapT_row); cudaFree(c->d_lapT_val);
+    cudaFree(c->band_prof);
     cudaFree(c->d_faces);
     cudaFree(c->d_face_uvs);
     cudaFree(c->d_tab);
@@ -591,6 +598,13 @@ int mm_texture_flow_backward(mm_ctx* c, int B, int C, int Hi, int Wi, int Ho, in
     MM_CUDA(cudaMemsetAsync(g_img, 0, (size_t)B * C * Hi * Wi * 4, (cudaStream_t)stream));
     MM_LAUNCH(mm_launch_texflow_bwd(c, B, C, Hi, Wi, Ho, Wo, concat, img, flow, g_out, g_img, g_flow, (cudaStream_t)stream),
               "texture_flow_bwd");
+    return MM_OK;
+}
+
+int mm_debug_band_profile(mm_ctx* c, long long* host_out, int ncta) {
+    MM_REQUIRE(c && host_out && ncta > 0 && ncta <= 8192, "ctx / host_out / ncta (1..8192)");
+    MM_REQUIRE(c->band_prof, "band profiling is off (MM_BAND_PROF=1 at ctx creation, band kernel in use)");
+    MM_CUDA(cudaMemcpy(host_out, c->band_prof, (size_t)ncta * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     return MM_OK;
 }
 

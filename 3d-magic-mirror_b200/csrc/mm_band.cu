@@ -44,6 +44,7 @@ struct BandParams {
     float* frec_out; float* vimg; float* face_normals; float* gfacc_zero;
     int nb_shift;            // log2(bands per image)
     int R;                   // local rows per band (multiple of 4, <= 252)
+    long long* prof;         // MM_BAND_PROF=1: [CTA][8] clock64 stamps at the phase boundaries (diagnostics), else NULL
 };
 
 struct WarpStage {
@@ -109,6 +110,9 @@ k_raster_band(const BandParams q)
     uint16_t* s_list = reinterpret_cast<uint16_t*>(s_ws + BD_WARPS);   // F
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
     const uint32_t lt = (1u << lane) - 1u;
+    long long* prof = q.prof ? q.prof + ((size_t)b * gridDim.x + band) * 8 : nullptr;
+#define BD_STAMP(i) do { if (prof && tid == 0) prof[i] = clock64(); } while (0)
+    BD_STAMP(0);
 
     // ---------------------------------------------------------------- P0: clears, camera, vertex transform
     for (int i = tid; i < npix; i += BD_THREADS) { s_z[i] = 0ull; s_l[i] = 0ull; }
@@ -140,6 +144,7 @@ k_raster_band(const BandParams q)
         }
     }
     __syncthreads();
+    BD_STAMP(1);
 
     // ---------------------------------------------------------------- PA: faces relevant to this band; this band's share of the records
     for (int f0 = 0; f0 < F; f0 += BD_THREADS) {
@@ -182,6 +187,7 @@ k_raster_band(const BandParams q)
     __syncthreads();
     const int nL = s_cnt[0];
     WarpStage& ws = s_ws[warp];
+    BD_STAMP(2);
 
     // ---------------------------------------------------------------- P1: hard visibility (front faces), row segments
     for (int base = warp * 32; base < nL; base += BD_THREADS) {
@@ -248,6 +254,7 @@ k_raster_band(const BandParams q)
         __syncwarp();
     }
     __syncthreads();
+    BD_STAMP(3);
 
     // ---------------------------------------------------------------- coverage bitmap of the band
     for (int wi = warp; wi < R * covw; wi += BD_WARPS) {
@@ -350,6 +357,7 @@ k_raster_band(const BandParams q)
         __syncwarp();
     }
     __syncthreads();
+    BD_STAMP(4);
 
     // ---------------------------------------------------------------- P3: truncated pixels, exact ordered re-scan (rare)
     for (int wi = 0; wi < R * covw; ++wi) {
@@ -421,6 +429,7 @@ k_raster_band(const BandParams q)
         }
     }
 
+    BD_STAMP(5);
     // ---------------------------------------------------------------- P4: the band's rows of zbuf / lacc -> global
     {
         unsigned long long* zb = p.zbuf + (size_t)b * HW;
@@ -444,6 +453,7 @@ k_raster_band(const BandParams q)
             }
         }
     }
+    if (prof && tid == 0) { prof[6] = clock64(); prof[7] = nL; }
 }
 
 size_t band_smem(const mm_ctx* c, int R) {
@@ -497,5 +507,6 @@ cudaError_t mm_launch_band_fwd(const mm_ctx* c, const mm_raster_params& p, const
     q.proj_x = c->proj_x; q.proj_y = c->proj_y;
     q.frec_out = frec; q.vimg = vimg; q.face_normals = face_normals; q.gfacc_zero = gfacc_zero;
     q.nb_shift = c->band_shift; q.R = c->band_rows;
+    q.prof = (c->band_prof && (size_t)p.B * (1u << c->band_shift) <= 8192) ? c->band_prof : nullptr;
     return mm_launch(k_raster_band, dim3(1 << c->band_shift, p.B), dim3(BD_THREADS), c->band_smem, s, false, q);
 }

@@ -60,6 +60,7 @@ struct mm_ctx {
     // forward geometry as ONE kernel over row bands held in shared memory (mm_band.cu; MM_BAND=0 selects the four-kernel chain)
     int band_on, band_shift, band_rows;
     size_t band_smem;
+    long long* band_prof;    // MM_BAND_PROF=1: [8192][8] per-CTA phase stamps of the last band launch (mm_debug_band_profile)
     unsigned plist_cap_max;  // test hook (MM_PLIST_CAP): caps the forward's pair list so that the backward's fallback path runs
     // device arrays
     int32_t* d_faces;        // [F,3]

@@ -150,7 +150,9 @@ def run_parity_case(mm, mesh="icosphere", B=2, image_size=32, ratio=1, no_mask=T
         pred0 = orc.render(no_mask=no_mask, **A_cpu)[0]
         d = gt_cpu[:, :3] - pred0[:, :3]
         near = d.abs() < 5e-3
-        gt_cpu[:, :3] = torch.where(near, (pred0[:, :3] + torch.where(d >= 0, 5e-3, -5e-3)).clamp(0, 1), gt_cpu[:, :3])
+        tgt = pred0[:, :3] + torch.where(d >= 0, 5e-3, -5e-3)
+        tgt = torch.where((tgt < 0) | (tgt > 1), 2 * pred0[:, :3] - tgt, tgt)          # stay inside [0,1]: step the other way
+        gt_cpu[:, :3] = torch.where(near, tgt, gt_cpu[:, :3])
     Ao = to_device(A_cpu, "cpu", requires_grad=True)
     rgb_o, fn_o, imn_o, fidx_o = orc.render(no_mask=no_mask, **Ao)
     loss_o, parts_o = orc.recon_data(rgb_o, gt_cpu, no_mask=no_mask, contour=contour, return_parts=True)

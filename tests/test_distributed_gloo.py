@@ -51,3 +51,62 @@ def test_algorithmic_bytes_match_survey_table():
     assert abs(fwd / 48 / 1e6 - 1.137) < 2e-3
     assert abs(bwd / 48 / 1e6 - 1.719) < 2e-3
     assert abs(step / 1e6 - 137.2) < 0.2
+
+
+def _em_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import __graft_entry__ as g
+    import parity_utils as pu
+    mm = g.load_package()
+    dr = mm.DiffRender(pu.get_mesh(mm, "sphere"), 64)
+    deltas = _em_deltas(dr.num_vertices)
+    mine = deltas[rank::world]                                  # this rank's shard of the training set
+    new, ok, cross = mm.sharded_template_update(dr.vertices_init[None], mine.sum(0), mine.shape[0],
+                                                dr.vertices_laplacian_matrix, em_step=0.7, warm_up=0.5, smooth=0.3, clip=0.05)
+    gathered = [torch.zeros_like(new) for _ in range(world)]
+    dist.all_gather(gathered, new.contiguous())
+    if rank == 0:
+        torch.save({"new": new, "ok": ok, "cross": cross, "equal_across_ranks": all(torch.equal(gathered[0], t) for t in gathered)}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _em_deltas(V, n=37):
+    g = torch.Generator().manual_seed(11)
+    return 0.03 * torch.randn(n, V, 3, generator=g) + 0.01 * torch.randn(1, V, 3, generator=g)
+
+
+def test_template_update_sharded_equals_single_process(tmp_path):
+    """SURVEY 8(e)-3 / trainer.py:994-1105: the per-epoch template update over a sharded training set (uneven shards: 19 + 18
+    samples) must give every rank the template a single process computes from the whole set."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import __graft_entry__ as g
+    import parity_utils as pu
+    mm = g.load_package()
+    dr = mm.DiffRender(pu.get_mesh(mm, "sphere"), 64)
+    deltas = _em_deltas(dr.num_vertices)
+    want, ok, cross = mm.template_update(dr.vertices_init[None], deltas.sum(0), deltas.shape[0], dr.vertices_laplacian_matrix,
+                                         em_step=0.7, warm_up=0.5, smooth=0.3, clip=0.05)
+    assert ok and want.shape == (1, dr.num_vertices, 3) and not torch.equal(want[0], dr.vertices_init)
+    # the reference's own lines (trainer.py:1073-1084), verbatim in form
+    last = deltas.sum(0) * 1.0 / deltas.shape[0]
+    last += torch.matmul(dr.vertices_laplacian_matrix, last) * 0.3
+    last[last > 0.05] = 0.05
+    last[last < -0.05] = -0.05
+    assert torch.allclose(want[0], dr.vertices_init + 0.5 * 0.7 * last, atol=1e-7)
+    out = str(tmp_path / "em.pt")
+    port = 29500 + ((os.getpid() + 977) % 2000)
+    mp.spawn(_em_worker, args=(2, port, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["ok"] and r["equal_across_ranks"]
+    assert torch.allclose(r["new"], want, atol=1e-6)            # the sum is re-associated across shards
+    # a step that would push a vertex through the depth-sign plane is rolled back (trainer.py:1092-1096)
+    big = torch.zeros(dr.num_vertices, 3)
+    big[:, 2] = -torch.sign(dr.vertices_init[:, 2]) * 10.0
+    same, ok2, cross2 = mm.template_update(dr.vertices_init[None], big * 4, 4, dr.vertices_laplacian_matrix, clip=5.0)
+    assert not ok2 and cross2 > 0 and torch.equal(same[0], dr.vertices_init)
