@@ -48,7 +48,6 @@ SIGNATURES = {
     "mm_template_features_backward": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "mm_texture_flow_forward": (c_int, [_P] + [c_int] * 7 + [_P, _P, _P, _P]),
     "mm_texture_flow_backward": (c_int, [_P] + [c_int] * 7 + [_P, _P, _P, _P, _P, _P]),
-    "mm_debug_band_profile": (c_int, [_P, _P, c_int]),
     "mm_ctx_set_timing": (c_int, [_P, c_int]),
     "mm_ctx_get_timing": (c_int, [_P, _P, c_int]),
 }

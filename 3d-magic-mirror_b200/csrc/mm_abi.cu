@@ -126,19 +126,11 @@ cudaError_t launch_vertex_fwd(const mm_ctx* c, int B, const mm_ws_layout& L, cha
                                 ws + L.zbuf, bytes0, nullptr, 0, s);
 }
 
-// forward geometry of a batch: face records + visibility buffer + soft-silhouette accumulators + candidate lists.  ONE kernel
-// over shared-memory row bands when the ctx's configuration fits (mm_band.cu), else vertex stage -> hard pass -> soft pass ->
-// overflow pass.  p.clr / p.nclr (fused step) name a buffer that is cleared on the side.
+// forward geometry of a batch: face records + visibility buffer + soft-silhouette accumulators + candidate lists (vertex stage ->
+// hard pass -> soft pass -> overflow pass).  p.clr / p.nclr (fused step) name a buffer that is cleared on the side.
 int launch_geometry_forward(const mm_ctx* c, int B, const mm_ws_layout& L, char* ws, const mm_raster_params& p,
                             const float* vertices, const float* azim, const float* elev, const float* dist, const float* bias,
                             float* face_normals, cudaStream_t s) {
-    if (c->band_on) {
-        MM_CUDA(cudaMemsetAsync(ws + L.ovf_count, 0, 16, s));          // the two list counters (global atomics)
-        if (c->timing) cudaEventRecord(c->ev[1], s);
-        MM_LAUNCH(mm_launch_band_fwd(c, p, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg),
-                                     face_normals, (float*)(ws + L.gfacc), s), "raster_band");
-        return MM_OK;
-    }
     MM_LAUNCH(launch_vertex_fwd(c, B, L, ws, vertices, azim, elev, dist, bias, face_normals, s), "vertex_fwd");
     if (c->timing) cudaEventRecord(c->ev[1], s);
     MM_LAUNCH(mm_launch_geom_fwd(c, p, s), "geom_fwd");
@@ -209,25 +201,6 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
         delete c;
         return fail(MM_E_CUDA, "cudaFuncSetAttribute(vertex kernels) failed: %s", cudaGetErrorString(e));
     }
-    {   // forward geometry in shared-memory row bands when the configuration fits (default), else the four-kernel chain
-        // measured at cfg-2 (profiles/r2_notes.md): 76 us vs 57 us for the chain -- every band re-does the vertex stage and the
-        // face selection, and the near-camera images' bands set the kernel time; off unless asked for
-        int want = 0;
-        if (const char* e = getenv("MM_BAND")) want = atoi(e) != 0;
-        c->band_on = 0;
-        if (want && mm_band_config(c, smem_max, &c->band_shift, &c->band_rows, &c->band_smem)) {
-            if (cudaError_t e = mm_band_set_smem(device, c->band_smem)) {
-                delete c;
-                return fail(MM_E_CUDA, "cudaFuncSetAttribute(band kernel) failed: %s", cudaGetErrorString(e));
-            }
-            c->band_on = 1;
-            if (const char* e = getenv("MM_BAND_PROF")) {
-                if (atoi(e) != 0 && cudaMalloc(&c->band_prof, 8192 * 8 * sizeof(long long)) != cudaSuccess) c->band_prof = nullptr;
-                if (c->band_prof) cudaMemset(c->band_prof, 0, 8192 * 8 * sizeof(long long));
-            }
-        }
-    }
-
     std::vector<int32_t> tab(3 * (size_t)H + 3 * (size_t)W);
     contour_tables(H, tab.data(), tab.data() + H, tab.data() + 2 * H);
     contour_tables(W, tab.data() + 3 * H, tab.data() + 3 * H + W, tab.data() + 3 * H + 2 * W);
@@ -254,7 +227,6 @@ int mm_ctx_destroy(mm_ctx* c) {
     cudaFree(c->d_edges); cudaFree(c->d_edge2faces); cudaFree(c->d_flip); cudaFree(c->d_sign_init);
     cudaFree(c->d_lap_off); cudaFree(c->d_lap_col); cudaFree(c->d_lap_val);
     cudaFree(c->d_lapT_off); cudaFree(c->d_lapT_row); cudaFree(c->d_lapT_val);
-    cudaFree(c->band_prof);
     cudaFree(c->d_faces);
     cudaFree(c->d_face_uvs);
     cudaFree(c->d_tab);
@@ -265,10 +237,7 @@ int mm_ctx_destroy(mm_ctx* c) {
 
 int mm_ctx_get_int(const mm_ctx* c, const char* key) {
     if (!c || !key) return -1;
-    const int geom = c->band_on ? 1 : 4;                    // band kernel | vertex + hard + soft + overflow
-    if (!strcmp(key, "band")) return c->band_on;
-    if (!strcmp(key, "band_count")) return c->band_on ? (1 << c->band_shift) : 0;
-    if (!strcmp(key, "band_rows")) return c->band_on ? c->band_rows : 0;
+    const int geom = 4;                                     // vertex + hard + soft + overflow
     if (!strcmp(key, "fused_kernels")) return geom + 3;     // + shading, soft backward, vertex backward
     if (!strcmp(key, "api_kernels")) return geom + 1 + 1 + 3;   // + shade fwd | recon | shade bwd, soft bwd, vertex bwd
     return -1;
@@ -598,13 +567,6 @@ int mm_texture_flow_backward(mm_ctx* c, int B, int C, int Hi, int Wi, int Ho, in
     MM_CUDA(cudaMemsetAsync(g_img, 0, (size_t)B * C * Hi * Wi * 4, (cudaStream_t)stream));
     MM_LAUNCH(mm_launch_texflow_bwd(c, B, C, Hi, Wi, Ho, Wo, concat, img, flow, g_out, g_img, g_flow, (cudaStream_t)stream),
               "texture_flow_bwd");
-    return MM_OK;
-}
-
-int mm_debug_band_profile(mm_ctx* c, long long* host_out, int ncta) {
-    MM_REQUIRE(c && host_out && ncta > 0 && ncta <= 8192, "ctx / host_out / ncta (1..8192)");
-    MM_REQUIRE(c->band_prof, "band profiling is off (MM_BAND_PROF=1 at ctx creation, band kernel in use)");
-    MM_CUDA(cudaMemcpy(host_out, c->band_prof, (size_t)ncta * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     return MM_OK;
 }
 

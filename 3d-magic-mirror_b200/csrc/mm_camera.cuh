@@ -1,6 +1,6 @@
 // mm_camera.cuh -- camera_position_from_spherical_angles (smr_utils.py:257-281) + generate_transformation_matrix
-// (smr_utils.py:284-311) + the vertex transform of kaolin prepare_vertices, shared by the vertex kernels (mm_vertex.cu) and the
-// per-band rasteriser (mm_band.cu): ONE statement of the arithmetic, so the face records are bit-identical whoever builds them.
+// (smr_utils.py:284-311) + the vertex transform of kaolin prepare_vertices: ONE statement of the arithmetic for every kernel
+// that needs it (mm_vertex.cu forward and backward), so the face records are bit-identical whoever builds them.
 #pragma once
 #include "mm_common.cuh"
 

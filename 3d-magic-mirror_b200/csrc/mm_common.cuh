@@ -121,6 +121,7 @@ struct mm_raster_params {
     uint32_t* ovf_count;     // [4]: {overflow pixels, candidate pairs recorded, -, -}
     unsigned long long* plist;    // [plist_cap]
     uint32_t plist_cap;
+
     float* gsoft;            // [B,H,W]
     int gsoft_iou_pending;   // 1: `gsoft` holds upstream + contour terms only; consumers add the IoU term (per-image sums) on the fly
     const float* face_uvs;   // [F,6]
@@ -207,8 +208,3 @@ cudaError_t mm_launch_texflow_fwd(const mm_ctx* c, int B, int C, int Hi, int Wi,
                                   const float* flow, float* out, cudaStream_t s);
 cudaError_t mm_launch_texflow_bwd(const mm_ctx* c, int B, int C, int Hi, int Wi, int Ho, int Wo, int concat, const float* img,
                                   const float* flow, const float* g_out, float* g_img, float* g_flow, cudaStream_t s);
-bool mm_band_config(const mm_ctx* c, size_t smem_optin, int* nb_shift, int* R, size_t* smem);
-cudaError_t mm_band_set_smem(int device, size_t bytes);
-cudaError_t mm_launch_band_fwd(const mm_ctx* c, const mm_raster_params& p, const float* vertices, const float* azim,
-                               const float* elev, const float* dist, const float* bias, float* frec, float* vimg,
-                               float* face_normals, float* gfacc_zero, cudaStream_t s);

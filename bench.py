@@ -526,7 +526,6 @@ def main():
             print(json.dumps({"profile_only": True, "value": value, "ms_per_step": ms / K}), flush=True)
         return
     fused_kernels = L.mm_ctx_get_int(fused.h.handle, b"fused_kernels")
-    band = L.mm_ctx_get_int(fused.h.handle, b"band")
 
     # ---- value_api: the reference's three calls (render -> recon_data -> backward) with device-resident inputs, eager and as
     # replayed CUDA graphs (same kernels either way; the eager figure is bounded by Python / autograd host time)
@@ -607,8 +606,7 @@ def main():
             "config": {"workload": "cfg-2 (BASELINE.json configs[1]): B=%d/GPU, ellipsoid V=%d F=%d, %dx%d, tex %dx%d, "
                                    "no_mask, contour 0.1, fused render+recon_data fwd+bwd" % (B_PER_GPU, V, F, H, W, Ht, Wt),
                        "l2": "inputs larger than L2: %d rotating input/output sets (%d x %.0f MB)" % (NSETS, NSETS, bytes_step / 1e6),
-                       "parallelism": "dp%d (images sharded, no data-path collective)" % world,
-                       "forward_geometry": "one kernel over shared-memory row bands" if band else "vertex -> hard -> soft -> overflow"},
+                       "parallelism": "dp%d (images sharded, no data-path collective)" % world},
             "clocks": clocks,
             "value_api": api.get("graph", {}).get("value"),
             "api": {"what": "DiffRender.render -> recon_data -> backward() (trainer.py:276,441,509), inputs resident in HBM, "

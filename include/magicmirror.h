@@ -35,8 +35,6 @@
  *
  * Environment switches read at mm_ctx_create (diagnostics; defaults are the measured best):
  *   MM_PDL=0        no programmatic dependent launch between the library's kernels
- *   MM_BAND=1       forward geometry as ONE kernel over shared-memory row bands (mm_band.cu) instead of the four-kernel chain
- *                   vertex -> hard -> soft -> overflow (the chain is the default and the fallback for sizes whose band does not fit)
  *   MM_VCHUNKS=n    CTAs per image of the vertex forward kernel (default 8)
  *   MM_PLIST_CAP=n  test hook: caps the forward's candidate list so the backward's fallback path runs
  */
@@ -73,10 +71,8 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F,
                   float sigmainv, float boxlen, int knum, float multiplier, float eps);
 int mm_ctx_destroy(mm_ctx* ctx);
 
-/* Introspection (tests, bench): "band" (1: the forward geometry runs as one kernel over shared-memory row bands, 0: the
- * four-kernel chain), "band_count" (bands per image), "band_rows", "fused_kernels" (kernel launches of one
- * mm_render_compare_fwd_bwd for H, W multiples of 4), "api_kernels" (render_forward + recon_data_forward + render_backward).
- * Returns -1 for an unknown key. */
+/* Introspection (tests, bench): "fused_kernels" (kernel launches of one mm_render_compare_fwd_bwd for H, W multiples of 4),
+ * "api_kernels" (render_forward + recon_data_forward + render_backward).  Returns -1 for an unknown key. */
 int mm_ctx_get_int(const mm_ctx* ctx, const char* key);
 
 /* Bytes of caller-owned scratch needed by any call on `ctx` with batch B. */
@@ -218,11 +214,6 @@ int mm_texture_flow_backward(mm_ctx* ctx, int B, int C, int Hi, int Wi, int Ho, 
  *   fvi [B,F,3,2] image-plane xy (unscaled), fvz [B,F,3] camera z, fnz [B,F] unit-normal z */
 int mm_debug_export_faces(mm_ctx* ctx, int B, const void* workspace, size_t workspace_bytes,
                           float* fvi, float* fvz, float* fnz, void* stream);
-
-/* Diagnostics: with MM_BAND_PROF=1 in the environment at mm_ctx_create, the band rasteriser stamps clock64 at its phase
- * boundaries; this copies [ncta][8] = {start, after vertex stage, after face selection, after hard pass, after soft pass,
- * after overflow pass, end, relevant faces} of the last launch (CTA = image * bands + band) to the host (synchronises). */
-int mm_debug_band_profile(mm_ctx* ctx, long long* host_out, int ncta);
 
 /* Measurement hook (bench.py): when enabled, mm_render_compare_fwd_bwd records a CUDA event on
  * `stream` around each of its launch groups.  mm_ctx_get_timing waits for the last call's final event
