@@ -187,9 +187,10 @@ class E2ERunner(object):
     staging, the same overlap the reference gets from its DataLoader + `.cuda(non_blocking=True)`, trainer.py:247);
     every byte is still copied inside the timed region, every step."""
 
-    def __init__(self, mm, dr, sets_cpu, device):
+    def __init__(self, mm, dr, sets_cpu, device, tex_mirror=False):
         import torch
         self.torch, self.dr, self.dev = torch, dr, device
+        self.tex_mirror = tex_mirror          # labelled variant (SURVEY 8f-3): the un-concatenated half of the atlas crosses PCIe
         keys = ['vertices', 'azimuths', 'elevations', 'distances', 'biases', 'textures', 'lights', 'bg']
         self.keys = keys
         # one pinned block per batch (what a DataLoader's collate + pin_memory hands over) and one device staging block per
@@ -200,6 +201,8 @@ class E2ERunner(object):
             with torch.no_grad():
                 gt, _ = dr.render(no_mask=True, **{k: v.to(device) for k, v in G.items()})
             src = {k: A[k].contiguous().float() for k in keys}
+            if tex_mirror:
+                src['textures'] = src['textures'][:, :, :src['textures'].shape[2] // 2].contiguous()
             src['gt'] = gt.cpu().contiguous()
             if shapes is None:
                 shapes, off = {}, 0
@@ -244,6 +247,8 @@ class E2ERunner(object):
         cur.wait_event(self.ready[slot])
         st = self.stage[slot]
         A = {k: st[k].detach().requires_grad_(True) for k in self.keys}
+        if self.tex_mirror:
+            A['_tex_mirror'] = True
         rgbs, _ = self.dr.render(no_mask=True, **A)
         loss = self.dr.recon_data(rgbs, st['gt'], no_mask=True, contour=0.1)
         loss.backward()
@@ -452,11 +457,17 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4-ddp"],
+                    help="cfg2 (default): the headline render-compare step; cfg3 / cfg4-ddp: a full trainer step (tools/trainer_bench.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="timed region only (for ncu): no e2e / cpu_baseline / per-kernel pass")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "cfg2":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import trainer_bench
+        return trainer_bench.run(args, sys.modules[__name__])
 
     import torch
     import torch.distributed as dist
@@ -554,6 +565,16 @@ def main():
     ms_e, units_e = aggregate(ms_e_local, B_PER_GPU * Ke, world)
     h2d_rank = e2e_runner.h2d_bytes * Ke / (ms_e_local * 1e-3) / 1e9          # this rank's achieved host->device rate
     pcie_alone = pcie_ceiling(torch, device, e2e_runner.h2d_bytes) if rank == 0 else 0.0
+    # labelled variant, NOT the headline: the texture handed over as the un-concatenated half (render(_tex_mirror=True))
+    ev = E2ERunner(mm, dr, sets, device, tex_mirror=True)
+    for i in range(3):
+        ev.step(i)
+    torch.cuda.synchronize()
+    ev.primed = False
+    ms_v, units_v = aggregate(timed(torch, world, ev.step, Ke), B_PER_GPU * Ke, world)
+    e2e_mirror = {"value": units_v / (ms_v * 1e-3), "h2d_bytes_per_step": ev.h2d_bytes,
+                  "what": "same three calls, atlas crosses PCIe as the un-concatenated half (bit-identical image); not the headline"}
+    del ev
     h2d_all = None
     if world > 1:
         t = torch.tensor([h2d_rank], dtype=torch.float64, device=device)
@@ -618,6 +639,7 @@ def main():
                     "h2d_gbs_per_rank": h2d_all if h2d_all else [h2d_rank],
                     "h2d_gbs_aggregate": sum(h2d_all) if h2d_all else h2d_rank,
                     "pcie_h2d_ceiling_gbs": pcie_alone,
+                    "variant_mirrored_atlas": e2e_mirror,
                     "pcie_note": "ceiling = the same pinned block copied alone on rank 0's link; e2e is bound by it "
                                  "(compute per step is %.3f ms, the copy %.3f ms)" % (ms / K, e2e_runner.h2d_bytes / max(pcie_alone, 1e-9) / 1e6),
                     "api": "DiffRender.render -> recon_data -> backward; one pinned host block per batch copied every step on a copy stream (double-buffered)"},

@@ -7,7 +7,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_rank(rank, world, port, B_per_rank, size, seed, out_path, mesh_name):
+def run_rank(rank, world, port, B_per_rank, size, seed, out_path, mesh_name, sized=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -27,7 +27,13 @@ def run_rank(rank, world, port, B_per_rank, size, seed, out_path, mesh_name):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     dr = mm.DiffRender(pu.get_mesh(mm, mesh_name), size, image_weight=1.0)
-    enc = se.make_encoder(dr.vertices_init, dr.height, dr.image_size, seed).to(dev)
+    if sized:          # the reference's parameter volume (33.8 M, tools/sized_encoder.py), BatchNorm frozen so that shards == whole batch
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sized_encoder
+        torch.manual_seed(seed)
+        enc = sized_encoder.SizedEncoder(dr, dr.height, dr.image_size, amp=False).to(dev).eval()
+    else:
+        enc = se.make_encoder(dr.vertices_init, dr.height, dr.image_size, seed).to(dev)
     ddp = DDP(enc, device_ids=[dev.index])
     images = se.make_images(B_per_rank * world, dr.height, dr.image_size, seed + 1)
     shard = images[rank * B_per_rank:(rank + 1) * B_per_rank].to(dev)       # rank r takes images [r*B, (r+1)*B)

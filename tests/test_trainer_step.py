@@ -100,3 +100,33 @@ def test_ddp_two_ranks_equal_single_process(mm, tmp_path):
     assert abs(got["loss_mean"] - float(loss)) <= 2e-6 * abs(float(loss)), (got["loss_mean"], float(loss))
     for n, p in enc.named_parameters():
         assert pu.rel_err(got["grads"][n], p.grad) <= 5e-4, (n, got["backend"])
+
+
+def test_ddp_two_ranks_real_parameter_volume(mm, tmp_path):
+    """The same equality with the gradient volume north_star talks about: the 33.8 M-parameter encoder of tools/sized_encoder.py
+    (the reference's AttributeEncoder has 33.7 M: a 135 MB fp32 all-reduce per step), fp32 convolutions, BatchNorm frozen (per-rank
+    batch statistics would make shards differ from the whole batch by design).  NCCL with one GPU per rank, else gloo."""
+    import sys
+    import torch.multiprocessing as mp
+    import ddp_worker
+    _no_tf32()
+    world, Bp, size, seed, mesh = 2, 2, 64, 60, "sphere"
+    out = str(tmp_path / "ddp_sized.pt")
+    mp.spawn(ddp_worker.run_rank, args=(world, _free_port(), Bp, size, seed, out, mesh, True), nprocs=world, join=True)
+    got = torch.load(out)
+    sys.path.insert(0, os.path.join(pu.ROOT, "tools"))
+    import sized_encoder
+    dr = mm.DiffRender(pu.get_mesh(mm, mesh), size, image_weight=1.0)
+    torch.manual_seed(seed)
+    enc = sized_encoder.SizedEncoder(dr, size, size, amp=False).to(DEV).eval()
+    nparam = sum(p.numel() for p in enc.parameters())
+    assert 33.0e6 < nparam < 34.5e6
+    images = se.make_images(Bp * world, size, size, seed + 1).to(DEV)
+    loss, _ = se.trainer_step_loss(dr, enc, images)
+    loss.backward()
+    assert abs(got["loss_mean"] - float(loss)) <= 1e-5 * abs(float(loss)), (got["loss_mean"], float(loss))
+    worst = 0.0
+    for n, p in enc.named_parameters():
+        assert n in got["grads"] and p.grad is not None, n
+        worst = max(worst, pu.rel_err(got["grads"][n], p.grad))
+    assert worst <= 2e-3, worst            # fp32 convolutions summed in a different order over a different batch split
