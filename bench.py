@@ -302,20 +302,25 @@ class ApiRunner(object):
         return self.last
 
 
-def pcie_ceiling(torch, device, nbytes, reps=20):
-    """Pinned host -> device copy of one e2e-sized block, alone on the link: the ceiling the e2e line is compared with."""
+def pcie_ceiling(torch, device, nbytes, reps=30, trials=3):
+    """Pinned host -> device copy of one e2e-sized block, alone on the link (best of `trials`): the ceiling the e2e line is
+    compared with."""
     src = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+    src.fill_(1.0)                                   # touch every page
     dst = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
-    for _ in range(3):
-        dst.copy_(src, non_blocking=True)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        dst.copy_(src, non_blocking=True)
-    e1.record()
-    torch.cuda.synchronize()
-    return nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    best = 0.0
+    for _ in range(trials):
+        for _ in range(5):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
 
 
 def timed(torch, world, fn, steps):
@@ -533,6 +538,11 @@ def main():
         kms = {k: acc[j] / nprof for j, k in enumerate(KERNELS)}
 
     if args.profile:
+        if os.environ.get("MM_PROFILE_API"):            # ncu: also a few eager steps of the three-call API path
+            r = ApiRunner(mm, dr, fused, graph=False)
+            for i in range(4):
+                r.step(i)
+            torch.cuda.synchronize()
         if rank == 0:
             print(json.dumps({"profile_only": True, "value": value, "ms_per_step": ms / K}), flush=True)
         return
