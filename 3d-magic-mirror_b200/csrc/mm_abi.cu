@@ -95,9 +95,10 @@ void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int tex_mirror, int no_
     memset(&p, 0, sizeof(p));
     p.B = B; p.V = c->V; p.F = c->F; p.H = c->H; p.W = c->W; p.Ht = Ht; p.Wt = Wt;
     p.Htp = tex_mirror ? Ht / 2 : Ht;
-    p.nstx = c->nstx; p.nsty = c->nsty; p.nst = c->nst; p.knum = c->knum;
+    p.knum = c->knum;
     p.sx = c->sx; p.sy = c->sy; p.blen = c->blen; p.multiplier = c->multiplier; p.eps = c->eps; p.sigmainv = c->sigmainv;
     p.no_mask = no_mask;
+    p.pdl_late = c->pdl_late;
     p.covw = (c->W + 31) / 32;
     p.face_uvs = c->d_face_uvs;
     p.tab = c->d_tab;
@@ -177,9 +178,6 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     c->sx = multiplier / (float)W;
     c->sy = multiplier / (float)H;
     c->blen = boxlen * multiplier;
-    c->nstx = (W + MM_ST_W - 1) / MM_ST_W;
-    c->nsty = (H + MM_ST_H - 1) / MM_ST_H;
-    c->nst = c->nstx * c->nsty;
     c->nparts_recon = (H * W + 2047) / 2048 < 1 ? 1 : (H * W + 2047) / 2048;     // ~2048 pixels per recon CTA
     c->num_sms = prop.multiProcessorCount;
     if (F > 65535) { delete c; return fail(MM_E_UNSUPPORTED, "F=%d exceeds the 16-bit face ids of the soft-pass lists", F); }
@@ -188,6 +186,10 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     c->nchunks = 8;
     c->pdl = 1;
     if (const char* e = getenv("MM_PDL")) c->pdl = atoi(e) != 0;
+    // measured (profiles/r2_notes.md): releasing the dependents at CTA exit instead of at the first instruction, in all five
+    // raster kernels, is worth 1.8 % of the step (0.1093 -> 0.1073 ms): the parked CTAs of the next kernel no longer take slots
+    c->pdl_late = 31;
+    if (const char* e = getenv("MM_PDL_LATE")) c->pdl_late = atoi(e);
     if (const char* e = getenv("MM_PLIST_CAP")) c->plist_cap_max = (unsigned)atoi(e);
     if (const char* e = getenv("MM_VCHUNKS")) { const int v = atoi(e); if (v > 0 && v <= 32) c->nchunks = v; }
     c->smem_vertex_fwd = mm_vertex_smem_fwd(c);

@@ -34,8 +34,6 @@
 #ifndef MM_VTHREADS
 #define MM_VTHREADS     512          // threads per CTA of the vertex-stage kernels
 #endif
-#define MM_ST_W         8            // unfused shading kernels: one warp = one 8 x 4 pixel sub-tile
-#define MM_ST_H         4
 #define MM_REC_FLOATS   12
 #define MM_GF           12           // floats per face of the backward accumulator `gfacc`: d/d corners (6), pad (2), d/d unit
                                      // normal (3), pad (1) -- 48 B, so the three groups are 16/8/16-byte aligned for vector REDs
@@ -50,13 +48,12 @@ struct mm_ctx {
     // derived
     float sx, sy;            // multiplier / W, multiplier / H  (fp32 division, DIBR_SPEC A.1)
     float blen;              // boxlen * multiplier
-    int nstx, nsty;          // sub-tile grid = ceil(W / 8) x ceil(H / 4)
-    int nst;                 // sub-tiles per image
     int nparts_recon;        // CTAs per image of the stand-alone recon_data kernels
     int nchunks;             // vertex forward: CTAs per image (each emits 1/nchunks of the face records)
     size_t smem_vertex_fwd;  // dynamic smem bytes of the vertex forward kernel
     int num_sms;
     int pdl;                 // 1 = dependent kernels are launched with programmatic stream serialization (default; MM_PDL=0 disables)
+    int pdl_late;            // see mm_raster_params.pdl_late (MM_PDL_LATE)
     // forward geometry as ONE kernel over row bands held in shared memory (mm_band.cu; MM_BAND=0 selects the four-kernel chain)
     int band_on, band_shift, band_rows;
     size_t band_smem;
@@ -109,9 +106,10 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
 struct mm_raster_params {
     int B, V, F, H, W, Ht, Wt;
     int Htp;                 // physical texture rows: Ht, or Ht/2 for a mirrored texture (mm_ctx_set_texture_mirror)
-    int nstx, nsty, nst, knum;
+    int knum;
     float sx, sy, blen, multiplier, eps, sigmainv;
     int no_mask;
+    int pdl_late;            // bit k: kernel k releases its dependents at CTA exit (0 hard, 1 soft_fwd, 2 soft_ovf, 3 shade, 4 soft_bwd)
     const float* frec;       // [B,F,12]
     unsigned long long* zbuf;     // [B,H,W]
     unsigned long long* lacc;     // [B,H,W]
@@ -155,6 +153,14 @@ struct mm_raster_params {
 #ifdef __CUDACC__
 __device__ __forceinline__ void mm_pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+// The same for a kernel whose grid is SEVERAL waves deep: the dependents are released when a CTA exits (a CTA that never
+// executes launch_dependents counts as having done so at exit) instead of at its first instruction, so that the next kernel's
+// CTAs -- which can only park at their own wait -- do not take the SM slots this kernel's later waves need.  `late` is a launch
+// parameter (experiment switch MM_PDL_LATE, bit per kernel).
+__device__ __forceinline__ void mm_pdl_prologue(bool late) {
+    if (!late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 template <typename... KArgs, typename... Args>

@@ -77,20 +77,6 @@ __device__ __forceinline__ float interp3(float w0, float w1, float w2, float c0,
     return ADD(ADD(MUL(w0, c0), MUL(w1, c1)), MUL(w2, c2));
 }
 
-// DIBR_SPEC A.2: returns true and fills (w, z) iff the pixel is inside the tight bbox and the triangle
-__device__ __forceinline__ bool hard_test(const FaceRec& r, float x0, float y0, float eps,
-                                          float& w0, float& w1, float& w2, float& zz) {
-    const float xmin = fminf(fminf(r.ax, r.bx), r.cx), xmax = fmaxf(fmaxf(r.ax, r.bx), r.cx);
-    const float ymin = fminf(fminf(r.ay, r.by), r.cy), ymax = fmaxf(fmaxf(r.ay, r.by), r.cy);
-    if (x0 < xmin || x0 >= xmax || y0 < ymin || y0 >= ymax) return false;
-    Bary b;
-    bary_eval(r, x0, y0, eps, b);
-    if (b.w0 < 0.0f || b.w1 < 0.0f || b.w2 < 0.0f) return false;
-    w0 = b.w0; w1 = b.w1; w2 = b.w2;
-    zz = ADD(ADD(MUL(b.w0, r.az), MUL(b.w1, r.bz)), MUL(b.w2, r.cz));
-    return true;
-}
-
 // DIBR_SPEC A.4: half-open test against the bbox enlarged by blen
 __device__ __forceinline__ bool soft_bbox_test(const FaceRec& r, float x0, float y0, float blen) {
     const float xmin = SUB(fminf(fminf(r.ax, r.bx), r.cx), blen), xmax = ADD(fmaxf(fmaxf(r.ax, r.bx), r.cx), blen);
@@ -98,45 +84,10 @@ __device__ __forceinline__ bool soft_bbox_test(const FaceRec& r, float x0, float
     return !(x0 < xmin || x0 >= xmax || y0 < ymin || y0 >= ymax);
 }
 
-// squared distance to the edge (x1,y1)-(x2,y2): perpendicular if the foot lies on the segment, else "far"
-__device__ __forceinline__ float edge_d2(float x1, float y1, float x2, float y2, float x0, float y0, float far) {
-    const float A = SUB(y2, y1), B = SUB(x1, x2), C = SUB(MUL(x2, y1), MUL(x1, y2));
-    const float up = ADD(ADD(MUL(A, x0), MUL(B, y0)), C);
-    const float down = ADD(MUL(A, A), MUL(B, B));
-    const float dn = ADD(down, 1e-10f);
-    float x3 = SUB(SUB(MUL(MUL(B, B), x0), MUL(MUL(A, B), y0)), MUL(A, C));
-    float y3 = SUB(SUB(MUL(MUL(A, A), y0), MUL(MUL(A, B), x0)), MUL(B, C));
-    x3 = DIV(x3, dn);
-    y3 = DIV(y3, dn);
-    const float direct = ADD(MUL(SUB(x3, x1), SUB(x3, x2)), MUL(SUB(y3, y1), SUB(y3, y2)));
-    return direct > 0.0f ? far : DIV(MUL(up, up), dn);
-}
-
-// DIBR_SPEC A.4: min over 3 edge + 3 vertex squared distances; returns d2 and the type 0..5
-__device__ __forceinline__ float soft_d2(const FaceRec& r, float x0, float y0, float mult, int& type) {
-    const float far = MUL(MUL(4.0f, mult), mult);
-    float d = edge_d2(r.ax, r.ay, r.bx, r.by, x0, y0, far);
-    type = 0;
-    float v = edge_d2(r.bx, r.by, r.cx, r.cy, x0, y0, far);
-    if (d > v) { d = v; type = 1; }
-    v = edge_d2(r.cx, r.cy, r.ax, r.ay, x0, y0, far);
-    if (d > v) { d = v; type = 2; }
-    v = ADD(MUL(SUB(x0, r.ax), SUB(x0, r.ax)), MUL(SUB(y0, r.ay), SUB(y0, r.ay)));
-    if (d > v) { d = v; type = 3; }
-    v = ADD(MUL(SUB(x0, r.bx), SUB(x0, r.bx)), MUL(SUB(y0, r.by), SUB(y0, r.by)));
-    if (d > v) { d = v; type = 4; }
-    v = ADD(MUL(SUB(x0, r.cx), SUB(x0, r.cx)), MUL(SUB(y0, r.cy), SUB(y0, r.cy)));
-    if (d > v) { d = v; type = 5; }
-    return d;
-}
-
-__device__ __forceinline__ float soft_prob(float d2, float sigmainv, float mult) {
-    const float z = DIV(DIV(MUL(sigmainv, d2), mult), mult);
-    return expf(-z);
-}
-
-// ---- production variants of the soft-silhouette distance.  The cancellation-prone quantities (A, B, C, up, down)
-// keep the reference's exact operation order; what changes is only HOW the well-conditioned tail is evaluated:
+// ---- soft-silhouette distance (DIBR_SPEC A.4): squared distance to each edge (perpendicular if the foot lies on the segment,
+// else "far") and to each vertex, minimum + its type 0..5.  The cancellation-prone quantities (A, B, C, up, down) keep the
+// reference's exact operation order; what differs from the oracle's literal statement is only HOW the well-conditioned tail
+// is evaluated:
 //   * the "foot of the perpendicular lies on the segment" test is done on the un-divided foot (X - x1*dn)(X - x2*dn) +
 //     (Y - y1*dn)(Y - y2*dn) > 0  (== direct * dn^2): two IEEE divisions less per edge; the decision can only differ
 //     where direct ~ 0, i.e. where the perpendicular and the vertex distance coincide (the min is continuous there);

@@ -412,7 +412,7 @@ template <bool VEC, bool HAS_GUP, int MODE>
 __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MINB)
 k_shade(const mm_raster_params p)
 {
-    mm_pdl_prologue();
+    mm_pdl_prologue((p.pdl_late & 8) != 0);
     __shared__ ShadeSmem sm;
     shade_role<VEC, HAS_GUP, MODE>(p, sm, blockIdx.x, blockIdx.y);
 }

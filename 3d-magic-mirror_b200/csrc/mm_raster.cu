@@ -7,21 +7,21 @@
 // bookkeeping: ncu showed ~4500 warp-instructions per 8x4-pixel tile for ~100 useful (pixel, face) pairs.  This file
 // SCATTERS instead: the unit of work is a face.
 //
-//   k_scatter<HARD>      4 lanes per (image, face): walk the face's tight bbox, exact DIB-R inside test + depth, resolve
-//                 visibility with ONE 64-bit atomicMax per covered pixel on a packed (order-preserving depth << 32 |
-//                 ~face) key.  max == "largest z, then smallest face index" == the reference's ordered scan with its
-//                 strictly-greater test, so `face_idx` is bit-exact and independent of thread order.  No binning, no
-//                 face lists.
-//   k_scatter<SOFT_FWD>  all faces: walk the bbox enlarged by `boxlen`; for every UNCOVERED pixel inside (exact
-//                 half-open test) evaluate the DIB-R distance / probability once and fold log(1 - p) and a candidate
-//                 count into the pixel's 64-bit accumulator with ONE integer atomicAdd (fixed point => order
-//                 independent => deterministic).  A pixel whose count reaches knum + 1 is appended to the overflow list.
-//   k_scatter<SOFT_BWD>  same walk; gradients are accumulated per face slot in shared memory and leave as <= 6 atomics
-//                 per face.
-//   k_soft_ovf    rare path (far cameras): DIB-R keeps only the FIRST knum candidates in face-index order.  One warp per
-//                 overflowed pixel replays the reference's ordered scan over all faces (32 faces per step, ballot keeps
-//                 the order) and stores the exact truncated product; the backward variant scatters the gradients of
-//                 exactly those knum candidates.
+//   k_scatter_hard  a warp owns 8 faces (of 8 different images); the (face, pixel) pairs of their EXACT tight-bbox rectangles are
+//                 numbered and dealt to the 32 lanes; a pair runs the exact DIB-R inside test + depth and resolves visibility
+//                 with ONE 64-bit atomicMax on a packed (order-preserving depth << 32 | ~face) key.  max == "largest z, then
+//                 smallest face index" == the reference's ordered scan with its strictly-greater test, so `face_idx` is
+//                 bit-exact and independent of thread order.  No binning, no face lists.
+//   k_soft_fwd     (mm_soft_fwd.cuh) all faces: walk the bbox enlarged by `boxlen` against the coverage bitmap; for every
+//                 UNCOVERED pixel inside (exact half-open test) evaluate the DIB-R distance / probability once and fold
+//                 log(1 - p) and a candidate count into the pixel's 64-bit accumulator with ONE integer atomicAdd (fixed
+//                 point => order independent => deterministic); the pairs go to a list the backward replays.  A pixel whose
+//                 count reaches knum + 1 is appended to the overflow list.
+//   k_soft_ovf_fwd rare path (far cameras): DIB-R keeps only the FIRST knum candidates in face-index order.  One CTA per
+//                 truncated pixel replays the reference's ordered scan over all faces and stores the exact truncated product.
+//   k_soft_bwd     ONE launch: CTAs < nlist replay the pair list (one pair per lane, vector REDs into the per-face
+//                 accumulators; if the list overflowed its buffer: the bbox walk again, scatter_warp<SOFT_BWD>), the rest redo
+//                 the truncated pixels and scatter the gradients of exactly those knum candidates.
 //   Backward re-derives every probability from the face records instead of storing Kaolin's knum-deep side buffers
 //   (B*H*W*30*(4+8+1) B = 307 MB at B=48,128^2).
 #include "mm_device.cuh"
@@ -53,7 +53,7 @@ struct WarpQ {
     float facc[6][FPW];      // backward: corner-gradient accumulators per slot
 };
 
-enum { MODE_HARD = 0, MODE_SOFT_FWD = 1, MODE_SOFT_BWD = 2 };
+enum { MODE_HARD = 0, MODE_SOFT_BWD = 2 };
 
 __device__ __forceinline__ FaceRec slot_rec(const WarpQ& wq, int slot) {
     FaceRec r;
@@ -122,15 +122,6 @@ __device__ __forceinline__ void eval_pair(const mm_raster_params& p, WarpQ& wq, 
         const float zz = ADD(ADD(MUL(bb.w0, r.az), MUL(bb.w1, r.bz)), MUL(bb.w2, r.cz));
         atomicMax(p.zbuf + (size_t)b * HW + pix, depth_key(zz, wq.face[slot]));
         atomicOr(p.cov + ((size_t)b * p.H + iy) * p.covw + (ix >> 5), 1u << (ix & 31));
-    } else if (MODE == MODE_SOFT_FWD) {
-        int type;
-        const float d2 = soft_d2_fast(r, px, py, p.multiplier, type);
-        const float prob = soft_prob_fast(d2, kz);
-        const unsigned long long old = atomicAdd(p.lacc + (size_t)b * HW + pix, lacc_term(log1pf(-prob)));
-        if (lacc_count(old) == p.knum) {                        // candidate knum+1: the pixel needs the ordered pass
-            const uint32_t s2 = atomicAdd(p.ovf_count, 1u);
-            p.ovf_list[s2] = (uint32_t)((size_t)b * HW + pix);
-        }
     } else {
         const float g = gsoft_at(p, b, pix);
         const float soft = p.rgba[(size_t)b * 4 * HW + 3 * HW + pix];
@@ -139,20 +130,6 @@ __device__ __forceinline__ void eval_pair(const mm_raster_params& p, WarpQ& wq, 
         soft_pair_grad(p, r, px, py, kz, inv_mult, g, 1.0f - soft, ga);
         #pragma unroll
         for (int k = 0; k < 6; ++k) if (ga[k] != 0.0f) atomicAdd(&wq.facc[k][slot], ga[k]);
-    }
-}
-
-// forward soft pass: append the pairs this warp just evaluated to the global pair list (one atomicAdd per batch);
-// all 32 lanes must call it.  If the list is full the count still grows, which tells the backward to fall back.
-__device__ __forceinline__ void record_pairs(const mm_raster_params& p, const WarpQ& wq, uint32_t e, int n, int lane)
-{
-    uint32_t base = 0u;
-    if (lane == 0) base = atomicAdd(p.ovf_count + 1, (uint32_t)n);
-    base = __shfl_sync(FULL, base, 0);
-    if (lane < n && base + (uint32_t)lane < p.plist_cap) {
-        const int slot = (int)(e >> 24);
-        const unsigned long long fg = (unsigned long long)((size_t)wq.img[slot] * p.F + wq.face[slot]);
-        p.plist[base + lane] = (fg << 32) | (unsigned long long)(e & 0xffffffu);
     }
 }
 
@@ -242,14 +219,12 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
             const uint32_t carry = wq.q[32 + lane];
             __syncwarp();
             eval_pair<MODE>(p, wq, e, kz, inv_mult);
-            if (MODE == MODE_SOFT_FWD) record_pairs(p, wq, e, 32, lane);
             qn -= 32;
             if (lane < qn) wq.q[lane] = carry;
             __syncwarp();
         }
     }
     if (MODE != MODE_HARD && lane < qn) eval_pair<MODE>(p, wq, wq.q[lane], kz, inv_mult);
-    if (MODE == MODE_SOFT_FWD && qn > 0) record_pairs(p, wq, lane < qn ? wq.q[lane] : 0u, qn, lane);
     if (MODE == MODE_SOFT_BWD) {
         __syncwarp();
         for (int idx = lane; idx < 6 * FPW; idx += 32) {
@@ -267,7 +242,7 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
 __global__ void __launch_bounds__(256)
 k_scatter_hard(const mm_raster_params p)
 {
-    mm_pdl_prologue();
+    mm_pdl_prologue((p.pdl_late & 1) != 0);
     __shared__ WarpQ s_wq[8];
     if (p.nclr) {                                      // the hard pass is issue-bound and leaves the memory system idle: clear
         const size_t nthreads = (size_t)gridDim.x * blockDim.x;      // the step's texture-gradient buffer on the side
@@ -284,7 +259,7 @@ k_scatter_hard(const mm_raster_params p)
 __global__ void __launch_bounds__(32 * SF_WARPS)
 k_soft_fwd(const mm_raster_params p)
 {
-    mm_pdl_prologue();
+    mm_pdl_prologue((p.pdl_late & 2) != 0);
     __shared__ SoftQ s_wq[SF_WARPS];
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     soft_fwd_role(p, s_wq[threadIdx.x >> 5], gwarp);
@@ -460,7 +435,7 @@ __device__ __forceinline__ void soft_ovf_role(const mm_raster_params& p, uint32_
 __global__ void __launch_bounds__(OVF_THREADS)
 k_soft_ovf_fwd(const mm_raster_params p)
 {
-    mm_pdl_prologue();
+    mm_pdl_prologue((p.pdl_late & 4) != 0);
     __shared__ uint32_t s_mask[OVF_MAX_WORDS];
     __shared__ int s_kept[MM_MAX_KNUM];
     soft_ovf_role<false>(p, s_mask, s_kept, blockIdx.x, gridDim.x);
@@ -471,7 +446,7 @@ k_soft_ovf_fwd(const mm_raster_params p)
 __global__ void __launch_bounds__(SB_THREADS)
 k_soft_bwd(const mm_raster_params p, const int nlist)
 {
-    mm_pdl_prologue();
+    mm_pdl_prologue((p.pdl_late & 16) != 0);
     __shared__ WarpQ s_wq[SB_THREADS / 32];
     __shared__ uint32_t s_mask[OVF_MAX_WORDS];
     __shared__ int s_kept[MM_MAX_KNUM];
