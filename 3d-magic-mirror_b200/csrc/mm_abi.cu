@@ -186,9 +186,10 @@ int mm_ctx_create(mm_ctx** out, int device, int V, int F, const int32_t* faces_h
     c->nchunks = 8;
     c->pdl = 1;
     if (const char* e = getenv("MM_PDL")) c->pdl = atoi(e) != 0;
-    // measured (profiles/r2_notes.md): releasing the dependents at CTA exit instead of at the first instruction, in all five
-    // raster kernels, is worth 1.8 % of the step (0.1093 -> 0.1073 ms): the parked CTAs of the next kernel no longer take slots
-    c->pdl_late = 31;
+    // measured (profiles/r2_notes.md section 4): releasing the dependents at CTA exit instead of at the first instruction in the
+    // four forward raster kernels (the parked CTAs of the next kernel no longer take slots), but EARLY in k_soft_bwd so that
+    // k_vertex_bwd's input-only prologue (cold loads, camera chain, vertex transform) runs under it: 0.1093 -> 0.1045 ms
+    c->pdl_late = 15;
     if (const char* e = getenv("MM_PDL_LATE")) c->pdl_late = atoi(e);
     if (const char* e = getenv("MM_PLIST_CAP")) c->plist_cap_max = (unsigned)atoi(e);
     if (const char* e = getenv("MM_VCHUNKS")) { const int v = atoi(e); if (v > 0 && v <= 32) c->nchunks = v; }

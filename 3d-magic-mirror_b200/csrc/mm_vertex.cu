@@ -41,7 +41,11 @@ k_vertex_fwd(const VertexFwdParams q,
              float* __restrict__ frec, float* __restrict__ vimg, float* __restrict__ face_normals,
              float* __restrict__ gfacc_zero, long long* __restrict__ img_fwd, long long* __restrict__ img_bwd)
 {
-    mm_pdl_prologue();
+    // First kernel of a step: WAIT FIRST, then release the dependents.  Nothing of this library can then run before the work
+    // that precedes the step in the stream (the producer of vertices / camera scalars / textures) is complete and visible --
+    // which is what lets k_vertex_bwd read the caller's inputs ahead of its own wait.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ float sm[];
     const int V = q.V, F = q.F;
     float* sT = sm;                    // 12
@@ -138,7 +142,11 @@ k_vertex_bwd(const VertexBwdParams q,
              float* __restrict__ g_vertices, float* __restrict__ g_azim, float* __restrict__ g_elev,
              float* __restrict__ g_dist, float* __restrict__ g_bias, float* __restrict__ g_lights)
 {
-    mm_pdl_prologue();
+    // Programmatic dependent launch: everything up to the face loop reads only the CALLER's inputs (vertices, camera scalars),
+    // which were complete before the step's first kernel ran (that kernel waited for them) -- so this prologue (two cold loads,
+    // the camera chain, 642 transforms) runs while the previous kernel (k_soft_bwd) is still draining; the wait sits right in
+    // front of the first read of what that kernel produced (gfacc, img_bwd).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ float sm[];
@@ -162,6 +170,7 @@ k_vertex_bwd(const VertexBwdParams q,
         svc[v * 3] = cx; svc[v * 3 + 1] = cy; svc[v * 3 + 2] = cz;
     }
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int fper = (F + VB_CLUSTER - 1) / VB_CLUSTER;
     const int f_end = min(F, (rank + 1) * fper);
     for (int f = rank * fper + threadIdx.x; f < f_end; f += blockDim.x) {

@@ -36,7 +36,7 @@
  * Environment switches read at mm_ctx_create (diagnostics; defaults are the measured best):
  *   MM_PDL=0        no programmatic dependent launch between the library's kernels
  *   MM_PDL_LATE=m   bit k set: raster kernel k releases its dependent launch at CTA exit instead of at its first instruction
- *                   (0 hard, 1 soft forward, 2 overflow, 3 shading, 4 soft backward; default 31)
+ *                   (0 hard, 1 soft forward, 2 overflow, 3 shading, 4 soft backward; default 15)
  *   MM_VCHUNKS=n    CTAs per image of the vertex forward kernel (default 8)
  *   MM_PLIST_CAP=n  test hook: caps the forward's candidate list so the backward's fallback path runs
  */
