@@ -657,3 +657,95 @@ def test_wgan_gp_consumer_gradient_reaches_render_inputs(mm):
                  biases='g_biases', textures='g_textures', lights='g_lights', bg='g_bg')
     for k, gk in names.items():
         assert pu.rel_err(out[gk], Ac[k].grad) <= 5e-5, k
+
+
+def test_lazy_fusion_edge_cases(mm):
+    """recon_data's gradient is handed to the render backward lazily; these are the autograd situations in which
+    that hand-over must still give what plain autograd would: a retained graph walked twice, a second recon_data on the same
+    image, another consumer of the image, an image that is not (any more) the untouched render output, and the whole step
+    captured into a CUDA graph."""
+    dr = mm.DiffRender(pu.get_mesh(mm, "sphere"), 64, image_weight=1.0)
+    A0 = pu.to_device(pu.make_attributes(dr.vertices_init, 3, 64, 64, 70), DEV)
+    with torch.no_grad():
+        gt1, _ = dr.render(no_mask=True, **pu.to_device(pu.make_attributes(dr.vertices_init, 3, 64, 64, 71), DEV))
+        gt2, _ = dr.render(no_mask=True, **pu.to_device(pu.make_attributes(dr.vertices_init, 3, 64, 64, 72), DEV))
+    keys = ('vertices', 'azimuths', 'textures', 'lights', 'bg')
+    w = torch.randn(3, 4, 64, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1)) * 1e-4
+
+    def leaf():
+        return {k: (v.clone().requires_grad_(k in keys) if torch.is_tensor(v) else v) for k, v in A0.items()}
+
+    def grads(A):
+        return {k: A[k].grad.clone() for k in keys}
+
+    def close(a, b, tol=3e-5):
+        for k in keys:
+            assert pu.rel_err(a[k], b[k]) <= tol, k
+
+    def reference(fn):                       # the same expression with lazy fusion off
+        dr.lazy_fusion = False
+        try:
+            A = leaf()
+            fn(A).backward()
+            return grads(A)
+        finally:
+            dr.lazy_fusion = True
+
+    one = lambda A: dr.recon_data(dr.render(no_mask=True, **A)[0], gt1, no_mask=True, contour=0.1)      # noqa: E731
+    g_one = reference(one)
+    # (a) retained graph, two backward walks: gradients accumulate to twice the single walk
+    A = leaf()
+    loss = one(A)
+    loss.backward(retain_graph=True)
+    loss.backward()
+    close(grads(A), {k: 2 * v for k, v in g_one.items()})
+    # (b) two recon_data calls on one image (the second cannot share the workspace's IoU sums: it takes the materialised path)
+    two = lambda A: (lambda X: dr.recon_data(X, gt1, no_mask=True, contour=0.1) + 0.5 * dr.recon_data(X, gt2, no_mask=True, contour=0.0))(  # noqa: E731
+        dr.render(no_mask=True, **A)[0])
+    A = leaf()
+    two(A).backward()
+    close(grads(A), reference(two))
+    # (c) another consumer of the image next to the lazily fused loss
+    mix = lambda A: (lambda X: 3.0 * dr.recon_data(X, gt1, no_mask=True, contour=0.1) + (X * w).sum())(dr.render(no_mask=True, **A)[0])  # noqa: E731
+    A = leaf()
+    mix(A).backward()
+    close(grads(A), reference(mix))
+    # (d) not the untouched render output: a clone, and an in-place edit -> materialised path, same numbers
+    for edit in (lambda X: X.clone(), lambda X: X.mul_(1.0)):
+        A = leaf()
+        X = edit(dr.render(no_mask=True, **A)[0])
+        dr.recon_data(X, gt1, no_mask=True, contour=0.1).backward()
+        close(grads(A), g_one)
+    # (e) the gradient with respect to the image ITSELF is the documented placeholder in lazy mode, the real one with it off
+    A = leaf()
+    X = dr.render(no_mask=True, **A)[0]
+    gX, = torch.autograd.grad(dr.recon_data(X, gt1, no_mask=True, contour=0.1), X)
+    assert float(gX.abs().max()) == 0.0
+    dr.lazy_fusion = False
+    X = dr.render(no_mask=True, **leaf())[0]
+    gX, = torch.autograd.grad(dr.recon_data(X, gt1, no_mask=True, contour=0.1), X)
+    dr.lazy_fusion = True
+    assert float(gX.abs().max()) > 0.0
+    # (f) the three calls captured into a CUDA graph and replayed: same loss, same gradients as eager
+    static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in A0.items()}
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            Aw = {k: (v.detach().requires_grad_(k in keys) if torch.is_tensor(v) else v) for k, v in static.items()}
+            one(Aw).backward()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        Ag = {k: (v.detach().requires_grad_(k in keys) if torch.is_tensor(v) else v) for k, v in static.items()}
+        lg = one(Ag)
+        lg.backward()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    A = leaf()
+    le = one(A)
+    le.backward()
+    assert abs(float(lg) - float(le)) <= 1e-6 * abs(float(le))
+    close({k: Ag[k].grad for k in keys}, grads(A))
