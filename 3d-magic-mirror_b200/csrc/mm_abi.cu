@@ -100,6 +100,13 @@ void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int tex_mirror, int no_
     p.no_mask = no_mask;
     p.pdl_late = c->pdl_late;
     p.covw = (c->W + 31) / 32;
+    p.nstrips = mm_shade_strips(c->H, c->W);
+    // shading CTAs per image that double as the overflow role when the image has truncated pixels (far cameras): about one
+    // resident wave over the batch, never more than are resident together (lanes of the row wait for their results)
+    p.novf = c->num_sms * 4 / B; p.novf = p.novf < 32 ? 32 : p.novf;
+    if (p.novf > p.nstrips) p.novf = p.nstrips;
+    if (p.novf > c->num_sms * 2) p.novf = c->num_sms * 2;
+    p.prof = c->prof;
     p.face_uvs = c->d_face_uvs;
     p.tab = c->d_tab;
 }
@@ -109,6 +116,7 @@ void set_ws(const mm_ctx* c, const mm_ws_layout& L, char* ws, mm_raster_params& 
     p.zbuf = (unsigned long long*)(ws + L.zbuf); p.lacc = (unsigned long long*)(ws + L.lacc);
     p.cov = (uint32_t*)(ws + L.cov);
     p.ovf_list = (uint32_t*)(ws + L.ovf_list); p.ovf_count = (uint32_t*)(ws + L.ovf_count);
+    p.ovf_cnt = (uint32_t*)(ws + L.ovf_cnt);
     p.gsoft = (float*)(ws + L.gsoft);
     p.plist = (unsigned long long*)(ws + L.plist); p.plist_cap = (uint32_t)((L.gsoft - L.plist) / 8);
     if (c->plist_cap_max && p.plist_cap > c->plist_cap_max) p.plist_cap = c->plist_cap_max;
@@ -120,15 +128,16 @@ void set_ws(const mm_ctx* c, const mm_ws_layout& L, char* ws, mm_raster_params& 
 // counters (one contiguous range) and the per-face backward accumulators for the rest of the step
 cudaError_t launch_vertex_fwd(const mm_ctx* c, int B, const mm_ws_layout& L, char* ws, const float* vertices, const float* azim,
                               const float* elev, const float* dist, const float* bias, float* face_normals, cudaStream_t s) {
-    // zbuf .. ovf_count are contiguous and 256-byte aligned: one clear range (16-byte units, tail padded inside the workspace)
-    const size_t bytes0 = mm_align_up((L.ovf_count + 16) - L.zbuf, 16);
+    // zbuf .. ovf_cnt are contiguous and 256-byte aligned: one clear range (16-byte units, tail padded inside the workspace)
+    const size_t bytes0 = mm_align_up((L.ovf_cnt + (size_t)B * 4) - L.zbuf, 16);
     return mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg), face_normals,
                                 (float*)(ws + L.gfacc), (long long*)(ws + L.img_fwd), (long long*)(ws + L.img_bwd),
                                 ws + L.zbuf, bytes0, nullptr, 0, s);
 }
 
 // forward geometry of a batch: face records + visibility buffer + soft-silhouette accumulators + candidate lists (vertex stage ->
-// hard pass -> soft pass -> overflow pass).  p.clr / p.nclr (fused step) name a buffer that is cleared on the side.
+// hard pass -> soft pass; truncated pixels are re-done inside the shading kernel).  p.clr / p.nclr (fused step) name a buffer
+// that is cleared on the side.
 int launch_geometry_forward(const mm_ctx* c, int B, const mm_ws_layout& L, char* ws, const mm_raster_params& p,
                             const float* vertices, const float* azim, const float* elev, const float* dist, const float* bias,
                             float* face_normals, cudaStream_t s) {
@@ -240,7 +249,7 @@ int mm_ctx_destroy(mm_ctx* c) {
 
 int mm_ctx_get_int(const mm_ctx* c, const char* key) {
     if (!c || !key) return -1;
-    const int geom = 4;                                     // vertex + hard + soft + overflow
+    const int geom = 3;                                     // vertex + hard + soft
     if (!strcmp(key, "fused_kernels")) return geom + 3;     // + shading, soft backward, vertex backward
     if (!strcmp(key, "api_kernels")) return geom + 1 + 1 + 3;   // + shade fwd | recon | shade bwd, soft bwd, vertex bwd
     return -1;
@@ -285,7 +294,7 @@ int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azi
     MM_COMMON_CHECKS(c, B, workspace, workspace_bytes);
     MM_REQUIRE(vertices && azim && elev && dist && bias && tex && lights, "NULL input");
     MM_REQUIRE(!no_mask || bg, "no_mask=1 requires bg");
-    MM_REQUIRE(rgba, "rgba (the forward output)");
+    (void)rgba;                  // (kept in the signature; the backward reads the silhouette from the workspace since ABI v3)
     MM_REQUIRE(Ht > 0 && Wt > 0 && (!tex_mirror || (Ht & 1) == 0), "texture size (even Ht for a mirrored texture)");
     MM_REQUIRE(g_vertices && g_azim && g_elev && g_dist && g_bias && g_tex && g_lights, "NULL gradient output");
     cudaStream_t s = (cudaStream_t)stream;
@@ -298,7 +307,6 @@ int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azi
     fill_params(c, B, Ht, Wt, tex_mirror, no_mask, p);
     set_ws(c, L, ws, p);
     p.tex = tex; p.lights = lights; p.bg = bg;
-    p.rgba = const_cast<float*>(rgba);
     p.g_rgba = g_rgba;
     p.g_tex = g_tex; p.g_bg = no_mask ? g_bg : nullptr;
     if (recon_gt) {
@@ -590,6 +598,11 @@ int mm_ctx_get_timing(mm_ctx* c, float* ms_host, int capacity) {
     for (int i = 0; i < 7; ++i) MM_CUDA(cudaEventElapsedTime(&ms_host[i], c->ev[i], c->ev[i + 1]));
     return 7;
 }
+
+#ifdef MM_PROF
+// MM_PROF builds only (not part of the ABI): device buffer [6][16384][4] u64 of per-warp time stamps, or NULL
+int mm_debug_profile(mm_ctx* c, unsigned long long* buf) { if (!c) return MM_E_INVALID; c->prof = buf; return MM_OK; }
+#endif
 
 int mm_debug_export_faces(mm_ctx* c, int B, const void* workspace, size_t workspace_bytes, float* fvi, float* fvz, float* fnz,
                           void* stream)

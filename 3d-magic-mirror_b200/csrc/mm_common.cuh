@@ -13,9 +13,11 @@
 //     lacc       [B,H,W] u64  soft-silhouette accumulator of uncovered pixels: fixed-point sum log(1-p) << 16 | count
 //     cov        [B,H,ceil(W/32)] u32 coverage bitmap written by the hard pass (atomicOr): the soft pass finds the UNCOVERED
 //                             pixels of a face's enlarged bbox with one word load per row instead of one zbuf load per pixel
-//     ovf_count  [4] u32   {pixels that saw more than knum candidates, candidate pairs recorded, -, -}
-//                          (zbuf, lacc, cov and ovf_count are contiguous: k_vertex_fwd clears them in one range)
-//     ovf_list   [B*H*W] u32  the truncated pixels (exact ordered re-scan by the overflow pass)
+//     ovf_count  [4] u32   {-, candidate pairs recorded, -, -}
+//     ovf_cnt    [B] u32   truncated pixels of each image (more than knum soft candidates)
+//                          (zbuf, lacc, cov, ovf_count and ovf_cnt are contiguous: k_vertex_fwd clears them in one range)
+//     ovf_list   [B,H*W] u32  per image: its truncated pixels (pixel index inside the image), re-done exactly, in face order, by
+//                             the shading kernel's overflow role
 //     plist      [2*B*H*W] u64 the (face, pixel) candidate pairs the forward soft pass evaluated, (image*F+face) << 32 |
 //                             iy << 12 | ix: the backward soft pass replays this dense list
 //     gsoft      [B,H,W]      d(loss)/d(silhouette) per pixel, handed from the shading stage to the geometry backward
@@ -54,10 +56,7 @@ struct mm_ctx {
     int num_sms;
     int pdl;                 // 1 = dependent kernels are launched with programmatic stream serialization (default; MM_PDL=0 disables)
     int pdl_late;            // see mm_raster_params.pdl_late (MM_PDL_LATE)
-    // forward geometry as ONE kernel over row bands held in shared memory (mm_band.cu; MM_BAND=0 selects the four-kernel chain)
-    int band_on, band_shift, band_rows;
-    size_t band_smem;
-    long long* band_prof;    // MM_BAND_PROF=1: [8192][8] per-CTA phase stamps of the last band launch (mm_debug_band_profile)
+    unsigned long long* prof;     // MM_PROF builds: device buffer of per-warp time stamps (mm_debug_profile), else NULL
     unsigned plist_cap_max;  // test hook (MM_PLIST_CAP): caps the forward's pair list so that the backward's fallback path runs
     // device arrays
     int32_t* d_faces;        // [F,3]
@@ -75,7 +74,7 @@ struct mm_ctx {
 };
 
 struct mm_ws_layout {
-    size_t frec, zbuf, lacc, cov, ovf_count, ovf_list, plist, gsoft, vimg, gfacc, img_fwd, ticket, img_bwd, total;
+    size_t frec, zbuf, lacc, cov, ovf_count, ovf_cnt, ovf_list, plist, gsoft, vimg, gfacc, img_fwd, ticket, img_bwd, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -84,11 +83,12 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     mm_ws_layout L;
     size_t off = 0;
     L.frec = off;     off = mm_align_up(off + (size_t)B * c->F * MM_REC_FLOATS * 4, 256);
-    // zbuf, lacc, cov and ovf_count are contiguous: one memset clears them at the start of every forward
+    // zbuf .. ovf_cnt are contiguous: one range, cleared at the start of every forward
     L.zbuf = off;     off = mm_align_up(off + (size_t)B * c->H * c->W * 8, 256);
     L.lacc = off;     off = mm_align_up(off + (size_t)B * c->H * c->W * 8, 256);
     L.cov = off;      off = mm_align_up(off + (size_t)B * c->H * ((c->W + 31) / 32) * 4, 256);
-    L.ovf_count = off; off = mm_align_up(off + 16, 256);
+    L.ovf_count = off; off = off + 16;
+    L.ovf_cnt = off;  off = mm_align_up(off + (size_t)B * 4, 256);
     L.ovf_list = off; off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.plist = off;    off = mm_align_up(off + (size_t)2 * B * c->H * c->W * 8, 256);
     L.gsoft = off;    off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
@@ -109,14 +109,17 @@ struct mm_raster_params {
     int knum;
     float sx, sy, blen, multiplier, eps, sigmainv;
     int no_mask;
-    int pdl_late;            // bit k: kernel k releases its dependents at CTA exit (0 hard, 1 soft_fwd, 2 soft_ovf, 3 shade, 4 soft_bwd)
+    int pdl_late;            // bit k: kernel k releases its dependents at CTA exit (0 hard, 1 soft_fwd, 3 shade, 4 soft_bwd)
     const float* frec;       // [B,F,12]
     unsigned long long* zbuf;     // [B,H,W]
     unsigned long long* lacc;     // [B,H,W]
     uint32_t* cov;           // [B,H,ceil(W/32)] coverage bitmap: bit set = some front face covers the pixel (hard pass, atomicOr)
     int covw;                // words per bitmap row
-    uint32_t* ovf_list;      // [B*H*W]
-    uint32_t* ovf_count;     // [4]: {overflow pixels, candidate pairs recorded, -, -}
+    uint32_t* ovf_list;      // [B,H*W] per-image lists of truncated pixels
+    uint32_t* ovf_count;     // [4]: {-, candidate pairs recorded, -, -}
+    uint32_t* ovf_cnt;       // [B] truncated pixels per image
+    int nstrips, novf;       // shading: CTAs per image; how many of them double as the overflow role
+    unsigned long long* prof;     // MM_PROF builds: per-warp time stamps (tools/probes/timeline.py), else NULL
     unsigned long long* plist;    // [plist_cap]
     uint32_t plist_cap;
 
@@ -163,6 +166,19 @@ __device__ __forceinline__ void mm_pdl_prologue(bool late) {
     if (!late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// ---- per-warp time stamps (MM_PROF builds only; tools/probes/timeline.py): prof[((kernel * 16384 + warp) * 4) + slot]
+#ifdef MM_PROF
+__device__ __forceinline__ void mm_prof_mark(unsigned long long* prof, int kid, int wid, int slot) {
+    if (prof && (threadIdx.x & 31) == 0 && wid < 16384) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        prof[((size_t)kid * 16384 + wid) * 4 + slot] = t;
+    }
+}
+#define MM_PROF_MARK(prof, kid, wid, slot) mm_prof_mark(prof, kid, wid, slot)
+#else
+#define MM_PROF_MARK(prof, kid, wid, slot) do { } while (0)
+#endif
 template <typename... KArgs, typename... Args>
 static inline cudaError_t mm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
                                     Args... args) {
@@ -190,6 +206,7 @@ cudaError_t mm_launch_template_fwd(const mm_ctx* c, int N, int h, int w, const f
 cudaError_t mm_launch_template_bwd(const mm_ctx* c, int N, int h, int w, const float* tmpl, const float* g_local,
                                    const float* g_ndiff, float* g_x, cudaStream_t s);
 int mm_template_max_plane(void);
+int mm_shade_strips(int H, int W);
 cudaError_t mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 cudaError_t mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 // shading: mode 0 = fused (forward + loss sums + RGB-side backward), 1 = forward only, 2 = backward only

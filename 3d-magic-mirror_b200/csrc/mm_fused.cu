@@ -14,6 +14,7 @@
 //   k_gsoft      H or W not a multiple of 4 only: d(loss)/d(silhouette) in its own pass (contour term through index tables).
 // The geometry backward (mm_raster.cu) consumes `gsoft`.
 #include "mm_device.cuh"
+#include "mm_soft_fwd.cuh"
 
 namespace {
 
@@ -50,6 +51,18 @@ __device__ __forceinline__ void store4(float* __restrict__ p, int n, const float
     }
 }
 
+// a truncated pixel whose exact accumulator has not been stored yet (see k_shade): spin on the word, served by L2
+__device__ __noinline__ unsigned long long lacc_wait_exact(const unsigned long long* a) {
+    unsigned long long v;
+    unsigned spins = 0;                               // (seconds of waiting = a broken dispatch order: trap, do not hang)
+    for (;;) {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a) : "memory");
+        if (lacc_count(v) == (int)MM_LACC_OVF) return v;
+        __nanosleep(200);
+        if (++spins > (1u << 23)) __trap();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- fused shading
 // A CTA of FUSED_WARPS warps owns a strip of FUSED_WARPS 16x8-pixel tiles.
 //   pass 1 (streaming): every thread handles 4 consecutive pixels as float4 accesses issued up front, shades them AS
@@ -70,27 +83,21 @@ __device__ __forceinline__ void store4(float* __restrict__ p, int n, const float
 #define FUSED_TILE_PX (FT_W * FT_H)
 
 struct ShadeSmem {
-    float lights[16];
     uint32_t list[FUSED_WARPS * FUSED_TILE_PX];      // face << 10 | warp << 7 | lane << 2 | j   (F <= 65535, <= 8 warps)
-    int count;
 };
 
 enum { SHADE_FUSED = 0, SHADE_FWD = 1, SHADE_BWD = 2 };
 
 template <bool VEC, bool HAS_GUP, int MODE>
-__device__ __forceinline__ void shade_role(const mm_raster_params& p, ShadeSmem& sm, const int bx, const int b)
+// (the caller has loaded the image's lights into s_lights, zeroed s_count and passed a block barrier)
+__device__ __forceinline__ void shade_role(const mm_raster_params& p, ShadeSmem& sm, const float* s_lights, int& s_count, const int bx, const int b)
 {
     constexpr bool OUT = MODE != SHADE_BWD;        // stores the image (rgba [+ imnormal, face_idx])
     constexpr bool SUMS = MODE == SHADE_FUSED;     // accumulates the loss sums (L1, IoU, contour)
     constexpr bool GRAD = MODE != SHADE_FWD;       // forms the RGB-side backward and d(loss)/d(silhouette)
     const bool analytic = GRAD && p.analytic_loss; // the recon_data gradient is formed in-kernel from gt
-    float* s_lights = sm.lights;
     uint32_t* s_list = sm.list;
-    int& s_count = sm.count;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
     const int H = p.H, W = p.W;
     const size_t HW = (size_t)H * W;
     const int ntx = (W + FT_W - 1) / FT_W;
@@ -127,6 +134,8 @@ __device__ __forceinline__ void shade_role(const mm_raster_params& p, ShadeSmem&
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     face[j] = (j < n) ? key_face(z[j]) : -1;
+                    if (MODE != SHADE_BWD && j < n && face[j] < 0 && lacc_count(l[j]) > p.knum && lacc_count(l[j]) != (int)MM_LACC_OVF)
+                        l[j] = lacc_wait_exact(la + j);                  // truncated pixel, exact value on its way
                     soft[j] = (face[j] >= 0) ? 1.0f : lacc_soft(l[j]);
                 }
             }
@@ -408,13 +417,41 @@ __device__ __forceinline__ void shade_role(const mm_raster_params& p, ShadeSmem&
     }
 }
 
+// grid (p.nstrips, B).  Forward modes (SHADE_FUSED / SHADE_FWD) also own the TRUNCATED pixels of the soft pass (more than knum
+// candidates: DIB-R keeps the first knum in face order, DIBR_SPEC A.4).  If image b has any (ovf_cnt[b], final when this kernel
+// starts; fetched together with the lights, one round trip for both), the first p.novf CTAs of its row first re-do their share
+// of them exactly, one CTA per pixel (soft_ovf_role), which replaces the pixel's accumulator by the exact word (count field
+// MM_LACC_OVF).  Nobody waits at CTA level: a lane of pass 1 that meets an accumulator with count > knum that is not exact yet
+// spins on THAT word (lacc_wait_exact).  The CTA it waits for is one of the row's first p.novf: CTAs are dispatched in order
+// and p.novf of them always fit on the GPU together, so the wait ends.  Almost always the count is zero and none of this runs;
+// it used to be a kernel of its own between the soft pass and the shading: 5 us of launch + drain latency for ~50 pixels per
+// step at cfg-2.
+struct ShadeOvfSmem { uint32_t mask[OVF_MAX_WORDS]; int kept[MM_MAX_KNUM]; };
+
+
 template <bool VEC, bool HAS_GUP, int MODE>
 __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MINB)
 k_shade(const mm_raster_params p)
 {
+    static_assert(FUSED_THREADS == OVF_THREADS, "the overflow role runs with the shading kernel's CTA shape");
     mm_pdl_prologue((p.pdl_late & 8) != 0);
-    __shared__ ShadeSmem sm;
-    shade_role<VEC, HAS_GUP, MODE>(p, sm, blockIdx.x, blockIdx.y);
+    __shared__ union { ShadeSmem sm; ShadeOvfSmem ov; } u;
+    __shared__ float s_lights[16];
+    __shared__ uint32_t s_trunc;
+    __shared__ int s_count;                          // covered pixels of the CTA's strip (shade_role)
+    const int b = blockIdx.y;
+    const int wid = (blockIdx.y * gridDim.x + blockIdx.x) * FUSED_WARPS + (threadIdx.x >> 5);
+    (void)wid;
+    MM_PROF_MARK(p.prof, 3, wid, 0);
+    if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
+    if (threadIdx.x == 0) s_count = 0;
+    if (MODE != SHADE_BWD && threadIdx.x == 32) s_trunc = p.ovf_cnt[b];
+    __syncthreads();
+    if (MODE != SHADE_BWD && s_trunc > blockIdx.x && (int)blockIdx.x < p.novf)
+        soft_ovf_role<false>(p, u.ov.mask, u.ov.kept, b, s_trunc, blockIdx.x, p.novf);     // (every pixel ends with a block barrier)
+    MM_PROF_MARK(p.prof, 3, wid, 1);
+    shade_role<VEC, HAS_GUP, MODE>(p, u.sm, s_lights, s_count, blockIdx.x, b);
+    MM_PROF_MARK(p.prof, 3, wid, 2);
 }
 
 // ---------------------------------------------------------------------------------------------- d(loss)/d(silhouette)
@@ -428,7 +465,10 @@ k_gsoft(const mm_raster_params p)
     const int b = blockIdx.y;
     const int H = p.H, W = p.W;
     const size_t HW = (size_t)H * W;
-    const float* alpha = p.rgba + (size_t)b * 4 * HW + 3 * HW;
+    // the silhouette, from the workspace (the image tensor itself is not an input of the backward)
+    const unsigned long long* zb = p.zbuf + (size_t)b * HW;
+    const unsigned long long* la = p.lacc + (size_t)b * HW;
+    auto alpha_at = [&](size_t i) { return zb[i] ? 1.0f : lacc_soft(la[i]); };
     const float* gmask = p.gt + (size_t)b * 4 * HW + 3 * HW;
     const float* gup = p.g_rgba ? p.g_rgba + (size_t)b * 4 * HW + 3 * HW : nullptr;
     float* gs = p.gsoft + (size_t)b * HW;
@@ -451,19 +491,19 @@ k_gsoft(const mm_raster_params p)
     const int32_t* colhi = p.tab + 3 * H + 2 * W;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < H * W) {
-        const float gm = gmask[i], m = alpha[i];
+        const float gm = gmask[i], m = alpha_at(i);
         float g = (gup ? gup[i] : 0.0f) - k_iou * (gm * De - Nb * (1.0f - gm)) * inv_de2;
         if (p.contour > 0.0f) {
             const int iy = i / W, ix = i - iy * W;
             const size_t rp = (size_t)refrow[iy] * W + refcol[ix];
-            const float mref = alpha[rp], gref = gmask[rp];
+            const float mref = alpha_at(rp), gref = gmask[rp];
             const float dlt = fabsf(m - mref) - fabsf(gm - gref);
             acc_c += dlt * dlt;
             float gc = 2.0f * dlt * sgnf(m - mref);
             for (int yy = rowlo[iy]; yy < rowhi[iy]; ++yy)
                 for (int xx = collo[ix]; xx < colhi[ix]; ++xx) {
                     const size_t q = (size_t)yy * W + xx;
-                    const float mq = alpha[q], gq = gmask[q];
+                    const float mq = alpha_at(q), gq = gmask[q];
                     const float dq = fabsf(mq - m) - fabsf(gq - gm);
                     gc -= 2.0f * dq * sgnf(mq - m);
                 }
@@ -485,8 +525,7 @@ static bool aligned16(const void* q) { return (((uintptr_t)q) & 15) == 0; }
 
 cudaError_t mm_launch_shade(const mm_ctx* c, const mm_raster_params& p, int mode, cudaStream_t s)
 {
-    const int ntiles = ((p.W + FT_W - 1) / FT_W) * ((p.H + FT_H - 1) / FT_H);
-    const dim3 grid((ntiles + FUSED_WARPS - 1) / FUSED_WARPS, p.B);
+    const dim3 grid(p.nstrips, p.B);
     const bool vec = (p.W & 3) == 0 && aligned16(p.zbuf) && aligned16(p.lacc) && aligned16(p.gt) && aligned16(p.bg) &&
                      aligned16(p.g_rgba) && aligned16(p.rgba) && aligned16(p.g_bg) && aligned16(p.gsoft) &&
                      aligned16(p.imnormal) && aligned16(p.face_idx_out);
@@ -502,6 +541,8 @@ cudaError_t mm_launch_shade(const mm_ctx* c, const mm_raster_params& p, int mode
                 : (gup ? k_shade<false, true, SHADE_BWD> : k_shade<false, false, SHADE_BWD>);
     return mm_launch(k, grid, dim3(FUSED_THREADS), 0, s, c->pdl != 0, p);
 }
+
+int mm_shade_strips(int H, int W) { return (((W + FT_W - 1) / FT_W) * ((H + FT_H - 1) / FT_H) + FUSED_WARPS - 1) / FUSED_WARPS; }
 
 cudaError_t mm_launch_gsoft(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {

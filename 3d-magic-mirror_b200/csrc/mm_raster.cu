@@ -17,9 +17,10 @@
 //                 log(1 - p) and a candidate count into the pixel's 64-bit accumulator with ONE integer atomicAdd (fixed
 //                 point => order independent => deterministic); the pairs go to a list the backward replays.  A pixel whose
 //                 count reaches knum + 1 is appended to the overflow list.
-//   k_soft_ovf_fwd rare path (far cameras): DIB-R keeps only the FIRST knum candidates in face-index order.  One CTA per
-//                 truncated pixel replays the reference's ordered scan over all faces and stores the exact truncated product.
-//   k_soft_bwd     ONE launch: CTAs < nlist replay the pair list (one pair per lane, vector REDs into the per-face
+//   (truncated pixels, far cameras: DIB-R keeps only the FIRST knum candidates in face-index order.  soft_ovf_role, in
+//                 mm_soft_fwd.cuh, replays the reference's ordered scan over all faces, one CTA per pixel, and stores the exact
+//                 truncated product; the forward runs it inside the shading kernel, there is no launch of its own.)
+//   k_soft_bwd     ONE launch: CTAs >= novf replay the pair list (one pair per lane, vector REDs into the per-face
 //                 accumulators; if the list overflowed its buffer: the bbox walk again, scatter_warp<SOFT_BWD>), the rest redo
 //                 the truncated pixels and scatter the gradients of exactly those knum candidates.
 //   Backward re-derives every probability from the face records instead of storing Kaolin's knum-deep side buffers
@@ -63,49 +64,6 @@ __device__ __forceinline__ FaceRec slot_rec(const WarpQ& wq, int slot) {
     return r;
 }
 
-// one (pixel, face) candidate's contribution to the face's 6 corner gradients (DIBR_SPEC A.5, fast tail)
-__device__ __forceinline__ void soft_pair_grad(const mm_raster_params& p, const FaceRec& r, float px, float py, float kz,
-                                               float inv_mult, float g_soft, float one_m_all, float (&ga)[6])
-{
-    int type;
-    const float d2s = soft_d2_fast(r, px, py, p.multiplier, type);
-    const float prob = soft_prob_fast(d2s, kz);
-    // dLdz = -sigmainv * dLdp * (1-allprob) / (1-prob+1e-6) * prob
-    const float dLdz = __fdividef(-p.sigmainv * g_soft * one_m_all, (1.0f - prob) + 1e-6f) * prob * inv_mult;
-    float v[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    if (type >= 3) {
-        const int i = type - 3;
-        const float x1 = (i == 0) ? r.ax : ((i == 1) ? r.bx : r.cx);
-        const float y1 = (i == 0) ? r.ay : ((i == 1) ? r.by : r.cy);
-        const float gx = dLdz * 2.0f * (x1 - px), gy = dLdz * 2.0f * (y1 - py);
-        #pragma unroll
-        for (int k = 0; k < 3; ++k) { v[2 * k] = (i == k) ? gx : 0.0f; v[2 * k + 1] = (i == k) ? gy : 0.0f; }
-    } else {
-        const int i = type, j = (type == 2) ? 0 : type + 1;
-        const float x1 = (i == 0) ? r.ax : ((i == 1) ? r.bx : r.cx);
-        const float y1 = (i == 0) ? r.ay : ((i == 1) ? r.by : r.cy);
-        const float x2 = (j == 0) ? r.ax : ((j == 1) ? r.bx : r.cx);
-        const float y2 = (j == 0) ? r.ay : ((j == 1) ? r.by : r.cy);
-        const float A = SUB(y2, y1), Bc = SUB(x1, x2), C = SUB(MUL(x2, y1), MUL(x1, y2));
-        const float up = ADD(ADD(MUL(A, px), MUL(Bc, py)), C);
-        const float rdn = __fdividef(1.0f, ADD(ADD(MUL(A, A), MUL(Bc, Bc)), 1e-10f));
-        const float d2 = up * up * rdn;
-        const float dzdA = 2.0f * (px * up - d2 * A) * rdn;
-        const float dzdB = 2.0f * (py * up - d2 * Bc) * rdn;
-        const float dzdC = 2.0f * up * rdn;
-        const float g1x = dLdz * (dzdB - y2 * dzdC), g1y = dLdz * (x2 * dzdC - dzdA);
-        const float g2x = dLdz * (y1 * dzdC - dzdB), g2y = dLdz * (dzdA - x1 * dzdC);
-        #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            v[2 * k] = (i == k) ? g1x : ((j == k) ? g2x : 0.0f);
-            v[2 * k + 1] = (i == k) ? g1y : ((j == k) ? g2y : 0.0f);
-        }
-    }
-    #pragma unroll
-    for (int k = 0; k < 6; ++k) ga[k] += v[k];
-}
-
-
 // one queued pair, evaluated by one lane (no warp collectives in here: the tail of the queue runs divergent)
 template <int MODE>
 __device__ __forceinline__ void eval_pair(const mm_raster_params& p, WarpQ& wq, uint32_t e, float kz, float inv_mult)
@@ -124,7 +82,7 @@ __device__ __forceinline__ void eval_pair(const mm_raster_params& p, WarpQ& wq, 
         atomicOr(p.cov + ((size_t)b * p.H + iy) * p.covw + (ix >> 5), 1u << (ix & 31));
     } else {
         const float g = gsoft_at(p, b, pix);
-        const float soft = p.rgba[(size_t)b * 4 * HW + 3 * HW + pix];
+        const float soft = lacc_soft(p.lacc[(size_t)b * HW + pix]);      // (candidates are uncovered pixels)
         if (g == 0.0f || !(soft > 0.0f)) return;
         float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
         soft_pair_grad(p, r, px, py, kz, inv_mult, g, 1.0f - soft, ga);
@@ -251,7 +209,9 @@ k_scatter_hard(const mm_raster_params p)
     }
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (p.B * p.F + FPW - 1) / FPW;
+    MM_PROF_MARK(p.prof, 1, gwarp, 0);
     if (gwarp < nwarps) scatter_warp<MODE_HARD>(p, s_wq[threadIdx.x >> 5], gwarp, nwarps);
+    MM_PROF_MARK(p.prof, 1, gwarp, 2);
 }
 
 // ---------------------------------------------------------------------------------------------- soft pass forward
@@ -262,7 +222,9 @@ k_soft_fwd(const mm_raster_params p)
     mm_pdl_prologue((p.pdl_late & 2) != 0);
     __shared__ SoftQ s_wq[SF_WARPS];
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    MM_PROF_MARK(p.prof, 2, gwarp, 0);
     soft_fwd_role(p, s_wq[threadIdx.x >> 5], gwarp);
+    MM_PROF_MARK(p.prof, 2, gwarp, 2);
 }
 
 // ---------------------------------------------------------------------------------------------- soft pass backward, list-driven
@@ -297,8 +259,11 @@ __device__ __forceinline__ void soft_bwd_list_role(const mm_raster_params& p, Wa
             const int b = (int)(fg / (uint32_t)p.F);
             const size_t pg = (size_t)b * HW + (size_t)iy * p.W + ix;
             const float g = gsoft_at(p, b, (size_t)iy * p.W + ix);
-            const float soft = p.rgba[(size_t)b * 4 * HW + 3 * HW + (size_t)iy * p.W + ix];
-            if (g != 0.0f && soft > 0.0f && lacc_count(p.lacc[pg]) != (int)MM_LACC_OVF) {
+            // the silhouette value comes from the workspace's accumulator (bit-identical to the image's alpha plane, which the
+            // backward therefore does not need: the caller may have edited the image in place)
+            const unsigned long long acc = p.lacc[pg];
+            const float soft = lacc_soft(acc);
+            if (g != 0.0f && soft > 0.0f && lacc_count(acc) != (int)MM_LACC_OVF) {
                 const float4* q4 = reinterpret_cast<const float4*>(p.frec) + (size_t)fg * 3;
                 const float4 c0 = __ldg(q4), c1 = __ldg(q4 + 1);
                 FaceRec r;
@@ -314,144 +279,49 @@ __device__ __forceinline__ void soft_bwd_list_role(const mm_raster_params& p, Wa
     }
 }
 
-// ---------------------------------------------------------------------------------------------- overflow (ordered) pass
-// DIB-R keeps only the FIRST knum candidates in face-index order (DIBR_SPEC A.4).  Pixels that saw more are re-done
-// here literally.  One CTA per overflowed pixel:
-//   phase 1  all F enlarged-bbox tests in ONE memory round trip (each thread owns F/128 faces, loads issued back to back);
-//            the per-warp ballots land in shared memory as hit words in face order.
-//   phase 2  warp 0 keeps the first knum set bits (running count over the words) and writes the kept faces, in order, to a
-//            shared list; then -- still warp 0, no further block barrier -- lane k evaluates candidate k, and the ordered
-//            product (forward) is folded with shuffles exactly in the reference's order; backward: lane k scatters the
-//            gradient of candidate k.
-// A handful of pixels per step take this path (far cameras), so the kernel is pure latency: launch + ~2 round trips.
-#define OVF_THREADS 128
-#define OVF_MAX_WORDS 2048          // F <= 65535
-#define OVF_UNROLL 5
-
-template <bool BWD>
-__device__ __forceinline__ void soft_ovf_role(const mm_raster_params& p, uint32_t* s_mask, int* s_kept, const int vblock, const int nvblocks)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t n = p.ovf_count[0];
-    const size_t HW = (size_t)p.H * p.W;
-    const float kz = p.sigmainv / p.multiplier / p.multiplier;
-    const float inv_mult = 1.0f / p.multiplier;
-    const int nw = (p.F + 31) >> 5;
-    const int niter = (p.F + OVF_THREADS - 1) / OVF_THREADS;              // faces per thread
-    for (uint32_t e = (uint32_t)vblock; e < n; e += (uint32_t)nvblocks) {
-        const uint32_t pg = p.ovf_list[e];
-        const int b = (int)(pg / HW);
-        const int pix = (int)(pg - (size_t)b * HW);
-        const int iy = pix / p.W, ix = pix - iy * p.W;
-        const float px = pix_x(ix, p.W, p.sx), py = pix_y(iy, p.H, p.sy);
-        const float4* rec4 = reinterpret_cast<const float4*>(p.frec + (size_t)b * p.F * MM_REC_FLOATS);
-        float g = 0.0f, one_m_all = 0.0f;
-        if (BWD) {
-            g = gsoft_at(p, b, (size_t)pix);
-            const float soft = p.rgba[(size_t)b * 4 * HW + 3 * HW + pix];
-            one_m_all = 1.0f - soft;
-            if (g == 0.0f || !(soft > 0.0f)) continue;          // block-uniform
-        }
-        // ---- phase 1: enlarged-bbox hit words, face order (word = f >> 5); OVF_UNROLL independent record loads in flight
-        for (int j0 = 0; j0 < niter; j0 += OVF_UNROLL) {
-            float4 c0[OVF_UNROLL], c1[OVF_UNROLL];
-            #pragma unroll
-            for (int u = 0; u < OVF_UNROLL; ++u) {
-                const int f = (j0 + u) * OVF_THREADS + threadIdx.x;
-                if (j0 + u < niter && f < p.F) { c0[u] = __ldg(rec4 + (size_t)f * 3); c1[u] = __ldg(rec4 + (size_t)f * 3 + 1); }
-                else { c0[u] = make_float4(0.f, 0.f, 0.f, 0.f); c1[u] = c0[u]; }
-            }
-            #pragma unroll
-            for (int u = 0; u < OVF_UNROLL; ++u) {
-                const int j = j0 + u;
-                const int f = j * OVF_THREADS + threadIdx.x;
-                bool hit = false;
-                if (j < niter && f < p.F) {
-                    FaceRec r;
-                    r.ax = c0[u].x; r.ay = c0[u].y; r.bx = c0[u].z; r.by = c0[u].w; r.cx = c1[u].x; r.cy = c1[u].y;
-                    r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
-                    hit = soft_bbox_test(r, px, py, p.blen);
-                }
-                const uint32_t m = __ballot_sync(FULL, hit);
-                const int word = j * (OVF_THREADS / 32) + warp;
-                if (lane == 0 && j < niter && word < nw) s_mask[word] = m;
-            }
-        }
-        __syncthreads();
-        // ---- phase 2 (warp 0): first knum set bits over all words -> ordered list of kept faces
-        if (warp == 0) {
-            int seen = 0;
-            for (int w0 = 0; w0 < nw && seen < p.knum; w0 += 32) {
-                const int wd = w0 + lane;
-                uint32_t m = (wd < nw) ? s_mask[wd] : 0u;
-                const int c = __popc(m);
-                int incl = c;
-                #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-                int pos = seen + incl - c;                       // candidates before this word
-                while (m && pos < p.knum) {                       // this word's bits, in face order
-                    const int bit = __ffs(m) - 1;
-                    m &= m - 1u;
-                    s_kept[pos++] = (wd << 5) + bit;
-                }
-                seen += __shfl_sync(FULL, incl, 31);
-            }
-            const int nk = min(seen, p.knum);
-            __syncwarp();
-            // ---- the kept candidates, one per lane (knum <= 64: two rounds at most)
-            float allprob = 1.0f;
-            for (int k0 = 0; k0 < nk; k0 += 32) {
-                const int k = k0 + lane;
-                const bool mine = k < nk;
-                const int f = mine ? s_kept[k] : 0;
-                FaceRec r;
-                {
-                    const float4 c0 = __ldg(rec4 + (size_t)f * 3), c1 = __ldg(rec4 + (size_t)f * 3 + 1);
-                    r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
-                    r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
-                }
-                if (BWD) {
-                    if (mine) {
-                        float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-                        soft_pair_grad(p, r, px, py, kz, inv_mult, g, one_m_all, ga);
-                        red_add_corners(p.gfacc + ((size_t)b * p.F + f) * MM_GF, ga);
-                    }
-                } else {
-                    float prob = 0.0f;
-                    if (mine) { int type; prob = soft_prob_fast(soft_d2_fast(r, px, py, p.multiplier, type), kz); }
-                    const int cnt = min(32, nk - k0);
-                    #pragma unroll 1
-                    for (int q = 0; q < cnt; ++q)                // the reference's ordered product
-                        allprob = allprob * (1.0f - __shfl_sync(FULL, prob, q));
-                }
-            }
-            if (!BWD && lane == 0) p.lacc[pg] = lacc_exact(allprob > 0.0f ? logf(allprob) : -2400.0f);
-        }
-        __syncthreads();
-    }
-}
-
-// forward: the overflow pass alone
-__global__ void __launch_bounds__(OVF_THREADS)
-k_soft_ovf_fwd(const mm_raster_params p)
-{
-    mm_pdl_prologue((p.pdl_late & 4) != 0);
-    __shared__ uint32_t s_mask[OVF_MAX_WORDS];
-    __shared__ int s_kept[MM_MAX_KNUM];
-    soft_ovf_role<false>(p, s_mask, s_kept, blockIdx.x, gridDim.x);
-}
-
-// backward: ONE launch for the two independent halves of the soft-silhouette backward -- the first `nlist` CTAs replay the
+// backward: ONE launch for the two independent halves of the soft-silhouette backward -- the CTAs from `novf` on replay the
 // pair list, the rest redo the truncated pixels (both only add into the per-face accumulators)
 __global__ void __launch_bounds__(SB_THREADS)
-k_soft_bwd(const mm_raster_params p, const int nlist)
+k_soft_bwd(const mm_raster_params p, const int novf)
 {
     mm_pdl_prologue((p.pdl_late & 16) != 0);
     __shared__ WarpQ s_wq[SB_THREADS / 32];
     __shared__ uint32_t s_mask[OVF_MAX_WORDS];
     __shared__ int s_kept[MM_MAX_KNUM];
-    if ((int)blockIdx.x < nlist) soft_bwd_list_role(p, s_wq, blockIdx.x, nlist);
-    else                         soft_ovf_role<true>(p, s_mask, s_kept, blockIdx.x - nlist, gridDim.x - nlist);
+    MM_PROF_MARK(p.prof, 4, blockIdx.x * (SB_THREADS / 32) + (threadIdx.x >> 5), 0);
+    // (the truncated pixels come FIRST in the grid: each costs a CTA ~3 us of pure latency, so they start at once and the
+    // list CTAs fill in behind them; the other way round they were the kernel's tail, profiles/r2_notes.md)
+    if ((int)blockIdx.x >= novf) {
+        soft_bwd_list_role(p, s_wq, blockIdx.x - novf, gridDim.x - novf);
+        MM_PROF_MARK(p.prof, 4, blockIdx.x * (SB_THREADS / 32) + (threadIdx.x >> 5), 2);
+        return;
+    }
+    // images with truncated pixels: the CTA fetches the counts of SB_THREADS images per round trip and lists the few that have
+    // any (usually none: one barrier and out); entries are dealt from a per-image rotated start so that one entry per image
+    // does not always land on the same CTA
+    const int vblock = blockIdx.x, nvblocks = novf;
+    __shared__ int s_img[SB_THREADS], s_rot[SB_THREADS];
+    __shared__ uint32_t s_cnt[SB_THREADS];
+    __shared__ int s_n;
+    for (int b0 = 0; b0 < p.B; b0 += SB_THREADS) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const uint32_t cnt = (b0 + (int)threadIdx.x < p.B) ? p.ovf_cnt[b0 + threadIdx.x] : 0u;
+        if (cnt) {                                              // (the rotation's modulo: once per listed image, not per CTA and image)
+            const int k = atomicAdd(&s_n, 1);
+            s_img[k] = b0 + threadIdx.x; s_cnt[k] = cnt; s_rot[k] = ((b0 + (int)threadIdx.x) * 61) % nvblocks;
+        }
+        __syncthreads();
+        MM_PROF_MARK(p.prof, 4, blockIdx.x * (SB_THREADS / 32) + (threadIdx.x >> 5), 1);
+        const int n = s_n;                                      // (block-uniform from here on)
+        for (int i = 0; i < n; ++i) {
+            int first = vblock + s_rot[i];
+            if (first >= nvblocks) first -= nvblocks;
+            if ((uint32_t)first < s_cnt[i]) soft_ovf_role<true>(p, s_mask, s_kept, s_img[i], s_cnt[i], first, nvblocks);
+        }
+        __syncthreads();
+    }
+    MM_PROF_MARK(p.prof, 4, blockIdx.x * (SB_THREADS / 32) + (threadIdx.x >> 5), 2);
 }
 
 }  // namespace
@@ -463,15 +333,13 @@ cudaError_t mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaS
     cudaError_t e = mm_launch(k_scatter_hard, dim3((warps + 7) / 8), dim3(256), 0, s, pdl, p);
     if (e != cudaSuccess) return e;
     const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW;
-    e = mm_launch(k_soft_fwd, dim3((nw + SF_WARPS - 1) / SF_WARPS), dim3(32 * SF_WARPS), 0, s, pdl, p);
-    if (e != cudaSuccess) return e;
-    return mm_launch(k_soft_ovf_fwd, dim3(c->num_sms * 16), dim3(OVF_THREADS), 0, s, pdl, p);
+    return mm_launch(k_soft_fwd, dim3((nw + SF_WARPS - 1) / SF_WARPS), dim3(32 * SF_WARPS), 0, s, pdl, p);
 }
 
 cudaError_t mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
     static_assert(SB_THREADS == OVF_THREADS, "the merged backward kernel runs both roles with one CTA shape");
     const int nlist = c->num_sms * 16, novf = c->num_sms * 8;
-    return mm_launch(k_soft_bwd, dim3(nlist + novf), dim3(SB_THREADS), 0, s, c->pdl != 0, p, nlist);
+    return mm_launch(k_soft_bwd, dim3(nlist + novf), dim3(SB_THREADS), 0, s, c->pdl != 0, p, novf);
 }
 

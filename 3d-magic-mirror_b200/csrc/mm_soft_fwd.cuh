@@ -81,8 +81,9 @@ __device__ __forceinline__ void soft_fwd_eval(const mm_raster_params& p, const S
     const float prob = soft_prob_fast(d2, kz);
     const unsigned long long old = atomicAdd(p.lacc + pg, lacc_term(log1pf(-prob)));
     if (lacc_count(old) == p.knum) {                            // candidate knum+1: the pixel needs the ordered pass
-        const uint32_t s2 = atomicAdd(p.ovf_count, 1u);
-        p.ovf_list[s2] = (uint32_t)pg;
+        const int b = wq.img[slot];
+        const uint32_t s2 = atomicAdd(p.ovf_cnt + b, 1u);
+        p.ovf_list[(size_t)b * p.H * p.W + s2] = (uint32_t)(iy * p.W + ix);
     }
 }
 
@@ -181,6 +182,169 @@ __device__ __forceinline__ void soft_fwd_role(const mm_raster_params& p, SoftQ& 
         const uint32_t e = lane < qn ? wq.q[lane] : 0u;
         if (lane < qn) soft_fwd_eval(p, wq, e, kz);
         soft_fwd_record(p, wq, e, qn, lane);
+    }
+}
+
+// one (pixel, face) candidate's contribution to the face's 6 corner gradients (DIBR_SPEC A.5, fast tail)
+__device__ __forceinline__ void soft_pair_grad(const mm_raster_params& p, const FaceRec& r, float px, float py, float kz,
+                                               float inv_mult, float g_soft, float one_m_all, float (&ga)[6])
+{
+    int type;
+    const float d2s = soft_d2_fast(r, px, py, p.multiplier, type);
+    const float prob = soft_prob_fast(d2s, kz);
+    // dLdz = -sigmainv * dLdp * (1-allprob) / (1-prob+1e-6) * prob
+    const float dLdz = __fdividef(-p.sigmainv * g_soft * one_m_all, (1.0f - prob) + 1e-6f) * prob * inv_mult;
+    float v[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (type >= 3) {
+        const int i = type - 3;
+        const float x1 = (i == 0) ? r.ax : ((i == 1) ? r.bx : r.cx);
+        const float y1 = (i == 0) ? r.ay : ((i == 1) ? r.by : r.cy);
+        const float gx = dLdz * 2.0f * (x1 - px), gy = dLdz * 2.0f * (y1 - py);
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) { v[2 * k] = (i == k) ? gx : 0.0f; v[2 * k + 1] = (i == k) ? gy : 0.0f; }
+    } else {
+        const int i = type, j = (type == 2) ? 0 : type + 1;
+        const float x1 = (i == 0) ? r.ax : ((i == 1) ? r.bx : r.cx);
+        const float y1 = (i == 0) ? r.ay : ((i == 1) ? r.by : r.cy);
+        const float x2 = (j == 0) ? r.ax : ((j == 1) ? r.bx : r.cx);
+        const float y2 = (j == 0) ? r.ay : ((j == 1) ? r.by : r.cy);
+        const float A = SUB(y2, y1), Bc = SUB(x1, x2), C = SUB(MUL(x2, y1), MUL(x1, y2));
+        const float up = ADD(ADD(MUL(A, px), MUL(Bc, py)), C);
+        const float rdn = __fdividef(1.0f, ADD(ADD(MUL(A, A), MUL(Bc, Bc)), 1e-10f));
+        const float d2 = up * up * rdn;
+        const float dzdA = 2.0f * (px * up - d2 * A) * rdn;
+        const float dzdB = 2.0f * (py * up - d2 * Bc) * rdn;
+        const float dzdC = 2.0f * up * rdn;
+        const float g1x = dLdz * (dzdB - y2 * dzdC), g1y = dLdz * (x2 * dzdC - dzdA);
+        const float g2x = dLdz * (y1 * dzdC - dzdB), g2y = dLdz * (dzdA - x1 * dzdC);
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[2 * k] = (i == k) ? g1x : ((j == k) ? g2x : 0.0f);
+            v[2 * k + 1] = (i == k) ? g1y : ((j == k) ? g2y : 0.0f);
+        }
+    }
+    #pragma unroll
+    for (int k = 0; k < 6; ++k) ga[k] += v[k];
+}
+
+
+
+// ---------------------------------------------------------------------------------------------- overflow (ordered) pass
+// DIB-R keeps only the FIRST knum candidates in face-index order (DIBR_SPEC A.4).  Pixels that saw more are re-done
+// here literally.  One CTA per overflowed pixel:
+//   phase 1  all F enlarged-bbox tests in ONE memory round trip (each thread owns F/128 faces, loads issued back to back);
+//            the per-warp ballots land in shared memory as hit words in face order.
+//   phase 2  warp 0 keeps the first knum set bits (running count over the words) and writes the kept faces, in order, to a
+//            shared list; then -- still warp 0, no further block barrier -- lane k evaluates candidate k, and the ordered
+//            product (forward) is folded with shuffles exactly in the reference's order; backward: lane k scatters the
+//            gradient of candidate k.
+// A handful of pixels per step take this path (far cameras): pure latency, ~2 round trips per pixel.  Forward: run by the
+// shading kernel's CTAs (mm_fused.cu); backward: by the tail CTAs of k_soft_bwd.
+#define OVF_THREADS 128
+#define OVF_MAX_WORDS 2048          // F <= 65535
+#define OVF_UNROLL 5
+
+// (this CTA takes entries first, first + stride, .. of the `count` entries of image b's list)
+template <bool BWD>
+__device__ __forceinline__ void soft_ovf_role(const mm_raster_params& p, uint32_t* s_mask, int* s_kept, const int b,
+                                              const uint32_t count, const int first, const int stride)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t HW = (size_t)p.H * p.W;
+    const uint32_t n = min(count, (uint32_t)HW);
+    const float kz = p.sigmainv / p.multiplier / p.multiplier;
+    const float inv_mult = 1.0f / p.multiplier;
+    const int nw = (p.F + 31) >> 5;
+    const int niter = (p.F + OVF_THREADS - 1) / OVF_THREADS;              // faces per thread
+    for (uint32_t e = (uint32_t)first; e < n; e += (uint32_t)stride) {
+        const int pix = (int)p.ovf_list[(size_t)b * HW + e];
+        const size_t pg = (size_t)b * HW + pix;
+        const int iy = pix / p.W, ix = pix - iy * p.W;
+        const float px = pix_x(ix, p.W, p.sx), py = pix_y(iy, p.H, p.sy);
+        const float4* rec4 = reinterpret_cast<const float4*>(p.frec + (size_t)b * p.F * MM_REC_FLOATS);
+        float g = 0.0f, one_m_all = 0.0f;
+        if (BWD) {
+            g = gsoft_at(p, b, (size_t)pix);
+            const float soft = lacc_soft(p.lacc[pg]);           // (the exact word stored by the forward)
+            one_m_all = 1.0f - soft;
+            if (g == 0.0f || !(soft > 0.0f)) continue;          // block-uniform
+        }
+        // ---- phase 1: enlarged-bbox hit words, face order (word = f >> 5); OVF_UNROLL independent record loads in flight
+        for (int j0 = 0; j0 < niter; j0 += OVF_UNROLL) {
+            float4 c0[OVF_UNROLL], c1[OVF_UNROLL];
+            #pragma unroll
+            for (int u = 0; u < OVF_UNROLL; ++u) {
+                const int f = (j0 + u) * OVF_THREADS + threadIdx.x;
+                if (j0 + u < niter && f < p.F) { c0[u] = __ldg(rec4 + (size_t)f * 3); c1[u] = __ldg(rec4 + (size_t)f * 3 + 1); }
+                else { c0[u] = make_float4(0.f, 0.f, 0.f, 0.f); c1[u] = c0[u]; }
+            }
+            #pragma unroll
+            for (int u = 0; u < OVF_UNROLL; ++u) {
+                const int j = j0 + u;
+                const int f = j * OVF_THREADS + threadIdx.x;
+                bool hit = false;
+                if (j < niter && f < p.F) {
+                    FaceRec r;
+                    r.ax = c0[u].x; r.ay = c0[u].y; r.bx = c0[u].z; r.by = c0[u].w; r.cx = c1[u].x; r.cy = c1[u].y;
+                    r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
+                    hit = soft_bbox_test(r, px, py, p.blen);
+                }
+                const uint32_t m = __ballot_sync(FULL, hit);
+                const int word = j * (OVF_THREADS / 32) + warp;
+                if (lane == 0 && j < niter && word < nw) s_mask[word] = m;
+            }
+        }
+        __syncthreads();
+        // ---- phase 2 (warp 0): first knum set bits over all words -> ordered list of kept faces
+        if (warp == 0) {
+            int seen = 0;
+            for (int w0 = 0; w0 < nw && seen < p.knum; w0 += 32) {
+                const int wd = w0 + lane;
+                uint32_t m = (wd < nw) ? s_mask[wd] : 0u;
+                const int c = __popc(m);
+                int incl = c;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+                int pos = seen + incl - c;                       // candidates before this word
+                while (m && pos < p.knum) {                       // this word's bits, in face order
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1u;
+                    s_kept[pos++] = (wd << 5) + bit;
+                }
+                seen += __shfl_sync(FULL, incl, 31);
+            }
+            const int nk = min(seen, p.knum);
+            __syncwarp();
+            // ---- the kept candidates, one per lane (knum <= 64: two rounds at most)
+            float allprob = 1.0f;
+            for (int k0 = 0; k0 < nk; k0 += 32) {
+                const int k = k0 + lane;
+                const bool mine = k < nk;
+                const int f = mine ? s_kept[k] : 0;
+                FaceRec r;
+                {
+                    const float4 c0 = __ldg(rec4 + (size_t)f * 3), c1 = __ldg(rec4 + (size_t)f * 3 + 1);
+                    r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
+                    r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
+                }
+                if (BWD) {
+                    if (mine) {
+                        float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+                        soft_pair_grad(p, r, px, py, kz, inv_mult, g, one_m_all, ga);
+                        red_add_corners(p.gfacc + ((size_t)b * p.F + f) * MM_GF, ga);
+                    }
+                } else {
+                    float prob = 0.0f;
+                    if (mine) { int type; prob = soft_prob_fast(soft_d2_fast(r, px, py, p.multiplier, type), kz); }
+                    const int cnt = min(32, nk - k0);
+                    #pragma unroll 1
+                    for (int q = 0; q < cnt; ++q)                // the reference's ordered product
+                        allprob = allprob * (1.0f - __shfl_sync(FULL, prob, q));
+                }
+            }
+            if (!BWD && lane == 0) p.lacc[pg] = lacc_exact(allprob > 0.0f ? logf(allprob) : -2400.0f);
+        }
+        __syncthreads();
     }
 }
 

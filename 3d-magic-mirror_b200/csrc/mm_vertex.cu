@@ -31,6 +31,7 @@ struct VertexFwdParams {
     // latency-bound camera / vertex work.
     uint4* clr0; size_t n0;
     uint4* clr1; size_t n1;
+    unsigned long long* prof;
 };
 
 __global__ void __launch_bounds__(MM_VTHREADS)
@@ -52,6 +53,7 @@ k_vertex_fwd(const VertexFwdParams q,
     float* svc = sm + 16;              // V*3 camera-space
     float* svi = svc + (size_t)V * 3;  // V*2 image-plane (unscaled)
     const int chunk = blockIdx.x, b = blockIdx.y;
+    MM_PROF_MARK(q.prof, 0, (b * gridDim.x + chunk) * (MM_VTHREADS / 32) + (threadIdx.x >> 5), 0);
     {
         const size_t nthreads = (size_t)gridDim.x * gridDim.y * blockDim.x;
         const size_t t = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
@@ -105,6 +107,7 @@ k_vertex_fwd(const VertexFwdParams q,
             g[0] = g[1] = g[2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
     }
+    MM_PROF_MARK(q.prof, 0, (b * gridDim.x + chunk) * (MM_VTHREADS / 32) + (threadIdx.x >> 5), 2);
 }
 
 // ------------------------------------------------------------------ backward
@@ -128,6 +131,7 @@ struct VertexBwdParams {
     float* loss;
     const long long* img_fwd;
     float image_weight, contour;
+    unsigned long long* prof;
 };
 
 __device__ __forceinline__ float fxv(const long long* a, double scale) { return (float)((double)(*a) / scale); }
@@ -147,6 +151,7 @@ k_vertex_bwd(const VertexBwdParams q,
     // the camera chain, 642 transforms) runs while the previous kernel (k_soft_bwd) is still draining; the wait sits right in
     // front of the first read of what that kernel produced (gfacc, img_bwd).
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    MM_PROF_MARK(q.prof, 5, (blockIdx.y * gridDim.x + blockIdx.x) * VB_WARPS + (threadIdx.x >> 5), 0);
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ float sm[];
@@ -171,6 +176,7 @@ k_vertex_bwd(const VertexBwdParams q,
     }
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    MM_PROF_MARK(q.prof, 5, (blockIdx.y * gridDim.x + blockIdx.x) * VB_WARPS + (threadIdx.x >> 5), 1);
     const int fper = (F + VB_CLUSTER - 1) / VB_CLUSTER;
     const int f_end = min(F, (rank + 1) * fper);
     for (int f = rank * fper + threadIdx.x; f < f_end; f += blockDim.x) {
@@ -350,6 +356,7 @@ k_vertex_bwd(const VertexBwdParams q,
             q.loss[3] = l_cont;
         }
     }
+    MM_PROF_MARK(q.prof, 5, (blockIdx.y * gridDim.x + blockIdx.x) * VB_WARPS + (threadIdx.x >> 5), 2);
 }
 
 __global__ void k_export_faces(int V, int F, float multiplier, const int32_t* __restrict__ faces,
@@ -379,7 +386,7 @@ cudaError_t mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, 
                           void* clr0, size_t bytes0, void* clr1, size_t bytes1, cudaStream_t s)
 {
     VertexFwdParams q;
-    q.clr0 = (uint4*)clr0; q.n0 = bytes0 / 16; q.clr1 = (uint4*)clr1; q.n1 = bytes1 / 16;
+    q.clr0 = (uint4*)clr0; q.n0 = bytes0 / 16; q.clr1 = (uint4*)clr1; q.n1 = bytes1 / 16; q.prof = c->prof;
     q.V = c->V; q.F = c->F; q.nchunks = c->nchunks;
     q.proj_x = c->proj_x; q.proj_y = c->proj_y; q.multiplier = c->multiplier;
     const dim3 grid(c->nchunks, B);
@@ -398,7 +405,7 @@ cudaError_t mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, 
     const size_t smem = ((size_t)c->V * 6) * sizeof(float);
     VertexBwdParams q;
     q.B = B; q.V = c->V; q.F = c->F; q.H = c->H; q.W = c->W; q.proj_x = c->proj_x; q.proj_y = c->proj_y;
-    q.loss = loss; q.img_fwd = img_fwd; q.image_weight = image_weight; q.contour = contour;
+    q.loss = loss; q.img_fwd = img_fwd; q.image_weight = image_weight; q.contour = contour; q.prof = c->prof;
     return mm_launch(k_vertex_bwd, dim3(VB_CLUSTER, B), dim3(VB_THREADS), smem, s, c->pdl != 0, q,
               (const int32_t*)c->d_faces, vertices, azim, elev, dist, bias, gfacc, g_face_normals, img_bwd, g_vertices,
               g_azim, g_elev, g_dist, g_bias, g_lights);

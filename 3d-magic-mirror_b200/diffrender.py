@@ -210,8 +210,10 @@ class _RenderFn(torch.autograd.Function):
         ctx.dr, ctx.no_mask, ctx.h, ctx.tex_mirror, ctx.rec = dr, bool(no_mask), h, bool(tex_mirror), rec
         ctx._mm_token = rec.token
         ctx.has_bg = bg is not None
+        # (the image itself is NOT saved: the backward reads the silhouette from the workspace, so the caller may edit the
+        # returned image in place, as it may with the reference's torch ops)
         ctx.save_for_backward(vertices, azim, elev, dist, biases, textures, lights,
-                              bg if bg is not None else torch.empty(0, device=dev), rgba)
+                              bg if bg is not None else torch.empty(0, device=dev))
         ctx.mark_non_differentiable(imn)
         if fidx is None:
             fidx = torch.empty(0, device=dev, dtype=torch.int32)
@@ -221,7 +223,7 @@ class _RenderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_rgba, g_fn, _g_imn, _g_fidx):
-        vertices, azim, elev, dist, biases, textures, lights, bg, rgba = ctx.saved_tensors
+        vertices, azim, elev, dist, biases, textures, lights, bg = ctx.saved_tensors
         h, rec = ctx.h, ctx.rec
         dev = vertices.device
         B = azim.shape[0]
@@ -241,7 +243,7 @@ class _RenderFn(torch.autograd.Function):
             g_bg = torch.empty_like(bg_t) if bg_t is not None else None
             rc = _lib.lib().mm_render_backward(h.handle, B, _ptr(vertices), _ptr(azim), _ptr(elev), _ptr(dist),
                                                _ptr(biases), _ptr(textures), Ht, Wt, 1 if ctx.tex_mirror else 0,
-                                               _ptr(lights), _ptr(bg_t), 1 if ctx.no_mask else 0, _ptr(rgba),
+                                               _ptr(lights), _ptr(bg_t), 1 if ctx.no_mask else 0, _ptr(None),
                                                _ptr(g_rgba), _ptr(g_fn), _ptr(gt), iw, contour, 1.0, _ptr(g_loss),
                                                _ptr(g_v), _ptr(g_az), _ptr(g_el), _ptr(g_di), _ptr(g_bi),
                                                _ptr(g_tex), _ptr(g_li), _ptr(g_bg), _ptr(rec.ws), rec.ws.numel(), _stream())

@@ -29,8 +29,8 @@ NSETS = 4                     # rotating input/output sets: 4 x ~137 MB > 126 MB
 # events switches programmatic dependent launch off across them, so these figures are a little above what the same
 # kernels cost inside the timed step; they are used for the roofline of the dominant kernel only.
 KERNELS = ["vertex_fwd", "geom_fwd", "shade_fused", "gsoft", "geom_bwd", "vertex_bwd", "tail"]
-# kernels of one fused step (mm_ctx_get_int "fused_kernels"): k_raster_band (or k_vertex_fwd, k_scatter_hard, k_soft_fwd,
-# k_soft_ovf_fwd), k_shade<fused>, k_soft_bwd (pair list + truncated pixels), k_vertex_bwd (which also finalises the loss);
+# kernels of one fused step (mm_ctx_get_int "fused_kernels"): k_vertex_fwd, k_scatter_hard, k_soft_fwd, k_shade<fused> (which
+# also re-does the truncated pixels), k_soft_bwd (truncated pixels + pair list), k_vertex_bwd (which also finalises the loss);
 # k_gsoft only runs for H or W not a multiple of 4
 
 def algorithmic_bytes(B, V, F, H, W, Ht, Wt, bg=True, extra=False):

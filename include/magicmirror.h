@@ -111,7 +111,8 @@ int mm_render_backward(mm_ctx* ctx, int B,
                        const float* vertices, const float* azim, const float* elev, const float* dist,
                        const float* bias, const float* tex, int Ht, int Wt, int tex_mirror, const float* lights,
                        const float* bg, int no_mask,
-                       const float* rgba /* forward output */,
+                       const float* rgba /* unused, may be NULL: the backward reads the silhouette from the workspace, so the
+                                            caller is free to edit the image in place after the forward */,
                        const float* g_rgba, const float* g_face_normals,
                        const float* recon_gt, float image_weight, float contour, float loss_scale,
                        const float* loss_scale_dev,
@@ -139,7 +140,7 @@ int mm_recon_data_backward(mm_ctx* ctx, int B, const float* pred, const float* g
  *   gt            [B,4,H,W]
  *   g_rgba_extra  [B,4,H,W] or NULL  (upstream gradient from another consumer, e.g. the GAN)
  *   g_face_normals [B,F,3] or NULL   (upstream gradient of face_normals, e.g. from calc_reg_loss, networks.py:422)
- *   rgba          [B,4,H,W] out (required: the backward pass re-reads the silhouette)
+ *   rgba          [B,4,H,W] out
  *   loss          [4] out, as mm_recon_data_forward */
 int mm_render_compare_fwd_bwd(mm_ctx* ctx, int B,
                               const float* vertices, const float* azim, const float* elev, const float* dist,

@@ -1,0 +1,69 @@
+"""Per-warp timeline of one fused step (GPU box; needs the MM_PROF build: tools/probes/build_prof.sh).
+Every warp of the six kernels stamps %globaltimer at entry (0), once its dependencies are satisfied (1, where the kernel has
+such a point) and at exit (2).  Prints, per kernel: when its warps started / became ready / ended relative to the step's first
+stamp, how long they ran, and how many warps of each kernel were alive at every 5 us tick.
+usage: [MM_FLOW=0|1] [MM_MIXED=0|1] python tools/probes/timeline.py [reps]"""
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+import __graft_entry__ as g
+import bench
+mm = g.load_package()
+from magic_mirror_b200 import _lib
+_lib.LIB_PATH = os.path.join(g.PKG_DIR, "libmagicmirror_prof.so")
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+dev = "cuda:0"
+dr, sets = bench.build_workload(mm, dev, 0)
+fr = bench.FusedRunner(mm, dr, sets, dev)
+L = mm.lib()
+L.mm_debug_profile.restype = ctypes.c_int
+L.mm_debug_profile.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+NK, NW = 6, 16384
+prof = torch.zeros(NK * NW * 4, dtype=torch.int64, device=dev)
+for i in range(20): fr.step(i)
+torch.cuda.synchronize()
+ms = bench.timed(torch, 1, fr.step, 500) / 500
+print("flow=%s mixed=%s  ms_per_step (no stamps) %.4f" % (os.environ.get("MM_FLOW", "1"), os.environ.get("MM_MIXED", "1"), ms))
+L.mm_debug_profile(fr.h.handle, ctypes.c_void_p(prof.data_ptr()))
+def ovf_counts(ws, B, F, H, W):
+    """truncated pixels per image, read from the workspace of the last step (layout: mm_ws_make in mm_common.cuh)"""
+    al = lambda x: (x + 255) // 256 * 256
+    off = al(B * F * 48); off = al(off + B * H * W * 8); off = al(off + B * H * W * 8)
+    off = al(off + B * H * ((W + 31) // 32) * 4) + 16
+    return ws.view(torch.uint8)[off:off + 4 * B].view(torch.int32).cpu().numpy()
+c = ovf_counts(fr.sets[0]['out']['ws'], fr.B, dr.num_faces, dr.height, dr.image_size)
+print("truncated pixels per image (set 0): total %d, images with any %d, max %d: %s" % (c.sum(), (c > 0).sum(), c.max(), sorted(c[c > 0].tolist(), reverse=True)))
+names = ["vertex_fwd", "hard", "soft_fwd", "shade", "soft_bwd", "vertex_bwd"]
+def q(a, ps=(0, 50, 90, 100)): return " ".join("%6.1f" % np.percentile(a, p) for p in ps)
+for r in range(reps):
+    for i in range(4): fr.step(r * 5 + i)          # a few back-to-back steps: the stamped one runs as inside a loop
+    torch.cuda.synchronize()
+    prof.zero_(); torch.cuda.synchronize()
+    fr.step(r * 5 + 4); fr.step(r * 5 + 5)          # (the second step overwrites the first one's stamps: steady state)
+    torch.cuda.synchronize()
+    t = prof.cpu().numpy().reshape(NK, NW, 4).astype(np.float64)
+    live = t[:, :, 0] > 0
+    t0 = t[:, :, 0][live].min()
+    print("rep %d: step span %.1f us  (percentiles 0/50/90/100, us from the step's first stamp)" % (r, (t[:, :, 2].max() - t0) / 1e3))
+    ticks = np.arange(0, (t[:, :, 2].max() - t0) / 1e3 + 5, 5.0)
+    for k in range(NK):
+        m = live[k] & (t[k, :, 2] > 0)
+        if not m.any(): continue
+        s, e = (t[k, m, 0] - t0) / 1e3, (t[k, m, 2] - t0) / 1e3
+        line = "  %-10s n=%5d  start %s | end %s | run %s" % (names[k], m.sum(), q(s), q(e), q(e - s))
+        rd = t[k, m, 1]
+        if (rd > 0).any():
+            w = (rd[rd > 0] - t0) / 1e3 - s[rd > 0]
+            line += " | wait %s" % q(w)
+        print(line)
+        if k == 4:                                     # soft_bwd: the overflow-role CTAs (the first 8 * SMs CTAs) separately
+            nl = 148 * 16 * 4
+            mm_ = m.copy(); mm_[148 * 8 * 4:] = False
+            if mm_.any():
+                s2, e2 = (t[k, mm_, 0] - t0) / 1e3, (t[k, mm_, 2] - t0) / 1e3
+                r2 = (t[k, mm_, 1] - t0) / 1e3
+                print("    overflow-role CTAs n=%d start %s | listed %s | end %s | run %s ; busy (run > 2 us): %d" % (mm_.sum(), q(s2), q(r2), q(e2), q(e2 - s2), int(((e2 - s2) > 2.0).sum())))
+        alive = [(int(((s <= x) & (e > x)).sum())) for x in ticks]
+        print("             alive@5us: " + " ".join("%5d" % a for a in alive))
