@@ -15,6 +15,7 @@
 // The geometry backward (mm_raster.cu) consumes `gsoft`.
 #include "mm_device.cuh"
 #include "mm_soft_fwd.cuh"
+#pragma nv_diag_suppress 128    // ("loop is not reachable": the forward-only instantiation leaves the covered-pixel loop early)
 
 namespace {
 

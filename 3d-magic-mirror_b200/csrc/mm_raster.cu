@@ -216,7 +216,10 @@ k_scatter_hard(const mm_raster_params p)
 
 // ---------------------------------------------------------------------------------------------- soft pass forward
 // (engine in mm_soft_fwd.cuh, shared with the fused step's merged soft + shading kernel)
-__global__ void __launch_bounds__(32 * SF_WARPS)
+#ifndef SF_MINB
+#define SF_MINB 10
+#endif
+__global__ void __launch_bounds__(32 * SF_WARPS, SF_MINB)
 k_soft_fwd(const mm_raster_params p)
 {
     mm_pdl_prologue((p.pdl_late & 2) != 0);

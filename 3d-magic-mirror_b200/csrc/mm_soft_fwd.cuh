@@ -60,15 +60,20 @@ __device__ __forceinline__ void exact_rect(const mm_raster_params& p, const Face
 // column block) tells which of its pixels are uncovered.  The set bits become queue entries (warp scan + per-lane bit
 // loop); whenever 32 are waiting the whole warp evaluates them, one candidate per lane, exactly as before.
 #define SF_QCAP (1024 + 64)
+#define SF_DCAP 192          // evaluated candidates staged per warp before they go to the global pair list
 
 struct SoftQ {
     uint32_t q[SF_QCAP];     // pending candidates: slot << 24 | iy << 12 | ix
+    uint32_t done[SF_DCAP];  // evaluated candidates (same encoding) waiting for their slots in the pair list
     float rec[6][8];         // the warp's 8 faces: image-plane corners
     int img[8];
     int face[8];
 };
 
-__device__ __forceinline__ void soft_fwd_eval(const mm_raster_params& p, const SoftQ& wq, uint32_t e, float kz)
+// One candidate: distance, probability, ONE integer atomicAdd into the pixel's accumulator.  Returns the accumulator's previous
+// word; the caller looks at it one round LATER (soft_fwd_check), so that the atomic's round trip overlaps the next round's
+// arithmetic instead of ending every round (the slowest warps of the kernel are the ones with five and more rounds).
+__device__ __forceinline__ unsigned long long soft_fwd_eval(const mm_raster_params& p, const SoftQ& wq, uint32_t e, float kz)
 {
     const int slot = (int)(e >> 24), iy = (int)((e >> 12) & 0xfffu), ix = (int)(e & 0xfffu);
     const size_t pg = (size_t)wq.img[slot] * p.H * p.W + (size_t)iy * p.W + ix;
@@ -79,24 +84,33 @@ __device__ __forceinline__ void soft_fwd_eval(const mm_raster_params& p, const S
     int type;
     const float d2 = soft_d2_fast(r, pix_x(ix, p.W, p.sx), pix_y(iy, p.H, p.sy), p.multiplier, type);
     const float prob = soft_prob_fast(d2, kz);
-    const unsigned long long old = atomicAdd(p.lacc + pg, lacc_term(log1pf(-prob)));
+    return atomicAdd(p.lacc + pg, lacc_term(log1pf(-prob)));
+}
+__device__ __forceinline__ void soft_fwd_check(const mm_raster_params& p, const SoftQ& wq, unsigned long long old, uint32_t e)
+{
     if (lacc_count(old) == p.knum) {                            // candidate knum+1: the pixel needs the ordered pass
+        const int slot = (int)(e >> 24), iy = (int)((e >> 12) & 0xfffu), ix = (int)(e & 0xfffu);
         const int b = wq.img[slot];
         const uint32_t s2 = atomicAdd(p.ovf_cnt + b, 1u);
         p.ovf_list[(size_t)b * p.H * p.W + s2] = (uint32_t)(iy * p.W + ix);
     }
 }
 
-// append the candidates this warp just evaluated to the global pair list (one atomicAdd per batch); all lanes call it
-__device__ __forceinline__ void soft_fwd_record(const mm_raster_params& p, const SoftQ& wq, uint32_t e, int n, int lane)
+// the staged candidates go to the global pair list: ONE atomicAdd for up to SF_DCAP of them (it was one per round of 32: a
+// second round trip at the end of every round); all lanes call it
+__device__ __forceinline__ void soft_fwd_flush(const mm_raster_params& p, const SoftQ& wq, int dn, int lane)
 {
+    if (dn == 0) return;
     uint32_t base = 0u;
-    if (lane == 0) base = atomicAdd(p.ovf_count + 1, (uint32_t)n);
+    if (lane == 0) base = atomicAdd(p.ovf_count + 1, (uint32_t)dn);
     base = __shfl_sync(FULL, base, 0);
-    if (lane < n && base + (uint32_t)lane < p.plist_cap) {
-        const int slot = (int)(e >> 24);
-        const unsigned long long fg = (unsigned long long)((size_t)wq.img[slot] * p.F + wq.face[slot]);
-        p.plist[base + lane] = (fg << 32) | (unsigned long long)(e & 0xffffffu);
+    for (int i = lane; i < dn; i += 32) {
+        if (base + (uint32_t)i < p.plist_cap) {
+            const uint32_t e = wq.done[i];
+            const int slot = (int)(e >> 24);
+            const unsigned long long fg = (unsigned long long)((size_t)wq.img[slot] * p.F + wq.face[slot]);
+            p.plist[base + i] = (fg << 32) | (unsigned long long)(e & 0xffffffu);
+        }
     }
 }
 
@@ -138,7 +152,13 @@ __device__ __forceinline__ void soft_fwd_role(const mm_raster_params& p, SoftQ& 
     int maxseg = nseg;
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxseg = max(maxseg, __shfl_xor_sync(FULL, maxseg, o));
-    int qn = 0;
+    int qn = 0, dn = 0;
+#ifdef MM_PROF
+    int ncand = 0;
+#endif
+    unsigned long long pend_old = 0ull;      // the previous round's accumulator word and candidate of this lane
+    uint32_t pend_e = 0u;
+    bool pend = false;
     // running (row, word) of this lane's segment `it * 4 + sub`, advanced by 4 segments per iteration without a division
     int row = iy0, wd = wd0 + sub;
     if (nwd > 0) while (wd >= wd0 + nwd) { wd -= nwd; ++row; }
@@ -164,12 +184,19 @@ __device__ __forceinline__ void soft_fwd_role(const mm_raster_params& p, SoftQ& 
                 wq.q[pos++] = hdr + (uint32_t)j;
             }
             qn += __shfl_sync(FULL, incl, 31);
+#ifdef MM_PROF
+            ncand += __shfl_sync(FULL, incl, 31);
+#endif
             __syncwarp();
             while (qn >= 32) {                                   // evaluate from the top of the queue: no shifting
                 qn -= 32;
                 const uint32_t e = wq.q[qn + lane];
-                soft_fwd_eval(p, wq, e, kz);
-                soft_fwd_record(p, wq, e, 32, lane);
+                const unsigned long long old = soft_fwd_eval(p, wq, e, kz);
+                if (pend) soft_fwd_check(p, wq, pend_old, pend_e);
+                pend_old = old; pend_e = e; pend = true;
+                if (dn + 32 > SF_DCAP) { __syncwarp(); soft_fwd_flush(p, wq, dn, lane); dn = 0; __syncwarp(); }
+                wq.done[dn + lane] = e;
+                dn += 32;
             }
             __syncwarp();
         }
@@ -178,11 +205,25 @@ __device__ __forceinline__ void soft_fwd_role(const mm_raster_params& p, SoftQ& 
             else { wd += 4; while (wd >= wd0 + nwd) { wd -= nwd; ++row; } }
         }
     }
+    // the tail of the queue; then the pair list FIRST (its slot allocation is a round trip of its own, which so overlaps the
+    // accumulator atomics still in flight) and the last look at the accumulators' previous words behind it
+    unsigned long long last_old = 0ull;
+    uint32_t last_e = 0u;
+    const bool last = lane < qn;
     if (qn > 0) {
-        const uint32_t e = lane < qn ? wq.q[lane] : 0u;
-        if (lane < qn) soft_fwd_eval(p, wq, e, kz);
-        soft_fwd_record(p, wq, e, qn, lane);
+        last_e = last ? wq.q[lane] : 0u;
+        if (last) last_old = soft_fwd_eval(p, wq, last_e, kz);
+        if (dn + qn > SF_DCAP) { __syncwarp(); soft_fwd_flush(p, wq, dn, lane); dn = 0; __syncwarp(); }
+        if (last) wq.done[dn + lane] = last_e;
+        dn += qn;
     }
+    __syncwarp();
+    soft_fwd_flush(p, wq, dn, lane);
+    if (pend) soft_fwd_check(p, wq, pend_old, pend_e);
+    if (last) soft_fwd_check(p, wq, last_old, last_e);
+#ifdef MM_PROF
+    if (p.prof && lane == 0 && gwarp < 16384) p.prof[((size_t)2 * 16384 + gwarp) * 4 + 3] = ((unsigned long long)maxseg << 32) | (unsigned)ncand;
+#endif
 }
 
 // one (pixel, face) candidate's contribution to the face's 6 corner gradients (DIBR_SPEC A.5, fast tail)

@@ -65,5 +65,16 @@ for r in range(reps):
                 s2, e2 = (t[k, mm_, 0] - t0) / 1e3, (t[k, mm_, 2] - t0) / 1e3
                 r2 = (t[k, mm_, 1] - t0) / 1e3
                 print("    overflow-role CTAs n=%d start %s | listed %s | end %s | run %s ; busy (run > 2 us): %d" % (mm_.sum(), q(s2), q(r2), q(e2), q(e2 - s2), int(((e2 - s2) > 2.0).sum())))
+        if k == 2:                                     # soft forward: run time against the warp's row-walk length and candidates
+            extra = t[k, m, 3].astype(np.int64)
+            mseg, ncand = extra >> 32, extra & 0xffffffff
+            run = e - s
+            for lo, hi in ((0, 4), (4, 6), (6, 8), (8, 10), (10, 13), (13, 99)):
+                sel = (run >= lo) & (run < hi)
+                if sel.any():
+                    print("    run %2d-%2d us: %5d warps, iterations p50/max %3d/%3d, candidates p50/max %4d/%4d, start p50 %.1f" % (
+                        lo, hi, sel.sum(), np.median(mseg[sel]), mseg[sel].max(), np.median(ncand[sel]), ncand[sel].max(), np.median(s[sel])))
+            print("    all warps: iterations sum %d, candidates sum %d; corr(run, iterations) %.2f, corr(run, candidates) %.2f" % (
+                mseg.sum(), ncand.sum(), np.corrcoef(run, mseg)[0, 1], np.corrcoef(run, ncand)[0, 1]))
         alive = [(int(((s <= x) & (e > x)).sum())) for x in ticks]
         print("             alive@5us: " + " ".join("%5d" % a for a in alive))
