@@ -101,11 +101,10 @@ void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int tex_mirror, int no_
     p.pdl_late = c->pdl_late;
     p.covw = (c->W + 31) / 32;
     p.nstrips = mm_shade_strips(c->H, c->W);
-    // shading CTAs per image that double as the overflow role when the image has truncated pixels (far cameras): about one
-    // resident wave over the batch, never more than are resident together (lanes of the row wait for their results)
-    p.novf = c->num_sms * 4 / B; p.novf = p.novf < 32 ? 32 : p.novf;
-    if (p.novf > p.nstrips) p.novf = p.nstrips;
-    if (p.novf > c->num_sms * 2) p.novf = c->num_sms * 2;
+    // the first CTAs of the shading grid double as the overflow role when there are truncated pixels (far cameras); never
+    // more than are resident together (lanes of later CTAs wait for their results)
+    p.novf = c->num_sms * 2;
+    if (p.novf > p.nstrips * B) p.novf = p.nstrips * B;
     p.prof = c->prof;
     p.face_uvs = c->d_face_uvs;
     p.tab = c->d_tab;
@@ -116,7 +115,7 @@ void set_ws(const mm_ctx* c, const mm_ws_layout& L, char* ws, mm_raster_params& 
     p.zbuf = (unsigned long long*)(ws + L.zbuf); p.lacc = (unsigned long long*)(ws + L.lacc);
     p.cov = (uint32_t*)(ws + L.cov);
     p.ovf_list = (uint32_t*)(ws + L.ovf_list); p.ovf_count = (uint32_t*)(ws + L.ovf_count);
-    p.ovf_cnt = (uint32_t*)(ws + L.ovf_cnt);
+    p.sched_n = (uint32_t*)(ws + L.sched_n); p.sched_list = (uint32_t*)(ws + L.sched_list);
     p.gsoft = (float*)(ws + L.gsoft);
     p.plist = (unsigned long long*)(ws + L.plist); p.plist_cap = (uint32_t)((L.gsoft - L.plist) / 8);
     if (c->plist_cap_max && p.plist_cap > c->plist_cap_max) p.plist_cap = c->plist_cap_max;
@@ -128,8 +127,8 @@ void set_ws(const mm_ctx* c, const mm_ws_layout& L, char* ws, mm_raster_params& 
 // counters (one contiguous range) and the per-face backward accumulators for the rest of the step
 cudaError_t launch_vertex_fwd(const mm_ctx* c, int B, const mm_ws_layout& L, char* ws, const float* vertices, const float* azim,
                               const float* elev, const float* dist, const float* bias, float* face_normals, cudaStream_t s) {
-    // zbuf .. ovf_cnt are contiguous and 256-byte aligned: one clear range (16-byte units, tail padded inside the workspace)
-    const size_t bytes0 = mm_align_up((L.ovf_cnt + (size_t)B * 4) - L.zbuf, 16);
+    // zbuf .. sched_n are contiguous and 256-byte aligned: one clear range (16-byte units)
+    const size_t bytes0 = mm_align_up((L.sched_n + 32) - L.zbuf, 16);
     return mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg), face_normals,
                                 (float*)(ws + L.gfacc), (long long*)(ws + L.img_fwd), (long long*)(ws + L.img_bwd),
                                 ws + L.zbuf, bytes0, nullptr, 0, s);

@@ -13,11 +13,12 @@
 //     lacc       [B,H,W] u64  soft-silhouette accumulator of uncovered pixels: fixed-point sum log(1-p) << 16 | count
 //     cov        [B,H,ceil(W/32)] u32 coverage bitmap written by the hard pass (atomicOr): the soft pass finds the UNCOVERED
 //                             pixels of a face's enlarged bbox with one word load per row instead of one zbuf load per pixel
-//     ovf_count  [4] u32   {-, candidate pairs recorded, -, -}
-//     ovf_cnt    [B] u32   truncated pixels of each image (more than knum soft candidates)
-//                          (zbuf, lacc, cov, ovf_count and ovf_cnt are contiguous: k_vertex_fwd clears them in one range)
-//     ovf_list   [B,H*W] u32  per image: its truncated pixels (pixel index inside the image), re-done exactly, in face order, by
-//                             the shading kernel's overflow role
+//     ovf_count  [4] u32   {truncated pixels (more than knum soft candidates), candidate pairs recorded, -, -}
+//     sched_n    [8] u32   shading schedule: number of 4-tile strips whose covered pixels need k = 0..4 rounds of the dense pass
+//                          (zbuf, lacc, cov, ovf_count and sched_n are contiguous: k_vertex_fwd clears them in one range)
+//     ovf_list   [B*H*W] u32  the truncated pixels, re-done exactly, in face order, by the shading kernel's overflow role
+//     sched_list [5,B*nstrips] u32  the strips (image * nstrips + strip) of each class, written by the soft pass from the coverage
+//                             bitmap; the shading kernel's CTAs take them longest class first (mm_fused.cu)
 //     plist      [2*B*H*W] u64 the (face, pixel) candidate pairs the forward soft pass evaluated, (image*F+face) << 32 |
 //                             iy << 12 | ix: the backward soft pass replays this dense list
 //     gsoft      [B,H,W]      d(loss)/d(silhouette) per pixel, handed from the shading stage to the geometry backward
@@ -40,6 +41,13 @@
 #define MM_GF           12           // floats per face of the backward accumulator `gfacc`: d/d corners (6), pad (2), d/d unit
                                      // normal (3), pad (1) -- 48 B, so the three groups are 16/8/16-byte aligned for vector REDs
 #define MM_MAX_KNUM     64
+// shading kernel geometry: a warp owns a 16 x 8-pixel tile, a CTA a strip of 4 consecutive tiles (row-major tile numbering)
+#define MM_SH_TW        16
+#define MM_SH_TH        8
+#define MM_SH_WARPS     4
+static inline int mm_shade_strips(int H, int W) {
+    return (((W + MM_SH_TW - 1) / MM_SH_TW) * ((H + MM_SH_TH - 1) / MM_SH_TH) + MM_SH_WARPS - 1) / MM_SH_WARPS;
+}
 
 struct mm_ctx {
     int device;
@@ -74,7 +82,7 @@ struct mm_ctx {
 };
 
 struct mm_ws_layout {
-    size_t frec, zbuf, lacc, cov, ovf_count, ovf_cnt, ovf_list, plist, gsoft, vimg, gfacc, img_fwd, ticket, img_bwd, total;
+    size_t frec, zbuf, lacc, cov, ovf_count, sched_n, ovf_list, sched_list, plist, gsoft, vimg, gfacc, img_fwd, ticket, img_bwd, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -83,13 +91,14 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     mm_ws_layout L;
     size_t off = 0;
     L.frec = off;     off = mm_align_up(off + (size_t)B * c->F * MM_REC_FLOATS * 4, 256);
-    // zbuf .. ovf_cnt are contiguous: one range, cleared at the start of every forward
+    // zbuf .. sched_n are contiguous: one range, cleared at the start of every forward
     L.zbuf = off;     off = mm_align_up(off + (size_t)B * c->H * c->W * 8, 256);
     L.lacc = off;     off = mm_align_up(off + (size_t)B * c->H * c->W * 8, 256);
     L.cov = off;      off = mm_align_up(off + (size_t)B * c->H * ((c->W + 31) / 32) * 4, 256);
     L.ovf_count = off; off = off + 16;
-    L.ovf_cnt = off;  off = mm_align_up(off + (size_t)B * 4, 256);
+    L.sched_n = off;  off = mm_align_up(off + 32, 256);
     L.ovf_list = off; off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
+    L.sched_list = off; off = mm_align_up(off + (size_t)5 * B * mm_shade_strips(c->H, c->W) * 4, 256);
     L.plist = off;    off = mm_align_up(off + (size_t)2 * B * c->H * c->W * 8, 256);
     L.gsoft = off;    off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.vimg = off;     off = mm_align_up(off + (size_t)B * c->V * 2 * 4, 256);
@@ -115,10 +124,11 @@ struct mm_raster_params {
     unsigned long long* lacc;     // [B,H,W]
     uint32_t* cov;           // [B,H,ceil(W/32)] coverage bitmap: bit set = some front face covers the pixel (hard pass, atomicOr)
     int covw;                // words per bitmap row
-    uint32_t* ovf_list;      // [B,H*W] per-image lists of truncated pixels
-    uint32_t* ovf_count;     // [4]: {-, candidate pairs recorded, -, -}
-    uint32_t* ovf_cnt;       // [B] truncated pixels per image
-    int nstrips, novf;       // shading: CTAs per image; how many of them double as the overflow role
+    uint32_t* ovf_list;      // [B*H*W] truncated pixels (global pixel index)
+    uint32_t* ovf_count;     // [4]: {truncated pixels, candidate pairs recorded, -, -}
+    uint32_t* sched_n;       // [8] strips per class of the shading schedule
+    uint32_t* sched_list;    // [5, B*nstrips]
+    int nstrips, novf;       // shading: strips (= CTAs) per image; how many CTAs (the first of the grid) double as the overflow role
     unsigned long long* prof;     // MM_PROF builds: per-warp time stamps (tools/probes/timeline.py), else NULL
     unsigned long long* plist;    // [plist_cap]
     uint32_t plist_cap;
@@ -206,7 +216,6 @@ cudaError_t mm_launch_template_fwd(const mm_ctx* c, int N, int h, int w, const f
 cudaError_t mm_launch_template_bwd(const mm_ctx* c, int N, int h, int w, const float* tmpl, const float* g_local,
                                    const float* g_ndiff, float* g_x, cudaStream_t s);
 int mm_template_max_plane(void);
-int mm_shade_strips(int H, int W);
 cudaError_t mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 cudaError_t mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s);
 // shading: mode 0 = fused (forward + loss sums + RGB-side backward), 1 = forward only, 2 = backward only

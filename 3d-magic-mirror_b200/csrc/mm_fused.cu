@@ -22,8 +22,8 @@ namespace {
 #ifndef FULL
 #define FULL 0xffffffffu
 #endif
-#define FT_W 16           // tile of one warp: 16 x 8 pixels, lane = (ly = lane >> 2, lx = lane & 3), 4 pixels per lane
-#define FT_H 8
+#define FT_W MM_SH_TW     // tile of one warp: 16 x 8 pixels, lane = (ly = lane >> 2, lx = lane & 3), 4 pixels per lane
+#define FT_H MM_SH_TH
 
 __device__ __forceinline__ float warp_sum(float v) {
     #pragma unroll
@@ -74,9 +74,7 @@ __device__ __noinline__ unsigned long long lacc_wait_exact(const unsigned long l
 // The first version ran the covered path inside the 4-pixel loop of pass 1: 77 % lane utilisation, ~150 registers (8 resident
 // warps per SM) and ~840 dependent warp-instructions per pixel quad at 2 warps per scheduler -- 46 us, latency-bound
 // (profiles/r1_notes.md).  Splitting the passes lets pass 2 run compacted and at a smaller register footprint.
-#ifndef FUSED_WARPS
-#define FUSED_WARPS 4
-#endif
+#define FUSED_WARPS MM_SH_WARPS
 #ifndef FUSED_MINB
 #define FUSED_MINB 4
 #endif
@@ -418,17 +416,19 @@ __device__ __forceinline__ void shade_role(const mm_raster_params& p, ShadeSmem&
     }
 }
 
-// grid (p.nstrips, B).  Forward modes (SHADE_FUSED / SHADE_FWD) also own the TRUNCATED pixels of the soft pass (more than knum
-// candidates: DIB-R keeps the first knum in face order, DIBR_SPEC A.4).  If image b has any (ovf_cnt[b], final when this kernel
-// starts; fetched together with the lights, one round trip for both), the first p.novf CTAs of its row first re-do their share
-// of them exactly, one CTA per pixel (soft_ovf_role), which replaces the pixel's accumulator by the exact word (count field
-// MM_LACC_OVF).  Nobody waits at CTA level: a lane of pass 1 that meets an accumulator with count > knum that is not exact yet
-// spins on THAT word (lacc_wait_exact).  The CTA it waits for is one of the row's first p.novf: CTAs are dispatched in order
-// and p.novf of them always fit on the GPU together, so the wait ends.  Almost always the count is zero and none of this runs;
-// it used to be a kernel of its own between the soft pass and the shading: 5 us of launch + drain latency for ~50 pixels per
+// grid (B * p.nstrips): one CTA per strip, taken in SCHEDULE order: the soft pass classed every strip by the rounds its dense
+// pass will need (shade_sched_produce, mm_soft_fwd.cuh); CTA i -- CTAs are dispatched in index order -- takes the i-th strip of
+// the longest-class-first order, so the few-microsecond background strips fill the end of the kernel instead of a 20 us strip
+// of a near-camera image starting in the last wave.
+// Forward modes (SHADE_FUSED / SHADE_FWD) also own the TRUNCATED pixels of the soft pass (more than knum candidates: DIB-R keeps
+// the first knum in face order, DIBR_SPEC A.4).  If there are any (ovf_count[0], final when this kernel starts; fetched together
+// with the schedule counters), the first p.novf CTAs of the grid first re-do their share of them exactly, one CTA per pixel
+// (soft_ovf_role), which replaces the pixel's accumulator by the exact word (count field MM_LACC_OVF).  Nobody waits at CTA
+// level: a lane of pass 1 that meets an accumulator with count > knum that is not exact yet spins on THAT word
+// (lacc_wait_exact).  The CTA it waits for is one of the grid's first p.novf, which are resident together, so the wait ends.
+// This used to be a kernel of its own between the soft pass and the shading: 5 us of launch + drain latency for ~40 pixels per
 // step at cfg-2.
 struct ShadeOvfSmem { uint32_t mask[OVF_MAX_WORDS]; int kept[MM_MAX_KNUM]; };
-
 
 template <bool VEC, bool HAS_GUP, int MODE>
 __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MINB)
@@ -438,20 +438,30 @@ k_shade(const mm_raster_params p)
     mm_pdl_prologue((p.pdl_late & 8) != 0);
     __shared__ union { ShadeSmem sm; ShadeOvfSmem ov; } u;
     __shared__ float s_lights[16];
-    __shared__ uint32_t s_trunc;
+    __shared__ uint32_t s_n[8];                      // strips per class (0..4), [5] = truncated pixels
+    __shared__ int s_sid;
     __shared__ int s_count;                          // covered pixels of the CTA's strip (shade_role)
-    const int b = blockIdx.y;
-    const int wid = (blockIdx.y * gridDim.x + blockIdx.x) * FUSED_WARPS + (threadIdx.x >> 5);
+    const int wid = blockIdx.x * FUSED_WARPS + (threadIdx.x >> 5);
     (void)wid;
     MM_PROF_MARK(p.prof, 3, wid, 0);
-    if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
+    if (threadIdx.x < 5) s_n[threadIdx.x] = p.sched_n[threadIdx.x];
+    if (threadIdx.x == 5) s_n[5] = (MODE != SHADE_BWD) ? p.ovf_count[0] : 0u;
     if (threadIdx.x == 0) s_count = 0;
-    if (MODE != SHADE_BWD && threadIdx.x == 32) s_trunc = p.ovf_cnt[b];
     __syncthreads();
-    if (MODE != SHADE_BWD && s_trunc > blockIdx.x && (int)blockIdx.x < p.novf)
-        soft_ovf_role<false>(p, u.ov.mask, u.ov.kept, b, s_trunc, blockIdx.x, p.novf);     // (every pixel ends with a block barrier)
+    if (threadIdx.x == 0) {                          // the blockIdx.x-th strip, longest class first
+        uint32_t r = blockIdx.x;
+        int k = 4;
+        while (k > 0 && r >= s_n[k]) { r -= s_n[k]; --k; }
+        s_sid = (int)p.sched_list[(size_t)k * gridDim.x + r];
+    }
+    if (MODE != SHADE_BWD && s_n[5] > blockIdx.x && (int)blockIdx.x < p.novf)
+        soft_ovf_role<false>(p, u.ov.mask, u.ov.kept, s_n[5], blockIdx.x, p.novf);     // (every pixel ends with a block barrier)
+    __syncthreads();
+    const int b = s_sid / p.nstrips, bx = s_sid - b * p.nstrips;
+    if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
+    __syncthreads();
     MM_PROF_MARK(p.prof, 3, wid, 1);
-    shade_role<VEC, HAS_GUP, MODE>(p, u.sm, s_lights, s_count, blockIdx.x, b);
+    shade_role<VEC, HAS_GUP, MODE>(p, u.sm, s_lights, s_count, bx, b);
     MM_PROF_MARK(p.prof, 3, wid, 2);
 }
 
@@ -526,7 +536,7 @@ static bool aligned16(const void* q) { return (((uintptr_t)q) & 15) == 0; }
 
 cudaError_t mm_launch_shade(const mm_ctx* c, const mm_raster_params& p, int mode, cudaStream_t s)
 {
-    const dim3 grid(p.nstrips, p.B);
+    const dim3 grid(p.nstrips * p.B);
     const bool vec = (p.W & 3) == 0 && aligned16(p.zbuf) && aligned16(p.lacc) && aligned16(p.gt) && aligned16(p.bg) &&
                      aligned16(p.g_rgba) && aligned16(p.rgba) && aligned16(p.g_bg) && aligned16(p.gsoft) &&
                      aligned16(p.imnormal) && aligned16(p.face_idx_out);
@@ -542,8 +552,6 @@ cudaError_t mm_launch_shade(const mm_ctx* c, const mm_raster_params& p, int mode
                 : (gup ? k_shade<false, true, SHADE_BWD> : k_shade<false, false, SHADE_BWD>);
     return mm_launch(k, grid, dim3(FUSED_THREADS), 0, s, c->pdl != 0, p);
 }
-
-int mm_shade_strips(int H, int W) { return (((W + FT_W - 1) / FT_W) * ((H + FT_H - 1) / FT_H) + FUSED_WARPS - 1) / FUSED_WARPS; }
 
 cudaError_t mm_launch_gsoft(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {

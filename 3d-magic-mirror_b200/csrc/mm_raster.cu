@@ -299,31 +299,7 @@ k_soft_bwd(const mm_raster_params p, const int novf)
         MM_PROF_MARK(p.prof, 4, blockIdx.x * (SB_THREADS / 32) + (threadIdx.x >> 5), 2);
         return;
     }
-    // images with truncated pixels: the CTA fetches the counts of SB_THREADS images per round trip and lists the few that have
-    // any (usually none: one barrier and out); entries are dealt from a per-image rotated start so that one entry per image
-    // does not always land on the same CTA
-    const int vblock = blockIdx.x, nvblocks = novf;
-    __shared__ int s_img[SB_THREADS], s_rot[SB_THREADS];
-    __shared__ uint32_t s_cnt[SB_THREADS];
-    __shared__ int s_n;
-    for (int b0 = 0; b0 < p.B; b0 += SB_THREADS) {
-        if (threadIdx.x == 0) s_n = 0;
-        __syncthreads();
-        const uint32_t cnt = (b0 + (int)threadIdx.x < p.B) ? p.ovf_cnt[b0 + threadIdx.x] : 0u;
-        if (cnt) {                                              // (the rotation's modulo: once per listed image, not per CTA and image)
-            const int k = atomicAdd(&s_n, 1);
-            s_img[k] = b0 + threadIdx.x; s_cnt[k] = cnt; s_rot[k] = ((b0 + (int)threadIdx.x) * 61) % nvblocks;
-        }
-        __syncthreads();
-        MM_PROF_MARK(p.prof, 4, blockIdx.x * (SB_THREADS / 32) + (threadIdx.x >> 5), 1);
-        const int n = s_n;                                      // (block-uniform from here on)
-        for (int i = 0; i < n; ++i) {
-            int first = vblock + s_rot[i];
-            if (first >= nvblocks) first -= nvblocks;
-            if ((uint32_t)first < s_cnt[i]) soft_ovf_role<true>(p, s_mask, s_kept, s_img[i], s_cnt[i], first, nvblocks);
-        }
-        __syncthreads();
-    }
+    soft_ovf_role<true>(p, s_mask, s_kept, p.ovf_count[0], blockIdx.x, novf);
     MM_PROF_MARK(p.prof, 4, blockIdx.x * (SB_THREADS / 32) + (threadIdx.x >> 5), 2);
 }
 

@@ -90,9 +90,8 @@ __device__ __forceinline__ void soft_fwd_check(const mm_raster_params& p, const 
 {
     if (lacc_count(old) == p.knum) {                            // candidate knum+1: the pixel needs the ordered pass
         const int slot = (int)(e >> 24), iy = (int)((e >> 12) & 0xfffu), ix = (int)(e & 0xfffu);
-        const int b = wq.img[slot];
-        const uint32_t s2 = atomicAdd(p.ovf_cnt + b, 1u);
-        p.ovf_list[(size_t)b * p.H * p.W + s2] = (uint32_t)(iy * p.W + ix);
+        const uint32_t s2 = atomicAdd(p.ovf_count, 1u);
+        p.ovf_list[s2] = (uint32_t)((size_t)wq.img[slot] * p.H * p.W + (size_t)iy * p.W + ix);
     }
 }
 
@@ -114,6 +113,36 @@ __device__ __forceinline__ void soft_fwd_flush(const mm_raster_params& p, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------- shading schedule
+// The shading kernel's CTAs cost between ~3 us (a strip of background) and ~20 us (a strip full of covered pixels: four rounds
+// of its dense pass), and with ~2.6 CTAs per resident slot the grid-order dispatch left a 15 us drain behind the last wave
+// (per-warp timeline, profiles/r2_notes.md; list-scheduling the measured run times longest-first: 33.5 -> 26.9 us).  So the
+// soft pass, which runs on the final coverage bitmap anyway, classes every strip by the rounds it will need -- one warp per
+// strip: 32 lanes = 4 tiles x 8 rows, one 16-bit slice of a bitmap word each -- and the shading CTAs take the strips longest
+// class first.
+__device__ __forceinline__ void shade_sched_produce(const mm_raster_params& p, const int widx, const int nwarps, const int lane)
+{
+    static_assert(MM_SH_WARPS * MM_SH_TH == 32 && MM_SH_TW == 16, "one lane per (tile, row), one 16-bit slice of a bitmap word each");
+    const int ntx = (p.W + MM_SH_TW - 1) / MM_SH_TW, ntiles = ntx * ((p.H + MM_SH_TH - 1) / MM_SH_TH);
+    const int nsid = p.B * p.nstrips;
+    for (int sid = widx; sid < nsid; sid += nwarps) {
+        const int b = sid / p.nstrips, s = sid - b * p.nstrips;
+        const int tile = s * MM_SH_WARPS + (lane >> 3);
+        int cnt = 0;
+        if (tile < ntiles) {
+            const int ty = tile / ntx, tx = tile - ty * ntx;
+            const int iy = ty * MM_SH_TH + (lane & 7), x0 = tx * MM_SH_TW;
+            if (iy < p.H) cnt = __popc((p.cov[((size_t)b * p.H + iy) * p.covw + (x0 >> 5)] >> (x0 & 31)) & 0xffffu);
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+        if (lane == 0) {
+            const int k = min(4, (cnt + 32 * MM_SH_WARPS - 1) / (32 * MM_SH_WARPS));
+            p.sched_list[(size_t)k * nsid + atomicAdd(p.sched_n + k, 1u)] = (uint32_t)sid;
+        }
+    }
+}
+
 #define SF_WARPS 4
 #define SF_FPW 8             // faces per warp: 4 lanes share a face and take its (row, column-block) segments round-robin, so the
                              // dependent chain of bitmap loads per warp is 4x shorter and there are 4x more warps to overlap it
@@ -122,6 +151,7 @@ __device__ __forceinline__ void soft_fwd_role(const mm_raster_params& p, SoftQ& 
     const int lane = threadIdx.x & 31;
     const int nwarps = (p.B * p.F + SF_FPW - 1) / SF_FPW;
     if (gwarp >= nwarps) return;
+    shade_sched_produce(p, gwarp, nwarps, lane);
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
 
     // ---- set-up: lane = (slot, sub); faces dealt with a stride of the warp count (a warp mixes 8 images: balanced)
@@ -285,21 +315,22 @@ __device__ __forceinline__ void soft_pair_grad(const mm_raster_params& p, const 
 #define OVF_MAX_WORDS 2048          // F <= 65535
 #define OVF_UNROLL 5
 
-// (this CTA takes entries first, first + stride, .. of the `count` entries of image b's list)
+// (this CTA takes entries first, first + stride, .. of the `count` listed pixels)
 template <bool BWD>
-__device__ __forceinline__ void soft_ovf_role(const mm_raster_params& p, uint32_t* s_mask, int* s_kept, const int b,
-                                              const uint32_t count, const int first, const int stride)
+__device__ __forceinline__ void soft_ovf_role(const mm_raster_params& p, uint32_t* s_mask, int* s_kept, const uint32_t count,
+                                              const int first, const int stride)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t HW = (size_t)p.H * p.W;
-    const uint32_t n = min(count, (uint32_t)HW);
+    const uint32_t n = count;
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
     const float inv_mult = 1.0f / p.multiplier;
     const int nw = (p.F + 31) >> 5;
     const int niter = (p.F + OVF_THREADS - 1) / OVF_THREADS;              // faces per thread
     for (uint32_t e = (uint32_t)first; e < n; e += (uint32_t)stride) {
-        const int pix = (int)p.ovf_list[(size_t)b * HW + e];
-        const size_t pg = (size_t)b * HW + pix;
+        const size_t pg = p.ovf_list[e];
+        const int b = (int)(pg / HW);
+        const int pix = (int)(pg - (size_t)b * HW);
         const int iy = pix / p.W, ix = pix - iy * p.W;
         const float px = pix_x(ix, p.W, p.sx), py = pix_y(iy, p.H, p.sy);
         const float4* rec4 = reinterpret_cast<const float4*>(p.frec + (size_t)b * p.F * MM_REC_FLOATS);

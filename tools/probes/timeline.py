@@ -27,14 +27,14 @@ torch.cuda.synchronize()
 ms = bench.timed(torch, 1, fr.step, 500) / 500
 print("flow=%s mixed=%s  ms_per_step (no stamps) %.4f" % (os.environ.get("MM_FLOW", "1"), os.environ.get("MM_MIXED", "1"), ms))
 L.mm_debug_profile(fr.h.handle, ctypes.c_void_p(prof.data_ptr()))
-def ovf_counts(ws, B, F, H, W):
-    """truncated pixels per image, read from the workspace of the last step (layout: mm_ws_make in mm_common.cuh)"""
+def ws_counters(ws, B, F, H, W):
+    """{truncated pixels, candidate pairs} and the shading schedule's class sizes of the last step (layout: mm_ws_make)"""
     al = lambda x: (x + 255) // 256 * 256
     off = al(B * F * 48); off = al(off + B * H * W * 8); off = al(off + B * H * W * 8)
-    off = al(off + B * H * ((W + 31) // 32) * 4) + 16
-    return ws.view(torch.uint8)[off:off + 4 * B].view(torch.int32).cpu().numpy()
-c = ovf_counts(fr.sets[0]['out']['ws'], fr.B, dr.num_faces, dr.height, dr.image_size)
-print("truncated pixels per image (set 0): total %d, images with any %d, max %d: %s" % (c.sum(), (c > 0).sum(), c.max(), sorted(c[c > 0].tolist(), reverse=True)))
+    off = al(off + B * H * ((W + 31) // 32) * 4)
+    return ws.view(torch.uint8)[off:off + 48].view(torch.int32).cpu().numpy()
+c = ws_counters(fr.sets[0]['out']['ws'], fr.B, dr.num_faces, dr.height, dr.image_size)
+print("set 0: truncated pixels %d, candidate pairs %d, strips per class (0..4 rounds) %s" % (c[0], c[1], c[4:9].tolist()))
 names = ["vertex_fwd", "hard", "soft_fwd", "shade", "soft_bwd", "vertex_bwd"]
 def q(a, ps=(0, 50, 90, 100)): return " ".join("%6.1f" % np.percentile(a, p) for p in ps)
 for r in range(reps):
@@ -58,6 +58,18 @@ for r in range(reps):
             w = (rd[rd > 0] - t0) / 1e3 - s[rd > 0]
             line += " | wait %s" % q(w)
         print(line)
+        if k == 3:                                     # shading: what would a work-ordered dispatch buy?  (greedy list scheduling
+            import heapq                               # of the measured per-CTA run times on the kernel's 4 x SMs slots)
+            st = t[k, :, 0].reshape(-1, 4); en = t[k, :, 2].reshape(-1, 4)
+            ok = (st > 0).all(axis=1) & (en > 0).all(axis=1)
+            run_cta = ((en.max(axis=1) - st.min(axis=1)) / 1e3)[ok]
+            def makespan(order, slots=148 * 4):
+                h = [0.0] * slots
+                for r in order: heapq.heapreplace(h, h[0] + r)
+                return max(h)
+            two = np.concatenate([run_cta[run_cta > 5.0], run_cta[run_cta <= 5.0]])
+            print("    shade CTAs %d: sum of runs / slots %.1f us; list-scheduled makespan: grid order %.1f, longest first %.1f, two classes (> 5 us first) %.1f, shortest first %.1f" % (
+                len(run_cta), run_cta.sum() / (148 * 4), makespan(run_cta), makespan(np.sort(run_cta)[::-1]), makespan(two), makespan(np.sort(run_cta))))
         if k == 4:                                     # soft_bwd: the overflow-role CTAs (the first 8 * SMs CTAs) separately
             nl = 148 * 16 * 4
             mm_ = m.copy(); mm_[148 * 8 * 4:] = False
