@@ -103,7 +103,8 @@ void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int tex_mirror, int no_
     p.nstrips = mm_shade_strips(c->H, c->W);
     // the first CTAs of the shading grid double as the overflow role when there are truncated pixels (far cameras); never
     // more than are resident together (lanes of later CTAs wait for their results)
-    p.novf = c->num_sms * 2;
+    // (3 per SM: the shading kernels keep 4-5 CTAs per SM resident, the margin is for whatever else shares the GPU)
+    p.novf = c->num_sms * 3;
     if (p.novf > p.nstrips * B) p.novf = p.nstrips * B;
     p.prof = c->prof;
     p.face_uvs = c->d_face_uvs;

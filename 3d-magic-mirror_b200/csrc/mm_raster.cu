@@ -292,14 +292,13 @@ k_soft_bwd(const mm_raster_params p, const int novf)
     __shared__ uint32_t s_mask[OVF_MAX_WORDS];
     __shared__ int s_kept[MM_MAX_KNUM];
     MM_PROF_MARK(p.prof, 4, blockIdx.x * (SB_THREADS / 32) + (threadIdx.x >> 5), 0);
-    // (the truncated pixels come FIRST in the grid: each costs a CTA ~3 us of pure latency, so they start at once and the
-    // list CTAs fill in behind them; the other way round they were the kernel's tail, profiles/r2_notes.md)
-    if ((int)blockIdx.x >= novf) {
-        soft_bwd_list_role(p, s_wq, blockIdx.x - novf, gridDim.x - novf);
-        MM_PROF_MARK(p.prof, 4, blockIdx.x * (SB_THREADS / 32) + (threadIdx.x >> 5), 2);
-        return;
-    }
-    soft_ovf_role<true>(p, s_mask, s_kept, p.ovf_count[0], blockIdx.x, novf);
+    // The truncated pixels are dealt to ALL CTAs of the grid (entry e to CTA e mod grid): each costs a CTA ~3 us of pure latency
+    // (~8 us with 5120 faces).  The first `novf` CTAs have nothing else to do and come FIRST in the grid, so the usual handful
+    // of entries starts at once (as the kernel's last CTAs they were its tail); the list CTAs behind them take their share
+    // after their part of the pair list, which only matters when there are thousands (far cameras, sphere2: 16 k).
+    if ((int)blockIdx.x >= novf) soft_bwd_list_role(p, s_wq, blockIdx.x - novf, gridDim.x - novf);
+    const uint32_t ntrunc = p.ovf_count[0];
+    if (ntrunc > blockIdx.x) soft_ovf_role<true>(p, s_mask, s_kept, ntrunc, blockIdx.x, gridDim.x);
     MM_PROF_MARK(p.prof, 4, blockIdx.x * (SB_THREADS / 32) + (threadIdx.x >> 5), 2);
 }
 
@@ -318,7 +317,8 @@ cudaError_t mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaS
 cudaError_t mm_launch_geom_bwd(const mm_ctx* c, const mm_raster_params& p, cudaStream_t s)
 {
     static_assert(SB_THREADS == OVF_THREADS, "the merged backward kernel runs both roles with one CTA shape");
-    const int nlist = c->num_sms * 16, novf = c->num_sms * 8;
+    // (swept in round 2: 16 + 8 CTAs per SM 0.0930 ms, 8 + 8 0.0930, 8 + 2 0.0923, 16 + 2 0.0927, 4 + 2 0.0939)
+    const int nlist = c->num_sms * 8, novf = c->num_sms * 2;
     return mm_launch(k_soft_bwd, dim3(nlist + novf), dim3(SB_THREADS), 0, s, c->pdl != 0, p, novf);
 }
 
