@@ -112,7 +112,7 @@ void fill_params(const mm_ctx* c, int B, int Ht, int Wt, int tex_mirror, int no_
 }
 
 void set_ws(const mm_ctx* c, const mm_ws_layout& L, char* ws, mm_raster_params& p) {
-    p.frec = (const float*)(ws + L.frec);
+    p.frec = (const float*)(ws + L.frec); p.frect = (const uint4*)(ws + L.frect);
     p.zbuf = (unsigned long long*)(ws + L.zbuf); p.lacc = (unsigned long long*)(ws + L.lacc);
     p.cov = (uint32_t*)(ws + L.cov);
     p.ovf_list = (uint32_t*)(ws + L.ovf_list); p.ovf_count = (uint32_t*)(ws + L.ovf_count);
@@ -132,7 +132,7 @@ cudaError_t launch_vertex_fwd(const mm_ctx* c, int B, const mm_ws_layout& L, cha
     const size_t bytes0 = mm_align_up((L.sched_n + 32) - L.zbuf, 16);
     return mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg), face_normals,
                                 (float*)(ws + L.gfacc), (long long*)(ws + L.img_fwd), (long long*)(ws + L.img_bwd),
-                                ws + L.zbuf, bytes0, nullptr, 0, s);
+                                ws + L.zbuf, bytes0, nullptr, 0, (uint4*)(ws + L.frect), s);
 }
 
 // forward geometry of a batch: face records + visibility buffer + soft-silhouette accumulators + candidate lists (vertex stage ->
@@ -337,7 +337,7 @@ int mm_face_normals_forward(mm_ctx* c, int B, const float* vertices, const float
     char* ws = (char*)workspace;
     MM_LAUNCH(mm_launch_vertex_fwd(c, B, vertices, azim, elev, dist, bias, (float*)(ws + L.frec), (float*)(ws + L.vimg), face_normals,
                                    (float*)(ws + L.gfacc), (long long*)(ws + L.img_fwd), (long long*)(ws + L.img_bwd), nullptr, 0,
-                                   nullptr, 0, (cudaStream_t)stream), "vertex_fwd");
+                                   nullptr, 0, nullptr, (cudaStream_t)stream), "vertex_fwd");
     return MM_OK;
 }
 

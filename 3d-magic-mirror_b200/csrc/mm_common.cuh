@@ -7,6 +7,7 @@
 //     refrow/rowlo/rowhi [H], refcol/collo/colhi [W] int32: nearest-down/nearest-up
 //                index tables of the contour term (networks.py:381-382)
 //   workspace (caller-owned, per call; mm_ws_make):
+//     frect      [B,F] uint4  the face's exact pixel rectangles, tight and enlarged (mm_device.cuh: face_rects), 16-bit packed
 //     frec       [B,F,12]  face records: (ax,ay,bx,by | cx,cy,az,bz | cz,nx,ny,nz), xy already multiplied by `multiplier`,
 //                          z camera-space, n = unit face normal in camera space.  48 B = 3 x float4 per face.
 //     zbuf       [B,H,W] u64  visibility buffer: (order-preserving depth << 32 | ~face), atomicMax-resolved; 0 = uncovered
@@ -82,7 +83,7 @@ struct mm_ctx {
 };
 
 struct mm_ws_layout {
-    size_t frec, zbuf, lacc, cov, ovf_count, sched_n, ovf_list, sched_list, plist, gsoft, vimg, gfacc, img_fwd, ticket, img_bwd, total;
+    size_t frec, frect, zbuf, lacc, cov, ovf_count, sched_n, ovf_list, sched_list, plist, gsoft, vimg, gfacc, img_fwd, ticket, img_bwd, total;
 };
 
 static inline size_t mm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -91,6 +92,7 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     mm_ws_layout L;
     size_t off = 0;
     L.frec = off;     off = mm_align_up(off + (size_t)B * c->F * MM_REC_FLOATS * 4, 256);
+    L.frect = off;    off = mm_align_up(off + (size_t)B * c->F * 16, 256);
     // zbuf .. sched_n are contiguous: one range, cleared at the start of every forward
     L.zbuf = off;     off = mm_align_up(off + (size_t)B * c->H * c->W * 8, 256);
     L.lacc = off;     off = mm_align_up(off + (size_t)B * c->H * c->W * 8, 256);
@@ -120,6 +122,7 @@ struct mm_raster_params {
     int no_mask;
     int pdl_late;            // bit k: kernel k releases its dependents at CTA exit (0 hard, 1 soft_fwd, 3 shade, 4 soft_bwd)
     const float* frec;       // [B,F,12]
+    const uint4* frect;      // [B,F] exact pixel rectangles (tight | enlarged)
     unsigned long long* zbuf;     // [B,H,W]
     unsigned long long* lacc;     // [B,H,W]
     uint32_t* cov;           // [B,H,ceil(W/32)] coverage bitmap: bit set = some front face covers the pixel (hard pass, atomicOr)
@@ -205,7 +208,7 @@ static inline cudaError_t mm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 bl
 cudaError_t mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec,
                           float* vimg, float* face_normals, float* gfacc_zero, long long* img_fwd, long long* img_bwd,
-                          void* clr0, size_t bytes0, void* clr1, size_t bytes1, cudaStream_t s);
+                          void* clr0, size_t bytes0, void* clr1, size_t bytes1, uint4* frect, cudaStream_t s);
 cudaError_t mm_launch_vertex_bwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* gfacc, const float* g_face_normals,
                           long long* img_bwd, float* g_vertices, float* g_azim, float* g_elev, float* g_dist,

@@ -84,6 +84,77 @@ __device__ __forceinline__ bool soft_bbox_test(const FaceRec& r, float x0, float
     return !(x0 < xmin || x0 >= xmax || y0 < ymin || y0 >= ymax);
 }
 
+// ------------------------------------------------------------------ exact pixel rectangles of a face's bbox
+struct PixRange { int ix0, ix1, iy0, iy1; };
+
+// Conservative pixel-index range, clipped to the image, of the scaled-NDC box [xl,xh) x [yl,yh)
+// (the exact half-open tests are redone per pixel).  Returns false if empty.
+template <class P>
+__device__ __forceinline__ bool pix_range(const P& p, float xl, float xh, float yl, float yh, PixRange& r)
+{
+    const float inv_sx = 1.0f / p.sx, inv_sy = 1.0f / p.sy;
+    float fx_lo = (xl * inv_sx + (float)(p.W - 1)) * 0.5f;
+    float fx_hi = (xh * inv_sx + (float)(p.W - 1)) * 0.5f;
+    float fy_lo = ((float)(p.H - 1) - yh * inv_sy) * 0.5f;
+    float fy_hi = ((float)(p.H - 1) - yl * inv_sy) * 0.5f;
+    // NaN/Inf coordinates (vertex on the camera plane) stay conservative: treat as "everywhere"
+    if (!(fx_lo == fx_lo) || !(fx_hi == fx_hi)) { fx_lo = -4.0f; fx_hi = 1.0e6f; }
+    if (!(fy_lo == fy_lo) || !(fy_hi == fy_hi)) { fy_lo = -4.0f; fy_hi = 1.0e6f; }
+    fx_lo = fminf(fmaxf(fx_lo, -4.0f), 1.0e6f); fx_hi = fminf(fmaxf(fx_hi, -4.0f), 1.0e6f);
+    fy_lo = fminf(fmaxf(fy_lo, -4.0f), 1.0e6f); fy_hi = fminf(fmaxf(fy_hi, -4.0f), 1.0e6f);
+    r.ix0 = max((int)floorf(fx_lo), 0);
+    r.ix1 = min((int)ceilf(fx_hi), p.W - 1);
+    r.iy0 = max((int)floorf(fy_lo), 0);
+    r.iy1 = min((int)ceilf(fy_hi), p.H - 1);
+    return r.ix0 <= r.ix1 && r.iy0 <= r.iy1;
+}
+
+// EXACT pixel rectangle of a face's bbox (tight, or enlarged by boxlen: DIBR_SPEC A.4) under the reference's half-open
+// fp32 test  xmin <= px < xmax, ymin <= py < ymax: conservative float->int estimate, then <= 2 correction steps per side
+// with the very comparison the reference uses (pixel centres are monotone in the index, so the exact set is a rectangle).
+template <class P>
+__device__ __forceinline__ void exact_rect(const P& p, const FaceRec& r, bool enlarged,
+                                           int& ix0, int& ix1, int& iy0, int& iy1)
+{
+    float xmin = fminf(fminf(r.ax, r.bx), r.cx), xmax = fmaxf(fmaxf(r.ax, r.bx), r.cx);
+    float ymin = fminf(fminf(r.ay, r.by), r.cy), ymax = fmaxf(fmaxf(r.ay, r.by), r.cy);
+    if (enlarged) { xmin = SUB(xmin, p.blen); xmax = ADD(xmax, p.blen); ymin = SUB(ymin, p.blen); ymax = ADD(ymax, p.blen); }
+    PixRange pr;
+    ix0 = 0; ix1 = -1; iy0 = 0; iy1 = -1;
+    if (pix_range(p, xmin, xmax, ymin, ymax, pr)) {
+        ix0 = pr.ix0; ix1 = pr.ix1; iy0 = pr.iy0; iy1 = pr.iy1;
+        while (ix0 <= ix1 && pix_x(ix0, p.W, p.sx) < xmin) ++ix0;
+        while (ix1 >= ix0 && pix_x(ix1, p.W, p.sx) >= xmax) --ix1;
+        while (iy0 <= iy1 && pix_y(iy0, p.H, p.sy) >= ymax) ++iy0;      // y decreases with the row index
+        while (iy1 >= iy0 && pix_y(iy1, p.H, p.sy) < ymin) --iy1;
+    }
+}
+
+// The two exact rectangles of a face -- tight (hard pass; EMPTY for a back face, DIBR_SPEC A.2: the hard pass sees front faces
+// only) and enlarged by boxlen (soft pass) -- are computed ONCE, by the vertex stage (one thread per face, where the record is in
+// registers anyway), and travel as four 16-bit pairs: x = tight ix0 | ix1 << 16, y = tight iy0 | iy1 << 16, z / w = enlarged.
+// The hard and the soft pass used to redo this per warp with 8 of 32 lanes active: ~2.3 M of their 8.3 M / 9.7 M
+// warp-instructions each at cfg-2, in kernels that are instruction-issue bound.  An empty rectangle is stored as (1, 0).
+__device__ __forceinline__ uint32_t rect_pack(int lo, int hi, bool empty) {
+    return empty ? (1u | (0u << 16)) : ((uint32_t)lo | ((uint32_t)hi << 16));
+}
+template <class P>
+__device__ __forceinline__ uint4 face_rects(const P& p, const FaceRec& r) {
+    int ix0, ix1, iy0, iy1;
+    uint4 o;
+    ix0 = 0; ix1 = -1; iy0 = 0; iy1 = -1;
+    if (r.nz >= 0.0f) exact_rect(p, r, false, ix0, ix1, iy0, iy1);
+    bool empty = ix1 < ix0 || iy1 < iy0;
+    o.x = rect_pack(ix0, ix1, empty); o.y = rect_pack(iy0, iy1, empty);
+    exact_rect(p, r, true, ix0, ix1, iy0, iy1);
+    empty = ix1 < ix0 || iy1 < iy0;
+    o.z = rect_pack(ix0, ix1, empty); o.w = rect_pack(iy0, iy1, empty);
+    return o;
+}
+__device__ __forceinline__ void rect_unpack(uint32_t xw, uint32_t yw, int& ix0, int& ix1, int& iy0, int& iy1) {
+    ix0 = (int)(xw & 0xffffu); ix1 = (int)(xw >> 16); iy0 = (int)(yw & 0xffffu); iy1 = (int)(yw >> 16);
+}
+
 // ---- soft-silhouette distance (DIBR_SPEC A.4): squared distance to each edge (perpendicular if the foot lies on the segment,
 // else "far") and to each vertex, minimum + its type 0..5.  The cancellation-prone quantities (A, B, C, up, down) keep the
 // reference's exact operation order; what differs from the oracle's literal statement is only HOW the well-conditioned tail

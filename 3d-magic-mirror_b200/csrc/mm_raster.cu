@@ -112,8 +112,9 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
             wq.rec[0][slot] = r.ax; wq.rec[1][slot] = r.ay; wq.rec[2][slot] = r.bx; wq.rec[3][slot] = r.by;
             wq.rec[4][slot] = r.cx; wq.rec[5][slot] = r.cy; wq.rec[6][slot] = r.az; wq.rec[7][slot] = r.bz;
             wq.rec[8][slot] = r.cz; wq.img[slot] = b; wq.face[slot] = f;
-            if (MODE != MODE_HARD || r.nz >= 0.0f)                   // DIBR_SPEC A.2: the hard pass sees front faces only
-                exact_rect(p, r, MODE != MODE_HARD, ix0, ix1, iy0, iy1);
+            const uint4 rc = p.frect[fid];                           // exact rectangles from the vertex stage
+            if (MODE == MODE_HARD) rect_unpack(rc.x, rc.y, ix0, ix1, iy0, iy1);
+            else rect_unpack(rc.z, rc.w, ix0, ix1, iy0, iy1);
         } else { wq.img[slot] = 0; wq.face[slot] = 0; }
         const int w = ix1 - ix0 + 1, h = iy1 - iy0 + 1;
         npx = (w > 0 && h > 0) ? w * h : 0;
@@ -130,6 +131,9 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
     #pragma unroll
     for (int sl = 0; sl < FPW; ++sl) pre[sl + 1] = pre[sl] + __shfl_sync(FULL, npx, sl);
     const int total = pre[FPW];
+#ifdef MM_PROF
+    if (MODE == MODE_HARD && p.prof && lane == 0 && gwarp < 16384) p.prof[((size_t)1 * 16384 + gwarp) * 4 + 3] = (unsigned long long)total;
+#endif
     if (lane < FPW) {
         int mine = 0;
         #pragma unroll
@@ -196,21 +200,85 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
     }
 }
 
-// hard pass kernel: one warp per 8 faces
-__global__ void __launch_bounds__(256)
+// hard pass kernel.  Set-up per warp as in scatter_warp (lanes 0..7: record -> smem, exact tight rectangle), but the (face, pixel)
+// pairs of the CTA's 64 faces are numbered TOGETHER and dealt to its 256 threads: a warp's 8 faces hold between 24 and 655
+// pairs at cfg-2 (median 91) and a warp's run time follows its pair count (per-warp timeline, profiles/r2_notes.md: correlation
+// 0.67, slowest warp 10 us in a kernel whose median warp takes 4.6 us) -- and the kernel, one wave, lasts as long as its
+// slowest warp.  Over 64 faces the counts even out.  The slot search is a 6-step binary search over the shared prefix.
+#define HARD_WARPS 8
+__global__ void __launch_bounds__(32 * HARD_WARPS)
 k_scatter_hard(const mm_raster_params p)
 {
     mm_pdl_prologue((p.pdl_late & 1) != 0);
-    __shared__ WarpQ s_wq[8];
+    __shared__ WarpQ s_wq[HARD_WARPS];
+    __shared__ int s_pre[HARD_WARPS * FPW + 1];
     if (p.nclr) {                                      // the hard pass is issue-bound and leaves the memory system idle: clear
         const size_t nthreads = (size_t)gridDim.x * blockDim.x;      // the step's texture-gradient buffer on the side
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nclr; i += nthreads) p.clr[i] = z;
     }
-    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // warp w of CTA c is "warp" w * gridDim.x + c of the batch-wide dealing: the CTA's 8 warps sit in 8 different image groups,
+    // so its 64 faces come from (up to) 64 different images and every CTA sees the same mix of near and far cameras (with 8
+    // CONSECUTIVE warps a CTA held 8 neighbouring faces of the same 8 images: 795 pairs at the median, 3143 at the maximum)
     const int nwarps = (p.B * p.F + FPW - 1) / FPW;
+    const int gwarp = (warp * (int)gridDim.x + (int)blockIdx.x < nwarps) ? warp * (int)gridDim.x + (int)blockIdx.x : nwarps;
     MM_PROF_MARK(p.prof, 1, gwarp, 0);
-    if (gwarp < nwarps) scatter_warp<MODE_HARD>(p, s_wq[threadIdx.x >> 5], gwarp, nwarps);
+    // ---- set-up: lanes 0..7 of every warp own one face each (dealt with a stride of the warp count: 8 different images)
+    if (lane < FPW) {
+        WarpQ& wq = s_wq[warp];
+        const int slot = lane;
+        const int fid = slot * nwarps + gwarp;
+        int ix0 = 0, ix1 = -1, iy0 = 0, iy1 = -1;
+        wq.img[slot] = 0; wq.face[slot] = 0;
+        if (gwarp < nwarps && fid < p.B * p.F) {
+            const int b = fid / p.F, f = fid - b * p.F;
+            const FaceRec r = load_rec(p.frec + (size_t)b * p.F * MM_REC_FLOATS, f);
+            wq.rec[0][slot] = r.ax; wq.rec[1][slot] = r.ay; wq.rec[2][slot] = r.bx; wq.rec[3][slot] = r.by;
+            wq.rec[4][slot] = r.cx; wq.rec[5][slot] = r.cy; wq.rec[6][slot] = r.az; wq.rec[7][slot] = r.bz;
+            wq.rec[8][slot] = r.cz; wq.img[slot] = b; wq.face[slot] = f;
+            const uint4 rc = p.frect[fid];                 // exact tight rectangle (empty for a back face), from the vertex stage
+            rect_unpack(rc.x, rc.y, ix0, ix1, iy0, iy1);
+        }
+        const int w = ix1 - ix0 + 1, h = iy1 - iy0 + 1;
+        wq.ix0[slot] = ix0; wq.iy0[slot] = iy0; wq.w[slot] = w > 0 ? w : 1;
+        wq.rw[slot] = __frcp_rn((float)(w > 0 ? w : 1));
+        s_pre[1 + warp * FPW + slot] = (w > 0 && h > 0) ? w * h : 0;
+    }
+    __syncthreads();
+    // ---- inclusive prefix of the 64 pair counts (warp 0, two values per lane)
+    if (warp == 0) {
+        int v0 = s_pre[1 + lane], v1 = s_pre[33 + lane];
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t0 = __shfl_up_sync(FULL, v0, o), t1 = __shfl_up_sync(FULL, v1, o);
+            if (lane >= o) { v0 += t0; v1 += t1; }
+        }
+        const int half = __shfl_sync(FULL, v0, 31);
+        s_pre[1 + lane] = v0; s_pre[33 + lane] = half + v1;
+        if (lane == 0) s_pre[0] = 0;
+    }
+    __syncthreads();
+    const int total = s_pre[HARD_WARPS * FPW];
+#ifdef MM_PROF
+    if (p.prof && lane == 0 && gwarp < 16384) p.prof[((size_t)1 * 16384 + gwarp) * 4 + 3] = (unsigned long long)total;
+#endif
+    // ---- the CTA's pairs, dealt to its 256 threads round-robin
+    #pragma unroll 1
+    for (int k = threadIdx.x; k < total; k += 32 * HARD_WARPS) {
+        int g = 0;
+        #pragma unroll
+        for (int step = HARD_WARPS * FPW / 2; step > 0; step >>= 1) g += (s_pre[g + step] <= k) ? step : 0;
+        WarpQ& wq = s_wq[g >> 3];
+        const int slot = g & 7;
+        const int local = k - s_pre[g];
+        const int w = wq.w[slot];
+        int dy = (int)(((float)local + 0.5f) * wq.rw[slot]);
+        int dx = local - dy * w;
+        if (dx < 0) { --dy; dx += w; } else if (dx >= w) { ++dy; dx -= w; }
+        const int ix = wq.ix0[slot] + dx, iy = wq.iy0[slot] + dy;
+        eval_pair<MODE_HARD>(p, wq, ((uint32_t)slot << 24) | ((uint32_t)iy << 12) | (uint32_t)ix, 0.0f, 0.0f);
+    }
     MM_PROF_MARK(p.prof, 1, gwarp, 2);
 }
 
@@ -308,7 +376,7 @@ cudaError_t mm_launch_geom_fwd(const mm_ctx* c, const mm_raster_params& p, cudaS
 {
     const bool pdl = c->pdl != 0;
     const int warps = (p.B * c->F + FPW - 1) / FPW;
-    cudaError_t e = mm_launch(k_scatter_hard, dim3((warps + 7) / 8), dim3(256), 0, s, pdl, p);
+    cudaError_t e = mm_launch(k_scatter_hard, dim3((warps + HARD_WARPS - 1) / HARD_WARPS), dim3(32 * HARD_WARPS), 0, s, pdl, p);
     if (e != cudaSuccess) return e;
     const int nw = (p.B * c->F + SF_FPW - 1) / SF_FPW;
     return mm_launch(k_soft_fwd, dim3((nw + SF_WARPS - 1) / SF_WARPS), dim3(32 * SF_WARPS), 0, s, pdl, p);

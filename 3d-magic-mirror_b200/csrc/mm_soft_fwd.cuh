@@ -9,49 +9,6 @@ namespace {
 #define FULL 0xffffffffu
 #endif
 
-struct PixRange { int ix0, ix1, iy0, iy1; };
-
-// Conservative pixel-index range, clipped to the image, of the scaled-NDC box [xl,xh) x [yl,yh)
-// (the exact half-open tests are redone per pixel).  Returns false if empty.
-__device__ __forceinline__ bool pix_range(const mm_raster_params& p, float xl, float xh, float yl, float yh, PixRange& r)
-{
-    const float inv_sx = 1.0f / p.sx, inv_sy = 1.0f / p.sy;
-    float fx_lo = (xl * inv_sx + (float)(p.W - 1)) * 0.5f;
-    float fx_hi = (xh * inv_sx + (float)(p.W - 1)) * 0.5f;
-    float fy_lo = ((float)(p.H - 1) - yh * inv_sy) * 0.5f;
-    float fy_hi = ((float)(p.H - 1) - yl * inv_sy) * 0.5f;
-    // NaN/Inf coordinates (vertex on the camera plane) stay conservative: treat as "everywhere"
-    if (!(fx_lo == fx_lo) || !(fx_hi == fx_hi)) { fx_lo = -4.0f; fx_hi = 1.0e6f; }
-    if (!(fy_lo == fy_lo) || !(fy_hi == fy_hi)) { fy_lo = -4.0f; fy_hi = 1.0e6f; }
-    fx_lo = fminf(fmaxf(fx_lo, -4.0f), 1.0e6f); fx_hi = fminf(fmaxf(fx_hi, -4.0f), 1.0e6f);
-    fy_lo = fminf(fmaxf(fy_lo, -4.0f), 1.0e6f); fy_hi = fminf(fmaxf(fy_hi, -4.0f), 1.0e6f);
-    r.ix0 = max((int)floorf(fx_lo), 0);
-    r.ix1 = min((int)ceilf(fx_hi), p.W - 1);
-    r.iy0 = max((int)floorf(fy_lo), 0);
-    r.iy1 = min((int)ceilf(fy_hi), p.H - 1);
-    return r.ix0 <= r.ix1 && r.iy0 <= r.iy1;
-}
-
-// EXACT pixel rectangle of a face's bbox (tight, or enlarged by boxlen: DIBR_SPEC A.4) under the reference's half-open
-// fp32 test  xmin <= px < xmax, ymin <= py < ymax: conservative float->int estimate, then <= 2 correction steps per side
-// with the very comparison the reference uses (pixel centres are monotone in the index, so the exact set is a rectangle).
-__device__ __forceinline__ void exact_rect(const mm_raster_params& p, const FaceRec& r, bool enlarged,
-                                           int& ix0, int& ix1, int& iy0, int& iy1)
-{
-    float xmin = fminf(fminf(r.ax, r.bx), r.cx), xmax = fmaxf(fmaxf(r.ax, r.bx), r.cx);
-    float ymin = fminf(fminf(r.ay, r.by), r.cy), ymax = fmaxf(fmaxf(r.ay, r.by), r.cy);
-    if (enlarged) { xmin = SUB(xmin, p.blen); xmax = ADD(xmax, p.blen); ymin = SUB(ymin, p.blen); ymax = ADD(ymax, p.blen); }
-    PixRange pr;
-    ix0 = 0; ix1 = -1; iy0 = 0; iy1 = -1;
-    if (pix_range(p, xmin, xmax, ymin, ymax, pr)) {
-        ix0 = pr.ix0; ix1 = pr.ix1; iy0 = pr.iy0; iy1 = pr.iy1;
-        while (ix0 <= ix1 && pix_x(ix0, p.W, p.sx) < xmin) ++ix0;
-        while (ix1 >= ix0 && pix_x(ix1, p.W, p.sx) >= xmax) --ix1;
-        while (iy0 <= iy1 && pix_y(iy0, p.H, p.sy) >= ymax) ++iy0;      // y decreases with the row index
-        while (iy1 >= iy0 && pix_y(iy1, p.H, p.sy) < ymin) --iy1;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------- soft pass forward
 // The candidates of the soft pass are the UNCOVERED pixels inside a face's enlarged bbox -- for most faces (the interior of
 // the object) there are none.  The pair engine above found that out with one 8-byte zbuf load + ~50 bookkeeping
@@ -170,7 +127,8 @@ __device__ __forceinline__ void soft_fwd_role(const mm_raster_params& p, SoftQ& 
             wq.rec[0][slot] = r.ax; wq.rec[1][slot] = r.ay; wq.rec[2][slot] = r.bx; wq.rec[3][slot] = r.by;
             wq.rec[4][slot] = r.cx; wq.rec[5][slot] = r.cy; wq.img[slot] = b; wq.face[slot] = f;
         }
-        exact_rect(p, r, true, ix0, ix1, iy0, iy1);
+        const uint4 rc = p.frect[fid];                        // exact enlarged rectangle, from the vertex stage
+        rect_unpack(rc.z, rc.w, ix0, ix1, iy0, iy1);
     }
     __syncwarp();
     // ---- (row, 32-column block) segments of the face's rectangle, row-major; this lane takes segments sub, sub+4, ..

@@ -11,7 +11,7 @@
 // the raster backward plus the optional upstream gradient of `face_normals`, and
 // chains through normals, projection, transform and the look-at construction down
 // to vertices, azimuth, elevation, distance and bias.
-#include "mm_common.cuh"
+#include "mm_device.cuh"
 #include "mm_camera.cuh"
 #include <math_constants.h>
 #include <cooperative_groups.h>
@@ -32,6 +32,10 @@ struct VertexFwdParams {
     uint4* clr0; size_t n0;
     uint4* clr1; size_t n1;
     unsigned long long* prof;
+    // the faces' exact pixel rectangles for the hard and the soft pass (face_rects; NULL: vertex stage alone)
+    uint4* frect;
+    int H, W;
+    float sx, sy, blen;
 };
 
 __global__ void __launch_bounds__(MM_VTHREADS)
@@ -98,6 +102,14 @@ k_vertex_fwd(const VertexFwdParams q,
                                      __fmul_rn(svi[i1 * 2], q.multiplier), __fmul_rn(svi[i1 * 2 + 1], q.multiplier));
         rec[f * 3 + 1] = make_float4(__fmul_rn(svi[i2 * 2], q.multiplier), __fmul_rn(svi[i2 * 2 + 1], q.multiplier), az, bz);
         rec[f * 3 + 2] = make_float4(cz, nx, ny, nz);
+        if (q.frect) {
+            FaceRec r;
+            r.ax = __fmul_rn(svi[i0 * 2], q.multiplier); r.ay = __fmul_rn(svi[i0 * 2 + 1], q.multiplier);
+            r.bx = __fmul_rn(svi[i1 * 2], q.multiplier); r.by = __fmul_rn(svi[i1 * 2 + 1], q.multiplier);
+            r.cx = __fmul_rn(svi[i2 * 2], q.multiplier); r.cy = __fmul_rn(svi[i2 * 2 + 1], q.multiplier);
+            r.az = az; r.bz = bz; r.cz = cz; r.nx = nx; r.ny = ny; r.nz = nz;
+            q.frect[(size_t)b * F + f] = face_rects(q, r);
+        }
         if (face_normals) {
             float* fn = face_normals + ((size_t)b * F + f) * 3;
             fn[0] = nx; fn[1] = ny; fn[2] = nz;
@@ -383,9 +395,10 @@ __global__ void k_export_faces(int V, int F, float multiplier, const int32_t* __
 cudaError_t mm_launch_vertex_fwd(const mm_ctx* c, int B, const float* vertices, const float* azim, const float* elev,
                           const float* dist, const float* bias, float* frec,
                           float* vimg, float* face_normals, float* gfacc_zero, long long* img_fwd, long long* img_bwd,
-                          void* clr0, size_t bytes0, void* clr1, size_t bytes1, cudaStream_t s)
+                          void* clr0, size_t bytes0, void* clr1, size_t bytes1, uint4* frect, cudaStream_t s)
 {
     VertexFwdParams q;
+    q.frect = frect; q.H = c->H; q.W = c->W; q.sx = c->sx; q.sy = c->sy; q.blen = c->blen;
     q.clr0 = (uint4*)clr0; q.n0 = bytes0 / 16; q.clr1 = (uint4*)clr1; q.n1 = bytes1 / 16; q.prof = c->prof;
     q.V = c->V; q.F = c->F; q.nchunks = c->nchunks;
     q.proj_x = c->proj_x; q.proj_y = c->proj_y; q.multiplier = c->multiplier;

@@ -77,6 +77,15 @@ for r in range(reps):
                 s2, e2 = (t[k, mm_, 0] - t0) / 1e3, (t[k, mm_, 2] - t0) / 1e3
                 r2 = (t[k, mm_, 1] - t0) / 1e3
                 print("    overflow-role CTAs n=%d start %s | listed %s | end %s | run %s ; busy (run > 2 us): %d" % (mm_.sum(), q(s2), q(r2), q(e2), q(e2 - s2), int(((e2 - s2) > 2.0).sum())))
+        if k == 1:                                     # hard pass: run time against the warp's (face, pixel) pairs
+            pairs = t[k, m, 3]
+            run = e - s
+            print("    start percentiles 50/90/95/99/100: %s" % q(s, (50, 90, 95, 99, 100)))
+            for lo, hi in ((0, 3), (3, 5), (5, 7), (7, 9), (9, 99)):
+                sel = (run >= lo) & (run < hi)
+                if sel.any():
+                    print("    run %2d-%2d us: %5d warps, pairs p50/max %5d/%5d, start p50 %.1f" % (lo, hi, sel.sum(), np.median(pairs[sel]), pairs[sel].max(), np.median(s[sel])))
+            print("    all warps: pairs sum %d, p50 %d, p90 %d, max %d; corr(run, pairs) %.2f" % (pairs.sum(), np.median(pairs), np.percentile(pairs, 90), pairs.max(), np.corrcoef(run, pairs)[0, 1]))
         if k == 2:                                     # soft forward: run time against the warp's row-walk length and candidates
             extra = t[k, m, 3].astype(np.int64)
             mseg, ncand = extra >> 32, extra & 0xffffffff
