@@ -7,11 +7,12 @@
 // bookkeeping: ncu showed ~4500 warp-instructions per 8x4-pixel tile for ~100 useful (pixel, face) pairs.  This file
 // SCATTERS instead: the unit of work is a face.
 //
-//   k_scatter_hard  a warp owns 8 faces (of 8 different images); the (face, pixel) pairs of their EXACT tight-bbox rectangles are
-//                 numbered and dealt to the 32 lanes; a pair runs the exact DIB-R inside test + depth and resolves visibility
-//                 with ONE 64-bit atomicMax on a packed (order-preserving depth << 32 | ~face) key.  max == "largest z, then
-//                 smallest face index" == the reference's ordered scan with its strictly-greater test, so `face_idx` is
-//                 bit-exact and independent of thread order.  No binning, no face lists.
+//   k_scatter_hard  a CTA owns 64 faces (8 warps x 8, from all image groups of the batch); the (face, pixel) pairs of their EXACT
+//                 tight-bbox rectangles (computed once by the vertex stage: frect) are numbered and dealt to the 256 threads; a
+//                 pair runs the exact DIB-R inside test + depth and resolves visibility with ONE 64-bit atomicMax on a packed
+//                 (order-preserving depth << 32 | ~face) key.  max == "largest z, then smallest face index" == the reference's
+//                 ordered scan with its strictly-greater test, so `face_idx` is bit-exact and independent of thread order.  No
+//                 binning, no face lists.
 //   k_soft_fwd     (mm_soft_fwd.cuh) all faces: walk the bbox enlarged by `boxlen` against the coverage bitmap; for every
 //                 UNCOVERED pixel inside (exact half-open test) evaluate the DIB-R distance / probability once and fold
 //                 log(1 - p) and a candidate count into the pixel's 64-bit accumulator with ONE integer atomicAdd (fixed
@@ -21,7 +22,7 @@
 //                 mm_soft_fwd.cuh, replays the reference's ordered scan over all faces, one CTA per pixel, and stores the exact
 //                 truncated product; the forward runs it inside the shading kernel, there is no launch of its own.)
 //   k_soft_bwd     ONE launch: CTAs >= novf replay the pair list (one pair per lane, vector REDs into the per-face
-//                 accumulators; if the list overflowed its buffer: the bbox walk again, scatter_warp<SOFT_BWD>), the rest redo
+//                 accumulators; if the list overflowed its buffer: the bbox walk again, scatter_warp_bwd), the rest redo
 //                 the truncated pixels and scatter the gradients of exactly those knum candidates.
 //   Backward re-derives every probability from the face records instead of storing Kaolin's knum-deep side buffers
 //   (B*H*W*30*(4+8+1) B = 307 MB at B=48,128^2).
@@ -30,17 +31,16 @@
 
 namespace {
 
-// ---------------------------------------------------------------------------------------------- the scatter engine
-// A warp owns FPW = 8 consecutive faces.  Set-up (8 lanes): load the record, compute the bbox (tight / enlarged) and
-// turn the half-open fp32 bbox test into an EXACT pixel rectangle (conservative float->int estimate, then <= 2
-// correction steps per side with the very comparison the reference uses; pixel centres are monotone in the index).
-// Every (face, pixel) pair of the 8 rectangles then gets a global number; the pairs are dealt to the 32 lanes
-// round-robin, so the warp is balanced whatever the face sizes, and no per-pixel bbox test is left.
-//   hard pass : every pair runs the inside test + depth (2 IEEE divisions) and, if inside, one atomicMax.
-//   soft pass : the expensive arithmetic applies only to UNCOVERED pixels, a sparse subset; running it inside the
-//               per-pair loop measured 80 warp-instructions per useful pair (~10 % lane utilisation).  So the loop
-//               only filters (one 8-byte load), ballot-compacts the qualifying pairs into a small shared-memory queue,
-//               and whenever 32 are waiting the whole warp evaluates them, one pair per lane.
+// ---------------------------------------------------------------------------------------------- the pair engine
+// FPW = 8 faces per warp; every face comes with its EXACT pixel rectangle (frect: the reference's half-open fp32 bbox test
+// turned into index ranges by the vertex stage), so the (face, pixel) pairs of a group of faces can be NUMBERED and dealt to
+// the lanes round-robin: balanced whatever the face sizes, and no per-pixel bbox test is left.
+//   hard pass (k_scatter_hard): pairs of a CTA's 64 faces over its 256 threads; every pair runs the inside test + depth
+//              (2 IEEE divisions) and, if inside, one atomicMax + one atomicOr.
+//   soft backward FALLBACK (scatter_warp_bwd; only if the forward's pair list overflowed its buffer): pairs of a warp's 8
+//              faces over its 32 lanes; the loop only filters (uncovered and not truncated: two 8-byte loads),
+//              ballot-compacts the qualifying pairs into a small shared-memory queue, and whenever 32 are waiting the
+//              whole warp evaluates them, one pair per lane.
 #define FPW 8
 
 struct WarpQ {
@@ -54,8 +54,6 @@ struct WarpQ {
     float facc[6][FPW];      // backward: corner-gradient accumulators per slot
 };
 
-enum { MODE_HARD = 0, MODE_SOFT_BWD = 2 };
-
 __device__ __forceinline__ FaceRec slot_rec(const WarpQ& wq, int slot) {
     FaceRec r;
     r.ax = wq.rec[0][slot]; r.ay = wq.rec[1][slot]; r.bx = wq.rec[2][slot]; r.by = wq.rec[3][slot];
@@ -64,47 +62,34 @@ __device__ __forceinline__ FaceRec slot_rec(const WarpQ& wq, int slot) {
     return r;
 }
 
-// one queued pair, evaluated by one lane (no warp collectives in here: the tail of the queue runs divergent)
-template <int MODE>
-__device__ __forceinline__ void eval_pair(const mm_raster_params& p, WarpQ& wq, uint32_t e, float kz, float inv_mult)
+// one queued pair of the soft backward's fallback walk, evaluated by one lane (no warp collectives in here: the tail of the
+// queue runs divergent)
+__device__ __forceinline__ void eval_pair_bwd(const mm_raster_params& p, WarpQ& wq, uint32_t e, float kz, float inv_mult)
 {
     const int slot = (int)(e >> 24), iy = (int)((e >> 12) & 0xfffu), ix = (int)(e & 0xfffu);
     const int b = wq.img[slot];
     const size_t HW = (size_t)p.H * p.W;
     const size_t pix = (size_t)iy * p.W + ix;
-    const float px = pix_x(ix, p.W, p.sx), py = pix_y(iy, p.H, p.sy);
-    const FaceRec r = slot_rec(wq, slot);
-    if (MODE == MODE_HARD) {
-        Bary bb;
-        if (!bary_eval_inside(r, px, py, p.eps, bb)) return;
-        const float zz = ADD(ADD(MUL(bb.w0, r.az), MUL(bb.w1, r.bz)), MUL(bb.w2, r.cz));
-        atomicMax(p.zbuf + (size_t)b * HW + pix, depth_key(zz, wq.face[slot]));
-        atomicOr(p.cov + ((size_t)b * p.H + iy) * p.covw + (ix >> 5), 1u << (ix & 31));
-    } else {
-        const float g = gsoft_at(p, b, pix);
-        const float soft = lacc_soft(p.lacc[(size_t)b * HW + pix]);      // (candidates are uncovered pixels)
-        if (g == 0.0f || !(soft > 0.0f)) return;
-        float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-        soft_pair_grad(p, r, px, py, kz, inv_mult, g, 1.0f - soft, ga);
-        #pragma unroll
-        for (int k = 0; k < 6; ++k) if (ga[k] != 0.0f) atomicAdd(&wq.facc[k][slot], ga[k]);
-    }
+    const float g = gsoft_at(p, b, pix);
+    const float soft = lacc_soft(p.lacc[(size_t)b * HW + pix]);      // (candidates are uncovered pixels)
+    if (g == 0.0f || !(soft > 0.0f)) return;
+    float ga[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    soft_pair_grad(p, slot_rec(wq, slot), pix_x(ix, p.W, p.sx), pix_y(iy, p.H, p.sy), kz, inv_mult, g, 1.0f - soft, ga);
+    #pragma unroll
+    for (int k = 0; k < 6; ++k) if (ga[k] != 0.0f) atomicAdd(&wq.facc[k][slot], ga[k]);
 }
 
-template <int MODE>
-__device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& wq, const int gwarp, const int nwarps)
+__device__ __forceinline__ void scatter_warp_bwd(const mm_raster_params& p, WarpQ& wq, const int gwarp, const int nwarps)
 {
     const int lane = threadIdx.x & 31;
     const size_t HW = (size_t)p.H * p.W;
     const float kz = p.sigmainv / p.multiplier / p.multiplier;
     const float inv_mult = 1.0f / p.multiplier;
-    // ---- set-up: lanes 0..7 each own one face of the warp: record -> smem, EXACT pixel rectangle of its bbox
+    // ---- set-up: lanes 0..7 each own one face of the warp: record -> smem, enlarged rectangle
     int npx = 0;
     if (lane < FPW) {
         const int slot = lane;
-        // faces are dealt to the warps with a stride of the warp count: a warp's 8 faces come from 8 different images,
-        // so near-camera images (faces ~30x larger) no longer load a few SMs (ncu r1c: busiest SM 1.7x the average)
-        const int fid = slot * nwarps + gwarp;
+        const int fid = slot * nwarps + gwarp;       // (faces dealt with a stride of the warp count: 8 different images)
         int ix0 = 0, ix1 = -1, iy0 = 0, iy1 = -1;
         if (fid < p.B * p.F) {
             const int b = fid / p.F, f = fid - b * p.F;
@@ -112,18 +97,15 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
             wq.rec[0][slot] = r.ax; wq.rec[1][slot] = r.ay; wq.rec[2][slot] = r.bx; wq.rec[3][slot] = r.by;
             wq.rec[4][slot] = r.cx; wq.rec[5][slot] = r.cy; wq.rec[6][slot] = r.az; wq.rec[7][slot] = r.bz;
             wq.rec[8][slot] = r.cz; wq.img[slot] = b; wq.face[slot] = f;
-            const uint4 rc = p.frect[fid];                           // exact rectangles from the vertex stage
-            if (MODE == MODE_HARD) rect_unpack(rc.x, rc.y, ix0, ix1, iy0, iy1);
-            else rect_unpack(rc.z, rc.w, ix0, ix1, iy0, iy1);
+            const uint4 rc = p.frect[fid];
+            rect_unpack(rc.z, rc.w, ix0, ix1, iy0, iy1);
         } else { wq.img[slot] = 0; wq.face[slot] = 0; }
         const int w = ix1 - ix0 + 1, h = iy1 - iy0 + 1;
         npx = (w > 0 && h > 0) ? w * h : 0;
         wq.ix0[slot] = ix0; wq.iy0[slot] = iy0; wq.w[slot] = w > 0 ? w : 1;
         wq.rw[slot] = __frcp_rn((float)(w > 0 ? w : 1));
-        if (MODE == MODE_SOFT_BWD) {
-            #pragma unroll
-            for (int k = 0; k < 6; ++k) wq.facc[k][slot] = 0.0f;
-        }
+        #pragma unroll
+        for (int k = 0; k < 6; ++k) wq.facc[k][slot] = 0.0f;
     }
     // exclusive prefix of the 8 pixel counts (every lane keeps all of them: the slot search below is 8 compares)
     int pre[FPW + 1];
@@ -131,9 +113,6 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
     #pragma unroll
     for (int sl = 0; sl < FPW; ++sl) pre[sl + 1] = pre[sl] + __shfl_sync(FULL, npx, sl);
     const int total = pre[FPW];
-#ifdef MM_PROF
-    if (MODE == MODE_HARD && p.prof && lane == 0 && gwarp < 16384) p.prof[((size_t)1 * 16384 + gwarp) * 4 + 3] = (unsigned long long)total;
-#endif
     if (lane < FPW) {
         int mine = 0;
         #pragma unroll
@@ -142,7 +121,7 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
     }
     __syncwarp();
 
-    // ---- the warp's (face, pixel) pairs, dealt to the 32 lanes round-robin: perfectly balanced whatever the face sizes
+    // ---- the warp's (face, pixel) pairs, dealt to the 32 lanes round-robin
     int qn = 0;
     const uint32_t lt = (1u << lane) - 1u;
     #pragma unroll 1
@@ -161,16 +140,8 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
             if (dx < 0) { --dy; dx += w; } else if (dx >= w) { ++dy; dx -= w; }
             const int ix = wq.ix0[slot] + dx, iy = wq.iy0[slot] + dy;
             entry = ((uint32_t)slot << 24) | ((uint32_t)iy << 12) | (uint32_t)ix;
-            if (MODE == MODE_HARD) cand = true;
-            else {
-                const size_t pg = (size_t)wq.img[slot] * HW + (size_t)iy * p.W + ix;
-                cand = (p.zbuf[pg] == 0ull);                                        // covered pixels get soft = 1
-                if (MODE == MODE_SOFT_BWD && cand) cand = lacc_count(p.lacc[pg]) != (int)MM_LACC_OVF;
-            }
-        }
-        if (MODE == MODE_HARD) {                                   // every pair needs the inside test: no compaction
-            if (cand) eval_pair<MODE>(p, wq, entry, kz, inv_mult);
-            continue;
+            const size_t pg = (size_t)wq.img[slot] * HW + (size_t)iy * p.W + ix;
+            cand = (p.zbuf[pg] == 0ull) && lacc_count(p.lacc[pg]) != (int)MM_LACC_OVF;    // uncovered, not truncated
         }
         const uint32_t m = __ballot_sync(FULL, cand);
         if (cand) wq.q[qn + __popc(m & lt)] = entry;
@@ -180,27 +151,25 @@ __device__ __forceinline__ void scatter_warp(const mm_raster_params& p, WarpQ& w
             const uint32_t e = wq.q[lane];
             const uint32_t carry = wq.q[32 + lane];
             __syncwarp();
-            eval_pair<MODE>(p, wq, e, kz, inv_mult);
+            eval_pair_bwd(p, wq, e, kz, inv_mult);
             qn -= 32;
             if (lane < qn) wq.q[lane] = carry;
             __syncwarp();
         }
     }
-    if (MODE != MODE_HARD && lane < qn) eval_pair<MODE>(p, wq, wq.q[lane], kz, inv_mult);
-    if (MODE == MODE_SOFT_BWD) {
-        __syncwarp();
-        for (int idx = lane; idx < 6 * FPW; idx += 32) {
-            const int kk = idx / FPW, sl = idx - kk * FPW;
-            const int fg = sl * nwarps + gwarp;
-            if (fg < p.B * p.F) {
-                const float v = wq.facc[kk][sl];
-                if (v != 0.0f) atomicAdd(p.gfacc + (size_t)fg * MM_GF + kk, v);
-            }
+    if (lane < qn) eval_pair_bwd(p, wq, wq.q[lane], kz, inv_mult);
+    __syncwarp();
+    for (int idx = lane; idx < 6 * FPW; idx += 32) {
+        const int kk = idx / FPW, sl = idx - kk * FPW;
+        const int fg = sl * nwarps + gwarp;
+        if (fg < p.B * p.F) {
+            const float v = wq.facc[kk][sl];
+            if (v != 0.0f) atomicAdd(p.gfacc + (size_t)fg * MM_GF + kk, v);
         }
     }
 }
 
-// hard pass kernel.  Set-up per warp as in scatter_warp (lanes 0..7: record -> smem, exact tight rectangle), but the (face, pixel)
+// hard pass kernel.  Set-up per warp (lanes 0..7: record -> smem, the face's exact tight rectangle); the (face, pixel)
 // pairs of the CTA's 64 faces are numbered TOGETHER and dealt to its 256 threads: a warp's 8 faces hold between 24 and 655
 // pairs at cfg-2 (median 91) and a warp's run time follows its pair count (per-warp timeline, profiles/r2_notes.md: correlation
 // 0.67, slowest warp 10 us in a kernel whose median warp takes 4.6 us) -- and the kernel, one wave, lasts as long as its
@@ -277,7 +246,14 @@ k_scatter_hard(const mm_raster_params p)
         int dx = local - dy * w;
         if (dx < 0) { --dy; dx += w; } else if (dx >= w) { ++dy; dx -= w; }
         const int ix = wq.ix0[slot] + dx, iy = wq.iy0[slot] + dy;
-        eval_pair<MODE_HARD>(p, wq, ((uint32_t)slot << 24) | ((uint32_t)iy << 12) | (uint32_t)ix, 0.0f, 0.0f);
+        // exact DIB-R inside test + depth, one atomicMax on the packed (depth, ~face) key, one bit of the coverage bitmap
+        Bary bb;
+        const FaceRec fr = slot_rec(wq, slot);
+        if (!bary_eval_inside(fr, pix_x(ix, p.W, p.sx), pix_y(iy, p.H, p.sy), p.eps, bb)) continue;
+        const float zz = ADD(ADD(MUL(bb.w0, fr.az), MUL(bb.w1, fr.bz)), MUL(bb.w2, fr.cz));
+        const int b = wq.img[slot];
+        atomicMax(p.zbuf + ((size_t)b * p.H + iy) * p.W + ix, depth_key(zz, wq.face[slot]));
+        atomicOr(p.cov + ((size_t)b * p.H + iy) * p.covw + (ix >> 5), 1u << (ix & 31));
     }
     MM_PROF_MARK(p.prof, 1, gwarp, 2);
 }
@@ -308,7 +284,7 @@ __device__ __forceinline__ void soft_bwd_list_role(const mm_raster_params& p, Wa
         const int nwarps = (p.B * p.F + FPW - 1) / FPW;           // shapes): redo the bbox walk with the filtering pair engine
         const int wstride = (nvblocks * SB_THREADS) >> 5;
         for (int gw = (vblock * SB_THREADS + threadIdx.x) >> 5; gw < nwarps; gw += wstride) {
-            scatter_warp<MODE_SOFT_BWD>(p, s_wq[threadIdx.x >> 5], gw, nwarps);
+            scatter_warp_bwd(p, s_wq[threadIdx.x >> 5], gw, nwarps);
             __syncwarp();
         }
         return;
