@@ -309,6 +309,7 @@ int mm_render_backward(mm_ctx* c, int B, const float* vertices, const float* azi
     p.tex = tex; p.lights = lights; p.bg = bg;
     p.g_rgba = g_rgba;
     p.g_tex = g_tex; p.g_bg = no_mask ? g_bg : nullptr;
+    p.gtex_pair = ((Wt & 1) == 0 && ((uintptr_t)g_tex & 7) == 0) ? 1 : 0;
     if (recon_gt) {
         p.gt = recon_gt; p.image_weight = image_weight; p.contour = contour; p.loss_scale = loss_scale;
         p.loss_scale_dev = loss_scale_dev;
@@ -418,6 +419,7 @@ int mm_render_compare_fwd_bwd(mm_ctx* c, int B, const float* vertices, const flo
     p.image_weight = image_weight; p.contour = contour; p.loss_scale = loss_scale;
     p.analytic_loss = 1;
     p.g_tex = g_tex; p.g_bg = no_mask ? g_bg : nullptr;
+    p.gtex_pair = ((Wt & 1) == 0 && ((uintptr_t)g_tex & 7) == 0) ? 1 : 0;
     // H, W multiples of 4: the contour term is tile-local, so d(loss)/d(silhouette) minus its IoU term is emitted by the
     // shading kernel and the geometry backward adds the IoU term from the per-image sums on the fly
     p.gsoft_iou_pending = ((c->H & 3) == 0 && (c->W & 3) == 0) ? 1 : 0;

@@ -156,6 +156,7 @@ struct mm_raster_params {
     int analytic_loss;
     float* gfacc;            // [B,F,MM_GF]
     float* g_tex;            // [B,3,Htp,Wt]
+    int gtex_pair;           // 1: Wt even and g_tex 8-byte aligned (texel pairs may leave as red.v2)
     float* g_bg;             // [B,3,H,W] or NULL
     uint4* clr; size_t nclr;  // buffer the hard pass clears on the side (fused step: the texture-gradient output), 16-byte units
 };
