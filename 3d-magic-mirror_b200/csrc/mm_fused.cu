@@ -76,8 +76,9 @@ __device__ __noinline__ unsigned long long lacc_wait_exact(const unsigned long l
 // (profiles/r1_notes.md).  Splitting the passes lets pass 2 run compacted and at a smaller register footprint.
 #define FUSED_WARPS MM_SH_WARPS
 #ifndef FUSED_MINB
-#define FUSED_MINB 4
-#endif
+#define FUSED_MINB 5         // 96 registers: 5 CTAs per SM.  Round 1 measured register caps as slower; with the lights and the
+#endif                       // schedule in shared memory the only spills at 96 are the five loss accumulators (outside the loops),
+                             // and the fifth CTA per SM is worth 0.6 us at cfg-2, 8 us at cfg-5 (profiles/r2_notes.md section 10)
 #define FUSED_THREADS (32 * FUSED_WARPS)
 #define FUSED_TILE_PX (FT_W * FT_H)
 

@@ -8,6 +8,9 @@ import __graft_entry__ as g
 import bench
 import parity_utils as pu
 mm = g.load_package()
+if os.environ.get("MM_LIB"):          # A/B of another build of the library (tools/probes/lib_ab.py)
+    from magic_mirror_b200 import _lib
+    _lib.LIB_PATH = os.path.join(g.PKG_DIR, os.environ["MM_LIB"])
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 dev = "cuda:0"
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0

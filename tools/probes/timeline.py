@@ -59,17 +59,17 @@ for r in range(reps):
             line += " | wait %s" % q(w)
         print(line)
         if k == 3:                                     # shading: what would a work-ordered dispatch buy?  (greedy list scheduling
-            import heapq                               # of the measured per-CTA run times on the kernel's 4 x SMs slots)
+            import heapq                               # of the measured per-CTA run times on the kernel's 5 x SMs slots)
             st = t[k, :, 0].reshape(-1, 4); en = t[k, :, 2].reshape(-1, 4)
             ok = (st > 0).all(axis=1) & (en > 0).all(axis=1)
             run_cta = ((en.max(axis=1) - st.min(axis=1)) / 1e3)[ok]
-            def makespan(order, slots=148 * 4):
+            def makespan(order, slots=148 * 5):
                 h = [0.0] * slots
                 for r in order: heapq.heapreplace(h, h[0] + r)
                 return max(h)
             two = np.concatenate([run_cta[run_cta > 5.0], run_cta[run_cta <= 5.0]])
             print("    shade CTAs %d: sum of runs / slots %.1f us; list-scheduled makespan: grid order %.1f, longest first %.1f, two classes (> 5 us first) %.1f, shortest first %.1f" % (
-                len(run_cta), run_cta.sum() / (148 * 4), makespan(run_cta), makespan(np.sort(run_cta)[::-1]), makespan(two), makespan(np.sort(run_cta))))
+                len(run_cta), run_cta.sum() / (148 * 5), makespan(run_cta), makespan(np.sort(run_cta)[::-1]), makespan(two), makespan(np.sort(run_cta))))
         if k == 4:                                     # soft_bwd: the overflow-role CTAs (the first 8 * SMs CTAs) separately
             nl = 148 * 16 * 4
             mm_ = m.copy(); mm_[148 * 8 * 4:] = False
