@@ -132,8 +132,8 @@ k_vertex_fwd(const VertexFwdParams q,
 #define VB_CLUSTER 4
 #endif
 #ifndef VB_THREADS
-#define VB_THREADS 384
-#endif
+#define VB_THREADS 512       // (swept in round 2, cluster x threads: 4 x 384 0.0864 ms, 4 x 512 0.0856, 2 x 768 0.0856, 2 x 1024 0.0861,
+#endif                       //  4 x 256 0.0873, 4 x 768 0.0917, 1 x 1024 0.0880, 8 x 256 0.0888)
 #define VB_WARPS (VB_THREADS / 32)
 
 struct VertexBwdParams {
