@@ -305,14 +305,16 @@ __device__ __forceinline__ void soft_bwd_list_role(const mm_raster_params& p, Wa
             const int iy = (int)((e >> 12) & 0xfffu), ix = (int)(e & 0xfffu);
             const int b = (int)(fg / (uint32_t)p.F);
             const size_t pg = (size_t)b * HW + (size_t)iy * p.W + ix;
-            const float g = gsoft_at(p, b, (size_t)iy * p.W + ix);
+            // the face record is fetched TOGETHER with the pixel's words (its address depends on the list entry alone): one
+            // round trip less in a kernel that is a chain of them
+            const float4* q4 = reinterpret_cast<const float4*>(p.frec) + (size_t)fg * 3;
+            const float4 c0 = __ldg(q4), c1 = __ldg(q4 + 1);
             // the silhouette value comes from the workspace's accumulator (bit-identical to the image's alpha plane, which the
             // backward therefore does not need: the caller may have edited the image in place)
             const unsigned long long acc = p.lacc[pg];
+            const float g = gsoft_at(p, b, (size_t)iy * p.W + ix);
             const float soft = lacc_soft(acc);
             if (g != 0.0f && soft > 0.0f && lacc_count(acc) != (int)MM_LACC_OVF) {
-                const float4* q4 = reinterpret_cast<const float4*>(p.frec) + (size_t)fg * 3;
-                const float4 c0 = __ldg(q4), c1 = __ldg(q4 + 1);
                 FaceRec r;
                 r.ax = c0.x; r.ay = c0.y; r.bx = c0.z; r.by = c0.w; r.cx = c1.x; r.cy = c1.y;
                 r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
