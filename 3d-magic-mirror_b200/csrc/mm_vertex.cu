@@ -65,6 +65,13 @@ k_vertex_fwd(const VertexFwdParams q,
         for (size_t i = t; i < q.n0; i += nthreads) q.clr0[i] = z;
         for (size_t i = t; i < q.n1; i += nthreads) q.clr1[i] = z;
     }
+    // this thread's first face: its vertex indices are static data of the ctx -- fetched here, under the camera chain and the
+    // vertex transform, instead of as one more round trip behind them
+    const int per_chunk = (F + q.nchunks - 1) / q.nchunks;
+    const int f_end = min(F, (chunk + 1) * per_chunk);
+    const int f_first = chunk * per_chunk + threadIdx.x;
+    int pi0 = 0, pi1 = 0, pi2 = 0;
+    if (f_first < f_end) { pi0 = faces[f_first * 3]; pi1 = faces[f_first * 3 + 1]; pi2 = faces[f_first * 3 + 2]; }
     if (threadIdx.x == 0) {
         Cam c;
         camera_setup(azim[b], elev[b], dist[b], bias[b * 2], bias[b * 2 + 1], c);
@@ -88,10 +95,9 @@ k_vertex_fwd(const VertexFwdParams q,
     }
     __syncthreads();
     float4* rec = reinterpret_cast<float4*>(frec + (size_t)b * F * MM_REC_FLOATS);
-    const int per_chunk = (F + q.nchunks - 1) / q.nchunks;
-    const int f_end = min(F, (chunk + 1) * per_chunk);
-    for (int f = chunk * per_chunk + threadIdx.x; f < f_end; f += blockDim.x) {
-        const int i0 = faces[f * 3], i1 = faces[f * 3 + 1], i2 = faces[f * 3 + 2];
+    for (int f = f_first; f < f_end; f += blockDim.x) {
+        int i0 = pi0, i1 = pi1, i2 = pi2;            // (the first face's indices were fetched ahead of the two barriers)
+        if (f != f_first) { i0 = faces[f * 3]; i1 = faces[f * 3 + 1]; i2 = faces[f * 3 + 2]; }
         const float ax = svc[i0 * 3], ay = svc[i0 * 3 + 1], az = svc[i0 * 3 + 2];
         const float bx = svc[i1 * 3], by = svc[i1 * 3 + 1], bz = svc[i1 * 3 + 2];
         const float cx = svc[i2 * 3], cy = svc[i2 * 3 + 1], cz = svc[i2 * 3 + 2];
@@ -187,12 +193,17 @@ k_vertex_bwd(const VertexBwdParams q,
         svc[v * 3] = cx; svc[v * 3 + 1] = cy; svc[v * 3 + 2] = cz;
     }
     __syncthreads();
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    MM_PROF_MARK(q.prof, 5, (blockIdx.y * gridDim.x + blockIdx.x) * VB_WARPS + (threadIdx.x >> 5), 1);
+    // (this thread's first face: vertex indices -- static ctx data -- fetched ahead of the wait too)
     const int fper = (F + VB_CLUSTER - 1) / VB_CLUSTER;
     const int f_end = min(F, (rank + 1) * fper);
-    for (int f = rank * fper + threadIdx.x; f < f_end; f += blockDim.x) {
-        const int idx[3] = {faces[f * 3], faces[f * 3 + 1], faces[f * 3 + 2]};
+    const int f_first = rank * fper + threadIdx.x;
+    int pidx[3] = {0, 0, 0};
+    if (f_first < f_end) { pidx[0] = faces[f_first * 3]; pidx[1] = faces[f_first * 3 + 1]; pidx[2] = faces[f_first * 3 + 2]; }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    MM_PROF_MARK(q.prof, 5, (blockIdx.y * gridDim.x + blockIdx.x) * VB_WARPS + (threadIdx.x >> 5), 1);
+    for (int f = f_first; f < f_end; f += blockDim.x) {
+        int idx[3] = {pidx[0], pidx[1], pidx[2]};
+        if (f != f_first) { idx[0] = faces[f * 3]; idx[1] = faces[f * 3 + 1]; idx[2] = faces[f * 3 + 2]; }
         float P[3][3];
         #pragma unroll
         for (int i = 0; i < 3; ++i) { P[i][0] = svc[idx[i] * 3]; P[i][1] = svc[idx[i] * 3 + 1]; P[i][2] = svc[idx[i] * 3 + 2]; }
