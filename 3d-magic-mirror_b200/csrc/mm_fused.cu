@@ -117,27 +117,19 @@ __device__ __forceinline__ void shade_role(const mm_raster_params& p, ShadeSmem&
         int face[4] = {-1, -1, -1, -1};
         float soft[4] = {0.0f, 0.0f, 0.0f, 0.0f}, gmv[4] = {0.0f, 0.0f, 0.0f, 0.0f}, gs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         if (active) {
-            // ---- every streamed input of the 4 pixels, issued up front
-            {
-                const unsigned long long* zb = p.zbuf + (size_t)b * HW + pix0;
-                const unsigned long long* la = p.lacc + (size_t)b * HW + pix0;
-                unsigned long long z[4], l[4] = {0ull, 0ull, 0ull, 0ull};
-                if (VEC) {
-                    const ulonglong2 z0 = *reinterpret_cast<const ulonglong2*>(zb), z1 = *reinterpret_cast<const ulonglong2*>(zb + 2);
-                    z[0] = z0.x; z[1] = z0.y; z[2] = z1.x; z[3] = z1.y;
-                    const ulonglong2 l0 = *reinterpret_cast<const ulonglong2*>(la), l1 = *reinterpret_cast<const ulonglong2*>(la + 2);
-                    l[0] = l0.x; l[1] = l0.y; l[2] = l1.x; l[3] = l1.y;
-                } else {
-                    #pragma unroll
-                    for (int j = 0; j < 4; ++j) { z[j] = (j < n) ? zb[j] : 0ull; l[j] = (j < n) ? la[j] : 0ull; }
-                }
+            // ---- every streamed input of the 4 pixels, issued up front (nothing that might wait, and no call, in between: the
+            // exact-value wait of a truncated pixel below is an opaque call the compiler will not move loads across)
+            const unsigned long long* zb = p.zbuf + (size_t)b * HW + pix0;
+            const unsigned long long* la = p.lacc + (size_t)b * HW + pix0;
+            unsigned long long z[4], l[4] = {0ull, 0ull, 0ull, 0ull};
+            if (VEC) {
+                const ulonglong2 z0 = *reinterpret_cast<const ulonglong2*>(zb), z1 = *reinterpret_cast<const ulonglong2*>(zb + 2);
+                z[0] = z0.x; z[1] = z0.y; z[2] = z1.x; z[3] = z1.y;
+                const ulonglong2 l0 = *reinterpret_cast<const ulonglong2*>(la), l1 = *reinterpret_cast<const ulonglong2*>(la + 2);
+                l[0] = l0.x; l[1] = l0.y; l[2] = l1.x; l[3] = l1.y;
+            } else {
                 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    face[j] = (j < n) ? key_face(z[j]) : -1;
-                    if (MODE != SHADE_BWD && j < n && face[j] < 0 && lacc_count(l[j]) > p.knum && lacc_count(l[j]) != (int)MM_LACC_OVF)
-                        l[j] = lacc_wait_exact(la + j);                  // truncated pixel, exact value on its way
-                    soft[j] = (face[j] >= 0) ? 1.0f : lacc_soft(l[j]);
-                }
+                for (int j = 0; j < 4; ++j) { z[j] = (j < n) ? zb[j] : 0ull; l[j] = (j < n) ? la[j] : 0ull; }
             }
             float bgv[3][4], gtv[4][4], gup[3][4];
             #pragma unroll
@@ -153,6 +145,13 @@ __device__ __forceinline__ void shade_role(const mm_raster_params& p, ShadeSmem&
                 else { gup[ch][0] = gup[ch][1] = gup[ch][2] = gup[ch][3] = 0.0f; }
             }
             if (HAS_GUP) load4<VEC>(p.g_rgba + ((size_t)b * 4 + 3) * HW + pix0, n, gs);      // upstream d/d(silhouette)
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                face[j] = (j < n) ? key_face(z[j]) : -1;
+                if (MODE != SHADE_BWD && j < n && face[j] < 0 && lacc_count(l[j]) > p.knum && lacc_count(l[j]) != (int)MM_LACC_OVF)
+                    l[j] = lacc_wait_exact(la + j);                  // truncated pixel, exact value on its way
+                soft[j] = (face[j] >= 0) ? 1.0f : lacc_soft(l[j]);
+            }
             #pragma unroll
             for (int j = 0; j < 4; ++j) gmv[j] = gtv[3][j];
             // channel by channel, each plane stored as soon as it is complete (keeps the live register set small: the kernel's
