@@ -181,11 +181,6 @@ k_scatter_hard(const mm_raster_params p)
     mm_pdl_prologue((p.pdl_late & 1) != 0);
     __shared__ WarpQ s_wq[HARD_WARPS];
     __shared__ int s_pre[HARD_WARPS * FPW + 1];
-    if (p.nclr) {                                      // the hard pass is issue-bound and leaves the memory system idle: clear
-        const size_t nthreads = (size_t)gridDim.x * blockDim.x;      // the step's texture-gradient buffer on the side
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nclr; i += nthreads) p.clr[i] = z;
-    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // warp w of CTA c is "warp" w * gridDim.x + c of the batch-wide dealing: the CTA's 8 warps sit in 8 different image groups,
     // so its 64 faces come from (up to) 64 different images and every CTA sees the same mix of near and far cameras (with 8
@@ -254,6 +249,14 @@ k_scatter_hard(const mm_raster_params p)
         const int b = wq.img[slot];
         atomicMax(p.zbuf + ((size_t)b * p.H + iy) * p.W + ix, depth_key(zz, wq.face[slot]));
         atomicOr(p.cov + ((size_t)b * p.H + iy) * p.covw + (ix >> 5), 1u << (ix & 31));
+    }
+    // The hard pass is issue-bound and leaves the memory system idle: it clears the step's texture-gradient buffer on the side --
+    // at the END of the CTA: nothing waits for these stores, and in front of the set-up they held every CTA's first loads back
+    // (ncu source page: 15 % of the kernel's stall samples on this loop when it came first).
+    if (p.nclr) {
+        const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nclr; i += nthreads) p.clr[i] = z;
     }
     MM_PROF_MARK(p.prof, 1, gwarp, 2);
 }

@@ -52,6 +52,15 @@ __device__ __forceinline__ void soft_fwd_check(const mm_raster_params& p, const 
     }
 }
 
+// the pair-list entry of candidate e of this warp
+__device__ __forceinline__ void soft_fwd_store_pair(const mm_raster_params& p, const SoftQ& wq, uint32_t e, uint32_t at)
+{
+    if (at < p.plist_cap) {
+        const int slot = (int)(e >> 24);
+        const unsigned long long fg = (unsigned long long)((size_t)wq.img[slot] * p.F + wq.face[slot]);
+        p.plist[at] = (fg << 32) | (unsigned long long)(e & 0xffffffu);
+    }
+}
 // the staged candidates go to the global pair list: ONE atomicAdd for up to SF_DCAP of them (it was one per round of 32: a
 // second round trip at the end of every round); all lanes call it
 __device__ __forceinline__ void soft_fwd_flush(const mm_raster_params& p, const SoftQ& wq, int dn, int lane)
@@ -60,14 +69,7 @@ __device__ __forceinline__ void soft_fwd_flush(const mm_raster_params& p, const 
     uint32_t base = 0u;
     if (lane == 0) base = atomicAdd(p.ovf_count + 1, (uint32_t)dn);
     base = __shfl_sync(FULL, base, 0);
-    for (int i = lane; i < dn; i += 32) {
-        if (base + (uint32_t)i < p.plist_cap) {
-            const uint32_t e = wq.done[i];
-            const int slot = (int)(e >> 24);
-            const unsigned long long fg = (unsigned long long)((size_t)wq.img[slot] * p.F + wq.face[slot]);
-            p.plist[base + i] = (fg << 32) | (unsigned long long)(e & 0xffffffu);
-        }
-    }
+    for (int i = lane; i < dn; i += 32) soft_fwd_store_pair(p, wq, wq.done[i], base + (uint32_t)i);
 }
 
 // ---------------------------------------------------------------------------------------------- shading schedule
@@ -193,20 +195,24 @@ __device__ __forceinline__ void soft_fwd_role(const mm_raster_params& p, SoftQ& 
             else { wd += 4; while (wd >= wd0 + nwd) { wd -= nwd; ++row; } }
         }
     }
-    // the tail of the queue; then the pair list FIRST (its slot allocation is a round trip of its own, which so overlaps the
-    // accumulator atomics still in flight) and the last look at the accumulators' previous words behind it
+    // The end of the warp is a chain of round trips; they are made to overlap: the slots of ALL staged candidates (including the
+    // tail about to be evaluated) are requested from the global pair list FIRST, the tail is evaluated under that round trip,
+    // then the pairs are stored, and the last looks at the accumulators' previous words come behind everything.
+    const int ntot = dn + qn;
+    uint32_t base = 0u;
+    if (lane == 0 && ntot > 0) base = atomicAdd(p.ovf_count + 1, (uint32_t)ntot);
     unsigned long long last_old = 0ull;
     uint32_t last_e = 0u;
     const bool last = lane < qn;
-    if (qn > 0) {
-        last_e = last ? wq.q[lane] : 0u;
-        if (last) last_old = soft_fwd_eval(p, wq, last_e, kz);
-        if (dn + qn > SF_DCAP) { __syncwarp(); soft_fwd_flush(p, wq, dn, lane); dn = 0; __syncwarp(); }
-        if (last) wq.done[dn + lane] = last_e;
-        dn += qn;
+    if (last) {
+        last_e = wq.q[lane];
+        last_old = soft_fwd_eval(p, wq, last_e, kz);
     }
-    __syncwarp();
-    soft_fwd_flush(p, wq, dn, lane);
+    if (ntot > 0) {
+        base = __shfl_sync(FULL, base, 0);
+        for (int i = lane; i < dn; i += 32) soft_fwd_store_pair(p, wq, wq.done[i], base + (uint32_t)i);
+        if (last) soft_fwd_store_pair(p, wq, last_e, base + (uint32_t)(dn + lane));
+    }
     if (pend) soft_fwd_check(p, wq, pend_old, pend_e);
     if (last) soft_fwd_check(p, wq, last_old, last_e);
 #ifdef MM_PROF
