@@ -39,6 +39,7 @@ SIGNATURES = {
     "mm_render_compare_fwd_bwd": (c_int, [_P, c_int] + _RENDER_IN + [_P, c_float, c_float, c_float] + [_P] * 2 + [_P] * 3 +
                                   [_P] * 8 + [_P, c_size_t, _P]),
     "mm_debug_export_faces": (c_int, [_P, c_int, _P, c_size_t, _P, _P, _P, _P]),
+    "mm_debug_workspace_offset": (c_size_t, [_P, c_int, ctypes.c_char_p]),
     "mm_face_normals_forward": (c_int, [_P, c_int] + [_P] * 6 + [_P, c_size_t, _P]),
     "mm_face_normals_backward": (c_int, [_P, c_int] + [_P] * 11 + [_P, c_size_t, _P]),
     "mm_ctx_set_regularizer_topology": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, c_float]),

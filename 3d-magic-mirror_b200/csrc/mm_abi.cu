@@ -601,6 +601,18 @@ int mm_ctx_get_timing(mm_ctx* c, float* ms_host, int capacity) {
     return 7;
 }
 
+size_t mm_debug_workspace_offset(const mm_ctx* c, int B, const char* block)
+{
+    if (!c || B <= 0 || !block) return (size_t)-1;
+    const mm_ws_layout L = mm_ws_make(c, B);
+    const struct { const char* name; size_t off; } tab[] = {
+        {"frec", L.frec}, {"frect", L.frect}, {"zbuf", L.zbuf}, {"lacc", L.lacc}, {"cov", L.cov}, {"ovf_count", L.ovf_count},
+        {"sched_n", L.sched_n}, {"ovf_list", L.ovf_list}, {"sched_list", L.sched_list}, {"plist", L.plist}, {"gsoft", L.gsoft},
+        {"gfacc", L.gfacc}, {"img_fwd", L.img_fwd}, {"img_bwd", L.img_bwd}};
+    for (const auto& t : tab) if (!strcmp(block, t.name)) return t.off;
+    return (size_t)-1;
+}
+
 #ifdef MM_PROF
 // MM_PROF builds only (not part of the ABI): device buffer [6][16384][4] u64 of per-warp time stamps, or NULL
 int mm_debug_profile(mm_ctx* c, unsigned long long* buf) { if (!c) return MM_E_INVALID; c->prof = buf; return MM_OK; }

@@ -218,10 +218,15 @@ int mm_texture_flow_backward(mm_ctx* ctx, int B, int C, int Hi, int Wi, int Ho, 
 int mm_debug_export_faces(mm_ctx* ctx, int B, const void* workspace, size_t workspace_bytes,
                           float* fvi, float* fvz, float* fnz, void* stream);
 
+/* Test / probe hook: byte offset of a named block of the workspace for batch size B ("frec", "frect", "zbuf", "lacc", "cov",
+ * "ovf_count", "sched_n", "ovf_list", "sched_list", "plist", "gsoft", "gfacc", "img_fwd", "img_bwd"; layout: csrc/mm_common.cuh),
+ * or (size_t)-1 for an unknown name.  Lets tests look at the counters and the shading schedule without restating the layout. */
+size_t mm_debug_workspace_offset(const mm_ctx* ctx, int B, const char* block);
+
 /* Measurement hook (bench.py): when enabled, mm_render_compare_fwd_bwd records a CUDA event on
  * `stream` around each of its launch groups.  mm_ctx_get_timing waits for the last call's final event
- * and writes the group durations in milliseconds, in launch order (vertex_fwd, geometry forward [hard + soft +
- * overflow], fused shading, d/d-silhouette pass [only for H or W not a multiple of 4], geometry backward,
+ * and writes the group durations in milliseconds, in launch order (vertex_fwd, geometry forward [hard + soft],
+ * fused shading, d/d-silhouette pass [only for H or W not a multiple of 4], geometry backward,
  * vertex_bwd + loss finalisation, -; capacity >= 7); returns the count written.  Event records switch
  * programmatic dependent launch off across them, so the figures are slightly above the in-step cost.
  * (The one piece of per-call state in a ctx: do not enable it on a ctx shared between threads.) */

@@ -351,6 +351,59 @@ def test_empty_scene_and_offscreen(mm):
     assert float(Ag['bg'].grad.abs().max()) > 0
 
 
+@pytest.mark.parametrize("size,ratio,mesh,kw", [(128, 1, "ellipsoid", {}), (64, 2, "smpl_uv_642", {}), (30, 1.2, "icosphere", {}),
+                                                 (64, 1, "sphere", dict(dist_range=(6.5, 7.0)))])
+def test_shading_schedule_and_truncation_counters(mm, size, ratio, mesh, kw):
+    """The soft pass classes every 4-tile strip of the shading kernel by the rounds its dense pass needs (the shading CTAs take
+    the strips longest class first) and lists the pixels with more than knum candidates: every strip must be listed exactly once,
+    in the class its covered pixels (from the image's own face_idx) put it in, and the far-camera case must have truncated pixels
+    (so the parity cases at that distance do exercise the in-kernel re-scan)."""
+    import ctypes
+    dr = mm.DiffRender(pu.get_mesh(mm, mesh), size, ratio=ratio)
+    H, W = dr.height, dr.image_size
+    B = 5
+    A = pu.to_device(pu.make_attributes(dr.vertices_init, B, H, W, 31, **kw), DEV)
+    A['_want_face_idx'] = True
+    h = dr._ctx(torch.device(DEV))
+    ws = h.workspace(B)
+    L = mm.lib()
+    rgba = torch.empty(B, 4, H, W, device=DEV); fn = torch.empty(B, dr.num_faces, 3, device=DEV)
+    imn = torch.empty(B, H, W, 3, device=DEV); fidx = torch.empty(B, H, W, device=DEV, dtype=torch.int32)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())     # noqa: E731
+    c = lambda k: A[k].contiguous()                 # noqa: E731
+    tex = c('textures')
+    rc = L.mm_render_forward(h.handle, B, P(c('vertices')), P(c('azimuths')), P(c('elevations')), P(c('distances')), P(c('biases')),
+                             P(tex), tex.shape[2], tex.shape[3], 0, P(c('lights')), P(c('bg')), 1, P(rgba), P(fn), P(imn), P(fidx),
+                             P(ws), ws.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, L.mm_last_error()
+    torch.cuda.synchronize()
+    off = lambda name: L.mm_debug_workspace_offset(h.handle, B, name.encode())      # noqa: E731
+    assert off("no such block") == ctypes.c_size_t(-1).value
+    word = lambda name, n: ws[off(name):off(name) + 4 * n].view(torch.int32).cpu().numpy()      # noqa: E731
+    ntx, nty = (W + 15) // 16, (H + 7) // 8
+    nstrips = (ntx * nty + 3) // 4
+    n = word("sched_n", 5)
+    assert int(n.sum()) == B * nstrips
+    lists = word("sched_list", 5 * B * nstrips).reshape(5, B * nstrips)
+    covered = (fidx >= 0).cpu().numpy()
+    want = np.zeros(B * nstrips, dtype=np.int64)
+    for b in range(B):
+        for t in range(ntx * nty):
+            ty, tx = divmod(t, ntx)
+            want[b * nstrips + t // 4] += covered[b, ty * 8:ty * 8 + 8, tx * 16:tx * 16 + 16].sum()
+    seen = []
+    for k in range(5):
+        ids = lists[k, :n[k]]
+        assert (np.minimum(4, (want[ids] + 127) // 128) == k).all(), k
+        seen.append(ids)
+    assert sorted(np.concatenate(seen).tolist()) == list(range(B * nstrips))
+    ntrunc = int(word("ovf_count", 1)[0])
+    if kw:
+        assert ntrunc > 0
+        pix = word("ovf_list", ntrunc)
+        assert len(set(pix.tolist())) == ntrunc and bool((covered.reshape(-1)[pix] == 0).all())     # uncovered, listed once
+
+
 # ------------------------------------------------------------------ SURVEY 8(f)-1: fused mesh regularisers
 @pytest.mark.parametrize("mesh,ratio,ell", [("sphere", 1, 1), ("smpl_uv_642", 2, 2), ("sphere2", 1, 1)])
 def test_mesh_regularisers_fused_kernel_vs_torch_statement(mm, mesh, ratio, ell):

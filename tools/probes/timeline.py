@@ -27,13 +27,13 @@ torch.cuda.synchronize()
 ms = bench.timed(torch, 1, fr.step, 500) / 500
 print("flow=%s mixed=%s  ms_per_step (no stamps) %.4f" % (os.environ.get("MM_FLOW", "1"), os.environ.get("MM_MIXED", "1"), ms))
 L.mm_debug_profile(fr.h.handle, ctypes.c_void_p(prof.data_ptr()))
-def ws_counters(ws, B, F, H, W):
-    """{truncated pixels, candidate pairs} and the shading schedule's class sizes of the last step (layout: mm_ws_make)"""
-    al = lambda x: (x + 255) // 256 * 256
-    off = al(B * F * 48); off = al(off + B * H * W * 8); off = al(off + B * H * W * 8)
-    off = al(off + B * H * ((W + 31) // 32) * 4)
-    return ws.view(torch.uint8)[off:off + 48].view(torch.int32).cpu().numpy()
-c = ws_counters(fr.sets[0]['out']['ws'], fr.B, dr.num_faces, dr.height, dr.image_size)
+def ws_counters(ws, h, B):
+    """{truncated pixels, candidate pairs, -, -} and the shading schedule's class sizes of the last step"""
+    L.mm_debug_workspace_offset.restype = ctypes.c_size_t
+    L.mm_debug_workspace_offset.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p]
+    rd = lambda name, n: ws[L.mm_debug_workspace_offset(h, B, name):][:4 * n].view(torch.int32).cpu().numpy()
+    return np.concatenate([rd(b"ovf_count", 4), rd(b"sched_n", 5)])
+c = ws_counters(fr.sets[0]['out']['ws'], fr.h.handle, fr.B)
 print("set 0: truncated pixels %d, candidate pairs %d, strips per class (0..4 rounds) %s" % (c[0], c[1], c[4:9].tolist()))
 names = ["vertex_fwd", "hard", "soft_fwd", "shade", "soft_bwd", "vertex_bwd"]
 def q(a, ps=(0, 50, 90, 100)): return " ".join("%6.1f" % np.percentile(a, p) for p in ps)
