@@ -10,7 +10,9 @@
 //   SHADE_BWD    mm_render_backward: the backward alone, re-deriving the forward per pixel.  The upstream gradient is any
 //                mix of a materialised g_rgba and the ANALYTIC recon_data gradient (lazy fusion: recon_data's backward hands
 //                over (gt, weights, a device scalar) instead of a (B,4,H,W) tensor; the IoU sums are in the workspace).
-// Sharing the body makes the images of the three entry points bit-identical by construction.
+// Sharing the body makes the images of the three entry points bit-identical by construction.  The forward modes also re-do the
+// truncated pixels of the soft pass (no launch of their own), and every mode takes its strips in the order of the shading
+// schedule the soft pass wrote (longest first): see k_shade.
 //   k_gsoft      H or W not a multiple of 4 only: d(loss)/d(silhouette) in its own pass (contour term through index tables).
 // The geometry backward (mm_raster.cu) consumes `gsoft`.
 #include "mm_device.cuh"

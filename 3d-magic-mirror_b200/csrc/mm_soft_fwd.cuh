@@ -1,5 +1,8 @@
-// mm_soft_fwd.cuh -- the soft-silhouette FORWARD engine (DIBR_SPEC A.4) as device functions, so that both the stand-alone
-// kernel (mm_raster.cu: k_soft_fwd, unfused API) and the fused step's merged soft + shading kernel (mm_fused.cu) can run it.
+// mm_soft_fwd.cuh -- the soft silhouette (DIBR_SPEC A.4) as device functions shared by mm_raster.cu and mm_fused.cu:
+//   soft_fwd_role        the forward walk of k_soft_fwd (candidate search on the coverage bitmap, evaluation, pair list)
+//   shade_sched_produce  the shading schedule k_soft_fwd writes on the side (strips classed by their covered pixels)
+//   soft_pair_grad       one candidate's gradient (k_soft_bwd)
+//   soft_ovf_role        the exact ordered re-scan of a truncated pixel: forward inside the shading kernel, backward in k_soft_bwd
 #pragma once
 #include "mm_device.cuh"
 
