@@ -18,8 +18,9 @@
 //     sched_n    [8] u32   shading schedule: number of 4-tile strips whose covered pixels need k = 0..4 rounds of the dense pass
 //                          (zbuf, lacc, cov, ovf_count and sched_n are contiguous: k_vertex_fwd clears them in one range)
 //     ovf_list   [B*H*W] u32  the truncated pixels, re-done exactly, in face order, by the shading kernel's overflow role
-//     sched_list [5,B*nstrips] u32  the strips (image * nstrips + strip) of each class, written by the soft pass from the coverage
-//                             bitmap; the shading kernel's CTAs take them longest class first (mm_fused.cu)
+//     sched_list [5,B*nstrips,16] u32  the strips of each class, written by the soft pass from the coverage bitmap: strip id
+//                             (image * nstrips + strip) and the image's 9 lights (what a shading CTA needs before it can
+//                             start: one round trip for both); the shading CTAs take them longest class first (mm_fused.cu)
 //     plist      [2*B*H*W] u64 the (face, pixel) candidate pairs the forward soft pass evaluated, (image*F+face) << 32 |
 //                             iy << 12 | ix: the backward soft pass replays this dense list
 //     gsoft      [B,H,W]      d(loss)/d(silhouette) per pixel, handed from the shading stage to the geometry backward
@@ -46,6 +47,7 @@
 #define MM_SH_TW        16
 #define MM_SH_TH        8
 #define MM_SH_WARPS     4
+#define MM_SCHED_WORDS  16           // words per entry of the shading schedule: strip id, the image's 9 lights, padding (64 B)
 static inline int mm_shade_strips(int H, int W) {
     return (((W + MM_SH_TW - 1) / MM_SH_TW) * ((H + MM_SH_TH - 1) / MM_SH_TH) + MM_SH_WARPS - 1) / MM_SH_WARPS;
 }
@@ -100,7 +102,7 @@ static inline mm_ws_layout mm_ws_make(const mm_ctx* c, int B) {
     L.ovf_count = off; off = off + 16;
     L.sched_n = off;  off = mm_align_up(off + 32, 256);
     L.ovf_list = off; off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
-    L.sched_list = off; off = mm_align_up(off + (size_t)5 * B * mm_shade_strips(c->H, c->W) * 4, 256);
+    L.sched_list = off; off = mm_align_up(off + (size_t)5 * B * mm_shade_strips(c->H, c->W) * MM_SCHED_WORDS * 4, 256);
     L.plist = off;    off = mm_align_up(off + (size_t)2 * B * c->H * c->W * 8, 256);
     L.gsoft = off;    off = mm_align_up(off + (size_t)B * c->H * c->W * 4, 256);
     L.vimg = off;     off = mm_align_up(off + (size_t)B * c->V * 2 * 4, 256);
@@ -130,7 +132,7 @@ struct mm_raster_params {
     uint32_t* ovf_list;      // [B*H*W] truncated pixels (global pixel index)
     uint32_t* ovf_count;     // [4]: {truncated pixels, candidate pairs recorded, -, -}
     uint32_t* sched_n;       // [8] strips per class of the shading schedule
-    uint32_t* sched_list;    // [5, B*nstrips]
+    uint32_t* sched_list;    // [5, B*nstrips, MM_SCHED_WORDS]
     int nstrips, novf;       // shading: strips (= CTAs) per image; how many CTAs (the first of the grid) double as the overflow role
     unsigned long long* prof;     // MM_PROF builds: per-warp time stamps (tools/probes/timeline.py), else NULL
     unsigned long long* plist;    // [plist_cap]

@@ -457,18 +457,18 @@ k_shade(const mm_raster_params p)
     if (threadIdx.x == 5) s_n[5] = (MODE != SHADE_BWD) ? p.ovf_count[0] : 0u;
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {                          // the blockIdx.x-th strip, longest class first
+    if (MODE != SHADE_BWD && s_n[5] > blockIdx.x && (int)blockIdx.x < p.novf)
+        soft_ovf_role<false>(p, u.ov.mask, u.ov.kept, s_n[5], blockIdx.x, p.novf);     // (every pixel ends with a block barrier)
+    {                                                // the blockIdx.x-th strip, longest class first: its id and its image's lights
         uint32_t r = blockIdx.x;
         int k = 4;
         while (k > 0 && r >= s_n[k]) { r -= s_n[k]; --k; }
-        s_sid = (int)p.sched_list[(size_t)k * gridDim.x + r];
+        const uint32_t* ent = p.sched_list + ((size_t)k * gridDim.x + r) * MM_SCHED_WORDS;
+        if (threadIdx.x == 0) s_sid = (int)ent[0];
+        else if (threadIdx.x < 10) s_lights[threadIdx.x - 1] = __uint_as_float(ent[threadIdx.x]);
     }
-    if (MODE != SHADE_BWD && s_n[5] > blockIdx.x && (int)blockIdx.x < p.novf)
-        soft_ovf_role<false>(p, u.ov.mask, u.ov.kept, s_n[5], blockIdx.x, p.novf);     // (every pixel ends with a block barrier)
     __syncthreads();
     const int b = s_sid / p.nstrips, bx = s_sid - b * p.nstrips;
-    if (threadIdx.x < 9) s_lights[threadIdx.x] = p.lights[b * 9 + threadIdx.x];
-    __syncthreads();
     MM_PROF_MARK(p.prof, 3, wid, 1);
     shade_role<VEC, HAS_GUP, MODE>(p, u.sm, s_lights, s_count, bx, b);
     MM_PROF_MARK(p.prof, 3, wid, 2);

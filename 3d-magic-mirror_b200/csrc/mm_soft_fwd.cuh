@@ -98,10 +98,13 @@ __device__ __forceinline__ void shade_sched_produce(const mm_raster_params& p, c
         }
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
-        if (lane == 0) {
-            const int k = min(4, (cnt + 32 * MM_SH_WARPS - 1) / (32 * MM_SH_WARPS));
-            p.sched_list[(size_t)k * nsid + atomicAdd(p.sched_n + k, 1u)] = (uint32_t)sid;
-        }
+        // entry: strip id + the image's lights (lanes 1..9), so that a shading CTA gets both with one round trip
+        const float lt = (lane >= 1 && lane <= 9) ? p.lights[b * 9 + lane - 1] : 0.0f;
+        const int k = min(4, (cnt + 32 * MM_SH_WARPS - 1) / (32 * MM_SH_WARPS));
+        uint32_t pos = 0u;
+        if (lane == 0) pos = atomicAdd(p.sched_n + k, 1u);
+        pos = __shfl_sync(FULL, pos, 0);
+        if (lane < 10) p.sched_list[((size_t)k * nsid + pos) * MM_SCHED_WORDS + lane] = lane == 0 ? (uint32_t)sid : __float_as_uint(lt);
     }
 }
 

@@ -384,7 +384,8 @@ def test_shading_schedule_and_truncation_counters(mm, size, ratio, mesh, kw):
     nstrips = (ntx * nty + 3) // 4
     n = word("sched_n", 5)
     assert int(n.sum()) == B * nstrips
-    lists = word("sched_list", 5 * B * nstrips).reshape(5, B * nstrips)
+    ent = word("sched_list", 5 * B * nstrips * 16).reshape(5, B * nstrips, 16)       # entry: strip id, the image's 9 lights, padding
+    lists = ent[:, :, 0]
     covered = (fidx >= 0).cpu().numpy()
     want = np.zeros(B * nstrips, dtype=np.int64)
     for b in range(B):
@@ -395,6 +396,8 @@ def test_shading_schedule_and_truncation_counters(mm, size, ratio, mesh, kw):
     for k in range(5):
         ids = lists[k, :n[k]]
         assert (np.minimum(4, (want[ids] + 127) // 128) == k).all(), k
+        lights = ent[k, :n[k], 1:10].copy().view(np.float32)
+        assert (lights == A['lights'].cpu().numpy()[ids // nstrips]).all()
         seen.append(ids)
     assert sorted(np.concatenate(seen).tolist()) == list(range(B * nstrips))
     ntrunc = int(word("ovf_count", 1)[0])
