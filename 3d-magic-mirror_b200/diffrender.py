@@ -26,7 +26,9 @@ from . import mesh as _mesh
 
 
 def _ptr(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    """Raw device address for a `void*` argument of the C ABI (ctypes converts the int; None is NULL).  A plain int instead of
+    a ctypes.c_void_p object: ~40 of these per training step sit on the eager path's host time."""
+    return t.data_ptr() if t is not None else None
 
 
 def _f32c(t):
@@ -36,8 +38,32 @@ def _f32c(t):
     return t.contiguous()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+class _NoGuard(object):
+    def __enter__(self): return None
+    def __exit__(self, *a): return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on(dev):
+    """torch.cuda.device(dev) only when `dev` is not the current device already (the usual case: one device per process);
+    the context manager costs ~5 us, three times per training step."""
+    idx = dev if isinstance(dev, int) else dev.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(idx)
+
+
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The current CUDA stream of the current device as a raw handle.  torch.cuda.current_stream() builds a Stream object
+    through three Python layers (~5 us, four times per step); the raw getter is one C call."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device()) or None
+    return torch.cuda.current_stream().cuda_stream or None
 
 
 class _CtxHandle(object):
@@ -194,7 +220,7 @@ class _RenderFn(torch.autograd.Function):
         dev = vertices.device
         H, W, F = dr.height, dr.image_size, dr.num_faces
         h = dr._ctx(dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             rgba = torch.empty(B, 4, H, W, device=dev, dtype=torch.float32)
             fn = torch.empty(B, F, 3, device=dev, dtype=torch.float32)
             imn = torch.empty(B, H, W, 3, device=dev, dtype=torch.float32)
@@ -236,7 +262,7 @@ class _RenderFn(torch.autograd.Function):
         g_rgba = _f32c(g_rgba) if g_rgba is not None else None
         g_fn = _f32c(g_fn) if g_fn is not None else None
         gt, iw, contour, g_loss = pend if pend is not None else (None, 0.0, 0.0, None)
-        with torch.cuda.device(dev):
+        with _on(dev):
             g_v = torch.empty_like(vertices)
             g_az, g_el, g_di = torch.empty_like(azim), torch.empty_like(elev), torch.empty_like(dist)
             g_bi, g_tex, g_li = torch.empty_like(biases), torch.empty_like(textures), torch.empty_like(lights)
@@ -265,7 +291,7 @@ class _FaceNormalsFn(torch.autograd.Function):
         if vertices.shape != (B, dr.num_vertices, 3):
             raise ValueError("vertices must be (B,%d,3), got %s" % (dr.num_vertices, tuple(vertices.shape)))
         h = dr._ctx(dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             fn = torch.empty(B, dr.num_faces, 3, device=dev, dtype=torch.float32)
             rec = _Record(h, B)
             rc = _lib.lib().mm_face_normals_forward(h.handle, B, _ptr(vertices), _ptr(azim), _ptr(elev), _ptr(dist), _ptr(biases),
@@ -281,7 +307,7 @@ class _FaceNormalsFn(torch.autograd.Function):
         dev = vertices.device
         B = azim.shape[0]
         ws = ctx.rec.ws
-        with torch.cuda.device(dev):
+        with _on(dev):
             g_fn = _f32c(g_fn)
             gv = torch.empty_like(vertices)
             ga, ge, gd = torch.empty_like(azim), torch.empty_like(elev), torch.empty_like(dist)
@@ -312,7 +338,7 @@ class _ReconFn(torch.autograd.Function):
         B, pred, gt = _check_recon_inputs(dr, pred, gt)
         dev = pred.device
         h = dr._ctx(dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             loss = torch.empty(4, device=dev, dtype=torch.float32)
             rec = _Record(h, B)
             rc = _lib.lib().mm_recon_data_forward(h.handle, B, _ptr(pred), _ptr(gt), float(image_weight),
@@ -329,7 +355,7 @@ class _ReconFn(torch.autograd.Function):
         B = pred.shape[0]
         dev = pred.device
         ws = ctx.rec.ws
-        with torch.cuda.device(dev):
+        with _on(dev):
             g_loss = _f32c(g_loss)
             g_pred = torch.empty_like(pred)
             rc = _lib.lib().mm_recon_data_backward(ctx.h.handle, B, _ptr(pred), _ptr(gt), ctx.iw, ctx.contour, 1.0,
@@ -350,7 +376,7 @@ class _ReconLazyFn(torch.autograd.Function):
         B, pred, gt = _check_recon_inputs(dr, pred, gt)
         dev = pred.device
         h = rec.h
-        with torch.cuda.device(dev):
+        with _on(dev):
             loss = torch.empty(4, device=dev, dtype=torch.float32)
             rc = _lib.lib().mm_recon_data_forward(h.handle, B, _ptr(pred), _ptr(gt), float(image_weight),
                                                   float(contour), _ptr(loss), _ptr(None), _ptr(rec.ws), rec.ws.numel(), _stream())
@@ -385,7 +411,7 @@ class _MeshRegFn(torch.autograd.Function):
         vertices = _f32c(vertices) if vertices is not None else None
         fn = _f32c(fn) if fn is not None else None
         h = dr._ctx(dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             terms = torch.zeros(8, device=dev, dtype=torch.float32)
             ws = torch.empty(B * 8 + 8, device=dev, dtype=torch.float32)
             rc = _lib.lib().mm_mesh_reg_forward(h.handle, B, _ptr(delta), _ptr(vertices), _ptr(fn), float(temp), float(eps),
@@ -407,7 +433,7 @@ class _MeshRegFn(torch.autograd.Function):
         vertices = vertices if has_v else None
         fn = fn if has_n else None
         dev = g_terms.device
-        with torch.cuda.device(dev):
+        with _on(dev):
             g_terms = _f32c(g_terms)
             gd = torch.empty_like(delta) if has_d else None
             gv = torch.empty_like(vertices) if has_v else None
@@ -435,7 +461,7 @@ class _TemplateFeaturesFn(torch.autograd.Function):
         if tmpl.shape[0] != V:
             raise ValueError("template must hold %d vertices (one template for the whole batch), got %s" % (V, tuple(template.shape)))
         hnd = dr._ctx(dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             local = torch.empty(B, C, V, 1, device=dev, dtype=torch.float32)
             ndiff = torch.empty(B, C, V, 1, device=dev, dtype=torch.float32)
             rc = _lib.lib().mm_template_features_forward(hnd.handle, B * C, h, w, _ptr(x), _ptr(tmpl), _ptr(local), _ptr(ndiff),
@@ -450,7 +476,7 @@ class _TemplateFeaturesFn(torch.autograd.Function):
         tmpl, = ctx.saved_tensors
         B, C, h, w = ctx.shape
         dev = tmpl.device
-        with torch.cuda.device(dev):
+        with _on(dev):
             g_local = _f32c(g_local) if g_local is not None else None
             g_ndiff = _f32c(g_ndiff) if g_ndiff is not None else None
             if g_local is None and g_ndiff is None:
@@ -478,7 +504,7 @@ class _TextureFlowFn(torch.autograd.Function):
         Ho, Wo = flow.shape[2:]
         dev = img.device
         h = dr._ctx(dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             out = torch.empty(B, C, Ho * (2 if concat else 1), Wo, device=dev, dtype=torch.float32)
             rc = _lib.lib().mm_texture_flow_forward(h.handle, B, C, Hi, Wi, Ho, Wo, 1 if concat else 0, _ptr(img), _ptr(flow),
                                                     _ptr(out), _stream())
@@ -492,7 +518,7 @@ class _TextureFlowFn(torch.autograd.Function):
         img, flow = ctx.saved_tensors
         B, C, Hi, Wi = img.shape
         Ho, Wo = flow.shape[2:]
-        with torch.cuda.device(img.device):
+        with _on(img.device):
             g_out = _f32c(g_out)
             g_img, g_flow = torch.empty_like(img), torch.empty_like(flow)
             rc = _lib.lib().mm_texture_flow_backward(ctx.h.handle, B, C, Hi, Wi, Ho, Wo, 1 if ctx.concat else 0, _ptr(img),
@@ -647,7 +673,7 @@ class DiffRender(object):
         gx = _check_plane(g_rgba_extra, "g_rgba_extra", (B, 4, H, W), dev) if g_rgba_extra is not None else None
         gfn = _check_plane(g_face_normals, "g_face_normals", (B, F, 3), dev) if g_face_normals is not None else None
         h = self._ctx(dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             out = {
                 'rgba': torch.empty(B, 4, H, W, device=dev), 'face_normals': torch.empty(B, F, 3, device=dev),
                 'loss': torch.empty(4, device=dev),
