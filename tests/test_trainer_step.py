@@ -70,7 +70,11 @@ def test_trainer_loop_reduces_loss(mm, tex_mirror):
         opt.step()
         losses.append(float(loss))
     assert all(l == l for l in losses)                     # no NaN
-    assert min(losses[-5:]) < 0.9 * losses[0], losses
+    # The loop reaches ~0.19 from 0.43 by step 16.  At this learning rate (Adam, beta1 = 0.5) the trajectory has isolated
+    # spikes -- the same loop through the CPU oracle alone jumps to 0.60 at step 18 and is back at 0.20 six steps later -- and
+    # where they fall depends on the last bits of the gradients (float-atomics order), so the statement is about the best loss
+    # the loop reaches, not about its last five steps (which is what this test asserted until a spike landed there).
+    assert min(losses[8:]) < 0.6 * losses[0], losses
 
 
 def _free_port():
