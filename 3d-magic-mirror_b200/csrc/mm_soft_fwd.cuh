@@ -273,8 +273,9 @@ __device__ __forceinline__ void soft_pair_grad(const mm_raster_params& p, const 
 // ---------------------------------------------------------------------------------------------- overflow (ordered) pass
 // DIB-R keeps only the FIRST knum candidates in face-index order (DIBR_SPEC A.4).  Pixels that saw more are re-done
 // here literally.  One CTA per overflowed pixel:
-//   phase 1  all F enlarged-bbox tests in ONE memory round trip (each thread owns F/128 faces, loads issued back to back);
-//            the per-warp ballots land in shared memory as hit words in face order.
+//   phase 1  all F enlarged-bbox tests (each thread owns F/128 faces, OVF_UNROLL loads in flight; the test is read off the exact
+//            rectangles of frect: 8 bytes and four integer compares per face); the per-warp ballots land in shared memory as
+//            hit words in face order.
 //   phase 2  warp 0 keeps the first knum set bits (running count over the words) and writes the kept faces, in order, to a
 //            shared list; then -- still warp 0, no further block barrier -- lane k evaluates candidate k, and the ordered
 //            product (forward) is folded with shuffles exactly in the reference's order; backward: lane k scatters the
@@ -283,7 +284,7 @@ __device__ __forceinline__ void soft_pair_grad(const mm_raster_params& p, const 
 // shading kernel's CTAs (mm_fused.cu); backward: by the tail CTAs of k_soft_bwd.
 #define OVF_THREADS 128
 #define OVF_MAX_WORDS 2048          // F <= 65535
-#define OVF_UNROLL 5
+#define OVF_UNROLL 8
 
 // (this CTA takes entries first, first + stride, .. of the `count` listed pixels)
 template <bool BWD>
@@ -311,26 +312,23 @@ __device__ __forceinline__ void soft_ovf_role(const mm_raster_params& p, uint32_
             one_m_all = 1.0f - soft;
             if (g == 0.0f || !(soft > 0.0f)) continue;          // block-uniform
         }
-        // ---- phase 1: enlarged-bbox hit words, face order (word = f >> 5); OVF_UNROLL independent record loads in flight
+        // ---- phase 1: hit words in face order (word = f >> 5).  "The pixel is inside the face's enlarged bbox" is read off the
+        // EXACT enlarged rectangle the vertex stage left in frect -- by construction the same decision as the reference's
+        // half-open fp32 test on the record, for 8 bytes and four integer compares per face instead of 32 bytes and the
+        // min / max / add chain; OVF_UNROLL independent loads in flight
+        const uint4* rects = p.frect + (size_t)b * p.F;
         for (int j0 = 0; j0 < niter; j0 += OVF_UNROLL) {
-            float4 c0[OVF_UNROLL], c1[OVF_UNROLL];
+            uint2 rc[OVF_UNROLL];
             #pragma unroll
             for (int u = 0; u < OVF_UNROLL; ++u) {
                 const int f = (j0 + u) * OVF_THREADS + threadIdx.x;
-                if (j0 + u < niter && f < p.F) { c0[u] = __ldg(rec4 + (size_t)f * 3); c1[u] = __ldg(rec4 + (size_t)f * 3 + 1); }
-                else { c0[u] = make_float4(0.f, 0.f, 0.f, 0.f); c1[u] = c0[u]; }
+                rc[u] = (j0 + u < niter && f < p.F) ? __ldg(reinterpret_cast<const uint2*>(rects + f) + 1) : make_uint2(1u, 1u);   // (.z, .w; (1, 0) = empty)
             }
             #pragma unroll
             for (int u = 0; u < OVF_UNROLL; ++u) {
                 const int j = j0 + u;
-                const int f = j * OVF_THREADS + threadIdx.x;
-                bool hit = false;
-                if (j < niter && f < p.F) {
-                    FaceRec r;
-                    r.ax = c0[u].x; r.ay = c0[u].y; r.bx = c0[u].z; r.by = c0[u].w; r.cx = c1[u].x; r.cy = c1[u].y;
-                    r.az = r.bz = r.cz = r.nx = r.ny = r.nz = 0.0f;
-                    hit = soft_bbox_test(r, px, py, p.blen);
-                }
+                const bool hit = ix >= (int)(rc[u].x & 0xffffu) && ix <= (int)(rc[u].x >> 16) &&
+                                 iy >= (int)(rc[u].y & 0xffffu) && iy <= (int)(rc[u].y >> 16);
                 const uint32_t m = __ballot_sync(FULL, hit);
                 const int word = j * (OVF_THREADS / 32) + warp;
                 if (lane == 0 && j < niter && word < nw) s_mask[word] = m;
