@@ -77,13 +77,6 @@ __device__ __forceinline__ float interp3(float w0, float w1, float w2, float c0,
     return ADD(ADD(MUL(w0, c0), MUL(w1, c1)), MUL(w2, c2));
 }
 
-// DIBR_SPEC A.4: half-open test against the bbox enlarged by blen
-__device__ __forceinline__ bool soft_bbox_test(const FaceRec& r, float x0, float y0, float blen) {
-    const float xmin = SUB(fminf(fminf(r.ax, r.bx), r.cx), blen), xmax = ADD(fmaxf(fmaxf(r.ax, r.bx), r.cx), blen);
-    const float ymin = SUB(fminf(fminf(r.ay, r.by), r.cy), blen), ymax = ADD(fmaxf(fmaxf(r.ay, r.by), r.cy), blen);
-    return !(x0 < xmin || x0 >= xmax || y0 < ymin || y0 >= ymax);
-}
-
 // ------------------------------------------------------------------ exact pixel rectangles of a face's bbox
 struct PixRange { int ix0, ix1, iy0, iy1; };
 
