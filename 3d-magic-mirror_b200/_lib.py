@@ -52,7 +52,7 @@ SIGNATURES = {
     "mm_ctx_set_timing": (c_int, [_P, c_int]),
     "mm_ctx_get_timing": (c_int, [_P, _P, c_int]),
 }
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class MagicMirrorError(RuntimeError):

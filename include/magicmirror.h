@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define MM_ABI_VERSION 2
+#define MM_ABI_VERSION 3     /* 3: mm_render_backward no longer reads `rgba`; mm_debug_workspace_offset; larger workspace */
 
 #define MM_OK            0
 #define MM_E_INVALID    -1   /* bad argument (NULL pointer, non-positive size, undersized workspace, wrong device, ...) */

@@ -76,7 +76,7 @@ def test_abi_library_exports_every_declared_symbol(mm):
     from magic_mirror_b200 import _lib
     assert set(_lib.SIGNATURES) == declared
     h.mm_abi_version.restype = ctypes.c_int
-    assert h.mm_abi_version() == 2
+    assert h.mm_abi_version() == 3
 
 
 def test_cpu_tensors_fail_loudly(mm):

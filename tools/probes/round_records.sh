@@ -1,6 +1,6 @@
 # the round's records on one GPU box: bench (default arguments), the reference arm, the ncu evidence of the same command, the other
 # BASELINE configs and the per-warp timeline.  usage: bash tools/probes/round_records.sh <tag>
-TAG=${1:-r2k}
+TAG=${1:-r2l}
 timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 300 gpurun_out/${TAG}_bench.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>/dev/null
 timeout 900 bash tools/profile_step.sh ${TAG} > /dev/null
