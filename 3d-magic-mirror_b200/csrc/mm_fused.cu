@@ -464,7 +464,7 @@ k_shade(const mm_raster_params p)
         int k = 4;
         while (k > 0 && r >= s_n[k]) { r -= s_n[k]; --k; }
         const uint32_t* ent = p.sched_list + ((size_t)k * gridDim.x + r) * MM_SCHED_WORDS;
-        if (threadIdx.x == 0) s_sid = (int)ent[0];
+        if (threadIdx.x == 0) s_sid = (int)min(ent[0], gridDim.x - 1u);      // (clamped: a backward on a workspace without a forward reads garbage, not out of bounds)
         else if (threadIdx.x < 10) s_lights[threadIdx.x - 1] = __uint_as_float(ent[threadIdx.x]);
     }
     __syncthreads();
