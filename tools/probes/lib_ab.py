@@ -1,5 +1,5 @@
 """A/B of library builds / switches on the GPU box: the fused step's time and the event-timed launch groups.
-usage: [MM_LIB=libmagicmirror_head.so] [MM_SHADE_SPLIT=..] [MM_PDL_LATE=..] python tools/probes/lib_ab.py [steps]"""
+usage: [MM_LIB=libmagicmirror_head.so] [MM_PDL_LATE=..] python tools/probes/lib_ab.py [steps]"""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -23,5 +23,5 @@ for i in range(n):
     fr.step(i); L.mm_ctx_get_timing(h, buf, 8)
     for j in range(7): acc[j] += buf[j]
 L.mm_ctx_set_timing(h, 0)
-tag = " ".join("%s=%s" % (k, os.environ[k]) for k in ("MM_LIB", "MM_SHADE_SPLIT", "MM_PDL_LATE") if k in os.environ)
+tag = " ".join("%s=%s" % (k, os.environ[k]) for k in ("MM_LIB", "MM_PDL_LATE") if k in os.environ)
 print("%-60s ms_per_step %.4f  groups_us %s" % (tag or "(defaults)", ms, {k: round(1e3 * a / n, 1) for k, a in zip(bench.KERNELS, acc)}), flush=True)
